@@ -1,0 +1,133 @@
+/* libstc.so -- C ABI of the B200-native sentinel-tree-cover hot path.
+ *
+ * The reference has no FFI: its boundary is Python module-level functions in
+ * src/download_and_predict_job.py that close over two tf.Session globals
+ * (:1785-1826).  Each entry point below cites the reference function it
+ * replaces; sentinel_tree_cover_b200/api.py is the ctypes binding and mirrors
+ * the reference signatures (INTEGRATION.md shows the maintainer-side patch).
+ *
+ * Conventions: every call returns 0 on success or a negative error code;
+ * stc_last_error(ctx) gives the message.  All arrays are C-contiguous,
+ * channel-innermost (NHWC) exactly as the reference's NumPy arrays.  Plain
+ * `*_host` pointers are host memory (pageable or pinned); `*_dev` pointers are
+ * device memory obtained from stc_malloc.  A context is bound to one CUDA
+ * device + one stream and is not thread-safe (the reference is single-threaded,
+ * one session per process); multi-GPU = one context per device/process.
+ * There is no CPU fallback: stc_create fails if no sm_100 device is present.
+ */
+#ifndef STC_H_
+#define STC_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct stc_ctx stc_ctx;
+
+#define STC_OK 0
+#define STC_ERR_CUDA (-1)
+#define STC_ERR_ARG (-2)
+#define STC_ERR_STATE (-3)
+#define STC_ERR_NOMEM (-4)
+
+/* ---- context (replaces the two tf.compat.v1.Session globals,
+ *      src/download_and_predict_job.py:1785-1826) ------------------------- */
+int stc_create(int device, stc_ctx** out);
+void stc_destroy(stc_ctx* ctx);
+const char* stc_last_error(stc_ctx* ctx);
+const char* stc_version(void);
+/* Number of kernels this context has launched so far (bench.py gpu_launches). */
+int64_t stc_launch_count(stc_ctx* ctx);
+/* 0 = tcgen05 implicit-GEMM convolutions (default), 1 = SIMT verification
+ * kernel (same data layout and fp16 operands; used by tests to bisect). */
+int stc_set_conv_impl(stc_ctx* ctx, int impl);
+
+/* ---- weights: canonical tensors of predict_graph-*.pb / superresolve_graph.pb
+ *      (names in sentinel_tree_cover_b200/weights.py).  Set every tensor, then
+ *      finalize (packs fp16 operand layouts on the device).  `which`: 0 =
+ *      predict graph, 1 = super-resolve graph. --------------------------- */
+int stc_set_weight(stc_ctx* ctx, const char* name, const float* data, int64_t n);
+int stc_finalize_weights(stc_ctx* ctx, int which);
+
+/* ---- device memory helpers (so the host side needs no CUDA binding) ---- */
+int stc_malloc(stc_ctx* ctx, size_t bytes, void** dptr);
+int stc_free(stc_ctx* ctx, void* dptr);
+int stc_malloc_host(stc_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+int stc_free_host(stc_ctx* ctx, void* hptr);
+int stc_h2d(stc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int stc_d2h(stc_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int stc_sync(stc_ctx* ctx);
+/* CUDA-event timing on the context's stream (bench.py): begin/end return ms. */
+int stc_timer_begin(stc_ctx* ctx);
+int stc_timer_end(stc_ctx* ctx, float* ms);
+/* Accumulated device time (ms) and launch count of the convolution kernels
+ * since the last reset -- measured with CUDA events around each conv launch
+ * when enabled (adds no sync; read after stc_sync). */
+int stc_conv_timing(stc_ctx* ctx, int enable_reset, float* total_ms, int64_t* launches);
+
+/* ---- model forward: predict_subtile (src/download_and_predict_job.py:328-369)
+ *      = sess.run(predict_logits, {predict_inp: x[B,T+1,H,W,17], predict_length})
+ *      x: frames 0..T-1 sequence, frame T the median frame (pb:strided_slice,
+ *      pb:strided_slice_1).  `length` is the uniform sequence length
+ *      (np.full(B, args.length), :354).  If normalize != 0, normalize_subtile
+ *      (:316-325) is applied first with min17/max17.  out: [B,H-14,W-14]. ---- */
+int stc_predict_host(stc_ctx* ctx, const float* x_host, int B, int T, int H, int W, int length,
+                     int normalize, const double* min17, const double* max17, float* out_host);
+int stc_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int W, int length,
+                    int normalize, const double* min17, const double* max17, float* out_dev);
+
+/* ---- assemble (process_subtiles :1274-1283 quarterly medians, :1152-1160 /
+ *      :1174 median frame, :1398-1407 17-channel layout; indices
+ *      src/preprocessing/indices.py:4-54 as in the 13-band contract of
+ *      src/download_and_predict_job_multiyear.py:794-838).
+ *      in : monthly [B,12,H,W,13]  (10 S2 bands, DEM, S1 VV, S1 VH)
+ *      out: [B,5,H,W,17] frames 0-3 = median of months (3q..3q+2), frame 4 =
+ *      median over the 12 months; channels [0:10] S2,[10] DEM,[11:13] S1,
+ *      [13:17] EVI,BI,MSAVI2,GRNDVI (computed per month, then the same medians). */
+int stc_assemble_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W, float* out_dev);
+int stc_assemble_host(stc_ctx* ctx, const float* monthly_host, int B, int H, int W, float* out_host);
+
+/* ---- fused tile path used by the throughput benchmark:
+ *      assemble -> normalize_subtile -> predict, monthly [B,12,H,W,13] -> [B,H-14,W-14] */
+int stc_predict_patches_host(stc_ctx* ctx, const float* monthly_host, int B, int H, int W,
+                             const double* min17, const double* max17, float* out_host);
+int stc_predict_patches_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W,
+                            const double* min17, const double* max17, float* out_dev);
+
+/* ---- temporal regrid + Whittaker + monthly mean as one linear operator
+ *      out[12,P,C] = M[12,n] . in[n,P,C]   (P = H*W pixels)
+ *      replaces calculate_and_save_best_images (src/downloading/utils.py:176-347)
+ *      + Smoother.interpolate_array (src/preprocessing/whittaker_smoother.py:44-69);
+ *      M is built on the host from the image dates (regrid.py). ------------- */
+int stc_temporal_matmul_host(stc_ctx* ctx, const float* in_host, const float* M_host,
+                             int n_in, int n_out, int64_t inner, float* out_host);
+int stc_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_host,
+                            int n_in, int n_out, int64_t inner, float* out_dev);
+
+/* ---- band indices, make_indices (src/download_and_predict_job.py:998-1006):
+ *      in [npix,C>=10] -> out [npix,4] = EVI,BI,MSAVI2,GRNDVI ------------- */
+int stc_indices_host(stc_ctx* ctx, const float* in_host, int64_t npix, int C, float* out_host);
+
+/* ---- temporal median over the leading axis (np.median(axis=0),
+ *      process_subtiles :1152-1160; n <= 32) ------------------------------ */
+int stc_temporal_median_host(stc_ctx* ctx, const float* in_host, int n, int64_t inner, float* out_host);
+
+/* ---- 20 m -> 10 m super-resolution: one sess.run of superresolve_graph.pb
+ *      (src/download_and_predict_job.py:110-120 `_worker_fn` body without the
+ *      pad/crop): x [N,H,W,10] (already reflect-padded by the caller),
+ *      bilinear [N,H,W,6] -> out [N,H,W,6] = pb:Add_2 -------------------- */
+int stc_superresolve_host(stc_ctx* ctx, const float* x_host, const float* bilinear_host,
+                          int N, int H, int W, float* out_host);
+
+/* ---- debug: copy an internal activation buffer of the last stc_predict_*
+ *      call to the host as float32 NHWC (interior only).  Names: "ccin",
+ *      "cat2", "p1", "cat1", "p2", "u2in", "u3in".  Returns the number of
+ *      floats written (or needed if out_host == NULL). --------------------- */
+int64_t stc_debug_read(stc_ctx* ctx, const char* name, float* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STC_H_ */

@@ -1,0 +1,136 @@
+"""TEST INFRASTRUCTURE (oracle) -- NumPy/SciPy restatement of the reference's temporal
+preprocessing arithmetic.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this; never the product path.
+
+Pinned against the reference's own functions executed through oracle/refshim.py
+(tools/make_golden.py -> tests/golden/preproc_*.npz; tests/test_oracle_preproc.py).
+All file:line citations are relative to /root/reference.
+"""
+import numpy as np
+import scipy.sparse as sparse
+from scipy.sparse.linalg import splu
+
+
+# ---- src/preprocessing/indices.py:4-54 -------------------------------------------------
+def grndvi(x):
+    nir, green, red = np.clip(x[..., 3], 0., 1), np.clip(x[..., 1], 0., 1), np.clip(x[..., 2], 0., 1)
+    return (nir - (green + red)) / ((nir + (green + red)) + 1e-5)
+
+
+def evi(x):
+    BLUE, RED, NIR = np.clip(x[..., 0], 0, 1), np.clip(x[..., 2], 0, 1), np.clip(x[..., 3], 0, 1)
+    return np.clip(2.5 * ((NIR - RED) / (NIR + (6 * RED) - (7.5 * BLUE) + 1)), -1.5, 1.5)
+
+
+def msavi2(x):
+    RED, NIR = np.clip(x[..., 2], 0, 1), np.clip(x[..., 3], 0, 1)
+    s = (2 * NIR + 1) ** 2 - 8 * (NIR - RED)
+    s[s < 0] = 0.
+    return np.clip((2 * NIR + 1 - np.sqrt(s)) / 2, -1, 1)
+
+
+def bi(x):
+    B11, B4, B8, B2 = (np.clip(x[..., 8], 0, 1), np.clip(x[..., 2], 0, 1), np.clip(x[..., 3], 0, 1), np.clip(x[..., 0], 0, 1))
+    return np.clip(((B11 + B4) - (B8 + B2)) / (((B11 + B4) + (B8 + B2)) + 1e-5), -1, 1)
+
+
+def make_indices(arr):
+    """src/download_and_predict_job.py:998-1006 -> [...,4] = EVI, BI, MSAVI2, GRNDVI (float32)."""
+    out = np.zeros(arr.shape[:-1] + (4,), np.float32)
+    out[..., 0], out[..., 1], out[..., 2], out[..., 3] = evi(arr), bi(arr), msavi2(arr), grndvi(arr)
+    return out
+
+
+# ---- src/download_and_predict_job.py:316-325 -------------------------------------------
+def normalize_subtile(subtile, min_all, max_all):
+    subtile = subtile.copy()
+    for band in range(subtile.shape[-1]):
+        mins, maxs = min_all[band], max_all[band]
+        subtile[..., band] = np.clip(subtile[..., band], mins, maxs)
+        subtile[..., band] = (subtile[..., band] - (maxs + mins) / 2) / ((maxs - mins) / 2)
+    return subtile
+
+
+# ---- medians + 17-channel frame layout --------------------------------------------------
+def assemble(monthly):
+    """monthly [B,12,H,W,13] -> [B,5,H,W,17].  Quarterly = np.median over month triples
+    (process_subtiles :1274-1278), frame 4 = np.median over the 12 steps (:1152-1160,1174);
+    channel layout [0:10] S2, [10] DEM, [11:13] S1, [13:17] indices (:1398-1407); indices
+    are computed per month from the 13-band cube as in
+    src/download_and_predict_job_multiyear.py:808-813, then reduced by the same medians."""
+    m = np.asarray(monthly, np.float32)
+    B, n, H, W, _ = m.shape
+    full = np.concatenate([m, make_indices(m)], axis=-1)            # [B,12,H,W,17]
+    q = np.median(full.reshape(B, 4, 3, H, W, 17), axis=2)
+    med = np.median(full, axis=1, keepdims=True)
+    return np.concatenate([q, med], axis=1).astype(np.float32)
+
+
+# ---- src/preprocessing/whittaker_smoother.py:10-69 --------------------------------------
+class WhittakerRef:
+    def __init__(self, lmbd=100, size=24):
+        d = np.zeros(5, np.float32)
+        d[2] = 1.
+        for _ in range(2):
+            d = d[:-1] - d[1:]
+        E = sparse.eye(size, format='csc', dtype=np.float32)
+        D = sparse.diags(d, np.arange(3), (size - 2, size), dtype=np.float32)
+        self.lu = splu(E + D.conj().T.dot(D) * lmbd)
+        self.size = size
+
+    def interpolate_array(self, x):
+        """x [24,H,W,C] -> [12,H,W,C]: splu solve per column, mean of consecutive pairs."""
+        shp = x.shape
+        z = self.lu.solve(np.array(x.reshape(self.size, -1)))
+        z = z.reshape((12, self.size // 12) + shp[1:])
+        return np.mean(z, axis=1)
+
+
+def regrid_apply(G, arr):
+    """keep_steps = sum_i w_i * img_i with float32 weights (src/downloading/utils.py:313-345)."""
+    G = np.asarray(G, np.float32)
+    out = np.zeros((G.shape[0],) + arr.shape[1:], np.float32)
+    for r in range(G.shape[0]):
+        nz = np.flatnonzero(G[r])
+        out[r] = np.sum(arr[nz] * G[r, nz][:, None, None, None], axis=0)
+    return out
+
+
+def smooth_stack(arr, G):
+    """smooth_large_tile numeric core (src/download_and_predict_job.py:1057-1096) given the
+    24 x n regrid matrix: bands and indices regridded + Whittaker-smoothed separately."""
+    sm = WhittakerRef()
+    bands = sm.interpolate_array(regrid_apply(G, arr))
+    if arr.shape[-1] != 10:
+        return bands.astype(np.float32)
+    idx = sm.interpolate_array(regrid_apply(G, make_indices(arr)))
+    return np.concatenate([bands, idx], -1).astype(np.float32)
+
+
+def temporal_matmul(M, arr):
+    return np.einsum('on,n...->o...', np.asarray(M, np.float64), np.asarray(arr, np.float64)).astype(np.float32)
+
+
+# ---- synthetic inputs --------------------------------------------
+def synth_monthly(B, H, seed, W=None):
+    """[B,12,H,W,13] float32: 10 S2 bands (smooth seasonal signal), DEM, S1 VV/VH."""
+    W = H if W is None else W
+    r = np.random.default_rng(seed)
+    base = r.uniform(0.02, 0.45, (B, 1, H, W, 10)).astype(np.float32)
+    phase = r.uniform(0, 2 * np.pi, (B, 1, H, W, 1)).astype(np.float32)
+    t = np.arange(12, dtype=np.float32).reshape(1, 12, 1, 1, 1)
+    s2 = base + 0.05 * np.sin(2 * np.pi * (t / 12) + phase) + r.normal(0, 0.01, (B, 12, H, W, 10)).astype(np.float32)
+    s2 = np.clip(s2, 0.001, 0.999).astype(np.float32)
+    dem = np.repeat(r.uniform(0, 0.4, (B, 1, H, W, 1)).astype(np.float32), 12, axis=1)
+    s1 = r.uniform(0.05, 0.95, (B, 12, H, W, 2)).astype(np.float32)
+    return np.ascontiguousarray(np.concatenate([s2, dem, s1], -1), np.float32)
+
+
+def synth_model_input(B, H, seed, T1=5):
+    """Normalised model input [B,T1,H,H,17] in [-1,1] with spatial structure."""
+    r = np.random.default_rng(seed)
+    k = H // 4 + 1
+    base = r.uniform(-1, 1, (B, 1, k, k, 17)).astype(np.float32)
+    base = np.repeat(np.repeat(base, 4, 2), 4, 3)[:, :, :H, :H]
+    x = base + 0.15 * r.standard_normal((B, T1, H, H, 17)).astype(np.float32)
+    return np.ascontiguousarray(np.clip(x, -1, 1), np.float32)

@@ -83,6 +83,7 @@ class GraphInterpreter:
     # ------------------------------------------------------------------
     def run(self, fetch, feeds):
         self.memo = {}
+        self.frames = {k: None for k in self.frames}   # while-loop results are per run
         self.feeds = {k: np.asarray(v) for k, v in feeds.items()}
         return self._eval(fetch, None)
 

@@ -1,0 +1,376 @@
+"""ctypes binding of libstc.so + host-side mirror of the reference's hot-path
+functions (same names, argument meaning, in-place / return contracts).
+
+Reference functions mirrored (all in /root/reference/src/download_and_predict_job.py
+unless noted):
+  normalize_subtile(subtile)                        :316-325  (in place)
+  predict_subtile(subtile, sess, op, size)          :328-369
+  make_indices(arr)                                 :998-1006
+  smooth_large_tile(arr, dates, interp)             :1057-1096
+  superresolve_large_tile(arr, sess)                :95-147   (in place on arr[..., 4:])
+The `sess` slot takes a StcSession (replaces the tf.compat.v1.Session globals,
+:1785-1826).  There is NO CPU fallback: if libstc.so or a CUDA sm_100 device is
+missing, StcSession() raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import weights as _weights
+from . import regrid as _regrid
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libstc.so")
+_lib = None
+
+# normalisation constants of the released model, src/download_and_predict_job.py:1829-1842
+MIN_ALL = [0.006576638437476157, 0.0162050812542916, 0.010040436408026246,
+           0.013351644159609368, 0.01965362020294499, 0.014229037918669413,
+           0.015289539940489814, 0.011993591210803388, 0.008239871824216068,
+           0.006546120393682765, 0.0, 0.0, 0.0, -0.1409399364817101,
+           -0.4973397113668104, -0.09731556326714398, -0.7193834232943873]
+MAX_ALL = [0.2691233691920348, 0.3740291447318227, 0.5171435111009385,
+           0.6027466239414053, 0.5650263218127718, 0.5747005416952773,
+           0.5933928435187305, 0.6034943160143434, 0.7472037842374304,
+           0.7000076295109483, 0.4, 0.948334642387533,
+           0.6729257769285485, 0.8177635298774327, 0.35768999002433816,
+           0.7545951919107605, 0.7602693339366691]
+
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+
+# every symbol include/stc.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("stc_create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    ("stc_destroy", None, [C.c_void_p]),
+    ("stc_last_error", C.c_char_p, [C.c_void_p]),
+    ("stc_version", C.c_char_p, []),
+    ("stc_launch_count", C.c_int64, [C.c_void_p]),
+    ("stc_set_conv_impl", C.c_int, [C.c_void_p, C.c_int]),
+    ("stc_set_weight", C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64]),
+    ("stc_finalize_weights", C.c_int, [C.c_void_p, C.c_int]),
+    ("stc_malloc", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    ("stc_free", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("stc_malloc_host", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    ("stc_free_host", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("stc_h2d", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    ("stc_d2h", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    ("stc_sync", C.c_int, [C.c_void_p]),
+    ("stc_timer_begin", C.c_int, [C.c_void_p]),
+    ("stc_timer_end", C.c_int, [C.c_void_p, _f32p]),
+    ("stc_conv_timing", C.c_int, [C.c_void_p, C.c_int, _f32p, C.POINTER(C.c_int64)]),
+    ("stc_predict_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
+    ("stc_predict_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
+    ("stc_assemble_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_assemble_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_predict_patches_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
+    ("stc_predict_patches_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
+    ("stc_temporal_matmul_host", C.c_int, [C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
+    ("stc_temporal_matmul_dev", C.c_int, [C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
+    ("stc_indices_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    ("stc_temporal_median_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    ("stc_superresolve_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_debug_read", C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p]),
+]
+
+
+def load_library(path=None):
+    """dlopen libstc.so and bind every declared symbol.  Raises if missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or _LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError("libstc.so not built (%s); run `python __graft_entry__.py build`. "
+                           "There is no CPU fallback." % p)
+    lib = C.CDLL(p)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, np.float64)
+    return a, a.ctypes.data_as(_f64p)
+
+
+class StcSession:
+    """Opaque handle passed wherever the reference passes a tf.Session."""
+
+    def __init__(self, device=0, predict_weights=None, superresolve_weights=None, conv_impl=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.stc_create(int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("stc_create(device=%d) failed with %d: a CUDA sm_100 (B200) device is required; "
+                               "there is no CPU fallback" % (device, rc))
+        self.h = h
+        self.device = device
+        self.length = 4            # args.length of the reference job (:354)
+        self.min_all = list(MIN_ALL)
+        self.max_all = list(MAX_ALL)
+        if conv_impl is None and os.environ.get("STC_CONV_IMPL"):
+            conv_impl = int(os.environ["STC_CONV_IMPL"])
+        if conv_impl is not None:
+            self._check(self.lib.stc_set_conv_impl(self.h, int(conv_impl)))
+        if predict_weights is not None:
+            self.load_predict(predict_weights)
+        if superresolve_weights is not None:
+            self.load_superresolve(superresolve_weights)
+
+    # -- plumbing ----------------------------------------------------------------
+    def _check(self, rc):
+        if rc is not None and rc < 0:
+            raise RuntimeError("libstc error %d: %s" % (rc, self.lib.stc_last_error(self.h).decode()))
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.stc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _set_weights(self, w, which):
+        for k, v in w.items():
+            v = np.ascontiguousarray(v, np.float32)
+            self._check(self.lib.stc_set_weight(self.h, k.encode(), v.ctypes.data_as(_f32p), v.size))
+        self._check(self.lib.stc_finalize_weights(self.h, which))
+
+    def load_predict(self, src):
+        """src: path to predict_graph-*.pb, path to .npz of canonical tensors, or dict."""
+        if isinstance(src, str):
+            src = _weights.load_predict_pb(src) if src.endswith(".pb") else _weights.load_npz(src)
+        self._set_weights(src, 0)
+
+    def load_superresolve(self, src):
+        if isinstance(src, str):
+            src = _weights.load_superresolve_pb(src) if src.endswith(".pb") else _weights.load_npz(src)
+        self._set_weights(src, 1)
+
+    def set_conv_impl(self, impl):
+        self._check(self.lib.stc_set_conv_impl(self.h, int(impl)))
+
+    def launch_count(self):
+        return int(self.lib.stc_launch_count(self.h))
+
+    # -- device memory (for benchmarks that keep inputs resident) ------------------
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.lib.stc_malloc(self.h, nbytes, C.byref(p)))
+        return p
+
+    def free(self, p):
+        self._check(self.lib.stc_free(self.h, p))
+
+    def pinned_empty(self, shape, dtype=np.float32):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(self.lib.stc_malloc_host(self.h, n, C.byref(p)))
+        buf = (C.c_char * n).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        arr._stc_pin = (self, p)
+        return arr
+
+    def h2d(self, dptr, arr):
+        self._check(self.lib.stc_h2d(self.h, dptr, _dptr(arr), arr.nbytes))
+
+    def d2h(self, arr, dptr):
+        self._check(self.lib.stc_d2h(self.h, _dptr(arr), dptr, arr.nbytes))
+
+    def sync(self):
+        self._check(self.lib.stc_sync(self.h))
+
+    def timer_begin(self):
+        self._check(self.lib.stc_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_float()
+        self._check(self.lib.stc_timer_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def conv_timing(self, enable_reset=-1):
+        ms, n = C.c_float(), C.c_int64()
+        self._check(self.lib.stc_conv_timing(self.h, enable_reset, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # -- model -------------------------------------------------------------------
+    def predict(self, x, length=None, normalize=False):
+        """x [B,T+1,H,W,17] float32 -> [B,H-14,W-14] float32 (pb:conv2d/Sigmoid)."""
+        x = np.ascontiguousarray(x, np.float32)
+        B, T1, H, W, Cc = x.shape
+        assert Cc == 17
+        length = int(self.length if length is None else length)
+        out = np.empty((B, H - 14, W - 14), np.float32)
+        mn, mnp = _f64(self.min_all)
+        mx, mxp = _f64(self.max_all)
+        self._check(self.lib.stc_predict_host(self.h, _dptr(x), B, T1 - 1, H, W, length, int(bool(normalize)), mnp, mxp, _dptr(out)))
+        return out
+
+    def predict_dev(self, x_dev, B, T, H, W, out_dev, length=None, normalize=False):
+        length = int(self.length if length is None else length)
+        mn, mnp = _f64(self.min_all)
+        mx, mxp = _f64(self.max_all)
+        self._check(self.lib.stc_predict_dev(self.h, x_dev, B, T, H, W, length, int(bool(normalize)), mnp, mxp, out_dev))
+
+    def assemble(self, monthly):
+        """monthly [B,12,H,W,13] -> [B,5,H,W,17] (see include/stc.h)."""
+        m = np.ascontiguousarray(monthly, np.float32)
+        B, n, H, W, Cc = m.shape
+        assert n == 12 and Cc == 13
+        out = np.empty((B, 5, H, W, 17), np.float32)
+        self._check(self.lib.stc_assemble_host(self.h, _dptr(m), B, H, W, _dptr(out)))
+        return out
+
+    def predict_patches(self, monthly, out=None):
+        """Fused tile path: monthly [B,12,H,W,13] -> tree-cover probabilities [B,H-14,W-14]."""
+        m = monthly if (monthly.dtype == np.float32 and monthly.flags.c_contiguous) else np.ascontiguousarray(monthly, np.float32)
+        B, n, H, W, Cc = m.shape
+        assert n == 12 and Cc == 13
+        if out is None:
+            out = np.empty((B, H - 14, W - 14), np.float32)
+        mn, mnp = _f64(self.min_all)
+        mx, mxp = _f64(self.max_all)
+        self._check(self.lib.stc_predict_patches_host(self.h, _dptr(m), B, H, W, mnp, mxp, _dptr(out)))
+        return out
+
+    def predict_patches_dev(self, m_dev, B, H, W, out_dev):
+        mn, mnp = _f64(self.min_all)
+        mx, mxp = _f64(self.max_all)
+        self._check(self.lib.stc_predict_patches_dev(self.h, m_dev, B, H, W, mnp, mxp, out_dev))
+
+    def debug_read(self, name):
+        n = self.lib.stc_debug_read(self.h, name.encode(), None)
+        self._check(n)
+        out = np.empty(n, np.float32)
+        self._check(self.lib.stc_debug_read(self.h, name.encode(), _dptr(out)))
+        return out
+
+    # -- preprocessing -------------------------------------------------------------
+    def temporal_matmul(self, arr, M):
+        """out[o] = sum_n M[o,n] * arr[n]  over the leading axis."""
+        a = np.ascontiguousarray(arr, np.float32)
+        M = np.ascontiguousarray(M, np.float32)
+        n_out, n_in = M.shape
+        assert a.shape[0] == n_in
+        inner = int(np.prod(a.shape[1:]))
+        out = np.empty((n_out,) + a.shape[1:], np.float32)
+        self._check(self.lib.stc_temporal_matmul_host(self.h, _dptr(a), M.ctypes.data_as(_f32p), n_in, n_out, inner, _dptr(out)))
+        return out
+
+    def indices(self, arr):
+        a = np.ascontiguousarray(arr, np.float32)
+        npix = int(np.prod(a.shape[:-1]))
+        out = np.empty(a.shape[:-1] + (4,), np.float32)
+        self._check(self.lib.stc_indices_host(self.h, _dptr(a), npix, a.shape[-1], _dptr(out)))
+        return out
+
+    def temporal_median(self, arr):
+        a = np.ascontiguousarray(arr, np.float32)
+        inner = int(np.prod(a.shape[1:]))
+        out = np.empty(a.shape[1:], np.float32)
+        self._check(self.lib.stc_temporal_median_host(self.h, _dptr(a), a.shape[0], inner, _dptr(out)))
+        return out
+
+    def superresolve(self, x10, bilinear6):
+        x = np.ascontiguousarray(x10, np.float32)
+        b = np.ascontiguousarray(bilinear6, np.float32)
+        N, H, W, _ = x.shape
+        out = np.empty((N, H, W, 6), np.float32)
+        self._check(self.lib.stc_superresolve_host(self.h, _dptr(x), _dptr(b), N, H, W, _dptr(out)))
+        return out
+
+
+# ======================================================================================
+# reference-signature functions
+# ======================================================================================
+def normalize_subtile(subtile, min_all=MIN_ALL, max_all=MAX_ALL):
+    """src/download_and_predict_job.py:316-325 -- in place, returns the same array.
+    (Host-side NumPy: the device path fuses this into the model's input packing.)"""
+    for band in range(0, subtile.shape[-1]):
+        mins, maxs = min_all[band], max_all[band]
+        subtile[..., band] = np.clip(subtile[..., band], mins, maxs)
+        midrange = (maxs + mins) / 2
+        rng = maxs - mins
+        subtile[..., band] = (subtile[..., band] - midrange) / (rng / 2)
+    return subtile
+
+
+def predict_subtile(subtile, sess, op=None, size=None):
+    """src/download_and_predict_job.py:328-369.  `op` is accepted for signature
+    compatibility (only predict_logits exists here).  All-zero input -> int 255 fill."""
+    SIZE = subtile.shape[1] - 14
+    size = SIZE if size is None else size
+    if np.sum(subtile) != 0:
+        if not isinstance(subtile.flat[0], np.floating):
+            assert np.max(subtile) > 1
+            subtile = subtile / 65535.
+        batch_x = subtile[np.newaxis].astype(np.float32)
+        preds = sess.predict(batch_x, length=sess.length).squeeze()
+        clip = (preds.shape[0] - size) // 2
+        if clip > 0:
+            preds = preds[clip:-clip, clip:-clip]
+        preds = np.float32(preds)
+    else:
+        preds = np.full((SIZE, SIZE), 255)
+    return preds
+
+
+def make_indices(arr, sess):
+    """src/download_and_predict_job.py:998-1006 (EVI, BI, MSAVI2, GRNDVI)."""
+    return sess.indices(arr)
+
+
+def smooth_large_tile(arr, dates, interp, sess):
+    """src/download_and_predict_job.py:1057-1096: median-fill missing px, indices,
+    15-day regrid + Whittaker + monthly mean -> (12,H,W,14).  The date logic and the
+    12 x n operator are built on the host (regrid.py); the arithmetic runs on the GPU."""
+    arr, dates, interp = _regrid.deal_w_missing_px(arr, dates, interp)
+    try:
+        M, _ = _regrid.monthly_operator(dates)
+    except Exception:
+        M = None
+    if M is None:
+        out = np.zeros((12, arr.shape[1], arr.shape[2], 14 if arr.shape[-1] == 10 else arr.shape[-1]), np.float32)
+        return out, [0, ], interp
+    sm = sess.temporal_matmul(arr, M)
+    if arr.shape[-1] == 10:
+        idx = sess.temporal_matmul(sess.indices(arr), M)
+        out = np.concatenate([sm, idx], axis=-1)
+    else:
+        out = sm
+    return out, dates, interp
+
+
+def superresolve_large_tile(arr, sess, wsize=110):
+    """src/download_and_predict_job.py:95-147.  110-px windows, last row/col anchored to
+    the edge.  Quirks kept on purpose: the bottom row of windows reads a PRE-resolution
+    copy of the bottom band (and that copy is updated in place window by window); the
+    right-most column is only processed in the bottom row (:133-143 never reach the other
+    right-edge windows).  Writes bands 4: of `arr` in place and returns it."""
+    from .windows import superres_windows
+    xs, ys = superres_windows(arr.shape[1], wsize), superres_windows(arr.shape[2], wsize)
+    bottom_band = np.copy(arr[:, xs[-1]:, ...])
+    for x in xs:
+        for y in ys:
+            bottom, right = (x == xs[-1]), (y == ys[-1])
+            if right and not bottom:
+                continue
+            src = bottom_band[:, :, y:y + wsize, ...] if bottom else arr[:, x:x + wsize, y:y + wsize, ...]
+            padded = np.pad(src, ((0, 0), (4, 4), (4, 4), (0, 0)), 'reflect')
+            resolved = sess.superresolve(padded, padded[..., 4:])
+            src[..., 4:] = resolved[:, 4:-4, 4:-4, :]
+            arr[:, x:x + wsize, y:y + wsize, ...] = src
+    return arr

@@ -1,0 +1,252 @@
+// extern "C" surface of libstc.so (declared in include/stc.h).
+#include "stc_common.cuh"
+#include <cstring>
+
+#define CTX_CHECK() do { if (!ctx) return STC_ERR_ARG; } while (0)
+
+extern "C" {
+
+const char* stc_version(void) { return "stc-b200 0.1 (sm_100a)"; }
+
+int stc_create(int device, stc_ctx** out) {
+  if (!out) return STC_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return STC_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return STC_ERR_CUDA;
+  if (prop.major != 10) return STC_ERR_STATE;  // sm_100a binary only; no fallback path exists
+  if (cudaSetDevice(device) != cudaSuccess) return STC_ERR_CUDA;
+  stc_ctx* ctx = new stc_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return STC_ERR_CUDA; }
+  cudaEventCreate(&ctx->t0); cudaEventCreate(&ctx->t1);
+  *out = ctx;
+  return STC_OK;
+}
+
+void stc_destroy(stc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  model_destroy(ctx);
+  sr_destroy(ctx);
+  for (auto& e : ctx->conv_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* stc_last_error(stc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t stc_launch_count(stc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int stc_set_conv_impl(stc_ctx* ctx, int impl) {
+  CTX_CHECK();
+  if (impl != 0 && impl != 1) STC_FAIL(STC_ERR_ARG, "conv impl must be 0 (tcgen05) or 1 (simt)");
+  ctx->conv_impl = impl;
+  return STC_OK;
+}
+
+int stc_set_weight(stc_ctx* ctx, const char* name, const float* data, int64_t n) {
+  CTX_CHECK();
+  if (!name || !data || n <= 0) STC_FAIL(STC_ERR_ARG, "set_weight: bad argument");
+  ctx->host_w[name] = std::vector<float>(data, data + n);
+  return STC_OK;
+}
+
+int stc_finalize_weights(stc_ctx* ctx, int which) {
+  CTX_CHECK();
+  cudaSetDevice(ctx->device);
+  if (which == 0) return model_finalize_weights(ctx);
+  if (which == 1) return sr_finalize_weights(ctx);
+  STC_FAIL(STC_ERR_ARG, "finalize_weights: which must be 0 or 1");
+}
+
+int stc_malloc(stc_ctx* ctx, size_t bytes, void** dptr) { CTX_CHECK(); cudaSetDevice(ctx->device); STC_CUDA(cudaMalloc(dptr, bytes)); return STC_OK; }
+int stc_free(stc_ctx* ctx, void* dptr) { CTX_CHECK(); STC_CUDA(cudaStreamSynchronize(ctx->stream)); STC_CUDA(cudaFree(dptr)); return STC_OK; }
+int stc_malloc_host(stc_ctx* ctx, size_t bytes, void** hptr) { CTX_CHECK(); STC_CUDA(cudaMallocHost(hptr, bytes)); return STC_OK; }
+int stc_free_host(stc_ctx* ctx, void* hptr) { CTX_CHECK(); STC_CUDA(cudaFreeHost(hptr)); return STC_OK; }
+int stc_h2d(stc_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CTX_CHECK(); STC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); return STC_OK;
+}
+int stc_d2h(stc_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CTX_CHECK(); STC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); return STC_OK;
+}
+int stc_sync(stc_ctx* ctx) { CTX_CHECK(); STC_CUDA(cudaStreamSynchronize(ctx->stream)); return STC_OK; }
+int stc_timer_begin(stc_ctx* ctx) { CTX_CHECK(); STC_CUDA(cudaEventRecord(ctx->t0, ctx->stream)); return STC_OK; }
+int stc_timer_end(stc_ctx* ctx, float* ms) {
+  CTX_CHECK();
+  STC_CUDA(cudaEventRecord(ctx->t1, ctx->stream));
+  STC_CUDA(cudaEventSynchronize(ctx->t1));
+  STC_CUDA(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+  return STC_OK;
+}
+int stc_conv_timing(stc_ctx* ctx, int enable_reset, float* total_ms, int64_t* launches) {
+  CTX_CHECK();
+  float tot = 0.f;
+  for (size_t i = 0; i < ctx->conv_events_used; ++i) {
+    float ms = 0.f;
+    STC_CUDA(cudaEventSynchronize(ctx->conv_events[i].second));
+    STC_CUDA(cudaEventElapsedTime(&ms, ctx->conv_events[i].first, ctx->conv_events[i].second));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int64_t)ctx->conv_events_used;
+  if (enable_reset >= 0) { ctx->time_convs = enable_reset != 0; ctx->conv_events_used = 0; }
+  return STC_OK;
+}
+
+// ---- helpers for host-buffer variants ------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+int stc_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int W, int length,
+                    int normalize, const double* min17, const double* max17, float* out_dev) {
+  CTX_CHECK();
+  return model_predict_dev(ctx, x_dev, B, T, H, W, length, normalize, min17, max17, out_dev);
+}
+
+int stc_predict_host(stc_ctx* ctx, const float* x_host, int B, int T, int H, int W, int length,
+                     int normalize, const double* min17, const double* max17, float* out_host) {
+  CTX_CHECK();
+  if (!x_host || !out_host || B < 1) STC_FAIL(STC_ERR_ARG, "predict: bad argument");
+  size_t nin = (size_t)B * (T + 1) * H * W * 17, nout = (size_t)B * (H - 14) * (W - 14);
+  DevBuf din, dout;
+  STC_CUDA(cudaMalloc(&din.p, nin * 4)); STC_CUDA(cudaMalloc(&dout.p, nout * 4));
+  STC_CUDA(cudaMemcpyAsync(din.p, x_host, nin * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = model_predict_dev(ctx, (const float*)din.p, B, T, H, W, length, normalize, min17, max17, (float*)dout.p);
+  if (rc) return rc;
+  STC_CUDA(cudaMemcpyAsync(out_host, dout.p, nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+int stc_assemble_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W, float* out_dev) {
+  CTX_CHECK();
+  return pre_assemble_dev(ctx, monthly_dev, B, H, W, out_dev);
+}
+
+int stc_assemble_host(stc_ctx* ctx, const float* monthly_host, int B, int H, int W, float* out_host) {
+  CTX_CHECK();
+  size_t nin = (size_t)B * 12 * H * W * 13, nout = (size_t)B * 5 * H * W * 17;
+  DevBuf din, dout;
+  STC_CUDA(cudaMalloc(&din.p, nin * 4)); STC_CUDA(cudaMalloc(&dout.p, nout * 4));
+  STC_CUDA(cudaMemcpyAsync(din.p, monthly_host, nin * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = pre_assemble_dev(ctx, (const float*)din.p, B, H, W, (float*)dout.p);
+  if (rc) return rc;
+  STC_CUDA(cudaMemcpyAsync(out_host, dout.p, nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+// monthly -> assemble -> normalize -> predict, processed in sub-batches so the f32
+// [b,5,H,W,17] intermediate stays small.
+static int predict_patches_core(stc_ctx* ctx, const float* monthly, bool host_in, int B, int H, int W,
+                                const double* min17, const double* max17, float* out, bool host_out) {
+  if (B < 1 || !monthly || !out || !min17 || !max17) STC_FAIL(STC_ERR_ARG, "predict_patches: bad argument");
+  const char* env = getenv("STC_CHUNK");
+  int chunk = env ? atoi(env) : 32;
+  if (chunk < 1) chunk = 1;
+  int Bc = B < chunk ? B : chunk;
+  size_t per_in = (size_t)12 * H * W * 13, per_mid = (size_t)5 * H * W * 17, per_out = (size_t)(H - 14) * (W - 14);
+  DevBuf din[2], dmid, dout;
+  STC_CUDA(cudaMalloc(&dmid.p, Bc * per_mid * 4));
+  if (host_in) { STC_CUDA(cudaMalloc(&din[0].p, Bc * per_in * 4)); STC_CUDA(cudaMalloc(&din[1].p, Bc * per_in * 4)); }
+  if (host_out) STC_CUDA(cudaMalloc(&dout.p, (size_t)B * per_out * 4));
+  float* o_dev = host_out ? (float*)dout.p : out;
+  int k = 0;
+  for (int b0 = 0; b0 < B; b0 += Bc, ++k) {
+    int nb = (B - b0) < Bc ? (B - b0) : Bc;
+    const float* src = monthly + (size_t)b0 * per_in;
+    if (host_in) {
+      STC_CUDA(cudaMemcpyAsync(din[k & 1].p, src, nb * per_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+      src = (const float*)din[k & 1].p;
+    }
+    int rc = pre_assemble_dev(ctx, src, nb, H, W, (float*)dmid.p); if (rc) return rc;
+    rc = model_predict_dev(ctx, (const float*)dmid.p, nb, 4, H, W, 4, 1, min17, max17, o_dev + (size_t)b0 * per_out);
+    if (rc) return rc;
+  }
+  if (host_out) STC_CUDA(cudaMemcpyAsync(out, o_dev, (size_t)B * per_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+int stc_predict_patches_host(stc_ctx* ctx, const float* monthly_host, int B, int H, int W,
+                             const double* min17, const double* max17, float* out_host) {
+  CTX_CHECK();
+  return predict_patches_core(ctx, monthly_host, true, B, H, W, min17, max17, out_host, true);
+}
+int stc_predict_patches_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W,
+                            const double* min17, const double* max17, float* out_dev) {
+  CTX_CHECK();
+  return predict_patches_core(ctx, monthly_dev, false, B, H, W, min17, max17, out_dev, false);
+}
+
+int stc_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_host, int n_in, int n_out, int64_t inner,
+                            float* out_dev) {
+  CTX_CHECK();
+  return pre_temporal_matmul_dev(ctx, in_dev, M_host, n_in, n_out, inner, out_dev);
+}
+int stc_temporal_matmul_host(stc_ctx* ctx, const float* in_host, const float* M_host, int n_in, int n_out, int64_t inner,
+                             float* out_host) {
+  CTX_CHECK();
+  if (!in_host || !M_host || !out_host || inner < 1) STC_FAIL(STC_ERR_ARG, "temporal_matmul: bad argument");
+  DevBuf din, dout;
+  STC_CUDA(cudaMalloc(&din.p, (size_t)n_in * inner * 4)); STC_CUDA(cudaMalloc(&dout.p, (size_t)n_out * inner * 4));
+  STC_CUDA(cudaMemcpyAsync(din.p, in_host, (size_t)n_in * inner * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = pre_temporal_matmul_dev(ctx, (const float*)din.p, M_host, n_in, n_out, inner, (float*)dout.p);
+  if (rc) return rc;
+  STC_CUDA(cudaMemcpyAsync(out_host, dout.p, (size_t)n_out * inner * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+int stc_indices_host(stc_ctx* ctx, const float* in_host, int64_t npix, int C, float* out_host) {
+  CTX_CHECK();
+  if (!in_host || !out_host || npix < 1) STC_FAIL(STC_ERR_ARG, "indices: bad argument");
+  DevBuf din, dout;
+  STC_CUDA(cudaMalloc(&din.p, (size_t)npix * C * 4)); STC_CUDA(cudaMalloc(&dout.p, (size_t)npix * 16));
+  STC_CUDA(cudaMemcpyAsync(din.p, in_host, (size_t)npix * C * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = pre_indices_dev(ctx, (const float*)din.p, npix, C, (float*)dout.p);
+  if (rc) return rc;
+  STC_CUDA(cudaMemcpyAsync(out_host, dout.p, (size_t)npix * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+int stc_temporal_median_host(stc_ctx* ctx, const float* in_host, int n, int64_t inner, float* out_host) {
+  CTX_CHECK();
+  if (!in_host || !out_host || inner < 1) STC_FAIL(STC_ERR_ARG, "temporal_median: bad argument");
+  DevBuf din, dout;
+  STC_CUDA(cudaMalloc(&din.p, (size_t)n * inner * 4)); STC_CUDA(cudaMalloc(&dout.p, (size_t)inner * 4));
+  STC_CUDA(cudaMemcpyAsync(din.p, in_host, (size_t)n * inner * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = pre_temporal_median_dev(ctx, (const float*)din.p, n, inner, (float*)dout.p);
+  if (rc) return rc;
+  STC_CUDA(cudaMemcpyAsync(out_host, dout.p, (size_t)inner * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+int stc_superresolve_host(stc_ctx* ctx, const float* x_host, const float* bilinear_host, int N, int H, int W, float* out_host) {
+  CTX_CHECK();
+  if (!x_host || !bilinear_host || !out_host) STC_FAIL(STC_ERR_ARG, "superresolve: bad argument");
+  size_t npx = (size_t)N * H * W;
+  DevBuf dx, db, dout;
+  STC_CUDA(cudaMalloc(&dx.p, npx * 40)); STC_CUDA(cudaMalloc(&db.p, npx * 24)); STC_CUDA(cudaMalloc(&dout.p, npx * 24));
+  STC_CUDA(cudaMemcpyAsync(dx.p, x_host, npx * 40, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(db.p, bilinear_host, npx * 24, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = sr_forward_dev(ctx, (const float*)dx.p, (const float*)db.p, N, H, W, (float*)dout.p);
+  if (rc) return rc;
+  STC_CUDA(cudaMemcpyAsync(out_host, dout.p, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+int64_t stc_debug_read(stc_ctx* ctx, const char* name, float* out_host) {
+  if (!ctx || !name) return STC_ERR_ARG;
+  return model_debug_read(ctx, name, out_host);
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Shared declarations for libstc (sm_100a).  See DESIGN.md for the data layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+#include <map>
+#include <vector>
+#include "../../include/stc.h"
+
+// ---------------------------------------------------------------------------------
+// Activation layout ("chunk-major"): an fp16 activation tensor with C channels over a
+// padded image batch [B][Hp][Wp] is stored as C/8 planes; plane c holds, for every
+// flattened padded pixel p = (b*Hp + yp)*Wp + xp, the 8 channels 8c..8c+7 as one
+// 16-byte unit (uint4).  Planes carry `guard` units of slack on both sides so that the
+// shifted-window reads of the implicit-GEMM convolution (p + dy*Wp + dx) never leave
+// the allocation.  A 3x3 tap is then a pure row shift of the K-major A operand: rows
+// are 16 B apart, so any shift keeps the 16-byte alignment UMMA descriptors need.
+// ---------------------------------------------------------------------------------
+struct Act {
+  uint4* base = nullptr;   // start of plane 0 (including guard)
+  int64_t plane = 0;       // uint4 units per plane (guard + Ptot + guard)
+  int guard = 0;
+  int chunks = 0;          // C/8
+  int B = 0, Hp = 0, Wp = 0;
+  int64_t Ptot() const { return (int64_t)B * Hp * Wp; }
+  __host__ __device__ uint4* at(int c) const { return base + (int64_t)c * plane + guard; }
+};
+
+// Raw (pre-normalisation) convolution output, fp32: N/4 planes of float4 per pixel.
+struct Raw {
+  float4* base = nullptr;
+  int64_t plane = 0;       // float4 units per plane (>= Ptot rounded to tiles)
+  int N = 0;
+};
+
+struct ConvParams {
+  // A operand: up to two channel sources (K-steps of 16 channels = 2 chunks each)
+  const uint4* a0[2]; int64_t a0_plane; int k0steps;
+  const uint4* a1[2]; int64_t a1_plane; int k1steps;
+  const uint4* w[2];            // packed weights [Ksteps][9 taps][2 chunks][N] uint4
+  float4* out[2]; int64_t out_plane;
+  double* stats[2];             // [B][G][2] (sum, sumsq) accumulated over valid outputs
+  const float* sse_w[2];        // MODE_CAND: 1x1 squeeze weights [N]
+  const float* bias;            // MODE_BIAS*: [N]
+  int N, G;
+  int B, Hp, Wp; int64_t Ptot;
+  int vy0, vy1, vx0, vx1;       // valid output range in padded coordinates
+  int mode;
+};
+enum { MODE_PLAIN = 0, MODE_PSCALE_SWISH = 1, MODE_SWISH = 2, MODE_CAND = 3,
+       MODE_BIAS = 4, MODE_BIAS_RELU = 5 };
+
+struct stc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int conv_impl = 0;
+  int num_sms = 148;
+  std::map<std::string, std::vector<float>> host_w;   // canonical name -> f32 tensor
+  // conv timing
+  bool time_convs = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
+  size_t conv_events_used = 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  void* model = nullptr;      // ModelState*
+  void* sr = nullptr;         // SuperresState*
+};
+
+#define STC_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (call);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + std::to_string(__LINE__); \
+      return STC_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define STC_FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// model entry points implemented in stc_model.cu
+int model_finalize_weights(stc_ctx* ctx);
+void model_destroy(stc_ctx* ctx);
+int model_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int W, int length,
+                      int normalize, const double* min17, const double* max17, float* out_dev);
+int64_t model_debug_read(stc_ctx* ctx, const char* name, float* out_host);
+int sr_finalize_weights(stc_ctx* ctx);
+void sr_destroy(stc_ctx* ctx);
+int sr_forward_dev(stc_ctx* ctx, const float* x_dev, const float* bil_dev, int N, int H, int W, float* out_dev);
+// conv launchers (stc_conv.cu)
+int launch_conv(stc_ctx* ctx, const ConvParams& p, int ndir);
+// preprocessing (stc_preproc.cu)
+int pre_assemble_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W, float* out_dev);
+int pre_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_host, int n_in, int n_out, int64_t inner, float* out_dev);
+int pre_indices_dev(stc_ctx* ctx, const float* in_dev, int64_t npix, int C, float* out_dev);
+int pre_temporal_median_dev(stc_ctx* ctx, const float* in_dev, int n, int64_t inner, float* out_dev);

@@ -1,0 +1,651 @@
+// ConvGRU + U-Net forward of predict_graph-<H>.pb on the chunk-major fp16 layout.
+// Reference call: src/download_and_predict_job.py:353-357 (sess.run(predict_logits, ...));
+// architecture: pb:down_16/bidirectional_rnn/*, pb:conv_median ... pb:conv2d/Sigmoid
+// (SURVEY.md section 8a rows M1-M5).  Convolutions run in stc_conv.cu; this file holds
+// the HBM-bound elementwise stages (input packing, GroupNorm apply + gating, sSE,
+// pooling / upsampling / concat placement, head) and the launch sequence.
+#include "stc_common.cuh"
+#include <cstring>
+#include <cmath>
+
+static constexpr float GN_EPS = 1e-5f;
+
+// --------------------------------------------------------------------------------------
+// device helpers
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 r;
+  __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
+  r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
+  return r;
+}
+__device__ __forceinline__ void unpack8(uint4 u, float* v) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { float2 f = __half22float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+}
+
+// Build per-channel GroupNorm affine (a, b): z = x*a + b, from (sum, sumsq) in double.
+// pb:*_norm/{moments,add,Sqrt,truediv,mul,add_1}: biased variance, eps inside the sqrt.
+__device__ __forceinline__ void gn_affine(const double* st /*[G][2]*/, int g, float count, float gamma, float beta,
+                                          float& a, float& b) {
+  double mean = st[2 * g] / (double)count;
+  double var = st[2 * g + 1] / (double)count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  float rstd = (float)(1.0 / sqrt(var + (double)GN_EPS));
+  a = rstd * gamma;
+  b = beta - (float)mean * a;
+}
+
+// --------------------------------------------------------------------------------------
+// input packing: x f32 [B,T1,H,W,17] -> X16 frames (32 channels = 4 chunks), optional
+// normalize_subtile (src/download_and_predict_job.py:316-325).  Sequence frames get a
+// reflect border (pb:.../gates/MirrorPad), the median frame a zero border (SAME conv).
+// --------------------------------------------------------------------------------------
+struct PrepParams {
+  const float* x; int B, T1, H, W;
+  uint4* dst; int64_t plane, frame_stride; int Hp, Wp;
+  int normalize; float lo[17], hi[17], mid[17], half[17];
+};
+
+__global__ void __launch_bounds__(256) prep_input_kernel(PrepParams p) {
+  const int t = blockIdx.y;
+  const int64_t P = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t Ptot = (int64_t)p.B * p.Hp * p.Wp;
+  if (P >= Ptot) return;
+  int hw = p.Hp * p.Wp;
+  int b = (int)(P / hw); int rem = (int)(P - (int64_t)b * hw);
+  int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+  int ys = yp - 1, xs = xp - 1;
+  bool border = (ys < 0 || ys >= p.H || xs < 0 || xs >= p.W);
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  const bool seq = (t < p.T1 - 1);
+  if (!border || seq) {
+    if (ys < 0) ys = 1; if (ys >= p.H) ys = p.H - 2;
+    if (xs < 0) xs = 1; if (xs >= p.W) xs = p.W - 2;
+    const float* s = p.x + ((((int64_t)b * p.T1 + t) * p.H + ys) * p.W + xs) * 17;
+#pragma unroll
+    for (int c = 0; c < 17; ++c) {
+      float x = s[c];
+      if (p.normalize) {
+        x = fminf(fmaxf(x, p.lo[c]), p.hi[c]);
+        x = __fdiv_rn(__fsub_rn(x, p.mid[c]), p.half[c]);
+      }
+      v[c] = x;
+    }
+  }
+  uint4* d = p.dst + (int64_t)t * p.frame_stride;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) d[(int64_t)c * p.plane + P] = pack8(v + 8 * c);
+}
+
+// --------------------------------------------------------------------------------------
+// ConvGRU gating stages (pb:.../while/<d>/conv_gru_cell/*)
+// --------------------------------------------------------------------------------------
+struct GruParams {
+  const float4* rawG[2]; int64_t rawG_plane;   // gates conv output, 64 ch (16 planes)
+  const float4* rawY[2]; int64_t rawY_plane;   // candidate conv output, 32 ch (8 planes)
+  float4* Hf[2]; int64_t Hf_plane;             // fp32 state, 32 ch (8 planes)
+  uint4* Hh[2]; uint4* RH[2]; int64_t act_plane; // fp16 copies with reflect border
+  uint4* cc[2]; int64_t cc_plane;              // final-step destination (CCin chunks), or null
+  const double* stG[2]; const double* stY[2];  // [B][16][2], [B][8][2]
+  const float* gam_r[2]; const float* bet_r[2]; const float* gam_u[2]; const float* bet_u[2];
+  const float* gam_y[2]; const float* bet_y[2];
+  int B, H, W, Hp, Wp;
+  float count;                                 // H*W*4 elements per group
+};
+
+__device__ __forceinline__ void write_reflect(uint4* plane_base, int64_t plane, int chunks, int b, int yp, int xp,
+                                              int Hp, int Wp, const uint4* vals) {
+  int ys[3] = {yp, (yp == 2) ? 0 : -1, (yp == Hp - 3) ? Hp - 1 : -1};
+  int xs[3] = {xp, (xp == 2) ? 0 : -1, (xp == Wp - 3) ? Wp - 1 : -1};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (ys[i] < 0) continue;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (xs[j] < 0) continue;
+      int64_t P = ((int64_t)b * Hp + ys[i]) * Wp + xs[j];
+      for (int c = 0; c < chunks; ++c) plane_base[(int64_t)c * plane + P] = vals[c];
+    }
+  }
+}
+
+// r = sigmoid(GN(g_r)); RH = r * h  (fp16, reflect border)
+__global__ void __launch_bounds__(256) gru_apply1_kernel(GruParams p) {
+  const int d = blockIdx.z, b = blockIdx.y;
+  __shared__ float sa[32], sb[32];
+  if (threadIdx.x < 32) {
+    int c = threadIdx.x;
+    gn_affine(p.stG[d] + (int64_t)b * 32, c >> 2, p.count, p.gam_r[d][c], p.bet_r[d][c], sa[c], sb[c]);
+  }
+  __syncthreads();
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.H * p.W) return;
+  int y = idx / p.W, x = idx - y * p.W;
+  int yp = y + 1, xp = x + 1;
+  int64_t P = ((int64_t)b * p.Hp + yp) * p.Wp + xp;
+  uint4 out[4];
+#pragma unroll
+  for (int c4 = 0; c4 < 8; c4 += 2) {
+    float v[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 g = p.rawG[d][(int64_t)(c4 + h) * p.rawG_plane + P];
+      float4 hs = p.Hf[d][(int64_t)(c4 + h) * p.Hf_plane + P];
+      int c = (c4 + h) * 4;
+      v[4 * h + 0] = sigm(g.x * sa[c] + sb[c]) * hs.x;
+      v[4 * h + 1] = sigm(g.y * sa[c + 1] + sb[c + 1]) * hs.y;
+      v[4 * h + 2] = sigm(g.z * sa[c + 2] + sb[c + 2]) * hs.z;
+      v[4 * h + 3] = sigm(g.w * sa[c + 3] + sb[c + 3]) * hs.w;
+    }
+    out[c4 >> 1] = pack8(v);
+  }
+  write_reflect(p.RH[d], p.act_plane, 4, b, yp, xp, p.Hp, p.Wp, out);
+}
+
+// u = sigmoid(GN(g_u)); h~ = u*h + (1-u)*tanh(GN(y)); h = 0.75 h + 0.25 h~ (zoneout, inference)
+__global__ void __launch_bounds__(256) gru_apply2_kernel(GruParams p) {
+  const int d = blockIdx.z, b = blockIdx.y;
+  __shared__ float ua[32], ub[32], ya[32], yb[32];
+  if (threadIdx.x < 32) {
+    int c = threadIdx.x;
+    gn_affine(p.stG[d] + (int64_t)b * 32, 8 + (c >> 2), p.count, p.gam_u[d][c], p.bet_u[d][c], ua[c], ub[c]);
+    gn_affine(p.stY[d] + (int64_t)b * 16, c >> 2, p.count, p.gam_y[d][c], p.bet_y[d][c], ya[c], yb[c]);
+  }
+  __syncthreads();
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.H * p.W) return;
+  int y = idx / p.W, x = idx - y * p.W;
+  int yp = y + 1, xp = x + 1;
+  int64_t P = ((int64_t)b * p.Hp + yp) * p.Wp + xp;
+  uint4 out[4];
+#pragma unroll
+  for (int c4 = 0; c4 < 8; c4 += 2) {
+    float v[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 g = p.rawG[d][(int64_t)(8 + c4 + h) * p.rawG_plane + P];
+      float4 yy = p.rawY[d][(int64_t)(c4 + h) * p.rawY_plane + P];
+      float4 hs = p.Hf[d][(int64_t)(c4 + h) * p.Hf_plane + P];
+      int c = (c4 + h) * 4;
+      float gu[4] = {g.x, g.y, g.z, g.w}, yv[4] = {yy.x, yy.y, yy.z, yy.w}, hv[4] = {hs.x, hs.y, hs.z, hs.w};
+      float hn[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float u = sigm(gu[k] * ua[c + k] + ub[c + k]);
+        float cand = tanhf(yv[k] * ya[c + k] + yb[c + k]);
+        float ht = u * hv[k] + (1.f - u) * cand;
+        hn[k] = 0.75f * hv[k] + 0.25f * ht;
+        v[4 * h + k] = hn[k];
+      }
+      p.Hf[d][(int64_t)(c4 + h) * p.Hf_plane + P] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    }
+    out[c4 >> 1] = pack8(v);
+  }
+  write_reflect(p.Hh[d], p.act_plane, 4, b, yp, xp, p.Hp, p.Wp, out);
+  if (p.cc[d]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p.cc[d][(int64_t)c * p.cc_plane + P] = out[c];
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// conv block tail: GroupNorm(8) -> sSE -> {identity/crop | maxpool2 | nearest x2} placement
+// into the consumer's fp16 buffer, or the 1x1 head + sigmoid (pb:<blk>_norm, csse_<blk>_*,
+// max_pooling2d*, up_sampling2d*, cropping2d*, conv2d/Sigmoid).
+// --------------------------------------------------------------------------------------
+struct ApplyParams {
+  const float4* raw; int64_t raw_plane; int C;
+  int sHp, sWp, so;            // source padded geometry; so = padded offset of valid output (1 SAME, 2 VALID)
+  const double* stats; float count;
+  const float* gamma; const float* beta; const float* sse_w; const float* sse_b;
+  uint4* dst; int64_t dst_plane; int dHp, dWp;
+  int Hd, Wd; int mode; int off;  // mode 0 identity(+crop off) 1 maxpool2 2 upsample2 3 head
+  const float* head_w; const float* head_b; float* head_out;
+};
+
+__global__ void __launch_bounds__(256) block_apply_kernel(ApplyParams p) {
+  extern __shared__ float s_ab[];   // [C] a, [C] b, [C] sse_w
+  float* sa = s_ab; float* sb = s_ab + p.C; float* sw = s_ab + 2 * p.C;
+  const int b = blockIdx.y;
+  const int gs = p.C / 8;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    gn_affine(p.stats + (int64_t)b * 16, c / gs, p.count, p.gamma[c], p.beta[c], sa[c], sb[c]);
+    sw[c] = p.sse_w[c];
+  }
+  __syncthreads();
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.Hd * p.Wd) return;
+  int yd = idx / p.Wd, xd = idx - yd * p.Wd;
+  int nsrc = (p.mode == 1) ? 4 : 1;
+  int64_t SP[4]; float sv[4];
+  for (int k = 0; k < nsrc; ++k) {
+    int ys, xs;
+    if (p.mode == 1) { ys = 2 * yd + (k >> 1); xs = 2 * xd + (k & 1); }
+    else if (p.mode == 2) { ys = yd >> 1; xs = xd >> 1; }
+    else { ys = yd + p.off; xs = xd + p.off; }
+    SP[k] = ((int64_t)b * p.sHp + ys + p.so) * p.sWp + xs + p.so;
+    float dot = 0.f;
+    for (int c4 = 0; c4 < p.C / 4; ++c4) {
+      float4 v = p.raw[(int64_t)c4 * p.raw_plane + SP[k]];
+      int c = c4 * 4;
+      dot += (v.x * sa[c] + sb[c]) * sw[c] + (v.y * sa[c + 1] + sb[c + 1]) * sw[c + 1] +
+             (v.z * sa[c + 2] + sb[c + 2]) * sw[c + 2] + (v.w * sa[c + 3] + sb[c + 3]) * sw[c + 3];
+    }
+    sv[k] = sigm(dot + p.sse_b[0]);
+  }
+  if (p.mode == 3) {
+    float acc = 0.f;
+    for (int c4 = 0; c4 < p.C / 4; ++c4) {
+      float4 v = p.raw[(int64_t)c4 * p.raw_plane + SP[0]];
+      int c = c4 * 4;
+      acc += (v.x * sa[c] + sb[c]) * sv[0] * p.head_w[c] + (v.y * sa[c + 1] + sb[c + 1]) * sv[0] * p.head_w[c + 1] +
+             (v.z * sa[c + 2] + sb[c + 2]) * sv[0] * p.head_w[c + 2] + (v.w * sa[c + 3] + sb[c + 3]) * sv[0] * p.head_w[c + 3];
+    }
+    p.head_out[((int64_t)b * p.Hd + yd) * p.Wd + xd] = sigm(acc + p.head_b[0]);
+    return;
+  }
+  int64_t DP = ((int64_t)b * p.dHp + yd + 1) * p.dWp + xd + 1;
+  for (int c8 = 0; c8 < p.C / 8; ++c8) {
+    float o[8];
+    for (int k = 0; k < nsrc; ++k) {
+      float4 v0 = p.raw[(int64_t)(2 * c8) * p.raw_plane + SP[k]];
+      float4 v1 = p.raw[(int64_t)(2 * c8 + 1) * p.raw_plane + SP[k]];
+      float t[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int c = c8 * 8 + i;
+        float z = (t[i] * sa[c] + sb[c]) * sv[k];
+        o[i] = (k == 0) ? z : fmaxf(o[i], z);
+      }
+    }
+    p.dst[(int64_t)c8 * p.dst_plane + DP] = pack8(o);
+  }
+}
+
+// decode an fp16 activation buffer interior to fp32 NHWC (debug / tests)
+__global__ void act_decode_kernel(const uint4* src, int64_t plane, int chunks, int B, int Hp, int Wp, float* out) {
+  int H = Hp - 2, W = Wp - 2;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = (int64_t)B * H * W * chunks;
+  if (idx >= n) return;
+  int c = (int)(idx % chunks); int64_t r = idx / chunks;
+  int x = (int)(r % W); r /= W; int y = (int)(r % H); int b = (int)(r / H);
+  int64_t P = ((int64_t)b * Hp + y + 1) * Wp + x + 1;
+  float v[8];
+  unpack8(src[(int64_t)c * plane + P], v);
+  float* o = out + (((int64_t)b * H + y) * W + x) * (chunks * 8) + c * 8;
+  for (int i = 0; i < 8; ++i) o[i] = v[i];
+}
+
+// --------------------------------------------------------------------------------------
+// host side: packed weights + scratch plan
+// --------------------------------------------------------------------------------------
+static const char* BLK[8] = {"conv_median", "conv_concat", "conv1", "conv2", "up2", "up2_out", "up3", "out"};
+static const int BLK_CIN[8] = {17, 128, 64, 128, 256, 256, 128, 128};
+static const int BLK_COUT[8] = {64, 64, 128, 256, 128, 128, 64, 64};
+
+struct DevAct {
+  Act a; size_t bytes = 0;
+};
+
+struct ModelState {
+  // packed weights
+  uint4* w_gates[2] = {nullptr, nullptr}; uint4* w_cand[2] = {nullptr, nullptr};
+  uint4* w_blk[8] = {nullptr};
+  float* fparams = nullptr;   // all small f32 vectors, contiguous
+  std::map<std::string, const float*> fp;
+  // scratch plan
+  int Bc = 0, H = 0, T1 = 0;
+  void* arena = nullptr; size_t arena_bytes = 0;
+  Act X16; int64_t x_frame_stride = 0;
+  Act Hh[2], RH[2], CCin, P1, CAT1, P2, U2in, U3in, CAT2;
+  Raw Hf[2], rawG[2], rawY[2], rawB;
+  double* stats = nullptr; size_t stats_bytes = 0;
+  double* stG = nullptr; double* stY = nullptr; double* stB = nullptr;
+  int lastB = 0;
+  bool weights_ready = false;
+};
+
+// pack HWIO f32 conv weights into [Ksteps][9][2][Npad][8] fp16 according to chanmap
+static std::vector<__half> pack_conv(const float* w, int Cin, int Cout, const std::vector<int>& chanmap, int Npad) {
+  int Ksteps = (int)chanmap.size() / 16;
+  std::vector<__half> out((size_t)Ksteps * 9 * 2 * Npad * 8);
+  for (int ks = 0; ks < Ksteps; ++ks)
+    for (int tap = 0; tap < 9; ++tap)
+      for (int ch = 0; ch < 2; ++ch)
+        for (int n = 0; n < Npad; ++n)
+          for (int k = 0; k < 8; ++k) {
+            int cin = chanmap[ks * 16 + ch * 8 + k];
+            float v = (cin >= 0 && n < Cout) ? w[((size_t)tap * Cin + cin) * Cout + n] : 0.f;
+            out[((((size_t)ks * 9 + tap) * 2 + ch) * Npad + n) * 8 + k] = __float2half_rn(v);
+          }
+  return out;
+}
+
+static int upload_packed(stc_ctx* ctx, const std::vector<__half>& h, uint4** dptr) {
+  if (*dptr) cudaFree(*dptr);
+  STC_CUDA(cudaMalloc((void**)dptr, h.size() * sizeof(__half)));
+  STC_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  return STC_OK;
+}
+
+int pack_and_upload_conv(stc_ctx* ctx, const float* w, int Cin, int Cout, const std::vector<int>& chanmap, int Npad, uint4** dptr) {
+  return upload_packed(ctx, pack_conv(w, Cin, Cout, chanmap, Npad), dptr);
+}
+
+static const std::vector<float>* getw(stc_ctx* ctx, const std::string& name, size_t n) {
+  auto it = ctx->host_w.find(name);
+  if (it == ctx->host_w.end() || it->second.size() != n) return nullptr;
+  return &it->second;
+}
+
+int model_finalize_weights(stc_ctx* ctx) {
+  ModelState* m = (ModelState*)ctx->model;
+  if (!m) { m = new ModelState(); ctx->model = m; }
+  // ---- conv kernels ----
+  std::vector<int> gru_map(64, -1);     // A channels: [x 0..16 | pad | h 0..31] -> cin [0..16 | - | 17..48]
+  for (int c = 0; c < 17; ++c) gru_map[c] = c;
+  for (int c = 0; c < 32; ++c) gru_map[32 + c] = 17 + c;
+  const char* dn[2] = {"fw", "bw"};
+  for (int d = 0; d < 2; ++d) {
+    auto* g = getw(ctx, std::string("gru.") + dn[d] + ".gates_w", 9 * 49 * 64);
+    auto* c = getw(ctx, std::string("gru.") + dn[d] + ".cand_w", 9 * 49 * 32);
+    if (!g || !c) STC_FAIL(STC_ERR_STATE, "missing GRU conv weights");
+    int rc = upload_packed(ctx, pack_conv(g->data(), 49, 64, gru_map, 64), &m->w_gates[d]); if (rc) return rc;
+    rc = upload_packed(ctx, pack_conv(c->data(), 49, 32, gru_map, 32), &m->w_cand[d]); if (rc) return rc;
+  }
+  for (int i = 0; i < 8; ++i) {
+    int cin = BLK_CIN[i], cout = BLK_COUT[i];
+    auto* w = getw(ctx, std::string(BLK[i]) + ".w", (size_t)9 * cin * cout);
+    if (!w) STC_FAIL(STC_ERR_STATE, std::string("missing weights for block ") + BLK[i]);
+    int cpad = (cin + 15) / 16 * 16;
+    if (i == 0) cpad = 32;
+    std::vector<int> map(cpad, -1);
+    for (int c = 0; c < cin; ++c) map[c] = c;
+    int rc = upload_packed(ctx, pack_conv(w->data(), cin, cout, map, cout), &m->w_blk[i]); if (rc) return rc;
+  }
+  // ---- small f32 vectors ----
+  std::vector<std::pair<std::string, size_t>> names;
+  for (int d = 0; d < 2; ++d) {
+    std::string p = std::string("gru.") + dn[d] + ".";
+    for (const char* s : {"r_gamma", "r_beta", "u_gamma", "u_beta", "y_gamma", "y_beta", "cand_sse_w"}) names.push_back({p + s, 32});
+  }
+  for (int i = 0; i < 8; ++i) {
+    std::string p = std::string(BLK[i]) + ".";
+    names.push_back({p + "gamma", (size_t)BLK_COUT[i]}); names.push_back({p + "beta", (size_t)BLK_COUT[i]});
+    names.push_back({p + "sse_w", (size_t)BLK_COUT[i]}); names.push_back({p + "sse_b", 1});
+  }
+  names.push_back({"head.w", 64}); names.push_back({"head.b", 1});
+  std::vector<float> flat; std::map<std::string, size_t> offs;
+  for (auto& nm : names) {
+    auto* v = getw(ctx, nm.first, nm.second);
+    if (!v) STC_FAIL(STC_ERR_STATE, "missing or mis-sized weight " + nm.first);
+    offs[nm.first] = flat.size();
+    flat.insert(flat.end(), v->begin(), v->end());
+    while (flat.size() % 4) flat.push_back(0.f);
+  }
+  if (m->fparams) cudaFree(m->fparams);
+  STC_CUDA(cudaMalloc((void**)&m->fparams, flat.size() * sizeof(float)));
+  STC_CUDA(cudaMemcpy(m->fparams, flat.data(), flat.size() * sizeof(float), cudaMemcpyHostToDevice));
+  m->fp.clear();
+  for (auto& o : offs) m->fp[o.first] = m->fparams + o.second;
+  m->weights_ready = true;
+  return STC_OK;
+}
+
+void model_destroy(stc_ctx* ctx) {
+  ModelState* m = (ModelState*)ctx->model;
+  if (!m) return;
+  for (int d = 0; d < 2; ++d) { cudaFree(m->w_gates[d]); cudaFree(m->w_cand[d]); }
+  for (int i = 0; i < 8; ++i) cudaFree(m->w_blk[i]);
+  cudaFree(m->fparams); cudaFree(m->arena); cudaFree(m->stats);
+  delete m; ctx->model = nullptr;
+}
+
+struct Geo { int H, Hp; int64_t P; };   // square images
+static Geo geo(int Bc, int H) { Geo g; g.H = H; g.Hp = H + 2; g.P = (int64_t)Bc * g.Hp * g.Hp; return g; }
+
+static size_t act_units(int chunks, const Geo& g, int& guard) {
+  guard = ((g.Hp + 2 + 512 + 7) / 8) * 8;
+  return (size_t)chunks * (size_t)(g.P + 2 * guard);
+}
+
+static int ensure_plan(stc_ctx* ctx, ModelState* m, int Bc, int H, int T1) {
+  if (m->arena && m->Bc == Bc && m->H == H && m->T1 == T1) return STC_OK;
+  if (m->arena) { cudaFree(m->arena); m->arena = nullptr; }
+  if (m->stats) { cudaFree(m->stats); m->stats = nullptr; }
+  const int p1 = H / 2, c1 = p1 - 2, p2 = c1 / 2, c2 = p2 - 2, u2 = 2 * c2, u3 = 2 * u2;
+  Geo g0 = geo(Bc, H), g1 = geo(Bc, p1), g2 = geo(Bc, p2), gu2 = geo(Bc, u2), gu3 = geo(Bc, u3);
+  struct Item { Act* a; int chunks; Geo g; };
+  std::vector<Item> acts = {
+      {&m->X16, 4 * T1, g0}, {&m->Hh[0], 4, g0}, {&m->Hh[1], 4, g0}, {&m->RH[0], 4, g0}, {&m->RH[1], 4, g0},
+      {&m->CCin, 16, g0}, {&m->P1, 8, g1}, {&m->CAT1, 32, gu2}, {&m->P2, 16, g2}, {&m->U2in, 32, gu2},
+      {&m->U3in, 16, gu3}, {&m->CAT2, 16, gu3}};
+  size_t total = 0;
+  std::vector<size_t> offs;
+  for (auto& it : acts) { int guard; size_t u = act_units(it.chunks, it.g, guard); offs.push_back(total); total += u * 16; }
+  // raw buffers (float4 planes): plane length = P0 rounded up to 512
+  int64_t rp = (g0.P + 511) / 512 * 512;
+  struct RItem { Raw* r; int planes; };
+  std::vector<RItem> raws = {{&m->Hf[0], 8}, {&m->Hf[1], 8}, {&m->rawG[0], 16}, {&m->rawG[1], 16},
+                             {&m->rawY[0], 8}, {&m->rawY[1], 8}, {&m->rawB, 16}};
+  std::vector<size_t> roffs;
+  for (auto& it : raws) { roffs.push_back(total); total += (size_t)it.planes * rp * 16; }
+  STC_CUDA(cudaMalloc(&m->arena, total));
+  STC_CUDA(cudaMemsetAsync(m->arena, 0, total, ctx->stream));
+  m->arena_bytes = total;
+  for (size_t i = 0; i < acts.size(); ++i) {
+    Act& a = *acts[i].a; int guard; act_units(acts[i].chunks, acts[i].g, guard);
+    a.base = (uint4*)((char*)m->arena + offs[i]); a.guard = guard; a.plane = acts[i].g.P + 2 * guard;
+    a.chunks = acts[i].chunks; a.B = Bc; a.Hp = acts[i].g.Hp; a.Wp = acts[i].g.Hp;
+  }
+  m->x_frame_stride = 4 * m->X16.plane;
+  for (size_t i = 0; i < raws.size(); ++i) {
+    Raw& r = *raws[i].r; r.base = (float4*)((char*)m->arena + roffs[i]); r.plane = rp; r.N = raws[i].planes * 4;
+  }
+  // stats: gates [T][2][Bc][16][2], cand [T][2][Bc][8][2], blocks [8][Bc][8][2]
+  int T = T1 - 1;
+  size_t nG = (size_t)T * 2 * Bc * 32, nY = (size_t)T * 2 * Bc * 16, nB = (size_t)8 * Bc * 16;
+  m->stats_bytes = (nG + nY + nB) * sizeof(double);
+  STC_CUDA(cudaMalloc((void**)&m->stats, m->stats_bytes));
+  m->stG = m->stats; m->stY = m->stats + nG; m->stB = m->stats + nG + nY;
+  m->Bc = Bc; m->H = H; m->T1 = T1;
+  return STC_OK;
+}
+
+static void set_valid(ConvParams& cp, const Act& a, bool same) {
+  cp.B = a.B; cp.Hp = a.Hp; cp.Wp = a.Wp; cp.Ptot = a.Ptot();
+  int lo = same ? 1 : 2;
+  cp.vy0 = lo; cp.vy1 = a.Hp - lo; cp.vx0 = lo; cp.vx1 = a.Wp - lo;
+}
+
+static int run_block_conv(stc_ctx* ctx, ModelState* m, int blk, const Act& in, int in_chunks, bool same, int B) {
+  ConvParams cp; memset(&cp, 0, sizeof(cp));
+  cp.a0[0] = in.at(0); cp.a0_plane = in.plane; cp.k0steps = in_chunks / 2; cp.k1steps = 0;
+  cp.a1[0] = nullptr; cp.a1_plane = 0;
+  cp.w[0] = m->w_blk[blk];
+  cp.out[0] = m->rawB.base; cp.out_plane = (int64_t)((in.Ptot() + 511) / 512 * 512);
+  cp.stats[0] = m->stB + (size_t)blk * m->Bc * 16;
+  cp.N = BLK_COUT[blk]; cp.G = 8;
+  set_valid(cp, in, same);
+  cp.B = B; cp.Ptot = (int64_t)B * in.Hp * in.Wp;
+  cp.mode = same ? MODE_PSCALE_SWISH : MODE_SWISH;
+  return launch_conv(ctx, cp, 1);
+}
+
+static int run_apply(stc_ctx* ctx, ModelState* m, int blk, const Act& src_geo, bool same, int mode, int off,
+                     Act* dst, int dst_chunk_off, int Hd, int B, float* head_out) {
+  ApplyParams ap; memset(&ap, 0, sizeof(ap));
+  ap.raw = m->rawB.base; ap.raw_plane = (int64_t)((src_geo.Ptot() + 511) / 512 * 512); ap.C = BLK_COUT[blk];
+  ap.sHp = src_geo.Hp; ap.sWp = src_geo.Wp; ap.so = same ? 1 : 2;
+  ap.stats = m->stB + (size_t)blk * m->Bc * 16;
+  int Hv = src_geo.Hp - 2 * ap.so;
+  ap.count = (float)Hv * (float)Hv * (float)(ap.C / 8);
+  std::string n = BLK[blk];
+  ap.gamma = m->fp[n + ".gamma"]; ap.beta = m->fp[n + ".beta"]; ap.sse_w = m->fp[n + ".sse_w"]; ap.sse_b = m->fp[n + ".sse_b"];
+  if (dst) { ap.dst = dst->at(dst_chunk_off); ap.dst_plane = dst->plane; ap.dHp = dst->Hp; ap.dWp = dst->Wp; }
+  ap.Hd = Hd; ap.Wd = Hd; ap.mode = mode; ap.off = off;
+  ap.head_w = m->fp["head.w"]; ap.head_b = m->fp["head.b"]; ap.head_out = head_out;
+  dim3 grid(cdiv((int64_t)Hd * Hd, 256), B);
+  block_apply_kernel<<<grid, 256, 3 * ap.C * sizeof(float), ctx->stream>>>(ap);
+  STC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return STC_OK;
+}
+
+static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, int B, int T, int H, int length,
+                         int normalize, const double* mn, const double* mx, float* out_dev) {
+  const int T1 = T + 1;
+  const int p1 = H / 2, c1 = p1 - 2, p2 = c1 / 2, c2 = p2 - 2, u2 = 2 * c2, u3 = 2 * u2;
+  (void)c2;
+  // ---- reset state ----
+  STC_CUDA(cudaMemsetAsync(m->stats, 0, m->stats_bytes, ctx->stream));
+  for (int d = 0; d < 2; ++d) {
+    STC_CUDA(cudaMemsetAsync(m->Hf[d].base, 0, (size_t)8 * m->Hf[d].plane * 16, ctx->stream));
+    STC_CUDA(cudaMemsetAsync(m->Hh[d].base, 0, (size_t)4 * m->Hh[d].plane * 16, ctx->stream));
+    STC_CUDA(cudaMemsetAsync(m->RH[d].base, 0, (size_t)4 * m->RH[d].plane * 16, ctx->stream));
+  }
+  // ---- pack input ----
+  {
+    PrepParams pp; memset(&pp, 0, sizeof(pp));
+    pp.x = x_dev; pp.B = B; pp.T1 = T1; pp.H = H; pp.W = H;
+    pp.dst = m->X16.at(0); pp.plane = m->X16.plane; pp.frame_stride = m->x_frame_stride;
+    pp.Hp = H + 2; pp.Wp = H + 2; pp.normalize = normalize;
+    for (int c = 0; c < 17; ++c) {
+      // normalize_subtile: python-float (double) mins/maxs, float32 array arithmetic
+      double lo = normalize ? mn[c] : 0.0, hi = normalize ? mx[c] : 1.0;
+      pp.lo[c] = (float)lo; pp.hi[c] = (float)hi; pp.mid[c] = (float)((hi + lo) / 2); pp.half[c] = (float)((hi - lo) / 2);
+    }
+    dim3 grid(cdiv((int64_t)B * pp.Hp * pp.Wp, 256), T1);
+    prep_input_kernel<<<grid, 256, 0, ctx->stream>>>(pp);
+    STC_CUDA(cudaGetLastError()); ctx->launches++;
+  }
+  // ---- bidirectional ConvGRU ----
+  const int steps = length < T ? length : T;
+  const char* dn[2] = {"fw", "bw"};
+  for (int t = 0; t < steps; ++t) {
+    int frame[2] = {t, length - 1 - t};
+    ConvParams cp; memset(&cp, 0, sizeof(cp));
+    for (int d = 0; d < 2; ++d) {
+      cp.a0[d] = m->X16.at(0) + (int64_t)frame[d] * m->x_frame_stride;
+      cp.a1[d] = m->Hh[d].at(0);
+      cp.w[d] = m->w_gates[d];
+      cp.out[d] = m->rawG[d].base;
+      cp.stats[d] = m->stG + ((size_t)t * 2 + d) * m->Bc * 32;
+    }
+    cp.a0_plane = m->X16.plane; cp.k0steps = 2; cp.a1_plane = m->Hh[0].plane; cp.k1steps = 2;
+    cp.out_plane = m->rawG[0].plane; cp.N = 64; cp.G = 16; cp.mode = MODE_PLAIN;
+    set_valid(cp, m->Hh[0], true); cp.B = B; cp.Ptot = (int64_t)B * cp.Hp * cp.Wp;
+    int rc = launch_conv(ctx, cp, 2); if (rc) return rc;
+
+    GruParams gp; memset(&gp, 0, sizeof(gp));
+    for (int d = 0; d < 2; ++d) {
+      std::string pre = std::string("gru.") + dn[d] + ".";
+      gp.rawG[d] = m->rawG[d].base; gp.rawY[d] = m->rawY[d].base; gp.Hf[d] = m->Hf[d].base;
+      gp.Hh[d] = m->Hh[d].at(0); gp.RH[d] = m->RH[d].at(0);
+      gp.cc[d] = (t == steps - 1) ? m->CCin.at(4 * d) : nullptr;
+      gp.stG[d] = m->stG + ((size_t)t * 2 + d) * m->Bc * 32;
+      gp.stY[d] = m->stY + ((size_t)t * 2 + d) * m->Bc * 16;
+      gp.gam_r[d] = m->fp[pre + "r_gamma"]; gp.bet_r[d] = m->fp[pre + "r_beta"];
+      gp.gam_u[d] = m->fp[pre + "u_gamma"]; gp.bet_u[d] = m->fp[pre + "u_beta"];
+      gp.gam_y[d] = m->fp[pre + "y_gamma"]; gp.bet_y[d] = m->fp[pre + "y_beta"];
+    }
+    gp.rawG_plane = m->rawG[0].plane; gp.rawY_plane = m->rawY[0].plane; gp.Hf_plane = m->Hf[0].plane;
+    gp.act_plane = m->Hh[0].plane; gp.cc_plane = m->CCin.plane;
+    gp.B = B; gp.H = H; gp.W = H; gp.Hp = H + 2; gp.Wp = H + 2; gp.count = (float)H * (float)H * 4.f;
+    dim3 ggrid(cdiv((int64_t)H * H, 256), B, 2);
+    gru_apply1_kernel<<<ggrid, 256, 0, ctx->stream>>>(gp);
+    STC_CUDA(cudaGetLastError()); ctx->launches++;
+
+    for (int d = 0; d < 2; ++d) {
+      cp.a1[d] = m->RH[d].at(0);
+      cp.w[d] = m->w_cand[d];
+      cp.out[d] = m->rawY[d].base;
+      cp.stats[d] = m->stY + ((size_t)t * 2 + d) * m->Bc * 16;
+      cp.sse_w[d] = m->fp[std::string("gru.") + dn[d] + ".cand_sse_w"];
+    }
+    cp.out_plane = m->rawY[0].plane; cp.N = 32; cp.G = 8; cp.mode = MODE_CAND;
+    rc = launch_conv(ctx, cp, 2); if (rc) return rc;
+
+    gru_apply2_kernel<<<ggrid, 256, 0, ctx->stream>>>(gp);
+    STC_CUDA(cudaGetLastError()); ctx->launches++;
+  }
+  // ---- U-Net ----
+  int rc;
+  Act xmed = m->X16; xmed.base = m->X16.base + (int64_t)T * m->x_frame_stride; xmed.chunks = 4;
+  rc = run_block_conv(ctx, m, 0, xmed, 4, true, B); if (rc) return rc;                       // conv_median
+  rc = run_apply(ctx, m, 0, m->CCin, true, 0, 0, &m->CCin, 8, H, B, nullptr); if (rc) return rc;
+  rc = run_block_conv(ctx, m, 1, m->CCin, 16, true, B); if (rc) return rc;                   // conv_concat
+  rc = run_apply(ctx, m, 1, m->CCin, true, 1, 0, &m->P1, 0, p1, B, nullptr); if (rc) return rc;
+  rc = run_apply(ctx, m, 1, m->CCin, true, 0, 6, &m->CAT2, 8, u3, B, nullptr); if (rc) return rc;
+  rc = run_block_conv(ctx, m, 2, m->P1, 8, false, B); if (rc) return rc;                     // conv1 (VALID)
+  rc = run_apply(ctx, m, 2, m->P1, false, 1, 0, &m->P2, 0, p2, B, nullptr); if (rc) return rc;
+  rc = run_apply(ctx, m, 2, m->P1, false, 0, 2, &m->CAT1, 16, u2, B, nullptr); if (rc) return rc;
+  rc = run_block_conv(ctx, m, 3, m->P2, 16, false, B); if (rc) return rc;                    // conv2 (VALID)
+  rc = run_apply(ctx, m, 3, m->P2, false, 2, 0, &m->U2in, 0, u2, B, nullptr); if (rc) return rc;
+  rc = run_block_conv(ctx, m, 4, m->U2in, 32, true, B); if (rc) return rc;                   // up2
+  rc = run_apply(ctx, m, 4, m->U2in, true, 0, 0, &m->CAT1, 0, u2, B, nullptr); if (rc) return rc;
+  rc = run_block_conv(ctx, m, 5, m->CAT1, 32, true, B); if (rc) return rc;                   // up2_out
+  rc = run_apply(ctx, m, 5, m->CAT1, true, 2, 0, &m->U3in, 0, u3, B, nullptr); if (rc) return rc;
+  rc = run_block_conv(ctx, m, 6, m->U3in, 16, true, B); if (rc) return rc;                   // up3
+  rc = run_apply(ctx, m, 6, m->U3in, true, 0, 0, &m->CAT2, 0, u3, B, nullptr); if (rc) return rc;
+  rc = run_block_conv(ctx, m, 7, m->CAT2, 16, false, B); if (rc) return rc;                  // out (VALID)
+  rc = run_apply(ctx, m, 7, m->CAT2, false, 3, 0, nullptr, 0, u3 - 2, B, out_dev); if (rc) return rc;
+  return STC_OK;
+}
+
+int model_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int W, int length,
+                      int normalize, const double* min17, const double* max17, float* out_dev) {
+  ModelState* m = (ModelState*)ctx->model;
+  if (!m || !m->weights_ready) STC_FAIL(STC_ERR_STATE, "predict: weights not finalized");
+  if (H != W) STC_FAIL(STC_ERR_ARG, "predict: H must equal W");
+  if (H % 4 != 0 || H < 28) STC_FAIL(STC_ERR_ARG, "predict: H must be a multiple of 4 and >= 28");
+  if (T < 1 || T > 12 || length < 1) STC_FAIL(STC_ERR_ARG, "predict: bad T/length");
+  if (normalize && (!min17 || !max17)) STC_FAIL(STC_ERR_ARG, "predict: normalize needs min/max");
+  if (B <= 0) return STC_OK;
+  const char* env = getenv("STC_CHUNK");
+  int chunk = env ? atoi(env) : 32;
+  if (chunk < 1) chunk = 1;
+  int Bc = B < chunk ? B : chunk;
+  int rc = ensure_plan(ctx, m, Bc, H, T + 1); if (rc) return rc;
+  const int Ho = H - 14;
+  for (int b0 = 0; b0 < B; b0 += Bc) {
+    int nb = (B - b0) < Bc ? (B - b0) : Bc;
+    rc = forward_chunk(ctx, m, x_dev + (size_t)b0 * (T + 1) * H * W * 17, nb, T, H, length, normalize, min17, max17,
+                       out_dev + (size_t)b0 * Ho * Ho);
+    if (rc) return rc;
+    m->lastB = nb;
+  }
+  return STC_OK;
+}
+
+int64_t model_debug_read(stc_ctx* ctx, const char* name, float* out_host) {
+  ModelState* m = (ModelState*)ctx->model;
+  if (!m || !m->arena) { ctx->err = "debug_read: no forward pass yet"; return STC_ERR_STATE; }
+  std::map<std::string, Act*> tab = {{"ccin", &m->CCin}, {"cat2", &m->CAT2}, {"p1", &m->P1}, {"cat1", &m->CAT1},
+                                     {"p2", &m->P2}, {"u2in", &m->U2in}, {"u3in", &m->U3in}, {"hh_fw", &m->Hh[0]},
+                                     {"hh_bw", &m->Hh[1]}, {"x16", &m->X16}};
+  auto it = tab.find(name);
+  if (it == tab.end()) { ctx->err = "debug_read: unknown buffer"; return STC_ERR_ARG; }
+  Act& a = *it->second;
+  int B = m->lastB, H = a.Hp - 2;
+  int64_t n = (int64_t)B * H * H * a.chunks * 8;
+  if (!out_host) return n;
+  float* d = nullptr;
+  if (cudaMalloc((void**)&d, n * sizeof(float)) != cudaSuccess) { ctx->err = "debug_read: cudaMalloc"; return STC_ERR_NOMEM; }
+  int64_t work = (int64_t)B * H * H * a.chunks;
+  act_decode_kernel<<<cdiv(work, 256), 256, 0, ctx->stream>>>(a.at(0), a.plane, a.chunks, B, a.Hp, a.Wp, d);
+  cudaError_t e = cudaMemcpyAsync(out_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) { ctx->err = std::string("debug_read: ") + cudaGetErrorString(e); return STC_ERR_CUDA; }
+  return n;
+}

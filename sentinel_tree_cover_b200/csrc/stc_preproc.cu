@@ -1,0 +1,211 @@
+// HBM-bound temporal preprocessing kernels (one thread owns one pixel(-channel) column of
+// n <= 32 time steps in registers; loads are coalesced across pixels).
+//   assemble_kernel        : process_subtiles medians + 17-channel frame layout + indices
+//                            (src/download_and_predict_job.py:1152-1160,1274-1283,1398-1407;
+//                             src/preprocessing/indices.py:4-54)
+//   temporal_matmul_kernel : calculate_and_save_best_images + Smoother.interpolate_array as
+//                            one 12 x n operator (src/downloading/utils.py:176-347,
+//                            src/preprocessing/whittaker_smoother.py:38-69)
+//   indices_kernel         : make_indices (src/download_and_predict_job.py:998-1006)
+//   temporal_median_kernel : np.median(axis=0) (:1152-1160)
+#include "stc_common.cuh"
+
+// ---- band indices, exactly the reference's float32 operation order ---------------------
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+// All arithmetic uses the explicit round-to-nearest intrinsics so nvcc cannot contract
+// mul+add into FMA: NumPy evaluates each float32 operation separately.
+__device__ __forceinline__ float idx_evi(float b2, float b3, float b4, float b8) {
+  // src/preprocessing/indices.py:15-27 : 2.5 * ((NIR-RED) / (NIR + 6*RED - 7.5*BLUE + 1))
+  float BLUE = clip01(b2), RED = clip01(b4), NIR = clip01(b8);
+  (void)b3;
+  float den = __fadd_rn(__fsub_rn(__fadd_rn(NIR, __fmul_rn(6.f, RED)), __fmul_rn(7.5f, BLUE)), 1.f);
+  float e = __fmul_rn(2.5f, __fdiv_rn(__fsub_rn(NIR, RED), den));
+  return fminf(fmaxf(e, -1.5f), 1.5f);
+}
+__device__ __forceinline__ float idx_bi(float b2, float b4, float b8, float b11) {
+  // src/preprocessing/indices.py:47-54
+  float B11 = clip01(b11), B4 = clip01(b4), B8 = clip01(b8), B2 = clip01(b2);
+  float p = __fadd_rn(B11, B4), q = __fadd_rn(B8, B2);
+  float v = __fdiv_rn(__fsub_rn(p, q), __fadd_rn(__fadd_rn(p, q), 1e-5f));
+  return fminf(fmaxf(v, -1.f), 1.f);
+}
+__device__ __forceinline__ float idx_msavi2(float b4, float b8) {
+  // src/preprocessing/indices.py:30-44
+  float RED = clip01(b4), NIR = clip01(b8);
+  float t = __fadd_rn(__fmul_rn(2.f, NIR), 1.f);
+  float s = __fsub_rn(__fmul_rn(t, t), __fmul_rn(8.f, __fsub_rn(NIR, RED)));
+  if (s < 0.f) s = 0.f;
+  float m = __fdiv_rn(__fsub_rn(t, __fsqrt_rn(s)), 2.f);
+  return fminf(fmaxf(m, -1.f), 1.f);
+}
+__device__ __forceinline__ float idx_grndvi(float b3, float b4, float b8) {
+  // src/preprocessing/indices.py:4-12
+  float nir = clip01(b8), green = clip01(b3), red = clip01(b4);
+  float gr = __fadd_rn(green, red);
+  float den = __fadd_rn(__fadd_rn(nir, gr), 1e-5f);
+  return __fdiv_rn(__fsub_rn(nir, gr), den);
+}
+
+__device__ __forceinline__ float med3(float a, float b, float c) {
+  return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));
+}
+
+template <int NMAX>
+__device__ __forceinline__ float median_n(float* v, int n) {
+  // insertion sort in registers/local; np.median: even n -> mean of the two middle values
+  for (int i = 1; i < n; ++i) {
+    float x = v[i]; int j = i - 1;
+    while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
+    v[j + 1] = x;
+  }
+  if (n & 1) return v[n >> 1];
+  return __fmul_rn(__fadd_rn(v[(n >> 1) - 1], v[n >> 1]), 0.5f);
+}
+
+__device__ __forceinline__ float median12(const float* in) {
+  float v[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) v[i] = in[i];
+  // fully unrolled odd-even transposition sort (12 passes), branch-free
+#pragma unroll
+  for (int pass = 0; pass < 12; ++pass) {
+#pragma unroll
+    for (int i = (pass & 1); i + 1 < 12; i += 2) {
+      float a = v[i], b = v[i + 1];
+      v[i] = fminf(a, b); v[i + 1] = fmaxf(a, b);
+    }
+  }
+  return __fmul_rn(__fadd_rn(v[5], v[6]), 0.5f);
+}
+
+// monthly [B,12,H,W,13] -> out [B,5,H,W,17]
+__global__ void __launch_bounds__(128) assemble_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                       int B, int HW) {
+  int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (int64_t)B * HW) return;
+  int b = (int)(pix / HW); int r = (int)(pix - (int64_t)b * HW);
+  const float* src = in + ((int64_t)b * 12 * HW + r) * 13;
+  float* dst = out + ((int64_t)b * 5 * HW + r) * 17;
+  const int64_t fs_in = (int64_t)HW * 13, fs_out = (int64_t)HW * 17;
+  float bands[5][12];   // B2, B3, B4, B8, B11 (channels 0,1,2,3,8)
+#pragma unroll
+  for (int c = 0; c < 13; ++c) {
+    float v[12];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) v[t] = src[t * fs_in + c];
+    if (c < 4) {
+#pragma unroll
+      for (int t = 0; t < 12; ++t) bands[c][t] = v[t];
+    } else if (c == 8) {
+#pragma unroll
+      for (int t = 0; t < 12; ++t) bands[4][t] = v[t];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q * fs_out + c] = med3(v[3 * q], v[3 * q + 1], v[3 * q + 2]);
+    dst[4 * fs_out + c] = median12(v);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v[12];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+      float b2 = bands[0][t], b3 = bands[1][t], b4 = bands[2][t], b8 = bands[3][t], b11 = bands[4][t];
+      v[t] = (k == 0) ? idx_evi(b2, b3, b4, b8) : (k == 1) ? idx_bi(b2, b4, b8, b11)
+           : (k == 2) ? idx_msavi2(b4, b8) : idx_grndvi(b3, b4, b8);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q * fs_out + 13 + k] = med3(v[3 * q], v[3 * q + 1], v[3 * q + 2]);
+    dst[4 * fs_out + 13 + k] = median12(v);
+  }
+}
+
+int pre_assemble_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W, float* out_dev) {
+  int64_t n = (int64_t)B * H * W;
+  assemble_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(monthly_dev, out_dev, B, H * W);
+  STC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return STC_OK;
+}
+
+// ---- out[o][i] = sum_n M[o][n] * in[n][i] ----------------------------------------------
+__constant__ float c_M[32 * 32];
+
+template <int VEC>
+__global__ void __launch_bounds__(256) temporal_matmul_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                              int n_in, int n_out, int64_t inner) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (i >= inner) return;
+  float v[32][VEC];
+  for (int n = 0; n < n_in; ++n) {
+    if (VEC == 4) {
+      float4 t = *reinterpret_cast<const float4*>(in + (int64_t)n * inner + i);
+      v[n][0] = t.x; v[n][1 % VEC] = t.y; v[n][2 % VEC] = t.z; v[n][3 % VEC] = t.w;
+    } else {
+      v[n][0] = in[(int64_t)n * inner + i];
+    }
+  }
+  for (int o = 0; o < n_out; ++o) {
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int n = 0; n < n_in; ++n) {
+      float m = c_M[o * 32 + n];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = fmaf(m, v[n][k], acc[k]);
+    }
+    if (VEC == 4) *reinterpret_cast<float4*>(out + (int64_t)o * inner + i) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+    else out[(int64_t)o * inner + i] = acc[0];
+  }
+}
+
+int pre_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_host, int n_in, int n_out, int64_t inner,
+                            float* out_dev) {
+  if (n_in < 1 || n_in > 32 || n_out < 1 || n_out > 32) STC_FAIL(STC_ERR_ARG, "temporal_matmul: n_in/n_out must be in 1..32");
+  float Mp[32 * 32] = {0};
+  for (int o = 0; o < n_out; ++o)
+    for (int n = 0; n < n_in; ++n) Mp[o * 32 + n] = M_host[o * n_in + n];
+  STC_CUDA(cudaMemcpyToSymbolAsync(c_M, Mp, sizeof(Mp), 0, cudaMemcpyHostToDevice, ctx->stream));
+  bool vec = (inner % 4 == 0) && (((uintptr_t)in_dev & 15) == 0) && (((uintptr_t)out_dev & 15) == 0);
+  if (vec) temporal_matmul_kernel<4><<<cdiv(inner / 4, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n_in, n_out, inner);
+  else temporal_matmul_kernel<1><<<cdiv(inner, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n_in, n_out, inner);
+  STC_CUDA(cudaGetLastError());
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));  // Mp is a stack buffer
+  ctx->launches++;
+  return STC_OK;
+}
+
+// ---- indices [npix,C] -> [npix,4] ---------------------------------------------------------
+__global__ void __launch_bounds__(256) indices_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t npix, int C) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const float* s = in + i * C;
+  float b2 = s[0], b3 = s[1], b4 = s[2], b8 = s[3], b11 = s[8];
+  float4 o = make_float4(idx_evi(b2, b3, b4, b8), idx_bi(b2, b4, b8, b11), idx_msavi2(b4, b8), idx_grndvi(b3, b4, b8));
+  *reinterpret_cast<float4*>(out + i * 4) = o;
+}
+
+int pre_indices_dev(stc_ctx* ctx, const float* in_dev, int64_t npix, int C, float* out_dev) {
+  if (C < 10) STC_FAIL(STC_ERR_ARG, "indices: need at least 10 bands");
+  indices_kernel<<<cdiv(npix, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, npix, C);
+  STC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return STC_OK;
+}
+
+// ---- temporal median ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) temporal_median_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int64_t inner) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= inner) return;
+  float v[32];
+  for (int t = 0; t < n; ++t) v[t] = in[(int64_t)t * inner + i];
+  out[i] = median_n<32>(v, n);
+}
+
+int pre_temporal_median_dev(stc_ctx* ctx, const float* in_dev, int n, int64_t inner, float* out_dev) {
+  if (n < 1 || n > 32) STC_FAIL(STC_ERR_ARG, "temporal_median: n must be in 1..32");
+  temporal_median_kernel<<<cdiv(inner, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n, inner);
+  STC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return STC_OK;
+}

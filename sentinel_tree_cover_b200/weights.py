@@ -4,7 +4,7 @@ The reference binds its models at src/download_and_predict_job.py:1785-1826
 (tf.import_graph_def of predict_graph-<SIZE+14>.pb and superresolve_graph.pb).
 Here the Const tensors are pulled straight out of the protobuf (pbread.py) and
 renamed to a short canonical scheme used by both the CUDA context and the
-oracle.  A canonical dict can be saved to / loaded from .npz so tests and the
+test checker.  A canonical dict can be saved to / loaded from .npz so tests and the
 benchmark run on machines that do not have the reference tree.
 
 Canonical names, predict graph:

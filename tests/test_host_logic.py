@@ -1,0 +1,82 @@
+"""CPU: library loading / ABI surface, sharding (world_size 2 over gloo)."""
+import os
+import re
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from sentinel_tree_cover_b200 import build, api
+    lib_path = build.build()
+    assert os.path.exists(lib_path)
+    lib = api.load_library()
+    header = open(os.path.join(ROOT, "include", "stc.h")).read()
+    declared = set(re.findall(r"\b(stc_[a-z0-9_]+)\s*\(", header))
+    bound = {s[0] for s in api.SYMBOLS}
+    assert declared == bound, (declared ^ bound)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.stc_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from sentinel_tree_cover_b200.api import StcSession
+    with pytest.raises(RuntimeError):
+        StcSession(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "sentinel_tree_cover_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M) and "oracle." not in src, fn
+
+
+def test_shard_range_partitions():
+    from sentinel_tree_cover_b200.shard import shard_range
+    for n in (0, 1, 7, 190, 36100):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sentinel_tree_cover_b200.shard import shard_range, broadcast_weights
+from sentinel_tree_cover_b200.weights import random_predict_weights
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+w = random_predict_weights(5) if rank == 0 else None
+w = broadcast_weights(w, dist)
+ref = random_predict_weights(5)
+assert sorted(w) == sorted(ref) and all(np.array_equal(w[k], ref[k]) for k in ref)
+lo, hi = shard_range(37, rank, world)
+t = torch.tensor([float(hi - lo)]); dist.all_reduce(t)
+assert int(t.item()) == 37
+tm = torch.tensor([1.0 + rank]); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+assert tm.item() == float(world)
+dist.barrier(); dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_weight_broadcast_and_sharding_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29617", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("OK") == 2
