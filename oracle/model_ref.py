@@ -29,8 +29,18 @@ def _t(a, dtype):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
 
 
+_QUANT = [None]   # set by PredictRef/SuperresolveRef(quant="fp16"): emulate fp16 conv operands
+
+
+def _q(t):
+    return t.to(torch.float16).to(t.dtype) if _QUANT[0] == "fp16" else t
+
+
 def _conv(x, w, pad):
-    """x NCHW, w HWIO numpy->OIHW. pad: 'zero' (SAME), 'reflect', 'valid'."""
+    """x NCHW, w HWIO numpy->OIHW. pad: 'zero' (SAME), 'reflect', 'valid'.
+    With quant="fp16" both operands are rounded to fp16 first (fp32 accumulate) -- the
+    arithmetic contract of the tensor-core path, used for tight GPU comparisons."""
+    x, w = _q(x), _q(w)
     if pad == "reflect":
         x = F.pad(x, (1, 1, 1, 1), mode="reflect")
         return F.conv2d(x, w)
@@ -56,8 +66,9 @@ def _partial_scale(H, W, dtype):
 
 
 class PredictRef:
-    def __init__(self, weights, dtype=torch.float32):
+    def __init__(self, weights, dtype=torch.float32, quant=None):
         self.dt = dtype
+        self.quant = quant
         self.w = {}
         for k, v in weights.items():
             if v.ndim == 4:
@@ -116,6 +127,7 @@ class PredictRef:
     def forward(self, x, length=None, taps=None):
         """x [B,T+1,H,W,17] float (normalised), frames 0..T-1 sequence, frame T median.
         Returns [B,H-14,W-14] probabilities (pb:conv2d/Sigmoid)."""
+        _QUANT[0] = self.quant
         x = _t(x, self.dt).permute(0, 1, 4, 2, 3)
         B, T1 = x.shape[:2]
         T = T1 - 1
@@ -134,6 +146,7 @@ class PredictRef:
         u3 = self.block("up3", F.interpolate(u2o, scale_factor=2, mode="nearest"), True, taps)
         o = self.block("out", torch.cat([u3, cc[:, :, 6:-6, 6:-6]], 1), False, taps)
         logit = (o * self.w["head.w"].view(1, 64, 1, 1)).sum(1) + self.w["head.b"]
+        _QUANT[0] = None
         return torch.sigmoid(logit).numpy()
 
 
@@ -141,13 +154,17 @@ class SuperresolveRef:
     """pb:superresolve_graph: [reflect-pad 1 + conv3x3 + bias] x6 with
     ReLU / x0.1 residuals, tanh, + bilinear input (Placeholder_1)."""
 
-    def __init__(self, weights, dtype=torch.float32):
+    def __init__(self, weights, dtype=torch.float32, quant=None):
         self.dt = dtype
+        self.quant = quant
         self.w = {k: (_t(np.transpose(v, (3, 2, 0, 1)), dtype) if v.ndim == 4 else _t(v, dtype))
                   for k, v in weights.items()}
 
     def _c(self, n, x):
         x = F.pad(x, (1, 1, 1, 1), mode="reflect")
+        if self.quant == "fp16":
+            h = lambda t: t.to(torch.float16).to(t.dtype)
+            return F.conv2d(h(x), h(self.w["sr.%s.w" % n]), self.w["sr.%s.b" % n])
         return F.conv2d(x, self.w["sr.%s.w" % n], self.w["sr.%s.b" % n])
 
     def forward(self, x10, bilinear6):

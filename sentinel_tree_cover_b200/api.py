@@ -70,6 +70,9 @@ SYMBOLS = [
     ("stc_indices_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     ("stc_temporal_median_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     ("stc_superresolve_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_mosaic_ratios_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_gauss_mosaic_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_debug_read", C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p]),
 ]
 
@@ -181,7 +184,8 @@ class StcSession:
         self._check(self.lib.stc_malloc_host(self.h, n, C.byref(p)))
         buf = (C.c_char * n).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-        arr._stc_pin = (self, p)
+        self._pins = getattr(self, '_pins', [])
+        self._pins.append(p)          # freed with the context's process; keeps the mapping alive
         return arr
 
     def h2d(self, dptr, arr):
@@ -293,6 +297,35 @@ class StcSession:
         return out
 
 
+    def mosaic(self, preds, xs, ys, out_shape, sigma=36):
+        """Gaussian overlap blend of subtile predictions (list/array [n,S,S], the arrays as
+        saved by process_subtiles) placed at (xs[i], ys[i]) -> uint8 canvas `out_shape`."""
+        n = len(preds)
+        S = np.asarray(preds[0]).shape[0]
+        P = np.empty((n, S, S), np.float32)
+        placed = np.zeros(n, np.int32)
+        for i, a in enumerate(preds):
+            scaled = np.array(a)                             # copy: the reference scales in place (:1570)
+            scaled[scaled < 255] = scaled[scaled < 255] * 100
+            placed[i] = int(np.sum(scaled) < S * S * 255)    # :1573 all-no-data subtiles are skipped
+            P[i] = np.asarray(a, np.float32)
+        xs = np.ascontiguousarray(xs, np.int32)
+        ys = np.ascontiguousarray(ys, np.int32)
+        gauss = np.ascontiguousarray(fspecial_gauss(S, sigma), np.float32)
+        mult = np.ones(n, np.float32)
+        if placed.all():                                     # an unplaced subtile makes calc_overlap raise -> no reweighting (:1597-1608)
+            ratios = np.empty(n, np.float32)
+            self._check(self.lib.stc_mosaic_ratios_host(self.h, _dptr(P), _dptr(xs), _dptr(ys), _dptr(placed), n, S, _dptr(ratios)))
+            with np.errstate(all="ignore"):
+                mult = (np.median(ratios) / ratios).astype(np.float32)
+                mult[mult > 1.5] = 1.5
+        out = np.empty(out_shape, np.uint8)
+        self._check(self.lib.stc_gauss_mosaic_host(self.h, _dptr(P), _dptr(xs), _dptr(ys), _dptr(placed), _dptr(gauss),
+                                                   _dptr(np.ascontiguousarray(mult, np.float32)), n, S,
+                                                   int(out_shape[0]), int(out_shape[1]), _dptr(out)))
+        return out
+
+
 # ======================================================================================
 # reference-signature functions
 # ======================================================================================
@@ -374,3 +407,28 @@ def superresolve_large_tile(arr, sess, wsize=110):
             src[..., 4:] = resolved[:, 4:-4, 4:-4, :]
             arr[:, x:x + wsize, y:y + wsize, ...] = src
     return arr
+
+
+def fspecial_gauss(size, sigma):
+    """src/download_and_predict_job.py:1489-1501 (float64)."""
+    x, y = np.mgrid[-size // 2 + 1:size // 2 + 1, -size // 2 + 1:size // 2 + 1]
+    return np.exp(-((x ** 2 + y ** 2) / (2.0 * sigma ** 2)))
+
+
+def load_mosaic_predictions(out_folder, depth, sess, size=None):
+    """src/download_and_predict_job.py:1515-1641 for depth == 1: walk processed/<x>/<y>.npy in
+    the reference's os.listdir order, blend on the GPU, return the uint8 tile."""
+    if depth != 1:
+        raise NotImplementedError("feature mosaics (depth > 1) are not part of this path yet")
+    x_tiles = [int(x) for x in os.listdir(out_folder) if '.DS' not in x]
+    preds, xs, ys = [], [], []
+    for x_tile in x_tiles:
+        y_tiles = [int(y[:-4]) for y in os.listdir(out_folder + str(x_tile) + "/") if '.DS' not in y]
+        for y_tile in y_tiles:
+            f = out_folder + str(x_tile) + "/" + str(y_tile) + ".npy"
+            if os.path.exists(f):
+                preds.append(np.load(f)); xs.append(x_tile); ys.append(y_tile)
+    S = size or preds[0].shape[0]
+    max_x = np.max(x_tiles) + S
+    max_y = np.max(y_tiles) + S          # like the reference: from the last listed x folder (:1535-1538)
+    return sess.mosaic(preds, xs, ys, (max_x, max_y))

@@ -141,18 +141,18 @@ int stc_assemble_host(stc_ctx* ctx, const float* monthly_host, int B, int H, int
   return STC_OK;
 }
 
-// monthly -> assemble -> normalize -> predict, processed in sub-batches so the f32
-// [b,5,H,W,17] intermediate stays small.
+// monthly -> (fused assemble + normalize + pack) -> predict.  Host inputs are staged through
+// two device buffers in sub-batches.
 static int predict_patches_core(stc_ctx* ctx, const float* monthly, bool host_in, int B, int H, int W,
                                 const double* min17, const double* max17, float* out, bool host_out) {
   if (B < 1 || !monthly || !out || !min17 || !max17) STC_FAIL(STC_ERR_ARG, "predict_patches: bad argument");
+  size_t per_in = (size_t)12 * H * W * 13, per_out = (size_t)(H - 14) * (W - 14);
+  if (!host_in && !host_out) return model_predict_patches_dev(ctx, monthly, B, H, W, min17, max17, out);
   const char* env = getenv("STC_CHUNK");
   int chunk = env ? atoi(env) : 32;
   if (chunk < 1) chunk = 1;
   int Bc = B < chunk ? B : chunk;
-  size_t per_in = (size_t)12 * H * W * 13, per_mid = (size_t)5 * H * W * 17, per_out = (size_t)(H - 14) * (W - 14);
-  DevBuf din[2], dmid, dout;
-  STC_CUDA(cudaMalloc(&dmid.p, Bc * per_mid * 4));
+  DevBuf din[2], dout;
   if (host_in) { STC_CUDA(cudaMalloc(&din[0].p, Bc * per_in * 4)); STC_CUDA(cudaMalloc(&din[1].p, Bc * per_in * 4)); }
   if (host_out) STC_CUDA(cudaMalloc(&dout.p, (size_t)B * per_out * 4));
   float* o_dev = host_out ? (float*)dout.p : out;
@@ -164,8 +164,7 @@ static int predict_patches_core(stc_ctx* ctx, const float* monthly, bool host_in
       STC_CUDA(cudaMemcpyAsync(din[k & 1].p, src, nb * per_in * 4, cudaMemcpyHostToDevice, ctx->stream));
       src = (const float*)din[k & 1].p;
     }
-    int rc = pre_assemble_dev(ctx, src, nb, H, W, (float*)dmid.p); if (rc) return rc;
-    rc = model_predict_dev(ctx, (const float*)dmid.p, nb, 4, H, W, 4, 1, min17, max17, o_dev + (size_t)b0 * per_out);
+    int rc = model_predict_patches_dev(ctx, src, nb, H, W, min17, max17, o_dev + (size_t)b0 * per_out);
     if (rc) return rc;
   }
   if (host_out) STC_CUDA(cudaMemcpyAsync(out, o_dev, (size_t)B * per_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -240,6 +239,52 @@ int stc_superresolve_host(stc_ctx* ctx, const float* x_host, const float* biline
   int rc = sr_forward_dev(ctx, (const float*)dx.p, (const float*)db.p, N, H, W, (float*)dout.p);
   if (rc) return rc;
   STC_CUDA(cudaMemcpyAsync(out_host, dout.p, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+
+static int mosaic_upload(stc_ctx* ctx, const float* preds, const int32_t* xs, const int32_t* ys, const int32_t* placed,
+                         int n, int S, DevBuf& dp, DevBuf& dx, DevBuf& dy, DevBuf& dpl) {
+  size_t np_ = (size_t)n * S * S * 4;
+  STC_CUDA(cudaMalloc(&dp.p, np_)); STC_CUDA(cudaMalloc(&dx.p, n * 4)); STC_CUDA(cudaMalloc(&dy.p, n * 4)); STC_CUDA(cudaMalloc(&dpl.p, n * 4));
+  STC_CUDA(cudaMemcpyAsync(dp.p, preds, np_, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(dx.p, xs, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(dy.p, ys, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(dpl.p, placed, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  return STC_OK;
+}
+
+int stc_mosaic_ratios_host(stc_ctx* ctx, const float* preds_host, const int32_t* xs, const int32_t* ys, const int32_t* placed,
+                           int n, int S, float* ratios_host) {
+  CTX_CHECK();
+  if (!preds_host || !xs || !ys || !placed || !ratios_host || n < 1 || S < 1) STC_FAIL(STC_ERR_ARG, "mosaic_ratios: bad argument");
+  DevBuf dp, dx, dy, dpl, dr;
+  int rc = mosaic_upload(ctx, preds_host, xs, ys, placed, n, S, dp, dx, dy, dpl); if (rc) return rc;
+  STC_CUDA(cudaMalloc(&dr.p, n * 4));
+  rc = pre_gauss_mosaic_dev(ctx, (const float*)dp.p, (const int*)dx.p, (const int*)dy.p, (const int*)dpl.p, nullptr, nullptr,
+                            (float*)dr.p, 0, n, S, 0, 0, nullptr, nullptr);
+  if (rc) return rc;
+  STC_CUDA(cudaMemcpyAsync(ratios_host, dr.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+int stc_gauss_mosaic_host(stc_ctx* ctx, const float* preds_host, const int32_t* xs, const int32_t* ys, const int32_t* placed,
+                          const float* gauss_host, const float* mult_host, int n, int S, int out_h, int out_w, uint8_t* out_host) {
+  CTX_CHECK();
+  if (!preds_host || !xs || !ys || !placed || !gauss_host || !mult_host || !out_host || n < 1 || S < 1 || out_h < 1 || out_w < 1)
+    STC_FAIL(STC_ERR_ARG, "gauss_mosaic: bad argument");
+  DevBuf dp, dx, dy, dpl, dg, dm, dt, dout;
+  int rc = mosaic_upload(ctx, preds_host, xs, ys, placed, n, S, dp, dx, dy, dpl); if (rc) return rc;
+  STC_CUDA(cudaMalloc(&dg.p, (size_t)S * S * 4)); STC_CUDA(cudaMalloc(&dm.p, n * 4));
+  STC_CUDA(cudaMalloc(&dt.p, (size_t)out_h * out_w)); STC_CUDA(cudaMalloc(&dout.p, (size_t)out_h * out_w));
+  STC_CUDA(cudaMemcpyAsync(dg.p, gauss_host, (size_t)S * S * 4, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(dm.p, mult_host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = pre_gauss_mosaic_dev(ctx, (const float*)dp.p, (const int*)dx.p, (const int*)dy.p, (const int*)dpl.p, (const float*)dg.p,
+                            (float*)dm.p, nullptr, 1, n, S, out_h, out_w, (unsigned char*)dt.p, (unsigned char*)dout.p);
+  if (rc) return rc;
+  STC_CUDA(cudaMemcpyAsync(out_host, dout.p, (size_t)out_h * out_w, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
   return STC_OK;
 }

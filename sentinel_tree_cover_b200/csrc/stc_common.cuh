@@ -86,6 +86,8 @@ int model_finalize_weights(stc_ctx* ctx);
 void model_destroy(stc_ctx* ctx);
 int model_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int W, int length,
                       int normalize, const double* min17, const double* max17, float* out_dev);
+int model_predict_patches_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W,
+                              const double* min17, const double* max17, float* out_dev);
 int64_t model_debug_read(stc_ctx* ctx, const char* name, float* out_host);
 int sr_finalize_weights(stc_ctx* ctx);
 void sr_destroy(stc_ctx* ctx);
@@ -97,3 +99,6 @@ int pre_assemble_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W
 int pre_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_host, int n_in, int n_out, int64_t inner, float* out_dev);
 int pre_indices_dev(stc_ctx* ctx, const float* in_dev, int64_t npix, int C, float* out_dev);
 int pre_temporal_median_dev(stc_ctx* ctx, const float* in_dev, int n, int64_t inner, float* out_dev);
+int pre_gauss_mosaic_dev(stc_ctx* ctx, const float* preds_dev, const int* xs_dev, const int* ys_dev, const int* placed_dev,
+                         const float* gauss_dev, float* mult_dev, float* ratios_dev, int stage,
+                         int n, int S, int Hc, int Wc, unsigned char* tmp_dev, unsigned char* out_dev);

@@ -5,6 +5,7 @@
 // the HBM-bound elementwise stages (input packing, GroupNorm apply + gating, sSE,
 // pooling / upsampling / concat placement, head) and the launch sequence.
 #include "stc_common.cuh"
+#include "stc_indices.cuh"
 #include <cstring>
 #include <cmath>
 
@@ -83,6 +84,93 @@ __global__ void __launch_bounds__(256) prep_input_kernel(PrepParams p) {
   uint4* d = p.dst + (int64_t)t * p.frame_stride;
 #pragma unroll
   for (int c = 0; c < 4; ++c) d[(int64_t)c * p.plane + P] = pack8(v + 8 * c);
+}
+
+// --------------------------------------------------------------------------------------
+// fused tile front end: monthly [B,12,H,W,13] -> quarterly/annual medians + indices
+// (assemble, stc_preproc.cu) -> normalize_subtile -> chunk-major fp16 frames with borders.
+// Skips the f32 [B,5,H,W,17] intermediate of the separate assemble + prep kernels.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ void write_border(uint4* base, int b, int yp, int xp, int Hp, int Wp,
+                                             const uint4& v, bool reflect) {
+  base[((int64_t)b * Hp + yp) * Wp + xp] = v;
+  if (!reflect) return;
+  int ys[3] = {yp, (yp == 2) ? 0 : -1, (yp == Hp - 3) ? Hp - 1 : -1};
+  int xs[3] = {xp, (xp == 2) ? 0 : -1, (xp == Wp - 3) ? Wp - 1 : -1};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (ys[i] < 0) continue;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (xs[j] < 0 || (i == 0 && j == 0)) continue;
+      base[((int64_t)b * Hp + ys[i]) * Wp + xs[j]] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) assemble_prep_kernel(const float* __restrict__ in, PrepParams p) {
+  int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = p.H * p.W;
+  if (pix >= (int64_t)p.B * HW) return;
+  int b = (int)(pix / HW); int r = (int)(pix - (int64_t)b * HW);
+  int y = r / p.W, x = r - y * p.W;
+  const float* src = in + ((int64_t)b * 12 * HW + r) * 13;
+  const int64_t fs_in = (int64_t)HW * 13;
+  float bands[5][12];
+  float fr[5][8];
+  auto norm = [&](float v, int c) { v = fminf(fmaxf(v, p.lo[c]), p.hi[c]); return __fdiv_rn(__fsub_rn(v, p.mid[c]), p.half[c]); };
+  auto flush = [&](int chunk) {
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      uint4 u = pack8(fr[f]);
+      uint4* d = p.dst + (int64_t)f * p.frame_stride + (int64_t)chunk * p.plane;
+      write_border(d, b, y + 1, x + 1, p.Hp, p.Wp, u, f < 4);
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < 13; ++c) {
+    float v[12];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) v[t] = src[t * fs_in + c];
+    if (c < 4) {
+#pragma unroll
+      for (int t = 0; t < 12; ++t) bands[c][t] = v[t];
+    } else if (c == 8) {
+#pragma unroll
+      for (int t = 0; t < 12; ++t) bands[4][t] = v[t];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fr[q][c & 7] = norm(med3(v[3 * q], v[3 * q + 1], v[3 * q + 2]), c);
+    fr[4][c & 7] = norm(median12(v), c);
+    if ((c & 7) == 7) flush(c >> 3);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = 13 + k;
+    float v[12];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+      float b2 = bands[0][t], b3 = bands[1][t], b4 = bands[2][t], b8 = bands[3][t], b11 = bands[4][t];
+      v[t] = (k == 0) ? idx_evi(b2, b3, b4, b8) : (k == 1) ? idx_bi(b2, b4, b8, b11)
+           : (k == 2) ? idx_msavi2(b4, b8) : idx_grndvi(b3, b4, b8);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fr[q][c & 7] = norm(med3(v[3 * q], v[3 * q + 1], v[3 * q + 2]), c);
+    fr[4][c & 7] = norm(median12(v), c);
+    if (c == 15) {
+      flush(1);
+#pragma unroll
+      for (int f = 0; f < 5; ++f)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fr[f][i] = 0.f;
+    }
+  }
+  flush(2);
+#pragma unroll
+  for (int f = 0; f < 5; ++f)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fr[f][i] = 0.f;
+  flush(3);
 }
 
 // --------------------------------------------------------------------------------------
@@ -501,7 +589,7 @@ static int run_apply(stc_ctx* ctx, ModelState* m, int blk, const Act& src_geo, b
   return STC_OK;
 }
 
-static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, int B, int T, int H, int length,
+static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const float* monthly_dev, int B, int T, int H, int length,
                          int normalize, const double* mn, const double* mx, float* out_dev) {
   const int T1 = T + 1;
   const int p1 = H / 2, c1 = p1 - 2, p2 = c1 / 2, c2 = p2 - 2, u2 = 2 * c2, u3 = 2 * u2;
@@ -524,8 +612,12 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, int B,
       double lo = normalize ? mn[c] : 0.0, hi = normalize ? mx[c] : 1.0;
       pp.lo[c] = (float)lo; pp.hi[c] = (float)hi; pp.mid[c] = (float)((hi + lo) / 2); pp.half[c] = (float)((hi - lo) / 2);
     }
-    dim3 grid(cdiv((int64_t)B * pp.Hp * pp.Wp, 256), T1);
-    prep_input_kernel<<<grid, 256, 0, ctx->stream>>>(pp);
+    if (monthly_dev) {
+      assemble_prep_kernel<<<cdiv((int64_t)B * H * H, 128), 128, 0, ctx->stream>>>(monthly_dev, pp);
+    } else {
+      dim3 grid(cdiv((int64_t)B * pp.Hp * pp.Wp, 256), T1);
+      prep_input_kernel<<<grid, 256, 0, ctx->stream>>>(pp);
+    }
     STC_CUDA(cudaGetLastError()); ctx->launches++;
   }
   // ---- bidirectional ConvGRU ----
@@ -619,7 +711,7 @@ int model_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int
   const int Ho = H - 14;
   for (int b0 = 0; b0 < B; b0 += Bc) {
     int nb = (B - b0) < Bc ? (B - b0) : Bc;
-    rc = forward_chunk(ctx, m, x_dev + (size_t)b0 * (T + 1) * H * W * 17, nb, T, H, length, normalize, min17, max17,
+    rc = forward_chunk(ctx, m, x_dev + (size_t)b0 * (T + 1) * H * W * 17, nullptr, nb, T, H, length, normalize, min17, max17,
                        out_dev + (size_t)b0 * Ho * Ho);
     if (rc) return rc;
     m->lastB = nb;
@@ -648,4 +740,28 @@ int64_t model_debug_read(stc_ctx* ctx, const char* name, float* out_host) {
   cudaFree(d);
   if (e != cudaSuccess) { ctx->err = std::string("debug_read: ") + cudaGetErrorString(e); return STC_ERR_CUDA; }
   return n;
+}
+
+// Fused tile path: monthly [B,12,H,W,13] (device) -> probabilities [B,H-14,W-14] (device).
+int model_predict_patches_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W,
+                              const double* min17, const double* max17, float* out_dev) {
+  ModelState* m = (ModelState*)ctx->model;
+  if (!m || !m->weights_ready) STC_FAIL(STC_ERR_STATE, "predict_patches: weights not finalized");
+  if (H != W || H % 4 != 0 || H < 28) STC_FAIL(STC_ERR_ARG, "predict_patches: H must equal W, be a multiple of 4 and >= 28");
+  if (!min17 || !max17) STC_FAIL(STC_ERR_ARG, "predict_patches: min/max required");
+  if (B <= 0) return STC_OK;
+  const char* env = getenv("STC_CHUNK");
+  int chunk = env ? atoi(env) : 32;
+  if (chunk < 1) chunk = 1;
+  int Bc = B < chunk ? B : chunk;
+  int rc = ensure_plan(ctx, m, Bc, H, 5); if (rc) return rc;
+  const int Ho = H - 14;
+  for (int b0 = 0; b0 < B; b0 += Bc) {
+    int nb = (B - b0) < Bc ? (B - b0) : Bc;
+    rc = forward_chunk(ctx, m, nullptr, monthly_dev + (size_t)b0 * 12 * H * W * 13, nb, 4, H, 4, 1, min17, max17,
+                       out_dev + (size_t)b0 * Ho * Ho);
+    if (rc) return rc;
+    m->lastB = nb;
+  }
+  return STC_OK;
 }
