@@ -134,6 +134,17 @@ int stc_gauss_mosaic_host(stc_ctx* ctx, const float* preds_host, const int32_t* 
                           const int32_t* placed, const float* gauss_host, const float* mult_host,
                           int n, int S, int out_h, int out_w, uint8_t* out_host);
 
+/* ---- cloud-mask feathering, id_areas_to_interp (src/preprocessing/cloud_removal.py:774-798,
+ *      closing_size 15) and the same stage of remove_cloud_and_shadows (:913-921, size 20):
+ *      per date with sum(mask) > 0:  a = 1 - min(EDT(1-mask),12)/12; a<0.2 -> 0;
+ *      grey_closing(a, size) (SciPy 'reflect' semantics).  masks/out [n,H,W] float32. ---- */
+int stc_feather_host(stc_ctx* ctx, const float* masks_host, int n, int H, int W, int closing_size, float* out_host);
+/* ---- scipy.ndimage.binary_dilation(x, iterations=k) with the 4-connected cross
+ *      (connectivity 1) or generate_binary_structure(2,2) (connectivity 2), border_value 0.
+ *      in/out [n,H,W] uint8 (0/1). ----------------------------------------------------- */
+int stc_binary_dilate_host(stc_ctx* ctx, const uint8_t* in_host, int n, int H, int W, int iterations,
+                           int connectivity, uint8_t* out_host);
+
 /* ---- debug: copy an internal activation buffer of the last stc_predict_*
  *      call to the host as float32 NHWC (interior only).  Names: "ccin",
  *      "cat2", "p1", "cat1", "p2", "u2in", "u3in".  Returns the number of

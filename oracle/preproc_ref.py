@@ -134,3 +134,80 @@ def synth_model_input(B, H, seed, T1=5):
     base = np.repeat(np.repeat(base, 4, 2), 4, 3)[:, :, :H, :H]
     x = base + 0.15 * r.standard_normal((B, T1, H, H, 17)).astype(np.float32)
     return np.ascontiguousarray(np.clip(x, -1, 1), np.float32)
+
+
+# ---- src/download_and_predict_job.py:1489-1641 (depth == 1) ----------------------------
+def fspecial_gauss(size, sigma):
+    x, y = np.mgrid[-size // 2 + 1:size // 2 + 1, -size // 2 + 1:size // 2 + 1]
+    return np.exp(-((x ** 2 + y ** 2) / (2.0 * sigma ** 2)))
+
+
+def mosaic(preds, xs, ys, out_shape, sigma=36, dilate_iters=10):
+    """load_mosaic_predictions for depth == 1, given the subtile arrays in the reference's layer
+    order.  (bn.nanmean -> np.nanmean as in the import shim.)"""
+    from scipy.ndimage import binary_dilation, generate_binary_structure
+    n = len(preds)
+    S = np.asarray(preds[0]).shape[0]
+    predictions = np.full((out_shape[0], out_shape[1], n), np.nan, dtype=np.float32)
+    mults = np.full((out_shape[0], out_shape[1], n), 0, dtype=np.float32)
+    for i in range(n):
+        prediction = np.array(preds[i])
+        prediction[prediction < 255] = prediction[prediction < 255] * 100
+        if np.sum(prediction) < S * S * 255:
+            prediction = prediction.T.astype(np.float32)
+            predictions[xs[i]:xs[i] + S, ys[i]:ys[i] + S, i] = prediction
+            f = fspecial_gauss(S, sigma)
+            f[prediction > 100] = 0.
+            mults[xs[i]:xs[i] + S, ys[i]:ys[i] + S, i] = f
+    ratios = np.zeros(n, np.float32)
+    mults[np.isnan(predictions)] = 0.
+    try:
+        with np.errstate(all="ignore"):
+            for i in range(n):
+                sub = predictions[..., i]
+                others = np.delete(predictions, i, -1)
+                others = others[~np.isnan(sub)].reshape((S, S, n - 1))
+                remove = np.argwhere(np.sum(np.isnan(others), axis=(0, 1)) == (S * S)).flatten()
+                others = np.nanmean(np.delete(others, remove, -1), axis=-1)
+                sub = sub[~np.isnan(sub)].reshape((S, S))
+                ratios[i] = np.nanmean(abs(others - sub))
+            multipliers = np.median(ratios) / ratios
+            multipliers[multipliers > 1.5] = 1.5
+        for i in range(n):
+            mults[..., i] *= multipliers[i]
+    except Exception:
+        pass
+    with np.errstate(all="ignore"):
+        predictions[predictions > 100] = np.nan
+        mults = mults / np.sum(mults, axis=-1)[..., np.newaxis]
+        nan_count = np.sum(np.isnan(predictions), axis=2)
+        out = np.nansum(predictions * mults, axis=-1)
+        out[nan_count == n] = np.nan
+        out[np.isnan(out)] = 255.
+        out = out.astype(np.uint8)
+    out[out <= .15 * 100] = 0.
+    out[out > 100] = 255.
+    no_images = binary_dilation(out == 255, structure=generate_binary_structure(2, 2), iterations=dilate_iters)
+    out[no_images] = 255
+    return out
+
+
+def synth_subtile_preds(L=618, S=158, seed=0, nodata_blocks=True, all_nodata=()):
+    """Synthetic saved subtile predictions for an L x L tile: smooth field + per-subtile bias,
+    optional 40x40 no-data blocks (255) and whole no-data subtiles (int 255 fill, :366)."""
+    from sentinel_tree_cover_b200.windows import subtile_windows
+    r = np.random.default_rng(seed)
+    folder, _ = subtile_windows(L, L, S)
+    yy, xx = np.mgrid[0:L, 0:L]
+    field = 0.5 + 0.45 * np.sin(xx / 37.0) * np.cos(yy / 53.0)
+    preds, xs, ys = [], [], []
+    for k, (x0, y0, _, _) in enumerate(folder):
+        if k in all_nodata:
+            p = np.full((S, S), 255)
+        else:
+            p = field[x0:x0 + S, y0:y0 + S].T + r.normal(0, 0.03, (S, S)) + r.normal(0, 0.02)
+            p = np.around(np.clip(p, 0.001, 0.999), 3).astype(np.float32)
+            if nodata_blocks and k % 7 == 3:
+                p[40:80, 80:120] = 255.
+        preds.append(p); xs.append(int(x0)); ys.append(int(y0))
+    return preds, xs, ys

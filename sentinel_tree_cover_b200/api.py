@@ -73,6 +73,8 @@ SYMBOLS = [
     ("stc_mosaic_ratios_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("stc_gauss_mosaic_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_feather_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_binary_dilate_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_debug_read", C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p]),
 ]
 
@@ -297,6 +299,24 @@ class StcSession:
         return out
 
 
+    def feather(self, masks, closing_size):
+        """[n,H,W] float32 0/1 masks -> feathered interpolation weights (see include/stc.h)."""
+        m = np.ascontiguousarray(masks, np.float32)
+        n, H, W = m.shape
+        out = np.empty_like(m)
+        self._check(self.lib.stc_feather_host(self.h, _dptr(m), n, H, W, int(closing_size), _dptr(out)))
+        return out
+
+    def binary_dilation(self, x, iterations=1, connectivity=1):
+        """scipy.ndimage.binary_dilation(x, structure=cross|3x3, iterations=k) on [H,W] or [n,H,W]."""
+        a = np.ascontiguousarray(np.asarray(x) != 0, np.uint8)
+        shp = a.shape
+        a3 = a.reshape((-1,) + shp[-2:])
+        out = np.empty_like(a3)
+        self._check(self.lib.stc_binary_dilate_host(self.h, _dptr(a3), a3.shape[0], shp[-2], shp[-1], int(iterations),
+                                                    int(connectivity), _dptr(out)))
+        return out.reshape(shp).astype(bool)
+
     def mosaic(self, preds, xs, ys, out_shape, sigma=36):
         """Gaussian overlap blend of subtile predictions (list/array [n,S,S], the arrays as
         saved by process_subtiles) placed at (xs[i], ys[i]) -> uint8 canvas `out_shape`."""
@@ -407,6 +427,12 @@ def superresolve_large_tile(arr, sess, wsize=110):
             src[..., 4:] = resolved[:, 4:-4, 4:-4, :]
             arr[:, x:x + wsize, y:y + wsize, ...] = src
     return arr
+
+
+def id_areas_to_interp(tiles, probs, shadows, image_dates, pfcps, sess):
+    """src/preprocessing/cloud_removal.py:774-798: feathered interpolation masks (closing 15)."""
+    a = np.clip(np.copy(probs).astype(np.float32), 0, 1)
+    return sess.feather(a, 15)
 
 
 def fspecial_gauss(size, sigma):

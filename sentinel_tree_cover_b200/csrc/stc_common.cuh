@@ -102,3 +102,7 @@ int pre_temporal_median_dev(stc_ctx* ctx, const float* in_dev, int n, int64_t in
 int pre_gauss_mosaic_dev(stc_ctx* ctx, const float* preds_dev, const int* xs_dev, const int* ys_dev, const int* placed_dev,
                          const float* gauss_dev, float* mult_dev, float* ratios_dev, int stage,
                          int n, int S, int Hc, int Wc, unsigned char* tmp_dev, unsigned char* out_dev);
+int pre_feather_dev(stc_ctx* ctx, const float* mask_dev, int n, int H, int W, int size, float* tmp_a, float* tmp_b,
+                    float* sums_dev, float* out_dev);
+int pre_binary_dilate_dev(stc_ctx* ctx, const unsigned char* in_dev, int n, int H, int W, int iterations, int conn,
+                          unsigned char* out_dev);

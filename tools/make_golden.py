@@ -119,8 +119,38 @@ def main():
     out["srtile_out_sub"] = res[:, ::3, ::3, 4:].astype(np.float32)
     out["srtile_out_sum"] = np.float64(res.astype(np.float64).sum())
     np.savez_compressed(os.path.join(OUT, "preproc.npz"), **out)
+    mosaic_golden()
     print("wrote", sorted(os.listdir(OUT)))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--mosaic-only" not in sys.argv:
     main()
+
+
+def mosaic_golden():
+    """load_mosaic_predictions run by the reference on synthetic subtile files."""
+    import shutil, tempfile
+    job = refshim.ref("download_and_predict_job")
+    out = {}
+    for case, kw in (("a", dict(seed=1)), ("b", dict(seed=2, all_nodata=(5,)))):
+        preds, xs, ys = P.synth_subtile_preds(618, 158, **kw)
+        d = tempfile.mkdtemp() + "/"
+        for p, x, y in zip(preds, xs, ys):
+            os.makedirs(d + str(x), exist_ok=True)
+            np.save(d + str(x) + "/" + str(y) + ".npy", p)
+        job.SIZE = 158
+        res = job.load_mosaic_predictions(d, 1)
+        # record the layer order the reference walked (os.listdir order)
+        order = []
+        for xt in [int(x) for x in os.listdir(d)]:
+            for yt in [int(y[:-4]) for y in os.listdir(d + str(xt) + "/")]:
+                order.append((xt, yt))
+        out["order_" + case] = np.array(order, np.int32)
+        out["out_" + case] = res
+        shutil.rmtree(d)
+    np.savez_compressed(os.path.join(OUT, "mosaic.npz"), **out)
+    print("mosaic golden", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__" and "--mosaic-only" in sys.argv:
+    mosaic_golden()
