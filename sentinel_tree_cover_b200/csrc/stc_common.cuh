@@ -47,6 +47,7 @@ struct ConvParams {
   int B, Hp, Wp; int64_t Ptot;
   int vy0, vy1, vx0, vx1;       // valid output range in padded coordinates
   int mode;
+  int out_fp16;                 // 1: write fp16 planes of uint4 (8 ch) instead of fp32 float4 planes
 };
 enum { MODE_PLAIN = 0, MODE_PSCALE_SWISH = 1, MODE_SWISH = 2, MODE_CAND = 3,
        MODE_BIAS = 4, MODE_BIAS_RELU = 5 };

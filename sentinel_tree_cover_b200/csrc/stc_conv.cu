@@ -155,7 +155,18 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(ConvParams p) {
       }
     }
     if (valid && p.stats[dir]) { atomicAdd(&sStat[b - b0][gcur][0], s); atomicAdd(&sStat[b - b0][gcur][1], ss); }
-    if constexpr (CPT >= 4) {
+    if (p.out_fp16) {
+      if constexpr (CPT >= 4) {
+        __half2 hh[CPT / 2];
+#pragma unroll
+        for (int n = 0; n < CPT / 2; ++n) hh[n] = __floats2half2_rn(acc[i][2 * n], acc[i][2 * n + 1]);
+        int nc = n0 + cg * CPT;
+        uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<uint4*>(p.out[dir]) + (int64_t)(nc >> 3) * p.out_plane + P);
+#pragma unroll
+        for (int q = 0; q < CPT / 4; ++q)
+          o[((nc >> 2) & 1) + q] = make_uint2(*reinterpret_cast<uint32_t*>(&hh[2 * q]), *reinterpret_cast<uint32_t*>(&hh[2 * q + 1]));
+      }
+    } else if constexpr (CPT >= 4) {
 #pragma unroll
       for (int q = 0; q < CPT / 4; ++q) {
         int nc = n0 + cg * CPT + 4 * q;
@@ -248,12 +259,25 @@ struct UmmaCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
 };
 
-template <int N, int NT>
-__global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int tiles_per_dir, int total_tiles) {
+__device__ __forceinline__ uint4 pack8h(const float* v) {
+  uint4 r;
+  __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
+  r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
+  return r;
+}
+
+// G = GroupNorm groups whose (sum, sumsq) the epilogue accumulates (0 = no statistics).
+// Statistics live in per-lane registers across the CTA's contiguous run of tiles and are
+// flushed (warp shuffle reduction + one fp64 atomic per value) only when the sample changes:
+// a few hundred atomics per launch instead of one per warp-row (the first version spent
+// >90% of the kernel serialised on same-address L2 reductions; profiles/r01_*).
+template <int N, int NT, int G>
+__global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int tiles_per_dir, int total_tiles, int tiles_per_cta) {
   using C = UmmaCfg<N, NT>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2], then tmem ptr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
   const uint32_t bar_base = smem_u32(bars);
   auto FULL = [&](int s) { return bar_base + 8u * s; };
@@ -277,12 +301,14 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int Ksteps = p.k0steps + p.k1steps;
   const uint32_t smem_base = smem_u32(smem);
+  const int tile_begin = blockIdx.x * tiles_per_cta;
+  const int tile_end = (tile_begin + tiles_per_cta < total_tiles) ? tile_begin + tiles_per_cta : total_tiles;
 
   if (warp == 0) {
     // ===================== producer: bulk copies global -> shared =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int dir = tile / tiles_per_dir;
         const int64_t p0 = (int64_t)(tile - dir * tiles_per_dir) * (NT * 128);
         for (int ks = 0; ks < Ksteps; ++ks) {
@@ -308,7 +334,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
     // ===================== MMA issuer (one elected lane) =====================
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int stage = 0; uint32_t phase = 0; int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const int as = it & 1;
       mbar_wait(TEMPTY(as), ((uint32_t)(it >> 1) & 1u) ^ 1u);
       tc_fence_after();
@@ -337,28 +363,57 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
+    constexpr int GA = (G > 0) ? G : 1;
+    constexpr int GS = N / GA;            // channels per group
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int hw = p.Hp * p.Wp;
-    constexpr int GS_MAX = 16;
+    float acc_s[GA], acc_ss[GA];
+#pragma unroll
+    for (int g = 0; g < GA; ++g) { acc_s[g] = 0.f; acc_ss[g] = 0.f; }
+    int cur_b = -1, cur_dir = 0;
+    auto flush_warp = [&]() {   // warp-uniform: reduce over lanes, lanes 0..2G-1 each add one value
+      if (G == 0 || cur_b < 0) return;
+#pragma unroll
+      for (int g = 0; g < GA; ++g) {
+        float s = acc_s[g], ss = acc_ss[g];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+        if (lane == 0) {
+          atomicAdd(&p.stats[cur_dir][((int64_t)cur_b * GA + g) * 2 + 0], (double)s);
+          atomicAdd(&p.stats[cur_dir][((int64_t)cur_b * GA + g) * 2 + 1], (double)ss);
+        }
+        acc_s[g] = 0.f; acc_ss[g] = 0.f;
+      }
+    };
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const int as = it & 1;
       const int dir = tile / tiles_per_dir;
       const int64_t p0 = (int64_t)(tile - dir * tiles_per_dir) * (NT * 128);
-      const int gs = N / p.G;
       mbar_wait(TFULL(as), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < NT; ++j) {
         const int64_t P = p0 + j * 128 + row;
-        int b, yp, xp;
-        pixel_coords(P < p.Ptot ? P : 0, p.Hp, p.Wp, b, yp, xp);
         const bool inb = P < p.Ptot;
+        int b, yp, xp;
+        pixel_coords(inb ? P : 0, p.Hp, p.Wp, b, yp, xp);
         const bool valid = inb && (yp >= p.vy0 && yp < p.vy1 && xp >= p.vx0 && xp < p.vx1);
         const float sc = (p.mode == MODE_PSCALE_SWISH) ? pscale(p, yp, xp) : 1.f;
-        const int bl0 = __shfl_sync(0xffffffffu, b, 0), bl31 = __shfl_sync(0xffffffffu, b, 31);
-        const bool uniform = (bl0 == bl31);
+        const float vm = valid ? 1.f : 0.f;
+        bool per_lane_flush = false;
+        if (G > 0 && p.stats[dir]) {
+          const unsigned mk = __ballot_sync(0xffffffffu, inb);
+          if (mk) {
+            const int bw = __shfl_sync(0xffffffffu, b, __ffs(mk) - 1);
+            const bool uniform = __all_sync(0xffffffffu, !inb || b == bw);
+            if (uniform) {
+              if (bw != cur_b || dir != cur_dir) { flush_warp(); cur_b = bw; cur_dir = dir; }
+            } else {              // the warp's 32 pixels straddle two samples (once per sample boundary)
+              flush_warp(); cur_b = -1; per_lane_flush = true;
+            }
+          }
+        }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::ACC_COLS + j * N);
         float sse = 1.f;
         if (p.mode == MODE_CAND) {
@@ -372,7 +427,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
           }
           sse = sigmoidf_(d);
         }
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < N; c0 += 16) {
           float v[16];
           tmem_ld16(taddr + c0, v);
@@ -385,42 +440,43 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
             else if (p.mode == MODE_BIAS) { x += __ldg(&p.bias[c0 + i]); }
             else if (p.mode == MODE_BIAS_RELU) { x = fmaxf(x + __ldg(&p.bias[c0 + i]), 0.f); }
             v[i] = x;
-          }
-          if (inb) {
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-              p.out[dir][(int64_t)((c0 >> 2) + qd) * p.out_plane + P] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
-          }
-          if (p.stats[dir]) {
-            // groups inside this 16-channel chunk: gs in {2,4,8,16,32}
-            const int ng = (gs >= 16) ? 1 : 16 / gs;
-            const int gw = (gs >= 16) ? 16 : gs;
-            for (int g = 0; g < ng; ++g) {
-              float s = 0.f, ss = 0.f;
-              if (valid) {
-                for (int i = 0; i < gw; ++i) { float x = v[g * gw + i]; s += x; ss += x * x; }
-              }
-              const int gidx = (c0 + g * gw) / gs;
-              if (uniform) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-                if (lane == 0 && bl0 < p.B) {
-                  atomicAdd(&p.stats[dir][((int64_t)bl0 * p.G + gidx) * 2 + 0], (double)s);
-                  atomicAdd(&p.stats[dir][((int64_t)bl0 * p.G + gidx) * 2 + 1], (double)ss);
-                }
-              } else if (valid) {
-                atomicAdd(&p.stats[dir][((int64_t)b * p.G + gidx) * 2 + 0], (double)s);
-                atomicAdd(&p.stats[dir][((int64_t)b * p.G + gidx) * 2 + 1], (double)ss);
-              }
+            if (G > 0) {
+              const float xm = x * vm;
+              acc_s[(c0 + i) / GS] += xm;
+              acc_ss[(c0 + i) / GS] += xm * xm;
             }
           }
+          if (inb) {
+            if (p.out_fp16) {
+              uint4* o = reinterpret_cast<uint4*>(p.out[dir]);
+              o[(int64_t)((c0 >> 3) + 0) * p.out_plane + P] = pack8h(v);
+              o[(int64_t)((c0 >> 3) + 1) * p.out_plane + P] = pack8h(v + 8);
+            } else {
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd)
+                p.out[dir][(int64_t)((c0 >> 2) + qd) * p.out_plane + P] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+            }
+          }
+        }
+        if (G > 0 && per_lane_flush) {
+#pragma unroll
+          for (int g = 0; g < GA; ++g) {
+            if (valid) {
+              atomicAdd(&p.stats[dir][((int64_t)b * GA + g) * 2 + 0], (double)acc_s[g]);
+              atomicAdd(&p.stats[dir][((int64_t)b * GA + g) * 2 + 1], (double)acc_ss[g]);
+            }
+            acc_s[g] = 0.f; acc_ss[g] = 0.f;
+          }
+        } else if (G > 0 && !p.stats[dir]) {
+#pragma unroll
+          for (int g = 0; g < GA; ++g) { acc_s[g] = 0.f; acc_ss[g] = 0.f; }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(TEMPTY(as));
     }
-    (void)hw; (void)GS_MAX;
+    flush_warp();
   }
   // ---- teardown ----
   tc_fence_before();
@@ -433,11 +489,11 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
 // --------------------------------------------------------------------------------------
 // host launchers
 // --------------------------------------------------------------------------------------
-template <int N, int NT>
+template <int N, int NT, int G>
 static int launch_umma(stc_ctx* ctx, const ConvParams& p, int ndir) {
   using C = UmmaCfg<N, NT>;
   static bool configured = false;
-  auto kern = conv3x3_umma_kernel<N, NT>;
+  auto kern = conv3x3_umma_kernel<N, NT, G>;
   if (!configured) {
     STC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
@@ -445,7 +501,9 @@ static int launch_umma(stc_ctx* ctx, const ConvParams& p, int ndir) {
   int tiles_per_dir = cdiv(p.Ptot, NT * 128);
   int total = tiles_per_dir * ndir;
   int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  kern<<<grid, 192, C::SMEM_BYTES, ctx->stream>>>(p, tiles_per_dir, total);
+  int tiles_per_cta = cdiv(total, grid);
+  grid = cdiv(total, tiles_per_cta);
+  kern<<<grid, 192, C::SMEM_BYTES, ctx->stream>>>(p, tiles_per_dir, total, tiles_per_cta);
   STC_CUDA(cudaGetLastError());
   return STC_OK;
 }
@@ -487,13 +545,16 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p, int ndir) {
   if (ctx->conv_impl == 1) {
     rc = launch_simt(ctx, p, ndir);
   } else {
-    switch (p.N) {
-      case 16: rc = launch_umma<16, 4>(ctx, p, ndir); break;
-      case 32: rc = launch_umma<32, 4>(ctx, p, ndir); break;
-      case 64: rc = launch_umma<64, 4>(ctx, p, ndir); break;
-      case 128: rc = launch_umma<128, 2>(ctx, p, ndir); break;
-      case 256: rc = launch_umma<256, 1>(ctx, p, ndir); break;
-      default: STC_FAIL(STC_ERR_ARG, "conv: unsupported N");
+    const int key = p.N * 100 + (p.stats[0] ? p.G : 0);
+    switch (key) {
+      case 1600: rc = launch_umma<16, 4, 0>(ctx, p, ndir); break;
+      case 3200: rc = launch_umma<32, 4, 0>(ctx, p, ndir); break;
+      case 3208: rc = launch_umma<32, 4, 8>(ctx, p, ndir); break;
+      case 6408: rc = launch_umma<64, 4, 8>(ctx, p, ndir); break;
+      case 6416: rc = launch_umma<64, 4, 16>(ctx, p, ndir); break;
+      case 12808: rc = launch_umma<128, 2, 8>(ctx, p, ndir); break;
+      case 25608: rc = launch_umma<256, 1, 8>(ctx, p, ndir); break;
+      default: STC_FAIL(STC_ERR_ARG, "conv: unsupported (N, groups) combination");
     }
   }
   if (rc != STC_OK) return rc;

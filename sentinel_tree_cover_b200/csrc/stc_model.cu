@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(128) assemble_prep_kernel(const float* __restr
 // ConvGRU gating stages (pb:.../while/<d>/conv_gru_cell/*)
 // --------------------------------------------------------------------------------------
 struct GruParams {
-  const float4* rawG[2]; int64_t rawG_plane;   // gates conv output, 64 ch (16 planes)
-  const float4* rawY[2]; int64_t rawY_plane;   // candidate conv output, 32 ch (8 planes)
+  const uint4* rawG[2]; int64_t rawG_plane;    // gates conv output, 64 ch fp16 (8 planes of 8 ch)
+  const uint4* rawY[2]; int64_t rawY_plane;    // candidate conv output, 32 ch fp16 (4 planes)
   float4* Hf[2]; int64_t Hf_plane;             // fp32 state, 32 ch (8 planes)
   uint4* Hh[2]; uint4* RH[2]; int64_t act_plane; // fp16 copies with reflect border
   uint4* cc[2]; int64_t cc_plane;              // final-step destination (CCin chunks), or null
@@ -187,6 +187,7 @@ struct GruParams {
   const float* gam_y[2]; const float* bet_y[2];
   int B, H, W, Hp, Wp;
   float count;                                 // H*W*4 elements per group
+  int h_zero;                                  // first step: h == 0, do not read the state buffers
 };
 
 __device__ __forceinline__ void write_reflect(uint4* plane_base, int64_t plane, int chunks, int b, int yp, int xp,
@@ -222,16 +223,16 @@ __global__ void __launch_bounds__(256) gru_apply1_kernel(GruParams p) {
   uint4 out[4];
 #pragma unroll
   for (int c4 = 0; c4 < 8; c4 += 2) {
-    float v[8];
+    float v[8], gr[8];
+    unpack8(p.rawG[d][(int64_t)(c4 >> 1) * p.rawG_plane + P], gr);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float4 g = p.rawG[d][(int64_t)(c4 + h) * p.rawG_plane + P];
       float4 hs = p.Hf[d][(int64_t)(c4 + h) * p.Hf_plane + P];
       int c = (c4 + h) * 4;
-      v[4 * h + 0] = sigm(g.x * sa[c] + sb[c]) * hs.x;
-      v[4 * h + 1] = sigm(g.y * sa[c + 1] + sb[c + 1]) * hs.y;
-      v[4 * h + 2] = sigm(g.z * sa[c + 2] + sb[c + 2]) * hs.z;
-      v[4 * h + 3] = sigm(g.w * sa[c + 3] + sb[c + 3]) * hs.w;
+      v[4 * h + 0] = sigm(gr[4 * h + 0] * sa[c] + sb[c]) * hs.x;
+      v[4 * h + 1] = sigm(gr[4 * h + 1] * sa[c + 1] + sb[c + 1]) * hs.y;
+      v[4 * h + 2] = sigm(gr[4 * h + 2] * sa[c + 2] + sb[c + 2]) * hs.z;
+      v[4 * h + 3] = sigm(gr[4 * h + 3] * sa[c + 3] + sb[c + 3]) * hs.w;
     }
     out[c4 >> 1] = pack8(v);
   }
@@ -256,14 +257,15 @@ __global__ void __launch_bounds__(256) gru_apply2_kernel(GruParams p) {
   uint4 out[4];
 #pragma unroll
   for (int c4 = 0; c4 < 8; c4 += 2) {
-    float v[8];
+    float v[8], gu8[8], yv8[8];
+    unpack8(p.rawG[d][(int64_t)(4 + (c4 >> 1)) * p.rawG_plane + P], gu8);
+    unpack8(p.rawY[d][(int64_t)(c4 >> 1) * p.rawY_plane + P], yv8);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float4 g = p.rawG[d][(int64_t)(8 + c4 + h) * p.rawG_plane + P];
-      float4 yy = p.rawY[d][(int64_t)(c4 + h) * p.rawY_plane + P];
-      float4 hs = p.Hf[d][(int64_t)(c4 + h) * p.Hf_plane + P];
+      float4 hs = p.h_zero ? make_float4(0.f, 0.f, 0.f, 0.f) : p.Hf[d][(int64_t)(c4 + h) * p.Hf_plane + P];
       int c = (c4 + h) * 4;
-      float gu[4] = {g.x, g.y, g.z, g.w}, yv[4] = {yy.x, yy.y, yy.z, yy.w}, hv[4] = {hs.x, hs.y, hs.z, hs.w};
+      float gu[4] = {gu8[4 * h], gu8[4 * h + 1], gu8[4 * h + 2], gu8[4 * h + 3]};
+      float yv[4] = {yv8[4 * h], yv8[4 * h + 1], yv8[4 * h + 2], yv8[4 * h + 3]}, hv[4] = {hs.x, hs.y, hs.z, hs.w};
       float hn[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -523,8 +525,8 @@ static int ensure_plan(stc_ctx* ctx, ModelState* m, int Bc, int H, int T1) {
   // raw buffers (float4 planes): plane length = P0 rounded up to 512
   int64_t rp = (g0.P + 511) / 512 * 512;
   struct RItem { Raw* r; int planes; };
-  std::vector<RItem> raws = {{&m->Hf[0], 8}, {&m->Hf[1], 8}, {&m->rawG[0], 16}, {&m->rawG[1], 16},
-                             {&m->rawY[0], 8}, {&m->rawY[1], 8}, {&m->rawB, 16}};
+  std::vector<RItem> raws = {{&m->Hf[0], 8}, {&m->Hf[1], 8}, {&m->rawG[0], 8}, {&m->rawG[1], 8},
+                             {&m->rawY[0], 4}, {&m->rawY[1], 4}, {&m->rawB, 16}};   // rawG/rawY hold fp16 (uint4 = 8 ch)
   std::vector<size_t> roffs;
   for (auto& it : raws) { roffs.push_back(total); total += (size_t)it.planes * rp * 16; }
   STC_CUDA(cudaMalloc(&m->arena, total));
@@ -595,12 +597,8 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
   const int p1 = H / 2, c1 = p1 - 2, p2 = c1 / 2, c2 = p2 - 2, u2 = 2 * c2, u3 = 2 * u2;
   (void)c2;
   // ---- reset state ----
+  // (the GRU state needs no clearing: step 0 runs with h == 0 folded in -- no h K-steps, no r*h stage)
   STC_CUDA(cudaMemsetAsync(m->stats, 0, m->stats_bytes, ctx->stream));
-  for (int d = 0; d < 2; ++d) {
-    STC_CUDA(cudaMemsetAsync(m->Hf[d].base, 0, (size_t)8 * m->Hf[d].plane * 16, ctx->stream));
-    STC_CUDA(cudaMemsetAsync(m->Hh[d].base, 0, (size_t)4 * m->Hh[d].plane * 16, ctx->stream));
-    STC_CUDA(cudaMemsetAsync(m->RH[d].base, 0, (size_t)4 * m->RH[d].plane * 16, ctx->stream));
-  }
   // ---- pack input ----
   {
     PrepParams pp; memset(&pp, 0, sizeof(pp));
@@ -633,15 +631,16 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
       cp.out[d] = m->rawG[d].base;
       cp.stats[d] = m->stG + ((size_t)t * 2 + d) * m->Bc * 32;
     }
-    cp.a0_plane = m->X16.plane; cp.k0steps = 2; cp.a1_plane = m->Hh[0].plane; cp.k1steps = 2;
+    cp.a0_plane = m->X16.plane; cp.k0steps = 2; cp.a1_plane = m->Hh[0].plane; cp.k1steps = (t == 0) ? 0 : 2;
     cp.out_plane = m->rawG[0].plane; cp.N = 64; cp.G = 16; cp.mode = MODE_PLAIN;
+    cp.out_fp16 = 1;   // GRU pre-norm tensors in fp16: +2e-5 on the probability map (CPU study)
     set_valid(cp, m->Hh[0], true); cp.B = B; cp.Ptot = (int64_t)B * cp.Hp * cp.Wp;
     int rc = launch_conv(ctx, cp, 2); if (rc) return rc;
 
     GruParams gp; memset(&gp, 0, sizeof(gp));
     for (int d = 0; d < 2; ++d) {
       std::string pre = std::string("gru.") + dn[d] + ".";
-      gp.rawG[d] = m->rawG[d].base; gp.rawY[d] = m->rawY[d].base; gp.Hf[d] = m->Hf[d].base;
+      gp.rawG[d] = (const uint4*)m->rawG[d].base; gp.rawY[d] = (const uint4*)m->rawY[d].base; gp.Hf[d] = m->Hf[d].base;
       gp.Hh[d] = m->Hh[d].at(0); gp.RH[d] = m->RH[d].at(0);
       gp.cc[d] = (t == steps - 1) ? m->CCin.at(4 * d) : nullptr;
       gp.stG[d] = m->stG + ((size_t)t * 2 + d) * m->Bc * 32;
@@ -653,9 +652,12 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
     gp.rawG_plane = m->rawG[0].plane; gp.rawY_plane = m->rawY[0].plane; gp.Hf_plane = m->Hf[0].plane;
     gp.act_plane = m->Hh[0].plane; gp.cc_plane = m->CCin.plane;
     gp.B = B; gp.H = H; gp.W = H; gp.Hp = H + 2; gp.Wp = H + 2; gp.count = (float)H * (float)H * 4.f;
+    gp.h_zero = (t == 0);
     dim3 ggrid(cdiv((int64_t)H * H, 256), B, 2);
-    gru_apply1_kernel<<<ggrid, 256, 0, ctx->stream>>>(gp);
-    STC_CUDA(cudaGetLastError()); ctx->launches++;
+    if (t > 0) {
+      gru_apply1_kernel<<<ggrid, 256, 0, ctx->stream>>>(gp);
+      STC_CUDA(cudaGetLastError()); ctx->launches++;
+    }
 
     for (int d = 0; d < 2; ++d) {
       cp.a1[d] = m->RH[d].at(0);
