@@ -124,12 +124,13 @@ int stc_superresolve_host(stc_ctx* ctx, const float* x_host, const float* biline
 /* ---- Gaussian overlap-blend mosaic, load_mosaic_predictions depth == 1
  *      (src/download_and_predict_job.py:1515-1641).  preds [n,S,S]: subtile predictions as
  *      saved (probabilities 0..1, 255 = no data), in the reference's layer order; xs/ys [n]
- *      canvas offsets; placed [n] = 0 for all-255 subtiles (:1573).  Step 1 returns the
- *      calc_overlap disagreement ratios (:1503-1512); the host forms the capped multipliers
- *      median(r)/r (:1603-1606); step 2 blends with fspecial_gauss weights (gauss [S,S] float32),
+ *      canvas offsets; placed [n] = 0 for all-255 subtiles (:1573).  Step 1 returns, per
+ *      subtile, the calc_overlap map |nanmean(others) - self| [n,S,S] (:1503-1512, NaN where
+ *      nothing overlaps); the host takes its nanmean and forms the capped multipliers
+ *      median(r)/r (:1603-1606) with NumPy; step 2 blends with fspecial_gauss weights (gauss [S,S] float32),
  *      applies the uint8 / no-data rules and the 10x 3x3 dilation of 255 (:1609-1640). ---- */
-int stc_mosaic_ratios_host(stc_ctx* ctx, const float* preds_host, const int32_t* xs, const int32_t* ys,
-                           const int32_t* placed, int n, int S, float* ratios_host);
+int stc_mosaic_diffs_host(stc_ctx* ctx, const float* preds_host, const int32_t* xs, const int32_t* ys,
+                          const int32_t* placed, int n, int S, float* diffs_host);
 int stc_gauss_mosaic_host(stc_ctx* ctx, const float* preds_host, const int32_t* xs, const int32_t* ys,
                           const int32_t* placed, const float* gauss_host, const float* mult_host,
                           int n, int S, int out_h, int out_w, uint8_t* out_host);

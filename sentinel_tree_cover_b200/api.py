@@ -70,7 +70,7 @@ SYMBOLS = [
     ("stc_indices_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     ("stc_temporal_median_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     ("stc_superresolve_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    ("stc_mosaic_ratios_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_mosaic_diffs_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("stc_gauss_mosaic_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_feather_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -334,9 +334,14 @@ class StcSession:
         gauss = np.ascontiguousarray(fspecial_gauss(S, sigma), np.float32)
         mult = np.ones(n, np.float32)
         if placed.all():                                     # an unplaced subtile makes calc_overlap raise -> no reweighting (:1597-1608)
-            ratios = np.empty(n, np.float32)
-            self._check(self.lib.stc_mosaic_ratios_host(self.h, _dptr(P), _dptr(xs), _dptr(ys), _dptr(placed), n, S, _dptr(ratios)))
-            with np.errstate(all="ignore"):
+            diffs = np.empty((n, S, S), np.float32)
+            self._check(self.lib.stc_mosaic_diffs_host(self.h, _dptr(P), _dptr(xs), _dptr(ys), _dptr(placed), n, S, _dptr(diffs)))
+            import warnings
+            with np.errstate(all="ignore"), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ratios = np.zeros(n, np.float32)
+                for i in range(n):
+                    ratios[i] = np.nanmean(diffs[i])          # NumPy's own pairwise float32 reduction (:1512)
                 mult = (np.median(ratios) / ratios).astype(np.float32)
                 mult[mult > 1.5] = 1.5
         out = np.empty(out_shape, np.uint8)

@@ -34,6 +34,13 @@ void stc_destroy(stc_ctx* ctx) {
   sr_destroy(ctx);
   for (auto& e : ctx->conv_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
+    if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
+    if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+  }
+  if (ctx->stage_out) cudaFree(ctx->stage_out);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -152,20 +159,42 @@ static int predict_patches_core(stc_ctx* ctx, const float* monthly, bool host_in
   int chunk = env ? atoi(env) : 32;
   if (chunk < 1) chunk = 1;
   int Bc = B < chunk ? B : chunk;
-  DevBuf din[2], dout;
-  if (host_in) { STC_CUDA(cudaMalloc(&din[0].p, Bc * per_in * 4)); STC_CUDA(cudaMalloc(&din[1].p, Bc * per_in * 4)); }
-  if (host_out) STC_CUDA(cudaMalloc(&dout.p, (size_t)B * per_out * 4));
-  float* o_dev = host_out ? (float*)dout.p : out;
+  if (!ctx->copy_stream) {
+    STC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+      STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  if (host_in && ctx->stage_in_bytes < Bc * per_in * 4) {
+    STC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 2; ++i) { if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]); ctx->stage_in[i] = nullptr; }
+    ctx->stage_in_bytes = Bc * per_in * 4;
+    for (int i = 0; i < 2; ++i) STC_CUDA(cudaMalloc(&ctx->stage_in[i], ctx->stage_in_bytes));
+  }
+  if (host_out && ctx->stage_out_bytes < (size_t)B * per_out * 4) {
+    STC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stage_out) cudaFree(ctx->stage_out);
+    ctx->stage_out_bytes = (size_t)B * per_out * 4;
+    STC_CUDA(cudaMalloc(&ctx->stage_out, ctx->stage_out_bytes));
+  }
+  float* o_dev = host_out ? (float*)ctx->stage_out : out;
   int k = 0;
   for (int b0 = 0; b0 < B; b0 += Bc, ++k) {
     int nb = (B - b0) < Bc ? (B - b0) : Bc;
     const float* src = monthly + (size_t)b0 * per_in;
+    const int sl = k & 1;
     if (host_in) {
-      STC_CUDA(cudaMemcpyAsync(din[k & 1].p, src, nb * per_in * 4, cudaMemcpyHostToDevice, ctx->stream));
-      src = (const float*)din[k & 1].p;
+      // copy stream: wait until the compute that last read this staging buffer is done, then copy
+      if (k >= 2) STC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[sl], 0));
+      STC_CUDA(cudaMemcpyAsync(ctx->stage_in[sl], src, nb * per_in * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+      STC_CUDA(cudaEventRecord(ctx->ev_ready[sl], ctx->copy_stream));
+      STC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[sl], 0));
+      src = (const float*)ctx->stage_in[sl];
     }
     int rc = model_predict_patches_dev(ctx, src, nb, H, W, min17, max17, o_dev + (size_t)b0 * per_out);
     if (rc) return rc;
+    if (host_in) STC_CUDA(cudaEventRecord(ctx->ev_free[sl], ctx->stream));
   }
   if (host_out) STC_CUDA(cudaMemcpyAsync(out, o_dev, (size_t)B * per_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -255,17 +284,18 @@ static int mosaic_upload(stc_ctx* ctx, const float* preds, const int32_t* xs, co
   return STC_OK;
 }
 
-int stc_mosaic_ratios_host(stc_ctx* ctx, const float* preds_host, const int32_t* xs, const int32_t* ys, const int32_t* placed,
-                           int n, int S, float* ratios_host) {
+int stc_mosaic_diffs_host(stc_ctx* ctx, const float* preds_host, const int32_t* xs, const int32_t* ys, const int32_t* placed,
+                          int n, int S, float* diffs_host) {
   CTX_CHECK();
-  if (!preds_host || !xs || !ys || !placed || !ratios_host || n < 1 || S < 1) STC_FAIL(STC_ERR_ARG, "mosaic_ratios: bad argument");
+  if (!preds_host || !xs || !ys || !placed || !diffs_host || n < 1 || n > 64 || S < 1) STC_FAIL(STC_ERR_ARG, "mosaic_diffs: bad argument");
   DevBuf dp, dx, dy, dpl, dr;
   int rc = mosaic_upload(ctx, preds_host, xs, ys, placed, n, S, dp, dx, dy, dpl); if (rc) return rc;
-  STC_CUDA(cudaMalloc(&dr.p, n * 4));
+  size_t bytes = (size_t)n * S * S * 4;
+  STC_CUDA(cudaMalloc(&dr.p, bytes));
   rc = pre_gauss_mosaic_dev(ctx, (const float*)dp.p, (const int*)dx.p, (const int*)dy.p, (const int*)dpl.p, nullptr, nullptr,
                             (float*)dr.p, 0, n, S, 0, 0, nullptr, nullptr);
   if (rc) return rc;
-  STC_CUDA(cudaMemcpyAsync(ratios_host, dr.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(diffs_host, dr.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
   return STC_OK;
 }

@@ -65,6 +65,11 @@ struct stc_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
   size_t conv_events_used = 0;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
+  // host-buffer tile path: H2D copies run on their own stream, double-buffered against compute
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  void* stage_in[2] = {nullptr, nullptr}; size_t stage_in_bytes = 0;
+  void* stage_out = nullptr; size_t stage_out_bytes = 0;
   void* model = nullptr;      // ModelState*
   void* sr = nullptr;         // SuperresState*
 };
@@ -101,7 +106,7 @@ int pre_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_ho
 int pre_indices_dev(stc_ctx* ctx, const float* in_dev, int64_t npix, int C, float* out_dev);
 int pre_temporal_median_dev(stc_ctx* ctx, const float* in_dev, int n, int64_t inner, float* out_dev);
 int pre_gauss_mosaic_dev(stc_ctx* ctx, const float* preds_dev, const int* xs_dev, const int* ys_dev, const int* placed_dev,
-                         const float* gauss_dev, float* mult_dev, float* ratios_dev, int stage,
+                         const float* gauss_dev, float* mult_dev, float* diffs_dev, int stage,
                          int n, int S, int Hc, int Wc, unsigned char* tmp_dev, unsigned char* out_dev);
 int pre_feather_dev(stc_ctx* ctx, const float* mask_dev, int n, int H, int W, int size, float* tmp_a, float* tmp_b,
                     float* sums_dev, float* out_dev);

@@ -21,6 +21,8 @@
 // small device helpers
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+// epilogue variant: ex2.approx + rcp.approx (relative error ~1e-6, far below the fp16 operand rounding)
+__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 
 __device__ __forceinline__ void pixel_coords(int64_t P, int Hp, int Wp, int& b, int& yp, int& xp) {
   int hw = Hp * Wp;
@@ -210,6 +212,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) break;
+    __nanosleep(32);                       // do not steal issue slots from the epilogue warps
     if (clock64() - t0 > 4000000000LL) {  // ~2 s: never hang the box, trap instead
       printf("stc: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
@@ -268,13 +271,22 @@ __device__ __forceinline__ uint4 pack8h(const float* v) {
   return r;
 }
 
-// G = GroupNorm groups whose (sum, sumsq) the epilogue accumulates (0 = no statistics).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Template parameters: N output channels, NT accumulators (128-pixel sub-tiles) per super-tile,
+// G GroupNorm groups whose (sum, sumsq) the epilogue accumulates (0 = none), MODE the fused
+// epilogue.  320 threads: warp 0 bulk-copy producer, warp 1 TMEM allocator + MMA issuer,
+// warps 2-9 epilogue (TMEM lane quarter = warp%4, column half = (warp-2)/4).
 // Statistics live in per-lane registers across the CTA's contiguous run of tiles and are
-// flushed (warp shuffle reduction + one fp64 atomic per value) only when the sample changes:
-// a few hundred atomics per launch instead of one per warp-row (the first version spent
-// >90% of the kernel serialised on same-address L2 reductions; profiles/r01_*).
-template <int N, int NT, int G>
-__global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int tiles_per_dir, int total_tiles, int tiles_per_cta) {
+// flushed (shuffle reduction + fp64 atomics) only when the sample changes.
+template <int N, int NT, int G, int MODE>
+__global__ void __launch_bounds__(320, 1) conv3x3_umma_kernel(ConvParams p, int tiles_per_dir, int total_tiles, int tiles_per_cta) {
   using C = UmmaCfg<N, NT>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -363,25 +375,29 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    constexpr int GA = (G > 0) ? G : 1;
-    constexpr int GS = N / GA;            // channels per group
-    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    constexpr bool SPLIT = (N >= 32);             // two warps share a lane quarter, each takes half the columns
+    constexpr int NH = SPLIT ? N / 2 : N;         // columns handled by a working warp
+    constexpr int GA = (G > 0) ? G / 2 : 1;       // groups inside this warp's column half
+    constexpr int GS = (G > 0) ? N / G : N;       // channels per group
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // 0: columns [0,N/2), 1: [N/2,N)
+    const int cbase = SPLIT ? half * NH : 0;
+    const bool working = SPLIT || half == 0;
     const int row = q * 32 + lane;
+    const int hw = p.Hp * p.Wp;
     float acc_s[GA], acc_ss[GA];
 #pragma unroll
     for (int g = 0; g < GA; ++g) { acc_s[g] = 0.f; acc_ss[g] = 0.f; }
     int cur_b = -1, cur_dir = 0;
-    auto flush_warp = [&]() {   // warp-uniform: reduce over lanes, lanes 0..2G-1 each add one value
+    auto flush_warp = [&]() {
       if (G == 0 || cur_b < 0) return;
+      double* st = p.stats[cur_dir] + ((int64_t)cur_b * G + half * GA) * 2;
 #pragma unroll
       for (int g = 0; g < GA; ++g) {
         float s = acc_s[g], ss = acc_ss[g];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-        if (lane == 0) {
-          atomicAdd(&p.stats[cur_dir][((int64_t)cur_b * GA + g) * 2 + 0], (double)s);
-          atomicAdd(&p.stats[cur_dir][((int64_t)cur_b * GA + g) * 2 + 1], (double)ss);
-        }
+        if (lane == 0) { atomicAdd(st + 2 * g, (double)s); atomicAdd(st + 2 * g + 1, (double)ss); }
         acc_s[g] = 0.f; acc_ss[g] = 0.f;
       }
     };
@@ -389,20 +405,22 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
     for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const int as = it & 1;
       const int dir = tile / tiles_per_dir;
-      const int64_t p0 = (int64_t)(tile - dir * tiles_per_dir) * (NT * 128);
+      const int p0 = (tile - dir * tiles_per_dir) * (NT * 128);
+      const bool has_stats = (G > 0) && (p.stats[dir] != nullptr);
+      float* const outp = reinterpret_cast<float*>(p.out[dir]);
       mbar_wait(TFULL(as), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < NT; ++j) {
-        const int64_t P = p0 + j * 128 + row;
-        const bool inb = P < p.Ptot;
-        int b, yp, xp;
-        pixel_coords(inb ? P : 0, p.Hp, p.Wp, b, yp, xp);
+      for (int j = 0; j < (working ? NT : 0); ++j) {
+        const int P = p0 + j * 128 + row;
+        const bool inb = P < (int)p.Ptot;
+        const int Pc = inb ? P : 0;
+        const int b = Pc / hw;
+        const int rem = Pc - b * hw;
+        const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
         const bool valid = inb && (yp >= p.vy0 && yp < p.vy1 && xp >= p.vx0 && xp < p.vx1);
-        const float sc = (p.mode == MODE_PSCALE_SWISH) ? pscale(p, yp, xp) : 1.f;
-        const float vm = valid ? 1.f : 0.f;
         bool per_lane_flush = false;
-        if (G > 0 && p.stats[dir]) {
+        if (has_stats) {
           const unsigned mk = __ballot_sync(0xffffffffu, inb);
           if (mk) {
             const int bw = __shfl_sync(0xffffffffu, b, __ffs(mk) - 1);
@@ -415,61 +433,60 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
           }
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::ACC_COLS + j * N);
-        float sse = 1.f;
-        if (p.mode == MODE_CAND) {
+        float scale = 1.f;
+        if (MODE == MODE_PSCALE_SWISH) scale = pscale(p, yp, xp);
+        if (MODE == MODE_CAND) {           // 1x1 squeeze over all N channels of the pixel (pb:candidate/convolution_1)
           float d = 0.f;
 #pragma unroll
           for (int c0 = 0; c0 < N; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + c0, v);
+            uint32_t r[16];
+            tmem_ld16_nowait(taddr + c0, r);
+            tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) d += v[i] * __ldg(&p.sse_w[dir][c0 + i]);
+            for (int i = 0; i < 16; ++i) d = fmaf(__uint_as_float(r[i]), __ldg(&p.sse_w[dir][c0 + i]), d);
           }
-          sse = sigmoidf_(d);
+          scale = fast_sigmoid(d);
         }
 #pragma unroll
-        for (int c0 = 0; c0 < N; c0 += 16) {
+        for (int c0 = 0; c0 < NH; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16_nowait(taddr + cbase + c0, r);
+          tmem_wait_ld();
           float v[16];
-          tmem_ld16(taddr + c0, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float x = v[i];
-            if (p.mode == MODE_PSCALE_SWISH) { x *= sc; x = x * sigmoidf_(x); }
-            else if (p.mode == MODE_SWISH) { x = x * sigmoidf_(x); }
-            else if (p.mode == MODE_CAND) { x *= sse; }
-            else if (p.mode == MODE_BIAS) { x += __ldg(&p.bias[c0 + i]); }
-            else if (p.mode == MODE_BIAS_RELU) { x = fmaxf(x + __ldg(&p.bias[c0 + i]), 0.f); }
+            float x = __uint_as_float(r[i]);
+            if (MODE == MODE_PSCALE_SWISH) { x *= scale; x = x * fast_sigmoid(x); }
+            else if (MODE == MODE_SWISH) { x = x * fast_sigmoid(x); }
+            else if (MODE == MODE_CAND) { x *= scale; }
+            else if (MODE == MODE_BIAS) { x += __ldg(&p.bias[cbase + c0 + i]); }
+            else if (MODE == MODE_BIAS_RELU) { x = fmaxf(x + __ldg(&p.bias[cbase + c0 + i]), 0.f); }
             v[i] = x;
             if (G > 0) {
-              const float xm = x * vm;
+              const float xm = valid ? x : 0.f;
               acc_s[(c0 + i) / GS] += xm;
-              acc_ss[(c0 + i) / GS] += xm * xm;
+              acc_ss[(c0 + i) / GS] = fmaf(xm, xm, acc_ss[(c0 + i) / GS]);
             }
           }
           if (inb) {
             if (p.out_fp16) {
-              uint4* o = reinterpret_cast<uint4*>(p.out[dir]);
-              o[(int64_t)((c0 >> 3) + 0) * p.out_plane + P] = pack8h(v);
-              o[(int64_t)((c0 >> 3) + 1) * p.out_plane + P] = pack8h(v + 8);
+              uint4* o = reinterpret_cast<uint4*>(outp) + (int64_t)((cbase + c0) >> 3) * p.out_plane + P;
+              o[0] = pack8h(v);
+              o[p.out_plane] = pack8h(v + 8);
             } else {
+              float4* o = reinterpret_cast<float4*>(outp) + (int64_t)((cbase + c0) >> 2) * p.out_plane + P;
 #pragma unroll
-              for (int qd = 0; qd < 4; ++qd)
-                p.out[dir][(int64_t)((c0 >> 2) + qd) * p.out_plane + P] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+              for (int qd = 0; qd < 4; ++qd) o[(int64_t)qd * p.out_plane] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
             }
           }
         }
         if (G > 0 && per_lane_flush) {
+          double* st = p.stats[dir] + ((int64_t)b * G + half * GA) * 2;
 #pragma unroll
           for (int g = 0; g < GA; ++g) {
-            if (valid) {
-              atomicAdd(&p.stats[dir][((int64_t)b * GA + g) * 2 + 0], (double)acc_s[g]);
-              atomicAdd(&p.stats[dir][((int64_t)b * GA + g) * 2 + 1], (double)acc_ss[g]);
-            }
+            if (valid) { atomicAdd(st + 2 * g, (double)acc_s[g]); atomicAdd(st + 2 * g + 1, (double)acc_ss[g]); }
             acc_s[g] = 0.f; acc_ss[g] = 0.f;
           }
-        } else if (G > 0 && !p.stats[dir]) {
-#pragma unroll
-          for (int g = 0; g < GA; ++g) { acc_s[g] = 0.f; acc_ss[g] = 0.f; }
         }
       }
       tc_fence_before();
@@ -489,21 +506,22 @@ __global__ void __launch_bounds__(192, 1) conv3x3_umma_kernel(ConvParams p, int 
 // --------------------------------------------------------------------------------------
 // host launchers
 // --------------------------------------------------------------------------------------
-template <int N, int NT, int G>
+template <int N, int NT, int G, int MODE>
 static int launch_umma(stc_ctx* ctx, const ConvParams& p, int ndir) {
   using C = UmmaCfg<N, NT>;
   static bool configured = false;
-  auto kern = conv3x3_umma_kernel<N, NT, G>;
+  auto kern = conv3x3_umma_kernel<N, NT, G, MODE>;
   if (!configured) {
     STC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
+  if (p.Ptot >= (1ll << 31) - 1024) STC_FAIL(STC_ERR_ARG, "conv: pixel space exceeds 2^31");
   int tiles_per_dir = cdiv(p.Ptot, NT * 128);
   int total = tiles_per_dir * ndir;
   int grid = total < ctx->num_sms ? total : ctx->num_sms;
   int tiles_per_cta = cdiv(total, grid);
   grid = cdiv(total, tiles_per_cta);
-  kern<<<grid, 192, C::SMEM_BYTES, ctx->stream>>>(p, tiles_per_dir, total, tiles_per_cta);
+  kern<<<grid, 320, C::SMEM_BYTES, ctx->stream>>>(p, tiles_per_dir, total, tiles_per_cta);
   STC_CUDA(cudaGetLastError());
   return STC_OK;
 }
@@ -545,16 +563,20 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p, int ndir) {
   if (ctx->conv_impl == 1) {
     rc = launch_simt(ctx, p, ndir);
   } else {
-    const int key = p.N * 100 + (p.stats[0] ? p.G : 0);
+    const int g = p.stats[0] ? p.G : 0;
+    const int key = (p.N * 100 + g) * 10 + p.mode;
     switch (key) {
-      case 1600: rc = launch_umma<16, 4, 0>(ctx, p, ndir); break;
-      case 3200: rc = launch_umma<32, 4, 0>(ctx, p, ndir); break;
-      case 3208: rc = launch_umma<32, 4, 8>(ctx, p, ndir); break;
-      case 6408: rc = launch_umma<64, 4, 8>(ctx, p, ndir); break;
-      case 6416: rc = launch_umma<64, 4, 16>(ctx, p, ndir); break;
-      case 12808: rc = launch_umma<128, 2, 8>(ctx, p, ndir); break;
-      case 25608: rc = launch_umma<256, 1, 8>(ctx, p, ndir); break;
-      default: STC_FAIL(STC_ERR_ARG, "conv: unsupported (N, groups) combination");
+      case (6400 + 16) * 10 + MODE_PLAIN:        rc = launch_umma<64, 4, 16, MODE_PLAIN>(ctx, p, ndir); break;        // GRU gates
+      case (3200 + 8) * 10 + MODE_CAND:          rc = launch_umma<32, 4, 8, MODE_CAND>(ctx, p, ndir); break;          // GRU candidate
+      case (6400 + 8) * 10 + MODE_PSCALE_SWISH:  rc = launch_umma<64, 4, 8, MODE_PSCALE_SWISH>(ctx, p, ndir); break;  // conv_median, conv_concat, up3
+      case (6400 + 8) * 10 + MODE_SWISH:         rc = launch_umma<64, 4, 8, MODE_SWISH>(ctx, p, ndir); break;         // out
+      case (12800 + 8) * 10 + MODE_PSCALE_SWISH: rc = launch_umma<128, 2, 8, MODE_PSCALE_SWISH>(ctx, p, ndir); break; // up2, up2_out
+      case (12800 + 8) * 10 + MODE_SWISH:        rc = launch_umma<128, 2, 8, MODE_SWISH>(ctx, p, ndir); break;        // conv1
+      case (25600 + 8) * 10 + MODE_SWISH:        rc = launch_umma<256, 1, 8, MODE_SWISH>(ctx, p, ndir); break;        // conv2
+      case (3200 + 0) * 10 + MODE_BIAS_RELU:     rc = launch_umma<32, 4, 0, MODE_BIAS_RELU>(ctx, p, ndir); break;     // DSen2
+      case (3200 + 0) * 10 + MODE_BIAS:          rc = launch_umma<32, 4, 0, MODE_BIAS>(ctx, p, ndir); break;
+      case (1600 + 0) * 10 + MODE_BIAS:          rc = launch_umma<16, 4, 0, MODE_BIAS>(ctx, p, ndir); break;
+      default: STC_FAIL(STC_ERR_ARG, "conv: unsupported (N, groups, mode) combination");
     }
   }
   if (rc != STC_OK) return rc;

@@ -43,33 +43,40 @@ __device__ __forceinline__ float np_sum(const float* a, int n) {
   return res;
 }
 
-// one block per layer: ratio_i = nanmean_px | nanmean_{j != i}(v_j) - v_i |   (calc_overlap)
-__global__ void __launch_bounds__(256) mosaic_ratio_kernel(MosaicParams p, float* ratios) {
+// one block per layer i: diff[i][a][b] = | nanmean_{j != i}(v_j) - v_i | over layer i's footprint
+// (calc_overlap :1503-1512 without the final nanmean, which the host takes with NumPy so the
+// float32 pairwise summation order is NumPy's own).  The mean over the other layers follows
+// np.nanmean(axis=-1) on the compacted layer axis: layer i deleted, layers that never touch the
+// footprint deleted (:1508-1509), NaN -> 0, NumPy add.reduce order, divided by the non-NaN count.
+__global__ void __launch_bounds__(256) mosaic_ratio_kernel(MosaicParams p, float* diffs) {
   const int i = blockIdx.x;
-  __shared__ double ssum[256]; __shared__ int scnt[256];
-  double acc = 0.0; int cnt = 0;
-  if (p.placed[i]) {
-    for (int idx = threadIdx.x; idx < p.S * p.S; idx += blockDim.x) {
+  __shared__ int keep[64]; __shared__ int L;
+  if (threadIdx.x == 0) {
+    int l = 0;
+    for (int j = 0; j < p.n; ++j) {
+      if (j == i || !p.placed[j]) continue;
+      int dx = p.xs[j] - p.xs[i], dy = p.ys[j] - p.ys[i];
+      if (dx > -p.S && dx < p.S && dy > -p.S && dy < p.S) keep[l++] = j;
+    }
+    L = l;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < p.S * p.S; idx += blockDim.x) {
+    float out = nanf("");
+    if (p.placed[i]) {
       int px = idx / p.S, py = idx - px * p.S;
       int X = p.xs[i] + px, Y = p.ys[i] + py;
       float vi; int a, b;
       layer_value(p, i, X, Y, vi, a, b);
-      float s = 0.f; int m = 0;
-      for (int j = 0; j < p.n; ++j) {
-        if (j == i) continue;
+      float vals[64]; int m = 0;
+      for (int l = 0; l < L; ++l) {
         float vj;
-        if (layer_value(p, j, X, Y, vj, a, b)) { s = __fadd_rn(s, vj); ++m; }
+        if (layer_value(p, keep[l], X, Y, vj, a, b)) { vals[l] = vj; ++m; } else vals[l] = 0.f;
       }
-      if (m > 0) { acc += (double)fabsf(__fsub_rn(__fdiv_rn(s, (float)m), vi)); ++cnt; }
+      if (m > 0) out = fabsf(__fsub_rn(__fdiv_rn(np_sum(vals, L), (float)m), vi));
     }
+    diffs[(int64_t)i * p.S * p.S + idx] = out;
   }
-  ssum[threadIdx.x] = acc; scnt[threadIdx.x] = cnt;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) ratios[i] = scnt[0] > 0 ? (float)(ssum[0] / scnt[0]) : nanf("");
 }
 
 // per canvas pixel: normalised Gaussian weights, weighted nansum, uint8 rules (:1609-1626)
@@ -117,12 +124,12 @@ __global__ void __launch_bounds__(256) mosaic_dilate_kernel(const unsigned char*
 }
 
 int pre_gauss_mosaic_dev(stc_ctx* ctx, const float* preds_dev, const int* xs_dev, const int* ys_dev, const int* placed_dev,
-                         const float* gauss_dev, float* mult_dev, float* ratios_dev, int stage,
+                         const float* gauss_dev, float* mult_dev, float* diffs_dev, int stage,
                          int n, int S, int Hc, int Wc, unsigned char* tmp_dev, unsigned char* out_dev) {
   if (n < 1 || n > 64) STC_FAIL(STC_ERR_ARG, "mosaic: 1..64 subtiles supported");
   MosaicParams p{preds_dev, xs_dev, ys_dev, placed_dev, gauss_dev, mult_dev, n, S, Hc, Wc};
   if (stage == 0) {
-    mosaic_ratio_kernel<<<n, 256, 0, ctx->stream>>>(p, ratios_dev);
+    mosaic_ratio_kernel<<<n, 256, 0, ctx->stream>>>(p, diffs_dev);
     STC_CUDA(cudaGetLastError()); ctx->launches++;
   } else {
     mosaic_blend_kernel<<<cdiv((int64_t)Hc * Wc, 128), 128, 0, ctx->stream>>>(p, tmp_dev);
