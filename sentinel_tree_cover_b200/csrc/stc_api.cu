@@ -179,22 +179,40 @@ static int predict_patches_core(stc_ctx* ctx, const float* monthly, bool host_in
     STC_CUDA(cudaMalloc(&ctx->stage_out, ctx->stage_out_bytes));
   }
   float* o_dev = host_out ? (float*)ctx->stage_out : out;
+  // Sub-batch k: H2D on the copy stream into staging buffer k&1, compute on scratch slot k&1
+  // (own stream), so copy(k+1), conv(k) and the elementwise stages of k-1/k overlap.
+  const bool dual = (B > Bc) && !getenv("STC_SINGLE_STREAM");
+  if (dual && !ctx->stream2) STC_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  if (!ctx->ev_fork) {
+    STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  if (dual) {
+    STC_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    STC_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  }
   int k = 0;
   for (int b0 = 0; b0 < B; b0 += Bc, ++k) {
     int nb = (B - b0) < Bc ? (B - b0) : Bc;
     const float* src = monthly + (size_t)b0 * per_in;
     const int sl = k & 1;
+    const int slot = dual ? sl : 0;
+    cudaStream_t cs = slot ? ctx->stream2 : ctx->stream;
     if (host_in) {
       // copy stream: wait until the compute that last read this staging buffer is done, then copy
       if (k >= 2) STC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[sl], 0));
       STC_CUDA(cudaMemcpyAsync(ctx->stage_in[sl], src, nb * per_in * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
       STC_CUDA(cudaEventRecord(ctx->ev_ready[sl], ctx->copy_stream));
-      STC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[sl], 0));
+      STC_CUDA(cudaStreamWaitEvent(cs, ctx->ev_ready[sl], 0));
       src = (const float*)ctx->stage_in[sl];
     }
-    int rc = model_predict_patches_dev(ctx, src, nb, H, W, min17, max17, o_dev + (size_t)b0 * per_out);
+    int rc = model_forward_slot(ctx, slot, src, nb, Bc, H, min17, max17, o_dev + (size_t)b0 * per_out);
     if (rc) return rc;
-    if (host_in) STC_CUDA(cudaEventRecord(ctx->ev_free[sl], ctx->stream));
+    if (host_in) STC_CUDA(cudaEventRecord(ctx->ev_free[sl], cs));
+  }
+  if (dual) {
+    STC_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    STC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   }
   if (host_out) STC_CUDA(cudaMemcpyAsync(out, o_dev, (size_t)B * per_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));

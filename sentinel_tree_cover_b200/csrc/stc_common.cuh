@@ -48,6 +48,7 @@ struct ConvParams {
   int vy0, vy1, vx0, vx1;       // valid output range in padded coordinates
   int mode;
   int out_fp16;                 // 1: write fp16 planes of uint4 (8 ch) instead of fp32 float4 planes
+  int exp_align;                // timing experiment (STC_EXP_ALIGN): see stc_conv.cu
 };
 enum { MODE_PLAIN = 0, MODE_PSCALE_SWISH = 1, MODE_SWISH = 2, MODE_CAND = 3,
        MODE_BIAS = 4, MODE_BIAS_RELU = 5 };
@@ -70,7 +71,11 @@ struct stc_ctx {
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   void* stage_in[2] = {nullptr, nullptr}; size_t stage_in_bytes = 0;
   void* stage_out = nullptr; size_t stage_out_bytes = 0;
-  void* model = nullptr;      // ModelState*
+  void* model = nullptr;      // ModelState* (slot 0)
+  void* model2 = nullptr;     // ModelState* (slot 1): second scratch arena so consecutive chunks overlap
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int last_slot = 0;
   void* sr = nullptr;         // SuperresState*
 };
 
@@ -112,3 +117,5 @@ int pre_feather_dev(stc_ctx* ctx, const float* mask_dev, int n, int H, int W, in
                     float* sums_dev, float* out_dev);
 int pre_binary_dilate_dev(stc_ctx* ctx, const unsigned char* in_dev, int n, int H, int W, int iterations, int conn,
                           unsigned char* out_dev);
+int model_forward_slot(stc_ctx* ctx, int slot, const float* monthly_dev, int nb, int Bc, int H,
+                       const double* min17, const double* max17, float* out_dev);

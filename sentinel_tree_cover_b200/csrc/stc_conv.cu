@@ -251,7 +251,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 
 template <int N, int NT>
 struct UmmaCfg {
-  static constexpr int R = NT * 128 + 2;                 // rows per staged segment
+  static constexpr int R = NT * 128 + 8;                 // rows per staged segment (multiple of 8: 128-B aligned blocks)
   static constexpr int A_BYTES = 3 * 2 * R * 16;
   static constexpr int B_BYTES = 9 * 2 * N * 16;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -362,7 +362,10 @@ __global__ void __launch_bounds__(320, 1) conv3x3_umma_kernel(ConvParams p, int 
             const uint64_t bdesc = make_desc(sb + (uint32_t)(tap * 2 * N * 16), N * 16, 128);
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-              const uint64_t adesc = make_desc(sa + (uint32_t)(((dy * 2) * C::R + j * 128 + dx) * 16), C::R * 16, 128);
+              // exp_align (STC_EXP_ALIGN=1, timing experiment only): drop the dx row shift so every
+              // A core matrix starts 128-B aligned -- results are wrong, the MMA rate is what is measured
+              const int dxe = p.exp_align ? 0 : dx;
+              const uint64_t adesc = make_desc(sa + (uint32_t)(((dy * 2) * C::R + j * 128 + dxe) * 16), C::R * 16, 128);
               tc_mma_f16(tmem_base + (uint32_t)(as * C::ACC_COLS + j * N), adesc, bdesc, IDESC, (ks > 0 || tap > 0) ? 1u : 0u);
             }
           }
@@ -544,7 +547,10 @@ static int launch_simt(stc_ctx* ctx, const ConvParams& p, int ndir) {
   return STC_OK;
 }
 
-int launch_conv(stc_ctx* ctx, const ConvParams& p, int ndir) {
+int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
+  static const int exp_align = getenv("STC_EXP_ALIGN") ? atoi(getenv("STC_EXP_ALIGN")) : 0;
+  ConvParams p = p_in;
+  p.exp_align = exp_align;
   if (p.mode == MODE_CAND && p.N != 32) STC_FAIL(STC_ERR_ARG, "conv: MODE_CAND requires N == 32");
   if (p.G > 16 || (p.G > 0 && p.N % p.G)) STC_FAIL(STC_ERR_ARG, "conv: bad group count");
   cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -437,9 +437,17 @@ static const std::vector<float>* getw(stc_ctx* ctx, const std::string& name, siz
   return &it->second;
 }
 
+static int finalize_slot(stc_ctx* ctx, void** slot);
+
 int model_finalize_weights(stc_ctx* ctx) {
-  ModelState* m = (ModelState*)ctx->model;
-  if (!m) { m = new ModelState(); ctx->model = m; }
+  int rc = finalize_slot(ctx, &ctx->model);
+  if (rc) return rc;
+  return finalize_slot(ctx, &ctx->model2);
+}
+
+static int finalize_slot(stc_ctx* ctx, void** slot) {
+  ModelState* m = (ModelState*)*slot;
+  if (!m) { m = new ModelState(); *slot = m; }
   // ---- conv kernels ----
   std::vector<int> gru_map(64, -1);     // A channels: [x 0..16 | pad | h 0..31] -> cin [0..16 | - | 17..48]
   for (int c = 0; c < 17; ++c) gru_map[c] = c;
@@ -492,19 +500,24 @@ int model_finalize_weights(stc_ctx* ctx) {
 }
 
 void model_destroy(stc_ctx* ctx) {
-  ModelState* m = (ModelState*)ctx->model;
-  if (!m) return;
-  for (int d = 0; d < 2; ++d) { cudaFree(m->w_gates[d]); cudaFree(m->w_cand[d]); }
-  for (int i = 0; i < 8; ++i) cudaFree(m->w_blk[i]);
-  cudaFree(m->fparams); cudaFree(m->arena); cudaFree(m->stats);
-  delete m; ctx->model = nullptr;
+  for (void** slot : {&ctx->model, &ctx->model2}) {
+    ModelState* m = (ModelState*)*slot;
+    if (!m) continue;
+    for (int d = 0; d < 2; ++d) { cudaFree(m->w_gates[d]); cudaFree(m->w_cand[d]); }
+    for (int i = 0; i < 8; ++i) cudaFree(m->w_blk[i]);
+    cudaFree(m->fparams); cudaFree(m->arena); cudaFree(m->stats);
+    delete m; *slot = nullptr;
+  }
+  if (ctx->stream2) { cudaStreamDestroy(ctx->stream2); ctx->stream2 = nullptr; }
+  if (ctx->ev_fork) { cudaEventDestroy(ctx->ev_fork); ctx->ev_fork = nullptr; }
+  if (ctx->ev_join) { cudaEventDestroy(ctx->ev_join); ctx->ev_join = nullptr; }
 }
 
 struct Geo { int H, Hp; int64_t P; };   // square images
 static Geo geo(int Bc, int H) { Geo g; g.H = H; g.Hp = H + 2; g.P = (int64_t)Bc * g.Hp * g.Hp; return g; }
 
 static size_t act_units(int chunks, const Geo& g, int& guard) {
-  guard = ((g.Hp + 2 + 512 + 7) / 8) * 8;
+  guard = ((g.Hp + 2 + 544 + 7) / 8) * 8;   // >= Wp + 1 + (NT*128 + 8) staged rows past the last tile
   return (size_t)chunks * (size_t)(g.P + 2 * guard);
 }
 
@@ -696,33 +709,63 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
   return STC_OK;
 }
 
-int model_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int W, int length,
-                      int normalize, const double* min17, const double* max17, float* out_dev) {
-  ModelState* m = (ModelState*)ctx->model;
-  if (!m || !m->weights_ready) STC_FAIL(STC_ERR_STATE, "predict: weights not finalized");
-  if (H != W) STC_FAIL(STC_ERR_ARG, "predict: H must equal W");
-  if (H % 4 != 0 || H < 28) STC_FAIL(STC_ERR_ARG, "predict: H must be a multiple of 4 and >= 28");
-  if (T < 1 || T > 12 || length < 1) STC_FAIL(STC_ERR_ARG, "predict: bad T/length");
-  if (normalize && (!min17 || !max17)) STC_FAIL(STC_ERR_ARG, "predict: normalize needs min/max");
+// Chunked forward over a device-resident batch.  Consecutive chunks alternate between two
+// scratch slots / streams so the HBM-bound elementwise stages of one chunk run in the shadow
+// of the tensor-bound convolutions of the other (STC_SINGLE_STREAM=1 disables this).
+static int run_chunks(stc_ctx* ctx, const float* x_dev, const float* monthly_dev, int B, int T, int H, int length,
+                      int normalize, const double* mn, const double* mx, float* out_dev) {
+  ModelState* ms[2] = {(ModelState*)ctx->model, (ModelState*)ctx->model2};
+  if (!ms[0] || !ms[0]->weights_ready || !ms[1] || !ms[1]->weights_ready) STC_FAIL(STC_ERR_STATE, "predict: weights not finalized");
   if (B <= 0) return STC_OK;
   const char* env = getenv("STC_CHUNK");
   int chunk = env ? atoi(env) : 32;
   if (chunk < 1) chunk = 1;
-  int Bc = B < chunk ? B : chunk;
-  int rc = ensure_plan(ctx, m, Bc, H, T + 1); if (rc) return rc;
+  const int Bc = B < chunk ? B : chunk;
+  const int nchunks = (B + Bc - 1) / Bc;
+  const bool dual = nchunks > 1 && !getenv("STC_SINGLE_STREAM");
+  cudaStream_t main_stream = ctx->stream;
+  if (dual) {
+    if (!ctx->stream2) STC_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    if (!ctx->ev_fork) {
+      STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    STC_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
+    STC_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  }
   const int Ho = H - 14;
-  for (int b0 = 0; b0 < B; b0 += Bc) {
-    int nb = (B - b0) < Bc ? (B - b0) : Bc;
-    rc = forward_chunk(ctx, m, x_dev + (size_t)b0 * (T + 1) * H * W * 17, nullptr, nb, T, H, length, normalize, min17, max17,
-                       out_dev + (size_t)b0 * Ho * Ho);
-    if (rc) return rc;
-    m->lastB = nb;
+  const size_t per_in = monthly_dev ? (size_t)12 * H * H * 13 : (size_t)(T + 1) * H * H * 17;
+  int rc = STC_OK, k = 0;
+  for (int b0 = 0; b0 < B && !rc; b0 += Bc, ++k) {
+    const int nb = (B - b0) < Bc ? (B - b0) : Bc;
+    const int slot = dual ? (k & 1) : 0;
+    ctx->stream = slot ? ctx->stream2 : main_stream;
+    rc = ensure_plan(ctx, ms[slot], Bc, H, T + 1);
+    if (!rc) rc = forward_chunk(ctx, ms[slot], x_dev ? x_dev + b0 * per_in : nullptr, monthly_dev ? monthly_dev + b0 * per_in : nullptr,
+                                nb, T, H, length, normalize, mn, mx, out_dev + (size_t)b0 * Ho * Ho);
+    ms[slot]->lastB = nb; ctx->last_slot = slot;
+  }
+  ctx->stream = main_stream;
+  if (rc) return rc;
+  if (dual) {
+    STC_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    STC_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
   }
   return STC_OK;
 }
 
+int model_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int W, int length,
+                      int normalize, const double* min17, const double* max17, float* out_dev) {
+  if (H != W) STC_FAIL(STC_ERR_ARG, "predict: H must equal W");
+  if (H % 4 != 0 || H < 28) STC_FAIL(STC_ERR_ARG, "predict: H must be a multiple of 4 and >= 28");
+  if (T < 1 || T > 12 || length < 1) STC_FAIL(STC_ERR_ARG, "predict: bad T/length");
+  if (normalize && (!min17 || !max17)) STC_FAIL(STC_ERR_ARG, "predict: normalize needs min/max");
+  return run_chunks(ctx, x_dev, nullptr, B, T, H, length, normalize, min17, max17, out_dev);
+}
+
 int64_t model_debug_read(stc_ctx* ctx, const char* name, float* out_host) {
-  ModelState* m = (ModelState*)ctx->model;
+  ModelState* m = (ModelState*)(ctx->last_slot ? ctx->model2 : ctx->model);
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   if (!m || !m->arena) { ctx->err = "debug_read: no forward pass yet"; return STC_ERR_STATE; }
   std::map<std::string, Act*> tab = {{"ccin", &m->CCin}, {"cat2", &m->CAT2}, {"p1", &m->P1}, {"cat1", &m->CAT1},
                                      {"p2", &m->P2}, {"u2in", &m->U2in}, {"u3in", &m->U3in}, {"hh_fw", &m->Hh[0]},
@@ -747,23 +790,25 @@ int64_t model_debug_read(stc_ctx* ctx, const char* name, float* out_host) {
 // Fused tile path: monthly [B,12,H,W,13] (device) -> probabilities [B,H-14,W-14] (device).
 int model_predict_patches_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W,
                               const double* min17, const double* max17, float* out_dev) {
-  ModelState* m = (ModelState*)ctx->model;
-  if (!m || !m->weights_ready) STC_FAIL(STC_ERR_STATE, "predict_patches: weights not finalized");
   if (H != W || H % 4 != 0 || H < 28) STC_FAIL(STC_ERR_ARG, "predict_patches: H must equal W, be a multiple of 4 and >= 28");
   if (!min17 || !max17) STC_FAIL(STC_ERR_ARG, "predict_patches: min/max required");
-  if (B <= 0) return STC_OK;
-  const char* env = getenv("STC_CHUNK");
-  int chunk = env ? atoi(env) : 32;
-  if (chunk < 1) chunk = 1;
-  int Bc = B < chunk ? B : chunk;
-  int rc = ensure_plan(ctx, m, Bc, H, 5); if (rc) return rc;
-  const int Ho = H - 14;
-  for (int b0 = 0; b0 < B; b0 += Bc) {
-    int nb = (B - b0) < Bc ? (B - b0) : Bc;
-    rc = forward_chunk(ctx, m, nullptr, monthly_dev + (size_t)b0 * 12 * H * W * 13, nb, 4, H, 4, 1, min17, max17,
-                       out_dev + (size_t)b0 * Ho * Ho);
-    if (rc) return rc;
-    m->lastB = nb;
-  }
+  return run_chunks(ctx, nullptr, monthly_dev, B, 4, H, 4, 1, min17, max17, out_dev);
+}
+
+// One chunk on scratch slot `slot` (0/1), enqueued on that slot's stream.  Used by the host-buffer
+// tile path, which interleaves its own H2D copies with the two slots.
+int model_forward_slot(stc_ctx* ctx, int slot, const float* monthly_dev, int nb, int Bc, int H,
+                       const double* min17, const double* max17, float* out_dev) {
+  ModelState* m = (ModelState*)(slot ? ctx->model2 : ctx->model);
+  if (!m || !m->weights_ready) STC_FAIL(STC_ERR_STATE, "predict_patches: weights not finalized");
+  if (H % 4 != 0 || H < 28 || nb < 1 || nb > Bc) STC_FAIL(STC_ERR_ARG, "predict_patches: bad shape");
+  if (slot && !ctx->stream2) STC_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  cudaStream_t saved = ctx->stream;
+  ctx->stream = slot ? ctx->stream2 : saved;
+  int rc = ensure_plan(ctx, m, Bc, H, 5);
+  if (!rc) rc = forward_chunk(ctx, m, nullptr, monthly_dev, nb, 4, H, 4, 1, min17, max17, out_dev);
+  ctx->stream = saved;
+  if (rc) return rc;
+  m->lastB = nb; ctx->last_slot = slot;
   return STC_OK;
 }

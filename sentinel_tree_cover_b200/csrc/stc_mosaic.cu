@@ -47,7 +47,7 @@ __device__ __forceinline__ float np_sum(const float* a, int n) {
 // (calc_overlap :1503-1512 without the final nanmean, which the host takes with NumPy so the
 // float32 pairwise summation order is NumPy's own).  The mean over the other layers follows
 // np.nanmean(axis=-1) on the compacted layer axis: layer i deleted, layers that never touch the
-// footprint deleted (:1508-1509), NaN -> 0, NumPy add.reduce order, divided by the non-NaN count.
+// footprint deleted (:1508-1509), NaN -> 0, divided by the non-NaN count.
 __global__ void __launch_bounds__(256) mosaic_ratio_kernel(MosaicParams p, float* diffs) {
   const int i = blockIdx.x;
   __shared__ int keep[64]; __shared__ int L;
@@ -68,12 +68,14 @@ __global__ void __launch_bounds__(256) mosaic_ratio_kernel(MosaicParams p, float
       int X = p.xs[i] + px, Y = p.ys[i] + py;
       float vi; int a, b;
       layer_value(p, i, X, Y, vi, a, b);
-      float vals[64]; int m = 0;
+      // np.delete(...) hands nanmean an array whose layer axis has the LARGEST stride, so NumPy
+      // reduces it as the outer loop: a plain sequential float32 sum in layer order (verified).
+      float s = 0.f; int m = 0;
       for (int l = 0; l < L; ++l) {
         float vj;
-        if (layer_value(p, keep[l], X, Y, vj, a, b)) { vals[l] = vj; ++m; } else vals[l] = 0.f;
+        if (layer_value(p, keep[l], X, Y, vj, a, b)) { s = __fadd_rn(s, vj); ++m; }
       }
-      if (m > 0) out = fabsf(__fsub_rn(__fdiv_rn(np_sum(vals, L), (float)m), vi));
+      if (m > 0) out = fabsf(__fsub_rn(__fdiv_rn(s, (float)m), vi));
     }
     diffs[(int64_t)i * p.S * p.S + idx] = out;
   }

@@ -138,7 +138,7 @@ static int sr_plan(stc_ctx* ctx, SrState* s, int N, int H, int W) {
   if (s->arena) { cudaFree(s->arena); s->arena = nullptr; }
   int Hp = H + 2, Wp = W + 2;
   int64_t P = (int64_t)N * Hp * Wp;
-  int guard = ((Wp + 2 + 512 + 7) / 8) * 8;
+  int guard = ((Wp + 2 + 544 + 7) / 8) * 8;
   int64_t plane = P + 2 * guard;
   int64_t rp = (P + 511) / 512 * 512;
   size_t bytes = (size_t)(2 + 4 + 4) * plane * 16 + (size_t)(8 + 8) * rp * 16;
