@@ -96,6 +96,13 @@ int stc_predict_patches_host(stc_ctx* ctx, const float* monthly_host, int B, int
 int stc_predict_patches_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W,
                             const double* min17, const double* max17, float* out_dev);
 
+/* Same, for uint16 patches: integer input follows predict_subtile's `subtile / 65535.`
+ * convention (:345-347); halves the host->device bytes of the tile path. */
+int stc_predict_patches_u16_host(stc_ctx* ctx, const uint16_t* monthly_host, int B, int H, int W,
+                                 const double* min17, const double* max17, float* out_host);
+int stc_predict_patches_u16_dev(stc_ctx* ctx, const uint16_t* monthly_dev, int B, int H, int W,
+                                const double* min17, const double* max17, float* out_dev);
+
 /* ---- temporal regrid + Whittaker + monthly mean as one linear operator
  *      out[12,P,C] = M[12,n] . in[n,P,C]   (P = H*W pixels)
  *      replaces calculate_and_save_best_images (src/downloading/utils.py:176-347)

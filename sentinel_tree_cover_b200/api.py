@@ -65,6 +65,8 @@ SYMBOLS = [
     ("stc_assemble_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_predict_patches_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
     ("stc_predict_patches_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
+    ("stc_predict_patches_u16_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
+    ("stc_predict_patches_u16_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
     ("stc_temporal_matmul_host", C.c_int, [C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
     ("stc_temporal_matmul_dev", C.c_int, [C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
     ("stc_indices_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
@@ -242,14 +244,17 @@ class StcSession:
 
     def predict_patches(self, monthly, out=None):
         """Fused tile path: monthly [B,12,H,W,13] -> tree-cover probabilities [B,H-14,W-14]."""
-        m = monthly if (monthly.dtype == np.float32 and monthly.flags.c_contiguous) else np.ascontiguousarray(monthly, np.float32)
+        u16 = monthly.dtype == np.uint16          # integer storage convention: x / 65535 (predict_subtile :345-347)
+        want = np.uint16 if u16 else np.float32
+        m = monthly if (monthly.dtype == want and monthly.flags.c_contiguous) else np.ascontiguousarray(monthly, want)
         B, n, H, W, Cc = m.shape
         assert n == 12 and Cc == 13
         if out is None:
             out = np.empty((B, H - 14, W - 14), np.float32)
         mn, mnp = _f64(self.min_all)
         mx, mxp = _f64(self.max_all)
-        self._check(self.lib.stc_predict_patches_host(self.h, _dptr(m), B, H, W, mnp, mxp, _dptr(out)))
+        fn = self.lib.stc_predict_patches_u16_host if u16 else self.lib.stc_predict_patches_host
+        self._check(fn(self.h, _dptr(m), B, H, W, mnp, mxp, _dptr(out)))
         return out
 
     def predict_patches_dev(self, m_dev, B, H, W, out_dev):

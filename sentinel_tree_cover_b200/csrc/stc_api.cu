@@ -153,6 +153,7 @@ int stc_assemble_host(stc_ctx* ctx, const float* monthly_host, int B, int H, int
 static int predict_patches_core(stc_ctx* ctx, const float* monthly, bool host_in, int B, int H, int W,
                                 const double* min17, const double* max17, float* out, bool host_out) {
   if (B < 1 || !monthly || !out || !min17 || !max17) STC_FAIL(STC_ERR_ARG, "predict_patches: bad argument");
+  const size_t esz = ctx->monthly_u16 ? 2 : 4;      // element size of the monthly patches
   size_t per_in = (size_t)12 * H * W * 13, per_out = (size_t)(H - 14) * (W - 14);
   if (!host_in && !host_out) return model_predict_patches_dev(ctx, monthly, B, H, W, min17, max17, out);
   const char* env = getenv("STC_CHUNK");
@@ -166,10 +167,10 @@ static int predict_patches_core(stc_ctx* ctx, const float* monthly, bool host_in
       STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
     }
   }
-  if (host_in && ctx->stage_in_bytes < Bc * per_in * 4) {
+  if (host_in && ctx->stage_in_bytes < Bc * per_in * esz) {
     STC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 2; ++i) { if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]); ctx->stage_in[i] = nullptr; }
-    ctx->stage_in_bytes = Bc * per_in * 4;
+    ctx->stage_in_bytes = Bc * per_in * esz;
     for (int i = 0; i < 2; ++i) STC_CUDA(cudaMalloc(&ctx->stage_in[i], ctx->stage_in_bytes));
   }
   if (host_out && ctx->stage_out_bytes < (size_t)B * per_out * 4) {
@@ -194,14 +195,14 @@ static int predict_patches_core(stc_ctx* ctx, const float* monthly, bool host_in
   int k = 0;
   for (int b0 = 0; b0 < B; b0 += Bc, ++k) {
     int nb = (B - b0) < Bc ? (B - b0) : Bc;
-    const float* src = monthly + (size_t)b0 * per_in;
+    const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(monthly) + (size_t)b0 * per_in * esz);
     const int sl = k & 1;
     const int slot = dual ? sl : 0;
     cudaStream_t cs = slot ? ctx->stream2 : ctx->stream;
     if (host_in) {
       // copy stream: wait until the compute that last read this staging buffer is done, then copy
       if (k >= 2) STC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[sl], 0));
-      STC_CUDA(cudaMemcpyAsync(ctx->stage_in[sl], src, nb * per_in * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+      STC_CUDA(cudaMemcpyAsync(ctx->stage_in[sl], src, nb * per_in * esz, cudaMemcpyHostToDevice, ctx->copy_stream));
       STC_CUDA(cudaEventRecord(ctx->ev_ready[sl], ctx->copy_stream));
       STC_CUDA(cudaStreamWaitEvent(cs, ctx->ev_ready[sl], 0));
       src = (const float*)ctx->stage_in[sl];
@@ -228,6 +229,24 @@ int stc_predict_patches_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H
                             const double* min17, const double* max17, float* out_dev) {
   CTX_CHECK();
   return predict_patches_core(ctx, monthly_dev, false, B, H, W, min17, max17, out_dev, false);
+}
+
+// uint16 patches (the reference's integer storage convention, predict_subtile :345-347: x / 65535)
+int stc_predict_patches_u16_host(stc_ctx* ctx, const uint16_t* monthly_host, int B, int H, int W,
+                                 const double* min17, const double* max17, float* out_host) {
+  CTX_CHECK();
+  ctx->monthly_u16 = 1;
+  int rc = predict_patches_core(ctx, reinterpret_cast<const float*>(monthly_host), true, B, H, W, min17, max17, out_host, true);
+  ctx->monthly_u16 = 0;
+  return rc;
+}
+int stc_predict_patches_u16_dev(stc_ctx* ctx, const uint16_t* monthly_dev, int B, int H, int W,
+                                const double* min17, const double* max17, float* out_dev) {
+  CTX_CHECK();
+  ctx->monthly_u16 = 1;
+  int rc = predict_patches_core(ctx, reinterpret_cast<const float*>(monthly_dev), false, B, H, W, min17, max17, out_dev, false);
+  ctx->monthly_u16 = 0;
+  return rc;
 }
 
 int stc_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_host, int n_in, int n_out, int64_t inner,

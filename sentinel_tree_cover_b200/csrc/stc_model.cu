@@ -108,33 +108,25 @@ __device__ __forceinline__ void write_border(uint4* base, int b, int yp, int xp,
   }
 }
 
-// grid (ceil(HW/128), B): a block owns 128 consecutive pixels of one sample.  The 12 monthly
-// slabs (128 px x 13 ch = 6.5 KB each, contiguous in HBM) are staged with 16-byte cp.async into
-// shared memory, so global reads are fully coalesced; each thread then gathers its pixel's
-// 13 channels with the conflict-free stride 13.
-__global__ void __launch_bounds__(128) assemble_prep_kernel(const float* __restrict__ in, PrepParams p) {
-  extern __shared__ __align__(16) float s_in[];            // [12][128*13]
+// grid (ceil(HW/128), B): a block owns 128 consecutive pixels of one sample; a warp's loads of one
+// month cover one contiguous 32 x 13-element run (L1 absorbs the 13 channel passes).
+// T = float, or uint16_t for the reference's integer storage convention (predict_subtile :345-347:
+// integer input is divided by 65535; float32 division of the exactly representable operands gives
+// the same float32 as NumPy's float64 division followed by astype(float32)).
+__device__ __forceinline__ float load_monthly(float v) { return v; }
+__device__ __forceinline__ float load_monthly(uint16_t v) { return __fdiv_rn((float)v, 65535.f); }
+
+template <typename T>
+__global__ void __launch_bounds__(128) assemble_prep_kernel(const T* __restrict__ in, PrepParams p) {
+  // (a cp.async shared-memory staged variant was measured 11% slower -- 80 KB/block leaves 8 warps
+  //  per SM and serialises load and sort phases; the direct form keeps 16 warps interleaving)
   const int HW = p.H * p.W;
   const int b = blockIdx.y;
-  const int r0 = blockIdx.x * 128;
-  const int npx = (HW - r0) < 128 ? (HW - r0) : 128;
-  {
-    const float* blk = in + ((int64_t)b * 12 * HW + r0) * 13;
-    const int nvec = (npx * 13) / 4;                         // HW % 4 == 0 and r0 % 4 == 0 -> 16-byte aligned
-    for (int t = 0; t < 12; ++t) {
-      const float4* g = reinterpret_cast<const float4*>(blk + (int64_t)t * HW * 13);
-      const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_in + t * 1664);
-      for (int i = threadIdx.x; i < nvec; i += 128)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i), "l"(g + i) : "memory");
-    }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-  }
-  if ((int)threadIdx.x >= npx) return;
-  const int r = r0 + threadIdx.x;
+  const int r = blockIdx.x * 128 + threadIdx.x;
+  if (r >= HW) return;
   int y = r / p.W, x = r - y * p.W;
-  const float* src = s_in + threadIdx.x * 13;
-  const int fs_in = 1664;
+  const T* src = in + ((int64_t)b * 12 * HW + r) * 13;
+  const int64_t fs_in = (int64_t)HW * 13;
   float bands[5][12];
   float fr[5][8];
   auto norm = [&](float v, int c) { v = fminf(fmaxf(v, p.lo[c]), p.hi[c]); return __fdiv_rn(__fsub_rn(v, p.mid[c]), p.half[c]); };
@@ -150,7 +142,7 @@ __global__ void __launch_bounds__(128) assemble_prep_kernel(const float* __restr
   for (int c = 0; c < 13; ++c) {
     float v[12];
 #pragma unroll
-    for (int t = 0; t < 12; ++t) v[t] = src[t * fs_in + c];
+    for (int t = 0; t < 12; ++t) v[t] = load_monthly(src[t * fs_in + c]);
     if (c < 4) {
 #pragma unroll
       for (int t = 0; t < 12; ++t) bands[c][t] = v[t];
@@ -320,75 +312,62 @@ struct ApplyParams {
   const float* head_w; const float* head_b; float* head_out;
 };
 
-// One thread per SOURCE pixel: in max-pool mode the four sources of a destination pixel sit in
-// four consecutive lanes and are combined with shuffles, otherwise source == destination thread.
-// The sSE squeeze  sum_c (x_c a_c + b_c) w_c  is evaluated as  K + sum_c x_c (a_c w_c)  with the
-// per-sample constants folded once per block (shared-memory tables read as float4).
 __global__ void __launch_bounds__(256) block_apply_kernel(ApplyParams p) {
-  extern __shared__ __align__(16) float s_ab[];   // [C] a, [C] b, [C] a*w (or a*head_w in head mode: unused), [1] K
-  float* sa = s_ab; float* sb = s_ab + p.C; float* saw = s_ab + 2 * p.C; float* shw = s_ab + 3 * p.C;
-  __shared__ float sK;
+  extern __shared__ float s_ab[];   // [C] a, [C] b, [C] sse_w
+  float* sa = s_ab; float* sb = s_ab + p.C; float* sw = s_ab + 2 * p.C;
   const int b = blockIdx.y;
   const int gs = p.C / 8;
-  if (threadIdx.x == 0) sK = 0.f;
-  __syncthreads();
-  float kpart = 0.f;
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    float a_, b_;
-    gn_affine(p.stats + (int64_t)b * 16, c / gs, p.count, p.gamma[c], p.beta[c], a_, b_);
-    const float w = p.sse_w[c];
-    sa[c] = a_; sb[c] = b_; saw[c] = a_ * w; kpart += b_ * w;
-    shw[c] = (p.mode == 3) ? p.head_w[c] : 0.f;
+    gn_affine(p.stats + (int64_t)b * 16, c / gs, p.count, p.gamma[c], p.beta[c], sa[c], sb[c]);
+    sw[c] = p.sse_w[c];
   }
-  if (kpart != 0.f) atomicAdd(&sK, kpart);
   __syncthreads();
-  const float K = sK + p.sse_b[0];
-  const int nsrc = (p.mode == 1) ? 4 : 1;
-  const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int didx = gidx / nsrc, k = gidx - didx * nsrc;
-  const bool active = didx < p.Hd * p.Wd;
-  const int dcl = active ? didx : 0;
-  const int yd = dcl / p.Wd, xd = dcl - yd * p.Wd;
-  int ys, xs;
-  if (p.mode == 1) { ys = 2 * yd + (k >> 1); xs = 2 * xd + (k & 1); }
-  else if (p.mode == 2) { ys = yd >> 1; xs = xd >> 1; }
-  else { ys = yd + p.off; xs = xd + p.off; }
-  const float4* src = p.raw + ((int64_t)b * p.sHp + ys + p.so) * p.sWp + xs + p.so;
-  const float4* saw4 = reinterpret_cast<const float4*>(saw);
-  float dot = 0.f;
-  for (int c4 = 0; c4 < p.C / 4; ++c4) {
-    const float4 v = src[(int64_t)c4 * p.raw_plane];
-    const float4 w = saw4[c4];
-    dot = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, dot))));
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.Hd * p.Wd) return;
+  int yd = idx / p.Wd, xd = idx - yd * p.Wd;
+  int nsrc = (p.mode == 1) ? 4 : 1;
+  int64_t SP[4]; float sv[4];
+  for (int k = 0; k < nsrc; ++k) {
+    int ys, xs;
+    if (p.mode == 1) { ys = 2 * yd + (k >> 1); xs = 2 * xd + (k & 1); }
+    else if (p.mode == 2) { ys = yd >> 1; xs = xd >> 1; }
+    else { ys = yd + p.off; xs = xd + p.off; }
+    SP[k] = ((int64_t)b * p.sHp + ys + p.so) * p.sWp + xs + p.so;
+    float dot = 0.f;
+    for (int c4 = 0; c4 < p.C / 4; ++c4) {
+      float4 v = p.raw[(int64_t)c4 * p.raw_plane + SP[k]];
+      int c = c4 * 4;
+      dot += (v.x * sa[c] + sb[c]) * sw[c] + (v.y * sa[c + 1] + sb[c + 1]) * sw[c + 1] +
+             (v.z * sa[c + 2] + sb[c + 2]) * sw[c + 2] + (v.w * sa[c + 3] + sb[c + 3]) * sw[c + 3];
+    }
+    sv[k] = sigm(dot + p.sse_b[0]);
   }
-  const float sv = sigm(dot + K);
-  const float4* sa4 = reinterpret_cast<const float4*>(sa);
-  const float4* sb4 = reinterpret_cast<const float4*>(sb);
   if (p.mode == 3) {
-    const float4* hw4 = reinterpret_cast<const float4*>(shw);
     float acc = 0.f;
     for (int c4 = 0; c4 < p.C / 4; ++c4) {
-      const float4 v = src[(int64_t)c4 * p.raw_plane];
-      const float4 a4 = sa4[c4], b4 = sb4[c4], h4 = hw4[c4];
-      acc += (fmaf(v.x, a4.x, b4.x) * h4.x + fmaf(v.y, a4.y, b4.y) * h4.y + fmaf(v.z, a4.z, b4.z) * h4.z + fmaf(v.w, a4.w, b4.w) * h4.w);
+      float4 v = p.raw[(int64_t)c4 * p.raw_plane + SP[0]];
+      int c = c4 * 4;
+      acc += (v.x * sa[c] + sb[c]) * sv[0] * p.head_w[c] + (v.y * sa[c + 1] + sb[c + 1]) * sv[0] * p.head_w[c + 1] +
+             (v.z * sa[c + 2] + sb[c + 2]) * sv[0] * p.head_w[c + 2] + (v.w * sa[c + 3] + sb[c + 3]) * sv[0] * p.head_w[c + 3];
     }
-    if (active) p.head_out[((int64_t)b * p.Hd + yd) * p.Wd + xd] = sigm(acc * sv + p.head_b[0]);
+    p.head_out[((int64_t)b * p.Hd + yd) * p.Wd + xd] = sigm(acc + p.head_b[0]);
     return;
   }
-  uint4* dst = p.dst + ((int64_t)b * p.dHp + yd + 1) * p.dWp + xd + 1;
+  int64_t DP = ((int64_t)b * p.dHp + yd + 1) * p.dWp + xd + 1;
   for (int c8 = 0; c8 < p.C / 8; ++c8) {
-    const float4 v0 = src[(int64_t)(2 * c8) * p.raw_plane], v1 = src[(int64_t)(2 * c8 + 1) * p.raw_plane];
-    const float4 a0 = sa4[2 * c8], a1 = sa4[2 * c8 + 1], b0 = sb4[2 * c8], b1 = sb4[2 * c8 + 1];
-    float o[8] = {fmaf(v0.x, a0.x, b0.x) * sv, fmaf(v0.y, a0.y, b0.y) * sv, fmaf(v0.z, a0.z, b0.z) * sv, fmaf(v0.w, a0.w, b0.w) * sv,
-                  fmaf(v1.x, a1.x, b1.x) * sv, fmaf(v1.y, a1.y, b1.y) * sv, fmaf(v1.z, a1.z, b1.z) * sv, fmaf(v1.w, a1.w, b1.w) * sv};
-    if (nsrc == 4) {
+    float o[8];
+    for (int k = 0; k < nsrc; ++k) {
+      float4 v0 = p.raw[(int64_t)(2 * c8) * p.raw_plane + SP[k]];
+      float4 v1 = p.raw[(int64_t)(2 * c8 + 1) * p.raw_plane + SP[k]];
+      float t[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        o[i] = fmaxf(o[i], __shfl_xor_sync(0xffffffffu, o[i], 1));
-        o[i] = fmaxf(o[i], __shfl_xor_sync(0xffffffffu, o[i], 2));
+        int c = c8 * 8 + i;
+        float z = (t[i] * sa[c] + sb[c]) * sv[k];
+        o[i] = (k == 0) ? z : fmaxf(o[i], z);
       }
     }
-    if (active && k == 0) dst[(int64_t)c8 * p.dst_plane] = pack8(o);
+    p.dst[(int64_t)c8 * p.dst_plane + DP] = pack8(o);
   }
 }
 
@@ -629,9 +608,8 @@ static int run_apply(stc_ctx* ctx, ModelState* m, int blk, const Act& src_geo, b
   if (dst) { ap.dst = dst->at(dst_chunk_off); ap.dst_plane = dst->plane; ap.dHp = dst->Hp; ap.dWp = dst->Wp; }
   ap.Hd = Hd; ap.Wd = Hd; ap.mode = mode; ap.off = off;
   ap.head_w = m->fp["head.w"]; ap.head_b = m->fp["head.b"]; ap.head_out = head_out;
-  const int nsrc = (mode == 1) ? 4 : 1;
-  dim3 grid(cdiv((int64_t)Hd * Hd * nsrc, 256), B);
-  block_apply_kernel<<<grid, 256, 4 * ap.C * sizeof(float), ctx->stream>>>(ap);
+  dim3 grid(cdiv((int64_t)Hd * Hd, 256), B);
+  block_apply_kernel<<<grid, 256, 3 * ap.C * sizeof(float), ctx->stream>>>(ap);
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;
@@ -657,12 +635,11 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
       pp.lo[c] = (float)lo; pp.hi[c] = (float)hi; pp.mid[c] = (float)((hi + lo) / 2); pp.half[c] = (float)((hi - lo) / 2);
     }
     if (monthly_dev) {
-      static bool smem_set = false;
-      if (!smem_set) {
-        STC_CUDA(cudaFuncSetAttribute(assemble_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 1664 * 4));
-        smem_set = true;
-      }
-      assemble_prep_kernel<<<dim3(cdiv((int64_t)H * H, 128), B), 128, 12 * 1664 * 4, ctx->stream>>>(monthly_dev, pp);
+      dim3 agrid(cdiv((int64_t)H * H, 128), B);
+      if (ctx->monthly_u16)
+        assemble_prep_kernel<uint16_t><<<agrid, 128, 0, ctx->stream>>>(reinterpret_cast<const uint16_t*>(monthly_dev), pp);
+      else
+        assemble_prep_kernel<float><<<agrid, 128, 0, ctx->stream>>>(monthly_dev, pp);
     } else {
       dim3 grid(cdiv((int64_t)B * pp.Hp * pp.Wp, 256), T1);
       prep_input_kernel<<<grid, 256, 0, ctx->stream>>>(pp);
@@ -779,7 +756,9 @@ static int run_chunks(stc_ctx* ctx, const float* x_dev, const float* monthly_dev
     const int slot = dual ? (k & 1) : 0;
     ctx->stream = slot ? ctx->stream2 : main_stream;
     rc = ensure_plan(ctx, ms[slot], Bc, H, T + 1);
-    if (!rc) rc = forward_chunk(ctx, ms[slot], x_dev ? x_dev + b0 * per_in : nullptr, monthly_dev ? monthly_dev + b0 * per_in : nullptr,
+    const float* mchunk = nullptr;
+    if (monthly_dev) mchunk = reinterpret_cast<const float*>(reinterpret_cast<const char*>(monthly_dev) + b0 * per_in * (ctx->monthly_u16 ? 2 : 4));
+    if (!rc) rc = forward_chunk(ctx, ms[slot], x_dev ? x_dev + b0 * per_in : nullptr, mchunk,
                                 nb, T, H, length, normalize, mn, mx, out_dev + (size_t)b0 * Ho * Ho);
     ms[slot]->lastB = nb; ctx->last_slot = slot;
   }
