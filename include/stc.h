@@ -142,6 +142,15 @@ int stc_gauss_mosaic_host(stc_ctx* ctx, const float* preds_host, const int32_t* 
                           const int32_t* placed, const float* gauss_host, const float* mult_host,
                           int n, int S, int out_h, int out_w, uint8_t* out_host);
 
+/* ---- storage codecs and the Sentinel-1 dB transform.
+ *      to_float32 (src/tof/tof_downloading.py:64-72): uint16 -> x/65535 float32;
+ *      to_int16 (:51-61): trunc(clip(x,0,1)*65535) -> uint16;
+ *      convert_to_db (src/download_and_predict_job.py:74-89): 10*log10(x+1/65535), floored at
+ *      -min_db, rescaled to [0,1]. ------------------------------------------------------ */
+int stc_to_float32_host(stc_ctx* ctx, const uint16_t* in_host, int64_t n, float* out_host);
+int stc_to_uint16_host(stc_ctx* ctx, const float* in_host, int64_t n, uint16_t* out_host);
+int stc_convert_to_db_host(stc_ctx* ctx, const float* in_host, int64_t n, float min_db, float* out_host);
+
 /* ---- cloud-mask feathering, id_areas_to_interp (src/preprocessing/cloud_removal.py:774-798,
  *      closing_size 15) and the same stage of remove_cloud_and_shadows (:913-921, size 20):
  *      per date with sum(mask) > 0:  a = 1 - min(EDT(1-mask),12)/12; a<0.2 -> 0;
@@ -152,6 +161,12 @@ int stc_feather_host(stc_ctx* ctx, const float* masks_host, int n, int H, int W,
  *      in/out [n,H,W] uint8 (0/1). ----------------------------------------------------- */
 int stc_binary_dilate_host(stc_ctx* ctx, const uint8_t* in_host, int n, int H, int W, int iterations,
                            int connectivity, uint8_t* out_host);
+
+/* ---- exact squared Euclidean distance to the nearest non-zero pixel of `target`, searched
+ *      within `radius` (radius^2+1 where none): the capped distance_transform_edt call sites
+ *      (cap 3: identify_bright_bare_surfaces src/download_and_predict_job.py:1117-1119;
+ *       cap 3/5: cloud_removal.py:1333-1336,1608-1611).  target [n,H,W] uint8 -> int32. ---- */
+int stc_edt_sq_host(stc_ctx* ctx, const uint8_t* target_host, int n, int H, int W, int radius, int32_t* out_host);
 
 /* ---- debug: copy an internal activation buffer of the last stc_predict_*
  *      call to the host as float32 NHWC (interior only).  Names: "ccin",

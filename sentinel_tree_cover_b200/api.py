@@ -75,8 +75,12 @@ SYMBOLS = [
     ("stc_mosaic_diffs_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("stc_gauss_mosaic_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_to_float32_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("stc_to_uint16_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("stc_convert_to_db_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     ("stc_feather_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_binary_dilate_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_edt_sq_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_debug_read", C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p]),
 ]
 
@@ -304,6 +308,24 @@ class StcSession:
         return out
 
 
+    def to_float32(self, arr_u16):
+        a = np.ascontiguousarray(arr_u16, np.uint16)
+        out = np.empty(a.shape, np.float32)
+        self._check(self.lib.stc_to_float32_host(self.h, _dptr(a), a.size, _dptr(out)))
+        return out
+
+    def to_uint16(self, arr):
+        a = np.ascontiguousarray(arr, np.float32)
+        out = np.empty(a.shape, np.uint16)
+        self._check(self.lib.stc_to_uint16_host(self.h, _dptr(a), a.size, _dptr(out)))
+        return out
+
+    def convert_to_db(self, arr, min_db):
+        a = np.ascontiguousarray(arr, np.float32)
+        out = np.empty(a.shape, np.float32)
+        self._check(self.lib.stc_convert_to_db_host(self.h, _dptr(a), a.size, float(min_db), _dptr(out)))
+        return out
+
     def feather(self, masks, closing_size):
         """[n,H,W] float32 0/1 masks -> feathered interpolation weights (see include/stc.h)."""
         m = np.ascontiguousarray(masks, np.float32)
@@ -321,6 +343,16 @@ class StcSession:
         self._check(self.lib.stc_binary_dilate_host(self.h, _dptr(a3), a3.shape[0], shp[-2], shp[-1], int(iterations),
                                                     int(connectivity), _dptr(out)))
         return out.reshape(shp).astype(bool)
+
+    def edt_capped(self, target, cap):
+        """min(distance_transform_edt(1 - target), cap) in float64 (exact integer search on the GPU,
+        square root on the host).  target [H,W] or [n,H,W], non-zero = distance-zero pixels."""
+        a = np.ascontiguousarray(np.asarray(target) != 0, np.uint8)
+        shp = a.shape
+        a3 = a.reshape((-1,) + shp[-2:])
+        d2 = np.empty(a3.shape, np.int32)
+        self._check(self.lib.stc_edt_sq_host(self.h, _dptr(a3), a3.shape[0], shp[-2], shp[-1], int(np.ceil(cap)), _dptr(d2)))
+        return np.minimum(np.sqrt(d2.astype(np.float64)), float(cap)).reshape(shp)
 
     def mosaic(self, preds, xs, ys, out_shape, sigma=36):
         """Gaussian overlap blend of subtile predictions (list/array [n,S,S], the arrays as
@@ -437,6 +469,75 @@ def superresolve_large_tile(arr, sess, wsize=110):
             src[..., 4:] = resolved[:, 4:-4, 4:-4, :]
             arr[:, x:x + wsize, y:y + wsize, ...] = src
     return arr
+
+
+def to_float32(array, sess):
+    """src/tof/tof_downloading.py:64-72: integer arrays -> x/65535 float32; float arrays pass through."""
+    if not isinstance(array.flat[0], np.floating):
+        assert np.max(array) > 1
+        array = sess.to_float32(array)
+    assert np.max(array) <= 1
+    assert array.dtype == np.float32
+    return array
+
+
+def to_int16(array, sess):
+    """src/tof/tof_downloading.py:51-61: float [0,1] -> uint16 trunc(x*65535)."""
+    assert np.min(array) >= 0, np.min(array)
+    assert np.max(array) <= 1
+    return sess.to_uint16(array)
+
+
+def convert_to_db(x, min_db, sess):
+    """src/download_and_predict_job.py:74-89."""
+    return sess.convert_to_db(x, min_db)
+
+
+def process_sentinel_1_tile(sentinel1, dates, sess):
+    """src/tof/tof_downloading.py:75-95: Sentinel-1 dates -> 24 steps -> median of consecutive pairs
+    (= their mean) -> 12 monthly composites, as one 12 x n operator applied on the GPU."""
+    M, _ = _regrid.s1_monthly_operator(dates)
+    return sess.temporal_matmul(sentinel1, M)
+
+
+def identify_bright_bare_surfaces(img, sess):
+    """src/download_and_predict_job.py:1099-1122: NIR/SWIR < 0.9, mean RGB > 0.2, EVI < 0.3 in more
+    than one frame -> open/close by dilations -> ramp min(EDT,3)/3, cropped by 7 px (float64).
+    The neighbourhood work (dilations, distance transform) runs on the GPU."""
+    BLUE, RED, NIR = np.clip(img[..., 0], 0, 1), np.clip(img[..., 2], 0, 1), np.clip(img[..., 3], 0, 1)
+    evis = np.clip(2.5 * ((NIR - RED) / (NIR + (6 * RED) - (7.5 * BLUE) + 1)), -1.5, 1.5)
+    cand = (img[..., 3] / (img[..., 8] + 0.01)) < 0.9
+    cand = cand * (np.mean(img[..., :3], axis=-1) > 0.2)
+    cand = cand * (evis < 0.3)
+    bright = np.sum(cand, axis=0) > 1
+    bright = sess.binary_dilation(1 - bright, iterations=2)
+    bright = sess.binary_dilation(1 - bright, iterations=1)
+    blurred = sess.edt_capped(bright, 3) / 3
+    return blurred[7:-7, 7:-7]
+
+
+def postprocess_subtile(preds, subtile_all, min_clear_images_per_date, sess, size=158):
+    """Post-filters of the subtile loop, src/download_and_predict_job.py:1408-1409,1451-1483:
+    no-image 40x40 block vote -> 255, bright-bare-surface attenuation, round to 3 decimals.
+    `subtile_all` is the (5, size+14, size+14, 17) stack BEFORE normalize_subtile."""
+    bright_surface = identify_bright_bare_surfaces(subtile_all, sess)
+    preds = np.array(preds, copy=True)
+    m = min_clear_images_per_date[6:-6, 6:-6]
+    no_images = m < 1
+    no_images = 1 - sess.binary_dilation(1 - no_images, iterations=6, connectivity=2)
+    no_images = sess.binary_dilation(no_images, iterations=6, connectivity=2)
+    if size == 158:
+        blocks, bs, frac = 4, 40, 0.25
+    elif size == 142:
+        blocks, bs, frac = 9, 16, 0.75
+    else:
+        blocks = None
+    if blocks:
+        v = np.reshape(no_images, (blocks, bs, blocks, bs)).sum(axis=(1, 3)) > (bs * bs) * frac
+        v = v.repeat(bs, axis=0).repeat(bs, axis=1)[1:-1, 1:-1]
+        preds[v] = 255.
+    preds = np.around(preds * bright_surface, 3)
+    return preds.astype(np.float32)
 
 
 def id_areas_to_interp(tiles, probs, shadows, image_dates, pfcps, sess):

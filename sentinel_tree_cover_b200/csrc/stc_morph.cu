@@ -88,6 +88,36 @@ __global__ void __launch_bounds__(256) binary_dilate_kernel(const unsigned char*
   out[idx] = o;
 }
 
+// squared Euclidean distance (exact, integer) from every pixel to the nearest non-zero pixel of
+// `target` within `radius`; radius*radius + 1 where none is that close.  The callers cap
+// distance_transform_edt at 3/5/12 px, so a windowed search is exact.
+__global__ void __launch_bounds__(256) edt_sq_kernel(const unsigned char* __restrict__ target, int* __restrict__ out,
+                                                     int n, int H, int W, int radius) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * H * W) return;
+  int x = (int)(idx % W); int64_t r = idx / W; int y = (int)(r % H); int d = (int)(r / H);
+  const unsigned char* m = target + (int64_t)d * H * W;
+  const int r2 = radius * radius;
+  int best = r2 + 1;
+  for (int dy = -radius; dy <= radius; ++dy) {
+    int yy = y + dy; if (yy < 0 || yy >= H) continue;
+    for (int dx = -radius; dx <= radius; ++dx) {
+      int xx = x + dx; if (xx < 0 || xx >= W) continue;
+      int d2 = dx * dx + dy * dy;
+      if (d2 < best && m[(int64_t)yy * W + xx]) best = d2;
+    }
+  }
+  out[idx] = best;
+}
+
+int pre_edt_sq_dev(stc_ctx* ctx, const unsigned char* target_dev, int n, int H, int W, int radius, int* out_dev) {
+  if (radius < 1 || radius > 64) STC_FAIL(STC_ERR_ARG, "edt_sq: radius must be in 1..64");
+  edt_sq_kernel<<<cdiv((int64_t)n * H * W, 256), 256, 0, ctx->stream>>>(target_dev, out_dev, n, H, W, radius);
+  STC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return STC_OK;
+}
+
 int pre_feather_dev(stc_ctx* ctx, const float* mask_dev, int n, int H, int W, int size, float* tmp_a, float* tmp_b,
                     float* sums_dev, float* out_dev) {
   if (size < 1 || size > 64) STC_FAIL(STC_ERR_ARG, "feather: closing size must be in 1..64");

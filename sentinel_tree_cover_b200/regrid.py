@@ -96,6 +96,14 @@ def monthly_operator(dates):
     return M.astype(np.float32), max_distance
 
 
+def s1_monthly_operator(dates):
+    """process_sentinel_1_tile (/root/reference/src/tof/tof_downloading.py:75-95): regrid to 24 steps,
+    then np.median of consecutive pairs -- the median of two values is their mean, so the whole
+    stage is the 12 x n operator A G (no Whittaker smoothing for Sentinel-1)."""
+    G, max_distance = regrid_matrix(dates)
+    return (pair_mean_matrix() @ G.astype(np.float64)).astype(np.float32), max_distance
+
+
 def id_missing_px(s2, thresh=11):
     bad = (s2[..., :10] == 0.0).sum(-1) + (s2[..., :10] >= 1.0).sum(-1)
     per_date = (bad > 1.0).sum(axis=(1, 2))
