@@ -36,6 +36,25 @@ def conv_flops_per_tile(Hin, T=4):
     return float(gru + blk)
 
 
+def gates_roofline(total_ms, n_launch, chunk, peaks):
+    """Roofline entry of the dominant tensor kernel, conv3x3_umma_kernel<64,4,16,PLAIN> (ConvGRU gates,
+    both directions of one `chunk`-tile sub-batch per launch).  Algorithmic FLOPs per launch: steps
+    1..3 contract [x(17) | h(32)] -> 64 (2*9*49*64 per pixel), step 0 only x (2*9*17*64)."""
+    if not n_launch:
+        return {"bound": "tensor", "achieved": None, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": None, "traffic": None}
+    px = 2 * chunk * H * H
+    flops_avg = px * (3 * 2 * 9 * 49 * 64 + 2 * 9 * 17 * 64) / 4.0
+    avg_s = total_ms / n_launch / 1000.0
+    achieved = flops_avg / avg_s / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"],
+            "traffic": 437.2e6,
+            "kernel": "conv3x3_umma_kernel<64,4,16,PLAIN> (ConvGRU gates)",
+            "note": "avg of %d launches: %.1f us; algorithmic %.3e FLOP/launch (%d tiles x 2 directions); peak = %s sustained "
+                    "bf16/fp16 dense; traffic = dram read+write of the steady-state launch from `ncu --set full` "
+                    "(profiles/r01_b_summary.md: 244 MB + 193 MB, algorithmic 237 + 237 MB); the instruction-level ceiling "
+                    "for N=64 is 44%% of peak (profiles/r01_umma_microbench.txt)" % (n_launch, 1e6 * avg_s, flops_avg, chunk, peaks["src"])}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -82,6 +101,11 @@ def cpu_reference_tiles_per_s(n_tiles, seed=1234):
     from oracle.model_ref import PredictRef
     from sentinel_tree_cover_b200.api import MIN_ALL, MAX_ALL
     from sentinel_tree_cover_b200.weights import random_predict_weights
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     model = PredictRef(random_predict_weights(0))
     m = P.synth_monthly(1, H, seed)
     t0 = time.time()
@@ -182,6 +206,7 @@ def main():
     ms = sess.timer_end()
     barrier()
     launches = sess.launch_count() - l0
+    gates_ms, gates_n = sess.conv_timing_kind(64, 16, 0)     # GRU gates conv = the dominant tensor kernel
     conv_ms, conv_launches = sess.conv_timing(0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -237,11 +262,13 @@ def main():
                             "d2h_bytes_per_step": nbytes_out, "ms_per_step": ms_u16_max / args.steps,
                             "note": "same call with uint16 patches (reference integer convention x/65535, predict_subtile :345-347)"},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
-                             "frac": (achieved / peaks["tf"]) if achieved else None, "traffic": None,
+                "roofline": gates_roofline(gates_ms, gates_n, min(B, int(os.environ.get("STC_CHUNK", "32"))), peaks),
+                "roofline_all_convs": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
+                             "frac": (achieved / peaks["tf"]) if achieved else None,
                              "kernel": "conv3x3_umma_kernel (all conv launches of the step)",
                              "note": "algorithmic conv FLOPs/step (%.3e) / summed CUDA-event duration of the %d conv launches "
-                                     "(%.2f ms of %.2f ms step time); peak = %s sustained bf16/fp16 dense"
+                                     "(%.2f ms of %.2f ms step time; launches of the two chunk slots overlap, so the sum can exceed "
+                                     "the step); peak = %s sustained bf16/fp16 dense"
                                      % (flops / args.steps, conv_launches, conv_ms / args.steps, ms / args.steps, peaks["src"])},
                 "clocks": sampler.summary(), "checksum": checksum}
         if not args.no_cpu_baseline:

@@ -66,6 +66,10 @@ int stc_timer_end(stc_ctx* ctx, float* ms);
  * since the last reset -- measured with CUDA events around each conv launch
  * when enabled (adds no sync; read after stc_sync). */
 int stc_conv_timing(stc_ctx* ctx, int enable_reset, float* total_ms, int64_t* launches);
+/* Same, restricted to one kernel instantiation: N output channels, GroupNorm groups
+ * accumulated (0 = none) and epilogue mode (0 plain, 1 partial-conv+Swish, 2 Swish, 3 GRU
+ * candidate, 4 bias, 5 bias+ReLU).  Call before the reset of stc_conv_timing. */
+int stc_conv_timing_kind(stc_ctx* ctx, int N, int groups, int mode, float* total_ms, int64_t* launches);
 
 /* ---- model forward: predict_subtile (src/download_and_predict_job.py:328-369)
  *      = sess.run(predict_logits, {predict_inp: x[B,T+1,H,W,17], predict_length})

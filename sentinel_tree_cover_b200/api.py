@@ -59,6 +59,7 @@ SYMBOLS = [
     ("stc_timer_begin", C.c_int, [C.c_void_p]),
     ("stc_timer_end", C.c_int, [C.c_void_p, _f32p]),
     ("stc_conv_timing", C.c_int, [C.c_void_p, C.c_int, _f32p, C.POINTER(C.c_int64)]),
+    ("stc_conv_timing_kind", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int64)]),
     ("stc_predict_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
     ("stc_predict_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
     ("stc_assemble_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -216,6 +217,11 @@ class StcSession:
     def conv_timing(self, enable_reset=-1):
         ms, n = C.c_float(), C.c_int64()
         self._check(self.lib.stc_conv_timing(self.h, enable_reset, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def conv_timing_kind(self, N, groups, mode):
+        ms, n = C.c_float(), C.c_int64()
+        self._check(self.lib.stc_conv_timing_kind(self.h, N, groups, mode, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     # -- model -------------------------------------------------------------------

@@ -103,6 +103,22 @@ int stc_conv_timing(stc_ctx* ctx, int enable_reset, float* total_ms, int64_t* la
   return STC_OK;
 }
 
+int stc_conv_timing_kind(stc_ctx* ctx, int N, int groups, int mode, float* total_ms, int64_t* launches) {
+  CTX_CHECK();
+  const int kind = (N * 100 + groups) * 10 + mode;
+  float tot = 0.f; int64_t cnt = 0;
+  for (size_t i = 0; i < ctx->conv_events_used; ++i) {
+    if (ctx->conv_event_kind[i] != kind) continue;
+    float ms = 0.f;
+    STC_CUDA(cudaEventSynchronize(ctx->conv_events[i].second));
+    STC_CUDA(cudaEventElapsedTime(&ms, ctx->conv_events[i].first, ctx->conv_events[i].second));
+    tot += ms; ++cnt;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = cnt;
+  return STC_OK;
+}
+
 // ---- helpers for host-buffer variants ------------------------------------------------
 struct DevBuf {
   void* p = nullptr;

@@ -65,6 +65,7 @@ struct stc_ctx {
   bool time_convs = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
   size_t conv_events_used = 0;
+  std::vector<int> conv_event_kind;   // (N*100 + groups)*10 + mode of each timed conv launch
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   // host-buffer tile path: H2D copies run on their own stream, double-buffered against compute
   cudaStream_t copy_stream = nullptr;

@@ -562,6 +562,8 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
     }
     e0 = ctx->conv_events[ctx->conv_events_used].first;
     e1 = ctx->conv_events[ctx->conv_events_used].second;
+    if (ctx->conv_event_kind.size() < ctx->conv_events.size()) ctx->conv_event_kind.resize(ctx->conv_events.size());
+    ctx->conv_event_kind[ctx->conv_events_used] = (p.N * 100 + (p.stats[0] ? p.G : 0)) * 10 + p.mode;
     ctx->conv_events_used++;
     STC_CUDA(cudaEventRecord(e0, ctx->stream));
   }

@@ -10,7 +10,7 @@ for f in ("bench_umma", "bench_simt"):
         d = json.load(open(os.path.join(D, f + ".json")))
         print(f, "value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "ms/step", round(d["ms_per_step"], 2),
               "roofline", round(d["roofline"]["achieved"], 1), round(d["roofline"]["frac"], 4), "launches", d["gpu_launches"],
-              re.search(r"\(([\d.]+ ms of [\d.]+ ms)", d["roofline"]["note"]).group(1), d["clocks"], "cpu", d.get("cpu_baseline", {}).get("value"))
+              d["roofline"].get("note","")[:60], d["clocks"], "cpu", d.get("cpu_baseline", {}).get("value"))
     except Exception as e:
         print(f, "n/a", e)
 p = os.path.join(D, "launches.csv")
