@@ -172,6 +172,18 @@ int stc_binary_dilate_host(stc_ctx* ctx, const uint8_t* in_host, int n, int H, i
  *       cap 3/5: cloud_removal.py:1333-1336,1608-1611).  target [n,H,W] uint8 -> int32. ---- */
 int stc_edt_sq_host(stc_ctx* ctx, const uint8_t* target_host, int n, int H, int W, int radius, int32_t* out_host);
 
+/* ---- multi-temporal cloud / shadow mask: identify_clouds_shadows(img, dem, bbx)
+ *      (src/preprocessing/cloud_removal.py:1215-1677) in the configuration the reference tree runs in
+ *      (forestmask.tif / urbanmask.tif absent: forest and potential-false-positive masks are zero).
+ *      img [T,H,W,10] float32 reflectance (1 <= T <= 32), dem [H,W] float32.
+ *      clouds_host [T,H,W] float32 0/1 (clouds | shadows | haze dates), fcps_host [T,H,W] uint8
+ *      (the dilated NIR/SWIR false-positive mask the reference returns second).
+ *      stage_host / stage_id: test tap -- when stage_host != NULL the uint8 [T,H,W] mask after stage
+ *      `stage_id` is copied out (1 Hollstein, 2 raw shadows, 3 cleaned shadows, 4 raw clouds,
+ *      5 +brightness/whiteness, 6 after false-positive removal, 7 after shape clean-up, 8 before haze). ---- */
+int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const float* dem_host, int T, int H, int W,
+                         float* clouds_host, uint8_t* fcps_host, uint8_t* stage_host, int stage_id);
+
 /* ---- debug: copy an internal activation buffer of the last stc_predict_*
  *      call to the host as float32 NHWC (interior only).  Names: "ccin",
  *      "cat2", "p1", "cat1", "p2", "u2in", "u3in".  Returns the number of

@@ -1,0 +1,286 @@
+"""TEST INFRASTRUCTURE (oracle) -- NumPy/SciPy restatement of the multi-temporal cloud / shadow
+mask, /root/reference/src/preprocessing/cloud_removal.py:1215-1677 (`identify_clouds_shadows`),
+for the configuration the reference tree actually runs in: `urbanmask.tif` / `forestmask.tif`
+are absent, so the forest mask and the potential-false-positive (urban) masks are all zero
+(:1131-1135, :1254-1257).  Pinned against the reference function itself executed through
+oracle/refshim.py (tests/test_cloud_masks.py).  Tests only; never imported by the product.
+
+The function returns the final (clouds, fcps) and, with `stages=True`, the intermediate
+arrays the CUDA pipeline is checked against stage by stage.
+"""
+import numpy as np
+from scipy.ndimage import binary_dilation as dil, distance_transform_edt as edt
+
+
+def _erode(x, k):
+    """1 - binary_dilation(x == 0, iterations=k): erosion that never eats in from the border."""
+    return 1 - dil(x == 0, iterations=k)
+
+
+def _winsum3(a):
+    """cloud_removal.py:1244-1249 with windowsize 3: 3x3 box sum, np.pad 'reflect' (no edge repeat)."""
+    p = np.pad(a, 1, mode="reflect")
+    p[3:] -= p[:-3]
+    p[:, 3:] -= p[:, :-3]
+    return p.cumsum(0)[2:].cumsum(1)[:, 2:]
+
+
+def shadow_window(t, T):
+    lo, hi = max(0, t - 4), min(T, t + 3)
+    if hi - lo == 3:
+        if hi == T:
+            lo = max(lo - 1, 0)
+        if lo == 0:
+            hi = min(hi + 1, T)
+    return list(range(lo, hi))
+
+
+def cloud_windows(t, T):
+    """others, close (initial list) of cloud_removal.py:1343-1361."""
+    lo, hi = max(0, t - 2), min(T, t + 3)
+    if hi - lo == 3:
+        if hi == T:
+            lo = max(lo - 2, 0)
+        if lo == 0:
+            hi = min(hi + 2, T)
+    others = list(range(lo, hi))
+    close = [max(0, t - 1), min(T - 1, t + 1)]
+    if close[1] - close[0] < 2:
+        if close[0] == 0:
+            close = [close[0] + 1, close[1] + 1]
+        else:
+            close = [close[0] - 1, close[1] - 1]
+    if close[-1] >= T - 2 and T > 3:
+        close = [close[0] - 1] + close
+    return others, close
+
+
+def identify_clouds_shadows(img, dem, stages=False):
+    img = np.asarray(img, np.float32)
+    T, H, W, _ = img.shape
+    st = {}
+    with np.errstate(all="ignore"):
+        ndwi = (img[..., 1] - img[..., 3]) / (img[..., 1] + img[..., 3])
+        water = np.nanmedian(ndwi, axis=0)
+        forest = np.zeros_like(dem)
+        # Hollstein "okay" cloud mask (:1230-1242)
+        clm = (img[..., 7] > 0.166) * (img[..., 1] > 0.28) * (img[..., 5] / img[..., 8] < 4.292)
+        for t in range(T):
+            clm[t] = dil(_erode(clm[t], 2), iterations=10)
+        st["water"], st["clm"] = water, clm.astype(np.uint8)
+
+        # ---- shadows (:1265-1324) ----
+        shadows = np.zeros((T, H, W), np.float32)
+        b4 = img[..., [0, 1, 7, 8]]
+        allref = np.copy(b4)
+        allref[clm > 0] = np.nan
+        allref = np.nanmedian(allref, axis=0)
+        allref[np.isnan(allref)] = np.median(b4, axis=0)[np.isnan(allref)]
+        for t in range(T):
+            win = shadow_window(t, T)
+            r = np.copy(b4)[win]
+            r[clm[win] > 0] = np.nan
+            rmax = np.nanmax(r, axis=0)
+            rmed = np.nanmedian(r, axis=0)
+            rmed[np.isnan(rmed)] = np.min(b4, axis=0)[np.isnan(rmed)]
+            x = img[t]
+            s = ((x[..., 8] - rmed[..., 3]) < -0.04) * ((x[..., 7] - rmed[..., 2]) < -0.04) * (x[..., 0] < 0.09) * \
+                ((x[..., 0] - rmed[..., 0]) < -0.02) * (x[..., 7] < 0.17)
+            d8a, d11 = (x[..., 7] - rmax[..., 2]) < -0.04, (x[..., 8] - rmax[..., 3]) < -0.04
+            dark = d11 * d8a * (x[..., 0] < 0.03) * (x[..., 7] < 0.18)
+            dark[water > 0] = 0
+            s = np.maximum(s, dark)
+            s[water > 0] = 0
+            slope = d8a * d11 * (x[..., 0] < 0.07) * (x[..., 7] < 0.18)
+            slope = slope * (np.sum(x[..., :3], axis=-1) < 0.28)
+            slope[water > 0] = 0
+            slope = slope * (dem >= 25)
+            s = np.maximum(s, slope)
+            wsh = ((x[..., 0] - allref[..., 0]) < -0.05) * ((x[..., 1] - allref[..., 1]) < -0.05) * (x[..., 7] < 0.03) * \
+                  ((allref[..., 1] - x[..., 1]) > 0.02) * (water > 0)
+            shadows[t] = s + wsh
+        st["shadows_raw"] = shadows.copy()
+        for t in range(T):
+            s = dil(_erode(shadows[t], 2), iterations=3)
+            d = edt(1 - s)
+            shadows[t] = 1 - (d > 5)
+        st["shadows_clean"] = shadows.copy()
+
+        # ---- clouds (:1342-1447) ----
+        clouds = np.zeros((T, H, W), np.float32)
+        rgb = img[..., [0, 1, 2]]
+        p25 = [np.percentile(img[..., b], 25, axis=0) for b in range(3)]
+        for t in range(T):
+            others, close = cloud_windows(t, T)
+            ref = np.copy(rgb)
+            if T > 2:
+                ref[shadows > 0] = np.nan
+                up = [np.nanmin(ref[others, ..., b], axis=0) for b in range(3)]
+                nanrep = np.isnan(up[0])
+                for b in range(3):
+                    up[b][nanrep] = p25[b][nanrep]
+                rc = np.nanmin(ref[close], axis=0).astype(np.float32)
+                lo_i, hi_i = close[0], close[-1]
+                for _ in range(10):
+                    if np.sum(np.isnan(rc) > 0):
+                        lo_i, hi_i = max(lo_i - 1, 0), min(hi_i + 1, T)
+                        cl2 = [k for k in range(lo_i, hi_i) if k != t]
+                        new = np.nanmin(ref[cl2], axis=0).astype(np.float32)
+                        rc[np.isnan(rc)] = new[np.isnan(rc)]
+                if np.sum(np.isnan(rc) > 0):
+                    rc[np.isnan(rc)] = np.min(img[..., :3], axis=0)[np.isnan(rc)]
+            else:
+                rc = np.min(ref, axis=0).astype(np.float32)
+                up = [rc[..., 0], rc[..., 1], rc[..., 2]]
+            thr = np.minimum((rc[..., 0] / 0.02 / 100) + 0.005, 0.10)
+            thr = np.maximum(thr, 0.05)
+            thr[forest == 1] -= 0.02
+            thr = np.maximum(thr, 0.04)
+            x = img[t]
+            ci = ((x[..., 0] - up[0]) > 0.08) * ((x[..., 1] - up[1]) > 0.08) * ((x[..., 2] - up[2]) > 0.07)
+            mean_i, mean_c, mod = 0., 1., 0.
+            while (mean_c - mean_i) > 0.075:
+                cc = ((x[..., 0] - rc[..., 0]) > (thr + mod + 0.01)) * ((x[..., 1] - rc[..., 1]) > (thr + mod + 0.01)) * \
+                     ((x[..., 2] - rc[..., 2]) > (thr + mod))
+                mean_i, mean_c = np.mean(ci > 0), np.mean(cc > 0)
+                mod += 0.0025
+            cc = cc * (np.sum(x[..., :3], axis=-1) < 0.75)
+            cc_nf = _erode(cc, 2)
+            cc = cc.astype(cc_nf.dtype) if cc.dtype == bool else cc
+            cc = np.where(forest == 0, cc_nf, cc)
+            clouds[t] = np.maximum(ci, cc)
+        st["clouds_raw"] = clouds.copy()
+
+        # ---- brightness z-score clouds (:1458-1481) ----
+        bm = np.sum(img[..., :3], axis=-1)
+        bm[np.logical_or(clouds > 0, shadows > 0)] = np.nan
+        medb = np.nanmedian(bm, axis=(1, 2))
+        bc = np.zeros_like(clouds, dtype=np.float32)
+        for t in range(T):
+            ratio = np.sum(img[t, ..., :3], axis=-1) / medb[t]
+            ratio[water > 0] = 1.
+            if np.sum(clouds[t] < 0.90):
+                sel = ratio[clouds[t] == 0]
+                z = (ratio - np.nanmean(sel)) / np.nanstd(sel)
+            else:
+                z = (ratio - np.nanmean(ratio)) / np.nanstd(ratio)
+            bc[t][z > 3.5] = 1.
+            bc[t] *= (water < 0)
+        multi = np.sum((bc - clouds) > 0, axis=0)
+        for t in range(T):
+            bc[t][multi > 1] = 0.
+        clouds = np.maximum(clouds, bc)
+        # whiteness false positives (:1484-1492)
+        for t in range(T):
+            mb = np.mean(img[t, ..., :3], axis=-1)
+            vr = np.max(img[t, ..., :3], axis=-1) - np.min(img[t, ..., :3], axis=-1)
+            fp = (mb < 0.4) * ((vr / mb) > 0.5)
+            clouds[t] = clouds[t] * (1 - fp)
+        st["clouds_bright"] = clouds.copy()
+
+        # ---- false-positive removal (:1497-1551); fcps == 0 without an urban mask ----
+        fcps = np.zeros((T, H, W), np.float32)
+        pfcps = np.zeros((T, H, W), np.float32)
+        nsr = (img[..., 3] / (img[..., 8] + 0.01)) < 0.75
+        nsr = dil(nsr, iterations=3)          # note: 3-D dilation over (T,H,W) with the 3-D cross (:1518)
+        for t in range(T):
+            lo, hi = max(t - 1, 0), min(t + 2, T)
+            bmin = np.min(img[lo:hi, ..., :3], axis=(0, 3))
+            isnt = ((np.mean(img[t, ..., :3], axis=-1) - bmin) < 0.4)
+            nsr[t][water < 0] = 0.
+            clouds[t][np.logical_and(nsr[t] > 0, isnt)] = 0.
+        for t in range(T):
+            fp = dil((water > 0) * (img[t, ..., 8] < 0.11), iterations=10)
+            clouds[t][fp] = 0.
+        for t in range(T):
+            clouds[t][_winsum3(clouds[t]) < 5] = 0.
+        for t in range(T):
+            bt = dil(np.sum(img[t, ..., :3], axis=-1) < 0.21, iterations=3)
+            bt = (bt * (1 - forest)).astype(np.uint8)
+            clouds[t][bt] = 0.                 # uint8 fancy index: rows 0/1 of the date are zeroed (:1546-1551)
+        st["clouds_fp"] = clouds.copy()
+
+        # ---- shape clean-up (:1590-1612) ----
+        for t in range(T):
+            c = _erode(clouds[t], 1)
+            pf = dil(pfcps[t], iterations=5)
+            urban = _erode(c * pf, 3)
+            nu = c * (1 - pf)
+            ws = _winsum3(nu)
+            large, small = np.copy(nu), np.copy(nu)
+            large[ws < 6] = 0.
+            small[ws >= 6] = 0.
+            small = dil(small, iterations=1)
+            large = dil(large, iterations=5)
+            nu = np.maximum(large, small)
+            d = edt(1 - nu)
+            nu = 1 - (d > 3)
+            clouds[t] = nu + urban
+        st["clouds_shape"] = clouds.copy()
+        # ---- shadow plausibility (:1617-1626) ----
+        for t in range(T):
+            ms, mc = np.mean(shadows[t]), np.mean(clouds[t])
+            if ms > (mc + 0.3) and mc < 0.3:
+                far = np.logical_or(dil(np.copy(clouds[t]), iterations=50), dem >= 30)
+                shadows[t] = shadows[t] * far
+            if np.mean(clouds[t]) < 0.05 and ((np.mean(shadows[t]) / np.mean(clouds[t])) > 3):
+                far = np.logical_or(dil(np.copy(clouds[t]), iterations=50), dem >= 30)
+                shadows[t] = shadows[t] * far
+        clouds = np.maximum(clouds, shadows)
+        fcps = dil(np.maximum(fcps, nsr), iterations=2)     # 3-D dilation again (:1630)
+        # ---- dark-blue shadow recovery (:1638-1648) ----
+        for t in range(T):
+            if np.mean(clouds[t]) < 0.9:
+                inv = 1 / img[t, ..., 0][clouds[t] == 0]
+                refv = np.mean(inv) + 2 * np.std(inv)
+                s = (1 / img[t, ..., 0] > refv) * (img[t, ..., 7] < 0.17)
+                s = dil(_erode(s, 2), iterations=2)
+                s[water > 0] = 0.
+                clouds[t] = np.maximum(clouds[t], s)
+        clouds[clouds > 1] = 1.
+        st["clouds_pre_haze"] = clouds.copy()
+        # ---- haze (:1652-1676) ----
+        mbr = np.mean(img[..., :3], axis=-1)
+        mean_b, std_b, std_w = [], [], []
+        for t in range(T):
+            if np.mean(clouds[t]) < 1:
+                sel = clouds[t] == 0
+                mean_b.append(np.mean(mbr[t][sel]))
+                std_b.append(np.std(mbr[t][sel]))
+                std_w.append(np.std(np.ptp(img[t, ..., :3][sel], axis=1)))
+        hb = mean_b / np.median(mean_b)
+        hs = std_b / np.median(std_b)
+        hw = std_w / np.median(std_w)
+        haze = np.logical_or((hb >= 1.5) * (hs <= 0.67) * (hw < 1), (hb >= 1.3) * (hs <= 0.5))
+        for k in range(len(haze)):
+            if haze[k]:
+                clouds[k] = 1.
+    if stages:
+        return clouds, fcps, st
+    return clouds, fcps
+
+
+def synth_cloudy_cube(T, H, W, seed):
+    """Sentinel-2-like cube [T,H,W,10] with vegetation/soil/water spectra, Gaussian-blob clouds
+    (+0.3..0.6 on every band) and displaced shadows (x0.3), plus a DEM [H,W]."""
+    r = np.random.default_rng(seed)
+    veg = np.array([0.035, 0.06, 0.045, 0.30, 0.10, 0.22, 0.28, 0.32, 0.17, 0.08], np.float32)
+    soil = np.array([0.09, 0.12, 0.15, 0.25, 0.18, 0.21, 0.23, 0.26, 0.30, 0.24], np.float32)
+    wat = np.array([0.05, 0.06, 0.04, 0.02, 0.03, 0.025, 0.02, 0.02, 0.01, 0.008], np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    mix = 0.5 + 0.5 * np.sin(xx / 17.0) * np.cos(yy / 23.0)
+    base = veg[None, None] * mix[..., None] + soil[None, None] * (1 - mix[..., None])
+    lake = (yy - H * 0.7) ** 2 + (xx - W * 0.25) ** 2 < (min(H, W) * 0.12) ** 2
+    base[lake] = wat
+    cube = np.repeat(base[None], T, 0) * (1 + 0.08 * np.sin(2 * np.pi * np.arange(T) / T))[:, None, None, None]
+    cube = cube + r.normal(0, 0.004, cube.shape)
+    for t in range(T):
+        for _ in range(r.integers(0, 3)):
+            cy, cx, s = r.integers(0, H), r.integers(0, W), r.uniform(5, 14)
+            blob = np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * s * s))
+            cube[t] += (r.uniform(0.3, 0.6) * (blob > 0.4))[..., None]
+            sy, sx = cy + int(1.5 * s), cx + int(1.2 * s)
+            sh = np.exp(-((yy - sy) ** 2 + (xx - sx) ** 2) / (2 * s * s)) > 0.45
+            cube[t][sh] *= 0.3
+    dem = (40 * (0.5 + 0.5 * np.sin(xx / 31.0 + yy / 47.0))).astype(np.float32)
+    return np.clip(cube, 0.001, 0.999).astype(np.float32), dem

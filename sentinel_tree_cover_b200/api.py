@@ -82,6 +82,8 @@ SYMBOLS = [
     ("stc_feather_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_binary_dilate_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_edt_sq_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_cloud_masks_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int]),
     ("stc_debug_read", C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p]),
 ]
 
@@ -360,6 +362,27 @@ class StcSession:
         self._check(self.lib.stc_edt_sq_host(self.h, _dptr(a3), a3.shape[0], shp[-2], shp[-1], int(np.ceil(cap)), _dptr(d2)))
         return np.minimum(np.sqrt(d2.astype(np.float64)), float(cap)).reshape(shp)
 
+    CLOUD_STAGES = {"clm": 1, "shadows_raw": 2, "shadows_clean": 3, "clouds_raw": 4, "clouds_bright": 5,
+                    "clouds_fp": 6, "clouds_shape": 7, "clouds_pre_haze": 8}
+
+    def cloud_masks(self, img, dem, stage=None):
+        """identify_clouds_shadows (cloud_removal.py:1215-1677), no forest/urban mask rasters.
+        img [T,H,W,>=10] float32 reflectance, dem [H,W] -> (clouds float32 [T,H,W], fcps bool [T,H,W]);
+        with `stage` (a CLOUD_STAGES name) also returns that intermediate uint8 mask (test tap)."""
+        a = np.ascontiguousarray(np.asarray(img)[..., :10], np.float32)
+        T, H, W, _ = a.shape
+        d = np.ascontiguousarray(dem, np.float32)
+        if d.shape != (H, W):
+            raise ValueError("dem shape %r does not match image %r" % (d.shape, (H, W)))
+        clouds = np.empty((T, H, W), np.float32)
+        fcps = np.empty((T, H, W), np.uint8)
+        tap = np.empty((T, H, W), np.uint8) if stage else None
+        self._check(self.lib.stc_cloud_masks_host(self.h, _dptr(a), _dptr(d), T, H, W, _dptr(clouds), _dptr(fcps),
+                                                  _dptr(tap) if stage else None, self.CLOUD_STAGES[stage] if stage else 0))
+        if stage:
+            return clouds, fcps.astype(bool), tap
+        return clouds, fcps.astype(bool)
+
     def mosaic(self, preds, xs, ys, out_shape, sigma=36):
         """Gaussian overlap blend of subtile predictions (list/array [n,S,S], the arrays as
         saved by process_subtiles) placed at (xs[i], ys[i]) -> uint8 canvas `out_shape`."""
@@ -504,6 +527,16 @@ def process_sentinel_1_tile(sentinel1, dates, sess):
     (= their mean) -> 12 monthly composites, as one 12 x n operator applied on the GPU."""
     M, _ = _regrid.s1_monthly_operator(dates)
     return sess.temporal_matmul(sentinel1, M)
+
+
+def identify_clouds_shadows(img, dem, bbx, sess):
+    """src/preprocessing/cloud_removal.py:1215-1677, same arguments and return value
+    `(clouds float32 [T,H,W], fcps bool [T,H,W])`.  `bbx` only positions the optional
+    forestmask.tif / urbanmask.tif rasters, which this tree does not ship (:1131-1135, :1254-1257),
+    so it is accepted and unused: forest and urban masks are zero, exactly the reference's
+    behaviour when those files are absent.  Runs entirely on the GPU (stc_cloud_masks_host)."""
+    del bbx
+    return sess.cloud_masks(img, dem)
 
 
 def identify_bright_bare_surfaces(img, sess):

@@ -1,0 +1,838 @@
+// Multi-temporal cloud / shadow mask, identify_clouds_shadows
+// (src/preprocessing/cloud_removal.py:1215-1677) for the configuration the reference tree runs in
+// (no urbanmask.tif / forestmask.tif: forest mask and potential-false-positive masks are zero).
+// All array arithmetic runs on the device; the host only drives data-dependent control flow
+// (the adaptive threshold loop :1425-1440, the per-date plausibility tests) from scalars the
+// device reduces.  One thread owns one pixel column of T <= 32 dates in registers for the
+// temporal stages; spatial stages are windowed searches with SciPy's border semantics.
+// Stage-by-stage parity is checked against oracle/cloud_ref.py (tests/test_cloud_masks.py).
+#include "stc_common.cuh"
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+
+#define CT_MAX 32
+
+namespace {
+
+struct Buf { void* p = nullptr; ~Buf() { if (p) cudaFree(p); } };
+
+// ---------------------------------------------------------------------------------------------
+// generic spatial primitives on [T][H][W] uint8 masks
+// ---------------------------------------------------------------------------------------------
+// out = inv_out ^ (exists q within L1 (conn 1) / Linf (conn 2) radius k of p, in-image, with (in[q] != 0) ^ inv_in)
+// three_d: the L1 ball also spans the date axis (scipy binary_dilation on a 3-D array, 3-D cross).
+__global__ void __launch_bounds__(256) k_dilate(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int T, int H,
+                                                int W, int k, int conn, int inv_in, int inv_out, int three_d) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)T * H * W) return;
+  int x = (int)(idx % W); int64_t r = idx / W; int y = (int)(r % H); int t = (int)(r / H);
+  unsigned char hit = 0;
+  int dt0 = three_d ? -k : 0, dt1 = three_d ? k : 0;
+  for (int dt = dt0; dt <= dt1 && !hit; ++dt) {
+    int tt = t + dt; if (tt < 0 || tt >= T) continue;
+    int kk = k - abs(dt);
+    const unsigned char* m = in + (int64_t)tt * H * W;
+    for (int dy = -kk; dy <= kk && !hit; ++dy) {
+      int yy = y + dy; if (yy < 0 || yy >= H) continue;
+      int span = conn == 1 ? kk - abs(dy) : kk;
+      for (int dx = -span; dx <= span; ++dx) {
+        int xx = x + dx; if (xx < 0 || xx >= W) continue;
+        if ((m[(int64_t)yy * W + xx] != 0) ^ inv_in) { hit = 1; break; }
+      }
+    }
+  }
+  out[idx] = hit ^ inv_out;
+}
+
+// out = exists non-zero pixel of `in` within Euclidean distance <= radius  (1 - (edt(1 - in) > radius))
+__global__ void __launch_bounds__(256) k_edt_grow(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int T, int H,
+                                                  int W, int radius) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)T * H * W) return;
+  int x = (int)(idx % W); int64_t r = idx / W; int y = (int)(r % H); int t = (int)(r / H);
+  const unsigned char* m = in + (int64_t)t * H * W;
+  const int r2 = radius * radius;
+  unsigned char hit = 0;
+  for (int dy = -radius; dy <= radius && !hit; ++dy) {
+    int yy = y + dy; if (yy < 0 || yy >= H) continue;
+    for (int dx = -radius; dx <= radius; ++dx) {
+      int xx = x + dx; if (xx < 0 || xx >= W) continue;
+      if (dx * dx + dy * dy <= r2 && m[(int64_t)yy * W + xx]) { hit = 1; break; }
+    }
+  }
+  out[idx] = hit;
+}
+
+// 3x3 window sum with np.pad(mode='reflect') borders (cloud_removal.py:1244-1249, windowsize 3)
+__device__ __forceinline__ int winsum3(const unsigned char* m, int y, int x, int H, int W) {
+  int s = 0;
+  for (int dy = -1; dy <= 1; ++dy) {
+    int yy = y + dy; if (yy < 0) yy = -yy; if (yy >= H) yy = 2 * H - 2 - yy;
+    for (int dx = -1; dx <= 1; ++dx) {
+      int xx = x + dx; if (xx < 0) xx = -xx; if (xx >= W) xx = 2 * W - 2 - xx;
+      s += m[(int64_t)yy * W + xx];
+    }
+  }
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small register sorts / order statistics
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void isort(float* v, int n) {
+  for (int i = 1; i < n; ++i) { float x = v[i]; int j = i - 1; while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; } v[j + 1] = x; }
+}
+__device__ __forceinline__ float median_sorted(const float* v, int n) {   // np.median / nanmedian on n valid values
+  if (n == 0) return nanf("");
+  return (n & 1) ? v[n >> 1] : __fmul_rn(__fadd_rn(v[(n >> 1) - 1], v[n >> 1]), 0.5f);
+}
+// np.percentile(a, 25, axis=0) for float32: linear interpolation with NumPy's _lerp in float32
+__device__ __forceinline__ float percentile25_sorted(const float* v, int n) {
+  double vi = 0.25 * (double)(n - 1);
+  int lo = (int)floor(vi);
+  float g = (float)(vi - (double)lo);
+  float a = v[lo], b = v[lo + 1 < n ? lo + 1 : n - 1];
+  float d = __fsub_rn(b, a);
+  return (g >= 0.5f) ? __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.f, g))) : __fadd_rn(a, __fmul_rn(d, g));
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage A: water mask, Hollstein mask, all-date shadow reference, 25th percentiles, minima
+// ---------------------------------------------------------------------------------------------
+struct StaticRefs {
+  float* water;       // [HW]   nanmedian_t NDWI
+  float* allref;      // [HW][4] nanmedian over dates of bands (0,1,7,8) with Hollstein-flagged dates removed
+  float* minb4;       // [HW][4] min over dates of bands (0,1,7,8)
+  float* p25;         // [HW][3] 25th percentile over dates of bands 0,1,2
+  float* minrgb;      // [HW][3] min over dates of bands 0,1,2
+};
+
+__global__ void __launch_bounds__(256) k_hollstein(const float* __restrict__ img, unsigned char* __restrict__ clm, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = img + i * 10;
+  clm[i] = (p[7] > 0.166f) && (p[1] > 0.28f) && (__fdiv_rn(p[5], p[8]) < 4.292f);
+}
+
+__global__ void __launch_bounds__(128) k_static_refs(const float* __restrict__ img, const unsigned char* __restrict__ clm, int T, int HW,
+                                                     StaticRefs o) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  float v[CT_MAX];
+  // water = nanmedian_t (B3 - B8)/(B3 + B8)
+  int n = 0;
+  for (int t = 0; t < T; ++t) {
+    const float* q = img + ((int64_t)t * HW + p) * 10;
+    float x = __fdiv_rn(__fsub_rn(q[1], q[3]), __fadd_rn(q[1], q[3]));
+    if (!isnan(x)) v[n++] = x;
+  }
+  isort(v, n);
+  o.water[p] = median_sorted(v, n);
+  const int bsel[4] = {0, 1, 7, 8};
+  for (int k = 0; k < 4; ++k) {
+    int nn = 0; float mn = INFINITY; float all[CT_MAX];
+    for (int t = 0; t < T; ++t) {
+      float x = img[((int64_t)t * HW + p) * 10 + bsel[k]];
+      all[t] = x; mn = fminf(mn, x);
+      if (!clm[(int64_t)t * HW + p]) v[nn++] = x;
+    }
+    isort(v, nn);
+    float r = median_sorted(v, nn);
+    if (isnan(r)) { isort(all, T); r = median_sorted(all, T); }   // np.median over all dates (:1303-1304)
+    o.allref[p * 4 + k] = r;
+    o.minb4[p * 4 + k] = mn;
+  }
+  for (int k = 0; k < 3; ++k) {
+    float mn = INFINITY;
+    for (int t = 0; t < T; ++t) { float x = img[((int64_t)t * HW + p) * 10 + k]; v[t] = x; mn = fminf(mn, x); }
+    isort(v, T);
+    o.p25[p * 3 + k] = percentile25_sorted(v, T);
+    o.minrgb[p * 3 + k] = mn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage B: per-date shadow candidates (:1265-1324)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shadow_candidates(const float* __restrict__ img, const unsigned char* __restrict__ clm,
+                                                           const float* __restrict__ dem, StaticRefs s, int T, int HW,
+                                                           const int* __restrict__ win_lo, const int* __restrict__ win_hi,
+                                                           unsigned char* __restrict__ shadows) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (p >= HW) return;
+  const int lo = win_lo[t], hi = win_hi[t];
+  const int bsel[4] = {0, 1, 7, 8};
+  float rmed[4], rmax[4];
+  for (int k = 0; k < 4; ++k) {
+    float v[CT_MAX]; int n = 0; float mx = -INFINITY;
+    for (int tt = lo; tt < hi; ++tt) {
+      if (clm[(int64_t)tt * HW + p]) continue;
+      float x = img[((int64_t)tt * HW + p) * 10 + bsel[k]];
+      v[n++] = x; mx = fmaxf(mx, x);
+    }
+    isort(v, n);
+    float m = median_sorted(v, n);
+    rmax[k] = n ? mx : nanf("");
+    rmed[k] = isnan(m) ? s.minb4[p * 4 + k] : m;
+  }
+  const float* x = img + ((int64_t)t * HW + p) * 10;
+  const float water = s.water[p];
+  const bool wpos = water > 0.f;
+  bool sh = (__fsub_rn(x[8], rmed[3]) < -0.04f) && (__fsub_rn(x[7], rmed[2]) < -0.04f) && (x[0] < 0.09f) &&
+            (__fsub_rn(x[0], rmed[0]) < -0.02f) && (x[7] < 0.17f);
+  const bool d8a = __fsub_rn(x[7], rmax[2]) < -0.04f, d11 = __fsub_rn(x[8], rmax[3]) < -0.04f;   // NaN compares false
+  bool dark = d11 && d8a && (x[0] < 0.03f) && (x[7] < 0.18f) && !wpos;
+  sh = (sh || dark) && !wpos;
+  float rgbsum = __fadd_rn(__fadd_rn(x[0], x[1]), x[2]);
+  bool slope = d8a && d11 && (x[0] < 0.07f) && (x[7] < 0.18f) && (rgbsum < 0.28f) && !wpos && (dem[p] >= 25.f);
+  sh = sh || slope;
+  const float* ar = s.allref + p * 4;
+  bool wsh = (__fsub_rn(x[0], ar[0]) < -0.05f) && (__fsub_rn(x[1], ar[1]) < -0.05f) && (x[7] < 0.03f) &&
+             (__fsub_rn(ar[1], x[1]) > 0.02f) && wpos;
+  shadows[(int64_t)t * HW + p] = sh || wsh;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage C: cloud references and candidates (:1342-1447)
+// ---------------------------------------------------------------------------------------------
+struct CloudWin { int others_lo, others_hi; int close[3]; int nclose; };
+
+// per pixel of date t: ri_upper (3), ri_close (3), close_thresh; clouds_i; all from registers
+__global__ void __launch_bounds__(128) k_cloud_refs(const float* __restrict__ img, const unsigned char* __restrict__ shadows,
+                                                    StaticRefs s, int T, int HW, int t, CloudWin w,
+                                                    float* __restrict__ rc_out /*[HW][3]*/, float* __restrict__ thr_out /*[HW]*/,
+                                                    unsigned char* __restrict__ ci_out /*[HW]*/) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  float ref[CT_MAX][3];
+  for (int tt = 0; tt < T; ++tt) {
+    const float* q = img + ((int64_t)tt * HW + p) * 10;
+    bool shd = (T > 2) && shadows[(int64_t)tt * HW + p];
+    for (int k = 0; k < 3; ++k) ref[tt][k] = shd ? nanf("") : q[k];
+  }
+  float up[3], rc[3];
+  if (T > 2) {
+    for (int k = 0; k < 3; ++k) {
+      float m = nanf("");
+      for (int tt = w.others_lo; tt < w.others_hi; ++tt) { float x = ref[tt][k]; if (!isnan(x)) m = isnan(m) ? x : fminf(m, x); }
+      up[k] = m;
+    }
+    if (isnan(up[0])) for (int k = 0; k < 3; ++k) up[k] = s.p25[p * 3 + k];
+    for (int k = 0; k < 3; ++k) {
+      float m = nanf("");
+      for (int c = 0; c < w.nclose; ++c) { int ci_ = w.close[c]; if (ci_ < 0) ci_ += T;   /* Python negative index */
+        float x = ref[ci_][k]; if (!isnan(x)) m = isnan(m) ? x : fminf(m, x); }
+      rc[k] = m;
+    }
+    // progressive widening (:1385-1394): the image-level `any NaN` test only bounds the number of
+    // rounds; per pixel the value is the first widened window that holds a valid date
+    int lo_i = w.close[0], hi_i = w.close[w.nclose - 1];
+    for (int it = 0; it < 10; ++it) {
+      lo_i = lo_i - 1 > 0 ? lo_i - 1 : 0; hi_i = hi_i + 1 < T ? hi_i + 1 : T;
+      for (int k = 0; k < 3; ++k) {
+        if (!isnan(rc[k])) continue;
+        float m = nanf("");
+        for (int tt = lo_i; tt < hi_i; ++tt) { if (tt == t) continue; float x = ref[tt][k]; if (!isnan(x)) m = isnan(m) ? x : fminf(m, x); }
+        rc[k] = m;
+      }
+    }
+    for (int k = 0; k < 3; ++k) if (isnan(rc[k])) rc[k] = s.minrgb[p * 3 + k];
+  } else {
+    for (int k = 0; k < 3; ++k) { float m = INFINITY; for (int tt = 0; tt < T; ++tt) m = fminf(m, ref[tt][k]); rc[k] = m; up[k] = m; }
+  }
+  float thr = __fadd_rn(__fdiv_rn(__fdiv_rn(rc[0], 0.02f), 100.f), 0.005f);
+  thr = fminf(thr, 0.10f); thr = fmaxf(thr, 0.05f); thr = fmaxf(thr, 0.04f);   // forest mask == 0 here
+  const float* x = img + ((int64_t)t * HW + p) * 10;
+  ci_out[p] = (__fsub_rn(x[0], up[0]) > 0.08f) && (__fsub_rn(x[1], up[1]) > 0.08f) && (__fsub_rn(x[2], up[2]) > 0.07f);
+  rc_out[p * 3 + 0] = rc[0]; rc_out[p * 3 + 1] = rc[1]; rc_out[p * 3 + 2] = rc[2];
+  thr_out[p] = thr;
+}
+
+// clouds_close for one modifier value (float32 arithmetic of `thr + mod + 0.01`), + counts
+__global__ void __launch_bounds__(256) k_cloud_close(const float* __restrict__ img, int HW, int t, const float* __restrict__ rc,
+                                                     const float* __restrict__ thr, float mod, unsigned char* __restrict__ cc,
+                                                     int* __restrict__ count) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned char v = 0;
+  if (p < HW) {
+    const float* x = img + ((int64_t)t * HW + p) * 10;
+    float a = __fadd_rn(__fadd_rn(thr[p], mod), 0.01f), b = __fadd_rn(thr[p], mod);
+    v = (__fsub_rn(x[0], rc[p * 3]) > a) && (__fsub_rn(x[1], rc[p * 3 + 1]) > a) && (__fsub_rn(x[2], rc[p * 3 + 2]) > b);
+    cc[p] = v;
+  }
+  unsigned bal = __ballot_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
+}
+
+__global__ void __launch_bounds__(256) k_count(const unsigned char* __restrict__ m, int n, int* __restrict__ count) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned char v = p < n ? m[p] : 0;
+  unsigned bal = __ballot_sync(0xffffffffu, v != 0);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
+}
+
+__global__ void __launch_bounds__(256) k_count_dates(const unsigned char* __restrict__ m, int HW, int* __restrict__ count) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x; const int t = blockIdx.y;
+  unsigned char v = p < HW ? m[(int64_t)t * HW + p] : 0;
+  unsigned bal = __ballot_sync(0xffffffffu, v != 0);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count + t, __popc(bal));
+}
+
+// cc &= (sum rgb < 0.75)
+__global__ void __launch_bounds__(256) k_cc_bright(const float* __restrict__ img, int HW, int t, unsigned char* __restrict__ cc) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float* x = img + ((int64_t)t * HW + p) * 10;
+  cc[p] = cc[p] && (__fadd_rn(__fadd_rn(x[0], x[1]), x[2]) < 0.75f);
+}
+__global__ void __launch_bounds__(256) k_or(const unsigned char* a, const unsigned char* b, unsigned char* o, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] | b[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage D: brightness z-score clouds (:1458-1481) and whiteness filter (:1484-1492)
+// ---------------------------------------------------------------------------------------------
+// exact k-th order statistics of the positive float32 values selected by (clouds==0 && shadows==0),
+// one block per date, MSB-first radix select on the bit patterns
+__global__ void __launch_bounds__(1024) k_masked_median(const float* __restrict__ img, const unsigned char* __restrict__ clouds,
+                                                        const unsigned char* __restrict__ shadows, int HW, float* __restrict__ med) {
+  const int t = blockIdx.x;
+  __shared__ int hist[256]; __shared__ unsigned prefix; __shared__ int kth; __shared__ int total;
+  __shared__ float found[2];
+  auto value = [&](int p, bool& ok) {
+    ok = !clouds[(int64_t)t * HW + p] && !shadows[(int64_t)t * HW + p];
+    const float* x = img + ((int64_t)t * HW + p) * 10;
+    return __fadd_rn(__fadd_rn(x[0], x[1]), x[2]);
+  };
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  int local = 0;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) { bool ok; float v = value(p, ok); if (ok && !isnan(v)) ++local; }
+  atomicAdd(&total, local);
+  __syncthreads();
+  const int n = total;
+  if (n == 0) { if (threadIdx.x == 0) med[t] = nanf(""); return; }
+  for (int which = 0; which < 2; ++which) {
+    if (threadIdx.x == 0) { prefix = 0; kth = (which == 0) ? (n - 1) / 2 : n / 2; }
+    __syncthreads();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      const unsigned pre = prefix;
+      const unsigned mask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+      for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+        bool ok; float v = value(p, ok);
+        if (!ok || isnan(v)) continue;
+        unsigned u = __float_as_uint(v); u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;   // order-preserving key
+        if ((u & mask) == (pre & mask)) atomicAdd(&hist[(u >> shift) & 255], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int k = kth, b = 0;
+        while (k >= hist[b]) { k -= hist[b]; ++b; }
+        kth = k; prefix = pre | ((unsigned)b << shift);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { unsigned u = prefix; u ^= (u >> 31) ? 0x80000000u : 0xffffffffu; found[which] = __uint_as_float(u); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) med[t] = (n & 1) ? found[0] : __fmul_rn(__fadd_rn(found[0], found[1]), 0.5f);
+}
+
+// ---- NumPy-exact float32 mean / std of a masked selection ------------------------------------
+// np.mean / np.std / np.nanmean / np.nanstd on `arr[mask]` (a compacted, contiguous float32 vector)
+// add with NumPy's pairwise summation: blocks of <= 128 elements summed with 8 strided accumulators,
+// halves split at a multiple of 8.  To be bit-identical the selection is compacted in row-major order
+// (k_compact), the recursion's leaves are enumerated, leaf sums are computed in parallel and then
+// combined in recursion order.
+// kind 0: brightness ratio over clouds==0 (or every pixel when all_px[t]); NaN -> 0 and not counted
+// kind 1: 1/blue over clouds==0      kind 2: mean rgb over clouds==0     kind 3: ptp(rgb) over clouds==0
+__global__ void __launch_bounds__(1024) k_compact(const float* __restrict__ img, const unsigned char* __restrict__ clouds,
+                                                  const float* __restrict__ water, const float* __restrict__ medb,
+                                                  const int* __restrict__ all_px, int HW, int kind, float* __restrict__ vals,
+                                                  int* __restrict__ cnts /*[T][2]: slots, valid*/) {
+  const int t = blockIdx.x;
+  __shared__ int wtot[32]; __shared__ int base; __shared__ int nvalid;
+  if (threadIdx.x == 0) { base = 0; nvalid = 0; }
+  __syncthreads();
+  const bool everything = (kind == 0) && all_px && all_px[t];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int p0 = 0; p0 < HW; p0 += 1024) {
+    const int p = p0 + threadIdx.x;
+    bool sel = false; float v = 0.f; bool valid = false;
+    if (p < HW) {
+      sel = everything || !clouds[(int64_t)t * HW + p];
+      if (sel) {
+        const float* x = img + ((int64_t)t * HW + p) * 10;
+        if (kind == 0) { float r = __fdiv_rn(__fadd_rn(__fadd_rn(x[0], x[1]), x[2]), medb[t]); v = (water[p] > 0.f) ? 1.f : r; }
+        else if (kind == 1) v = __fdiv_rn(1.f, x[0]);
+        else if (kind == 2) v = __fdiv_rn(__fadd_rn(__fadd_rn(x[0], x[1]), x[2]), 3.f);
+        else v = __fsub_rn(fmaxf(fmaxf(x[0], x[1]), x[2]), fminf(fminf(x[0], x[1]), x[2]));
+        valid = true;
+        if (kind == 0 && isnan(v)) { v = 0.f; valid = false; }
+      }
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, sel);
+    unsigned balv = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) wtot[wid] = __popc(bal);
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += wtot[w];
+    if (sel) vals[(int64_t)t * HW + base + woff + __popc(bal & ((1u << lane) - 1u))] = v;
+    if (lane == 0 && balv) atomicAdd(&nvalid, __popc(balv));
+    __syncthreads();
+    if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 32; ++w) s += wtot[w]; base += s; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { cnts[2 * t] = base; cnts[2 * t + 1] = nvalid; }
+}
+
+__device__ __forceinline__ float np_leaf_sum(const float* a, int n, int pass, float mean) {
+  auto g = [&](int i) { float v = a[i]; if (pass) { float d = __fsub_rn(v, mean); v = __fmul_rn(d, d); } return v; };
+  if (n < 8) { float r = 0.f; for (int i = 0; i < n; ++i) r = __fadd_rn(r, g(i)); return r; }
+  float r[8];
+  for (int k = 0; k < 8; ++k) r[k] = g(k);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], g(i + k));
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __fadd_rn(res, g(i));
+  return res;
+}
+__device__ float np_combine(const float* leaf, int n) {     // replay of the pairwise recursion over leaf sums (single thread)
+  struct F { int n, stage; float a; };
+  F st[40]; int sp = 0; st[0].n = n; st[0].stage = 0; st[0].a = 0.f;
+  float ret = 0.f; int li = 0;
+  while (sp >= 0) {
+    F& f = st[sp];
+    if (f.n <= 128) { ret = leaf[li++]; --sp; continue; }
+    int n2 = f.n / 2; n2 -= n2 % 8;
+    if (f.stage == 0) { f.stage = 1; ++sp; st[sp].n = n2; st[sp].stage = 0; }
+    else if (f.stage == 1) { f.a = ret; f.stage = 2; ++sp; st[sp].n = f.n - n2; st[sp].stage = 0; }
+    else { ret = __fadd_rn(f.a, ret); --sp; }
+  }
+  return ret;
+}
+// out[t] = {mean, std} as float32 exactly as NumPy computes them (finite inputs; a date whose
+// brightness median is NaN has no valid slot and yields NaN, as np.nanmean / np.nanstd do).
+__global__ void __launch_bounds__(1024) k_np_moments(const float* __restrict__ vals,
+                                                     const int* __restrict__ cnts, int HW, int leaf_cap, int2* __restrict__ leaves,
+                                                     float* __restrict__ leafsum, float* __restrict__ out /*[T][2]*/) {
+  const int t = blockIdx.x;
+  const float* a = vals + (int64_t)t * HW;
+  int2* lv = leaves + (int64_t)t * leaf_cap; float* ls = leafsum + (int64_t)t * leaf_cap;
+  const int n = cnts[2 * t], nvalid = cnts[2 * t + 1];
+  __shared__ int L; __shared__ float mean_s;
+  if (nvalid == 0) { if (threadIdx.x == 0) { out[2 * t] = nanf(""); out[2 * t + 1] = nanf(""); } return; }
+  if (threadIdx.x == 0) {
+    int2 st[40]; int sp = 0; st[0] = make_int2(0, n); int l = 0;
+    while (sp >= 0) {
+      int2 f = st[sp--];
+      if (f.y <= 128) { lv[l++] = f; continue; }
+      int n2 = f.y / 2; n2 -= n2 % 8;
+      st[++sp] = make_int2(f.x + n2, f.y - n2);
+      st[++sp] = make_int2(f.x, n2);
+    }
+    L = l;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 2; ++pass) {
+    const float mean = pass ? mean_s : 0.f;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+      const float* q = a + lv[l].x; const int m = lv[l].y;
+      ls[l] = np_leaf_sum(q, m, pass, mean);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = np_combine(ls, n);
+      float r = (float)((double)s / (double)nvalid);     // float32 / intp -> float64 divide -> float32
+      if (pass == 0) { mean_s = r; out[2 * t] = r; } else out[2 * t + 1] = __fsqrt_rn(r);
+    }
+    __syncthreads();
+  }
+}
+
+// brightness_clouds[t] = (z > 3.5) * (water < 0)
+__global__ void __launch_bounds__(256) k_bright_clouds(const float* __restrict__ img, const float* __restrict__ water,
+                                                       const float* __restrict__ medb, const float* __restrict__ mom, int T, int HW,
+                                                       unsigned char* __restrict__ bc) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x; const int t = blockIdx.y;
+  if (p >= HW) return;
+  const float* x = img + ((int64_t)t * HW + p) * 10;
+  float ratio = __fdiv_rn(__fadd_rn(__fadd_rn(x[0], x[1]), x[2]), medb[t]);
+  if (water[p] > 0.f) ratio = 1.f;
+  float mean = mom[t * 2], sd = mom[t * 2 + 1];
+  float z = __fdiv_rn(__fsub_rn(ratio, mean), sd);
+  bc[(int64_t)t * HW + p] = (z > 3.5f) && (water[p] < 0.f);
+}
+
+// multi = sum_t (bc - clouds) > 0 ; bc[t][multi > 1] = 0 ; clouds = max(clouds, bc) ; whiteness filter
+__global__ void __launch_bounds__(256) k_bright_merge(const float* __restrict__ img, const unsigned char* __restrict__ bc, int T, int HW,
+                                                      unsigned char* __restrict__ clouds) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  int multi = 0;
+  for (int t = 0; t < T; ++t) multi += (bc[(int64_t)t * HW + p] && !clouds[(int64_t)t * HW + p]);
+  for (int t = 0; t < T; ++t) {
+    unsigned char c = clouds[(int64_t)t * HW + p] | ((multi > 1) ? 0 : bc[(int64_t)t * HW + p]);
+    const float* x = img + ((int64_t)t * HW + p) * 10;
+    float mb = __fdiv_rn(__fadd_rn(__fadd_rn(x[0], x[1]), x[2]), 3.f);
+    float vr = __fsub_rn(fmaxf(fmaxf(x[0], x[1]), x[2]), fminf(fminf(x[0], x[1]), x[2]));
+    bool fp = (mb < 0.4f) && (__fdiv_rn(vr, mb) > 0.5f);
+    clouds[(int64_t)t * HW + p] = c && !fp;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage E: false-positive removal (:1514-1551)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nsr(const float* __restrict__ img, unsigned char* __restrict__ nsr, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = img + i * 10;
+  nsr[i] = __fdiv_rn(p[3], __fadd_rn(p[8], 0.01f)) < 0.75f;
+}
+// nsr[t][water<0] = 0 ; clouds[t][nsr & isnt_cloud] = 0 ; water/B11 candidate for the next stage
+__global__ void __launch_bounds__(256) k_fp1(const float* __restrict__ img, const float* __restrict__ water, int T, int HW,
+                                             unsigned char* __restrict__ nsr, unsigned char* __restrict__ clouds,
+                                             unsigned char* __restrict__ wfp) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x; const int t = blockIdx.y;
+  if (p >= HW) return;
+  const int lo = t - 1 > 0 ? t - 1 : 0, hi = t + 2 < T ? t + 2 : T;
+  float bmin = INFINITY;
+  for (int tt = lo; tt < hi; ++tt) { const float* q = img + ((int64_t)tt * HW + p) * 10; bmin = fminf(bmin, fminf(fminf(q[0], q[1]), q[2])); }
+  const float* x = img + ((int64_t)t * HW + p) * 10;
+  float bi = __fdiv_rn(__fadd_rn(__fadd_rn(x[0], x[1]), x[2]), 3.f);
+  bool isnt = __fsub_rn(bi, bmin) < 0.4f;
+  int64_t i = (int64_t)t * HW + p;
+  unsigned char ns = nsr[i]; if (water[p] < 0.f) ns = 0; nsr[i] = ns;
+  if (ns && isnt) clouds[i] = 0;
+  wfp[i] = (water[p] > 0.f) && (x[8] < 0.11f);
+}
+__global__ void __launch_bounds__(256) k_clear_where(unsigned char* __restrict__ clouds, const unsigned char* __restrict__ m, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && m[i]) clouds[i] = 0;
+}
+__global__ void __launch_bounds__(256) k_winsum_lt(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int T, int H,
+                                                   int W, int thresh) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)T * H * W) return;
+  int x = (int)(idx % W); int64_t r = idx / W; int y = (int)(r % H); int t = (int)(r / H);
+  const unsigned char* m = in + (int64_t)t * H * W;
+  out[idx] = (winsum3(m, y, x, H, W) < thresh) ? 0 : m[(int64_t)y * W + x];
+}
+__global__ void __launch_bounds__(256) k_dark(const float* __restrict__ img, unsigned char* __restrict__ o, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = img + i * 10;
+  o[i] = __fadd_rn(__fadd_rn(p[0], p[1]), p[2]) < 0.21f;
+}
+// `clouds[i][brightness_threshold.astype(uint8)] = 0` (:1546-1551) is integer fancy indexing: it zeroes
+// ROW 0 of the date if any mask pixel is 0 and ROW 1 if any is 1.  flags[t] = {any zero, any one}.
+__global__ void __launch_bounds__(256) k_any01(const unsigned char* __restrict__ m, int HW, int* __restrict__ flags) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x; const int t = blockIdx.y;
+  if (p >= HW) return;
+  if (m[(int64_t)t * HW + p]) flags[2 * t + 1] = 1; else flags[2 * t] = 1;
+}
+__global__ void __launch_bounds__(256) k_zero_rows(unsigned char* __restrict__ clouds, const int* __restrict__ flags, int H, int W) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x; const int t = blockIdx.y;
+  if (x >= W) return;
+  if (flags[2 * t]) clouds[((int64_t)t * H + 0) * W + x] = 0;
+  if (flags[2 * t + 1] && H > 1) clouds[((int64_t)t * H + 1) * W + x] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage F: shape clean-up (:1590-1612) with pfcps == 0
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_split_size(const unsigned char* __restrict__ c, unsigned char* __restrict__ large,
+                                                    unsigned char* __restrict__ small, int T, int H, int W) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)T * H * W) return;
+  int x = (int)(idx % W); int64_t r = idx / W; int y = (int)(r % H); int t = (int)(r / H);
+  const unsigned char* m = c + (int64_t)t * H * W;
+  int ws = winsum3(m, y, x, H, W);
+  unsigned char v = m[(int64_t)y * W + x];
+  large[idx] = (ws < 6) ? 0 : v;
+  small[idx] = (ws >= 6) ? 0 : v;
+}
+__global__ void __launch_bounds__(256) k_and_or_dem(unsigned char* __restrict__ shadows, const unsigned char* __restrict__ near,
+                                                    const float* __restrict__ dem, int HW) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  if (!(near[p] || dem[p] >= 30.f)) shadows[p] = 0;
+}
+// dark-blue shadow candidates of one date: 1/B2 > ref && B8A < 0.17
+__global__ void __launch_bounds__(256) k_darkblue(const float* __restrict__ img, int HW, int t, float ref, unsigned char* __restrict__ o) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float* x = img + ((int64_t)t * HW + p) * 10;
+  o[p] = (__fdiv_rn(1.f, x[0]) > ref) && (x[7] < 0.17f);
+}
+__global__ void __launch_bounds__(256) k_or_nowater(unsigned char* __restrict__ clouds, const unsigned char* __restrict__ s,
+                                                    const float* __restrict__ water, int HW) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  if (s[p] && !(water[p] > 0.f)) clouds[p] = 1;
+}
+__global__ void __launch_bounds__(256) k_fill(unsigned char* p, int64_t n, unsigned char v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void __launch_bounds__(256) k_to_float(const unsigned char* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] ? 1.f : 0.f;
+}
+
+float median_host(std::vector<float> v) {            // np.median of a short float32 list (NaN propagates)
+  for (float x : v) if (x != x) return x;
+  std::sort(v.begin(), v.end());
+  size_t n = v.size();
+  volatile float s = (n & 1) ? v[n / 2] : v[n / 2 - 1] + v[n / 2];
+  return (n & 1) ? s : s / 2.f;
+}
+
+}  // namespace
+
+#include <algorithm>
+
+// windows of cloud_removal.py:1266-1273 and :1343-1361 (integer logic, host)
+static void shadow_window(int t, int T, int& lo, int& hi) {
+  lo = t - 4 > 0 ? t - 4 : 0; hi = t + 3 < T ? t + 3 : T;
+  if (hi - lo == 3) { if (hi == T) lo = lo - 1 > 0 ? lo - 1 : 0; if (lo == 0) hi = hi + 1 < T ? hi + 1 : T; }
+}
+static CloudWin cloud_window(int t, int T) {
+  CloudWin w; memset(&w, 0, sizeof(w));
+  int lo = t - 2 > 0 ? t - 2 : 0, hi = t + 3 < T ? t + 3 : T;
+  if (hi - lo == 3) { if (hi == T) lo = lo - 2 > 0 ? lo - 2 : 0; if (lo == 0) hi = hi + 2 < T ? hi + 2 : T; }
+  w.others_lo = lo; w.others_hi = hi;
+  int c0 = t - 1 > 0 ? t - 1 : 0, c1 = t + 1 < T - 1 ? t + 1 : T - 1;
+  if (c1 - c0 < 2) { if (c0 == 0) { c0 += 1; c1 += 1; } else { c0 -= 1; c1 -= 1; } }
+  if (c1 >= T - 2 && T > 3) { w.close[0] = c0 - 1; w.close[1] = c0; w.close[2] = c1; w.nclose = 3; }
+  else { w.close[0] = c0; w.close[1] = c1; w.nclose = 2; }
+  return w;
+}
+
+#define LAUNCH1D(kern, n, ...) do { kern<<<cdiv((n), 256), 256, 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
+
+extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const float* dem_host, int T, int H, int W,
+                                    float* clouds_host, uint8_t* fcps_host, uint8_t* stage_host, int stage_id) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!img_host || !dem_host || !clouds_host || !fcps_host || T < 1 || T > CT_MAX || H < 3 || W < 3)
+    STC_FAIL(STC_ERR_ARG, "cloud_masks: bad argument (1 <= T <= 32)");
+  const int HW = H * W; const int64_t N = (int64_t)T * HW;
+  Buf d_img, d_dem, d_clm, d_a, d_b, d_c, d_sh, d_cl, d_bc, d_nsr, d_water, d_allref, d_minb4, d_p25, d_minrgb, d_rc, d_thr,
+      d_ci, d_cc, d_cnt, d_win, d_med, d_mom, d_flags, d_all, d_out, d_vals, d_leaves, d_leafsum, d_cnts;
+  STC_CUDA(cudaMalloc(&d_img.p, N * 40)); STC_CUDA(cudaMalloc(&d_dem.p, HW * 4));
+  for (Buf* b : {&d_clm, &d_a, &d_b, &d_c, &d_sh, &d_cl, &d_bc, &d_nsr}) STC_CUDA(cudaMalloc(&b->p, N));
+  STC_CUDA(cudaMalloc(&d_water.p, HW * 4)); STC_CUDA(cudaMalloc(&d_allref.p, HW * 16)); STC_CUDA(cudaMalloc(&d_minb4.p, HW * 16));
+  STC_CUDA(cudaMalloc(&d_p25.p, HW * 12)); STC_CUDA(cudaMalloc(&d_minrgb.p, HW * 12)); STC_CUDA(cudaMalloc(&d_rc.p, HW * 12));
+  STC_CUDA(cudaMalloc(&d_thr.p, HW * 4)); STC_CUDA(cudaMalloc(&d_ci.p, HW)); STC_CUDA(cudaMalloc(&d_cc.p, HW));
+  STC_CUDA(cudaMalloc(&d_cnt.p, 64)); STC_CUDA(cudaMalloc(&d_win.p, 2 * CT_MAX * 4)); STC_CUDA(cudaMalloc(&d_med.p, CT_MAX * 4));
+  STC_CUDA(cudaMalloc(&d_mom.p, CT_MAX * 2 * 4)); STC_CUDA(cudaMalloc(&d_flags.p, 2 * CT_MAX * 4)); STC_CUDA(cudaMalloc(&d_all.p, CT_MAX * 4));
+  STC_CUDA(cudaMalloc(&d_out.p, N * 4));
+  const int leaf_cap = HW / 32 + 8;
+  STC_CUDA(cudaMalloc(&d_vals.p, N * 4)); STC_CUDA(cudaMalloc(&d_leaves.p, (size_t)T * leaf_cap * 8));
+  STC_CUDA(cudaMalloc(&d_leafsum.p, (size_t)T * leaf_cap * 4)); STC_CUDA(cudaMalloc(&d_cnts.p, CT_MAX * 2 * 4));
+  const float* img = (const float*)d_img.p; const float* dem = (const float*)d_dem.p;
+  unsigned char *clm = (unsigned char*)d_clm.p, *ta = (unsigned char*)d_a.p, *tb = (unsigned char*)d_b.p, *tc = (unsigned char*)d_c.p,
+                *sh = (unsigned char*)d_sh.p, *cl = (unsigned char*)d_cl.p, *bc = (unsigned char*)d_bc.p, *nsr = (unsigned char*)d_nsr.p;
+  STC_CUDA(cudaMemcpyAsync(d_img.p, img_host, N * 40, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(d_dem.p, dem_host, HW * 4, cudaMemcpyHostToDevice, ctx->stream));
+  StaticRefs sr{(float*)d_water.p, (float*)d_allref.p, (float*)d_minb4.p, (float*)d_p25.p, (float*)d_minrgb.p};
+  const float* water = sr.water;
+  auto dilate = [&](const unsigned char* in, unsigned char* out, int64_t frames, int k, int conn, int inv_in, int inv_out, int three_d) {
+    k_dilate<<<cdiv(frames * HW, 256), 256, 0, ctx->stream>>>(in, out, (int)frames, H, W, k, conn, inv_in, inv_out, three_d);
+    ctx->launches++;
+  };
+  auto dump = [&](int id, const unsigned char* src) -> int {     // stage taps for the tests
+    if (stage_host && stage_id == id) {
+      STC_CUDA(cudaMemcpyAsync(stage_host, src, N, cudaMemcpyDeviceToHost, ctx->stream));
+      STC_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return STC_OK;
+  };
+  // NumPy-exact float32 {mean, std} of f_kind over the clear pixels of every date -> mom_h[t*2..], cnt_h[t*2..]
+  std::vector<float> mom_h(2 * CT_MAX); std::vector<int> cnt_h(2 * CT_MAX);
+  auto moments = [&](int kind, const float* medb, const int* all_px, bool to_host) -> int {
+    k_compact<<<T, 1024, 0, ctx->stream>>>(img, cl, water, medb, all_px, HW, kind, (float*)d_vals.p, (int*)d_cnts.p);
+    k_np_moments<<<T, 1024, 0, ctx->stream>>>((const float*)d_vals.p, (const int*)d_cnts.p, HW, leaf_cap, (int2*)d_leaves.p,
+                                              (float*)d_leafsum.p, (float*)d_mom.p);
+    ctx->launches += 2;
+    if (to_host) {
+      STC_CUDA(cudaMemcpyAsync(mom_h.data(), d_mom.p, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      STC_CUDA(cudaMemcpyAsync(cnt_h.data(), d_cnts.p, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      STC_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return STC_OK;
+  };
+  int rc_;
+
+  // ---- A: Hollstein mask (erode 2, dilate 10), static per-pixel references ----
+  LAUNCH1D(k_hollstein, N, img, ta, N);
+  dilate(ta, tb, T, 2, 1, 1, 1, 0);
+  dilate(tb, clm, T, 10, 1, 0, 0, 0);
+  k_static_refs<<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, clm, T, HW, sr); ctx->launches++;
+  if ((rc_ = dump(1, clm))) return rc_;
+
+  // ---- B: shadows ----
+  {
+    int wl[2 * CT_MAX];
+    for (int t = 0; t < T; ++t) shadow_window(t, T, wl[t], wl[CT_MAX + t]);
+    STC_CUDA(cudaMemcpyAsync(d_win.p, wl, sizeof(wl), cudaMemcpyHostToDevice, ctx->stream));
+    k_shadow_candidates<<<dim3(cdiv(HW, 128), T), 128, 0, ctx->stream>>>(img, clm, dem, sr, T, HW, (const int*)d_win.p,
+                                                                         (const int*)d_win.p + CT_MAX, ta);
+    ctx->launches++;
+    STC_CUDA(cudaStreamSynchronize(ctx->stream));   // wl is a stack buffer
+    if ((rc_ = dump(2, ta))) return rc_;
+    dilate(ta, tb, T, 2, 1, 1, 1, 0);
+    dilate(tb, tc, T, 3, 1, 0, 0, 0);
+    LAUNCH1D(k_edt_grow, N, tc, sh, T, H, W, 5);
+    if ((rc_ = dump(3, sh))) return rc_;
+  }
+
+  // ---- C: clouds ----
+  for (int t = 0; t < T; ++t) {
+    CloudWin w = cloud_window(t, T);
+    k_cloud_refs<<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, sh, sr, T, HW, t, w, (float*)d_rc.p, (float*)d_thr.p, (unsigned char*)d_ci.p);
+    ctx->launches++;
+    int cnt[2] = {0, 0};
+    STC_CUDA(cudaMemsetAsync(d_cnt.p, 0, 8, ctx->stream));
+    LAUNCH1D(k_count, HW, (const unsigned char*)d_ci.p, HW, (int*)d_cnt.p);
+    double mean_i = 0.0, mean_c = 1.0, mod = 0.0;
+    bool first = true;
+    while ((mean_c - mean_i) > 0.075) {
+      STC_CUDA(cudaMemsetAsync((int*)d_cnt.p + 1, 0, 4, ctx->stream));
+      LAUNCH1D(k_cloud_close, HW, img, HW, t, (const float*)d_rc.p, (const float*)d_thr.p, (float)mod, (unsigned char*)d_cc.p, (int*)d_cnt.p + 1);
+      STC_CUDA(cudaMemcpyAsync(cnt, d_cnt.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      STC_CUDA(cudaStreamSynchronize(ctx->stream));
+      mean_i = (double)cnt[0] / HW; mean_c = (double)cnt[1] / HW;
+      mod += 0.0025; first = false;
+      if (mod > 10.0) STC_FAIL(STC_ERR_STATE, "cloud_masks: threshold loop did not converge");
+    }
+    (void)first;
+    LAUNCH1D(k_cc_bright, HW, img, HW, t, (unsigned char*)d_cc.p);
+    dilate((const unsigned char*)d_cc.p, ta, 1, 2, 1, 1, 1, 0);                 // erode 2 (forest mask == 0 everywhere)
+    LAUNCH1D(k_or, HW, (const unsigned char*)d_ci.p, ta, cl + (int64_t)t * HW, (int64_t)HW);
+  }
+  if ((rc_ = dump(4, cl))) return rc_;
+
+  // ---- D: brightness z-score + whiteness ----
+  {
+    k_masked_median<<<T, 1024, 0, ctx->stream>>>(img, cl, sh, HW, (float*)d_med.p); ctx->launches++;
+    // `if np.sum(clouds[i] < 0.90)`: select clear pixels when any exists, else every pixel
+    int allpx[CT_MAX];
+    STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
+    k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(cl, HW, (int*)d_all.p); ctx->launches++;
+    STC_CUDA(cudaMemcpyAsync(allpx, d_all.p, T * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    STC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int t = 0; t < T; ++t) allpx[t] = (allpx[t] == HW);
+    STC_CUDA(cudaMemcpyAsync(d_all.p, allpx, T * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc_ = moments(0, (const float*)d_med.p, (const int*)d_all.p, false))) return rc_;
+    k_bright_clouds<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(img, water, (const float*)d_med.p, (const float*)d_mom.p, T, HW, bc);
+    ctx->launches++;
+    LAUNCH1D(k_bright_merge, HW, img, bc, T, HW, cl);
+    STC_CUDA(cudaStreamSynchronize(ctx->stream));   // allpx is a stack buffer
+    if ((rc_ = dump(5, cl))) return rc_;
+  }
+
+  // ---- E: false positives ----
+  LAUNCH1D(k_nsr, N, img, ta, N);
+  dilate(ta, nsr, T, 3, 1, 0, 0, 1);                                            // 3-D dilation (:1518)
+  k_fp1<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(img, water, T, HW, nsr, cl, ta); ctx->launches++;
+  dilate(ta, tb, T, 10, 1, 0, 0, 0);
+  LAUNCH1D(k_clear_where, N, cl, tb, N);
+  LAUNCH1D(k_winsum_lt, N, cl, ta, T, H, W, 5);
+  STC_CUDA(cudaMemcpyAsync(cl, ta, N, cudaMemcpyDeviceToDevice, ctx->stream));
+  LAUNCH1D(k_dark, N, img, ta, N);
+  dilate(ta, tb, T, 3, 1, 0, 0, 0);
+  STC_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * CT_MAX * 4, ctx->stream));
+  k_any01<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tb, HW, (int*)d_flags.p); ctx->launches++;
+  k_zero_rows<<<dim3(cdiv(W, 256), T), 256, 0, ctx->stream>>>(cl, (const int*)d_flags.p, H, W); ctx->launches++;
+  if ((rc_ = dump(6, cl))) return rc_;
+
+  // ---- F: shape clean-up (pfcps == 0: no urban clouds) ----
+  dilate(cl, ta, T, 1, 1, 1, 1, 0);                                             // erode 1
+  LAUNCH1D(k_split_size, N, ta, tb, tc, T, H, W);                               // tb = large, tc = small
+  dilate(tc, cl, T, 1, 1, 0, 0, 0);
+  dilate(tb, ta, T, 5, 1, 0, 0, 0);
+  LAUNCH1D(k_or, N, cl, ta, tb, N);
+  LAUNCH1D(k_edt_grow, N, tb, cl, T, H, W, 3);
+  if ((rc_ = dump(7, cl))) return rc_;
+
+  // ---- G: shadow plausibility (:1617-1626), per date on scalar means ----
+  for (int t = 0; t < T; ++t) {
+    int c2[2] = {0, 0};
+    STC_CUDA(cudaMemsetAsync(d_cnt.p, 0, 8, ctx->stream));
+    LAUNCH1D(k_count, HW, sh + (int64_t)t * HW, HW, (int*)d_cnt.p);
+    LAUNCH1D(k_count, HW, cl + (int64_t)t * HW, HW, (int*)d_cnt.p + 1);
+    STC_CUDA(cudaMemcpyAsync(c2, d_cnt.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    STC_CUDA(cudaStreamSynchronize(ctx->stream));
+    // np.mean of a float32 0/1 array: exact for these sizes
+    float ms = (float)((double)c2[0] / HW), mc = (float)((double)c2[1] / HW);
+    auto restrict_far = [&]() -> int {
+      const unsigned char* src = cl + (int64_t)t * HW; unsigned char* dst = ta;
+      for (int it = 0; it < 5; ++it) {                                          // 50 cross iterations = 5 x L1 radius 10
+        dilate(src, dst, 1, 10, 1, 0, 0, 0);
+        src = dst; dst = (dst == ta) ? tb : ta;
+      }
+      LAUNCH1D(k_and_or_dem, HW, sh + (int64_t)t * HW, src, dem, HW);
+      return STC_OK;
+    };
+    if (ms > (mc + 0.3f) && mc < 0.3f) restrict_far();
+    if (mc < 0.05f) {
+      STC_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4, ctx->stream));
+      LAUNCH1D(k_count, HW, sh + (int64_t)t * HW, HW, (int*)d_cnt.p);
+      STC_CUDA(cudaMemcpyAsync(c2, d_cnt.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      STC_CUDA(cudaStreamSynchronize(ctx->stream));
+      float ms2 = (float)((double)c2[0] / HW);
+      if ((ms2 / mc) > 3.f) restrict_far();                                     // mc == 0: inf > 3 (or nan: false), as NumPy
+    }
+  }
+  LAUNCH1D(k_or, N, cl, sh, cl, N);
+  dilate(nsr, tc, T, 2, 1, 0, 0, 1);                                            // fcps = dilate3d(max(0, nsr), 2)
+  STC_CUDA(cudaMemcpyAsync(fcps_host, tc, N, cudaMemcpyDeviceToHost, ctx->stream));
+
+  // ---- H: dark-blue shadow recovery (:1638-1648) ----
+  {
+    if ((rc_ = moments(1, nullptr, nullptr, true))) return rc_;
+    for (int t = 0; t < T; ++t) {
+      float frac = (float)((double)(HW - cnt_h[2 * t]) / HW);                   // np.mean(clouds[t]) as float32
+      if (!(frac < 0.9f)) continue;
+      volatile float two_sd = 2.f * mom_h[2 * t + 1];
+      float ref = mom_h[2 * t] + two_sd;
+      LAUNCH1D(k_darkblue, HW, img, HW, t, ref, ta);
+      dilate(ta, tb, 1, 2, 1, 1, 1, 0);
+      dilate(tb, ta, 1, 2, 1, 0, 0, 0);
+      LAUNCH1D(k_or_nowater, HW, cl + (int64_t)t * HW, ta, water, HW);
+    }
+    if ((rc_ = dump(8, cl))) return rc_;
+  }
+
+  // ---- I: haze (:1652-1676), float32 list arithmetic as NumPy does it ----
+  {
+    std::vector<float> meanb, stdb, stdw;
+    if ((rc_ = moments(2, nullptr, nullptr, true))) return rc_;
+    std::vector<float> mb(mom_h.begin(), mom_h.begin() + 2 * T); std::vector<int> nclear(T);
+    for (int t = 0; t < T; ++t) nclear[t] = cnt_h[2 * t];
+    if ((rc_ = moments(3, nullptr, nullptr, true))) return rc_;
+    for (int t = 0; t < T; ++t)
+      if (nclear[t] > 0) { meanb.push_back(mb[2 * t]); stdb.push_back(mb[2 * t + 1]); stdw.push_back(mom_h[2 * t + 1]); }
+    if (!meanb.empty()) {
+      const float m1 = median_host(meanb), m2 = median_host(stdb), m3 = median_host(stdw);
+      for (size_t k = 0; k < meanb.size(); ++k) {        // the reference indexes `haze` by list position, not by date (:1674-1676)
+        volatile float hb = meanb[k] / m1, hs = stdb[k] / m2, hw = stdw[k] / m3;
+        bool haze = ((hb >= 1.5f) && (hs <= 0.67f) && (hw < 1.f)) || ((hb >= 1.3f) && (hs <= 0.5f));
+        if (haze) LAUNCH1D(k_fill, HW, cl + (int64_t)k * HW, (int64_t)HW, (unsigned char)1);
+      }
+    }
+  }
+  LAUNCH1D(k_to_float, N, cl, (float*)d_out.p, N);
+  STC_CUDA(cudaGetLastError());
+  STC_CUDA(cudaMemcpyAsync(clouds_host, d_out.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
