@@ -92,6 +92,36 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+_T0 = time.time()
+
+
+def _log(msg):
+    print("[bench %6.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
+def _host_cores():
+    """Usable physical cores: affinity mask, halved when SMT siblings are listed, capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        info = open("/proc/cpuinfo").read()
+        sib = int(info.split("siblings")[1].split(":")[1].split()[0])
+        cores = int(info.split("cpu cores")[1].split(":")[1].split()[0])
+        if sib > cores:
+            n = max(1, n // (sib // cores))
+    except Exception:
+        pass
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_reference_tiles_per_s(n_tiles, seed=1234):
     """The oracle port of the same step on the host cores (torch-CPU restatement of the frozen
     graph + NumPy preprocessing).  TF CPU session substituted by a torch-CPU restatement of the
@@ -101,11 +131,11 @@ def cpu_reference_tiles_per_s(n_tiles, seed=1234):
     from oracle.model_ref import PredictRef
     from sentinel_tree_cover_b200.api import MIN_ALL, MAX_ALL
     from sentinel_tree_cover_b200.weights import random_predict_weights
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
-    try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except Exception:
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can.
+    # torch's own default (physical cores) is left alone; only a forced single thread is raised.
+    if torch.get_num_threads() == 1:
+        torch.set_num_threads(_host_cores())
+    _log("cpu baseline: %d tiles on %d threads" % (n_tiles, torch.get_num_threads()))
     model = PredictRef(random_predict_weights(0))
     m = P.synth_monthly(1, H, seed)
     t0 = time.time()
@@ -193,6 +223,7 @@ def main():
             dist.barrier()
 
     # ---- device-resident timing (value) ----
+    _log("inputs resident; warm-up")
     for _ in range(args.warmup):
         sess.predict_patches_dev(d_in, B, H, H, d_out)
     barrier()
@@ -211,6 +242,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     # ---- end-to-end through the host-buffer C-ABI (e2e) ----
+    _log("device-resident timing done (%.1f ms/step); e2e" % (ms / args.steps))
     for _ in range(1):
         sess.predict_patches(host_in, out=host_out)
     barrier()
@@ -224,6 +256,7 @@ def main():
     ms_e2e = max(ms_e2e, wall_e2e)           # the host-buffer call is synchronous: take the larger clock
     checksum = float(host_out.astype(np.float64).sum())
     # ---- same, with the patches in the reference's uint16 storage convention (x/65535) ----
+    _log("e2e done; uint16 e2e")
     host_u16 = sess.pinned_empty((B, 12, H, H, 13), np.uint16)
     for i in range(B):
         host_u16[i] = np.clip(np.rint(host_in[i] * 65535.0), 0, 65535).astype(np.uint16)
