@@ -46,14 +46,18 @@ __global__ void __launch_bounds__(256) k_dilate(const unsigned char* __restrict_
   out[idx] = hit ^ inv_out;
 }
 
-// out = exists non-zero pixel of `in` within Euclidean distance <= radius  (1 - (edt(1 - in) > radius))
+// out = exists non-zero pixel of `in` within Euclidean distance <= radius  (1 - (edt(1 - in) > radius)).
+// A frame with no non-zero pixel has no background for scipy's distance_transform_edt, which then
+// measures from the virtual site (row -1, column 0): d^2 = (y+1)^2 + x^2 (scipy 1.x feature-transform
+// initialisation; pinned by tests/test_cloud_masks.py against the reference run in this image).
 __global__ void __launch_bounds__(256) k_edt_grow(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int T, int H,
-                                                  int W, int radius) {
+                                                  int W, int radius, const int* __restrict__ frame_count) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)T * H * W) return;
   int x = (int)(idx % W); int64_t r = idx / W; int y = (int)(r % H); int t = (int)(r / H);
   const unsigned char* m = in + (int64_t)t * H * W;
   const int r2 = radius * radius;
+  if (frame_count[t] == 0) { out[idx] = ((y + 1) * (y + 1) + x * x) <= r2; return; }
   unsigned char hit = 0;
   for (int dy = -radius; dy <= radius && !hit; ++dy) {
     int yy = y + dy; if (yy < 0 || yy >= H) continue;
@@ -690,7 +694,9 @@ extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const f
     if ((rc_ = dump(2, ta))) return rc_;
     dilate(ta, tb, T, 2, 1, 1, 1, 0);
     dilate(tb, tc, T, 3, 1, 0, 0, 0);
-    LAUNCH1D(k_edt_grow, N, tc, sh, T, H, W, 5);
+    STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
+    k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tc, HW, (int*)d_all.p); ctx->launches++;
+    LAUNCH1D(k_edt_grow, N, tc, sh, T, H, W, 5, (const int*)d_all.p);
     if ((rc_ = dump(3, sh))) return rc_;
   }
 
@@ -760,7 +766,9 @@ extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const f
   dilate(tc, cl, T, 1, 1, 0, 0, 0);
   dilate(tb, ta, T, 5, 1, 0, 0, 0);
   LAUNCH1D(k_or, N, cl, ta, tb, N);
-  LAUNCH1D(k_edt_grow, N, tb, cl, T, H, W, 3);
+  STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
+  k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tb, HW, (int*)d_all.p); ctx->launches++;
+  LAUNCH1D(k_edt_grow, N, tb, cl, T, H, W, 3, (const int*)d_all.p);
   if ((rc_ = dump(7, cl))) return rc_;
 
   // ---- G: shadow plausibility (:1617-1626), per date on scalar means ----
