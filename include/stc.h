@@ -172,6 +172,27 @@ int stc_binary_dilate_host(stc_ctx* ctx, const uint8_t* in_host, int n, int H, i
  *       cap 3/5: cloud_removal.py:1333-1336,1608-1611).  target [n,H,W] uint8 -> int32. ---- */
 int stc_edt_sq_host(stc_ctx* ctx, const uint8_t* target_host, int n, int H, int W, int radius, int32_t* out_host);
 
+/* ---- missing-pixel bookkeeping: id_missing_px (src/preprocessing/interpolation.py:5-23) and the NaN-date
+ *      test of deal_w_missing_px (src/download_and_predict_job.py:1048).  arr [n,H,W,C] float32.
+ *      bad_px[t] = number of pixels of date t with more than one of the first 10 bands == 0 or >= 1;
+ *      nan_vals[t] = number of NaN values of date t.  The caller applies the thresholds. ---- */
+int stc_missing_px_host(stc_ctx* ctx, const float* arr_host, int n, int H, int W, int C, int32_t* bad_px_host,
+                        int32_t* nan_vals_host);
+
+/* ---- temporal median fill of the 0 / 1 sentinels, deal_w_missing_px (src/download_and_predict_job.py:1039-1047):
+ *      in date order, every value == 0 is replaced by the CURRENT np.median over dates of its pixel-band
+ *      column (earlier dates already filled), then the same for values == 1.  arr [n,H,W,C] float32 in
+ *      place, n <= 96; nan_vals[t] = NaN values of date t afterwards. ---- */
+int stc_median_fill_host(stc_ctx* ctx, float* arr_host, int n, int H, int W, int C, int32_t* nan_vals_host);
+
+/* ---- 20 m / 40 m -> 10 m band stack of process_tile (src/download_and_predict_job.py:743-782):
+ *      out[...,0:4] = s2_10; out[...,4:8] = bilinear x2 of the four 20 m bands; out[...,8:10] = 2x2 mean
+ *      pool then bilinear of the two 40 m bands, with the odd-shape cases of :760-782.  Bilinear =
+ *      skimage.transform.resize(order=1) = scipy.ndimage.zoom(order=1, mode='mirror', grid_mode=True).
+ *      s2_10 [n,2h,2w,4], s2_20 [n,h,w,6] -> out [n,2h,2w,10] float32. ---- */
+int stc_build_sentinel2_host(stc_ctx* ctx, const float* s2_10_host, const float* s2_20_host, int n, int h, int w,
+                             float* out_host);
+
 /* ---- multi-temporal cloud / shadow mask: identify_clouds_shadows(img, dem, bbx)
  *      (src/preprocessing/cloud_removal.py:1215-1677) in the configuration the reference tree runs in
  *      (forestmask.tif / urbanmask.tif absent: forest and potential-false-positive masks are zero).

@@ -98,7 +98,8 @@ def install():
     def resize(img, shape, order=1, **kw):
         img = np.asarray(img)
         zoom = [s / float(i) for s, i in zip(shape, img.shape)]
-        return ndi.zoom(img, zoom, order=order, mode="nearest" if order == 0 else "reflect",
+        # skimage's default mode 'reflect' is ndimage's 'mirror' (skimage.transform._warps._to_ndimage_mode)
+        return ndi.zoom(img, zoom, order=order, mode="nearest" if order == 0 else "mirror",
                         grid_mode=True, prefilter=False)
     sys.modules["skimage.transform"].resize = resize
 

@@ -82,6 +82,9 @@ SYMBOLS = [
     ("stc_feather_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_binary_dilate_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_edt_sq_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_missing_px_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    ("stc_median_fill_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_build_sentinel2_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_cloud_masks_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int]),
     ("stc_debug_read", C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p]),
@@ -362,6 +365,36 @@ class StcSession:
         self._check(self.lib.stc_edt_sq_host(self.h, _dptr(a3), a3.shape[0], shp[-2], shp[-1], int(np.ceil(cap)), _dptr(d2)))
         return np.minimum(np.sqrt(d2.astype(np.float64)), float(cap)).reshape(shp)
 
+    def missing_px_counts(self, arr):
+        """Per date of arr [n,H,W,C]: (#pixels with >1 of the first 10 bands == 0 or >= 1, #NaN values)."""
+        a = np.ascontiguousarray(arr, np.float32)
+        n, H, W, Cc = a.shape
+        bad = np.zeros(n, np.int32)
+        nans = np.zeros(n, np.int32)
+        self._check(self.lib.stc_missing_px_host(self.h, _dptr(a), n, H, W, Cc, _dptr(bad), _dptr(nans)))
+        return bad, nans
+
+    def median_fill(self, arr):
+        """In-place 0 / 1 sentinel fill with the running temporal median (deal_w_missing_px :1039-1047).
+        arr must be a C-contiguous float32 [n,H,W,C] array; returns the per-date NaN counts afterwards."""
+        if not (isinstance(arr, np.ndarray) and arr.dtype == np.float32 and arr.flags.c_contiguous and arr.ndim == 4):
+            raise ValueError("median_fill needs a C-contiguous float32 [n,H,W,C] array (filled in place)")
+        n, H, W, Cc = arr.shape
+        nans = np.zeros(n, np.int32)
+        self._check(self.lib.stc_median_fill_host(self.h, _dptr(arr), n, H, W, Cc, _dptr(nans)))
+        return nans
+
+    def build_sentinel2(self, s2_10, s2_20):
+        """process_tile :743-782: (n,2h,2w,4) 10 m bands + (n,h,w,6) 20/40 m bands -> (n,2h,2w,10) float32."""
+        a = np.ascontiguousarray(s2_10, np.float32)
+        b = np.ascontiguousarray(s2_20, np.float32)
+        n, h, w, c6 = b.shape
+        if c6 != 6 or a.shape != (n, 2 * h, 2 * w, 4):
+            raise ValueError("shapes %r / %r are not (n,2h,2w,4) / (n,h,w,6)" % (a.shape, b.shape))
+        out = np.empty((n, 2 * h, 2 * w, 10), np.float32)
+        self._check(self.lib.stc_build_sentinel2_host(self.h, _dptr(a), _dptr(b), n, h, w, _dptr(out)))
+        return out
+
     CLOUD_STAGES = {"clm": 1, "shadows_raw": 2, "shadows_clean": 3, "clouds_raw": 4, "clouds_bright": 5,
                     "clouds_fp": 6, "clouds_shape": 7, "clouds_pre_haze": 8}
 
@@ -457,11 +490,46 @@ def make_indices(arr, sess):
     return sess.indices(arr)
 
 
+def id_missing_px(sentinel2, thresh, sess):
+    """src/preprocessing/interpolation.py:5-23: dates with >= H^2/thresh pixels having more than one
+    band (of the first 10) equal to 0 or >= 1.  The per-date pixel counts come from the GPU."""
+    bad, _ = sess.missing_px_counts(sentinel2)
+    return np.argwhere(bad >= (sentinel2.shape[1] ** 2) / thresh).flatten()
+
+
+def deal_w_missing_px(arr, dates, interp, sess):
+    """src/download_and_predict_job.py:1031-1054.  Date bookkeeping (np.delete) on the host, counting and
+    the running-median fill on the GPU.  Like the reference, `arr` is filled IN PLACE when no date was
+    dropped first (np.delete makes a copy otherwise)."""
+    missing_px = id_missing_px(arr, 10, sess)
+    if len(missing_px) > 0:
+        dates = np.delete(dates, missing_px)
+        arr = np.delete(arr, missing_px, 0)
+        interp = np.delete(interp, missing_px, 0)
+    if arr.dtype == np.float32 and arr.flags.c_contiguous:
+        nans = sess.median_fill(arr)
+    else:
+        filled = np.ascontiguousarray(arr, np.float32)
+        nans = sess.median_fill(filled)
+        arr[...] = filled
+    to_remove = np.argwhere(nans > 0).flatten()
+    if len(to_remove) > 0:
+        dates = np.delete(dates, to_remove)
+        arr = np.delete(arr, to_remove, 0)
+        interp = np.delete(interp, to_remove, 0)
+    return arr, dates, interp
+
+
+def build_sentinel2(s2_10, s2_20, sess):
+    """The 20 m -> 10 m upsampling block of process_tile (src/download_and_predict_job.py:743-782)."""
+    return sess.build_sentinel2(s2_10, s2_20)
+
+
 def smooth_large_tile(arr, dates, interp, sess):
     """src/download_and_predict_job.py:1057-1096: median-fill missing px, indices,
     15-day regrid + Whittaker + monthly mean -> (12,H,W,14).  The date logic and the
     12 x n operator are built on the host (regrid.py); the arithmetic runs on the GPU."""
-    arr, dates, interp = _regrid.deal_w_missing_px(arr, dates, interp)
+    arr, dates, interp = deal_w_missing_px(arr, dates, interp, sess)
     try:
         M, _ = _regrid.monthly_operator(dates)
     except Exception:

@@ -10,8 +10,7 @@ image dates (a handful of integers per tile) stays in NumPy and is folded into O
                          /root/reference/src/preprocessing/whittaker_smoother.py:10-42
   pair_mean_matrix()     A (12 x 24): mean of consecutive pairs -- :64-67
   monthly_operator(d)    M = A S G (12 x n), float32
-  deal_w_missing_px      /root/reference/src/download_and_predict_job.py:1031-1054
-  id_missing_px          /root/reference/src/preprocessing/interpolation.py:5-23
+(The array work of deal_w_missing_px / id_missing_px runs on the GPU: api.deal_w_missing_px.)
 """
 import numpy as np
 
@@ -104,27 +103,3 @@ def s1_monthly_operator(dates):
     return (pair_mean_matrix() @ G.astype(np.float64)).astype(np.float32), max_distance
 
 
-def id_missing_px(s2, thresh=11):
-    bad = (s2[..., :10] == 0.0).sum(-1) + (s2[..., :10] >= 1.0).sum(-1)
-    per_date = (bad > 1.0).sum(axis=(1, 2))
-    return np.argwhere(per_date >= (s2.shape[1] ** 2) / thresh).flatten()
-
-
-def deal_w_missing_px(arr, dates, interp):
-    missing = id_missing_px(arr, 10)
-    if len(missing) > 0:
-        dates = np.delete(dates, missing)
-        arr = np.delete(arr, missing, 0)
-        interp = np.delete(interp, missing, 0)
-    for sentinel in (0, 1):
-        if np.sum(arr == sentinel) > 0:
-            for i in range(arr.shape[0]):
-                a = arr[i]
-                sel = a == sentinel
-                a[sel] = np.median(arr, axis=0)[sel]
-    bad = np.argwhere(np.sum(np.isnan(arr), axis=(1, 2, 3)) > 0).flatten()
-    if len(bad) > 0:
-        dates = np.delete(dates, bad)
-        arr = np.delete(arr, bad, 0)
-        interp = np.delete(interp, bad, 0)
-    return arr, dates, interp
