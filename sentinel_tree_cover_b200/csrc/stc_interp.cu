@@ -115,7 +115,8 @@ struct AxisTap { int i0, i1; double w0, w1; };
 __device__ __forceinline__ AxisTap axis_tap(int k, int n_in, int n_out) {
   double zoom = (double)n_in / (double)n_out;
   double cc = __dsub_rn(__dmul_rn((double)k + 0.5, zoom), 0.5);
-  if (cc < 0.0) cc = (n_in <= 1) ? 0.0 : -cc;
+  if (n_in <= 1) cc = 0.0;            // map_coordinate(mirror) with a single sample
+  else if (cc < 0.0) cc = -cc;
   double fl = floor(cc);
   AxisTap t; t.i0 = (int)fl; t.i1 = t.i0 + 1;
   if (n_in <= 1) { t.i0 = t.i1 = 0; }
