@@ -166,6 +166,22 @@ int stc_feather_host(stc_ctx* ctx, const float* masks_host, int n, int H, int W,
 int stc_binary_dilate_host(stc_ctx* ctx, const uint8_t* in_host, int n, int H, int W, int iterations,
                            int connectivity, uint8_t* out_host);
 
+/* ---- cloud / shadow removal: remove_cloud_and_shadows(tiles, probs, shadows, image_dates, pfcps, sentinel1)
+ *      (src/preprocessing/cloud_removal.py:888-973; make_aligned_mosaic :578-699, align_interp_array_randomforest
+ *      :316-575, calculate_clouds_in_mosaic :703-732).  tiles [n,H,W,10] float32 are rewritten IN PLACE
+ *      (cloudy pixels blended with the NNLS-aligned cloud-free mosaic), probs [n,H,W] float32 is the cloud|shadow
+ *      mask, pfcps [n,H,W] uint8 the false-positive mask of stc_cloud_masks_host (only date 0 is read, as in the
+ *      reference).  mt_state: the 624 MT19937 words + position of Python's `random.getstate()[1]`; the
+ *      reference draws its training sample with random.shuffle, and the same generator is advanced here, so a
+ *      pinned random.seed reproduces the reference's sample; the advanced state is written back.
+ *      areas_out [n,H,W] float32 = the feathered interpolation weights (+ residual mosaic clouds, clipped to 1);
+ *      to_remove_out[n] = 1 for dates that are 100 % interpolated; mosaic_out [H,W,10] optional (may be NULL).
+ *      1 <= n <= 32.  Situations in which the reference itself raises (a date with <= 1 % usable pixels, an empty
+ *      fit set, a one-element EVI stratum, NNLS not converging) return STC_ERR_STATE with the cause in
+ *      stc_last_error. ---- */
+int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H, int W,
+                           uint32_t* mt_state, float* areas_out_host, int32_t* to_remove_out_host, float* mosaic_out_host);
+
 /* ---- exact squared Euclidean distance to the nearest non-zero pixel of `target`, searched
  *      within `radius` (radius^2+1 where none): the capped distance_transform_edt call sites
  *      (cap 3: identify_bright_bare_surfaces src/download_and_predict_job.py:1117-1119;

@@ -85,6 +85,8 @@ SYMBOLS = [
     ("stc_missing_px_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("stc_median_fill_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_build_sentinel2_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_remove_clouds_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     ("stc_cloud_masks_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int]),
     ("stc_debug_read", C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p]),
@@ -416,6 +418,30 @@ class StcSession:
             return clouds, fcps.astype(bool), tap
         return clouds, fcps.astype(bool)
 
+    def remove_clouds(self, tiles, probs, pfcps, mt_state, want_mosaic=False):
+        """remove_cloud_and_shadows core (cloud_removal.py:888-973).  tiles: C-contiguous float32 [n,H,W,10],
+        rewritten in place.  mt_state: uint32[625] (Python `random.getstate()[1]`), advanced in place.
+        Returns (areas [n,H,W] float32, to_remove list[, mosaic [H,W,10]])."""
+        if not (isinstance(tiles, np.ndarray) and tiles.dtype == np.float32 and tiles.flags.c_contiguous and tiles.ndim == 4
+                and tiles.shape[-1] == 10):
+            raise ValueError("remove_clouds needs a C-contiguous float32 [n,H,W,10] array (blended in place)")
+        n, H, W, _ = tiles.shape
+        p = np.ascontiguousarray(probs, np.float32)
+        f = np.ascontiguousarray(np.asarray(pfcps) != 0, np.uint8).reshape(-1, H, W)
+        if p.shape != (n, H, W) or f.shape[0] not in (1, n):
+            raise ValueError("mask shapes %r / %r do not match tiles %r" % (p.shape, f.shape, tiles.shape))
+        if f.shape[0] != n:
+            f = np.ascontiguousarray(np.repeat(f, n, 0))
+        if not (isinstance(mt_state, np.ndarray) and mt_state.dtype == np.uint32 and mt_state.shape == (625,)):
+            raise ValueError("mt_state must be a uint32[625] array")
+        areas = np.empty((n, H, W), np.float32)
+        rem = np.zeros(n, np.int32)
+        mosaic = np.empty((H, W, 10), np.float32) if want_mosaic else None
+        self._check(self.lib.stc_remove_clouds_host(self.h, _dptr(tiles), _dptr(p), _dptr(f), n, H, W, _dptr(mt_state), _dptr(areas),
+                                                    _dptr(rem), _dptr(mosaic) if want_mosaic else None))
+        out = (areas, [int(i) for i in np.flatnonzero(rem)])
+        return out + (mosaic,) if want_mosaic else out
+
     def mosaic(self, preds, xs, ys, out_shape, sigma=36):
         """Gaussian overlap blend of subtile predictions (list/array [n,S,S], the arrays as
         saved by process_subtiles) placed at (xs[i], ys[i]) -> uint8 canvas `out_shape`."""
@@ -651,6 +677,35 @@ def id_areas_to_interp(tiles, probs, shadows, image_dates, pfcps, sess):
     """src/preprocessing/cloud_removal.py:774-798: feathered interpolation masks (closing 15)."""
     a = np.clip(np.copy(probs).astype(np.float32), 0, 1)
     return sess.feather(a, 15)
+
+
+def remove_cloud_and_shadows(tiles, probs, shadows, image_dates, pfcps, sentinel1, mosaic=None, sess=None):
+    """src/preprocessing/cloud_removal.py:888-973, same arguments and return value
+    `(tiles, areas_interpolated, to_remove)`; `tiles` is blended IN PLACE like the reference.
+    `shadows`, `image_dates` and `sentinel1` are accepted and unused (the reference body never reads
+    them: the S1 stack was dropped from the fit, :339-343, :400-407).  The reference samples its
+    regression pixels with Python's global `random`; this wrapper hands the generator state to the
+    library and stores the advanced state back, so `random.seed(k)` before the call gives the
+    reference's sample and leaves `random` where the reference would leave it.
+    The reference's debug dumps (mosaic.npy, tiles.npy, ... into the CWD, :925-927,972) are not written."""
+    import random
+    if sess is None:
+        raise RuntimeError("remove_cloud_and_shadows needs an StcSession (sess=...); there is no CPU path")
+    if mosaic is not None:
+        raise NotImplementedError("a precomputed mosaic is never passed by the reference's callers "
+                                  "(src/download_and_predict_job.py:935-944) and is not supported")
+    del shadows, image_dates, sentinel1
+    if isinstance(tiles, np.ndarray) and tiles.dtype == np.float32 and tiles.flags.c_contiguous:
+        work = tiles
+    else:
+        work = np.ascontiguousarray(tiles, np.float32)
+    version, internal, gauss = random.getstate()
+    state = np.array(internal, dtype=np.uint32)
+    areas, to_remove = sess.remove_clouds(work, probs, pfcps, state)
+    random.setstate((version, tuple(int(v) for v in state), gauss))
+    if work is not tiles:
+        tiles[...] = work
+    return tiles, areas, to_remove
 
 
 def fspecial_gauss(size, sigma):

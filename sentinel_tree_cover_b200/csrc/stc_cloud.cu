@@ -620,6 +620,13 @@ static CloudWin cloud_window(int t, int T) {
   return w;
 }
 
+// shared with stc_cloudfill.cu: binary dilation / erosion-by-dilation on [frames][H][W] uint8 masks
+void maskop_dilate(stc_ctx* ctx, const unsigned char* in, unsigned char* out, int frames, int H, int W, int k, int conn, int inv_in,
+                   int inv_out, int three_d) {
+  k_dilate<<<cdiv((int64_t)frames * H * W, 256), 256, 0, ctx->stream>>>(in, out, frames, H, W, k, conn, inv_in, inv_out, three_d);
+  ctx->launches++;
+}
+
 #define LAUNCH1D(kern, n, ...) do { kern<<<cdiv((n), 256), 256, 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
 
 extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const float* dem_host, int T, int H, int W,

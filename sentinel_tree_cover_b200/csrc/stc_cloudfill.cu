@@ -1,0 +1,774 @@
+// Cloud / shadow removal: remove_cloud_and_shadows (src/preprocessing/cloud_removal.py:888-973) with
+// make_aligned_mosaic (:578-699), align_interp_array_randomforest (:316-575) and
+// calculate_clouds_in_mosaic (:703-732).
+//
+// Division of labour.  Device: every array operation -- feathering, the cloud-free mosaic with its
+// per-date median / std matching, snow and EVI features, order statistics (radix select), the
+// float64 Gram matrices of the sampled clear pixels, the 11-variable non-negative least squares
+// (Lawson-Hanson on the Gram form, the algorithm scipy.optimize.nnls itself runs), prediction and
+// blending, the residual-cloud mask.  Host (this file, C++): control flow on scalar counts and the
+// reference's sampling bookkeeping -- index lists per EVI stratum shuffled with Python's Mersenne
+// Twister (random.shuffle), whose 625-word state the caller passes in and gets back, so a pinned
+// random.seed reproduces the reference's sample exactly.
+//
+// Exactness.  Everything up to the regression is bit-identical to NumPy (float32 reductions follow
+// NumPy's order: axis-0 sums are sequential, medians / percentiles are exact order statistics with
+// NumPy's float32 lerp).  The regression is float64 with a different summation order than
+// LAPACK/BLAS: filled pixels agree to ~1e-6 relative (tests/test_cloud_fill.py: rtol 1e-4).
+#include "stc_common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#define CF_MAX_DATES 32
+#define NF 11          // regression features: 10 mosaic bands + snow
+
+void maskop_dilate(stc_ctx* ctx, const unsigned char* in, unsigned char* out, int frames, int H, int W, int k, int conn, int inv_in,
+                   int inv_out, int three_d);
+
+namespace {
+
+struct DBuf {
+  void* p = nullptr;
+  ~DBuf() { if (p) cudaFree(p); }
+  template <typename T> T* as() { return (T*)p; }
+};
+
+__device__ __forceinline__ void isortf(float* v, int n) {
+  for (int i = 1; i < n; ++i) { float x = v[i]; int j = i - 1; while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; } v[j + 1] = x; }
+}
+// np.median over <= 32 values (NaN propagates)
+__device__ __forceinline__ float np_median_small(float* v, int n) {
+  for (int i = 0; i < n; ++i) if (isnan(v[i])) return v[i];
+  isortf(v, n);
+  return (n & 1) ? v[n >> 1] : __fdiv_rn(__fadd_rn(v[(n >> 1) - 1], v[n >> 1]), 2.f);
+}
+// NumPy's float32 linear-interpolation quantile between two neighbouring order statistics
+__device__ __host__ inline void np_quantile_pos(int n, double q, int& lo, float& g) {
+  double vi = (double)n * q + (1.0 + q * (-1.0)) - 1.0;       // _compute_virtual_index(n, q, alpha=1, beta=1)
+  if (vi < 0) vi = 0;
+  double fl = floor(vi);
+  lo = (int)fl; g = (float)(vi - fl);
+  if (lo >= n - 1) { lo = n - 1; g = 0.f; }
+}
+__device__ __forceinline__ float np_lerp(float a, float b, float g) {
+  float d = __fsub_rn(b, a);
+  return (g >= 0.5f) ? __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.f, g))) : __fadd_rn(a, __fmul_rn(d, g));
+}
+
+// ---------------------------------------------------------------------------------------------
+// mosaic stage
+// ---------------------------------------------------------------------------------------------
+// water0[p] = np.median_t NDWI > 0 ; divisor[p] = sum_t (1 - a_t) (sequential float32)
+__global__ void __launch_bounds__(128) k_mosaic_prep(const float* __restrict__ tiles, const float* __restrict__ areas, int n, int HW,
+                                                     unsigned char* __restrict__ water0, float* __restrict__ divisor) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  float v[CF_MAX_DATES];
+  float d = 0.f;
+  for (int t = 0; t < n; ++t) {
+    const float* x = tiles + ((int64_t)t * HW + p) * 10;
+    v[t] = __fdiv_rn(__fsub_rn(x[1], x[3]), __fadd_rn(x[1], x[3]));
+    float om = __fsub_rn(1.f, areas[(int64_t)t * HW + p]);
+    d = t ? __fadd_rn(d, om) : om;
+  }
+  water0[p] = np_median_small(v, n) > 0.f;
+  divisor[p] = d;
+}
+
+// reference image of date i: mean of the other dates over pixels usable for both (:598-616)
+__global__ void __launch_bounds__(128) k_mosaic_ref(const float* __restrict__ tiles, const float* __restrict__ areas,
+                                                    const unsigned char* __restrict__ water, int n, int HW, int i,
+                                                    float* __restrict__ ref /*[HW][10]*/, unsigned char* __restrict__ flag) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  bool ok = (areas[(int64_t)i * HW + p] < 0.25f) && !water[p];
+  float s[10]; float cnt = 0.f;
+#pragma unroll
+  for (int c = 0; c < 10; ++c) s[c] = 0.f;
+  if (ok) {
+    for (int b = 0; b < n; ++b) {
+      if (b == i || !(areas[(int64_t)b * HW + p] < 1.f)) continue;
+      const float* x = tiles + ((int64_t)b * HW + p) * 10;
+#pragma unroll
+      for (int c = 0; c < 10; ++c) s[c] = __fadd_rn(s[c], x[c]);
+      cnt = __fadd_rn(cnt, 1.f);
+    }
+  }
+  ok = ok && cnt > 0.f;
+  if (ok) {
+#pragma unroll
+    for (int c = 0; c < 10; ++c) ref[(int64_t)p * 10 + c] = __fdiv_rn(s[c], cnt);
+  }
+  flag[p] = ok;
+}
+
+// order-preserving compaction positions of a flag image: pos[p] = rank of p among flagged pixels; total -> *count
+// (single block; HW <= a few 100k)
+__global__ void __launch_bounds__(1024) k_scan_flags(const unsigned char* __restrict__ flag, int HW, int* __restrict__ pos,
+                                                     int* __restrict__ count) {
+  __shared__ int wtot[32]; __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int p0 = 0; p0 < HW; p0 += 1024) {
+    const int p = p0 + threadIdx.x;
+    const bool f = p < HW && flag[p];
+    unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) wtot[wid] = __popc(bal);
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += wtot[w];
+    if (p < HW) pos[p] = f ? base + woff + __popc(bal & ((1u << lane) - 1u)) : -1;
+    __syncthreads();
+    if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 32; ++w) s += wtot[w]; base += s; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base;
+}
+
+// gather the flagged rows of date i and of the reference image: rows[0] = src [K][10], rows[1] = ref [K][10]
+__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ tiles_i, const float* __restrict__ ref,
+                                                     const int* __restrict__ pos, int HW, float* __restrict__ src_rows,
+                                                     float* __restrict__ ref_rows) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)HW * 10) return;
+  int p = (int)(idx / 10), c = (int)(idx % 10);
+  int r = pos[p];
+  if (r < 0) return;
+  src_rows[(int64_t)r * 10 + c] = tiles_i[idx];
+  ref_rows[(int64_t)r * 10 + c] = ref[idx];
+}
+
+// exact k-th order statistics of a strided float32 column by MSB-first radix select; one block per (matrix, column)
+struct SelectJob { const float* data; int64_t stride; int n; int k; };
+__device__ float block_radix_select(const float* __restrict__ data, int64_t stride, int n, int k) {
+  __shared__ int hist[256]; __shared__ unsigned prefix; __shared__ int kth;
+  if (threadIdx.x == 0) { prefix = 0; kth = k; }
+  __syncthreads();
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned pre = prefix;
+    const unsigned mask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      unsigned u = __float_as_uint(data[(int64_t)i * stride]); u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
+      if ((u & mask) == (pre & mask)) atomicAdd(&hist[(u >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int kk = kth, b = 0;
+      while (b < 255 && kk >= hist[b]) { kk -= hist[b]; ++b; }
+      kth = kk; prefix = pre | ((unsigned)b << shift);
+    }
+    __syncthreads();
+  }
+  unsigned u = prefix; u ^= (u >> 31) ? 0x80000000u : 0xffffffffu;
+  __syncthreads();
+  return __uint_as_float(u);
+}
+// quantile q of each job's column with NumPy's float32 lerp (q = 0.5 gives np.median's (a+b)/2 for even n:
+// a + (b-a)*0.5 differs from (a+b)/2 in float32, so the median has its own flag)
+__global__ void __launch_bounds__(1024) k_quantile(const SelectJob* __restrict__ jobs, const double* __restrict__ q, int median_mode,
+                                                   float* __restrict__ out) {
+  const SelectJob j = jobs[blockIdx.x];
+  if (j.n <= 0) { if (threadIdx.x == 0) out[blockIdx.x] = nanf(""); return; }
+  if (median_mode) {
+    float a = block_radix_select(j.data, j.stride, j.n, (j.n - 1) / 2);
+    float b = (j.n & 1) ? a : block_radix_select(j.data, j.stride, j.n, j.n / 2);
+    if (threadIdx.x == 0) out[blockIdx.x] = (j.n & 1) ? a : __fdiv_rn(__fadd_rn(a, b), 2.f);
+    return;
+  }
+  int lo; float g;
+  np_quantile_pos(j.n, q[blockIdx.x], lo, g);
+  float a = block_radix_select(j.data, j.stride, j.n, lo);
+  float b = (lo + 1 < j.n) ? block_radix_select(j.data, j.stride, j.n, lo + 1) : a;
+  if (threadIdx.x == 0) out[blockIdx.x] = np_lerp(a, b, g);
+}
+
+// np.nanstd(rows, axis=0) of a [K][10] float32 matrix: NumPy reduces axis 0 row by row, i.e. each column is a
+// SEQUENTIAL float32 sum.  One warp per column; lanes prefetch 32 rows, every lane replays the same chain.
+// grid = 2 matrices, block = 10 warps.
+__global__ void __launch_bounds__(320) k_col_std(const float* __restrict__ m0, const float* __restrict__ m1, int K, float* __restrict__ out) {
+  const float* m = blockIdx.x ? m1 : m0;
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float avg = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {
+    float s = 0.f;
+    float nxt = (lane < K) ? m[(int64_t)lane * 10 + c] : 0.f;
+    for (int r0 = 0; r0 < K; r0 += 32) {
+      float v = nxt;
+      int rn = r0 + 32 + lane;
+      nxt = (rn < K) ? m[(int64_t)rn * 10 + c] : 0.f;
+      if (pass) { float d = __fsub_rn(v, avg); v = __fmul_rn(d, d); }
+      const int cnt = (K - r0) < 32 ? (K - r0) : 32;
+      for (int l = 0; l < cnt; ++l) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, l));
+    }
+    float r = (float)((double)s / (double)K);
+    if (pass == 0) avg = r; else if (lane == 0) out[blockIdx.x * 10 + c] = __fsqrt_rn(r);
+  }
+}
+
+// params[c] = std_ref/std_src, params[10+c] = med_ref - med_src*mult   (stats: med[0..9]=src, [10..19]=ref; std same)
+__global__ void k_scale_params(const float* __restrict__ med, const float* __restrict__ sd, float* __restrict__ params) {
+  int c = threadIdx.x;
+  if (c >= 10) return;
+  float mult = __fdiv_rn(sd[10 + c], sd[c]);
+  params[c] = mult;
+  params[10 + c] = __fsub_rn(med[10 + c], __fmul_rn(med[c], mult));
+}
+
+__global__ void __launch_bounds__(256) k_mosaic_accum(const float* __restrict__ tiles_i, const float* __restrict__ area_i,
+                                                      const unsigned char* __restrict__ water, const float* __restrict__ params,
+                                                      int HW, float* __restrict__ mosaic) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)HW * 10) return;
+  int p = (int)(idx / 10), c = (int)(idx % 10);
+  float x = tiles_i[idx];
+  if (!water[p]) x = __fadd_rn(__fmul_rn(x, params[c]), params[10 + c]);
+  mosaic[idx] = __fadd_rn(mosaic[idx], __fmul_rn(__fsub_rn(1.f, area_i[p]), x));
+}
+
+__global__ void __launch_bounds__(128) k_mosaic_final(const float* __restrict__ tiles, const float* __restrict__ divisor, int n, int HW,
+                                                      float* __restrict__ mosaic) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)HW * 10) return;
+  int p = (int)(idx / 10);
+  float d = divisor[p]; if (d < 0.f) d = 0.f;
+  float m = __fdiv_rn(mosaic[idx], d);
+  float v[CF_MAX_DATES]; float mn = INFINITY, mx = -INFINITY;
+  for (int t = 0; t < n; ++t) { v[t] = tiles[(int64_t)t * HW * 10 + idx]; mn = fminf(mn, v[t]); mx = fmaxf(mx, v[t]); }
+  if (isnan(m)) {
+    isortf(v, n);
+    int lo; float g; np_quantile_pos(n, 10.0 / 100.0, lo, g);
+    m = np_lerp(v[lo], v[lo + 1 < n ? lo + 1 : n - 1], g);
+  }
+  m = fmaxf(m, mn); m = fminf(m, mx);
+  mosaic[idx] = m;
+}
+
+__global__ void __launch_bounds__(256) k_fill_f(float* p, int64_t n, float v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-date alignment stage
+// ---------------------------------------------------------------------------------------------
+// water1[p] = NDWI(np.median_t tiles) > 0 (:939)
+__global__ void __launch_bounds__(128) k_water_of_median(const float* __restrict__ tiles, int n, int HW, unsigned char* __restrict__ water) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  float v[CF_MAX_DATES];
+  for (int t = 0; t < n; ++t) v[t] = tiles[((int64_t)t * HW + p) * 10 + 1];
+  float g = np_median_small(v, n);
+  for (int t = 0; t < n; ++t) v[t] = tiles[((int64_t)t * HW + p) * 10 + 3];
+  float nir = np_median_small(v, n);
+  water[p] = __fdiv_rn(__fsub_rn(g, nir), __fadd_rn(g, nir)) > 0.f;
+}
+
+// counts[t] = {#a>0, #a==0, #a<1, #a==1, #(a==0 && !water)}
+__global__ void __launch_bounds__(256) k_area_counts(const float* __restrict__ areas, const unsigned char* __restrict__ water, int HW,
+                                                     int* __restrict__ counts) {
+  const int t = blockIdx.y; int p = blockIdx.x * blockDim.x + threadIdx.x;
+  float a = p < HW ? areas[(int64_t)t * HW + p] : -1.f;
+  bool in = p < HW;
+  unsigned b0 = __ballot_sync(0xffffffffu, in && a > 0.f), b1 = __ballot_sync(0xffffffffu, in && a == 0.f),
+           b2 = __ballot_sync(0xffffffffu, in && a < 1.f), b3 = __ballot_sync(0xffffffffu, in && a == 1.f),
+           b4 = __ballot_sync(0xffffffffu, in && a == 0.f && !water[p < HW ? p : 0]);
+  if ((threadIdx.x & 31) == 0) {
+    if (b0) atomicAdd(counts + t * 5 + 0, __popc(b0));
+    if (b1) atomicAdd(counts + t * 5 + 1, __popc(b1));
+    if (b2) atomicAdd(counts + t * 5 + 2, __popc(b2));
+    if (b3) atomicAdd(counts + t * 5 + 3, __popc(b3));
+    if (b4) atomicAdd(counts + t * 5 + 4, __popc(b4));
+  }
+}
+
+// snow probability of one pixel-date (:348-370), float32 as NumPy evaluates it
+__device__ __forceinline__ float snow_prob(const float* x) {
+  float ndsi = __fdiv_rn(__fsub_rn(x[1], x[8]), __fadd_rn(x[1], x[8]));
+  if (ndsi < 0.10f) ndsi = 0.f;
+  if (ndsi > 0.42f) ndsi = 0.42f;
+  float p = __fdiv_rn(__fsub_rn(ndsi, 0.1f), 0.32f);
+  if (x[3] < 0.10f) p = 0.f;
+  if (x[3] > 0.35f && p > 0.f) p = 1.f;
+  if (x[0] < 0.10f) p = 0.f;
+  if (x[0] > 0.22f && p > 0.f) p = 1.f;
+  if (__fdiv_rn(x[0], x[2]) < 0.75f) p = 0.f;
+  return p;
+}
+__global__ void __launch_bounds__(256) k_snow_mean(const float* __restrict__ tiles, int n, int HW, float* __restrict__ snow) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  float s = 0.f;
+  for (int t = 0; t < n; ++t) { float v = snow_prob(tiles + ((int64_t)t * HW + p) * 10); s = t ? __fadd_rn(s, v) : v; }
+  snow[p] = (float)((double)s / (double)n);
+}
+
+__device__ __forceinline__ float evi_of(const float* x) {
+  float den = __fadd_rn(__fsub_rn(__fadd_rn(x[3], __fmul_rn(6.f, x[2])), __fmul_rn(7.5f, x[0])), 1.f);
+  float e = __fmul_rn(2.5f, __fdiv_rn(__fsub_rn(x[3], x[2]), den));
+  return fminf(fmaxf(e, -1.5f), 1.5f);
+}
+// rows of date t usable for the fit (a_t == 0 and not water), appended at row_base in pixel order:
+// rowsrc[r] = t*HW + p, evi[r] = EVI(tiles[t][p])
+__global__ void __launch_bounds__(1024) k_collect_rows(const float* __restrict__ tiles, const float* __restrict__ areas,
+                                                       const unsigned char* __restrict__ water, int HW, int t, int row_base,
+                                                       int* __restrict__ rowsrc, float* __restrict__ evi) {
+  __shared__ int wtot[32]; __shared__ int base;
+  if (threadIdx.x == 0) base = row_base;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int p0 = 0; p0 < HW; p0 += 1024) {
+    const int p = p0 + threadIdx.x;
+    const bool f = p < HW && areas[(int64_t)t * HW + p] == 0.f && !water[p];
+    unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) wtot[wid] = __popc(bal);
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += wtot[w];
+    if (f) {
+      int r = base + woff + __popc(bal & ((1u << lane) - 1u));
+      rowsrc[r] = t * HW + p;
+      evi[r] = evi_of(tiles + ((int64_t)t * HW + p) * 10);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 32; ++w) s += wtot[w]; base += s; }
+    __syncthreads();
+  }
+}
+
+// stratum bits of every row against the six EVI percentiles b = {2,20,40,60,80,98} (:455-467)
+__global__ void __launch_bounds__(256) k_strata(const float* __restrict__ evi, const float* __restrict__ b, int K, unsigned char* __restrict__ lab) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= K) return;
+  float e = evi[r];
+  unsigned char m = 0;
+  if (e < b[0]) m |= 1;                       // p2
+  if (e < b[1]) m |= 2;                       // p20
+  if (e >= b[1] && e < b[2]) m |= 4;          // p40
+  if (e >= b[2] && e < b[3]) m |= 8;          // p60
+  if (e >= b[3] && e < b[4]) m |= 16;         // p80
+  if (e >= b[4]) m |= 32;                     // p100
+  if (e >= b[5]) m |= 64;                     // p98
+  lab[r] = m;
+}
+
+// float64 Gram sums over the sampled rows.  Features u_j = [mosaic bands, snow], c_j = clip(u_j, 0.005, 1)
+// for j < 10 (c_10 = u_10), targets y_b = tile bands of the row's (date, pixel).
+// acc layout (583 doubles): UU[11][11], CU[11][11] (c_j * u_k), CC[11][11], UY[11][10], CY[11][10].
+#define GRAM_N (3 * NF * NF + 2 * NF * 10)
+#define GRAM_ROWS 64
+__global__ void __launch_bounds__(640) k_gram(const float* __restrict__ tiles, const float* __restrict__ mosaic, const float* __restrict__ snow,
+                                              const int* __restrict__ rowsrc, const int* __restrict__ sample, int S, int HW,
+                                              double* __restrict__ partial /*[grid][GRAM_N]*/) {
+  __shared__ float u[GRAM_ROWS][NF], c[GRAM_ROWS][NF], y[GRAM_ROWS][10];
+  const int q = threadIdx.x;
+  int kind = -1, j = 0, k = 0;
+  if (q < 3 * NF * NF) { kind = q / (NF * NF); j = (q % (NF * NF)) / NF; k = q % NF; }
+  else if (q < GRAM_N) { int r = q - 3 * NF * NF; kind = 3 + r / (NF * 10); j = (r % (NF * 10)) / 10; k = r % 10; }
+  double acc = 0.0;
+  for (int s0 = blockIdx.x * GRAM_ROWS; s0 < S; s0 += gridDim.x * GRAM_ROWS) {
+    const int rows = (S - s0) < GRAM_ROWS ? (S - s0) : GRAM_ROWS;
+    __syncthreads();
+    for (int e = threadIdx.x; e < rows * 21; e += blockDim.x) {
+      int r = e / 21, f = e % 21;
+      int src = rowsrc[sample[s0 + r]];
+      int p = src % HW;
+      if (f < 10) { float v = mosaic[(int64_t)p * 10 + f]; u[r][f] = v; c[r][f] = fminf(fmaxf(v, 0.005f), 1.f); }
+      else if (f == 10) { float v = snow[p]; u[r][10] = v; c[r][10] = v; }
+      else y[r][f - 11] = tiles[(int64_t)src * 10 + (f - 11)];
+    }
+    __syncthreads();
+    if (kind >= 0) {
+      for (int r = 0; r < rows; ++r) {
+        double a, b;
+        switch (kind) {
+          case 0: a = u[r][j]; b = u[r][k]; break;
+          case 1: a = c[r][j]; b = u[r][k]; break;
+          case 2: a = c[r][j]; b = c[r][k]; break;
+          case 3: a = u[r][j]; b = y[r][k]; break;
+          default: a = c[r][j]; b = y[r][k]; break;
+        }
+        acc += a * b;
+      }
+    }
+  }
+  if (kind >= 0) partial[(int64_t)blockIdx.x * GRAM_N + q] = acc;
+}
+__global__ void __launch_bounds__(640) k_gram_reduce(const double* __restrict__ partial, int nblk, double* __restrict__ gram) {
+  int q = threadIdx.x;
+  if (q >= GRAM_N) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[(int64_t)b * GRAM_N + q];
+  gram[q] = s;
+}
+
+// Lawson-Hanson NNLS on the normal equations, as scipy.optimize.nnls does (AtA, Atb in float64,
+// tol = 10*max(m,n)*eps, maxiter = 3n).  Band b's design matrix has bands < b clipped (the reference
+// clips column b in place AFTER copying train_x for band b, :527-540).  One thread per band.
+__device__ bool solve_sym(const double* G, const double* r, const bool* P, double* s) {
+  int id[NF], m = 0;
+  for (int i = 0; i < NF; ++i) { if (P[i]) id[m++] = i; s[i] = 0.0; }
+  double A[NF][NF + 1];
+  for (int a = 0; a < m; ++a) { for (int b = 0; b < m; ++b) A[a][b] = G[id[a] * NF + id[b]]; A[a][m] = r[id[a]]; }
+  for (int col = 0; col < m; ++col) {
+    int piv = col; double best = fabs(A[col][col]);
+    for (int a = col + 1; a < m; ++a) if (fabs(A[a][col]) > best) { best = fabs(A[a][col]); piv = a; }
+    if (best == 0.0) return false;
+    if (piv != col) for (int b = col; b <= m; ++b) { double t = A[col][b]; A[col][b] = A[piv][b]; A[piv][b] = t; }
+    for (int a = col + 1; a < m; ++a) {
+      double f = A[a][col] / A[col][col];
+      for (int b = col; b <= m; ++b) A[a][b] -= f * A[col][b];
+    }
+  }
+  for (int a = m - 1; a >= 0; --a) {
+    double t = A[a][m];
+    for (int b = a + 1; b < m; ++b) t -= A[a][b] * s[id[b]];
+    s[id[a]] = t / A[a][a];
+  }
+  return true;
+}
+__global__ void k_nnls(const double* __restrict__ gram, int S, double* __restrict__ coef /*[10][NF]*/, int* __restrict__ status) {
+  const int band = threadIdx.x;
+  if (band >= 10) return;
+  const double *UU = gram, *CU = gram + NF * NF, *CC = gram + 2 * NF * NF, *UY = gram + 3 * NF * NF, *CY = UY + NF * 10;
+  double G[NF * NF], r[NF];
+  for (int j = 0; j < NF; ++j) {
+    const bool cj = j < band;
+    r[j] = cj ? CY[j * 10 + band] : UY[j * 10 + band];
+    for (int k = 0; k < NF; ++k) {
+      const bool ck = k < band;
+      G[j * NF + k] = (cj && ck) ? CC[j * NF + k] : cj ? CU[j * NF + k] : ck ? CU[k * NF + j] : UU[j * NF + k];
+    }
+  }
+  const double tol = 10.0 * (double)(S > NF ? S : NF) * 2.220446049250313e-16;
+  const int maxiter = 3 * NF;
+  double x[NF], s[NF], w[NF]; bool P[NF];
+  for (int j = 0; j < NF; ++j) { x[j] = 0.0; s[j] = 0.0; w[j] = r[j]; P[j] = false; }
+  int iter = 0, st = 1;
+  while (true) {
+    bool allP = true, any = false;
+    for (int j = 0; j < NF; ++j) { if (!P[j]) { allP = false; if (w[j] > tol) any = true; } }
+    if (allP || !any) break;
+    int kbest = 0; double best = -INFINITY;
+    for (int j = 0; j < NF; ++j) { double v = P[j] ? 0.0 : w[j]; if (v > best) { best = v; kbest = j; } }   // argmax(w * ~P)
+    P[kbest] = true;
+    if (!solve_sym(G, r, P, s)) { st = -2; break; }
+    while (iter < maxiter) {
+      double mn = INFINITY;
+      for (int j = 0; j < NF; ++j) if (P[j] && s[j] < mn) mn = s[j];
+      if (!(mn < 0)) break;
+      ++iter;
+      double alpha = INFINITY;
+      for (int j = 0; j < NF; ++j) if (P[j] && s[j] < 0) { double a = x[j] / (x[j] - s[j]); if (a < alpha) alpha = a; }
+      for (int j = 0; j < NF; ++j) { x[j] *= (1 - alpha); x[j] += alpha * s[j]; }
+      for (int j = 0; j < NF; ++j) if (x[j] <= tol) P[j] = false;
+      if (!solve_sym(G, r, P, s)) { st = -2; break; }
+    }
+    if (st < 0) break;
+    for (int j = 0; j < NF; ++j) { x[j] = s[j]; }
+    for (int j = 0; j < NF; ++j) { double t = r[j]; for (int k = 0; k < NF; ++k) t -= G[j * NF + k] * x[k]; w[j] = t; }
+    if (iter == maxiter) { st = -1; break; }
+  }
+  for (int j = 0; j < NF; ++j) coef[band * NF + j] = x[j];
+  status[band] = st;
+}
+
+// tiles[d] = tiles[d]*(1-a) + fill*a with fill = regression prediction from [mosaic, snow] (use_coef) or the mosaic itself
+__global__ void __launch_bounds__(256) k_predict_blend(float* __restrict__ tiles_d, const float* __restrict__ area_d,
+                                                       const float* __restrict__ mosaic, const float* __restrict__ snow,
+                                                       const double* __restrict__ coef, int use_coef, int HW) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float a = area_d[p];
+  if (!(a > 0.f)) return;            // a == 0: tiles*1 + 0*0 leaves the pixel unchanged
+  float f[NF];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) f[j] = mosaic[(int64_t)p * 10 + j];
+  f[10] = snow ? snow[p] : 0.f;
+  const float om = __fsub_rn(1.f, a);
+  for (int b = 0; b < 10; ++b) {
+    float fill;
+    if (use_coef) {
+      double t = 0.0;
+      for (int j = 0; j < NF; ++j) t += (double)f[j] * coef[b * NF + j];
+      fill = (float)t;
+    } else fill = f[b];
+    float* x = tiles_d + (int64_t)p * 10 + b;
+    *x = __fadd_rn(__fmul_rn(*x, om), __fmul_rn(fill, a));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual clouds in the mosaic (:703-732)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_only_one(const float* __restrict__ areas, const unsigned char* __restrict__ pf, int n, int HW,
+                                                  unsigned char* __restrict__ only1, int* __restrict__ count) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned char v = 0;
+  if (p < HW) {
+    int clear = 0;
+    for (int t = 0; t < n; ++t) clear += !(areas[(int64_t)t * HW + p] > 0.f);
+    v = (clear < 2) || pf[p];
+    only1[p] = v;
+  }
+  unsigned bal = __ballot_sync(0xffffffffu, v != 0);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
+}
+// compact mosaic blue / red of the multi-image pixels (~only1) in pixel order
+__global__ void __launch_bounds__(256) k_gather_br(const float* __restrict__ mosaic, const int* __restrict__ pos, int HW,
+                                                   float* __restrict__ blue, float* __restrict__ red) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  int r = pos[p];
+  if (r < 0) return;
+  blue[r] = mosaic[(int64_t)p * 10]; red[r] = mosaic[(int64_t)p * 10 + 2];
+}
+__global__ void __launch_bounds__(256) k_not(const unsigned char* in, unsigned char* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = !in[i];
+}
+__global__ void __launch_bounds__(256) k_mosaic_clouds(const float* __restrict__ mosaic, const unsigned char* __restrict__ only1,
+                                                       const unsigned char* __restrict__ pf, const float* __restrict__ refs, int HW,
+                                                       unsigned char* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float* m = mosaic + (int64_t)p * 10;
+  bool c = (m[0] > refs[0]) && (m[2] > refs[1]) && only1[p] && (__fadd_rn(__fadd_rn(m[0], m[1]), m[2]) < 1.f);
+  out[p] = c && !pf[p];
+}
+__global__ void __launch_bounds__(256) k_add_clip(float* __restrict__ areas, const unsigned char* __restrict__ c, int n, int HW) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * HW) return;
+  float v = __fadd_rn(areas[i], c[i % HW] ? 1.f : 0.f);
+  areas[i] = v > 1.f ? 1.f : v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Python's random.shuffle on the MT19937 state handed over by the caller (CPython Lib/random.py:
+// shuffle -> _randbelow_with_getrandbits -> getrandbits(k) = genrand_uint32() >> (32 - k))
+// ---------------------------------------------------------------------------------------------
+struct PyRandom {
+  uint32_t mt[624]; int idx;
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int k = 0; k < 624; ++k) {
+        uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+        mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+    return y;
+  }
+  uint32_t randbelow(uint32_t n) {
+    int k = 32 - __builtin_clz(n);       // n.bit_length(), n >= 1
+    uint32_t r;
+    do { r = next() >> (32 - k); } while (r >= n);
+    return r;
+  }
+  void shuffle(std::vector<int>& x) {
+    for (size_t i = x.size(); i-- > 1;) { uint32_t j = randbelow((uint32_t)i + 1); std::swap(x[i], x[j]); }
+  }
+};
+
+}  // namespace
+
+namespace {
+__global__ void __launch_bounds__(256) k_count_zero(const unsigned char* __restrict__ m, int n, int* __restrict__ count) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned bal = __ballot_sync(0xffffffffu, p < n && m[p] == 0);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
+}
+}  // namespace
+
+#define CF_LAUNCH(kern, grid, block, ...) do { kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
+#define CF_SYNC() STC_CUDA(cudaStreamSynchronize(ctx->stream))
+
+extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H,
+                                      int W, uint32_t* mt_state, float* areas_host, int32_t* to_remove_host, float* mosaic_host) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!tiles_host || !probs_host || !pfcps_host || !mt_state || !areas_host || !to_remove_host || n < 1 || n > CF_MAX_DATES || H < 3 ||
+      W < 3 || mt_state[624] > 624)
+    STC_FAIL(STC_ERR_ARG, "remove_clouds: bad argument (1 <= n <= 32, MT19937 state of 624 words + position)");
+  const int HW = H * W; const int64_t N = (int64_t)n * HW;
+  DBuf d_tiles, d_areas, d_probs, d_ta, d_tb, d_sums, d_water0, d_water1, d_flag, d_u8a, d_u8b, d_pf, d_ref, d_pos, d_src_rows,
+      d_ref_rows, d_mosaic, d_div, d_snow, d_rowsrc, d_evi, d_lab, d_sample, d_partial, d_gram, d_coef, d_status, d_jobs, d_q, d_qout,
+      d_sd, d_params, d_cnt, d_counts, d_pfall;
+  const int gram_blocks = 296;
+  STC_CUDA(cudaMalloc(&d_tiles.p, N * 40)); STC_CUDA(cudaMalloc(&d_areas.p, N * 4)); STC_CUDA(cudaMalloc(&d_probs.p, N * 4));
+  STC_CUDA(cudaMalloc(&d_ta.p, N * 4)); STC_CUDA(cudaMalloc(&d_tb.p, N * 4)); STC_CUDA(cudaMalloc(&d_sums.p, CF_MAX_DATES * 4));
+  for (DBuf* b : {&d_water0, &d_water1, &d_flag, &d_u8a, &d_u8b, &d_pf}) STC_CUDA(cudaMalloc(&b->p, HW));
+  STC_CUDA(cudaMalloc(&d_pfall.p, N));
+  STC_CUDA(cudaMalloc(&d_ref.p, (int64_t)HW * 40)); STC_CUDA(cudaMalloc(&d_pos.p, (int64_t)HW * 4));
+  STC_CUDA(cudaMalloc(&d_src_rows.p, (int64_t)HW * 40)); STC_CUDA(cudaMalloc(&d_ref_rows.p, (int64_t)HW * 40));
+  STC_CUDA(cudaMalloc(&d_mosaic.p, (int64_t)HW * 40)); STC_CUDA(cudaMalloc(&d_div.p, (int64_t)HW * 4)); STC_CUDA(cudaMalloc(&d_snow.p, (int64_t)HW * 4));
+  STC_CUDA(cudaMalloc(&d_rowsrc.p, (int64_t)HW * 12)); STC_CUDA(cudaMalloc(&d_evi.p, (int64_t)HW * 12)); STC_CUDA(cudaMalloc(&d_lab.p, (int64_t)HW * 3));
+  STC_CUDA(cudaMalloc(&d_sample.p, (int64_t)HW * 12));
+  STC_CUDA(cudaMalloc(&d_partial.p, (size_t)gram_blocks * GRAM_N * 8)); STC_CUDA(cudaMalloc(&d_gram.p, GRAM_N * 8));
+  STC_CUDA(cudaMalloc(&d_coef.p, 10 * NF * 8)); STC_CUDA(cudaMalloc(&d_status.p, 64));
+  STC_CUDA(cudaMalloc(&d_jobs.p, 32 * sizeof(SelectJob))); STC_CUDA(cudaMalloc(&d_q.p, 32 * 8)); STC_CUDA(cudaMalloc(&d_qout.p, 32 * 4));
+  STC_CUDA(cudaMalloc(&d_sd.p, 32 * 4)); STC_CUDA(cudaMalloc(&d_params.p, 32 * 4)); STC_CUDA(cudaMalloc(&d_cnt.p, 64));
+  STC_CUDA(cudaMalloc(&d_counts.p, CF_MAX_DATES * 5 * 4));
+  float* tiles = d_tiles.as<float>(); float* areas = d_areas.as<float>(); float* mosaic = d_mosaic.as<float>();
+  unsigned char *water0 = d_water0.as<unsigned char>(), *water1 = d_water1.as<unsigned char>(), *flag = d_flag.as<unsigned char>(),
+                *u8a = d_u8a.as<unsigned char>(), *u8b = d_u8b.as<unsigned char>(), *pf = d_pf.as<unsigned char>();
+  int* cnt = d_cnt.as<int>();
+  STC_CUDA(cudaMemcpyAsync(tiles, tiles_host, N * 40, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(d_probs.p, probs_host, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(d_pfall.p, pfcps_host, N, cudaMemcpyHostToDevice, ctx->stream));
+
+  auto run_quantiles = [&](const std::vector<SelectJob>& jobs, const std::vector<double>& q, int median_mode, float* out_dev) -> int {
+    STC_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(SelectJob), cudaMemcpyHostToDevice, ctx->stream));
+    if (!median_mode) STC_CUDA(cudaMemcpyAsync(d_q.p, q.data(), q.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CF_LAUNCH(k_quantile, (int)jobs.size(), 1024, d_jobs.as<SelectJob>(), d_q.as<double>(), median_mode, out_dev);
+    CF_SYNC();      // jobs / q are host vectors
+    return STC_OK;
+  };
+  int rc;
+
+  // ---- 1. feather the masks (:908-921, closing size 20) ----
+  if ((rc = pre_feather_dev(ctx, d_probs.as<float>(), n, H, W, 20, d_ta.as<float>(), d_tb.as<float>(), d_sums.as<float>(), areas))) return rc;
+
+  // ---- 2. cloud-free mosaic (:578-699) ----
+  CF_LAUNCH(k_mosaic_prep, cdiv(HW, 128), 128, tiles, areas, n, HW, u8a, d_div.as<float>());
+  maskop_dilate(ctx, u8a, u8b, 1, H, W, 2, 1, 1, 0, 0);          // dilate(1 - water, 2)
+  maskop_dilate(ctx, u8b, water0, 1, H, W, 5, 1, 1, 0, 0);       // dilate(1 - that, 5)
+  STC_CUDA(cudaMemsetAsync(mosaic, 0, (int64_t)HW * 40, ctx->stream));
+  STC_CUDA(cudaMemsetAsync(cnt, 0, 64, ctx->stream));
+  CF_LAUNCH(k_count_zero, cdiv(HW, 256), 256, water0, HW, cnt + 1);
+  int land_px = 0;
+  for (int i = 0; i < n; ++i) {
+    CF_LAUNCH(k_mosaic_ref, cdiv(HW, 128), 128, tiles, areas, water0, n, HW, i, d_ref.as<float>(), flag);
+    CF_LAUNCH(k_scan_flags, 1, 1024, flag, HW, d_pos.as<int>(), cnt);
+    int hc[2];
+    STC_CUDA(cudaMemcpyAsync(hc, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CF_SYNC();
+    const int K = hc[0]; land_px = hc[1];
+    if (K > 1000) {
+      CF_LAUNCH(k_gather_rows, cdiv((int64_t)HW * 10, 256), 256, tiles + (int64_t)i * HW * 10, d_ref.as<float>(), d_pos.as<int>(), HW,
+                d_src_rows.as<float>(), d_ref_rows.as<float>());
+      std::vector<SelectJob> jobs;
+      for (int m = 0; m < 2; ++m)
+        for (int c = 0; c < 10; ++c) jobs.push_back({(m ? d_ref_rows.as<float>() : d_src_rows.as<float>()) + c, 10, K, 0});
+      if ((rc = run_quantiles(jobs, {}, 1, d_qout.as<float>()))) return rc;
+      CF_LAUNCH(k_col_std, 2, 320, d_src_rows.as<float>(), d_ref_rows.as<float>(), K, d_sd.as<float>());
+      CF_LAUNCH(k_scale_params, 1, 32, d_qout.as<float>(), d_sd.as<float>(), d_params.as<float>());
+      CF_LAUNCH(k_mosaic_accum, cdiv((int64_t)HW * 10, 256), 256, tiles + (int64_t)i * HW * 10, areas + (int64_t)i * HW, water0,
+                d_params.as<float>(), HW, mosaic);
+    } else if (land_px > 0) {
+      CF_LAUNCH(k_fill_f, cdiv(HW, 256), 256, areas + (int64_t)i * HW, (int64_t)HW, 1.f);      // interp[i] = 1. (:679-680)
+    }
+  }
+  CF_LAUNCH(k_mosaic_final, cdiv((int64_t)HW * 10, 128), 128, tiles, d_div.as<float>(), n, HW, mosaic);
+  if (mosaic_host) STC_CUDA(cudaMemcpyAsync(mosaic_host, mosaic, (int64_t)HW * 40, cudaMemcpyDeviceToHost, ctx->stream));
+
+  // ---- 3. per-date alignment and blending (:939-959, :316-575) ----
+  CF_LAUNCH(k_water_of_median, cdiv(HW, 128), 128, tiles, n, HW, water1);
+  STC_CUDA(cudaMemsetAsync(d_counts.p, 0, CF_MAX_DATES * 5 * 4, ctx->stream));
+  CF_LAUNCH(k_area_counts, dim3(cdiv(HW, 256), n), 256, areas, water1, HW, d_counts.as<int>());
+  std::vector<int> counts(n * 5);
+  STC_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, n * 20, cudaMemcpyDeviceToHost, ctx->stream));
+  CF_SYNC();
+  PyRandom rng; memcpy(rng.mt, mt_state, 624 * 4); rng.idx = (int)mt_state[624];
+  std::vector<unsigned char> lab;
+  for (int d = 0; d < n; ++d) {
+    const int c_pos = counts[d * 5], c_zero = counts[d * 5 + 1], c_lt1 = counts[d * 5 + 2], c_one = counts[d * 5 + 3];
+    to_remove_host[d] = (c_one == HW);
+    if (!(c_pos > 0 && c_zero > 0)) {
+      if (c_pos > 0)      // no clear pixel at all: the interpolated array stays the raw mosaic
+        CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, (const float*)nullptr,
+                  d_coef.as<double>(), 0, HW);
+      continue;
+    }
+    if (!((double)c_lt1 / (double)HW > 0.01))
+      STC_FAIL(STC_ERR_STATE, "remove_clouds: date with <= 1% non-saturated pixels -- the reference raises UnboundLocalError here (cloud_removal.py:575)");
+    int lo, hi;
+    if (c_zero > 40000) { lo = d; hi = d + 1; }
+    else { lo = (d == n - 1) ? std::max(d - 2, 0) : std::max(d - 1, 0); hi = std::min(d + 2, n); }
+    CF_LAUNCH(k_snow_mean, cdiv(HW, 256), 256, tiles, n, HW, d_snow.as<float>());
+    int K = 0;
+    for (int t = lo; t < hi; ++t) {
+      CF_LAUNCH(k_collect_rows, 1, 1024, tiles, areas, water1, HW, t, K, d_rowsrc.as<int>(), d_evi.as<float>());
+      K += counts[t * 5 + 4];
+    }
+    if (K < 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: no clear land pixel to fit on -- the reference fails in np.percentile here");
+    {
+      std::vector<SelectJob> jobs(6, SelectJob{d_evi.as<float>(), 1, K, 0});
+      std::vector<double> q = {2 / 100.0, 20 / 100.0, 40 / 100.0, 60 / 100.0, 80 / 100.0, 98 / 100.0};
+      if ((rc = run_quantiles(jobs, q, 0, d_qout.as<float>()))) return rc;
+    }
+    CF_LAUNCH(k_strata, cdiv(K, 256), 256, d_evi.as<float>(), d_qout.as<float>(), K, d_lab.as<unsigned char>());
+    lab.resize(K);
+    STC_CUDA(cudaMemcpyAsync(lab.data(), d_lab.p, K, cudaMemcpyDeviceToHost, ctx->stream));
+    CF_SYNC();
+    // sampling bookkeeping (:447-497): index lists per stratum, Python random.shuffle, concatenate, shuffle, truncate
+    std::vector<int> p2, p20, p40, p60, p80, p100, p98;
+    for (int r = 0; r < K; ++r) {
+      unsigned char m = lab[r];
+      if (m & 1) p2.push_back(r);
+      if (m & 2) p20.push_back(r);
+      if (m & 4) p40.push_back(r);
+      if (m & 8) p60.push_back(r);
+      if (m & 16) p80.push_back(r);
+      if (m & 32) p100.push_back(r);
+      if (m & 64) p98.push_back(r);
+    }
+    for (auto* v : {&p20, &p40, &p60, &p80, &p100})      // p2 / p98 go through np.repeat first, which accepts a 0-d array
+      if (v->size() == 1)
+        STC_FAIL(STC_ERR_STATE, "remove_clouds: single-element EVI stratum -- the reference raises TypeError (shuffle of a 0-d array)");
+    auto repeat10 = [](std::vector<int>& v) { std::vector<int> o; o.reserve(v.size() * 10); for (int x : v) for (int k = 0; k < 10; ++k) o.push_back(x); v.swap(o); };
+    repeat10(p98); repeat10(p2);
+    rng.shuffle(p2); rng.shuffle(p98); rng.shuffle(p20); rng.shuffle(p40); rng.shuffle(p60); rng.shuffle(p80); rng.shuffle(p100);
+    const size_t n_i = (size_t)(std::min(90000, K) / 5);
+    std::vector<int> sample;
+    auto append = [&](const std::vector<int>& v, size_t limit) { sample.insert(sample.end(), v.begin(), v.begin() + std::min(limit, v.size())); };
+    append(p2, p2.size()); append(p20, n_i); append(p40, n_i); append(p60, n_i); append(p80, n_i); append(p100, n_i); append(p98, p98.size());
+    rng.shuffle(sample);
+    if ((int)sample.size() > K) sample.resize(K);
+    const int S = (int)sample.size();
+    STC_CUDA(cudaMemcpyAsync(d_sample.p, sample.data(), (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int gb = std::min(gram_blocks, cdiv(S, GRAM_ROWS));
+    CF_LAUNCH(k_gram, gb, 640, tiles, mosaic, d_snow.as<float>(), d_rowsrc.as<int>(), d_sample.as<int>(), S, HW, d_partial.as<double>());
+    CF_LAUNCH(k_gram_reduce, 1, 640, d_partial.as<double>(), gb, d_gram.as<double>());
+    CF_LAUNCH(k_nnls, 1, 32, d_gram.as<double>(), S, d_coef.as<double>(), d_status.as<int>());
+    int status[10];
+    STC_CUDA(cudaMemcpyAsync(status, d_status.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
+    CF_SYNC();      // also keeps `sample` alive until uploaded
+    for (int b = 0; b < 10; ++b)
+      if (status[b] != 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: NNLS did not converge (scipy.optimize.nnls raises RuntimeError)");
+    CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, d_snow.as<float>(),
+              d_coef.as<double>(), 1, HW);
+  }
+  memcpy(mt_state, rng.mt, 624 * 4); mt_state[624] = (uint32_t)rng.idx;
+
+  // ---- 4. residual clouds in the mosaic (:703-732) ----
+  maskop_dilate(ctx, d_pfall.as<unsigned char>(), pf, 1, H, W, 10, 1, 0, 0, 0);      // pfcps[0] (single frame when n == 1)
+  STC_CUDA(cudaMemsetAsync(cnt, 0, 8, ctx->stream));
+  CF_LAUNCH(k_only_one, cdiv(HW, 256), 256, areas, pf, n, HW, u8a, cnt);
+  int only_cnt = 0;
+  STC_CUDA(cudaMemcpyAsync(&only_cnt, cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CF_SYNC();
+  if (only_cnt != HW) {
+    CF_LAUNCH(k_not, cdiv(HW, 256), 256, u8a, flag, HW);
+    CF_LAUNCH(k_scan_flags, 1, 1024, flag, HW, d_pos.as<int>(), cnt);
+    float* blue = d_src_rows.as<float>(); float* red = d_ref_rows.as<float>();
+    CF_LAUNCH(k_gather_br, cdiv(HW, 256), 256, mosaic, d_pos.as<int>(), HW, blue, red);
+    const int K2 = HW - only_cnt;
+    std::vector<SelectJob> jobs = {SelectJob{blue, 1, K2, 0}, SelectJob{red, 1, K2, 0}};
+    if ((rc = run_quantiles(jobs, {99 / 100.0, 99 / 100.0}, 0, d_qout.as<float>()))) return rc;
+    CF_LAUNCH(k_mosaic_clouds, cdiv(HW, 256), 256, mosaic, u8a, pf, d_qout.as<float>(), HW, u8b);
+    maskop_dilate(ctx, u8b, flag, 1, H, W, 3, 1, 1, 0, 0);
+    maskop_dilate(ctx, flag, u8b, 1, H, W, 8, 1, 1, 0, 0);
+    CF_LAUNCH(k_add_clip, cdiv(N, 256), 256, areas, u8b, n, HW);
+  }
+  STC_CUDA(cudaGetLastError());
+  STC_CUDA(cudaMemcpyAsync(tiles_host, tiles, N * 40, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(areas_host, areas, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CF_SYNC();
+  return STC_OK;
+}
