@@ -159,7 +159,11 @@ __global__ void __launch_bounds__(256) k_build_sentinel2(const float* __restrict
       AxisTap ty = axis_tap(y - oy, ph, H - oy), tx = axis_tap(x - ox, pw, W - ox);
       auto pooled = [&](int i, int j) {
         const float* m = src + ((int64_t)(2 * i + oy) * w + (2 * j + ox)) * 6 + b;
-        return __fdiv_rn(__fadd_rn(__fadd_rn(m[0], m[6]), __fadd_rn(m[(int64_t)w * 6], m[(int64_t)w * 6 + 6])), 4.f);
+        // np.mean(axis=(1,3)) of the (ph,2,pw,2) view: row pairs first; with a single pooled column NumPy
+        // coalesces the 2x2 block into one contiguous run of four and adds it left to right
+        const float a = m[0], b2 = m[6], c2 = m[(int64_t)w * 6], d = m[(int64_t)w * 6 + 6];
+        const float s4 = (pw == 1) ? __fadd_rn(__fadd_rn(__fadd_rn(a, b2), c2), d) : __fadd_rn(__fadd_rn(a, b2), __fadd_rn(c2, d));
+        return __fdiv_rn(s4, 4.f);
       };
       double acc = 0.0;
       acc = __dadd_rn(acc, __dmul_rn(__dmul_rn((double)pooled(ty.i0, tx.i0), ty.w0), tx.w0));
