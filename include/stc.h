@@ -146,6 +146,29 @@ int stc_gauss_mosaic_host(stc_ctx* ctx, const float* preds_host, const int32_t* 
                           const int32_t* placed, const float* gauss_host, const float* mult_host,
                           int n, int S, int out_h, int out_w, uint8_t* out_host);
 
+/* ---- np.sum of `nseg` contiguous float32 segments of length `len` in NumPy's pairwise order (bit-identical
+ *      to np.sum on a contiguous array): mode 0 plain; mode 1 values < 255 are multiplied by 100 first (the
+ *      in-place scaling + "is this subtile all no-data" sum of load_mosaic_predictions,
+ *      src/download_and_predict_job.py:1570-1573); mode 2 NaN -> 0 and valid[s] = number of non-NaN values
+ *      (np.nanmean of calc_overlap's difference maps, :1503-1512).  valid_host may be NULL. ---- */
+int stc_np_sum_host(stc_ctx* ctx, const float* data_host, int nseg, int len, int mode, float* sum_host, int32_t* valid_host);
+
+/* ---- normalize_subtile (src/download_and_predict_job.py:316-325), in place on x [npx,C] float32:
+ *      clip to [min,max] then (x - (max+min)/2) / ((max-min)/2), constants are Python floats (double). ---- */
+int stc_normalize_host(stc_ctx* ctx, float* x_host, int64_t npx, int C, const double* mins, const double* maxs);
+
+/* ---- identify_bright_bare_surfaces (src/download_and_predict_job.py:1099-1122): img [F,H,W,C>=9] float32 ->
+ *      ramp [(H-14),(W-14)] float64 = min(EDT,3)/3 of the opened bright-surface mask, cropped by 7. ---- */
+int stc_bright_bare_host(stc_ctx* ctx, const float* img_host, int F, int H, int W, int C, double* ramp_host);
+
+/* ---- post-filters of the subtile loop (src/download_and_predict_job.py:1408-1409,1451-1483): bright-bare
+ *      attenuation, no-image block vote -> 255 (S == 158: 4x4 blocks of 40 px, > 25 %; S == 142: 9x9 blocks of
+ *      16 px, > 75 %), np.around(.., 3).  preds [S,S] float32, img [F,S+14,S+14,C] (stack BEFORE
+ *      normalisation), min_clear [S+14,S+14] float32 (min_clear_images_per_date before its [6:-6] crop)
+ *      -> out [S,S] float32. ---- */
+int stc_postprocess_subtile_host(stc_ctx* ctx, const float* preds_host, const float* img_host, const float* min_clear_host,
+                                 int S, int F, int C, float* out_host);
+
 /* ---- storage codecs and the Sentinel-1 dB transform.
  *      to_float32 (src/tof/tof_downloading.py:64-72): uint16 -> x/65535 float32;
  *      to_int16 (:51-61): trunc(clip(x,0,1)*65535) -> uint16;

@@ -85,6 +85,10 @@ SYMBOLS = [
     ("stc_missing_px_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("stc_median_fill_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_build_sentinel2_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_np_sum_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    ("stc_normalize_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    ("stc_bright_bare_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_postprocess_subtile_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_remove_clouds_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     ("stc_cloud_masks_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -418,6 +422,49 @@ class StcSession:
             return clouds, fcps.astype(bool), tap
         return clouds, fcps.astype(bool)
 
+    def np_sum(self, data, mode=0):
+        """np.sum of every row of a contiguous float32 [nseg, len] array in NumPy's pairwise order.
+        mode 1: values < 255 scaled by 100 first; mode 2: nan-sum.  Returns (sums float32, valid counts)."""
+        a = np.ascontiguousarray(data, np.float32)
+        nseg, ln = a.shape
+        sums = np.empty(nseg, np.float32)
+        valid = np.empty(nseg, np.int32)
+        self._check(self.lib.stc_np_sum_host(self.h, _dptr(a), nseg, ln, int(mode), _dptr(sums), _dptr(valid)))
+        return sums, valid
+
+    def normalize(self, x, mins, maxs):
+        """normalize_subtile arithmetic in place on a C-contiguous float32 [..., C] array."""
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous):
+            raise ValueError("normalize needs a C-contiguous float32 array (normalised in place)")
+        Cc = x.shape[-1]
+        mn = np.ascontiguousarray(mins, np.float64)
+        mx = np.ascontiguousarray(maxs, np.float64)
+        if mn.shape != (Cc,) or mx.shape != (Cc,):
+            raise ValueError("need %d minima / maxima" % Cc)
+        self._check(self.lib.stc_normalize_host(self.h, _dptr(x), x.size // Cc, Cc, _dptr(mn), _dptr(mx)))
+        return x
+
+    def bright_bare(self, img):
+        """identify_bright_bare_surfaces: img [F,H,W,C] -> float64 ramp [(H-14),(W-14)]."""
+        a = np.ascontiguousarray(img, np.float32)
+        F, H, W, Cc = a.shape
+        out = np.empty((H - 14, W - 14), np.float64)
+        self._check(self.lib.stc_bright_bare_host(self.h, _dptr(a), F, H, W, Cc, _dptr(out)))
+        return out
+
+    def postprocess_subtile(self, preds, subtile_all, min_clear):
+        """Post-filters of the subtile loop (:1408-1409,1451-1483) -> float32 [S,S]."""
+        p = np.ascontiguousarray(preds, np.float32)
+        a = np.ascontiguousarray(subtile_all, np.float32)
+        m = np.ascontiguousarray(min_clear, np.float32)
+        S = p.shape[0]
+        F, H, W, Cc = a.shape
+        if p.shape != (S, S) or (H, W) != (S + 14, S + 14) or m.shape != (S + 14, S + 14):
+            raise ValueError("shapes %r / %r / %r are not (S,S) / (F,S+14,S+14,C) / (S+14,S+14)" % (p.shape, a.shape, m.shape))
+        out = np.empty((S, S), np.float32)
+        self._check(self.lib.stc_postprocess_subtile_host(self.h, _dptr(p), _dptr(a), _dptr(m), S, F, Cc, _dptr(out)))
+        return out
+
     def remove_clouds(self, tiles, probs, pfcps, mt_state, want_mosaic=False):
         """remove_cloud_and_shadows core (cloud_removal.py:888-973).  tiles: C-contiguous float32 [n,H,W,10],
         rewritten in place.  mt_state: uint32[625] (Python `random.getstate()[1]`), advanced in place.
@@ -450,10 +497,10 @@ class StcSession:
         P = np.empty((n, S, S), np.float32)
         placed = np.zeros(n, np.int32)
         for i, a in enumerate(preds):
-            scaled = np.array(a)                             # copy: the reference scales in place (:1570)
-            scaled[scaled < 255] = scaled[scaled < 255] * 100
-            placed[i] = int(np.sum(scaled) < S * S * 255)    # :1573 all-no-data subtiles are skipped
             P[i] = np.asarray(a, np.float32)
+        # :1570-1573: values < 255 are scaled by 100, an all-no-data subtile (sum == S*S*255) is skipped
+        sums, _ = self.np_sum(P.reshape(n, S * S), mode=1)
+        placed[:] = sums < S * S * 255
         xs = np.ascontiguousarray(xs, np.int32)
         ys = np.ascontiguousarray(ys, np.int32)
         gauss = np.ascontiguousarray(fspecial_gauss(S, sigma), np.float32)
@@ -461,12 +508,11 @@ class StcSession:
         if placed.all():                                     # an unplaced subtile makes calc_overlap raise -> no reweighting (:1597-1608)
             diffs = np.empty((n, S, S), np.float32)
             self._check(self.lib.stc_mosaic_diffs_host(self.h, _dptr(P), _dptr(xs), _dptr(ys), _dptr(placed), n, S, _dptr(diffs)))
-            import warnings
-            with np.errstate(all="ignore"), warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                ratios = np.zeros(n, np.float32)
-                for i in range(n):
-                    ratios[i] = np.nanmean(diffs[i])          # NumPy's own pairwise float32 reduction (:1512)
+            # np.nanmean of every difference map (:1512): pairwise float32 sum of the non-NaN values on the GPU,
+            # float32(sum / count) like NumPy's scalar path; what is left here are n scalars
+            sums, valid = self.np_sum(diffs.reshape(n, S * S), mode=2)
+            with np.errstate(all="ignore"):
+                ratios = (sums.astype(np.float64) / valid).astype(np.float32)
                 mult = (np.median(ratios) / ratios).astype(np.float32)
                 mult[mult > 1.5] = 1.5
         out = np.empty(out_shape, np.uint8)
@@ -479,15 +525,17 @@ class StcSession:
 # ======================================================================================
 # reference-signature functions
 # ======================================================================================
-def normalize_subtile(subtile, min_all=MIN_ALL, max_all=MAX_ALL):
-    """src/download_and_predict_job.py:316-325 -- in place, returns the same array.
-    (Host-side NumPy: the device path fuses this into the model's input packing.)"""
-    for band in range(0, subtile.shape[-1]):
-        mins, maxs = min_all[band], max_all[band]
-        subtile[..., band] = np.clip(subtile[..., band], mins, maxs)
-        midrange = (maxs + mins) / 2
-        rng = maxs - mins
-        subtile[..., band] = (subtile[..., band] - midrange) / (rng / 2)
+def normalize_subtile(subtile, min_all=MIN_ALL, max_all=MAX_ALL, sess=None):
+    """src/download_and_predict_job.py:316-325 -- in place, returns the same array.  Runs on the GPU
+    (stc_normalize_host); the batched predict path (`StcSession.predict(..., normalize=True)`,
+    `predict_patches`) fuses the same arithmetic into the model's input packing instead."""
+    if sess is None:
+        raise RuntimeError("normalize_subtile needs an StcSession (sess=...); there is no CPU path")
+    if isinstance(subtile, np.ndarray) and subtile.dtype == np.float32 and subtile.flags.c_contiguous:
+        return sess.normalize(subtile, min_all, max_all)
+    work = np.ascontiguousarray(subtile, np.float32)
+    sess.normalize(work, min_all, max_all)
+    subtile[...] = work
     return subtile
 
 
@@ -499,7 +547,8 @@ def predict_subtile(subtile, sess, op=None, size=None):
     if np.sum(subtile) != 0:
         if not isinstance(subtile.flat[0], np.floating):
             assert np.max(subtile) > 1
-            subtile = subtile / 65535.
+            # `subtile / 65535.` (float64) followed by astype(float32) == correctly rounded float32 x/65535
+            subtile = sess.to_float32(np.ascontiguousarray(subtile).astype(np.uint16, copy=False))
         batch_x = subtile[np.newaxis].astype(np.float32)
         preds = sess.predict(batch_x, length=sess.length).squeeze()
         clip = (preds.shape[0] - size) // 2
@@ -635,42 +684,20 @@ def identify_clouds_shadows(img, dem, bbx, sess):
 
 def identify_bright_bare_surfaces(img, sess):
     """src/download_and_predict_job.py:1099-1122: NIR/SWIR < 0.9, mean RGB > 0.2, EVI < 0.3 in more
-    than one frame -> open/close by dilations -> ramp min(EDT,3)/3, cropped by 7 px (float64).
-    The neighbourhood work (dilations, distance transform) runs on the GPU."""
-    BLUE, RED, NIR = np.clip(img[..., 0], 0, 1), np.clip(img[..., 2], 0, 1), np.clip(img[..., 3], 0, 1)
-    evis = np.clip(2.5 * ((NIR - RED) / (NIR + (6 * RED) - (7.5 * BLUE) + 1)), -1.5, 1.5)
-    cand = (img[..., 3] / (img[..., 8] + 0.01)) < 0.9
-    cand = cand * (np.mean(img[..., :3], axis=-1) > 0.2)
-    cand = cand * (evis < 0.3)
-    bright = np.sum(cand, axis=0) > 1
-    bright = sess.binary_dilation(1 - bright, iterations=2)
-    bright = sess.binary_dilation(1 - bright, iterations=1)
-    blurred = sess.edt_capped(bright, 3) / 3
-    return blurred[7:-7, 7:-7]
+    than one frame -> open by dilations -> ramp min(EDT,3)/3, cropped by 7 px (float64).
+    One GPU call (stc_bright_bare_host)."""
+    return sess.bright_bare(img)
 
 
 def postprocess_subtile(preds, subtile_all, min_clear_images_per_date, sess, size=158):
     """Post-filters of the subtile loop, src/download_and_predict_job.py:1408-1409,1451-1483:
     no-image 40x40 block vote -> 255, bright-bare-surface attenuation, round to 3 decimals.
-    `subtile_all` is the (5, size+14, size+14, 17) stack BEFORE normalize_subtile."""
-    bright_surface = identify_bright_bare_surfaces(subtile_all, sess)
-    preds = np.array(preds, copy=True)
-    m = min_clear_images_per_date[6:-6, 6:-6]
-    no_images = m < 1
-    no_images = 1 - sess.binary_dilation(1 - no_images, iterations=6, connectivity=2)
-    no_images = sess.binary_dilation(no_images, iterations=6, connectivity=2)
-    if size == 158:
-        blocks, bs, frac = 4, 40, 0.25
-    elif size == 142:
-        blocks, bs, frac = 9, 16, 0.75
-    else:
-        blocks = None
-    if blocks:
-        v = np.reshape(no_images, (blocks, bs, blocks, bs)).sum(axis=(1, 3)) > (bs * bs) * frac
-        v = v.repeat(bs, axis=0).repeat(bs, axis=1)[1:-1, 1:-1]
-        preds[v] = 255.
-    preds = np.around(preds * bright_surface, 3)
-    return preds.astype(np.float32)
+    `subtile_all` is the (5, size+14, size+14, 17) stack BEFORE normalize_subtile,
+    `min_clear_images_per_date` the (size+14, size+14) map before its [6:-6] crop.
+    One GPU call (stc_postprocess_subtile_host)."""
+    if np.asarray(preds).shape != (size, size):
+        raise ValueError("preds shape %r is not (%d, %d)" % (np.asarray(preds).shape, size, size))
+    return sess.postprocess_subtile(preds, subtile_all, min_clear_images_per_date)
 
 
 def id_areas_to_interp(tiles, probs, shadows, image_dates, pfcps, sess):

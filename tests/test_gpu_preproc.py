@@ -46,3 +46,32 @@ def test_temporal_matmul_vs_reference_smooth(sess):
     b = r.uniform(0, 0.5, a.shape).astype(np.float32)
     lhs = sess.temporal_matmul(a + b, M)
     assert np.abs(lhs - (sess.temporal_matmul(a, M) + sess.temporal_matmul(b, M))).max() < 2e-6
+
+
+@pytest.mark.gpu
+def test_normalize_subtile_gpu_matches_reference_golden(sess):
+    """normalize_subtile (:316-325) on the GPU: bit-exact against the reference's own output."""
+    import os
+    from sentinel_tree_cover_b200.api import normalize_subtile
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "preproc.npz"))
+    x = g["norm_in"].copy()
+    out = normalize_subtile(x, sess=sess)
+    assert out is x
+    assert np.array_equal(x, g["norm_out"])
+    with pytest.raises(RuntimeError):
+        normalize_subtile(g["norm_in"].copy())
+
+
+@pytest.mark.gpu
+def test_np_sum_matches_numpy_pairwise(sess):
+    r = np.random.default_rng(5)
+    for ln in (1, 7, 8, 127, 128, 129, 1000, 24964, 100003):
+        a = (r.random((3, ln)) * r.choice([1e-4, 1.0, 1e4], (3, ln))).astype(np.float32)
+        s, v = sess.np_sum(a, 0)
+        assert np.array_equal(s, np.array([np.sum(a[i]) for i in range(3)], np.float32)), ln
+        b = a.copy(); b[r.random(b.shape) < 0.1] = np.nan
+        s, v = sess.np_sum(b, 2)
+        with np.errstate(all="ignore"):
+            want = np.array([np.nanmean(b[i]) for i in range(3)], np.float32)
+        got = (s.astype(np.float64) / v).astype(np.float32)
+        assert np.array_equal(got, want, equal_nan=True), ln
