@@ -168,42 +168,80 @@ __device__ float block_radix_select(const float* __restrict__ data, int64_t stri
   __syncthreads();
   return __uint_as_float(u);
 }
-// quantile q of each job's column with NumPy's float32 lerp (q = 0.5 gives np.median's (a+b)/2 for even n:
-// a + (b-a)*0.5 differs from (a+b)/2 in float32, so the median has its own flag)
+// the order statistic of rank k+1 given a = rank k: a again if more than k+1 values are <= a, else min(x > a)
+__device__ float block_next_stat(const float* __restrict__ data, int64_t stride, int n, float a, int k) {
+  __shared__ int cnt_le; __shared__ unsigned min_gt;
+  if (threadIdx.x == 0) { cnt_le = 0; min_gt = 0xffffffffu; }
+  __syncthreads();
+  unsigned ka = __float_as_uint(a); ka ^= (ka >> 31) ? 0xffffffffu : 0x80000000u;
+  int c = 0; unsigned mn = 0xffffffffu;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    unsigned u = __float_as_uint(data[(int64_t)i * stride]); u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
+    if (u <= ka) ++c; else if (u < mn) mn = u;
+  }
+  for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); unsigned t = __shfl_xor_sync(0xffffffffu, mn, o); mn = t < mn ? t : mn; }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt_le, c); atomicMin(&min_gt, mn); }
+  __syncthreads();
+  float b;
+  if (cnt_le >= k + 2) b = a;
+  else { unsigned u = min_gt; u ^= (u >> 31) ? 0x80000000u : 0xffffffffu; b = __uint_as_float(u); }
+  __syncthreads();
+  return b;
+}
+// quantile q of each job's column with NumPy's float32 lerp (np.median's even case is (a+b)/2, which differs from
+// a + (b-a)*0.5 in float32, so the median has its own flag)
 __global__ void __launch_bounds__(1024) k_quantile(const SelectJob* __restrict__ jobs, const double* __restrict__ q, int median_mode,
                                                    float* __restrict__ out) {
   const SelectJob j = jobs[blockIdx.x];
   if (j.n <= 0) { if (threadIdx.x == 0) out[blockIdx.x] = nanf(""); return; }
   if (median_mode) {
     float a = block_radix_select(j.data, j.stride, j.n, (j.n - 1) / 2);
-    float b = (j.n & 1) ? a : block_radix_select(j.data, j.stride, j.n, j.n / 2);
+    float b = (j.n & 1) ? a : block_next_stat(j.data, j.stride, j.n, a, (j.n - 1) / 2);
     if (threadIdx.x == 0) out[blockIdx.x] = (j.n & 1) ? a : __fdiv_rn(__fadd_rn(a, b), 2.f);
     return;
   }
   int lo; float g;
   np_quantile_pos(j.n, q[blockIdx.x], lo, g);
   float a = block_radix_select(j.data, j.stride, j.n, lo);
-  float b = (lo + 1 < j.n) ? block_radix_select(j.data, j.stride, j.n, lo + 1) : a;
+  float b = (lo + 1 < j.n && g != 0.f) ? block_next_stat(j.data, j.stride, j.n, a, lo) : a;
   if (threadIdx.x == 0) out[blockIdx.x] = np_lerp(a, b, g);
 }
 
 // np.nanstd(rows, axis=0) of a [K][10] float32 matrix: NumPy reduces axis 0 row by row, i.e. each column is a
-// SEQUENTIAL float32 sum.  One warp per column; lanes prefetch 32 rows, every lane replays the same chain.
+// SEQUENTIAL float32 sum (a dependent chain of K adds, 4 clk each at best).  One warp per column: the 32 lanes
+// prefetch a tile of 512 rows into shared memory (double-buffered through registers), then every lane replays
+// the same chain from broadcast shared-memory reads, so the loads are off the dependency chain.
 // grid = 2 matrices, block = 10 warps.
+#define CS_TILE 512
 __global__ void __launch_bounds__(320) k_col_std(const float* __restrict__ m0, const float* __restrict__ m1, int K, float* __restrict__ out) {
+  __shared__ float tile[10][CS_TILE];
   const float* m = blockIdx.x ? m1 : m0;
   const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tl = tile[c];
   float avg = 0.f;
   for (int pass = 0; pass < 2; ++pass) {
     float s = 0.f;
-    float nxt = (lane < K) ? m[(int64_t)lane * 10 + c] : 0.f;
-    for (int r0 = 0; r0 < K; r0 += 32) {
-      float v = nxt;
-      int rn = r0 + 32 + lane;
-      nxt = (rn < K) ? m[(int64_t)rn * 10 + c] : 0.f;
-      if (pass) { float d = __fsub_rn(v, avg); v = __fmul_rn(d, d); }
-      const int cnt = (K - r0) < 32 ? (K - r0) : 32;
-      for (int l = 0; l < cnt; ++l) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, l));
+    float pre[CS_TILE / 32];
+#pragma unroll
+    for (int j = 0; j < CS_TILE / 32; ++j) { int r = j * 32 + lane; pre[j] = (r < K) ? m[(int64_t)r * 10 + c] : 0.f; }
+    for (int r0 = 0; r0 < K; r0 += CS_TILE) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < CS_TILE / 32; ++j) {
+        float v = pre[j];
+        if (pass) { float d = __fsub_rn(v, avg); v = __fmul_rn(d, d); }
+        tl[j * 32 + lane] = v;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < CS_TILE / 32; ++j) { int r = r0 + CS_TILE + j * 32 + lane; pre[j] = (r < K) ? m[(int64_t)r * 10 + c] : 0.f; }
+      const int cnt = (K - r0) < CS_TILE ? (K - r0) : CS_TILE;
+      if (cnt == CS_TILE) {
+#pragma unroll 16
+        for (int l = 0; l < CS_TILE; ++l) s = __fadd_rn(s, tl[l]);
+      } else {
+        for (int l = 0; l < cnt; ++l) s = __fadd_rn(s, tl[l]);
+      }
     }
     float r = (float)((double)s / (double)K);
     if (pass == 0) avg = r; else if (lane == 0) out[blockIdx.x * 10 + c] = __fsqrt_rn(r);
