@@ -1,0 +1,224 @@
+// Array work of process_tile's front half (src/download_and_predict_job.py:684-832, 995-997) that is not
+// already covered by the codec / upsampling / cloud kernels: Sentinel-1 saturated-value fill, DEM 5x5
+// median filter, the Sen2Cor consecutive-date rule, the snow mask, per-date threshold counts, clip / scale.
+// All HBM-bound single-pass kernels.
+#include "stc_common.cuh"
+
+void maskop_dilate(stc_ctx* ctx, const unsigned char* in, unsigned char* out, int frames, int H, int W, int k, int conn, int inv_in,
+                   int inv_out, int three_d);
+
+namespace {
+
+struct TBuf { void* p = nullptr; ~TBuf() { if (p) cudaFree(p); } template <typename T> T* as() { return (T*)p; } };
+
+// ---- exact median of every contiguous float32 segment (np.median of a 1-D array), one block per segment ----
+__device__ float seg_radix_select(const float* __restrict__ data, int n, int k) {
+  __shared__ int hist[256]; __shared__ unsigned prefix; __shared__ int kth;
+  if (threadIdx.x == 0) { prefix = 0; kth = k; }
+  __syncthreads();
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned pre = prefix;
+    const unsigned mask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      unsigned u = __float_as_uint(data[i]); u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
+      if ((u & mask) == (pre & mask)) atomicAdd(&hist[(u >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int kk = kth, b = 0;
+      while (b < 255 && kk >= hist[b]) { kk -= hist[b]; ++b; }
+      kth = kk; prefix = pre | ((unsigned)b << shift);
+    }
+    __syncthreads();
+  }
+  unsigned u = prefix; u ^= (u >> 31) ? 0x80000000u : 0xffffffffu;
+  __syncthreads();
+  return __uint_as_float(u);
+}
+// s1_i[s1_i == 1] = np.median(s1_i[s1_i < 65535]) (:702-705): the median runs over ALL values of the date
+// (both polarisations; every value is < 65535 after the /65535 scaling), then replaces the saturated ones
+__global__ void __launch_bounds__(1024) k_s1_fill(float* __restrict__ s1, int len) {
+  float* a = s1 + (int64_t)blockIdx.x * len;
+  __shared__ int any_one;
+  if (threadIdx.x == 0) any_one = 0;
+  __syncthreads();
+  int f = 0;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) f |= (a[i] == 1.0f);
+  if (f) any_one = 1;
+  __syncthreads();
+  if (!any_one) return;
+  float lo = seg_radix_select(a, len, (len - 1) / 2);
+  float hi = (len & 1) ? lo : seg_radix_select(a, len, len / 2);
+  const float med = (len & 1) ? lo : __fdiv_rn(__fadd_rn(lo, hi), 2.f);
+  for (int i = threadIdx.x; i < len; i += blockDim.x) if (a[i] == 1.0f) a[i] = med;
+}
+
+// scipy.ndimage.median_filter(dem, size=5), mode='reflect' (d c b a | a b c d): rank 12 of the 25 window values
+__global__ void __launch_bounds__(256) k_median5(const float* __restrict__ in, int H, int W, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  const int y = i / W, x = i % W;
+  float v[25]; int n = 0;
+  for (int dy = -2; dy <= 2; ++dy) {
+    int yy = y + dy;
+    while (yy < 0 || yy >= H) yy = yy < 0 ? -yy - 1 : 2 * H - 1 - yy;
+    for (int dx = -2; dx <= 2; ++dx) {
+      int xx = x + dx;
+      while (xx < 0 || xx >= W) xx = xx < 0 ? -xx - 1 : 2 * W - 1 - xx;
+      v[n++] = in[yy * W + xx];
+    }
+  }
+  for (int a = 1; a < 25; ++a) { float t = v[a]; int b = a - 1; while (b >= 0 && v[b] > t) { v[b + 1] = v[b]; --b; } v[b + 1] = t; }
+  out[i] = v[12];
+}
+
+// Sen2Cor mask rule (:688-695): walking the dates in order, a pixel flagged in two consecutive dates is cleared in both
+__global__ void __launch_bounds__(256) k_clm_pairs(float* __restrict__ clm, int n, int HW) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  for (int i = 0; i < n; ++i) {
+    const int lo = i - 1 > 0 ? i - 1 : 0, hi = i + 1 < n ? i + 1 : n;      // frames [lo, hi)
+    float s = 0.f;
+    for (int t = lo; t < hi; ++t) s = __fadd_rn(s, clm[(int64_t)t * HW + p]);
+    if (s == 2.f) for (int t = lo; t < hi; ++t) clm[(int64_t)t * HW + p] = 0.f;
+  }
+}
+
+// snow_filter(arr) > 0 (:808-825): per-date counts and the per-pixel count over dates
+__device__ __forceinline__ bool snow_flag(const float* x) {
+  float ndsi = __fdiv_rn(__fsub_rn(x[1], x[8]), __fadd_rn(x[1], x[8]));
+  if (ndsi < 0.10f) ndsi = 0.f;
+  if (ndsi > 0.42f) ndsi = 0.42f;
+  float p = __fdiv_rn(__fsub_rn(ndsi, 0.1f), 0.32f);
+  if (x[3] < 0.10f) p = 0.f;
+  if (x[3] > 0.35f && p > 0.f) p = 1.f;
+  if (x[0] < 0.10f) p = 0.f;
+  if (x[0] > 0.22f && p > 0.f) p = 1.f;
+  if (__fdiv_rn(x[0], x[2]) < 0.75f) p = 0.f;
+  return p > 0.f;
+}
+__global__ void __launch_bounds__(256) k_snow(const float* __restrict__ s2, int n, int HW, int* __restrict__ per_date,
+                                              unsigned char* __restrict__ low_snow /* mean_t < 0.7 */) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = 0;
+  for (int t = 0; t < n; ++t) {
+    bool f = p < HW && snow_flag(s2 + ((int64_t)t * HW + p) * 10);
+    c += f;
+    unsigned bal = __ballot_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(per_date + t, __popc(bal));
+  }
+  if (p < HW) low_snow[p] = ((double)c / (double)n) < 0.7;
+}
+
+__global__ void __launch_bounds__(256) k_count_gt(const float* __restrict__ data, int len, float thresh, int* __restrict__ out) {
+  const int sgm = blockIdx.y; int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool f = i < len && data[(int64_t)sgm * len + i] > thresh;
+  unsigned bal = __ballot_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(out + sgm, __popc(bal));
+}
+// mode 0: np.clip(x, lo, hi) (NaN kept)     mode 1: x / lo
+__global__ void __launch_bounds__(256) k_elementwise(float* __restrict__ x, int64_t n, int mode, float lo, float hi) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = x[i];
+  if (mode == 0) { if (!isnan(v)) v = fminf(fmaxf(v, lo), hi); }
+  else v = __fdiv_rn(v, lo);
+  x[i] = v;
+}
+// a = max(a, b with fcps zeroed)  (clm[fcps] = 0; cloudshad = np.maximum(cloudshad, clm), :842-845)
+__global__ void __launch_bounds__(256) k_max_masked(float* __restrict__ a, const float* __restrict__ b, const unsigned char* __restrict__ zero,
+                                                    int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float bv = (zero && zero[i]) ? 0.f : b[i];
+  a[i] = fmaxf(a[i], bv);
+}
+
+}  // namespace
+
+#define TP_FINISH() do { STC_CUDA(cudaStreamSynchronize(ctx->stream)); STC_CUDA(cudaGetLastError()); return STC_OK; } while (0)
+
+extern "C" int stc_s1_fill_host(stc_ctx* ctx, float* s1_host, int m, int H, int W, int C) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!s1_host || m < 1 || H < 1 || W < 1 || C < 1) STC_FAIL(STC_ERR_ARG, "s1_fill: bad argument");
+  const int len = H * W * C; TBuf d;
+  STC_CUDA(cudaMalloc(&d.p, (size_t)m * len * 4));
+  STC_CUDA(cudaMemcpyAsync(d.p, s1_host, (size_t)m * len * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_s1_fill<<<m, 1024, 0, ctx->stream>>>(d.as<float>(), len); ctx->launches++;
+  STC_CUDA(cudaMemcpyAsync(s1_host, d.p, (size_t)m * len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TP_FINISH();
+}
+
+extern "C" int stc_median_filter5_host(stc_ctx* ctx, const float* in_host, int H, int W, float* out_host) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!in_host || !out_host || H < 1 || W < 1) STC_FAIL(STC_ERR_ARG, "median_filter5: bad argument");
+  TBuf a, b;
+  STC_CUDA(cudaMalloc(&a.p, (size_t)H * W * 4)); STC_CUDA(cudaMalloc(&b.p, (size_t)H * W * 4));
+  STC_CUDA(cudaMemcpyAsync(a.p, in_host, (size_t)H * W * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_median5<<<cdiv(H * W, 256), 256, 0, ctx->stream>>>(a.as<float>(), H, W, b.as<float>()); ctx->launches++;
+  STC_CUDA(cudaMemcpyAsync(out_host, b.p, (size_t)H * W * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TP_FINISH();
+}
+
+extern "C" int stc_clm_pairs_host(stc_ctx* ctx, float* clm_host, int n, int H, int W) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!clm_host || n < 1 || H < 1 || W < 1) STC_FAIL(STC_ERR_ARG, "clm_pairs: bad argument");
+  TBuf d; const size_t bytes = (size_t)n * H * W * 4;
+  STC_CUDA(cudaMalloc(&d.p, bytes));
+  STC_CUDA(cudaMemcpyAsync(d.p, clm_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  k_clm_pairs<<<cdiv(H * W, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, H * W); ctx->launches++;
+  STC_CUDA(cudaMemcpyAsync(clm_host, d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TP_FINISH();
+}
+
+extern "C" int stc_snow_host(stc_ctx* ctx, const float* s2_host, int n, int H, int W, int32_t* per_date_host, uint8_t* snow_host) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!s2_host || !per_date_host || !snow_host || n < 1 || H < 1 || W < 1) STC_FAIL(STC_ERR_ARG, "snow: bad argument");
+  const int HW = H * W; TBuf d, cnt, a, b;
+  STC_CUDA(cudaMalloc(&d.p, (size_t)n * HW * 40)); STC_CUDA(cudaMalloc(&cnt.p, n * 4)); STC_CUDA(cudaMalloc(&a.p, HW)); STC_CUDA(cudaMalloc(&b.p, HW));
+  STC_CUDA(cudaMemcpyAsync(d.p, s2_host, (size_t)n * HW * 40, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemsetAsync(cnt.p, 0, n * 4, ctx->stream));
+  k_snow<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, HW, cnt.as<int>(), a.as<unsigned char>()); ctx->launches++;
+  maskop_dilate(ctx, a.as<unsigned char>(), b.as<unsigned char>(), 1, H, W, 2, 1, 0, 1, 0);     // 1 - binary_dilation(snow < 0.7, 2)
+  STC_CUDA(cudaMemcpyAsync(per_date_host, cnt.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(snow_host, b.p, HW, cudaMemcpyDeviceToHost, ctx->stream));
+  TP_FINISH();
+}
+
+extern "C" int stc_count_gt_host(stc_ctx* ctx, const float* data_host, int nseg, int len, float thresh, int32_t* counts_host) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!data_host || !counts_host || nseg < 1 || len < 1) STC_FAIL(STC_ERR_ARG, "count_gt: bad argument");
+  TBuf d, cnt;
+  STC_CUDA(cudaMalloc(&d.p, (size_t)nseg * len * 4)); STC_CUDA(cudaMalloc(&cnt.p, nseg * 4));
+  STC_CUDA(cudaMemcpyAsync(d.p, data_host, (size_t)nseg * len * 4, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemsetAsync(cnt.p, 0, nseg * 4, ctx->stream));
+  k_count_gt<<<dim3(cdiv(len, 256), nseg), 256, 0, ctx->stream>>>(d.as<float>(), len, thresh, cnt.as<int>()); ctx->launches++;
+  STC_CUDA(cudaMemcpyAsync(counts_host, cnt.p, nseg * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TP_FINISH();
+}
+
+extern "C" int stc_elementwise_host(stc_ctx* ctx, float* x_host, int64_t n, int mode, float a, float b) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!x_host || n < 1 || mode < 0 || mode > 1) STC_FAIL(STC_ERR_ARG, "elementwise: bad argument");
+  TBuf d;
+  STC_CUDA(cudaMalloc(&d.p, (size_t)n * 4));
+  STC_CUDA(cudaMemcpyAsync(d.p, x_host, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_elementwise<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, mode, a, b); ctx->launches++;
+  STC_CUDA(cudaMemcpyAsync(x_host, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TP_FINISH();
+}
+
+extern "C" int stc_max_masked_host(stc_ctx* ctx, float* a_host, const float* b_host, const uint8_t* zero_host, int64_t n) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!a_host || !b_host || n < 1) STC_FAIL(STC_ERR_ARG, "max_masked: bad argument");
+  TBuf a, b, z;
+  STC_CUDA(cudaMalloc(&a.p, (size_t)n * 4)); STC_CUDA(cudaMalloc(&b.p, (size_t)n * 4));
+  STC_CUDA(cudaMemcpyAsync(a.p, a_host, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(b.p, b_host, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (zero_host) { STC_CUDA(cudaMalloc(&z.p, (size_t)n)); STC_CUDA(cudaMemcpyAsync(z.p, zero_host, (size_t)n, cudaMemcpyHostToDevice, ctx->stream)); }
+  k_max_masked<<<cdiv(n, 256), 256, 0, ctx->stream>>>(a.as<float>(), b.as<float>(), zero_host ? z.as<unsigned char>() : nullptr, n); ctx->launches++;
+  STC_CUDA(cudaMemcpyAsync(a_host, a.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TP_FINISH();
+}
