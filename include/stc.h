@@ -169,6 +169,26 @@ int stc_bright_bare_host(stc_ctx* ctx, const float* img_host, int F, int H, int 
 int stc_postprocess_subtile_host(stc_ctx* ctx, const float* preds_host, const float* img_host, const float* min_clear_host,
                                  int S, int F, int C, float* out_host);
 
+/* ---- array work of process_tile's front half (src/download_and_predict_job.py:684-832, 995-997) ----
+ * stc_s1_fill_host:        s1 [m,H,W,C] float32 in place: values == 1 of every date are replaced by np.median over
+ *                          ALL values of that date (`s1_i[s1_i == 1] = np.median(s1_i[s1_i < 65535], axis=0)`, :702-705).
+ * stc_median_filter5_host: scipy.ndimage.median_filter(dem, size=5) (mode 'reflect'), :713.
+ * stc_clm_pairs_host:      Sen2Cor mask [n,H,W] float32 in place: in date order, a pixel set in two consecutive
+ *                          dates is cleared in both (:688-695).
+ * stc_snow_host:           snow_filter(sentinel2) > 0 (:808-825): per_date[t] = flagged pixels of date t;
+ *                          snow [H,W] uint8 = 1 - binary_dilation(mean_t < 0.7, iterations=2) (:827-829).
+ * stc_count_gt_host:       counts[s] = #(data[s,:] > thresh) (the np.mean(interp > 0, axis=(1,2)) tests, :863,880,...).
+ * stc_elementwise_host:    mode 0 np.clip(x, a, b) in place (:996), mode 1 x / a in place (`dem / 90`, :995).
+ * stc_max_masked_host:     a = np.maximum(a, b) after `b[zero] = 0` (clm[fcps] = 0; cloudshad = max(cloudshad, clm), :842-845);
+ *                          zero may be NULL. ---- */
+int stc_s1_fill_host(stc_ctx* ctx, float* s1_host, int m, int H, int W, int C);
+int stc_median_filter5_host(stc_ctx* ctx, const float* in_host, int H, int W, float* out_host);
+int stc_clm_pairs_host(stc_ctx* ctx, float* clm_host, int n, int H, int W);
+int stc_snow_host(stc_ctx* ctx, const float* s2_host, int n, int H, int W, int32_t* per_date_host, uint8_t* snow_host);
+int stc_count_gt_host(stc_ctx* ctx, const float* data_host, int nseg, int len, float thresh, int32_t* counts_host);
+int stc_elementwise_host(stc_ctx* ctx, float* x_host, int64_t n, int mode, float a, float b);
+int stc_max_masked_host(stc_ctx* ctx, float* a_host, const float* b_host, const uint8_t* zero_host, int64_t n);
+
 /* ---- storage codecs and the Sentinel-1 dB transform.
  *      to_float32 (src/tof/tof_downloading.py:64-72): uint16 -> x/65535 float32;
  *      to_int16 (:51-61): trunc(clip(x,0,1)*65535) -> uint16;
