@@ -178,7 +178,10 @@ int stc_postprocess_subtile_host(stc_ctx* ctx, const float* preds_host, const fl
  * stc_snow_host:           snow_filter(sentinel2) > 0 (:808-825): per_date[t] = flagged pixels of date t;
  *                          snow [H,W] uint8 = 1 - binary_dilation(mean_t < 0.7, iterations=2) (:827-829).
  * stc_count_gt_host:       counts[s] = #(data[s,:] > thresh) (the np.mean(interp > 0, axis=(1,2)) tests, :863,880,...).
- * stc_elementwise_host:    mode 0 np.clip(x, a, b) in place (:996), mode 1 x / a in place (`dem / 90`, :995).
+ * stc_count_lt_axis0_host: out[i] = #(data[t,i] < thresh over the n dates) (`np.sum(interp_tile < 0.33, axis=0)`, :1355).
+ * stc_elementwise_host:    mode 0 np.clip(x, a, b) in place (:996), mode 1 x / a in place (`dem / 90`, :995),
+ *                          mode 2 NaN -> a in place (interpolate_na_vals, src/preprocessing/interpolation.py:42-56: the
+ *                          NaN-propagating median of a column that holds a NaN is NaN, reset to 0, so every NaN becomes 0).
  * stc_max_masked_host:     a = np.maximum(a, b) after `b[zero] = 0` (clm[fcps] = 0; cloudshad = max(cloudshad, clm), :842-845);
  *                          zero may be NULL. ---- */
 int stc_s1_fill_host(stc_ctx* ctx, float* s1_host, int m, int H, int W, int C);
@@ -186,6 +189,7 @@ int stc_median_filter5_host(stc_ctx* ctx, const float* in_host, int H, int W, fl
 int stc_clm_pairs_host(stc_ctx* ctx, float* clm_host, int n, int H, int W);
 int stc_snow_host(stc_ctx* ctx, const float* s2_host, int n, int H, int W, int32_t* per_date_host, uint8_t* snow_host);
 int stc_count_gt_host(stc_ctx* ctx, const float* data_host, int nseg, int len, float thresh, int32_t* counts_host);
+int stc_count_lt_axis0_host(stc_ctx* ctx, const float* data_host, int n, int64_t len, float thresh, int32_t* out_host);
 int stc_elementwise_host(stc_ctx* ctx, float* x_host, int64_t n, int mode, float a, float b);
 int stc_max_masked_host(stc_ctx* ctx, float* a_host, const float* b_host, const uint8_t* zero_host, int64_t n);
 

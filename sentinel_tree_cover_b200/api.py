@@ -90,6 +90,7 @@ SYMBOLS = [
     ("stc_clm_pairs_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("stc_snow_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("stc_count_gt_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    ("stc_count_lt_axis0_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_void_p]),
     ("stc_elementwise_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float]),
     ("stc_max_masked_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     ("stc_np_sum_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -118,14 +118,23 @@ __global__ void __launch_bounds__(256) k_count_gt(const float* __restrict__ data
   unsigned bal = __ballot_sync(0xffffffffu, f);
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(out + sgm, __popc(bal));
 }
-// mode 0: np.clip(x, lo, hi) (NaN kept)     mode 1: x / lo
+// mode 0: np.clip(x, lo, hi) (NaN kept)     mode 1: x / lo     mode 2: NaN -> lo
 __global__ void __launch_bounds__(256) k_elementwise(float* __restrict__ x, int64_t n, int mode, float lo, float hi) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = x[i];
   if (mode == 0) { if (!isnan(v)) v = fminf(fmaxf(v, lo), hi); }
-  else v = __fdiv_rn(v, lo);
+  else if (mode == 1) v = __fdiv_rn(v, lo);
+  else if (isnan(v)) v = lo;
   x[i] = v;
+}
+// out[i] = #(data[t][i] < thresh over t)   (np.sum(interp < 0.33, axis=0), :1355)
+__global__ void __launch_bounds__(256) k_count_lt_axis0(const float* __restrict__ data, int n, int64_t len, float thresh, int* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  int c = 0;
+  for (int t = 0; t < n; ++t) c += data[(int64_t)t * len + i] < thresh;
+  out[i] = c;
 }
 // a = max(a, b with fcps zeroed)  (clm[fcps] = 0; cloudshad = np.maximum(cloudshad, clm), :842-845)
 __global__ void __launch_bounds__(256) k_max_masked(float* __restrict__ a, const float* __restrict__ b, const unsigned char* __restrict__ zero,
@@ -201,7 +210,7 @@ extern "C" int stc_count_gt_host(stc_ctx* ctx, const float* data_host, int nseg,
 
 extern "C" int stc_elementwise_host(stc_ctx* ctx, float* x_host, int64_t n, int mode, float a, float b) {
   if (!ctx) return STC_ERR_ARG;
-  if (!x_host || n < 1 || mode < 0 || mode > 1) STC_FAIL(STC_ERR_ARG, "elementwise: bad argument");
+  if (!x_host || n < 1 || mode < 0 || mode > 2) STC_FAIL(STC_ERR_ARG, "elementwise: bad argument");
   TBuf d;
   STC_CUDA(cudaMalloc(&d.p, (size_t)n * 4));
   STC_CUDA(cudaMemcpyAsync(d.p, x_host, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -220,5 +229,16 @@ extern "C" int stc_max_masked_host(stc_ctx* ctx, float* a_host, const float* b_h
   if (zero_host) { STC_CUDA(cudaMalloc(&z.p, (size_t)n)); STC_CUDA(cudaMemcpyAsync(z.p, zero_host, (size_t)n, cudaMemcpyHostToDevice, ctx->stream)); }
   k_max_masked<<<cdiv(n, 256), 256, 0, ctx->stream>>>(a.as<float>(), b.as<float>(), zero_host ? z.as<unsigned char>() : nullptr, n); ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(a_host, a.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TP_FINISH();
+}
+
+extern "C" int stc_count_lt_axis0_host(stc_ctx* ctx, const float* data_host, int n, int64_t len, float thresh, int32_t* out_host) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!data_host || !out_host || n < 1 || len < 1) STC_FAIL(STC_ERR_ARG, "count_lt_axis0: bad argument");
+  TBuf d, o;
+  STC_CUDA(cudaMalloc(&d.p, (size_t)n * len * 4)); STC_CUDA(cudaMalloc(&o.p, (size_t)len * 4));
+  STC_CUDA(cudaMemcpyAsync(d.p, data_host, (size_t)n * len * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_count_lt_axis0<<<cdiv(len, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, len, thresh, o.as<int>()); ctx->launches++;
+  STC_CUDA(cudaMemcpyAsync(out_host, o.p, (size_t)len * 4, cudaMemcpyDeviceToHost, ctx->stream));
   TP_FINISH();
 }

@@ -251,3 +251,113 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
     dem = divide(dem, 90, sess)                                                           # :995
     sentinel2 = clip01(sentinel2, sess)                                                   # :996
     return sentinel2, image_dates, interp, s1, dem, cloudshad, snow
+
+
+def nan_to_zero(x, sess):
+    """interpolation.interpolate_na_vals (src/preprocessing/interpolation.py:42-56): NaN -> the temporal median,
+    which is NaN (np/bn.median propagate NaN) and therefore reset to 0 -- i.e. every NaN becomes 0."""
+    a = np.ascontiguousarray(x, np.float32)
+    _check(sess, sess.lib.stc_elementwise_host(sess.h, _ptr(a), a.size, 2, 0.0, 0.0))
+    return a
+
+
+def count_lt_axis0(data, thresh, sess):
+    a = np.ascontiguousarray(data, np.float32)
+    n = a.shape[0]
+    out = np.empty(a.shape[1:], np.int32)
+    _check(sess, sess.lib.stc_count_lt_axis0_host(sess.h, _ptr(a), n, a.size // n, float(thresh), _ptr(out)))
+    return out
+
+
+def process_subtiles(x, y, s2=None, dates=None, interp=None, s1=None, dem=None, sess=None, bbx=None, size=158, train_bbx=None,
+                     local_path="", length=4):
+    """:1125-1486 for the prediction path (args.process, no --gen_feats / --gen_composite /
+    --make_training_data): medians, smoothing, quarterly composites, 6x6 overlapping windows with the
+    reference's edge padding, 17-channel assembly, prediction, post-filters, one
+    `<local_path><x>/<y>/processed/<folder_y>/<folder_x>.npy` per subtile (float32, 255 = no data).
+    B200 shape of the loop: all subtiles of the tile go through ONE batched forward.
+    Not reproduced (I/O products, out of scope): ard_ndmi.hkl, ard_dates.npy, the composite GeoTIFF / ARD
+    uploads (:1161-1205).  `bbx` / `train_bbx` are accepted and unused, like in the prediction path."""
+    if sess is None:
+        raise RuntimeError("process_subtiles needs an StcSession (sess=...); there is no CPU path")
+    SIZE = size
+    x = str(int(x)); y = str(int(y))
+    x = x[:-2] if ".0" in x else x
+    y = y[:-2] if ".0" in y else y
+
+    s2 = nan_to_zero(np.float32(s2), sess)                                                # :1148-1149
+    s2_median = np.concatenate([sess.temporal_median(s2), sess.temporal_median(sess.indices(s2))], axis=-1)   # :1151-1159
+    s2, dates, interp = _api.smooth_large_tile(s2, dates, interp, sess)                   # :1171
+    s2_median = s2_median[np.newaxis]
+    s1_median = sess.temporal_median(s1)[np.newaxis].astype(np.float32)                   # :1174
+    if length == 4:                                                                       # :1274-1278 quarterly medians
+        s2 = np.stack([sess.temporal_median(s2[3 * q:3 * q + 3]) for q in range(4)])
+        s1 = np.stack([sess.temporal_median(s1[3 * q:3 * q + 3]) for q in range(4)])
+    elif length == 1:
+        s2 = np.repeat(sess.temporal_median(s2)[np.newaxis], 4, axis=0)
+        s1 = np.repeat(sess.temporal_median(s1)[np.newaxis], 4, axis=0)
+
+    from .windows import subtile_windows
+    tiles_folder, tiles_array = subtile_windows(s1.shape[1], s1.shape[2], size, 6 if SIZE != 222 else 7)
+    path = f'{local_path}{str(x)}/{str(y)}/processed/'
+    clear_all = count_lt_axis0(interp, 0.33, sess)                                        # np.sum(interp < 0.33, axis=0), whole tile
+
+    stacks, clears, outputs, no_data = [], [], [], []
+    for t in range(len(tiles_folder)):
+        tile_folder, tile_array = tiles_folder[t], tiles_array[t]
+        start_x, start_y = tile_array[0], tile_array[1]
+        folder_x, folder_y = tile_folder[0], tile_folder[1]
+        end_x, end_y = start_x + tile_array[2], start_y + tile_array[3]
+        subtile = np.copy(s2[:, start_x:end_x, start_y:end_y, :])
+        subtile_median_s2 = np.copy(s2_median[:, start_x:end_x, start_y:end_y, :])
+        subtile_median_s1 = np.copy(s1_median[:, start_x:end_x, start_y:end_y, :])
+        dem_subtile = dem[np.newaxis, start_x:end_x, start_y:end_y]
+        s1_subtile = np.copy(s1[:, start_x:end_x, start_y:end_y, :])
+        min_clear = clear_all[start_x:end_x, start_y:end_y]
+        no_images = bool(np.percentile(min_clear, 50) < 1)                                # :1357 (scalar decision)
+        # :1369-1388 edge padding; pad_u / pad_d deliberately keep their value from earlier iterations, as the
+        # reference's second block reads them for the x-direction pad of min_clear
+        if subtile.shape[2] == SIZE + 7:
+            pad_u = 7 if start_y == 0 else 0
+            pad_d = 7 if start_y != 0 else 0
+            subtile = np.pad(subtile, ((0, 0), (0, 0), (pad_u, pad_d), (0, 0)), 'reflect')
+            s1_subtile = np.pad(s1_subtile, ((0, 0), (0, 0), (pad_u, pad_d), (0, 0)), 'reflect')
+            dem_subtile = np.pad(dem_subtile, ((0, 0), (0, 0), (pad_u, pad_d)), 'reflect')
+            subtile_median_s2 = np.pad(subtile_median_s2, ((0, 0), (0, 0), (pad_u, pad_d), (0, 0)), 'reflect')
+            subtile_median_s1 = np.pad(subtile_median_s1, ((0, 0), (0, 0), (pad_u, pad_d), (0, 0)), 'reflect')
+            min_clear = np.pad(min_clear, ((0, 0), (pad_u, pad_d)), 'reflect')
+        if subtile.shape[1] == SIZE + 7:
+            pad_l = 7 if start_x == 0 else 0
+            pad_r = 7 if start_x != 0 else 0
+            subtile = np.pad(subtile, ((0, 0), (pad_l, pad_r), (0, 0), (0, 0)), 'reflect')
+            s1_subtile = np.pad(s1_subtile, ((0, 0), (pad_l, pad_r), (0, 0), (0, 0)), 'reflect')
+            dem_subtile = np.pad(dem_subtile, ((0, 0), (pad_l, pad_r), (0, 0)), 'reflect')
+            subtile_median_s2 = np.pad(subtile_median_s2, ((0, 0), (pad_l, pad_r), (0, 0), (0, 0)), 'reflect')
+            subtile_median_s1 = np.pad(subtile_median_s1, ((0, 0), (pad_l, pad_r), (0, 0), (0, 0)), 'reflect')
+            min_clear = np.pad(min_clear, ((pad_u, pad_d), (0, 0)), 'reflect')
+        subtile_all = np.zeros((length + 1, SIZE + 14, SIZE + 14, 17), dtype=np.float32)   # :1391-1401 (copies only)
+        subtile_all[:-1, ..., :10] = subtile[..., :10]
+        subtile_all[:-1, ..., 11:13] = s1_subtile
+        subtile_all[:-1, ..., 13:] = subtile[..., 10:]
+        subtile_all[:, ..., 10] = dem_subtile.repeat(length + 1, axis=0)
+        subtile_all[-1, ..., :10] = subtile_median_s2[..., :10]
+        subtile_all[-1, ..., 11:13] = subtile_median_s1
+        subtile_all[-1, ..., 13:] = subtile_median_s2[..., 10:]
+        no_images = True if len(dates) < 2 else no_images
+        stacks.append(subtile_all); clears.append(min_clear); no_data.append(no_images)
+        outputs.append(f"{path}{str(folder_y)}/{str(folder_x)}.npy")
+
+    # one batched forward for every subtile that has data (normalize_subtile fused into the input packing)
+    valid = [i for i, nd in enumerate(no_data) if not nd]
+    preds_all = [None] * len(stacks)
+    if valid:
+        batch = np.stack([stacks[i] for i in valid])
+        p = sess.predict(batch, length=length, normalize=True)
+        clip = (p.shape[1] - SIZE) // 2
+        for k, i in enumerate(valid):
+            preds_all[i] = p[k, clip:p.shape[1] - clip, clip:p.shape[2] - clip] if clip > 0 else p[k]
+    for i in range(len(stacks)):
+        preds = preds_all[i] if preds_all[i] is not None else np.full((SIZE, SIZE), 255, np.float32)
+        preds = sess.postprocess_subtile(preds, stacks[i], clears[i])                     # :1451-1483
+        os.makedirs(os.path.realpath(os.path.dirname(outputs[i])), exist_ok=True)
+        np.save(outputs[i], preds)
