@@ -15,6 +15,14 @@ static constexpr float GN_EPS = 1e-5f;
 // device helpers
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+// MUFU-based variants for the HBM-bound GRU gating kernels (32-64 transcendentals per pixel made them
+// issue-bound): __expf / __fdividef are accurate to ~2 ulp on the ranges GroupNorm produces, far inside the
+// fp16 activation rounding that follows.
+__device__ __forceinline__ float sigm_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanh_fast(float v) {
+  const float e = __expf(-2.0f * fabsf(v));                  // in (0, 1]: no overflow
+  return copysignf(__fdividef(1.0f - e, 1.0f + e), v);
+}
 
 __device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 r;
@@ -240,10 +248,10 @@ __global__ void __launch_bounds__(256) gru_apply1_kernel(GruParams p) {
     for (int h = 0; h < 2; ++h) {
       float4 hs = p.Hf[d][(int64_t)(c4 + h) * p.Hf_plane + P];
       int c = (c4 + h) * 4;
-      v[4 * h + 0] = sigm(gr[4 * h + 0] * sa[c] + sb[c]) * hs.x;
-      v[4 * h + 1] = sigm(gr[4 * h + 1] * sa[c + 1] + sb[c + 1]) * hs.y;
-      v[4 * h + 2] = sigm(gr[4 * h + 2] * sa[c + 2] + sb[c + 2]) * hs.z;
-      v[4 * h + 3] = sigm(gr[4 * h + 3] * sa[c + 3] + sb[c + 3]) * hs.w;
+      v[4 * h + 0] = sigm_fast(gr[4 * h + 0] * sa[c] + sb[c]) * hs.x;
+      v[4 * h + 1] = sigm_fast(gr[4 * h + 1] * sa[c + 1] + sb[c + 1]) * hs.y;
+      v[4 * h + 2] = sigm_fast(gr[4 * h + 2] * sa[c + 2] + sb[c + 2]) * hs.z;
+      v[4 * h + 3] = sigm_fast(gr[4 * h + 3] * sa[c + 3] + sb[c + 3]) * hs.w;
     }
     out[c4 >> 1] = pack8(v);
   }
@@ -280,8 +288,8 @@ __global__ void __launch_bounds__(256) gru_apply2_kernel(GruParams p) {
       float hn[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float u = sigm(gu[k] * ua[c + k] + ub[c + k]);
-        float cand = tanhf(yv[k] * ya[c + k] + yb[c + k]);
+        float u = sigm_fast(gu[k] * ua[c + k] + ub[c + k]);
+        float cand = tanh_fast(yv[k] * ya[c + k] + yb[c + k]);
         float ht = u * hv[k] + (1.f - u) * cand;
         hn[k] = 0.75f * hv[k] + 0.25f * ht;
         v[4 * h + k] = hn[k];
@@ -368,6 +376,104 @@ __global__ void __launch_bounds__(256) block_apply_kernel(ApplyParams p) {
       }
     }
     p.dst[(int64_t)c8 * p.dst_plane + DP] = pack8(o);
+  }
+}
+
+// Same block tail, compiled per (C, MODE) so that the channel loops unroll and all plane loads of a pixel are in
+// flight at once (the runtime-C loop above keeps one 16-byte load per thread in flight, ~48 % of HBM peak).
+// The sSE logit is folded to dot(v, a*w) + (sum b*w + bias); for C == 64 the raw values stay in registers
+// between the logit pass and the output pass.
+__device__ __forceinline__ float fast_sigm(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+
+template <int C, int MODE>
+__global__ void __launch_bounds__(256, 2) block_apply_t(ApplyParams p) {
+  __shared__ float4 s_a[C / 4], s_b[C / 4], s_w[C / 4];     // GN scale, GN shift, logit (or head) weights a*w
+  __shared__ float s_red[8];
+  __shared__ float s_bias;
+  const int b = blockIdx.y;
+  constexpr int gs = C / 8;
+  float part = 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a, bb;
+    gn_affine(p.stats + (int64_t)b * 16, c / gs, p.count, p.gamma[c], p.beta[c], a, bb);
+    const float w = p.sse_w[c];
+    reinterpret_cast<float*>(s_a)[c] = a; reinterpret_cast<float*>(s_b)[c] = bb; reinterpret_cast<float*>(s_w)[c] = a * w;
+    part += bb * w;
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += s_red[w]; s_bias = s + p.sse_b[0]; }
+  __syncthreads();
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= p.Hd * p.Wd) return;
+  const int yd = idx / p.Wd, xd = idx - yd * p.Wd;
+  constexpr int NSRC = (MODE == 1) ? 4 : 1;
+  constexpr bool KEEP = (C == 64) && (MODE != 1);
+  int64_t SP[NSRC]; float sv[NSRC];
+  float4 keep[KEEP ? C / 4 : 1];
+#pragma unroll
+  for (int k = 0; k < NSRC; ++k) {
+    int ys, xs;
+    if (MODE == 1) { ys = 2 * yd + (k >> 1); xs = 2 * xd + (k & 1); }
+    else if (MODE == 2) { ys = yd >> 1; xs = xd >> 1; }
+    else { ys = yd + p.off; xs = xd + p.off; }
+    SP[k] = ((int64_t)b * p.sHp + ys + p.so) * p.sWp + xs + p.so;
+    float dot = s_bias;
+#pragma unroll
+    for (int c0 = 0; c0 < C / 4; c0 += 16) {
+      float4 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = p.raw[(int64_t)(c0 + j) * p.raw_plane + SP[k]];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 w = s_w[c0 + j];
+        dot += v[j].x * w.x + v[j].y * w.y + v[j].z * w.z + v[j].w * w.w;
+        if (KEEP) keep[c0 + j] = v[j];
+      }
+    }
+    sv[k] = fast_sigm(dot);
+  }
+  if (MODE == 3) {      // 1x1 head: sigmoid(sum_c z_c * sv * hw_c + hb)
+    float acc = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float4 v = KEEP ? keep[c4] : p.raw[(int64_t)c4 * p.raw_plane + SP[0]];
+      const float4 a = s_a[c4], bb = s_b[c4];
+      const float4 hw = *reinterpret_cast<const float4*>(p.head_w + 4 * c4);
+      acc += (v.x * a.x + bb.x) * hw.x + (v.y * a.y + bb.y) * hw.y + (v.z * a.z + bb.z) * hw.z + (v.w * a.w + bb.w) * hw.w;
+    }
+    p.head_out[((int64_t)b * p.Hd + yd) * p.Wd + xd] = fast_sigm(acc * sv[0] + p.head_b[0]);
+    return;
+  }
+  const int64_t DP = ((int64_t)b * p.dHp + yd + 1) * p.dWp + xd + 1;
+#pragma unroll
+  for (int c8 = 0; c8 < C / 8; ++c8) {
+    float o[8];
+    const float4 a0 = s_a[2 * c8], a1 = s_a[2 * c8 + 1], b0 = s_b[2 * c8], b1 = s_b[2 * c8 + 1];
+    const float sa8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, sb8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < NSRC; ++k) {
+      const float4 v0 = KEEP ? keep[2 * c8] : p.raw[(int64_t)(2 * c8) * p.raw_plane + SP[k]];
+      const float4 v1 = KEEP ? keep[2 * c8 + 1] : p.raw[(int64_t)(2 * c8 + 1) * p.raw_plane + SP[k]];
+      const float t[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float z = (t[i] * sa8[i] + sb8[i]) * sv[k];
+        o[i] = (k == 0) ? z : fmaxf(o[i], z);
+      }
+    }
+    p.dst[(int64_t)c8 * p.dst_plane + DP] = pack8(o);
+  }
+}
+
+template <int C>
+static void launch_apply_c(const ApplyParams& ap, dim3 grid, cudaStream_t s) {
+  switch (ap.mode) {
+    case 0: block_apply_t<C, 0><<<grid, 256, 0, s>>>(ap); break;
+    case 1: block_apply_t<C, 1><<<grid, 256, 0, s>>>(ap); break;
+    case 2: block_apply_t<C, 2><<<grid, 256, 0, s>>>(ap); break;
+    default: block_apply_t<C, 3><<<grid, 256, 0, s>>>(ap); break;
   }
 }
 
@@ -609,7 +715,12 @@ static int run_apply(stc_ctx* ctx, ModelState* m, int blk, const Act& src_geo, b
   ap.Hd = Hd; ap.Wd = Hd; ap.mode = mode; ap.off = off;
   ap.head_w = m->fp["head.w"]; ap.head_b = m->fp["head.b"]; ap.head_out = head_out;
   dim3 grid(cdiv((int64_t)Hd * Hd, 256), B);
-  block_apply_kernel<<<grid, 256, 3 * ap.C * sizeof(float), ctx->stream>>>(ap);
+  static const bool old_apply = getenv("STC_APPLY_OLD") != nullptr;      // A/B switch for profiling
+  if (old_apply) block_apply_kernel<<<grid, 256, 3 * ap.C * sizeof(float), ctx->stream>>>(ap);
+  else if (ap.C == 64) launch_apply_c<64>(ap, grid, ctx->stream);
+  else if (ap.C == 128) launch_apply_c<128>(ap, grid, ctx->stream);
+  else if (ap.C == 256) launch_apply_c<256>(ap, grid, ctx->stream);
+  else STC_FAIL(STC_ERR_ARG, "block tail: unsupported channel count");
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;
