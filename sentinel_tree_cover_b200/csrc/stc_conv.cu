@@ -249,13 +249,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 
-template <int N, int NT>
+// OCC = CTAs resident per SM.  OCC 2 halves the shared-memory budget (2 or 3 shallower stages) and the TMEM budget
+// (<= 256 columns per CTA) so that two MMA issuers feed the tensor pipe of one SM (profiles/r01_umma_microbench3.txt:
+// the per-instruction issue floor is per issuer, two concurrent streams raise small-N throughput by 1.2-1.4x).
+template <int N, int NT, int OCC = 1>
 struct UmmaCfg {
   static constexpr int R = NT * 128 + 8;                 // rows per staged segment (multiple of 8: 128-B aligned blocks)
   static constexpr int A_BYTES = 3 * 2 * R * 16;
   static constexpr int B_BYTES = 9 * 2 * N * 16;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (3 * STAGE_BYTES <= 200 * 1024) ? 3 : 2;
+  static constexpr int BUDGET = (OCC == 2) ? 110 * 1024 : 200 * 1024;
+  static constexpr int STAGES = (3 * STAGE_BYTES <= BUDGET) ? 3 : 2;
+  static_assert(2 * STAGE_BYTES + 256 <= ((OCC == 2) ? 113 : 227) * 1024, "stages do not fit the shared-memory budget");
+  static_assert(OCC == 1 || 2 * NT * N <= 256, "two resident CTAs share the 512 TMEM columns");
   static constexpr int ACC_COLS = NT * N;                // per accumulator stage
   static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
                                    : (2 * ACC_COLS <= 256) ? 256 : 512;
@@ -285,9 +291,9 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // warps 2-9 epilogue (TMEM lane quarter = warp%4, column half = (warp-2)/4).
 // Statistics live in per-lane registers across the CTA's contiguous run of tiles and are
 // flushed (shuffle reduction + fp64 atomics) only when the sample changes.
-template <int N, int NT, int G, int MODE>
-__global__ void __launch_bounds__(320, 1) conv3x3_umma_kernel(ConvParams p, int tiles_per_dir, int total_tiles, int tiles_per_cta) {
-  using C = UmmaCfg<N, NT>;
+template <int N, int NT, int G, int MODE, int OCC = 1>
+__global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, int tiles_per_dir, int total_tiles, int tiles_per_cta) {
+  using C = UmmaCfg<N, NT, OCC>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
@@ -509,11 +515,11 @@ __global__ void __launch_bounds__(320, 1) conv3x3_umma_kernel(ConvParams p, int 
 // --------------------------------------------------------------------------------------
 // host launchers
 // --------------------------------------------------------------------------------------
-template <int N, int NT, int G, int MODE>
+template <int N, int NT, int G, int MODE, int OCC = 1>
 static int launch_umma(stc_ctx* ctx, const ConvParams& p, int ndir) {
-  using C = UmmaCfg<N, NT>;
+  using C = UmmaCfg<N, NT, OCC>;
   static bool configured = false;
-  auto kern = conv3x3_umma_kernel<N, NT, G, MODE>;
+  auto kern = conv3x3_umma_kernel<N, NT, G, MODE, OCC>;
   if (!configured) {
     STC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
@@ -521,7 +527,8 @@ static int launch_umma(stc_ctx* ctx, const ConvParams& p, int ndir) {
   if (p.Ptot >= (1ll << 31) - 1024) STC_FAIL(STC_ERR_ARG, "conv: pixel space exceeds 2^31");
   int tiles_per_dir = cdiv(p.Ptot, NT * 128);
   int total = tiles_per_dir * ndir;
-  int grid = total < ctx->num_sms ? total : ctx->num_sms;
+  const int slots = ctx->num_sms * OCC;
+  int grid = total < slots ? total : slots;
   int tiles_per_cta = cdiv(total, grid);
   grid = cdiv(total, tiles_per_cta);
   kern<<<grid, 320, C::SMEM_BYTES, ctx->stream>>>(p, tiles_per_dir, total, tiles_per_cta);
@@ -549,6 +556,7 @@ static int launch_simt(stc_ctx* ctx, const ConvParams& p, int ndir) {
 
 int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
   static const int exp_align = getenv("STC_EXP_ALIGN") ? atoi(getenv("STC_EXP_ALIGN")) : 0;
+  static const int occ2 = getenv("STC_CONV_OCC2") ? atoi(getenv("STC_CONV_OCC2")) : 0;   // bit 0: GRU convs, bit 1: N=64 block convs
   ConvParams p = p_in;
   p.exp_align = exp_align;
   if (p.mode == MODE_CAND && p.N != 32) STC_FAIL(STC_ERR_ARG, "conv: MODE_CAND requires N == 32");
@@ -574,10 +582,14 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
     const int g = p.stats[0] ? p.G : 0;
     const int key = (p.N * 100 + g) * 10 + p.mode;
     switch (key) {
-      case (6400 + 16) * 10 + MODE_PLAIN:        rc = launch_umma<64, 4, 16, MODE_PLAIN>(ctx, p, ndir); break;        // GRU gates
-      case (3200 + 8) * 10 + MODE_CAND:          rc = launch_umma<32, 4, 8, MODE_CAND>(ctx, p, ndir); break;          // GRU candidate
-      case (6400 + 8) * 10 + MODE_PSCALE_SWISH:  rc = launch_umma<64, 4, 8, MODE_PSCALE_SWISH>(ctx, p, ndir); break;  // conv_median, conv_concat, up3
-      case (6400 + 8) * 10 + MODE_SWISH:         rc = launch_umma<64, 4, 8, MODE_SWISH>(ctx, p, ndir); break;         // out
+      case (6400 + 16) * 10 + MODE_PLAIN:                                                                               // GRU gates
+        rc = (occ2 & 1) ? launch_umma<64, 2, 16, MODE_PLAIN, 2>(ctx, p, ndir) : launch_umma<64, 4, 16, MODE_PLAIN>(ctx, p, ndir); break;
+      case (3200 + 8) * 10 + MODE_CAND:                                                                                 // GRU candidate
+        rc = (occ2 & 1) ? launch_umma<32, 2, 8, MODE_CAND, 2>(ctx, p, ndir) : launch_umma<32, 4, 8, MODE_CAND>(ctx, p, ndir); break;
+      case (6400 + 8) * 10 + MODE_PSCALE_SWISH:                                                                         // conv_median, conv_concat, up3
+        rc = (occ2 & 2) ? launch_umma<64, 2, 8, MODE_PSCALE_SWISH, 2>(ctx, p, ndir) : launch_umma<64, 4, 8, MODE_PSCALE_SWISH>(ctx, p, ndir); break;
+      case (6400 + 8) * 10 + MODE_SWISH:                                                                                // out
+        rc = (occ2 & 2) ? launch_umma<64, 2, 8, MODE_SWISH, 2>(ctx, p, ndir) : launch_umma<64, 4, 8, MODE_SWISH>(ctx, p, ndir); break;
       case (12800 + 8) * 10 + MODE_PSCALE_SWISH: rc = launch_umma<128, 2, 8, MODE_PSCALE_SWISH>(ctx, p, ndir); break; // up2, up2_out
       case (12800 + 8) * 10 + MODE_SWISH:        rc = launch_umma<128, 2, 8, MODE_SWISH>(ctx, p, ndir); break;        // conv1
       case (25600 + 8) * 10 + MODE_SWISH:        rc = launch_umma<256, 1, 8, MODE_SWISH>(ctx, p, ndir); break;        // conv2
