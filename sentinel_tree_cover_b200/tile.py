@@ -24,7 +24,7 @@ def _ptr(a):
 
 # ---- thin session helpers for the tile-prep entry points (include/stc.h) ----
 def s1_fill(s1, sess):
-    a = np.ascontiguousarray(s1, np.float32)
+    a = np.array(s1, dtype=np.float32, order="C")      # always a copy: the caller's array is left alone
     m, H, W, Cc = a.shape
     _check(sess, sess.lib.stc_s1_fill_host(sess.h, _ptr(a), m, H, W, Cc))
     return a
@@ -38,7 +38,7 @@ def median_filter5(dem, sess):
 
 
 def clm_pairs(clm, sess):
-    a = np.ascontiguousarray(clm, np.float32)
+    a = np.array(clm, dtype=np.float32, order="C")      # always a copy: the caller's array is left alone
     _check(sess, sess.lib.stc_clm_pairs_host(sess.h, _ptr(a), a.shape[0], a.shape[1], a.shape[2]))
     return a
 
@@ -63,13 +63,13 @@ def count_gt(data, thresh, sess):
 
 
 def clip01(x, sess):
-    a = np.ascontiguousarray(x, np.float32)
+    a = np.array(x, dtype=np.float32, order="C")      # always a copy: the caller's array is left alone
     _check(sess, sess.lib.stc_elementwise_host(sess.h, _ptr(a), a.size, 0, 0.0, 1.0))
     return a
 
 
 def divide(x, d, sess):
-    a = np.ascontiguousarray(x, np.float32)
+    a = np.array(x, dtype=np.float32, order="C")      # always a copy: the caller's array is left alone
     _check(sess, sess.lib.stc_elementwise_host(sess.h, _ptr(a), a.size, 1, float(d), 0.0))
     return a
 
@@ -256,7 +256,7 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
 def nan_to_zero(x, sess):
     """interpolation.interpolate_na_vals (src/preprocessing/interpolation.py:42-56): NaN -> the temporal median,
     which is NaN (np/bn.median propagate NaN) and therefore reset to 0 -- i.e. every NaN becomes 0."""
-    a = np.ascontiguousarray(x, np.float32)
+    a = np.array(x, dtype=np.float32, order="C")
     _check(sess, sess.lib.stc_elementwise_host(sess.h, _ptr(a), a.size, 2, 0.0, 0.0))
     return a
 

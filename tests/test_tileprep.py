@@ -51,6 +51,8 @@ def test_snow_mask_counts_and_dilation(sess):
     s2 = r.uniform(0.02, 0.6, (6, 48, 44, 10)).astype(np.float32)
     s2[:, 10:30, 5:25, 8] *= 0.1                                           # low SWIR -> high NDSI -> snow
     s2[:, 10:30, 5:25, 0] += 0.2
+    s2[:, 10:30, 5:25, 2] = s2[:, 10:30, 5:25, 0]                          # B2/B4 = 1
+    s2[:, 10:30, 5:25, 3] = 0.4                                            # bright NIR
     ndsis = snow_filter(np.copy(s2)) > 0
     per_date, snow = tile.snow_mask(s2, sess)
     assert np.array_equal(per_date, ndsis.sum(axis=(1, 2)))
