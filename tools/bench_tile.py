@@ -1,0 +1,44 @@
+"""One whole tile through the mirrored per-tile drivers, raw arrays -> uint8 tree-cover tile:
+process_tile (decode, dB, upsample, cloud masks / removal) -> superresolve_large_tile -> process_subtiles
+(smoothing, 36 subtiles, one batched forward, post-filters, .npy files) -> load_mosaic_predictions.
+Synthetic raw tile (oracle.tile_ref, 618 x 618 px, n dates); prints per-stage wall times as one JSON line.
+Usage (GPU box): python tools/bench_tile.py [--n 12] [--reps 2]"""
+import argparse, json, os, random, sys, tempfile, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=12)
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    from oracle import tile_ref                       # synthetic raw tile only
+    from sentinel_tree_cover_b200 import api, tile
+    gold = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+    sess = api.StcSession(0, predict_weights=os.path.join(gold, "weights_predict_172.npz"),
+                          superresolve_weights=os.path.join(gold, "weights_superresolve.npz"))
+    store = tile_ref.FakeStore(tile_ref.synth_raw_tile(91, n=args.n, h=309, w=309))
+    res = []
+    for rep in range(args.reps):
+        root = tempfile.mkdtemp() + "/"
+        random.seed(4)
+        t = [time.perf_counter()]
+        s2, dates, interp, s1, dem, cloudshad, snow = tile.process_tile(1, 2, None, "/nonexistent/", [0, 0, 1, 1], make_shadow=True,
+                                                                        sess=sess, loader=store.load, exists=store.exists)
+        t.append(time.perf_counter())
+        s2 = api.superresolve_large_tile(np.ascontiguousarray(s2), sess)
+        t.append(time.perf_counter())
+        tile.process_subtiles(1, 2, s2, dates, interp, s1, dem, sess, [0, 0, 1, 1], 158, None, local_path=root, length=4)
+        t.append(time.perf_counter())
+        out = api.load_mosaic_predictions(root + "1/2/processed/", 1, sess)
+        t.append(time.perf_counter())
+        d = np.diff(t) * 1e3
+        res.append({"process_tile_ms": round(d[0], 1), "superresolve_ms": round(d[1], 1), "process_subtiles_ms": round(d[2], 1),
+                    "mosaic_ms": round(d[3], 1), "total_ms": round(float(d.sum()), 1), "dates_kept": int(len(dates)),
+                    "out_shape": list(out.shape), "out_dtype": str(out.dtype), "tree_cover_mean": round(float(out[out <= 100].mean()), 2)})
+    print(json.dumps({"tile": "618x618, %d dates, synthetic raw (uint16 S2/S1, f32 DEM)" % args.n, "runs": res}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
