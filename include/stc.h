@@ -193,6 +193,28 @@ int stc_count_lt_axis0_host(stc_ctx* ctx, const float* data_host, int n, int64_t
 int stc_elementwise_host(stc_ctx* ctx, float* x_host, int64_t n, int mode, float a, float b);
 int stc_max_masked_host(stc_ctx* ctx, float* a_host, const float* b_host, const uint8_t* zero_host, int64_t n);
 
+/* ---- fused, device-resident steps of process_subtiles (src/download_and_predict_job.py:1125-1486): one upload per entry,
+ *      the kernels of the unfused entry points chained on the device, only the kept results copied back.
+ * stc_s2_medians_host: s2 [n,H,W,10] -> median14 [H,W,14] = np.median over the raw dates of the 10 bands and of
+ *      EVI/BI/MSAVI2/GRNDVI (:1151-1159); bad_px[n] as stc_missing_px_host; *nan_total = NaN values found, in which case
+ *      they are set to 0 (interpolate_na_vals :1148) and s2_host is rewritten.
+ * stc_smooth_quarterly_host: s2 [n,H,W,10] (dates already screened) -> running-median fill of the 0/1 sentinels
+ *      (deal_w_missing_px :1039-1047), indices, the 12 x n regrid/Whittaker/monthly operator M (smooth_large_tile :1057-1096)
+ *      -> s2_monthly [12,H,W,14] (optional), s2_quarterly [4,H,W,14] = medians of months 0-2, 3-5, 6-8, 9-11 (:1274-1276,
+ *      optional); s1 [12,H,W,2] (optional) -> s1_quarterly [4,H,W,2], s1_median [H,W,2] (:1174, :1277-1278).
+ *      nan_after[n]: NaN values per date after the fill; if any is non-zero nothing else is computed and the caller
+ *      drops those dates first (:1048-1053).
+ * stc_predict_postprocess_host: x [B,T+1,H,H,17] un-normalised subtile stacks, min_clear [B,H,H] float32, no_data[B]
+ *      -> out [B,H-14,H-14]: normalize_subtile + forward (:1420-1421) for the batch, 255 fill for no_data subtiles
+ *      (:1417), then the post-filters of stc_postprocess_subtile_host (:1451-1483), all on the device. ---- */
+int stc_s2_medians_host(stc_ctx* ctx, float* s2_host, int n, int H, int W, float* median14_host, int32_t* bad_px_host,
+                        int64_t* nan_total_host);
+int stc_smooth_quarterly_host(stc_ctx* ctx, const float* s2_host, int n, int H, int W, const float* M_host, const float* s1_host,
+                              float* s2_monthly_host, float* s2_quarterly_host, float* s1_quarterly_host, float* s1_median_host,
+                              int32_t* nan_after_host);
+int stc_predict_postprocess_host(stc_ctx* ctx, const float* x_host, const float* min_clear_host, const int32_t* no_data_host, int B,
+                                 int T, int H, int length, const double* min17, const double* max17, float* out_host);
+
 /* ---- storage codecs and the Sentinel-1 dB transform.
  *      to_float32 (src/tof/tof_downloading.py:64-72): uint16 -> x/65535 float32;
  *      to_int16 (:51-61): trunc(clip(x,0,1)*65535) -> uint16;

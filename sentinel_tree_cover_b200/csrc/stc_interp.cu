@@ -59,6 +59,19 @@ __global__ void __launch_bounds__(128) k_median_fill(float* __restrict__ arr, in
 
 }  // namespace
 
+// device-level entry points shared with stc_tilefuse.cu
+int interp_missing_counts_dev(stc_ctx* ctx, const float* arr_dev, int n, int HW, int C, int* bad_px_dev, int* nan_vals_dev) {
+  k_missing_counts<<<dim3(cdiv((int64_t)HW, 256), n), 256, 0, ctx->stream>>>(arr_dev, HW, C, bad_px_dev, nan_vals_dev);
+  ctx->launches++;
+  return STC_OK;
+}
+int interp_median_fill_dev(stc_ctx* ctx, float* arr_dev, int n, int64_t cols) {
+  if (n > FILL_MAX_DATES) STC_FAIL(STC_ERR_ARG, "median_fill: more than 96 dates");
+  k_median_fill<<<cdiv(cols, 128), 128, 0, ctx->stream>>>(arr_dev, n, cols);
+  ctx->launches++;
+  return STC_OK;
+}
+
 extern "C" int stc_missing_px_host(stc_ctx* ctx, const float* arr_host, int n, int H, int W, int C, int32_t* bad_px_host,
                                    int32_t* nan_vals_host) {
   if (!ctx) return STC_ERR_ARG;

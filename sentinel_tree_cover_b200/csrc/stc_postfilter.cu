@@ -215,6 +215,26 @@ extern "C" int stc_bright_bare_host(stc_ctx* ctx, const float* img_host, int F, 
   return STC_OK;
 }
 
+// device-level post-filter of one subtile (all pointers on the device); scratch: a,b [H*H] u8, d2 [H*H] int, ramp [S*S] double,
+// na,nb [(S+2)^2] u8, vote [256] u8
+int post_subtile_dev(stc_ctx* ctx, const float* preds_dev, const float* img_dev, const float* mc_dev, int S, int F, int C,
+                     unsigned char* a, unsigned char* b, int* d2, double* ramp, unsigned char* na, unsigned char* nb, unsigned char* vote,
+                     float* out_dev) {
+  const int H = S + 14, Hm = S + 2;
+  int rc = bright_bare_dev(ctx, img_dev, F, H, H, C, a, b, d2, ramp);
+  if (rc) return rc;
+  int blocks = 0, bs = 0, thresh = 0;
+  if (S == 158) { blocks = 4; bs = 40; thresh = 400; }         // sum > 40*40*0.25
+  else if (S == 142) { blocks = 9; bs = 16; thresh = 192; }    // sum > 16*16*0.75
+  k_lt1<<<cdiv(Hm * Hm, 256), 256, 0, ctx->stream>>>(mc_dev, H, H, 6, na);
+  maskop_dilate(ctx, na, nb, 1, Hm, Hm, 6, 2, 1, 1, 0);   // 1 - dilate(1 - x, 3x3, 6)
+  maskop_dilate(ctx, nb, na, 1, Hm, Hm, 6, 2, 0, 0, 0);   // dilate(.., 3x3, 6)
+  if (blocks) k_block_vote<<<dim3(blocks, blocks), 256, 0, ctx->stream>>>(na, blocks, bs, thresh, vote);
+  k_attenuate_round<<<cdiv(S * S, 256), 256, 0, ctx->stream>>>(preds_dev, ramp, blocks ? vote : nullptr, S, blocks, bs, out_dev);
+  ctx->launches += 3;
+  return STC_OK;
+}
+
 // preds [S,S] float32; img [F,S+14,S+14,C] (the subtile stack before normalisation); min_clear [S+14,S+14] float32
 // (min_clear_images_per_date before its [6:-6] crop).  Block vote only for S == 158 (4x4 blocks of 40, > 25 %) and
 // S == 142 (9x9 blocks of 16, > 75 %), as in the reference.
@@ -232,18 +252,9 @@ extern "C" int stc_postprocess_subtile_host(stc_ctx* ctx, const float* preds_hos
   STC_CUDA(cudaMemcpyAsync(img.p, img_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(preds.p, preds_host, (size_t)S * S * 4, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(mc.p, min_clear_host, (size_t)H * H * 4, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = bright_bare_dev(ctx, img.as<float>(), F, H, H, C, a.as<unsigned char>(), b.as<unsigned char>(), d2.as<int>(), ramp.as<double>());
+  int rc = post_subtile_dev(ctx, preds.as<float>(), img.as<float>(), mc.as<float>(), S, F, C, a.as<unsigned char>(), b.as<unsigned char>(),
+                            d2.as<int>(), ramp.as<double>(), na.as<unsigned char>(), nb.as<unsigned char>(), vote.as<unsigned char>(), out.as<float>());
   if (rc) return rc;
-  int blocks = 0, bs = 0, thresh = 0;
-  if (S == 158) { blocks = 4; bs = 40; thresh = 400; }         // sum > 40*40*0.25
-  else if (S == 142) { blocks = 9; bs = 16; thresh = 192; }    // sum > 16*16*0.75
-  k_lt1<<<cdiv(Hm * Hm, 256), 256, 0, ctx->stream>>>(mc.as<float>(), H, H, 6, na.as<unsigned char>());
-  maskop_dilate(ctx, na.as<unsigned char>(), nb.as<unsigned char>(), 1, Hm, Hm, 6, 2, 1, 1, 0);   // 1 - dilate(1 - x, 3x3, 6)
-  maskop_dilate(ctx, nb.as<unsigned char>(), na.as<unsigned char>(), 1, Hm, Hm, 6, 2, 0, 0, 0);   // dilate(.., 3x3, 6)
-  if (blocks) k_block_vote<<<dim3(blocks, blocks), 256, 0, ctx->stream>>>(na.as<unsigned char>(), blocks, bs, thresh, vote.as<unsigned char>());
-  k_attenuate_round<<<cdiv(S * S, 256), 256, 0, ctx->stream>>>(preds.as<float>(), ramp.as<double>(), blocks ? vote.as<unsigned char>() : nullptr,
-                                                               S, blocks, bs, out.as<float>());
-  ctx->launches += 3;
   STC_CUDA(cudaMemcpyAsync(out_host, out.p, (size_t)S * S * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
   STC_CUDA(cudaGetLastError());

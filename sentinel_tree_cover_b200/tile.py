@@ -284,23 +284,69 @@ def process_subtiles(x, y, s2=None, dates=None, interp=None, s1=None, dem=None, 
     x = str(int(x)); y = str(int(y))
     x = x[:-2] if ".0" in x else x
     y = y[:-2] if ".0" in y else y
+    import time as _time
+    _t = [_time.perf_counter()]
+    _trace = os.environ.get("STC_TILE_TIMING")
 
-    s2 = nan_to_zero(np.float32(s2), sess)                                                # :1148-1149
-    s2_median = np.concatenate([sess.temporal_median(s2), sess.temporal_median(sess.indices(s2))], axis=-1)   # :1151-1159
-    s2, dates, interp = _api.smooth_large_tile(s2, dates, interp, sess)                   # :1171
-    s2_median = s2_median[np.newaxis]
-    s1_median = sess.temporal_median(s1)[np.newaxis].astype(np.float32)                   # :1174
-    if length == 4:                                                                       # :1274-1278 quarterly medians
-        s2 = np.stack([sess.temporal_median(s2[3 * q:3 * q + 3]) for q in range(4)])
-        s1 = np.stack([sess.temporal_median(s1[3 * q:3 * q + 3]) for q in range(4)])
-    elif length == 1:
-        s2 = np.repeat(sess.temporal_median(s2)[np.newaxis], 4, axis=0)
-        s1 = np.repeat(sess.temporal_median(s1)[np.newaxis], 4, axis=0)
+    def _mark(name):
+        if _trace:
+            _t.append(_time.perf_counter())
+            print("[process_subtiles] %-28s %7.1f ms" % (name, (_t[-1] - _t[-2]) * 1e3), file=__import__("sys").stderr)
+
+    # :1148-1159 NaN -> 0, medians of the raw dates (bands + indices), missing-pixel counts: one upload
+    s2 = np.array(s2, dtype=np.float32, order="C")
+    n0, Hh, Ww, _ = s2.shape
+    s2_median = np.empty((Hh, Ww, 14), np.float32)
+    bad_px = np.zeros(n0, np.int32)
+    nan_total = _api.C.c_int64(0)
+    _check(sess, sess.lib.stc_s2_medians_host(sess.h, _ptr(s2), n0, Hh, Ww, _ptr(s2_median), _ptr(bad_px), _api.C.byref(nan_total)))
+    _mark("nan fill + medians + indices")
+    # :1171 smooth_large_tile (deal_w_missing_px -> indices -> regrid / Whittaker / monthly mean) and :1174, :1274-1278
+    # the quarterly / annual medians, fused on the device; the date screening stays here (scalars)
+    missing = np.argwhere(bad_px >= (s2.shape[1] ** 2) / 10).flatten()                   # id_missing_px(arr, 10)
+    if len(missing) > 0:
+        dates = np.delete(dates, missing)
+        s2 = np.delete(s2, missing, 0)
+        interp = np.delete(interp, missing, 0)
+    s1 = np.ascontiguousarray(s1, np.float32)
+    fused = length == 4 and s1.shape[0] == 12
+    if fused:
+        try:
+            M, _ = _api._regrid.monthly_operator(dates)
+        except Exception:
+            M = None
+        fused = M is not None
+    if fused:
+        M = np.ascontiguousarray(M, np.float32)
+        s2q = np.empty((4, Hh, Ww, 14), np.float32)
+        s1q = np.empty((4, Hh, Ww, 2), np.float32)
+        s1_median = np.empty((1, Hh, Ww, 2), np.float32)
+        nan_after = np.zeros(s2.shape[0], np.int32)
+        s2c = np.ascontiguousarray(s2)
+        _check(sess, sess.lib.stc_smooth_quarterly_host(sess.h, _ptr(s2c), s2c.shape[0], Hh, Ww, _ptr(M), _ptr(s1), None, _ptr(s2q), _ptr(s1q),
+                                                        _ptr(s1_median), _ptr(nan_after)))
+        fused = not nan_after.any()
+    if fused:
+        s2, s1 = s2q, s1q
+        s2_median = s2_median[np.newaxis]
+        _mark("smooth + quarterly (fused)")
+    else:                      # NaN dates after the fill, no usable dates, or length != 4: statement-by-statement path
+        s2, dates, interp = _api.smooth_large_tile(s2, dates, interp, sess)
+        s2_median = s2_median[np.newaxis]
+        s1_median = sess.temporal_median(s1)[np.newaxis].astype(np.float32)
+        if length == 4:
+            s2 = np.stack([sess.temporal_median(s2[3 * q:3 * q + 3]) for q in range(4)])
+            s1 = np.stack([sess.temporal_median(s1[3 * q:3 * q + 3]) for q in range(4)])
+        elif length == 1:
+            s2 = np.repeat(sess.temporal_median(s2)[np.newaxis], 4, axis=0)
+            s1 = np.repeat(sess.temporal_median(s1)[np.newaxis], 4, axis=0)
+        _mark("smooth + quarterly (unfused)")
 
     from .windows import subtile_windows
     tiles_folder, tiles_array = subtile_windows(s1.shape[1], s1.shape[2], size, 6 if SIZE != 222 else 7)
     path = f'{local_path}{str(x)}/{str(y)}/processed/'
     clear_all = count_lt_axis0(interp, 0.33, sess)                                        # np.sum(interp < 0.33, axis=0), whole tile
+    _mark("quarterly medians + counts")
 
     stacks, clears, outputs, no_data = [], [], [], []
     for t in range(len(tiles_folder)):
@@ -347,17 +393,20 @@ def process_subtiles(x, y, s2=None, dates=None, interp=None, s1=None, dem=None, 
         stacks.append(subtile_all); clears.append(min_clear); no_data.append(no_images)
         outputs.append(f"{path}{str(folder_y)}/{str(folder_x)}.npy")
 
-    # one batched forward for every subtile that has data (normalize_subtile fused into the input packing)
-    valid = [i for i, nd in enumerate(no_data) if not nd]
-    preds_all = [None] * len(stacks)
-    if valid:
-        batch = np.stack([stacks[i] for i in valid])
-        p = sess.predict(batch, length=length, normalize=True)
-        clip = (p.shape[1] - SIZE) // 2
-        for k, i in enumerate(valid):
-            preds_all[i] = p[k, clip:p.shape[1] - clip, clip:p.shape[2] - clip] if clip > 0 else p[k]
+    _mark("window slicing / padding")
+    # one call: normalisation + batched forward + post-filters on the device for every subtile of the tile
+    batch = np.stack(stacks)
+    clear = np.ascontiguousarray(np.stack(clears), np.float32)
+    flags = np.ascontiguousarray(np.array(no_data, dtype=np.int32))
+    if batch.shape[1:] != (length + 1, SIZE + 14, SIZE + 14, 17) or clear.shape[1:] != (SIZE + 14, SIZE + 14):
+        raise ValueError("subtile stacks %r / clear-image maps %r do not have the expected geometry" % (batch.shape, clear.shape))
+    out = np.empty((len(stacks), SIZE, SIZE), np.float32)
+    mn, mnp = _api._f64(sess.min_all)
+    mx, mxp = _api._f64(sess.max_all)
+    _check(sess, sess.lib.stc_predict_postprocess_host(sess.h, _ptr(batch), _ptr(clear), _ptr(flags), len(stacks), length, SIZE + 14, length,
+                                                       mnp, mxp, _ptr(out)))
+    _mark("forward + post-filters (fused)")
     for i in range(len(stacks)):
-        preds = preds_all[i] if preds_all[i] is not None else np.full((SIZE, SIZE), 255, np.float32)
-        preds = sess.postprocess_subtile(preds, stacks[i], clears[i])                     # :1451-1483
         os.makedirs(os.path.realpath(os.path.dirname(outputs[i])), exist_ok=True)
-        np.save(outputs[i], preds)
+        np.save(outputs[i], out[i])
+    _mark("save")
