@@ -215,6 +215,18 @@ int stc_smooth_quarterly_host(stc_ctx* ctx, const float* s2_host, int n, int H, 
 int stc_predict_postprocess_host(stc_ctx* ctx, const float* x_host, const float* min_clear_host, const int32_t* no_data_host, int B,
                                  int T, int H, int length, const double* min17, const double* max17, float* out_host);
 
+/* ---- the subtile loop of process_subtiles (:1345-1486) for one tile in one call: the windows are gathered on the device
+ *      (reference reflect padding of edge subtiles, :1369-1388) from the quarterly composites s2q [T,H,W,14], s1q [T,H,W,2],
+ *      the medians s2med [H,W,14], s1med [H,W,2], dem [H,W] and clear [H,W] int32 (= np.sum(interp < 0.33, axis=0)); 17-channel
+ *      stacks, the no-image test np.percentile(min_clear, 50) < 1 on the unpadded window (or force_no_data, :1409), the
+ *      normalised batched forward and the post-filters follow on the device.  windows [nt][12] int32 per subtile:
+ *      row0, col0, rows, cols of the array window; data pads (rows before/after, cols before/after); min_clear pads (same
+ *      order; the reference pads that map with its own, partly stale, variables).  out [nt,S,S] float32, no_data [nt]. ---- */
+int stc_process_subtiles_host(stc_ctx* ctx, const float* s2q_host, const float* s1q_host, const float* s2med_host,
+                              const float* s1med_host, const float* dem_host, const int32_t* clear_host, int H, int W, int nt,
+                              const int32_t* windows_host, int S, int T, int length, int force_no_data,
+                              const double* min17, const double* max17, float* out_host, int32_t* no_data_host);
+
 /* ---- storage codecs and the Sentinel-1 dB transform.
  *      to_float32 (src/tof/tof_downloading.py:64-72): uint16 -> x/65535 float32;
  *      to_int16 (:51-61): trunc(clip(x,0,1)*65535) -> uint16;

@@ -143,3 +143,133 @@ extern "C" int stc_predict_postprocess_host(stc_ctx* ctx, const float* x_host, c
   STC_CUDA(cudaGetLastError());
   return STC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// stc_process_subtiles_host: the subtile loop of process_subtiles (:1345-1486) for one tile, on the device:
+// window gather with the reference's reflect padding -> 17-channel stacks -> no-image test -> normalise + batched
+// forward -> post-filters.  The host passes only the window table (integers) and gets the predictions back.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Win { int r0, c0, nr, nc, pr0, pr1, pc0, pc1, mr0, mr1, mc0, mc1; };   // data window, data pads (rows, cols), min_clear pads
+
+__device__ __forceinline__ int reflect_idx(int i, int pad0, int len) {      // np.pad(..., 'reflect'): no edge repeat
+  int j = i - pad0;
+  if (j < 0) j = -j;
+  if (j >= len) j = 2 * (len - 1) - j;
+  return j;
+}
+
+// x [nt][T+1][P][P][17], P = S + 14
+__global__ void __launch_bounds__(256) k_gather_subtiles(const float* __restrict__ s2q, const float* __restrict__ s1q,
+                                                         const float* __restrict__ s2med, const float* __restrict__ s1med,
+                                                         const float* __restrict__ dem, const Win* __restrict__ wins, int T, int H, int W,
+                                                         int P, float* __restrict__ x) {
+  const int t = blockIdx.z, f = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * P) return;
+  const Win w = wins[t];
+  const int r = w.r0 + reflect_idx(i / P, w.pr0, w.nr), c = w.c0 + reflect_idx(i % P, w.pc0, w.nc);
+  const int64_t px = (int64_t)r * W + c;
+  const float* b14 = (f < T) ? s2q + ((int64_t)f * H * W + px) * 14 : s2med + px * 14;
+  const float* b2 = (f < T) ? s1q + ((int64_t)f * H * W + px) * 2 : s1med + px * 2;
+  float* o = x + ((((int64_t)t * (T + 1) + f) * P * P) + i) * 17;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) o[k] = b14[k];
+  o[10] = dem[px];
+  o[11] = b2[0]; o[12] = b2[1];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[13 + k] = b14[10 + k];
+}
+// min_clear maps [nt][P][P] (float32) with their own pads + the no-image test on the UNPADDED window (:1355-1357):
+// np.percentile(min_clear, 50) < 1  <=>  both middle order statistics average below 1 (integers >= 0)
+__global__ void __launch_bounds__(256) k_gather_clear(const int* __restrict__ clear, const Win* __restrict__ wins, int W, int P,
+                                                      float* __restrict__ mc) {
+  const int t = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * P) return;
+  const Win w = wins[t];
+  const int r = w.r0 + reflect_idx(i / P, w.mr0, w.nr), c = w.c0 + reflect_idx(i % P, w.mc0, w.nc);
+  mc[(int64_t)t * P * P + i] = (float)clear[(int64_t)r * W + c];
+}
+__global__ void __launch_bounds__(256) k_no_image_test(const int* __restrict__ clear, const Win* __restrict__ wins, int W, int force,
+                                                       int* __restrict__ flags) {
+  const int t = blockIdx.x;
+  const Win w = wins[t];
+  __shared__ int c0, c01;
+  if (threadIdx.x == 0) { c0 = 0; c01 = 0; }
+  __syncthreads();
+  int a = 0, b = 0;
+  const int n = w.nr * w.nc;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int v = clear[(int64_t)(w.r0 + i / w.nc) * W + w.c0 + i % w.nc];
+    a += (v == 0); b += (v <= 1);
+  }
+  atomicAdd(&c0, a); atomicAdd(&c01, b);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool none;
+    if (n & 1) none = c0 >= (n + 1) / 2;                       // the middle value is 0
+    else none = (c0 >= n / 2) && (c01 >= n / 2 + 1);           // sorted[n/2-1] == 0 and sorted[n/2] <= 1: mean < 1
+    flags[t] = (none || force) ? 1 : 0;
+  }
+}
+__global__ void __launch_bounds__(256) k_fill_if(float* __restrict__ preds, const int* __restrict__ flags, int per, float v) {
+  const int t = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < per && flags[t]) preds[(int64_t)t * per + i] = v;
+}
+
+}  // namespace
+
+extern "C" int stc_process_subtiles_host(stc_ctx* ctx, const float* s2q_host, const float* s1q_host, const float* s2med_host,
+                                         const float* s1med_host, const float* dem_host, const int32_t* clear_host, int H, int W, int nt,
+                                         const int32_t* windows_host /*[nt][12]*/, int S, int T, int length, int force_no_data,
+                                         const double* min17, const double* max17, float* out_host, int32_t* no_data_host) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!s2q_host || !s1q_host || !s2med_host || !s1med_host || !dem_host || !clear_host || !windows_host || !out_host || !no_data_host ||
+      nt < 1 || T < 1 || S < 14 || !min17 || !max17)
+    STC_FAIL(STC_ERR_ARG, "process_subtiles: bad argument");
+  const int P = S + 14; const int64_t HW = (int64_t)H * W;
+  for (int t = 0; t < nt; ++t) {
+    const int32_t* w = windows_host + 12 * t;
+    if (w[0] < 0 || w[1] < 0 || w[2] < 8 || w[3] < 8 || w[0] + w[2] > H || w[1] + w[3] > W) STC_FAIL(STC_ERR_ARG, "process_subtiles: window outside the tile");
+    if (w[4] + w[5] + w[2] != P || w[6] + w[7] + w[3] != P || w[8] + w[9] + w[2] != P || w[10] + w[11] + w[3] != P)
+      STC_FAIL(STC_ERR_ARG, "process_subtiles: window + padding does not give a (size+14)^2 subtile (the reference fails in its reshape here)");
+    for (int k = 4; k < 12; ++k) if (w[k] < 0 || w[k] >= 8) STC_FAIL(STC_ERR_ARG, "process_subtiles: bad padding");
+  }
+  FBuf s2q, s1q, s2m, s1m, dem, clr, win, x, mc, flags, preds, out, a, b, d2, ramp, na, nb, vote;
+  const size_t per = (size_t)(T + 1) * P * P * 17;
+  STC_CUDA(cudaMalloc(&s2q.p, (size_t)T * HW * 56)); STC_CUDA(cudaMalloc(&s1q.p, (size_t)T * HW * 8)); STC_CUDA(cudaMalloc(&s2m.p, HW * 56));
+  STC_CUDA(cudaMalloc(&s1m.p, HW * 8)); STC_CUDA(cudaMalloc(&dem.p, HW * 4)); STC_CUDA(cudaMalloc(&clr.p, HW * 4));
+  STC_CUDA(cudaMalloc(&win.p, (size_t)nt * sizeof(Win))); STC_CUDA(cudaMalloc(&x.p, per * nt * 4)); STC_CUDA(cudaMalloc(&mc.p, (size_t)nt * P * P * 4));
+  STC_CUDA(cudaMalloc(&flags.p, nt * 4)); STC_CUDA(cudaMalloc(&preds.p, (size_t)nt * S * S * 4)); STC_CUDA(cudaMalloc(&out.p, (size_t)nt * S * S * 4));
+  STC_CUDA(cudaMalloc(&a.p, P * P)); STC_CUDA(cudaMalloc(&b.p, P * P)); STC_CUDA(cudaMalloc(&d2.p, (size_t)P * P * 4));
+  STC_CUDA(cudaMalloc(&ramp.p, (size_t)S * S * 8)); STC_CUDA(cudaMalloc(&na.p, (S + 2) * (S + 2))); STC_CUDA(cudaMalloc(&nb.p, (S + 2) * (S + 2)));
+  STC_CUDA(cudaMalloc(&vote.p, 256));
+  STC_CUDA(cudaMemcpyAsync(s2q.p, s2q_host, (size_t)T * HW * 56, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(s1q.p, s1q_host, (size_t)T * HW * 8, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(s2m.p, s2med_host, HW * 56, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(s1m.p, s1med_host, HW * 8, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(dem.p, dem_host, HW * 4, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(clr.p, clear_host, HW * 4, cudaMemcpyHostToDevice, ctx->stream));
+  static_assert(sizeof(Win) == 48, "window table layout");
+  STC_CUDA(cudaMemcpyAsync(win.p, windows_host, (size_t)nt * 48, cudaMemcpyHostToDevice, ctx->stream));
+  k_gather_subtiles<<<dim3(cdiv(P * P, 256), T + 1, nt), 256, 0, ctx->stream>>>(s2q.as<float>(), s1q.as<float>(), s2m.as<float>(), s1m.as<float>(),
+                                                                              dem.as<float>(), win.as<Win>(), T, H, W, P, x.as<float>());
+  k_gather_clear<<<dim3(cdiv(P * P, 256), nt), 256, 0, ctx->stream>>>(clr.as<int>(), win.as<Win>(), W, P, mc.as<float>());
+  k_no_image_test<<<nt, 256, 0, ctx->stream>>>(clr.as<int>(), win.as<Win>(), W, force_no_data, flags.as<int>());
+  ctx->launches += 3;
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));      // host staging buffers may go away
+  TF_CHECK(model_predict_dev(ctx, x.as<float>(), nt, T, P, P, length, 1, min17, max17, preds.as<float>()));
+  k_fill_if<<<dim3(cdiv(S * S, 256), nt), 256, 0, ctx->stream>>>(preds.as<float>(), flags.as<int>(), S * S, 255.f); ctx->launches++;
+  for (int i = 0; i < nt; ++i)
+    TF_CHECK(post_subtile_dev(ctx, preds.as<float>() + (size_t)i * S * S, x.as<float>() + per * i, mc.as<float>() + (size_t)i * P * P, S, T + 1, 17,
+                              a.as<unsigned char>(), b.as<unsigned char>(), d2.as<int>(), ramp.as<double>(), na.as<unsigned char>(),
+                              nb.as<unsigned char>(), vote.as<unsigned char>(), out.as<float>() + (size_t)i * S * S));
+  STC_CUDA(cudaMemcpyAsync(out_host, out.p, (size_t)nt * S * S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(no_data_host, flags.p, nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  STC_CUDA(cudaGetLastError());
+  return STC_OK;
+}

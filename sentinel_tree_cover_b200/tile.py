@@ -348,6 +348,44 @@ def process_subtiles(x, y, s2=None, dates=None, interp=None, s1=None, dem=None, 
     clear_all = count_lt_axis0(interp, 0.33, sess)                                        # np.sum(interp < 0.33, axis=0), whole tile
     _mark("quarterly medians + counts")
 
+    if fused and not os.environ.get("STC_TILE_HOST_GATHER"):
+        # window table only (integers); gather, stacks, no-image test, forward and post-filters run on the device
+        table = np.zeros((len(tiles_folder), 12), np.int32)
+        outputs = []
+        for t in range(len(tiles_folder)):
+            start_x, start_y, nr, nc = [int(v) for v in tiles_array[t]]
+            folder_x, folder_y = tiles_folder[t][0], tiles_folder[t][1]
+            nr = min(start_x + nr, s2.shape[1]) - start_x
+            nc = min(start_y + nc, s2.shape[2]) - start_y
+            row = [start_x, start_y, nr, nc, 0, 0, 0, 0, 0, 0, 0, 0]
+            if nc == SIZE + 7:                                   # :1369-1377 (second array axis)
+                pad_u = 7 if start_y == 0 else 0
+                pad_d = 7 if start_y != 0 else 0
+                row[6], row[7] = pad_u, pad_d
+                row[10], row[11] = pad_u, pad_d
+            if nr == SIZE + 7:                                   # :1378-1388 (first array axis); min_clear is padded with
+                pad_l = 7 if start_x == 0 else 0                 # (pad_u, pad_d) there -- whatever those variables hold
+                pad_r = 7 if start_x != 0 else 0
+                row[4], row[5] = pad_l, pad_r
+                row[8], row[9] = pad_u, pad_d                    # NameError in the reference too if never set
+            table[t] = row
+            outputs.append(f"{path}{str(folder_y)}/{str(folder_x)}.npy")
+        out = np.empty((len(table), SIZE, SIZE), np.float32)
+        flags = np.zeros(len(table), np.int32)
+        mn, mnp = _api._f64(sess.min_all)
+        mx, mxp = _api._f64(sess.max_all)
+        dem32 = np.ascontiguousarray(dem, np.float32)
+        s2m = np.ascontiguousarray(s2_median[0]); s1m = np.ascontiguousarray(s1_median[0])
+        _check(sess, sess.lib.stc_process_subtiles_host(sess.h, _ptr(s2), _ptr(s1), _ptr(s2m), _ptr(s1m), _ptr(dem32), _ptr(clear_all),
+                                                        s2.shape[1], s2.shape[2], len(table), _ptr(table), SIZE, length, length,
+                                                        int(len(dates) < 2), mnp, mxp, _ptr(out), _ptr(flags)))
+        _mark("gather + forward + post-filters (device)")
+        for i in range(len(table)):
+            os.makedirs(os.path.realpath(os.path.dirname(outputs[i])), exist_ok=True)
+            np.save(outputs[i], out[i])
+        _mark("save")
+        return
+
     stacks, clears, outputs, no_data = [], [], [], []
     for t in range(len(tiles_folder)):
         tile_folder, tile_array = tiles_folder[t], tiles_array[t]

@@ -16,8 +16,12 @@ def test_golden_layout():
 
 
 @pytest.mark.gpu
-def test_gpu_process_subtiles_matches_reference_golden(sess, tmp_path):
+@pytest.mark.parametrize("host_gather", [False, True])
+def test_gpu_process_subtiles_matches_reference_golden(sess, tmp_path, monkeypatch, host_gather):
+    """Both routes: windows gathered on the device (default) and the statement-by-statement host gather."""
     from sentinel_tree_cover_b200.tile import process_subtiles
+    if host_gather:
+        monkeypatch.setenv("STC_TILE_HOST_GATHER", "1")
     g = np.load(GOLD)
     seed, n, H, W = [int(v) for v in g["case"]]
     s2, dates, interp, s1, dem = subtiles_ref.synth_ard(seed, n, H, W)
