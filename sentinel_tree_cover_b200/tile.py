@@ -131,6 +131,14 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
     if sess is None:
         raise RuntimeError("process_tile needs an StcSession (sess=...); there is no CPU path")
     load = loader or _default_loader
+    import time as _time
+    _t = [_time.perf_counter()]
+    _trace = os.environ.get("STC_TILE_TIMING")
+
+    def _mark(name):
+        if _trace:
+            _t.append(_time.perf_counter())
+            print("[process_tile] %-32s %7.1f ms" % (name, (_t[-1] - _t[-2]) * 1e3), file=__import__("sys").stderr)
     x = str(int(x)); y = str(int(y))
     x = x[:-2] if ".0" in x else x
     y = y[:-2] if ".0" in y else y
@@ -160,6 +168,7 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
     s1[..., -1] = sess.convert_to_db(np.ascontiguousarray(s1[..., -1]), 22)               # :707-708
     s1[..., -2] = sess.convert_to_db(np.ascontiguousarray(s1[..., -2]), 22)
     s1 = s1.astype(np.float32)
+    _mark("load + S1 decode/fill/dB")
 
     s2_10 = _api.to_float32(load(s2_10_file), sess)
     s2_20 = _api.to_float32(load(s2_20_file), sess)
@@ -176,7 +185,9 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
     if len(s2_20.shape) == 3:
         s2_20 = s2_20[np.newaxis]
 
+    _mark("S2 decode + DEM filter + adjust")
     sentinel2 = sess.build_sentinel2(s2_10, s2_20)                                        # :743-782
+    _mark("build_sentinel2")
 
     missing_px = _api.id_missing_px(sentinel2, 2, sess)                                   # :786
     if len(missing_px) > 0:
@@ -199,6 +210,8 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
         if clm is not None:
             clm = np.delete(clm, to_remove, axis=0)
     # interpolation.interpolate_missing_vals (:833) is a no-op: its guard `s2 >= 1 and s2 == 0` is never true
+
+    _mark("missing px + snow")
 
     def masks(first):
         nonlocal clm
@@ -231,10 +244,12 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
                 cloudshad, fcps = masks(False)
                 if attempt < 2:
                     interp = _api.id_areas_to_interp(sentinel2, cloudshad, cloudshad, image_dates, fcps, sess)
+        _mark("cloud masks + feather + screening")
         interp = _api.id_areas_to_interp(sentinel2, cloudshad, cloudshad, image_dates, fcps, sess)   # :917
         if not (isinstance(sentinel2, np.ndarray) and sentinel2.dtype == np.float32 and sentinel2.flags.c_contiguous):
             sentinel2 = np.ascontiguousarray(sentinel2, np.float32)
         _, interp, to_remove = _api.remove_cloud_and_shadows(sentinel2, cloudshad, cloudshad, image_dates, fcps, None, sess=sess)
+        _mark("remove_cloud_and_shadows")
         if len(to_remove) > 0:                                                            # :972-990
             clouds = np.delete(clouds, to_remove, axis=0)
             image_dates = np.delete(image_dates, to_remove)
@@ -250,6 +265,7 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
 
     dem = divide(dem, 90, sess)                                                           # :995
     sentinel2 = clip01(sentinel2, sess)                                                   # :996
+    _mark("clip + dem scale")
     return sentinel2, image_dates, interp, s1, dem, cloudshad, snow
 
 
