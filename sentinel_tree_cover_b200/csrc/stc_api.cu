@@ -41,6 +41,10 @@ void stc_destroy(stc_ctx* ctx) {
   }
   if (ctx->stage_out) cudaFree(ctx->stage_out);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->hi_stream[i]) cudaStreamDestroy(ctx->hi_stream[i]);
+    for (int j = 0; j < 2; ++j) if (ctx->ev_lane[i][j]) cudaEventDestroy(ctx->ev_lane[i][j]);
+  }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -77,6 +77,8 @@ struct stc_ctx {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int last_slot = 0;
+  cudaStream_t hi_stream[2] = {nullptr, nullptr};       // high-priority conv lanes (stc_conv.cu), one per chunk slot
+  cudaEvent_t ev_lane[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   int monthly_u16 = 0;        // the monthly patches of the current call are uint16 (x/65535), not float32
   void* sr = nullptr;         // SuperresState*
 };

@@ -223,6 +223,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// One elected lane of a converged warp.  The MMA / bulk-copy issue loops run on the WHOLE warp with warp-uniform values
+// and predicate only the instruction with this flag: inside `if (lane == 0)` nvcc cannot prove the descriptors uniform
+// and wraps every UTCHMMA in a convergence loop (R2UR, ELECT, PLOP3, BRA.U.ANY: 55-70 clk per MMA, the "issue floor"
+// of profiles/r01_umma_microbench*.txt); with uniform operands the SASS is a straight line of UTCHMMA.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred px;\nelect.sync _|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -247,6 +256,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // (stride between 8-row groups), [46,48) version=1, [61,64) layout_type=0.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+// Incremental form for the issue loops: shared-memory addresses are < 256 KB and 16-byte aligned, so the 14-bit start
+// field never carries; a descriptor for "base + r rows" (r in 16-byte units) is (hi, lo + r): one uniform add per MMA.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return (saddr >> 4) | ((lbo >> 4) << 16); }
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo) {
+  constexpr uint32_t HI = (128u >> 4) | (1u << 14);           // SBO = 128 B, descriptor version 1
+  return ((uint64_t)HI << 32) | (uint64_t)lo;
 }
 
 // OCC = CTAs resident per SM.  OCC 2 halves the shared-memory budget (2 or 3 shallower stages) and the TMEM budget
@@ -285,104 +302,15 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Template parameters: N output channels, NT accumulators (128-pixel sub-tiles) per super-tile,
-// G GroupNorm groups whose (sum, sumsq) the epilogue accumulates (0 = none), MODE the fused
-// epilogue.  320 threads: warp 0 bulk-copy producer, warp 1 TMEM allocator + MMA issuer,
-// warps 2-9 epilogue (TMEM lane quarter = warp%4, column half = (warp-2)/4).
-// Statistics live in per-lane registers across the CTA's contiguous run of tiles and are
-// flushed (shuffle reduction + fp64 atomics) only when the sample changes.
-template <int N, int NT, int G, int MODE, int OCC = 1>
-__global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, int tiles_per_dir, int total_tiles, int tiles_per_cta) {
-  using C = UmmaCfg<N, NT, OCC>;
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-  const uint32_t bar_base = smem_u32(bars);
-  auto FULL = [&](int s) { return bar_base + 8u * s; };
-  auto EMPTY = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-  auto TFULL = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
-  auto TEMPTY = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  const int Ksteps = p.k0steps + p.k1steps;
-  const uint32_t smem_base = smem_u32(smem);
-  const int tile_begin = blockIdx.x * tiles_per_cta;
-  const int tile_end = (tile_begin + tiles_per_cta < total_tiles) ? tile_begin + tiles_per_cta : total_tiles;
-
-  if (warp == 0) {
-    // ===================== producer: bulk copies global -> shared =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int dir = tile / tiles_per_dir;
-        const int64_t p0 = (int64_t)(tile - dir * tiles_per_dir) * (NT * 128);
-        for (int ks = 0; ks < Ksteps; ++ks) {
-          const uint4* src; int64_t plane; int c;
-          if (ks < p.k0steps) { src = p.a0[dir]; plane = p.a0_plane; c = 2 * ks; }
-          else { src = p.a1[dir]; plane = p.a1_plane; c = 2 * (ks - p.k0steps); }
-          mbar_wait(EMPTY(stage), phase ^ 1);
-          mbar_expect_tx(FULL(stage), (uint32_t)C::STAGE_BYTES);
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-#pragma unroll
-          for (int seg = 0; seg < 3; ++seg)
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-              const uint4* g = src + (int64_t)(c + ch) * plane + p0 + (int64_t)(seg - 1) * p.Wp - 1;
-              bulk_g2s(sa + (uint32_t)((seg * 2 + ch) * C::R * 16), g, (uint32_t)(C::R * 16), FULL(stage));
-            }
-          bulk_g2s(sa + C::A_BYTES, p.w[dir] + (int64_t)ks * 9 * 2 * N, (uint32_t)C::B_BYTES, FULL(stage));
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one elected lane) =====================
-    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int stage = 0; uint32_t phase = 0; int it = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
-      const int as = it & 1;
-      mbar_wait(TEMPTY(as), ((uint32_t)(it >> 1) & 1u) ^ 1u);
-      tc_fence_after();
-      for (int ks = 0; ks < Ksteps; ++ks) {
-        mbar_wait(FULL(stage), phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + C::A_BYTES;
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint64_t bdesc = make_desc(sb + (uint32_t)(tap * 2 * N * 16), N * 16, 128);
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-              // exp_align (STC_EXP_ALIGN=1, timing experiment only): drop the dx row shift so every
-              // A core matrix starts 128-B aligned -- results are wrong, the MMA rate is what is measured
-              const int dxe = p.exp_align ? 0 : dx;
-              const uint64_t adesc = make_desc(sa + (uint32_t)(((dy * 2) * C::R + j * 128 + dxe) * 16), C::R * 16, 128);
-              tc_mma_f16(tmem_base + (uint32_t)(as * C::ACC_COLS + j * N), adesc, bdesc, IDESC, (ks > 0 || tap > 0) ? 1u : 0u);
-            }
-          }
-          tc_commit(EMPTY(stage));
-          if (ks == Ksteps - 1) tc_commit(TFULL(as));
-        }
-        __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else {
+// Epilogue shared by both tcgen05 kernels: warps 2-9, TMEM -> registers -> global, fused MODE arithmetic and
+// GroupNorm partial sums.  `tile` is the global super-tile index (dir = tile / tiles_per_dir).
+template <int N, int NT, int G, int MODE>
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per_dir, int tile_begin, int tile_end,
+                                              uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int warp, int lane) {
+  constexpr int ACC_COLS = NT * N;
+  auto TFULL = [&](int s) { return tfull0 + 8u * s; };
+  auto TEMPTY = [&](int s) { return tempty0 + 8u * s; };
+  {
     // ===================== epilogue: TMEM -> registers -> global =====================
     constexpr bool SPLIT = (N >= 32);             // two warps share a lane quarter, each takes half the columns
     constexpr int NH = SPLIT ? N / 2 : N;         // columns handled by a working warp
@@ -420,7 +348,8 @@ __global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, in
       mbar_wait(TFULL(as), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < (working ? NT : 0); ++j) {
+      // timing experiments (STC_EXP_ALIGN bits, results invalid): 2 = no epilogue work at all, 4 = no global stores
+      for (int j = 0; j < ((working && !(p.exp_align & 2)) ? NT : 0); ++j) {
         const int P = p0 + j * 128 + row;
         const bool inb = P < (int)p.Ptot;
         const int Pc = inb ? P : 0;
@@ -441,7 +370,7 @@ __global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, in
             }
           }
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::ACC_COLS + j * N);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS + j * N);
         float scale = 1.f;
         if (MODE == MODE_PSCALE_SWISH) scale = pscale(p, yp, xp);
         if (MODE == MODE_CAND) {           // 1x1 squeeze over all N channels of the pixel (pb:candidate/convolution_1)
@@ -477,7 +406,7 @@ __global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, in
               acc_ss[(c0 + i) / GS] = fmaf(xm, xm, acc_ss[(c0 + i) / GS]);
             }
           }
-          if (inb) {
+          if (inb && !(p.exp_align & 4)) {
             if (p.out_fp16) {
               uint4* o = reinterpret_cast<uint4*>(outp) + (int64_t)((cbase + c0) >> 3) * p.out_plane + P;
               o[0] = pack8h(v);
@@ -504,11 +433,258 @@ __global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, in
     }
     flush_warp();
   }
+}
+
+// Template parameters: N output channels, NT accumulators (128-pixel sub-tiles) per super-tile,
+// G GroupNorm groups whose (sum, sumsq) the epilogue accumulates (0 = none), MODE the fused
+// epilogue.  320 threads: warp 0 bulk-copy producer, warp 1 TMEM allocator + MMA issuer,
+// warps 2-9 epilogue (TMEM lane quarter = warp%4, column half = (warp-2)/4).
+// Statistics live in per-lane registers across the CTA's contiguous run of tiles and are
+// flushed (shuffle reduction + fp64 atomics) only when the sample changes.
+template <int N, int NT, int G, int MODE, int OCC = 1>
+__global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, int tiles_per_dir, int total_tiles, int tiles_per_cta) {
+  using C = UmmaCfg<N, NT, OCC>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  const uint32_t bar_base = smem_u32(bars);
+  auto FULL = [&](int s) { return bar_base + 8u * s; };
+  auto EMPTY = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto TFULL = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto TEMPTY = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  const int Ksteps = p.k0steps + p.k1steps;
+  const uint32_t smem_base = smem_u32(smem);
+  const int tile_begin = blockIdx.x * tiles_per_cta;
+  const int tile_end = (tile_begin + tiles_per_cta < total_tiles) ? tile_begin + tiles_per_cta : total_tiles;
+
+  if (warp == 0) {
+    // ===================== producer: bulk copies global -> shared =====================
+    {
+      const uint32_t leader = elect_one();
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int dir = tile / tiles_per_dir;
+        const int64_t p0 = (int64_t)(tile - dir * tiles_per_dir) * (NT * 128);
+        for (int ks = 0; ks < Ksteps; ++ks) {
+          const uint4* src; int64_t plane; int c;
+          if (ks < p.k0steps) { src = p.a0[dir]; plane = p.a0_plane; c = 2 * ks; }
+          else { src = p.a1[dir]; plane = p.a1_plane; c = 2 * (ks - p.k0steps); }
+          mbar_wait(EMPTY(stage), phase ^ 1);
+          if (leader) mbar_expect_tx(FULL(stage), (uint32_t)C::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+#pragma unroll
+          for (int seg = 0; seg < 3; ++seg)
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              const uint4* g = src + (int64_t)(c + ch) * plane + p0 + (int64_t)(seg - 1) * p.Wp - 1;
+              if (leader) bulk_g2s(sa + (uint32_t)((seg * 2 + ch) * C::R * 16), g, (uint32_t)(C::R * 16), FULL(stage));
+            }
+          if (leader) bulk_g2s(sa + C::A_BYTES, p.w[dir] + (int64_t)ks * 9 * 2 * N, (uint32_t)C::B_BYTES, FULL(stage));
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, instruction predicated on the elected lane) =====================
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const int as = it & 1;
+      mbar_wait(TEMPTY(as), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int ks = 0; ks < Ksteps; ++ks) {
+        mbar_wait(FULL(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t a_lo = desc_lo(sa, C::R * 16), b_lo = desc_lo(sa + C::A_BYTES, N * 16);
+        const uint32_t tacc = tmem_base + (uint32_t)(as * C::ACC_COLS);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - dy * 3;
+          const uint64_t bdesc = desc_join(b_lo + (uint32_t)(tap * 2 * N));
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            // exp_align (STC_EXP_ALIGN=1, timing experiment only): drop the dx row shift so every
+            // A core matrix starts 128-B aligned -- results are wrong, the MMA rate is what is measured
+            const int dxe = (p.exp_align & 1) ? 0 : dx;
+            const uint64_t adesc = desc_join(a_lo + (uint32_t)((dy * 2) * C::R + j * 128 + dxe));
+            if (leader) tc_mma_f16(tacc + (uint32_t)(j * N), adesc, bdesc, IDESC, (ks > 0 || tap > 0) ? 1u : 0u);
+          }
+        }
+        if (leader) tc_commit(EMPTY(stage));
+        if (leader && ks == Ksteps - 1) tc_commit(TFULL(as));
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    conv_epilogue<N, NT, G, MODE>(p, tiles_per_dir, tile_begin, tile_end, tmem_base, TFULL(0), TEMPTY(0), warp, lane);
+  }
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ======================================================================================
+// tcgen05 kernel, second generation (default).
+//
+// Why: for M = 128, K = 16 a tcgen05.mma with both operands in shared memory reads 4 KB of A and 32*N B of B;
+// measured (profiles/r01_umma_microbench3.txt) the tensor pipe retires one such instruction every
+// max(N/2, 32 + N/4) clk once TWO threads issue concurrently (a single issuer saturates at 55-72 clk), i.e. small-N
+// convolutions are bound by the shared-memory operand reads, and every byte the copy engine writes into shared
+// memory competes with them.  So this kernel
+//   * runs two MMA-issuing warps (1 and 10), each owning half of the super-tile's NT accumulators;
+//   * stages ONE row range per 8-channel chunk, [p0 - Wp - 1, p0 + NT*128 + Wp + 1): all nine taps are row shifts
+//     (dy*Wp + dx) into it.  The three per-dy segments of the first kernel overlapped by NT*128 - Wp rows each;
+//     the union is 44 % fewer bytes through L2 and into shared memory at Wp = 174;
+//   * keeps the packed weights resident in shared memory for the CTA's lifetime when they fit (WRES: both ConvGRU
+//     convolutions, conv_median, DSen2) instead of re-fetching 9 taps x 2 chunks x N x 16 B per K-step;
+//   * gives every CTA tiles of one direction only (resident weights are per direction).
+// Geometry that depends on Wp is passed at launch: RU rows per chunk (multiple of 8), `stages` pipeline depth.
+// ======================================================================================
+template <int N, int NT, int G, int MODE, bool WRES>
+__global__ void __launch_bounds__(352, 2) conv3x3_umma2_kernel(ConvParams p, int tiles_per_dir, int ndir, int tiles_per_cta,
+                                                                int RU, int stages, int iss) {
+  constexpr int B_BYTES = 9 * 2 * N * 16;
+  constexpr int ACC_COLS = NT * N;
+  constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
+                            : (2 * ACC_COLS <= 256) ? 256 : 512;
+  constexpr int MAXS = 8;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int Ksteps = p.k0steps + p.k1steps;
+  const uint32_t a_bytes = 2u * (uint32_t)RU * 16u;
+  const uint32_t stage_bytes = a_bytes + (WRES ? 0u : (uint32_t)B_BYTES);
+  const uint32_t w_bytes = WRES ? (uint32_t)(Ksteps * B_BYTES) : 0u;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t stage_base = smem_base + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + w_bytes + (uint32_t)stages * stage_bytes);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAXS + 5);
+  const uint32_t bar_base = smem_u32(bars);
+  auto FULL = [&](int s) { return bar_base + 8u * s; };
+  auto EMPTY = [&](int s) { return bar_base + 8u * (MAXS + s); };
+  auto TFULL = [&](int s) { return bar_base + 8u * (2 * MAXS + s); };
+  auto TEMPTY = [&](int s) { return bar_base + 8u * (2 * MAXS + 2 + s); };
+  const uint32_t WFULL = bar_base + 8u * (2 * MAXS + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), (uint32_t)iss); }
+    for (int s = 0; s < 2; ++s) { mbar_init(TFULL(s), (uint32_t)iss); mbar_init(TEMPTY(s), 8); }
+    mbar_init(WFULL, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  // this CTA's contiguous run of super-tiles, all of one direction
+  const int dir = blockIdx.x % ndir;
+  const int local0 = (blockIdx.x / ndir) * tiles_per_cta;
+  const int local1 = (local0 + tiles_per_cta < tiles_per_dir) ? local0 + tiles_per_cta : tiles_per_dir;
+  const int tile_begin = dir * tiles_per_dir + local0;
+  const int tile_end = dir * tiles_per_dir + (local1 > local0 ? local1 : local0);
+
+  if (warp == 0) {
+    // ===================== producer: bulk copies global -> shared =====================
+    if (tile_begin < tile_end) {
+      const uint32_t leader = elect_one();
+      if (WRES && leader) {
+        mbar_expect_tx(WFULL, w_bytes);
+        bulk_g2s(smem_base, p.w[dir], w_bytes, WFULL);
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int64_t p0 = (int64_t)(tile - dir * tiles_per_dir) * (NT * 128);
+        for (int ks = 0; ks < Ksteps; ++ks) {
+          const uint4* src; int64_t plane; int c;
+          if (ks < p.k0steps) { src = p.a0[dir]; plane = p.a0_plane; c = 2 * ks; }
+          else { src = p.a1[dir]; plane = p.a1_plane; c = 2 * (ks - p.k0steps); }
+          mbar_wait(EMPTY(stage), phase ^ 1);
+          if (leader) mbar_expect_tx(FULL(stage), stage_bytes);
+          const uint32_t sa = stage_base + (uint32_t)stage * stage_bytes;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const uint4* g = src + (int64_t)(c + ch) * plane + p0 - p.Wp - 1;
+            if (leader) bulk_g2s(sa + (uint32_t)ch * (uint32_t)RU * 16u, g, (uint32_t)RU * 16u, FULL(stage));
+          }
+          if (!WRES && leader) bulk_g2s(sa + a_bytes, p.w[dir] + (int64_t)ks * 9 * 2 * N, (uint32_t)B_BYTES, FULL(stage));
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 10) {
+    // ===================== MMA issuers (whole warp, instruction predicated on the elected lane) =====================
+    const int me = (warp == 1) ? 0 : 1;
+    if (me < iss) {
+      constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const int jper = NT / iss;                                      // accumulators of the super-tile per issuer
+      const uint32_t lbo_a = (uint32_t)RU * 16u;
+      const uint32_t leader = elect_one();
+      const int jlo = me * jper, jhi = jlo + jper;                    // warp-uniform: this issuer's accumulators
+      if (WRES && tile_begin < tile_end) { mbar_wait(WFULL, 0); tc_fence_after(); }
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+        const int as = it & 1;
+        mbar_wait(TEMPTY(as), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        for (int ks = 0; ks < Ksteps; ++ks) {
+          mbar_wait(FULL(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = stage_base + (uint32_t)stage * stage_bytes;
+          const uint32_t a_lo = desc_lo(sa, lbo_a);
+          const uint32_t b_lo = desc_lo(WRES ? smem_base + (uint32_t)(ks * B_BYTES) : sa + a_bytes, N * 16);
+          const uint32_t tacc = tmem_base + (uint32_t)(as * ACC_COLS);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint64_t bdesc = desc_join(b_lo + (uint32_t)(tap * 2 * N));
+            const uint32_t a_tap = a_lo + (uint32_t)(dy * p.Wp + dx);       // tap = row shift of the staged range
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+              if (j >= jlo && j < jhi)
+                if (leader) tc_mma_f16(tacc + (uint32_t)(j * N), desc_join(a_tap + (uint32_t)(j * 128)), bdesc, IDESC, (ks > 0 || tap > 0) ? 1u : 0u);
+            }
+          }
+          if (leader) tc_commit(EMPTY(stage));
+          if (leader && ks == Ksteps - 1) tc_commit(TFULL(as));
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    conv_epilogue<N, NT, G, MODE>(p, tiles_per_dir, tile_begin, tile_end, tmem_base, TFULL(0), TEMPTY(0), warp, lane);
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }
 
@@ -536,6 +712,40 @@ static int launch_umma(stc_ctx* ctx, const ConvParams& p, int ndir) {
   return STC_OK;
 }
 
+// v2 launcher.  Returns STC_ERR_ARG + "fallback" (rc = 1) when the geometry does not fit shared memory.
+template <int N, int NT, int G, int MODE, bool WRES>
+static int launch_umma2(stc_ctx* ctx, const ConvParams& p, int ndir, int iss_req) {
+  constexpr int B_BYTES = 9 * 2 * N * 16;
+  // Shared-memory budget: leave room (default 27 KB + registers) for blocks of the HBM-bound elementwise kernels of the
+  // other chunk to be co-resident with the persistent conv CTA (STC_CONV_SMEM_KB, A/B switch).
+  static const int SMEM_MAX = (getenv("STC_CONV_SMEM_KB") ? atoi(getenv("STC_CONV_SMEM_KB")) : 200) * 1024;
+  static bool configured = false;
+  auto kern = conv3x3_umma2_kernel<N, NT, G, MODE, WRES>;
+  if (!configured) {
+    STC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  if (p.Ptot >= (1ll << 31) - 1024) STC_FAIL(STC_ERR_ARG, "conv: pixel space exceeds 2^31");
+  const int Ksteps = p.k0steps + p.k1steps;
+  const int RU = (NT * 128 + 2 * p.Wp + 2 + 7) / 8 * 8;
+  const int stage_bytes = 2 * RU * 16 + (WRES ? 0 : B_BYTES);
+  const int w_bytes = WRES ? Ksteps * B_BYTES : 0;
+  int stages = (SMEM_MAX - 256 - w_bytes) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (WRES && stages < 3) return launch_umma2<N, NT, G, MODE, false>(ctx, p, ndir, iss_req);   // budget too small for resident weights
+  if (stages < 2) return 1;                        // caller reports the geometry as unsupported
+  const int smem_bytes = w_bytes + stages * stage_bytes + 256;
+  const int tiles_per_dir = cdiv(p.Ptot, NT * 128);
+  int per_dir = ctx->num_sms / ndir;               // CTAs per direction
+  if (per_dir > tiles_per_dir) per_dir = tiles_per_dir;
+  const int tiles_per_cta = cdiv(tiles_per_dir, per_dir);
+  per_dir = cdiv(tiles_per_dir, tiles_per_cta);
+  const int iss = (NT >= 2 && iss_req >= 2) ? 2 : 1;
+  kern<<<per_dir * ndir, 352, smem_bytes, ctx->stream>>>(p, tiles_per_dir, ndir, tiles_per_cta, RU, stages, iss);
+  STC_CUDA(cudaGetLastError());
+  return STC_OK;
+}
+
 static int launch_simt(stc_ctx* ctx, const ConvParams& p, int ndir) {
   dim3 block(256);
   if (p.N % 64 == 0) {
@@ -557,6 +767,11 @@ static int launch_simt(stc_ctx* ctx, const ConvParams& p, int ndir) {
 int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
   static const int exp_align = getenv("STC_EXP_ALIGN") ? atoi(getenv("STC_EXP_ALIGN")) : 0;
   static const int occ2 = getenv("STC_CONV_OCC2") ? atoi(getenv("STC_CONV_OCC2")) : 0;   // bit 0: GRU convs, bit 1: N=64 block convs
+  // A/B switches (profiling): kernel generation, MMA issuers per CTA, resident weights
+  static const int conv_v = getenv("STC_CONV_V") ? atoi(getenv("STC_CONV_V")) : 2;
+  static const int conv_iss = getenv("STC_CONV_ISS") ? atoi(getenv("STC_CONV_ISS")) : 1;
+  static const int conv_wres = getenv("STC_CONV_WRES") ? atoi(getenv("STC_CONV_WRES")) : 1;
+  static const int conv_prio = getenv("STC_CONV_PRIO") ? atoi(getenv("STC_CONV_PRIO")) : 1;
   ConvParams p = p_in;
   p.exp_align = exp_align;
   if (p.mode == MODE_CAND && p.N != 32) STC_FAIL(STC_ERR_ARG, "conv: MODE_CAND requires N == 32");
@@ -573,14 +788,55 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
     if (ctx->conv_event_kind.size() < ctx->conv_events.size()) ctx->conv_event_kind.resize(ctx->conv_events.size());
     ctx->conv_event_kind[ctx->conv_events_used] = (p.N * 100 + (p.stats[0] ? p.G : 0)) * 10 + p.mode;
     ctx->conv_events_used++;
-    STC_CUDA(cudaEventRecord(e0, ctx->stream));
   }
+  // Priority lane: the tensor-bound conv kernels of a chunk are enqueued on a high-priority side stream (forked from and
+  // joined back into the chunk's own stream), so that while the HBM-bound elementwise kernels of the OTHER chunk occupy
+  // the SMs the block scheduler places the persistent conv CTAs first and lets elementwise blocks fill the leftover
+  // threads / registers, instead of running the two kernel classes back to back (scheduling).
+  cudaStream_t base_stream = ctx->stream;
+  int lane_slot = -1;
+  if (conv_prio && ctx->conv_impl != 1) {
+    lane_slot = (ctx->stream2 && ctx->stream == ctx->stream2) ? 1 : 0;
+    if (!ctx->hi_stream[lane_slot]) {
+      int lo = 0, hi = 0;
+      STC_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      STC_CUDA(cudaStreamCreateWithPriority(&ctx->hi_stream[lane_slot], cudaStreamNonBlocking, hi));
+      STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_lane[lane_slot][0], cudaEventDisableTiming));
+      STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_lane[lane_slot][1], cudaEventDisableTiming));
+    }
+    STC_CUDA(cudaEventRecord(ctx->ev_lane[lane_slot][0], base_stream));
+    STC_CUDA(cudaStreamWaitEvent(ctx->hi_stream[lane_slot], ctx->ev_lane[lane_slot][0], 0));
+    ctx->stream = ctx->hi_stream[lane_slot];
+  }
+  struct Restore { stc_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, base_stream};
+  if (e0) STC_CUDA(cudaEventRecord(e0, ctx->stream));
   int rc;
+  const int g = p.stats[0] ? p.G : 0;
+  const int key = (p.N * 100 + g) * 10 + p.mode;
   if (ctx->conv_impl == 1) {
     rc = launch_simt(ctx, p, ndir);
+  } else if (conv_v >= 2) {
+    // second-generation kernel; weights resident in shared memory when all K-steps fit next to >= 3 stages
+    // (the launcher itself falls back to per-stage weights when the resident copy would leave fewer than 3 stages)
+    const bool wres = conv_wres && (p.k0steps + p.k1steps) * 9 * 2 * p.N * 16 <= 80 * 1024;
+#define STC_V2(NN, NTT, GG, MM) (wres ? launch_umma2<NN, NTT, GG, MM, true>(ctx, p, ndir, conv_iss) \
+                                      : launch_umma2<NN, NTT, GG, MM, false>(ctx, p, ndir, conv_iss))
+    switch (key) {
+      case (6400 + 16) * 10 + MODE_PLAIN:        rc = STC_V2(64, 4, 16, MODE_PLAIN); break;          // GRU gates
+      case (3200 + 8) * 10 + MODE_CAND:          rc = STC_V2(32, 4, 8, MODE_CAND); break;            // GRU candidate
+      case (6400 + 8) * 10 + MODE_PSCALE_SWISH:  rc = STC_V2(64, 4, 8, MODE_PSCALE_SWISH); break;    // conv_median, conv_concat, up3
+      case (6400 + 8) * 10 + MODE_SWISH:         rc = launch_umma2<64, 4, 8, MODE_SWISH, false>(ctx, p, ndir, conv_iss); break;         // out
+      case (12800 + 8) * 10 + MODE_PSCALE_SWISH: rc = launch_umma2<128, 2, 8, MODE_PSCALE_SWISH, false>(ctx, p, ndir, conv_iss); break; // up2, up2_out
+      case (12800 + 8) * 10 + MODE_SWISH:        rc = launch_umma2<128, 2, 8, MODE_SWISH, false>(ctx, p, ndir, conv_iss); break;        // conv1
+      case (25600 + 8) * 10 + MODE_SWISH:        rc = launch_umma2<256, 1, 8, MODE_SWISH, false>(ctx, p, ndir, conv_iss); break;        // conv2
+      case (3200 + 0) * 10 + MODE_BIAS_RELU:     rc = launch_umma2<32, 4, 0, MODE_BIAS_RELU, true>(ctx, p, ndir, conv_iss); break;      // DSen2
+      case (3200 + 0) * 10 + MODE_BIAS:          rc = launch_umma2<32, 4, 0, MODE_BIAS, true>(ctx, p, ndir, conv_iss); break;
+      case (1600 + 0) * 10 + MODE_BIAS:          rc = launch_umma2<16, 4, 0, MODE_BIAS, true>(ctx, p, ndir, conv_iss); break;
+      default: STC_FAIL(STC_ERR_ARG, "conv: unsupported (N, groups, mode) combination");
+    }
+#undef STC_V2
+    if (rc == 1) STC_FAIL(STC_ERR_ARG, "conv: image rows too wide for the shared-memory staging (set STC_CONV_V=1)");
   } else {
-    const int g = p.stats[0] ? p.G : 0;
-    const int key = (p.N * 100 + g) * 10 + p.mode;
     switch (key) {
       case (6400 + 16) * 10 + MODE_PLAIN:                                                                               // GRU gates
         rc = (occ2 & 1) ? launch_umma<64, 2, 16, MODE_PLAIN, 2>(ctx, p, ndir) : launch_umma<64, 4, 16, MODE_PLAIN>(ctx, p, ndir); break;
@@ -602,5 +858,9 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
   if (rc != STC_OK) return rc;
   ctx->launches++;
   if (e1) STC_CUDA(cudaEventRecord(e1, ctx->stream));
+  if (lane_slot >= 0) {
+    STC_CUDA(cudaEventRecord(ctx->ev_lane[lane_slot][1], ctx->stream));
+    STC_CUDA(cudaStreamWaitEvent(base_stream, ctx->ev_lane[lane_slot][1], 0));
+  }
   return STC_OK;
 }
