@@ -41,7 +41,7 @@ void stc_destroy(stc_ctx* ctx) {
   }
   if (ctx->stage_out) cudaFree(ctx->stage_out);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < stc_ctx::MAX_SLOTS; ++i) {
     if (ctx->hi_stream[i]) cudaStreamDestroy(ctx->hi_stream[i]);
     for (int j = 0; j < 2; ++j) if (ctx->ev_lane[i][j]) cudaEventDestroy(ctx->ev_lane[i][j]);
   }
@@ -200,40 +200,41 @@ static int predict_patches_core(stc_ctx* ctx, const float* monthly, bool host_in
     STC_CUDA(cudaMalloc(&ctx->stage_out, ctx->stage_out_bytes));
   }
   float* o_dev = host_out ? (float*)ctx->stage_out : out;
-  // Sub-batch k: H2D on the copy stream into staging buffer k&1, compute on scratch slot k&1
-  // (own stream), so copy(k+1), conv(k) and the elementwise stages of k-1/k overlap.
-  const bool dual = (B > Bc) && !getenv("STC_SINGLE_STREAM");
-  if (dual && !ctx->stream2) STC_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-  if (!ctx->ev_fork) {
-    STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-  }
-  if (dual) {
+  // Sub-batch k: H2D on the copy stream into staging buffer k&1, compute on scratch slot k % ns (own stream), so
+  // copy(k+1), conv(k) and the elementwise stages of the neighbouring chunks overlap.  A staging buffer is free again
+  // as soon as the front-end kernel of its chunk has read it (ev_free).
+  const int nchunks = (B + Bc - 1) / Bc;
+  int ns = getenv("STC_SINGLE_STREAM") ? 1 : model_num_slots();
+  if (ns > nchunks) ns = nchunks;
+  if (!ctx->ev_fork) STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  if (ns > 1) {
     STC_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
-    STC_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    for (int i = 1; i < ns; ++i) {
+      if (!ctx->ev_join[i]) STC_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+      STC_CUDA(cudaStreamWaitEvent(model_slot_stream(ctx, i), ctx->ev_fork, 0));
+    }
   }
   int k = 0;
   for (int b0 = 0; b0 < B; b0 += Bc, ++k) {
     int nb = (B - b0) < Bc ? (B - b0) : Bc;
     const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(monthly) + (size_t)b0 * per_in * esz);
     const int sl = k & 1;
-    const int slot = dual ? sl : 0;
-    cudaStream_t cs = slot ? ctx->stream2 : ctx->stream;
+    const int slot = k % ns;
+    cudaStream_t cs = model_slot_stream(ctx, slot);
     if (host_in) {
-      // copy stream: wait until the compute that last read this staging buffer is done, then copy
+      // copy stream: wait until the front end that last read this staging buffer is done, then copy
       if (k >= 2) STC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[sl], 0));
       STC_CUDA(cudaMemcpyAsync(ctx->stage_in[sl], src, nb * per_in * esz, cudaMemcpyHostToDevice, ctx->copy_stream));
       STC_CUDA(cudaEventRecord(ctx->ev_ready[sl], ctx->copy_stream));
       STC_CUDA(cudaStreamWaitEvent(cs, ctx->ev_ready[sl], 0));
       src = (const float*)ctx->stage_in[sl];
     }
-    int rc = model_forward_slot(ctx, slot, src, nb, Bc, H, min17, max17, o_dev + (size_t)b0 * per_out);
+    int rc = model_forward_slot(ctx, slot, src, nb, Bc, H, min17, max17, o_dev + (size_t)b0 * per_out, host_in ? ctx->ev_free[sl] : nullptr);
     if (rc) return rc;
-    if (host_in) STC_CUDA(cudaEventRecord(ctx->ev_free[sl], cs));
   }
-  if (dual) {
-    STC_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
-    STC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  for (int i = 1; i < ns; ++i) {
+    STC_CUDA(cudaEventRecord(ctx->ev_join[i], ctx->slot_stream[i]));
+    STC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
   }
   if (host_out) STC_CUDA(cudaMemcpyAsync(out, o_dev, (size_t)B * per_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -72,13 +72,16 @@ struct stc_ctx {
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   void* stage_in[2] = {nullptr, nullptr}; size_t stage_in_bytes = 0;
   void* stage_out = nullptr; size_t stage_out_bytes = 0;
-  void* model = nullptr;      // ModelState* (slot 0)
-  void* model2 = nullptr;     // ModelState* (slot 1): second scratch arena so consecutive chunks overlap
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Chunk slots: consecutive sub-batches of a call run on separate scratch arenas / streams so that the HBM-bound
+  // elementwise kernels of some overlap the tensor-bound convolutions of others (slot 0 uses `stream`).
+  static constexpr int MAX_SLOTS = 4;
+  void* slots[MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr};              // ModelState* per slot
+  cudaStream_t slot_stream[MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr}; // [0] unused (= stream)
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  int cur_slot = 0;           // slot whose kernels are being enqueued (selects the conv priority lane)
   int last_slot = 0;
-  cudaStream_t hi_stream[2] = {nullptr, nullptr};       // high-priority conv lanes (stc_conv.cu), one per chunk slot
-  cudaEvent_t ev_lane[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  cudaStream_t hi_stream[MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // high-priority conv lanes (stc_conv.cu)
+  cudaEvent_t ev_lane[MAX_SLOTS][2] = {};
   int monthly_u16 = 0;        // the monthly patches of the current call are uint16 (x/65535), not float32
   void* sr = nullptr;         // SuperresState*
 };
@@ -122,4 +125,6 @@ int pre_feather_dev(stc_ctx* ctx, const float* mask_dev, int n, int H, int W, in
 int pre_binary_dilate_dev(stc_ctx* ctx, const unsigned char* in_dev, int n, int H, int W, int iterations, int conn,
                           unsigned char* out_dev);
 int model_forward_slot(stc_ctx* ctx, int slot, const float* monthly_dev, int nb, int Bc, int H,
-                       const double* min17, const double* max17, float* out_dev);
+                       const double* min17, const double* max17, float* out_dev, cudaEvent_t input_consumed);
+int model_num_slots();
+cudaStream_t model_slot_stream(stc_ctx* ctx, int slot);

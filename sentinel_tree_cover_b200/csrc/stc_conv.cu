@@ -716,9 +716,9 @@ static int launch_umma(stc_ctx* ctx, const ConvParams& p, int ndir) {
 template <int N, int NT, int G, int MODE, bool WRES>
 static int launch_umma2(stc_ctx* ctx, const ConvParams& p, int ndir, int iss_req) {
   constexpr int B_BYTES = 9 * 2 * N * 16;
-  // Shared-memory budget: leave room (default 27 KB + registers) for blocks of the HBM-bound elementwise kernels of the
+  // Shared-memory budget: leave room (default 64 KB + registers; measured best of 131/163/195/227) for blocks of the HBM-bound elementwise kernels of the
   // other chunk to be co-resident with the persistent conv CTA (STC_CONV_SMEM_KB, A/B switch).
-  static const int SMEM_MAX = (getenv("STC_CONV_SMEM_KB") ? atoi(getenv("STC_CONV_SMEM_KB")) : 200) * 1024;
+  static const int SMEM_MAX = (getenv("STC_CONV_SMEM_KB") ? atoi(getenv("STC_CONV_SMEM_KB")) : 163) * 1024;
   static bool configured = false;
   auto kern = conv3x3_umma2_kernel<N, NT, G, MODE, WRES>;
   if (!configured) {
@@ -796,7 +796,7 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
   cudaStream_t base_stream = ctx->stream;
   int lane_slot = -1;
   if (conv_prio && ctx->conv_impl != 1) {
-    lane_slot = (ctx->stream2 && ctx->stream == ctx->stream2) ? 1 : 0;
+    lane_slot = ctx->cur_slot;
     if (!ctx->hi_stream[lane_slot]) {
       int lo = 0, hi = 0;
       STC_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
