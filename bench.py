@@ -37,7 +37,7 @@ def conv_flops_per_tile(Hin, T=4):
 
 
 def gates_roofline(total_ms, n_launch, chunk, peaks):
-    """Roofline entry of the dominant tensor kernel, conv3x3_umma_kernel<64,4,16,PLAIN> (ConvGRU gates,
+    """Roofline entry of the dominant tensor kernel, conv3x3_umma2_kernel<64,4,16,PLAIN,WRES> (ConvGRU gates,
     both directions of one `chunk`-tile sub-batch per launch).  Algorithmic FLOPs per launch: steps
     1..3 contract [x(17) | h(32)] -> 64 (2*9*49*64 per pixel), step 0 only x (2*9*17*64)."""
     if not n_launch:
@@ -47,12 +47,35 @@ def gates_roofline(total_ms, n_launch, chunk, peaks):
     avg_s = total_ms / n_launch / 1000.0
     achieved = flops_avg / avg_s / 1e12
     return {"bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"],
-            "traffic": 437.2e6,
-            "kernel": "conv3x3_umma_kernel<64,4,16,PLAIN> (ConvGRU gates)",
+            "traffic": 398.0e6,
+            "kernel": "conv3x3_umma2_kernel<64,4,16,PLAIN,WRES> (ConvGRU gates)",
             "note": "avg of %d launches: %.1f us; algorithmic %.3e FLOP/launch (%d tiles x 2 directions); peak = %s sustained "
-                    "bf16/fp16 dense; traffic = dram read+write of the steady-state launch from `ncu --set full` "
-                    "(profiles/r01_b_summary.md: 244 MB + 193 MB, algorithmic 237 + 237 MB); the instruction-level ceiling "
-                    "for N=64 is 44%% of peak (profiles/r01_umma_microbench.txt)" % (n_launch, 1e6 * avg_s, flops_avg, chunk, peaks["src"])}
+                    "bf16/fp16 dense; traffic = dram read+write per launch from ncu (profiles/r01_f_summary.md: 213 MB + 185 MB; "
+                    "algorithmic 202 + 231 MB); structural ceiling of this formulation: an M128 x N64 x K16 tcgen05.mma with both "
+                    "operands in shared memory retires every 48 clk (operand reads, profiles/r01_umma_microbench5.txt) = 67%% of the "
+                    "dense rate, times 49/64 useful K and 168^2/170^2 useful rows = 50%% of the burst peak"
+                    % (n_launch, 1e6 * avg_s, flops_avg, chunk, peaks["src"])}
+
+
+def hbm_roofline(trace_csv, chunk, peaks):
+    """Roofline entry of the kernel with the largest share of the step, gru_apply2_kernel (GroupNorm + gating + zoneout
+    blend of one ConvGRU step, both directions of one sub-batch per launch; HBM-bound).  Algorithmic bytes per pixel and
+    direction: read u-gates 64 + candidate 64 + fp32 state 128 (no state at step 0), write fp32 state 128 + fp16 state 64
+    (+ 64 into the U-Net concat buffer at the last step).  Durations come from CUDA events around every launch of one
+    extra single-stream step (stc_trace), so each launch owns the GPU."""
+    import csv
+    durs = [float(r["end_ms"]) - float(r["start_ms"]) for r in csv.DictReader(open(trace_csv)) if r["label"] == "apply2"]
+    if not durs:
+        return None
+    px = 2 * chunk * H * H
+    bytes_avg = px * ((128 + 3 * 256) / 4.0 + (3 * 192 + 256) / 4.0)
+    avg_s = sum(durs) / len(durs) / 1000.0
+    achieved = bytes_avg / avg_s / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
+            "traffic": 734.0e6, "kernel": "gru_apply2_kernel (ConvGRU gating + state update)",
+            "note": "avg of %d launches: %.1f us; algorithmic %.3e B/launch (%d tiles x 2 directions); peak = %s HBM copy "
+                    "bandwidth; traffic = dram read+write per launch from ncu (profiles/r01_f_summary.md: 411 MB + 323 MB)"
+                    % (len(durs), 1e6 * avg_s, bytes_avg, chunk, peaks["src"])}
 
 
 def measured_peaks():
@@ -276,7 +299,7 @@ def main():
     gates_ms_ovl, gates_n_ovl = sess.conv_timing_kind(64, 16, 0)   # GRU gates conv = the dominant tensor kernel
     conv_ms, conv_launches = sess.conv_timing(0)
     # ---- roofline pass: the same K steps on ONE stream, so that every conv launch owns the GPU while its
-    #      CUDA events bracket it (in the production schedule above two chunk streams share the SMs and the
+    #      CUDA events bracket it (in the production schedule above several chunk streams share the SMs and the
     #      per-launch durations include the other stream's kernels).  Not part of `value`. ----
     os.environ["STC_SINGLE_STREAM"] = "1"
     sess.predict_patches_dev(d_in, B, H, H, d_out)
@@ -289,6 +312,11 @@ def main():
     barrier()
     gates_ms, gates_n = sess.conv_timing_kind(64, 16, 0)
     conv_ms_single, conv_launches_single = sess.conv_timing(0)
+    trace_csv = os.path.join(ROOT, "gpurun_out", "bench_trace_rank%d.csv" % rank)
+    os.makedirs(os.path.dirname(trace_csv), exist_ok=True)
+    sess.trace(1)                            # one extra single-stream step with events around EVERY kernel (not timed)
+    sess.predict_patches_dev(d_in, B, H, H, d_out)
+    sess.trace(0, trace_csv)
     del os.environ["STC_SINGLE_STREAM"]
     # ---- end-to-end through the host-buffer C-ABI (e2e) ----
     _log("device-resident timing done (%.1f ms/step); e2e" % (ms / args.steps))
@@ -335,7 +363,7 @@ def main():
         roof = gates_roofline(gates_ms, gates_n, min(B, int(os.environ.get("STC_CHUNK", "32"))), peaks)
         if gates_n_ovl:
             roof["note"] += "; timed with every launch alone on the GPU (single-stream pass of the same %d steps, %.2f ms/step); in the " \
-                            "production two-stream schedule the same launches average %.1f us because two chunks share the SMs" \
+                            "production multi-slot schedule the same launches average %.1f us because chunks share the SMs" \
                             % (args.steps, ms_single / args.steps, 1e3 * gates_ms_ovl / gates_n_ovl)
         line = {"metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -352,11 +380,12 @@ def main():
                             "note": "same call with uint16 patches (reference integer convention x/65535, predict_subtile :345-347)"},
                 "gpu_launches": int(launches),
                 "roofline": roof,
+                "roofline_hbm": hbm_roofline(trace_csv, min(B, int(os.environ.get("STC_CHUNK", "32"))), peaks),
                 "roofline_all_convs": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
                              "frac": (achieved / peaks["tf"]) if achieved else None,
-                             "kernel": "conv3x3_umma_kernel (all conv launches of the step)",
+                             "kernel": "conv3x3_umma2_kernel (all conv launches of the step)",
                              "note": "algorithmic conv FLOPs/step (%.3e) / summed CUDA-event duration of the %d conv launches of the "
-                                     "single-stream pass (%.2f ms of its %.2f ms step; the two-stream production step takes %.2f ms, "
+                                     "single-stream pass (%.2f ms of its %.2f ms step; the multi-slot production step takes %.2f ms, "
                                      "its overlapping launches sum to %.2f ms); peak = %s sustained bf16/fp16 dense"
                                      % (flops / args.steps, conv_launches_single, conv_ms_single / args.steps, ms_single / args.steps,
                                         ms / args.steps, conv_ms / args.steps, peaks["src"])},

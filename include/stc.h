@@ -70,6 +70,10 @@ int stc_conv_timing(stc_ctx* ctx, int enable_reset, float* total_ms, int64_t* la
  * accumulated (0 = none) and epilogue mode (0 plain, 1 partial-conv+Swish, 2 Swish, 3 GRU
  * candidate, 4 bias, 5 bias+ReLU).  Call before the reset of stc_conv_timing. */
 int stc_conv_timing_kind(stc_ctx* ctx, int N, int groups, int mode, float* total_ms, int64_t* launches);
+/* Kernel timeline of the model path (profiling aid): enable != 0 starts recording CUDA events around every kernel
+ * of the forward; enable == 0 stops, synchronises and writes `label,slot,start_ms,end_ms` rows to csv_path.
+ * A start stamp is the time the kernel became the head of its stream, not the time its first block ran. */
+int stc_trace(stc_ctx* ctx, int enable, const char* csv_path);
 
 /* ---- model forward: predict_subtile (src/download_and_predict_job.py:328-369)
  *      = sess.run(predict_logits, {predict_inp: x[B,T+1,H,W,17], predict_length})

@@ -60,6 +60,7 @@ SYMBOLS = [
     ("stc_timer_end", C.c_int, [C.c_void_p, _f32p]),
     ("stc_conv_timing", C.c_int, [C.c_void_p, C.c_int, _f32p, C.POINTER(C.c_int64)]),
     ("stc_conv_timing_kind", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int64)]),
+    ("stc_trace", C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
     ("stc_predict_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
     ("stc_predict_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
     ("stc_assemble_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -250,6 +251,10 @@ class StcSession:
         ms, n = C.c_float(), C.c_int64()
         self._check(self.lib.stc_conv_timing_kind(self.h, N, groups, mode, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def trace(self, enable, csv_path=None):
+        """Kernel timeline of the model path (profiling aid, stc_trace)."""
+        self._check(self.lib.stc_trace(self.h, int(enable), csv_path.encode() if csv_path else None))
 
     # -- model -------------------------------------------------------------------
     def predict(self, x, length=None, normalize=False):

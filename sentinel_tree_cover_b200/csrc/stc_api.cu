@@ -1,5 +1,6 @@
 // extern "C" surface of libstc.so (declared in include/stc.h).
 #include "stc_common.cuh"
+#include <cstdio>
 #include <cstring>
 
 #define CTX_CHECK() do { if (!ctx) return STC_ERR_ARG; } while (0)
@@ -120,6 +121,27 @@ int stc_conv_timing_kind(stc_ctx* ctx, int N, int groups, int mode, float* total
   }
   if (total_ms) *total_ms = tot;
   if (launches) *launches = cnt;
+  return STC_OK;
+}
+
+int stc_trace(stc_ctx* ctx, int enable, const char* csv_path) {
+  CTX_CHECK();
+  if (enable) { ctx->trace.clear(); ctx->trace_on = true; return STC_OK; }
+  ctx->trace_on = false;
+  STC_CUDA(cudaDeviceSynchronize());
+  if (!csv_path || ctx->trace.empty()) return STC_OK;
+  FILE* f = fopen(csv_path, "w");
+  if (!f) STC_FAIL(STC_ERR_ARG, "trace: cannot open csv path");
+  fprintf(f, "label,slot,start_ms,end_ms\n");
+  for (auto& r : ctx->trace) {
+    float t0 = 0.f, t1 = 0.f;
+    cudaEventElapsedTime(&t0, ctx->trace[0].a, r.a);
+    cudaEventElapsedTime(&t1, ctx->trace[0].a, r.b);
+    fprintf(f, "%s,%d,%.4f,%.4f\n", r.label, r.slot, t0, t1);
+  }
+  for (auto& r : ctx->trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  fclose(f);
+  ctx->trace.clear();
   return STC_OK;
 }
 

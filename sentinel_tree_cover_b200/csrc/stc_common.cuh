@@ -82,6 +82,9 @@ struct stc_ctx {
   int last_slot = 0;
   cudaStream_t hi_stream[MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // high-priority conv lanes (stc_conv.cu)
   cudaEvent_t ev_lane[MAX_SLOTS][2] = {};
+  // kernel timeline (stc_trace)
+  struct TraceRec { cudaEvent_t a, b; const char* label; int slot; };
+  std::vector<TraceRec> trace; bool trace_on = false;
   int monthly_u16 = 0;        // the monthly patches of the current call are uint16 (x/65535), not float32
   void* sr = nullptr;         // SuperresState*
 };
@@ -96,6 +99,19 @@ struct stc_ctx {
   } while (0)
 
 #define STC_FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+
+// timeline helpers: bracket one launch on ctx->stream
+static inline void trace_begin(stc_ctx* ctx, const char* label) {
+  if (!ctx->trace_on) return;
+  stc_ctx::TraceRec r; r.label = label; r.slot = ctx->cur_slot;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, ctx->stream);
+  ctx->trace.push_back(r);
+}
+static inline void trace_end(stc_ctx* ctx) {
+  if (!ctx->trace_on || ctx->trace.empty()) return;
+  cudaEventRecord(ctx->trace.back().b, ctx->stream);
+}
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -810,6 +810,7 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
   }
   struct Restore { stc_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, base_stream};
   if (e0) STC_CUDA(cudaEventRecord(e0, ctx->stream));
+  trace_begin(ctx, p.N == 64 && p.mode == MODE_PLAIN ? "conv_gates" : p.mode == MODE_CAND ? "conv_cand" : p.N == 64 ? "conv_n64" : p.N == 128 ? "conv_n128" : p.N == 256 ? "conv_n256" : "conv_other");
   int rc;
   const int g = p.stats[0] ? p.G : 0;
   const int key = (p.N * 100 + g) * 10 + p.mode;
@@ -857,6 +858,7 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
   }
   if (rc != STC_OK) return rc;
   ctx->launches++;
+  trace_end(ctx);
   if (e1) STC_CUDA(cudaEventRecord(e1, ctx->stream));
   if (lane_slot >= 0) {
     STC_CUDA(cudaEventRecord(ctx->ev_lane[lane_slot][1], ctx->stream));

@@ -867,11 +867,13 @@ static int run_apply(stc_ctx* ctx, ModelState* m, int blk, const Act& src_geo, b
   ap.head_w = m->fp["head.w"]; ap.head_b = m->fp["head.b"]; ap.head_out = head_out;
   dim3 grid(cdiv((int64_t)Hd * Hd, 256), B);
   static const bool old_apply = getenv("STC_APPLY_OLD") != nullptr;      // A/B switch for profiling
+  trace_begin(ctx, "block_apply");
   if (old_apply) block_apply_kernel<<<grid, 256, 3 * ap.C * sizeof(float), ctx->stream>>>(ap);
   else if (ap.C == 64) launch_apply_c<64>(ap, grid, ctx->stream);
   else if (ap.C == 128) launch_apply_c<128>(ap, grid, ctx->stream);
   else if (ap.C == 256) launch_apply_c<256>(ap, grid, ctx->stream);
   else STC_FAIL(STC_ERR_ARG, "block tail: unsupported channel count");
+  trace_end(ctx);
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;
@@ -896,6 +898,7 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
       double lo = normalize ? mn[c] : 0.0, hi = normalize ? mx[c] : 1.0;
       pp.lo[c] = (float)lo; pp.hi[c] = (float)hi; pp.mid[c] = (float)((hi + lo) / 2); pp.half[c] = (float)((hi - lo) / 2);
     }
+    trace_begin(ctx, "front");
     static const bool fe_direct = getenv("STC_FRONT_DIRECT") != nullptr;       // A/B switch: the direct-load kernel
     if (monthly_dev && !fe_direct) {
       // staged front end: half[] carries the reciprocal (the product is rounded to fp16 right after)
@@ -924,6 +927,7 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
       prep_input_kernel<<<grid, 256, 0, ctx->stream>>>(pp);
     }
     STC_CUDA(cudaGetLastError()); ctx->launches++;
+    trace_end(ctx);
     if (input_consumed) STC_CUDA(cudaEventRecord(input_consumed, ctx->stream));   // the caller may refill its input buffer
   }
   // ---- bidirectional ConvGRU ----
@@ -963,7 +967,9 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
     gp.h_zero = (t == 0);
     dim3 ggrid(cdiv((int64_t)H * H, 256), B, 2);
     if (t > 0) {
+      trace_begin(ctx, "apply1");
       gru_apply1_kernel<<<ggrid, 256, 0, ctx->stream>>>(gp);
+      trace_end(ctx);
       STC_CUDA(cudaGetLastError()); ctx->launches++;
     }
 
@@ -977,7 +983,9 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
     cp.out_plane = m->rawY[0].plane; cp.N = 32; cp.G = 8; cp.mode = MODE_CAND;
     rc = launch_conv(ctx, cp, 2); if (rc) return rc;
 
+    trace_begin(ctx, "apply2");
     gru_apply2_kernel<<<ggrid, 256, 0, ctx->stream>>>(gp);
+    trace_end(ctx);
     STC_CUDA(cudaGetLastError()); ctx->launches++;
   }
   // ---- U-Net ----

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--trace", default="", help="write a kernel timeline CSV of one extra step")
     a = ap.parse_args()
     from sentinel_tree_cover_b200.api import StcSession
     from sentinel_tree_cover_b200.weights import random_predict_weights
@@ -53,6 +54,11 @@ def main():
             res[name] = {"avg_us": 1000.0 * t / c, "n": c, "ms_per_step": t / a.steps}
     t, c = sess.conv_timing(0)
     res["conv_ms_per_step"] = t / a.steps
+    if a.trace:
+        sess.sync()
+        sess.trace(1)
+        sess.predict_patches_dev(d_in, a.batch, H, H, d_out)
+        sess.trace(0, a.trace)
     sess.d2h(out, d_out); sess.sync()
     res["checksum"] = float(out.astype(np.float64).sum())
     res["max"] = float(out.max())
