@@ -83,6 +83,14 @@ int stc_trace(stc_ctx* ctx, int enable, const char* csv_path);
  *      (:316-325) is applied first with min17/max17.  out: [B,H-14,W-14]. ---- */
 int stc_predict_host(stc_ctx* ctx, const float* x_host, int B, int T, int H, int W, int length,
                      int normalize, const double* min17, const double* max17, float* out_host);
+/* Same forward, additionally returning the two feature taps of the --gen_feats path
+ * (src/download_and_predict_job.py:1429-1431,1807-1809): early = pb:gru_drop/drop_block2d/cond/Merge (the
+ * bidirectional ConvGRU output, 64 ch) centre-cropped to the output size like predict_subtile does (:360-362),
+ * late = pb:csse_out_mul/mul (the last block's sSE output, 64 ch).  early/late: [B,H-14,W-14,64] float32;
+ * probs_host [B,H-14,W-14] may be NULL. */
+int stc_predict_feats_host(stc_ctx* ctx, const float* x_host, int B, int T, int H, int W, int length,
+                           int normalize, const double* min17, const double* max17,
+                           float* probs_host, float* early_host, float* late_host);
 int stc_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int W, int length,
                     int normalize, const double* min17, const double* max17, float* out_dev);
 
@@ -149,6 +157,12 @@ int stc_mosaic_diffs_host(stc_ctx* ctx, const float* preds_host, const int32_t* 
 int stc_gauss_mosaic_host(stc_ctx* ctx, const float* preds_host, const int32_t* xs, const int32_t* ys,
                           const int32_t* placed, const float* gauss_host, const float* mult_host,
                           int n, int S, int out_h, int out_w, uint8_t* out_host);
+/* Feature mosaic: load_mosaic_predictions with depth > 1 (src/download_and_predict_job.py:1540-1592,1628-1635).
+ * feats [n,S,S,D] int16 as saved by process_subtiles --gen_feats (feats/<y>/<x>.npy), layers in the reference's
+ * os.listdir order; plain Gaussian weights normalised over the layers, nansum, int16 truncation.
+ * out: [D,out_h,out_w] int16.  (The reference walks the depth axis 8 channels at a time for memory reasons only.) */
+int stc_feature_mosaic_host(stc_ctx* ctx, const int16_t* feats_host, const int32_t* xs, const int32_t* ys,
+                            const float* gauss_host, int n, int S, int D, int out_h, int out_w, int16_t* out_host);
 
 /* ---- np.sum of `nseg` contiguous float32 segments of length `len` in NumPy's pairwise order (bit-identical
  *      to np.sum on a contiguous array): mode 0 plain; mode 1 values < 255 are multiplied by 100 first (the
@@ -238,6 +252,9 @@ int stc_process_subtiles_host(stc_ctx* ctx, const float* s2q_host, const float* 
  *      -min_db, rescaled to [0,1]. ------------------------------------------------------ */
 int stc_to_float32_host(stc_ctx* ctx, const uint16_t* in_host, int64_t n, float* out_host);
 int stc_to_uint16_host(stc_ctx* ctx, const float* in_host, int64_t n, uint16_t* out_host);
+/* float_to_int16 (src/download_and_predict_job.py:174-180): NaN -> -32768, clip to +-32.768 (for precision 1000),
+ * x * precision, int16 truncation -- the storage codec of the --gen_feats feature stacks. */
+int stc_float_to_int16_host(stc_ctx* ctx, const float* in_host, int64_t n, int precision, int16_t* out_host);
 int stc_convert_to_db_host(stc_ctx* ctx, const float* in_host, int64_t n, float min_db, float* out_host);
 
 /* ---- cloud-mask feathering, id_areas_to_interp (src/preprocessing/cloud_removal.py:774-798,

@@ -211,3 +211,51 @@ def synth_subtile_preds(L=618, S=158, seed=0, nodata_blocks=True, all_nodata=())
                 p[40:80, 80:120] = 255.
         preds.append(p); xs.append(int(x0)); ys.append(int(y0))
     return preds, xs, ys
+
+
+def float_to_int16(arr, precision=1000):
+    """src/download_and_predict_job.py:174-180."""
+    arr = np.array(arr, copy=True)
+    arr[np.isnan(arr)] = -32768
+    arr = np.clip(arr, (-32768 / precision), (32767 / precision))
+    arr = arr * precision
+    return np.int16(arr)
+
+
+def mosaic_feats(feats, xs, ys, out_shape, depth, sigma=36):
+    """load_mosaic_predictions for depth > 1 (src/download_and_predict_job.py:1540-1592,1628-1635), given the
+    saved int16 feature stacks [S,S,>=depth] in the reference's layer order: 8 channels at a time, plain Gaussian
+    weights normalised over the layer axis, nansum, int16 truncation."""
+    S = feats[0].shape[0]
+    N = len(feats)
+    output = np.full((depth,) + tuple(out_shape), 0., dtype=np.int16)
+    for start in np.arange(0, depth, 8):
+        end = start + 8
+        predictions = np.full((8, out_shape[0], out_shape[1], N), np.nan, dtype=np.float32)
+        mults = np.full((1, out_shape[0], out_shape[1], N), 0, dtype=np.float32)
+        for i, (f, x, y) in enumerate(zip(feats, xs, ys)):
+            prediction = f[..., start:end]
+            prediction = (prediction).T.astype(np.float32)
+            predictions[:, x:x + S, y:y + S, i] = prediction
+            mults[:, x:x + S, y:y + S, i] = fspecial_gauss(S, sigma)
+        with np.errstate(all="ignore"):
+            mults = mults / np.sum(mults, axis=-1)[..., np.newaxis]
+            p = np.nansum(predictions * mults, axis=-1)
+            output[start:end] = np.int16(p)
+    return output
+
+
+def synth_subtile_feats(L=250, S=158, D=16, seed=0):
+    """Synthetic saved int16 feature stacks for an L x L tile (smooth fields + noise, x1000 codes)."""
+    from sentinel_tree_cover_b200.windows import subtile_windows
+    r = np.random.default_rng(seed)
+    folder, _ = subtile_windows(L, L, S)
+    yy, xx = np.mgrid[0:L, 0:L]
+    feats, xs, ys = [], [], []
+    for k, (x0, y0, _, _) in enumerate(folder):
+        f = np.empty((S, S, D), np.float32)
+        for c in range(D):
+            field = np.sin(xx / (17.0 + c)) * np.cos(yy / (29.0 - c)) * (1.0 + 0.3 * c)
+            f[..., c] = field[x0:x0 + S, y0:y0 + S].T + r.normal(0, 0.05, (S, S))
+        feats.append(float_to_int16(f)); xs.append(int(x0)); ys.append(int(y0))
+    return feats, xs, ys

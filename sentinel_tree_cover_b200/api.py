@@ -62,6 +62,9 @@ SYMBOLS = [
     ("stc_conv_timing_kind", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int64)]),
     ("stc_trace", C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
     ("stc_predict_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
+    ("stc_predict_feats_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("stc_float_to_int16_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    ("stc_feature_mosaic_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_predict_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_void_p]),
     ("stc_assemble_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_assemble_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -267,6 +270,42 @@ class StcSession:
         mn, mnp = _f64(self.min_all)
         mx, mxp = _f64(self.max_all)
         self._check(self.lib.stc_predict_host(self.h, _dptr(x), B, T1 - 1, H, W, length, int(bool(normalize)), mnp, mxp, _dptr(out)))
+        return out
+
+    def predict_feats(self, x, length=None, normalize=False):
+        """Forward plus the two --gen_feats taps: (probs [B,H-14,W-14], early [B,H-14,W-14,64], late [..,64])
+        = pb:conv2d/Sigmoid, pb:gru_drop/drop_block2d/cond/Merge (centre-cropped), pb:csse_out_mul/mul."""
+        x = np.ascontiguousarray(x, np.float32)
+        B, T1, H, W, Cc = x.shape
+        assert Cc == 17
+        length = int(self.length if length is None else length)
+        probs = np.empty((B, H - 14, W - 14), np.float32)
+        early = np.empty((B, H - 14, W - 14, 64), np.float32)
+        late = np.empty((B, H - 14, W - 14, 64), np.float32)
+        mn, mnp = _f64(self.min_all)
+        mx, mxp = _f64(self.max_all)
+        self._check(self.lib.stc_predict_feats_host(self.h, _dptr(x), B, T1 - 1, H, W, length, int(bool(normalize)), mnp, mxp,
+                                                    _dptr(probs), _dptr(early), _dptr(late)))
+        return probs, early, late
+
+    def float_to_int16(self, arr, precision=1000):
+        a = np.ascontiguousarray(arr, np.float32)
+        out = np.empty(a.shape, np.int16)
+        self._check(self.lib.stc_float_to_int16_host(self.h, _dptr(a), a.size, int(precision), _dptr(out)))
+        return out
+
+    def mosaic_feats(self, feats, xs, ys, out_shape, sigma=36):
+        """Feature mosaic (load_mosaic_predictions, depth > 1): feats list of [S,S,D] int16 stacks in the reference's
+        layer order -> [D, out_shape[0], out_shape[1]] int16."""
+        n = len(feats)
+        F = np.ascontiguousarray(np.stack([np.asarray(f) for f in feats]), np.int16)
+        S, D = F.shape[1], F.shape[3]
+        xs = np.ascontiguousarray(xs, np.int32)
+        ys = np.ascontiguousarray(ys, np.int32)
+        gauss = np.ascontiguousarray(fspecial_gauss(S, sigma), np.float32)
+        out = np.empty((D, int(out_shape[0]), int(out_shape[1])), np.int16)
+        self._check(self.lib.stc_feature_mosaic_host(self.h, _dptr(F), _dptr(xs), _dptr(ys), _dptr(gauss), n, S, D,
+                                                     int(out_shape[0]), int(out_shape[1]), _dptr(out)))
         return out
 
     def predict_dev(self, x_dev, B, T, H, W, out_dev, length=None, normalize=False):
@@ -560,18 +599,32 @@ def normalize_subtile(subtile, min_all=MIN_ALL, max_all=MAX_ALL, sess=None):
     return subtile
 
 
+# Tensor names a caller of the reference passes as `op` (src/download_and_predict_job.py:1807-1809)
+PREDICT_LOGITS = "predict/conv2d_13/Sigmoid:0"
+PREDICT_LATEFEATS = "predict/csse_out_mul/mul:0"
+PREDICT_EARLYFEATS = "predict/gru_drop/drop_block2d/cond/Merge:0"
+
+
 def predict_subtile(subtile, sess, op=None, size=None):
-    """src/download_and_predict_job.py:328-369.  `op` is accepted for signature
-    compatibility (only predict_logits exists here).  All-zero input -> int 255 fill."""
+    """src/download_and_predict_job.py:328-369.  `op` selects the output like the reference's tensor handle:
+    None / PREDICT_LOGITS -> probabilities, PREDICT_LATEFEATS / PREDICT_EARLYFEATS -> the 64-channel feature taps
+    of the --gen_feats path (:1430-1431), squeezed and centre-cropped to `size` the same way.  All-zero input ->
+    int 255 fill."""
     SIZE = subtile.shape[1] - 14
     size = SIZE if size is None else size
+    if op not in (None, PREDICT_LOGITS, PREDICT_LATEFEATS, PREDICT_EARLYFEATS):
+        raise ValueError("predict_subtile: unknown output tensor %r" % (op,))
     if np.sum(subtile) != 0:
         if not isinstance(subtile.flat[0], np.floating):
             assert np.max(subtile) > 1
             # `subtile / 65535.` (float64) followed by astype(float32) == correctly rounded float32 x/65535
             subtile = sess.to_float32(np.ascontiguousarray(subtile).astype(np.uint16, copy=False))
         batch_x = subtile[np.newaxis].astype(np.float32)
-        preds = sess.predict(batch_x, length=sess.length).squeeze()
+        if op in (PREDICT_LATEFEATS, PREDICT_EARLYFEATS):
+            _, early, late = sess.predict_feats(batch_x, length=sess.length)
+            preds = (late if op == PREDICT_LATEFEATS else early).squeeze()    # early is already cropped to H-14
+        else:
+            preds = sess.predict(batch_x, length=sess.length).squeeze()
         clip = (preds.shape[0] - size) // 2
         if clip > 0:
             preds = preds[clip:-clip, clip:-clip]
@@ -579,6 +632,11 @@ def predict_subtile(subtile, sess, op=None, size=None):
     else:
         preds = np.full((SIZE, SIZE), 255)
     return preds
+
+
+def float_to_int16(arr, sess, precision=1000):
+    """src/download_and_predict_job.py:174-180 (the NaN replacement is in place there too)."""
+    return sess.float_to_int16(arr, precision)
 
 
 def make_indices(arr, sess):
@@ -763,10 +821,9 @@ def fspecial_gauss(size, sigma):
 
 
 def load_mosaic_predictions(out_folder, depth, sess, size=None):
-    """src/download_and_predict_job.py:1515-1641 for depth == 1: walk processed/<x>/<y>.npy in
-    the reference's os.listdir order, blend on the GPU, return the uint8 tile."""
-    if depth != 1:
-        raise NotImplementedError("feature mosaics (depth > 1) are not part of this path yet")
+    """src/download_and_predict_job.py:1515-1641: walk <out_folder>/<x>/<y>.npy in the reference's os.listdir order
+    and blend on the GPU.  depth == 1: probabilities -> the uint8 tile; depth > 1: int16 feature stacks
+    [S,S,>=depth] -> int16 [depth, max_x, max_y] (:1587-1592,1628-1635)."""
     x_tiles = [int(x) for x in os.listdir(out_folder) if '.DS' not in x]
     preds, xs, ys = [], [], []
     for x_tile in x_tiles:
@@ -778,4 +835,6 @@ def load_mosaic_predictions(out_folder, depth, sess, size=None):
     S = size or preds[0].shape[0]
     max_x = np.max(x_tiles) + S
     max_y = np.max(y_tiles) + S          # like the reference: from the last listed x folder (:1535-1538)
-    return sess.mosaic(preds, xs, ys, (max_x, max_y))
+    if depth == 1:
+        return sess.mosaic(preds, xs, ys, (max_x, max_y))
+    return sess.mosaic_feats([p[..., :depth] for p in preds], xs, ys, (max_x, max_y))

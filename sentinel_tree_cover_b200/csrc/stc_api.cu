@@ -172,6 +172,27 @@ int stc_predict_host(stc_ctx* ctx, const float* x_host, int B, int T, int H, int
   return STC_OK;
 }
 
+int stc_predict_feats_host(stc_ctx* ctx, const float* x_host, int B, int T, int H, int W, int length,
+                           int normalize, const double* min17, const double* max17,
+                           float* probs_host, float* early_host, float* late_host) {
+  CTX_CHECK();
+  if (!x_host || !early_host || !late_host || B < 1) STC_FAIL(STC_ERR_ARG, "predict_feats: bad argument");
+  size_t nin = (size_t)B * (T + 1) * H * W * 17, nout = (size_t)B * (H - 14) * (W - 14);
+  DevBuf din, dout, de, dl;
+  STC_CUDA(cudaMalloc(&din.p, nin * 4)); STC_CUDA(cudaMalloc(&dout.p, nout * 4));
+  STC_CUDA(cudaMalloc(&de.p, nout * 64 * 4)); STC_CUDA(cudaMalloc(&dl.p, nout * 64 * 4));
+  STC_CUDA(cudaMemcpyAsync(din.p, x_host, nin * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->feat_early_dev = (float*)de.p; ctx->feat_late_dev = (float*)dl.p;
+  int rc = model_predict_dev(ctx, (const float*)din.p, B, T, H, W, length, normalize, min17, max17, (float*)dout.p);
+  ctx->feat_early_dev = ctx->feat_late_dev = nullptr;
+  if (rc) return rc;
+  if (probs_host) STC_CUDA(cudaMemcpyAsync(probs_host, dout.p, nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(early_host, de.p, nout * 64 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(late_host, dl.p, nout * 64 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
 int stc_assemble_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W, float* out_dev) {
   CTX_CHECK();
   return pre_assemble_dev(ctx, monthly_dev, B, H, W, out_dev);
@@ -395,6 +416,26 @@ int stc_gauss_mosaic_host(stc_ctx* ctx, const float* preds_host, const int32_t* 
                             (float*)dm.p, nullptr, 1, n, S, out_h, out_w, (unsigned char*)dt.p, (unsigned char*)dout.p);
   if (rc) return rc;
   STC_CUDA(cudaMemcpyAsync(out_host, dout.p, (size_t)out_h * out_w, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+int stc_feature_mosaic_host(stc_ctx* ctx, const int16_t* feats_host, const int32_t* xs, const int32_t* ys, const float* gauss_host,
+                            int n, int S, int D, int out_h, int out_w, int16_t* out_host) {
+  CTX_CHECK();
+  if (!feats_host || !xs || !ys || !gauss_host || !out_host || n < 1 || S < 1 || D < 1 || out_h < 1 || out_w < 1)
+    STC_FAIL(STC_ERR_ARG, "feature_mosaic: bad argument");
+  DevBuf df, dx, dy, dg, dout;
+  const size_t nf = (size_t)n * S * S * D, no = (size_t)D * out_h * out_w;
+  STC_CUDA(cudaMalloc(&df.p, nf * 2)); STC_CUDA(cudaMalloc(&dx.p, n * 4)); STC_CUDA(cudaMalloc(&dy.p, n * 4));
+  STC_CUDA(cudaMalloc(&dg.p, (size_t)S * S * 4)); STC_CUDA(cudaMalloc(&dout.p, no * 2));
+  STC_CUDA(cudaMemcpyAsync(df.p, feats_host, nf * 2, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(dx.p, xs, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(dy.p, ys, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(dg.p, gauss_host, (size_t)S * S * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = pre_feature_mosaic_dev(ctx, (const short*)df.p, (const int*)dx.p, (const int*)dy.p, (const float*)dg.p, n, S, D, out_h, out_w, (short*)dout.p);
+  if (rc) return rc;
+  STC_CUDA(cudaMemcpyAsync(out_host, dout.p, no * 2, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
   return STC_OK;
 }

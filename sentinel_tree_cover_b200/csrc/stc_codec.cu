@@ -32,6 +32,18 @@ __global__ void __launch_bounds__(256) convert_to_db_kernel(const float* __restr
   out[i] = fminf(fmaxf(x, 0.f), 1.f);
 }
 
+// float_to_int16 (src/download_and_predict_job.py:174-180): NaN -> -32768, clip to [-32768/p, 32767/p] (float32 bounds),
+// * p, np.int16() truncation.  Used for the --gen_feats feature stacks (p = 1000).
+__global__ void __launch_bounds__(256) float_to_int16_kernel(const float* __restrict__ in, int16_t* __restrict__ out, int64_t n,
+                                                              float lo, float hi, float precision) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = in[i];
+  if (isnan(v)) v = -32768.f;
+  v = fminf(fmaxf(v, lo), hi);
+  out[i] = (int16_t)__fmul_rn(v, precision);
+}
+
 namespace {
 struct Buf { void* p = nullptr; ~Buf() { if (p) cudaFree(p); } };
 }
@@ -58,6 +70,21 @@ int stc_to_uint16_host(stc_ctx* ctx, const float* in_host, int64_t n, uint16_t* 
   STC_CUDA(cudaMalloc(&a.p, n * 4)); STC_CUDA(cudaMalloc(&b.p, n * 2));
   STC_CUDA(cudaMemcpyAsync(a.p, in_host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
   to_uint16_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (uint16_t*)b.p, n);
+  STC_CUDA(cudaGetLastError()); ctx->launches++;
+  STC_CUDA(cudaMemcpyAsync(out_host, b.p, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+int stc_float_to_int16_host(stc_ctx* ctx, const float* in_host, int64_t n, int precision, int16_t* out_host) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!in_host || !out_host || n < 1 || precision < 1) STC_FAIL(STC_ERR_ARG, "float_to_int16: bad argument");
+  Buf a, b;
+  STC_CUDA(cudaMalloc(&a.p, n * 4)); STC_CUDA(cudaMalloc(&b.p, n * 2));
+  STC_CUDA(cudaMemcpyAsync(a.p, in_host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  // np.clip(float32 array, python float, python float): the bounds are float64 scalars cast to float32
+  float_to_int16_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (int16_t*)b.p, n, (float)(-32768.0 / precision),
+                                                              (float)(32767.0 / precision), (float)precision);
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(out_host, b.p, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -85,6 +85,9 @@ struct stc_ctx {
   // kernel timeline (stc_trace)
   struct TraceRec { cudaEvent_t a, b; const char* label; int slot; };
   std::vector<TraceRec> trace; bool trace_on = false;
+  // --gen_feats taps of the current call (device, [B,H-14,W-14,64] float32) and of the chunk being enqueued
+  float* feat_early_dev = nullptr; float* feat_late_dev = nullptr;
+  float* feat_early_chunk = nullptr; float* feat_late_chunk = nullptr;
   int monthly_u16 = 0;        // the monthly patches of the current call are uint16 (x/65535), not float32
   void* sr = nullptr;         // SuperresState*
 };
@@ -136,6 +139,8 @@ int pre_temporal_median_dev(stc_ctx* ctx, const float* in_dev, int n, int64_t in
 int pre_gauss_mosaic_dev(stc_ctx* ctx, const float* preds_dev, const int* xs_dev, const int* ys_dev, const int* placed_dev,
                          const float* gauss_dev, float* mult_dev, float* diffs_dev, int stage,
                          int n, int S, int Hc, int Wc, unsigned char* tmp_dev, unsigned char* out_dev);
+int pre_feature_mosaic_dev(stc_ctx* ctx, const short* feats_dev, const int* xs_dev, const int* ys_dev, const float* gauss_dev,
+                           int n, int S, int D, int Hc, int Wc, short* out_dev);
 int pre_feather_dev(stc_ctx* ctx, const float* mask_dev, int n, int H, int W, int size, float* tmp_a, float* tmp_b,
                     float* sums_dev, float* out_dev);
 int pre_binary_dilate_dev(stc_ctx* ctx, const unsigned char* in_dev, int n, int H, int W, int iterations, int conn,

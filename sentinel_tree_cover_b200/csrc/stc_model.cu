@@ -451,6 +451,7 @@ struct ApplyParams {
   uint4* dst; int64_t dst_plane; int dHp, dWp;
   int Hd, Wd; int mode; int off;  // mode 0 identity(+crop off) 1 maxpool2 2 upsample2 3 head
   const float* head_w; const float* head_b; float* head_out;
+  float* feat_out;             // mode 3, optional: the block's sSE output (pb:csse_out_mul/mul) [B,Hd,Wd,C] float32
 };
 
 __global__ void __launch_bounds__(256) block_apply_kernel(ApplyParams p) {
@@ -577,6 +578,15 @@ __global__ void __launch_bounds__(256, 2) block_apply_t(ApplyParams p) {
       acc += (v.x * a.x + bb.x) * hw.x + (v.y * a.y + bb.y) * hw.y + (v.z * a.z + bb.z) * hw.z + (v.w * a.w + bb.w) * hw.w;
     }
     p.head_out[((int64_t)b * p.Hd + yd) * p.Wd + xd] = fast_sigm(acc * sv[0] + p.head_b[0]);
+    if (p.feat_out) {     // --gen_feats late features (src/download_and_predict_job.py:1430, pb:csse_out_mul/mul)
+      float4* fo = reinterpret_cast<float4*>(p.feat_out + (((int64_t)b * p.Hd + yd) * p.Wd + xd) * C);
+#pragma unroll
+      for (int c4 = 0; c4 < C / 4; ++c4) {
+        const float4 v = KEEP ? keep[c4] : p.raw[(int64_t)c4 * p.raw_plane + SP[0]];
+        const float4 a = s_a[c4], bb = s_b[c4];
+        fo[c4] = make_float4((v.x * a.x + bb.x) * sv[0], (v.y * a.y + bb.y) * sv[0], (v.z * a.z + bb.z) * sv[0], (v.w * a.w + bb.w) * sv[0]);
+      }
+    }
     return;
   }
   const int64_t DP = ((int64_t)b * p.dHp + yd + 1) * p.dWp + xd + 1;
@@ -608,6 +618,22 @@ static void launch_apply_c(const ApplyParams& ap, dim3 grid, cudaStream_t s) {
     case 2: block_apply_t<C, 2><<<grid, 256, 0, s>>>(ap); break;
     default: block_apply_t<C, 3><<<grid, 256, 0, s>>>(ap); break;
   }
+}
+
+// --gen_feats early features (src/download_and_predict_job.py:1431, pb:gru_drop/drop_block2d/cond/Merge = the
+// bidirectional ConvGRU output, DropBlock is the identity at inference): channels 0..63 of the concat buffer,
+// centre-cropped by `crop` like predict_subtile does (:360-362), float32 [B,Hd,Hd,64].
+__global__ void feat_early_kernel(const uint4* src, int64_t plane, int B, int Hp, int Wp, int crop, int Hd, float* out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = (int64_t)B * Hd * Hd * 8;
+  if (idx >= n) return;
+  int c = (int)(idx & 7); int64_t r = idx >> 3;
+  int x = (int)(r % Hd); r /= Hd; int y = (int)(r % Hd); int b = (int)(r / Hd);
+  int64_t P = ((int64_t)b * Hp + y + crop + 1) * Wp + x + crop + 1;
+  float v[8];
+  unpack8(src[(int64_t)c * plane + P], v);
+  float4* o = reinterpret_cast<float4*>(out + (((int64_t)b * Hd + y) * Hd + x) * 64 + c * 8);
+  o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
 // decode an fp16 activation buffer interior to fp32 NHWC (debug / tests)
@@ -865,6 +891,7 @@ static int run_apply(stc_ctx* ctx, ModelState* m, int blk, const Act& src_geo, b
   if (dst) { ap.dst = dst->at(dst_chunk_off); ap.dst_plane = dst->plane; ap.dHp = dst->Hp; ap.dWp = dst->Wp; }
   ap.Hd = Hd; ap.Wd = Hd; ap.mode = mode; ap.off = off;
   ap.head_w = m->fp["head.w"]; ap.head_b = m->fp["head.b"]; ap.head_out = head_out;
+  ap.feat_out = (mode == 3) ? ctx->feat_late_chunk : nullptr;
   dim3 grid(cdiv((int64_t)Hd * Hd, 256), B);
   static const bool old_apply = getenv("STC_APPLY_OLD") != nullptr;      // A/B switch for profiling
   trace_begin(ctx, "block_apply");
@@ -988,6 +1015,13 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
     trace_end(ctx);
     STC_CUDA(cudaGetLastError()); ctx->launches++;
   }
+  // ---- optional feature taps (--gen_feats) ----
+  const int Ho_f = u3 - 2;
+  if (ctx->feat_early_chunk) {
+    int64_t work = (int64_t)B * Ho_f * Ho_f * 8;
+    feat_early_kernel<<<cdiv(work, 256), 256, 0, ctx->stream>>>(m->CCin.at(0), m->CCin.plane, B, m->CCin.Hp, m->CCin.Wp, (H - Ho_f) / 2, Ho_f, ctx->feat_early_chunk);
+    STC_CUDA(cudaGetLastError()); ctx->launches++;
+  }
   // ---- U-Net ----
   int rc;
   Act xmed = m->X16; xmed.base = m->X16.base + (int64_t)T * m->x_frame_stride; xmed.chunks = 4;
@@ -1050,12 +1084,15 @@ static int run_chunks(stc_ctx* ctx, const float* x_dev, const float* monthly_dev
     rc = ensure_plan(ctx, m, Bc, H, T + 1);
     const float* mchunk = nullptr;
     if (monthly_dev) mchunk = reinterpret_cast<const float*>(reinterpret_cast<const char*>(monthly_dev) + b0 * per_in * (ctx->monthly_u16 ? 2 : 4));
+    ctx->feat_early_chunk = ctx->feat_early_dev ? ctx->feat_early_dev + (size_t)b0 * Ho * Ho * 64 : nullptr;
+    ctx->feat_late_chunk = ctx->feat_late_dev ? ctx->feat_late_dev + (size_t)b0 * Ho * Ho * 64 : nullptr;
     if (!rc) rc = forward_chunk(ctx, m, x_dev ? x_dev + b0 * per_in : nullptr, mchunk,
                                 nb, T, H, length, normalize, mn, mx, out_dev + (size_t)b0 * Ho * Ho, nullptr);
     m->lastB = nb; ctx->last_slot = slot;
   }
   ctx->stream = main_stream;
   ctx->cur_slot = 0;
+  ctx->feat_early_chunk = ctx->feat_late_chunk = nullptr;
   if (rc) return rc;
   for (int i = 1; i < ns; ++i) {
     STC_CUDA(cudaEventRecord(ctx->ev_join[i], ctx->slot_stream[i]));

@@ -125,6 +125,41 @@ __global__ void __launch_bounds__(256) mosaic_dilate_kernel(const unsigned char*
   out[idx] = o;
 }
 
+// Feature mosaic, load_mosaic_predictions with depth > 1 (src/download_and_predict_job.py:1540-1592,1628-1635):
+// every saved int16 feature stack [S,S,D] is transposed, placed, weighted with the plain Gaussian (no no-data
+// zeroing, no overlap reweighting), weights normalised over the layer axis, nansum, int16 truncation.  Float32
+// reductions over the layer axis follow NumPy's pairwise order (np_sum).  out: [D][Hc][Wc] int16.
+__global__ void __launch_bounds__(128) mosaic_feats_kernel(const short* feats, const int* xs, const int* ys, const float* gauss,
+                                                           int n, int S, int D, int Hc, int Wc, short* out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Hc * Wc) return;
+  int X = idx / Wc, Y = idx - X * Wc;
+  float w[64], v[64];
+  int64_t src[64];
+  for (int i = 0; i < n; ++i) {
+    int px = X - xs[i], py = Y - ys[i];
+    if (px < 0 || py < 0 || px >= S || py >= S) { w[i] = 0.f; src[i] = -1; }
+    else { w[i] = gauss[px * S + py]; src[i] = (((int64_t)i * S + py) * S + px) * D; }   // prediction.T[c, px, py] = prediction[py, px, c]
+  }
+  const float W = np_sum(w, n);
+  for (int i = 0; i < n; ++i) w[i] = __fdiv_rn(w[i], W);          // 0/0 = NaN where nothing covers the pixel
+  for (int c = 0; c < D; ++c) {
+    for (int i = 0; i < n; ++i) {
+      float prod = (src[i] >= 0) ? __fmul_rn((float)feats[src[i] + c], w[i]) : nanf("");
+      v[i] = isnan(prod) ? 0.f : prod;                              // np.nansum
+    }
+    out[((int64_t)c * Hc + X) * Wc + Y] = (short)np_sum(v, n);     // np.int16(): truncation
+  }
+}
+
+int pre_feature_mosaic_dev(stc_ctx* ctx, const short* feats_dev, const int* xs_dev, const int* ys_dev, const float* gauss_dev,
+                           int n, int S, int D, int Hc, int Wc, short* out_dev) {
+  if (n < 1 || n > 64) STC_FAIL(STC_ERR_ARG, "feature mosaic: 1..64 subtiles supported");
+  mosaic_feats_kernel<<<cdiv((int64_t)Hc * Wc, 128), 128, 0, ctx->stream>>>(feats_dev, xs_dev, ys_dev, gauss_dev, n, S, D, Hc, Wc, out_dev);
+  STC_CUDA(cudaGetLastError()); ctx->launches++;
+  return STC_OK;
+}
+
 int pre_gauss_mosaic_dev(stc_ctx* ctx, const float* preds_dev, const int* xs_dev, const int* ys_dev, const int* placed_dev,
                          const float* gauss_dev, float* mult_dev, float* diffs_dev, int stage,
                          int n, int S, int Hc, int Wc, unsigned char* tmp_dev, unsigned char* out_dev) {

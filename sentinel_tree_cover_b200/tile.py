@@ -286,12 +286,14 @@ def count_lt_axis0(data, thresh, sess):
 
 
 def process_subtiles(x, y, s2=None, dates=None, interp=None, s1=None, dem=None, sess=None, bbx=None, size=158, train_bbx=None,
-                     local_path="", length=4):
-    """:1125-1486 for the prediction path (args.process, no --gen_feats / --gen_composite /
+                     local_path="", length=4, gen_feats=False):
+    """:1125-1486 for the prediction path (args.process, optionally --gen_feats; no --gen_composite /
     --make_training_data): medians, smoothing, quarterly composites, 6x6 overlapping windows with the
     reference's edge padding, 17-channel assembly, prediction, post-filters, one
     `<local_path><x>/<y>/processed/<folder_y>/<folder_x>.npy` per subtile (float32, 255 = no data).
     B200 shape of the loop: all subtiles of the tile go through ONE batched forward.
+    gen_feats (:1429-1448): for every subtile with data, `feats/<folder_y>/<folder_x>.npy` = int16 x1000 of
+    [early features 0..31 | late features 0..31] (one more batched forward that returns both taps).
     Not reproduced (I/O products, out of scope): ard_ndmi.hkl, ard_dates.npy, the composite GeoTIFF / ARD
     uploads (:1161-1205).  `bbx` / `train_bbx` are accepted and unused, like in the prediction path."""
     if sess is None:
@@ -364,7 +366,7 @@ def process_subtiles(x, y, s2=None, dates=None, interp=None, s1=None, dem=None, 
     clear_all = count_lt_axis0(interp, 0.33, sess)                                        # np.sum(interp < 0.33, axis=0), whole tile
     _mark("quarterly medians + counts")
 
-    if fused and not os.environ.get("STC_TILE_HOST_GATHER"):
+    if fused and not gen_feats and not os.environ.get("STC_TILE_HOST_GATHER"):
         # window table only (integers); gather, stacks, no-image test, forward and post-filters run on the device
         table = np.zeros((len(tiles_folder), 12), np.int32)
         outputs = []
@@ -464,3 +466,16 @@ def process_subtiles(x, y, s2=None, dates=None, interp=None, s1=None, dem=None, 
         os.makedirs(os.path.realpath(os.path.dirname(outputs[i])), exist_ok=True)
         np.save(outputs[i], out[i])
     _mark("save")
+    if gen_feats:                                                                         # :1429-1446
+        live = [i for i in range(len(stacks)) if not no_data[i]]
+        if live:
+            _, early, late = sess.predict_feats(batch[live], length=length, normalize=True)
+            both = sess.float_to_int16(np.concatenate([early[..., :32], late[..., :32]], axis=-1))
+            root = f'{local_path}{str(x)}/{str(y)}/'
+            for k, i in enumerate(live):
+                out_f = outputs[i].replace(path, root + "feats/")
+                os.makedirs(os.path.realpath(os.path.dirname(out_f)), exist_ok=True)
+                np.save(out_f, both[k])
+            os.makedirs(os.path.realpath(root + "raw/feats/"), exist_ok=True)
+            os.makedirs(os.path.realpath(root + "ard/"), exist_ok=True)
+        _mark("features")

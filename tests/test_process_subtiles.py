@@ -41,3 +41,34 @@ def test_gpu_process_subtiles_matches_reference_golden(sess, tmp_path, monkeypat
         worst = max(worst, float(np.abs(got[m] - want[m]).max()) if m.any() else 0.0)
         assert np.allclose(got[~m], want[~m], rtol=0, atol=1e-3), (fy, fx)
     assert worst <= 1.5e-3, worst      # 1e-3 model tolerance + half a rounding step
+
+
+@pytest.mark.gpu
+def test_gpu_process_subtiles_gen_feats(sess, tmp_path):
+    """--gen_feats (:1429-1446): same prediction files, plus feats/<fy>/<fx>.npy = int16 [158,158,64]
+    ([early 0..31 | late 0..31] x 1000) for every subtile that was predicted (numerics of the taps:
+    tests/test_feats.py), and the feature mosaic of the tile."""
+    from sentinel_tree_cover_b200.tile import process_subtiles
+    from sentinel_tree_cover_b200.api import load_mosaic_predictions
+    g = np.load(GOLD)
+    seed, n, H, W = [int(v) for v in g["case"]]
+    s2, dates, interp, s1, dem = subtiles_ref.synth_ard(seed, n, H, W)
+    root = str(tmp_path) + "/"
+    process_subtiles(3, 4, s2, dates, interp, s1, dem, sess, [0, 0, 1, 1], 158, None, local_path=root, length=4, gen_feats=True)
+    pred_path, feat_path = root + "3/4/processed/", root + "3/4/feats/"
+    n_feats = 0
+    for fy in os.listdir(pred_path):
+        for f in os.listdir(pred_path + fy):
+            want = g["pred_%d_%d" % (int(fy), int(f[:-4]))]
+            got = np.load(pred_path + fy + "/" + f)
+            assert np.array_equal(got == 255, want == 255)
+            ff = feat_path + fy + "/" + f
+            if os.path.exists(ff):
+                a = np.load(ff)
+                assert a.dtype == np.int16 and a.shape == (158, 158, 64) and np.abs(a.astype(np.int32)).max() > 100
+                n_feats += 1
+            else:
+                assert (want == 255).all()          # only subtiles without any usable image skip the features
+    assert n_feats > 0 and os.path.isdir(root + "3/4/raw/feats/") and os.path.isdir(root + "3/4/ard/")
+    m = load_mosaic_predictions(feat_path, 64, sess)
+    assert m.dtype == np.int16 and m.shape[0] == 64 and np.abs(m.astype(np.int32)).max() > 100

@@ -120,10 +120,11 @@ def main():
     out["srtile_out_sum"] = np.float64(res.astype(np.float64).sum())
     np.savez_compressed(os.path.join(OUT, "preproc.npz"), **out)
     mosaic_golden()
+    mosaic_feats_golden()
     print("wrote", sorted(os.listdir(OUT)))
 
 
-if __name__ == "__main__" and "--mosaic-only" not in sys.argv:
+if __name__ == "__main__" and "--mosaic-only" not in sys.argv and "--mosaic-feats-only" not in sys.argv:
     main()
 
 
@@ -152,5 +153,36 @@ def mosaic_golden():
     print("mosaic golden", {k: v.shape for k, v in out.items()})
 
 
+def mosaic_feats_golden():
+    """load_mosaic_predictions(depth=16) and float_to_int16 run by the reference on synthetic feature files."""
+    import shutil, tempfile
+    job = refshim.ref("download_and_predict_job")
+    out = {}
+    feats, xs, ys = P.synth_subtile_feats(250, 158, 16, seed=3)
+    d = tempfile.mkdtemp() + "/"
+    for f, x, y in zip(feats, xs, ys):
+        os.makedirs(d + str(x), exist_ok=True)
+        np.save(d + str(x) + "/" + str(y) + ".npy", f)
+    job.SIZE = 158
+    with np.errstate(all="ignore"):
+        res = job.load_mosaic_predictions(d, 16)
+    order = []
+    for xt in [int(x) for x in os.listdir(d)]:
+        for yt in [int(y[:-4]) for y in os.listdir(d + str(xt) + "/")]:
+            order.append((xt, yt))
+    out["order"] = np.array(order, np.int32)
+    out["out"] = res
+    shutil.rmtree(d)
+    r = np.random.default_rng(11)
+    x = (r.normal(0, 12, (64, 33)) * r.choice([0.01, 1, 5], (64, 33))).astype(np.float32)
+    x[3, 4] = np.nan; x[0, 0] = 40.0; x[1, 1] = -40.0; x[2, 2] = 32.767; x[5, 5] = -32.768
+    out["f2i_in"] = x
+    out["f2i_out"] = job.float_to_int16(x.copy())
+    np.savez_compressed(os.path.join(OUT, "mosaic_feats.npz"), **out)
+    print("mosaic feats golden", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__" and "--mosaic-only" in sys.argv:
     mosaic_golden()
+if __name__ == "__main__" and "--mosaic-feats-only" in sys.argv:
+    mosaic_feats_golden()
