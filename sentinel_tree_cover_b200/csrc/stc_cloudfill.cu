@@ -16,6 +16,8 @@
 // NumPy's float32 lerp).  The regression is float64 with a different summation order than
 // LAPACK/BLAS: filled pixels agree to ~1e-6 relative (tests/test_cloud_fill.py: rtol 1e-4).
 #include "stc_common.cuh"
+#include <chrono>
+#include <cstdio>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -77,12 +79,16 @@ __global__ void __launch_bounds__(128) k_mosaic_prep(const float* __restrict__ t
   divisor[p] = d;
 }
 
-// reference image of date i: mean of the other dates over pixels usable for both (:598-616)
+// reference image of date i = i0 + blockIdx.y: mean of the other dates over pixels usable for both (:598-616);
+// ref / flag are per-date slabs ([n][HW][10], [n][HW]) so that all dates run in one launch
 __global__ void __launch_bounds__(128) k_mosaic_ref(const float* __restrict__ tiles, const float* __restrict__ areas,
-                                                    const unsigned char* __restrict__ water, int n, int HW, int i,
-                                                    float* __restrict__ ref /*[HW][10]*/, unsigned char* __restrict__ flag) {
+                                                    const unsigned char* __restrict__ water, int n, int HW, int i0,
+                                                    float* __restrict__ ref_all, unsigned char* __restrict__ flag_all) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
+  const int i = i0 + blockIdx.y;
+  float* ref = ref_all + (int64_t)i * HW * 10;
+  unsigned char* flag = flag_all + (int64_t)i * HW;
   bool ok = (areas[(int64_t)i * HW + p] < 0.25f) && !water[p];
   float s[10]; float cnt = 0.f;
 #pragma unroll
@@ -106,9 +112,11 @@ __global__ void __launch_bounds__(128) k_mosaic_ref(const float* __restrict__ ti
 
 // order-preserving compaction positions of a flag image: pos[p] = rank of p among flagged pixels; total -> *count
 // (single block; HW <= a few 100k)
-__global__ void __launch_bounds__(1024) k_scan_flags(const unsigned char* __restrict__ flag, int HW, int* __restrict__ pos,
+__global__ void __launch_bounds__(1024) k_scan_flags(const unsigned char* __restrict__ flag_all, int HW, int* __restrict__ pos_all,
                                                      int* __restrict__ count) {
   __shared__ int wtot[32]; __shared__ int base;
+  const unsigned char* flag = flag_all + (int64_t)blockIdx.x * HW;       // one block per flag image
+  int* pos = pos_all + (int64_t)blockIdx.x * HW;
   if (threadIdx.x == 0) base = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -125,20 +133,23 @@ __global__ void __launch_bounds__(1024) k_scan_flags(const unsigned char* __rest
     if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 32; ++w) s += wtot[w]; base += s; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *count = base;
+  if (threadIdx.x == 0) count[blockIdx.x] = base;
 }
 
-// gather the flagged rows of date i and of the reference image: rows[0] = src [K][10], rows[1] = ref [K][10]
-__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ tiles_i, const float* __restrict__ ref,
-                                                     const int* __restrict__ pos, int HW, float* __restrict__ src_rows,
-                                                     float* __restrict__ ref_rows) {
+// gather the flagged rows of date i = i0 + blockIdx.y and of its reference image into per-date slabs:
+// src_rows[i] = [K_i][10], ref_rows[i] = [K_i][10]
+__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ tiles, const float* __restrict__ ref_all,
+                                                     const int* __restrict__ pos_all, int HW, int i0, float* __restrict__ src_rows_all,
+                                                     float* __restrict__ ref_rows_all) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)HW * 10) return;
+  const int i = i0 + blockIdx.y;
+  const int64_t slab = (int64_t)i * HW * 10;
   int p = (int)(idx / 10), c = (int)(idx % 10);
-  int r = pos[p];
+  int r = pos_all[(int64_t)i * HW + p];
   if (r < 0) return;
-  src_rows[(int64_t)r * 10 + c] = tiles_i[idx];
-  ref_rows[(int64_t)r * 10 + c] = ref[idx];
+  src_rows_all[slab + (int64_t)r * 10 + c] = tiles[slab + idx];
+  ref_rows_all[slab + (int64_t)r * 10 + c] = ref_all[slab + idx];
 }
 
 // exact k-th order statistics of a strided float32 column by MSB-first radix select; one block per (matrix, column)
@@ -211,11 +222,17 @@ __global__ void __launch_bounds__(1024) k_quantile(const SelectJob* __restrict__
 // SEQUENTIAL float32 sum (a dependent chain of K adds, 4 clk each at best).  One warp per column: the 32 lanes
 // prefetch a tile of 512 rows into shared memory (double-buffered through registers), then every lane replays
 // the same chain from broadcast shared-memory reads, so the loads are off the dependency chain.
-// grid = 2 matrices, block = 10 warps.
+// grid = (2 matrices, dates), block = 10 warps: the chains of all dates run side by side (one launch per date kept
+// 2 of 148 SMs busy for 3.5 ms, 43 % of the preprocessing chain).
 #define CS_TILE 512
-__global__ void __launch_bounds__(320) k_col_std(const float* __restrict__ m0, const float* __restrict__ m1, int K, float* __restrict__ out) {
+__global__ void __launch_bounds__(320) k_col_std(const float* __restrict__ m0_all, const float* __restrict__ m1_all, int64_t slab,
+                                                 const int* __restrict__ Ks, int i0, float* __restrict__ out_all) {
   __shared__ float tile[10][CS_TILE];
-  const float* m = blockIdx.x ? m1 : m0;
+  const int date = i0 + blockIdx.y;
+  const int K = Ks[date];
+  if (K <= 1000) return;                                   // date not aligned (:617)
+  const float* m = (blockIdx.x ? m1_all : m0_all) + (int64_t)date * slab;
+  float* out = out_all + (int64_t)date * 20;
   const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* tl = tile[c];
   float avg = 0.f;
@@ -249,9 +266,10 @@ __global__ void __launch_bounds__(320) k_col_std(const float* __restrict__ m0, c
 }
 
 // params[c] = std_ref/std_src, params[10+c] = med_ref - med_src*mult   (stats: med[0..9]=src, [10..19]=ref; std same)
-__global__ void k_scale_params(const float* __restrict__ med, const float* __restrict__ sd, float* __restrict__ params) {
+__global__ void k_scale_params(const float* __restrict__ med_all, const float* __restrict__ sd_all, float* __restrict__ params_all) {
   int c = threadIdx.x;
   if (c >= 10) return;
+  const float* med = med_all + blockIdx.x * 20; const float* sd = sd_all + blockIdx.x * 20; float* params = params_all + blockIdx.x * 20;
   float mult = __fdiv_rn(sd[10 + c], sd[c]);
   params[c] = mult;
   params[10 + c] = __fsub_rn(med[10 + c], __fmul_rn(med[c], mult));
@@ -352,30 +370,24 @@ __device__ __forceinline__ float evi_of(const float* x) {
 }
 // rows of date t usable for the fit (a_t == 0 and not water), appended at row_base in pixel order:
 // rowsrc[r] = t*HW + p, evi[r] = EVI(tiles[t][p])
-__global__ void __launch_bounds__(1024) k_collect_rows(const float* __restrict__ tiles, const float* __restrict__ areas,
-                                                       const unsigned char* __restrict__ water, int HW, int t, int row_base,
-                                                       int* __restrict__ rowsrc, float* __restrict__ evi) {
-  __shared__ int wtot[32]; __shared__ int base;
-  if (threadIdx.x == 0) base = row_base;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int p0 = 0; p0 < HW; p0 += 1024) {
-    const int p = p0 + threadIdx.x;
-    const bool f = p < HW && areas[(int64_t)t * HW + p] == 0.f && !water[p];
-    unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) wtot[wid] = __popc(bal);
-    __syncthreads();
-    int woff = 0;
-    for (int w = 0; w < wid; ++w) woff += wtot[w];
-    if (f) {
-      int r = base + woff + __popc(bal & ((1u << lane) - 1u));
-      rowsrc[r] = t * HW + p;
-      evi[r] = evi_of(tiles + ((int64_t)t * HW + p) * 10);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 32; ++w) s += wtot[w]; base += s; }
-    __syncthreads();
-  }
+// Clear-land pixels of date t in pixel order (:421-433).  The selection (weights == 0, not water) does not change while
+// the dates are blended, so the order-preserving positions of ALL dates are computed once (k_flag_clear_land +
+// k_scan_flags, one block per date) and the per-date step is a fully parallel gather of the row sources and of the EVI
+// of the (already partly blended) tiles.
+__global__ void __launch_bounds__(256) k_flag_clear_land(const float* __restrict__ areas, const unsigned char* __restrict__ water, int HW,
+                                                         unsigned char* __restrict__ flag_all) {
+  const int t = blockIdx.y; const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  flag_all[(int64_t)t * HW + p] = areas[(int64_t)t * HW + p] == 0.f && !water[p];
+}
+__global__ void __launch_bounds__(256) k_collect_rows(const float* __restrict__ tiles, const int* __restrict__ pos_t, int HW, int t, int row_base,
+                                                      int* __restrict__ rowsrc, float* __restrict__ evi) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const int r = pos_t[p];
+  if (r < 0) return;
+  rowsrc[row_base + r] = t * HW + p;
+  evi[row_base + r] = evi_of(tiles + ((int64_t)t * HW + p) * 10);
 }
 
 // stratum bits of every row against the six EVI percentiles b = {2,20,40,60,80,98} (:455-467)
@@ -590,27 +602,47 @@ __global__ void __launch_bounds__(256) k_add_clip(float* __restrict__ areas, con
 // shuffle -> _randbelow_with_getrandbits -> getrandbits(k) = genrand_uint32() >> (32 - k))
 // ---------------------------------------------------------------------------------------------
 struct PyRandom {
+  // CPython's MT19937 (Modules/_randommodule.c): `mt` is the untempered state Python exports with getstate(), `idx` its
+  // position.  The replay of random.shuffle over ~1e6-element index lists per date is the one long host loop of
+  // remove_clouds, so a whole block of 624 outputs is regenerated and tempered at once (three modulo-free loops the
+  // compiler vectorises) and next() only reads the buffer.
   uint32_t mt[624]; int idx;
-  uint32_t next() {
-    if (idx >= 624) {
-      for (int k = 0; k < 624; ++k) {
-        uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
-        mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      }
-      idx = 0;
-    }
-    uint32_t y = mt[idx++];
-    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
-    return y;
+  uint32_t out[624]; bool out_valid = false;
+  static inline uint32_t twist(uint32_t u, uint32_t v, uint32_t m) {
+    const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
+    return m ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
   }
-  uint32_t randbelow(uint32_t n) {
-    int k = 32 - __builtin_clz(n);       // n.bit_length(), n >= 1
+  void temper_all() {
+    for (int k = 0; k < 624; ++k) {
+      uint32_t y = mt[k];
+      y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+      out[k] = y;
+    }
+    out_valid = true;
+  }
+  void regen() {
+    for (int k = 0; k < 227; ++k) mt[k] = twist(mt[k], mt[k + 1], mt[k + 397]);
+    for (int k = 227; k < 623; ++k) mt[k] = twist(mt[k], mt[k + 1], mt[k - 227]);
+    mt[623] = twist(mt[623], mt[0], mt[396]);
+    temper_all();
+    idx = 0;
+  }
+  inline uint32_t next() {
+    if (idx >= 624) regen();
+    else if (!out_valid) temper_all();
+    return out[idx++];
+  }
+  inline uint32_t randbelow(uint32_t n) {
+    const int sh = __builtin_clz(n);     // 32 - n.bit_length(), n >= 1
+    // (~10 ns per shuffled element on the host; a variant that examines two candidates with conditional moves instead of
+    //  the unpredictable accept branch measured the same, so the plain _randbelow_with_getrandbits loop stays)
     uint32_t r;
-    do { r = next() >> (32 - k); } while (r >= n);
+    do { r = next() >> sh; } while (r >= n);
     return r;
   }
   void shuffle(std::vector<int>& x) {
-    for (size_t i = x.size(); i-- > 1;) { uint32_t j = randbelow((uint32_t)i + 1); std::swap(x[i], x[j]); }
+    int* v = x.data();
+    for (size_t i = x.size(); i-- > 1;) { const uint32_t j = randbelow((uint32_t)i + 1); const int t = v[i]; v[i] = v[j]; v[j] = t; }
   }
 };
 
@@ -634,6 +666,17 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
       W < 3 || mt_state[624] > 624)
     STC_FAIL(STC_ERR_ARG, "remove_clouds: bad argument (1 <= n <= 32, MT19937 state of 624 words + position)");
   const int HW = H * W; const int64_t N = (int64_t)n * HW;
+  // STC_CF_TIMING=1: wall time of each phase on stderr (the marks synchronise the stream)
+  static const bool cf_timing = getenv("STC_CF_TIMING") != nullptr;
+  auto cf_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double cf_t = cf_now();
+  auto cf_mark = [&](const char* what) {
+    if (!cf_timing) return;
+    cudaStreamSynchronize(ctx->stream);
+    const double t = cf_now();
+    fprintf(stderr, "[remove_clouds] %-34s %8.1f ms\n", what, t - cf_t);
+    cf_t = t;
+  };
   DBuf d_tiles, d_areas, d_probs, d_ta, d_tb, d_sums, d_water0, d_water1, d_flag, d_u8a, d_u8b, d_pf, d_ref, d_pos, d_src_rows,
       d_ref_rows, d_mosaic, d_div, d_snow, d_rowsrc, d_evi, d_lab, d_sample, d_partial, d_gram, d_coef, d_status, d_jobs, d_q, d_qout,
       d_sd, d_params, d_cnt, d_counts, d_pfall;
@@ -669,9 +712,11 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
   };
   int rc;
 
+  cf_mark("alloc + upload");
   // ---- 1. feather the masks (:908-921, closing size 20) ----
   if ((rc = pre_feather_dev(ctx, d_probs.as<float>(), n, H, W, 20, d_ta.as<float>(), d_tb.as<float>(), d_sums.as<float>(), areas))) return rc;
 
+  cf_mark("feather");
   // ---- 2. cloud-free mosaic (:578-699) ----
   CF_LAUNCH(k_mosaic_prep, cdiv(HW, 128), 128, tiles, areas, n, HW, u8a, d_div.as<float>());
   maskop_dilate(ctx, u8a, u8b, 1, H, W, 2, 1, 1, 0, 0);          // dilate(1 - water, 2)
@@ -679,41 +724,71 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
   STC_CUDA(cudaMemsetAsync(mosaic, 0, (int64_t)HW * 40, ctx->stream));
   STC_CUDA(cudaMemsetAsync(cnt, 0, 64, ctx->stream));
   CF_LAUNCH(k_count_zero, cdiv(HW, 256), 256, water0, HW, cnt + 1);
+  // All dates at once: reference images, compaction positions, row gathers, 20 medians + 20 standard deviations and the
+  // scale parameters of every date run in ONE launch each (per-date slabs), because a single date offers two blocks of
+  // work to 148 SMs (the column chains of np.nanstd are sequential by definition).  Only the accumulation into the mosaic
+  // stays in date order (float32 sum order).  A date that cannot be aligned (<= 1000 usable pixels) sets its weights to 1
+  // (:679-680), which changes the reference images of the LATER dates: the batch is then cut at that date and restarted
+  // behind it, exactly reproducing the sequential loop.
+  DBuf d_refall, d_flagall, d_posall, d_srcall, d_refrowsall, d_Ks, d_medall, d_sdall, d_paramsall, d_jobsall;
+  const int64_t slab = (int64_t)HW * 10;
+  STC_CUDA(cudaMalloc(&d_refall.p, (size_t)n * slab * 4)); STC_CUDA(cudaMalloc(&d_srcall.p, (size_t)n * slab * 4));
+  STC_CUDA(cudaMalloc(&d_refrowsall.p, (size_t)n * slab * 4));
+  STC_CUDA(cudaMalloc(&d_flagall.p, (size_t)n * HW)); STC_CUDA(cudaMalloc(&d_posall.p, (size_t)n * HW * 4));
+  STC_CUDA(cudaMalloc(&d_Ks.p, CF_MAX_DATES * 4)); STC_CUDA(cudaMalloc(&d_medall.p, CF_MAX_DATES * 20 * 4));
+  STC_CUDA(cudaMalloc(&d_sdall.p, CF_MAX_DATES * 20 * 4)); STC_CUDA(cudaMalloc(&d_paramsall.p, CF_MAX_DATES * 20 * 4));
+  STC_CUDA(cudaMalloc(&d_jobsall.p, CF_MAX_DATES * 20 * sizeof(SelectJob)));
   int land_px = 0;
-  for (int i = 0; i < n; ++i) {
-    CF_LAUNCH(k_mosaic_ref, cdiv(HW, 128), 128, tiles, areas, water0, n, HW, i, d_ref.as<float>(), flag);
-    CF_LAUNCH(k_scan_flags, 1, 1024, flag, HW, d_pos.as<int>(), cnt);
-    int hc[2];
-    STC_CUDA(cudaMemcpyAsync(hc, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(&land_px, cnt + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<int> Ks(n, 0);
+  int start = 0;
+  while (start < n) {
+    const int m = n - start;
+    CF_LAUNCH(k_mosaic_ref, dim3(cdiv(HW, 128), m), 128, tiles, areas, water0, n, HW, start, d_refall.as<float>(), d_flagall.as<unsigned char>());
+    CF_LAUNCH(k_scan_flags, m, 1024, d_flagall.as<unsigned char>() + (int64_t)start * HW, HW, d_posall.as<int>() + (int64_t)start * HW,
+              d_Ks.as<int>() + start);
+    STC_CUDA(cudaMemcpyAsync(Ks.data() + start, d_Ks.as<int>() + start, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CF_SYNC();
-    const int K = hc[0]; land_px = hc[1];
-    if (K > 1000) {
-      CF_LAUNCH(k_gather_rows, cdiv((int64_t)HW * 10, 256), 256, tiles + (int64_t)i * HW * 10, d_ref.as<float>(), d_pos.as<int>(), HW,
-                d_src_rows.as<float>(), d_ref_rows.as<float>());
+    int f = start;
+    while (f < n && Ks[f] > 1000) ++f;                       // dates [start, f) are final
+    if (f > start) {
+      const int cv = f - start;
+      CF_LAUNCH(k_gather_rows, dim3(cdiv(slab, 256), cv), 256, tiles, d_refall.as<float>(), d_posall.as<int>(), HW, start,
+                d_srcall.as<float>(), d_refrowsall.as<float>());
       std::vector<SelectJob> jobs;
-      for (int m = 0; m < 2; ++m)
-        for (int c = 0; c < 10; ++c) jobs.push_back({(m ? d_ref_rows.as<float>() : d_src_rows.as<float>()) + c, 10, K, 0});
-      if ((rc = run_quantiles(jobs, {}, 1, d_qout.as<float>()))) return rc;
-      CF_LAUNCH(k_col_std, 2, 320, d_src_rows.as<float>(), d_ref_rows.as<float>(), K, d_sd.as<float>());
-      CF_LAUNCH(k_scale_params, 1, 32, d_qout.as<float>(), d_sd.as<float>(), d_params.as<float>());
-      CF_LAUNCH(k_mosaic_accum, cdiv((int64_t)HW * 10, 256), 256, tiles + (int64_t)i * HW * 10, areas + (int64_t)i * HW, water0,
-                d_params.as<float>(), HW, mosaic);
-    } else if (land_px > 0) {
-      CF_LAUNCH(k_fill_f, cdiv(HW, 256), 256, areas + (int64_t)i * HW, (int64_t)HW, 1.f);      // interp[i] = 1. (:679-680)
+      for (int i = start; i < f; ++i)
+        for (int mm = 0; mm < 2; ++mm)
+          for (int c = 0; c < 10; ++c)
+            jobs.push_back({(mm ? d_refrowsall.as<float>() : d_srcall.as<float>()) + (int64_t)i * slab + c, 10, Ks[i], 0});
+      STC_CUDA(cudaMemcpyAsync(d_jobsall.p, jobs.data(), jobs.size() * sizeof(SelectJob), cudaMemcpyHostToDevice, ctx->stream));
+      CF_LAUNCH(k_quantile, (int)jobs.size(), 1024, d_jobsall.as<SelectJob>(), (const double*)nullptr, 1, d_medall.as<float>() + start * 20);
+      CF_LAUNCH(k_col_std, dim3(2, cv), 320, d_srcall.as<float>(), d_refrowsall.as<float>(), slab, d_Ks.as<int>(), start, d_sdall.as<float>());
+      CF_LAUNCH(k_scale_params, cv, 32, d_medall.as<float>() + start * 20, d_sdall.as<float>() + start * 20, d_paramsall.as<float>() + start * 20);
+      for (int i = start; i < f; ++i)
+        CF_LAUNCH(k_mosaic_accum, cdiv(slab, 256), 256, tiles + (int64_t)i * slab, areas + (int64_t)i * HW, water0,
+                  d_paramsall.as<float>() + i * 20, HW, mosaic);
+      CF_SYNC();                                             // `jobs` is a host vector
     }
+    if (f < n && land_px > 0)
+      CF_LAUNCH(k_fill_f, cdiv(HW, 256), 256, areas + (int64_t)f * HW, (int64_t)HW, 1.f);      // interp[i] = 1. (:679-680)
+    start = f + 1;
   }
   CF_LAUNCH(k_mosaic_final, cdiv((int64_t)HW * 10, 128), 128, tiles, d_div.as<float>(), n, HW, mosaic);
   if (mosaic_host) STC_CUDA(cudaMemcpyAsync(mosaic_host, mosaic, (int64_t)HW * 40, cudaMemcpyDeviceToHost, ctx->stream));
 
+  cf_mark("mosaic");
   // ---- 3. per-date alignment and blending (:939-959, :316-575) ----
   CF_LAUNCH(k_water_of_median, cdiv(HW, 128), 128, tiles, n, HW, water1);
   STC_CUDA(cudaMemsetAsync(d_counts.p, 0, CF_MAX_DATES * 5 * 4, ctx->stream));
   CF_LAUNCH(k_area_counts, dim3(cdiv(HW, 256), n), 256, areas, water1, HW, d_counts.as<int>());
+  CF_LAUNCH(k_flag_clear_land, dim3(cdiv(HW, 256), n), 256, areas, water1, HW, d_flagall.as<unsigned char>());
+  CF_LAUNCH(k_scan_flags, n, 1024, d_flagall.as<unsigned char>(), HW, d_posall.as<int>(), d_Ks.as<int>());
   std::vector<int> counts(n * 5);
   STC_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, n * 20, cudaMemcpyDeviceToHost, ctx->stream));
   CF_SYNC();
   PyRandom rng; memcpy(rng.mt, mt_state, 624 * 4); rng.idx = (int)mt_state[624];
   std::vector<unsigned char> lab;
+  double t_gpu1 = 0, t_bucket = 0, t_shuffle = 0, t_gpu2 = 0; long long n_draw = 0;
   for (int d = 0; d < n; ++d) {
     const int c_pos = counts[d * 5], c_zero = counts[d * 5 + 1], c_lt1 = counts[d * 5 + 2], c_one = counts[d * 5 + 3];
     to_remove_host[d] = (c_one == HW);
@@ -728,10 +803,11 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
     int lo, hi;
     if (c_zero > 40000) { lo = d; hi = d + 1; }
     else { lo = (d == n - 1) ? std::max(d - 2, 0) : std::max(d - 1, 0); hi = std::min(d + 2, n); }
+    double tt0 = cf_timing ? cf_now() : 0;
     CF_LAUNCH(k_snow_mean, cdiv(HW, 256), 256, tiles, n, HW, d_snow.as<float>());
     int K = 0;
     for (int t = lo; t < hi; ++t) {
-      CF_LAUNCH(k_collect_rows, 1, 1024, tiles, areas, water1, HW, t, K, d_rowsrc.as<int>(), d_evi.as<float>());
+      CF_LAUNCH(k_collect_rows, cdiv(HW, 256), 256, tiles, d_posall.as<int>() + (int64_t)t * HW, HW, t, K, d_rowsrc.as<int>(), d_evi.as<float>());
       K += counts[t * 5 + 4];
     }
     if (K < 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: no clear land pixel to fit on -- the reference fails in np.percentile here");
@@ -744,8 +820,15 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
     lab.resize(K);
     STC_CUDA(cudaMemcpyAsync(lab.data(), d_lab.p, K, cudaMemcpyDeviceToHost, ctx->stream));
     CF_SYNC();
+    double tt1 = cf_timing ? cf_now() : 0; t_gpu1 += tt1 - tt0;
     // sampling bookkeeping (:447-497): index lists per stratum, Python random.shuffle, concatenate, shuffle, truncate
     std::vector<int> p2, p20, p40, p60, p80, p100, p98;
+    {
+      size_t cntb[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (int r = 0; r < K; ++r) { const unsigned char m = lab[r]; for (int k = 0; k < 7; ++k) cntb[k] += (m >> k) & 1u; }
+      p2.reserve(cntb[0] * 10); p20.reserve(cntb[1]); p40.reserve(cntb[2]); p60.reserve(cntb[3]); p80.reserve(cntb[4]);
+      p100.reserve(cntb[5]); p98.reserve(cntb[6] * 10);
+    }
     for (int r = 0; r < K; ++r) {
       unsigned char m = lab[r];
       if (m & 1) p2.push_back(r);
@@ -761,6 +844,8 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
         STC_FAIL(STC_ERR_STATE, "remove_clouds: single-element EVI stratum -- the reference raises TypeError (shuffle of a 0-d array)");
     auto repeat10 = [](std::vector<int>& v) { std::vector<int> o; o.reserve(v.size() * 10); for (int x : v) for (int k = 0; k < 10; ++k) o.push_back(x); v.swap(o); };
     repeat10(p98); repeat10(p2);
+    double tt2 = cf_timing ? cf_now() : 0; t_bucket += tt2 - tt1;
+    n_draw += (long long)(p2.size() + p98.size() + p20.size() + p40.size() + p60.size() + p80.size() + p100.size());
     rng.shuffle(p2); rng.shuffle(p98); rng.shuffle(p20); rng.shuffle(p40); rng.shuffle(p60); rng.shuffle(p80); rng.shuffle(p100);
     const size_t n_i = (size_t)(std::min(90000, K) / 5);
     std::vector<int> sample;
@@ -769,6 +854,7 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
     rng.shuffle(sample);
     if ((int)sample.size() > K) sample.resize(K);
     const int S = (int)sample.size();
+    double tt3 = cf_timing ? cf_now() : 0; t_shuffle += tt3 - tt2;
     STC_CUDA(cudaMemcpyAsync(d_sample.p, sample.data(), (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
     const int gb = std::min(gram_blocks, cdiv(S, GRAM_ROWS));
     CF_LAUNCH(k_gram, gb, 640, tiles, mosaic, d_snow.as<float>(), d_rowsrc.as<int>(), d_sample.as<int>(), S, HW, d_partial.as<double>());
@@ -781,9 +867,12 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
       if (status[b] != 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: NNLS did not converge (scipy.optimize.nnls raises RuntimeError)");
     CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, d_snow.as<float>(),
               d_coef.as<double>(), 1, HW);
+    if (cf_timing) t_gpu2 += cf_now() - tt3;
   }
+  if (cf_timing) fprintf(stderr, "[remove_clouds]   per-date: gpu(collect..strata) %.1f, buckets %.1f, shuffles %.1f (%lld elements), gpu(gram..nnls) %.1f ms\n", t_gpu1, t_bucket, t_shuffle, n_draw, t_gpu2);
   memcpy(mt_state, rng.mt, 624 * 4); mt_state[624] = (uint32_t)rng.idx;
 
+  cf_mark("per-date alignment + blend");
   // ---- 4. residual clouds in the mosaic (:703-732) ----
   maskop_dilate(ctx, d_pfall.as<unsigned char>(), pf, 1, H, W, 10, 1, 0, 0, 0);      // pfcps[0] (single frame when n == 1)
   STC_CUDA(cudaMemsetAsync(cnt, 0, 8, ctx->stream));
@@ -805,8 +894,10 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
     CF_LAUNCH(k_add_clip, cdiv(N, 256), 256, areas, u8b, n, HW);
   }
   STC_CUDA(cudaGetLastError());
+  cf_mark("residual clouds");
   STC_CUDA(cudaMemcpyAsync(tiles_host, tiles, N * 40, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(areas_host, areas, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CF_SYNC();
+  cf_mark("download");
   return STC_OK;
 }
