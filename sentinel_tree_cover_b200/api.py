@@ -376,12 +376,17 @@ class StcSession:
         self._check(self.lib.stc_temporal_median_host(self.h, _dptr(a), a.shape[0], inner, _dptr(out)))
         return out
 
-    def superresolve(self, x10, bilinear6):
+    def superresolve(self, x10, bilinear6=None):
+        """pb:superresolve graph on [N,H,W,10] float32 (+ the bilinear input [N,H,W,6]; None = x10[..., 4:], which is
+        what superresolve_large_tile feeds) -> the six resolved bands [N,H,W,6]."""
         x = np.ascontiguousarray(x10, np.float32)
-        b = np.ascontiguousarray(bilinear6, np.float32)
         N, H, W, _ = x.shape
         out = np.empty((N, H, W, 6), np.float32)
-        self._check(self.lib.stc_superresolve_host(self.h, _dptr(x), _dptr(b), N, H, W, _dptr(out)))
+        if bilinear6 is None:
+            self._check(self.lib.stc_superresolve_host(self.h, _dptr(x), None, N, H, W, _dptr(out)))
+        else:
+            b = np.ascontiguousarray(bilinear6, np.float32)
+            self._check(self.lib.stc_superresolve_host(self.h, _dptr(x), _dptr(b), N, H, W, _dptr(out)))
         return out
 
 
@@ -705,20 +710,32 @@ def superresolve_large_tile(arr, sess, wsize=110):
     the edge.  Quirks kept on purpose: the bottom row of windows reads a PRE-resolution
     copy of the bottom band (and that copy is updated in place window by window); the
     right-most column is only processed in the bottom row (:133-143 never reach the other
-    right-edge windows).  Writes bands 4: of `arr` in place and returns it."""
+    right-edge windows).  Writes bands 4: of `arr` in place and returns it.
+    Windows that cannot see each other's output go through the network in ONE batched call: the interior
+    windows tile the array without overlap and read `arr` before anything is written; the bottom row
+    reads the copy, where only the last (edge-anchored) window overlaps its left neighbour and therefore
+    runs second.  Results are written back in the reference's order (later windows overwrite earlier ones)."""
     from .windows import superres_windows
     xs, ys = superres_windows(arr.shape[1], wsize), superres_windows(arr.shape[2], wsize)
     bottom_band = np.copy(arr[:, xs[-1]:, ...])
-    for x in xs:
-        for y in ys:
-            bottom, right = (x == xs[-1]), (y == ys[-1])
-            if right and not bottom:
-                continue
-            src = bottom_band[:, :, y:y + wsize, ...] if bottom else arr[:, x:x + wsize, y:y + wsize, ...]
-            padded = np.pad(src, ((0, 0), (4, 4), (4, 4), (0, 0)), 'reflect')
-            resolved = sess.superresolve(padded, padded[..., 4:])
-            src[..., 4:] = resolved[:, 4:-4, 4:-4, :]
-            arr[:, x:x + wsize, y:y + wsize, ...] = src
+    order = [(x, y) for x in xs for y in ys if not (y == ys[-1] and x != xs[-1])]
+    n = arr.shape[0]
+
+    def run(wins):
+        srcs = [bottom_band[:, :, y:y + wsize, ...] if x == xs[-1] else arr[:, x:x + wsize, y:y + wsize, ...] for x, y in wins]
+        padded = np.concatenate([np.pad(s, ((0, 0), (4, 4), (4, 4), (0, 0)), 'reflect') for s in srcs])
+        resolved = sess.superresolve(padded)
+        for k, s in enumerate(srcs):
+            s[..., 4:] = resolved[k * n:(k + 1) * n, 4:-4, 4:-4, :]
+        return srcs
+
+    last_overlaps = len(ys) > 1 and ys[-1] < ys[-2] + wsize           # the edge-anchored bottom window reads its neighbour's output
+    first = [w for w in order if not (last_overlaps and w == (xs[-1], ys[-1]))]
+    done = dict(zip(first, run(first)))
+    if last_overlaps:
+        done[(xs[-1], ys[-1])] = run([(xs[-1], ys[-1])])[0]
+    for x, y in order:                                               # the reference's write order
+        arr[:, x:x + wsize, y:y + wsize, ...] = done[(x, y)]
     return arr
 
 

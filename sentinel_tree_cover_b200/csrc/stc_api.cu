@@ -360,12 +360,15 @@ int stc_temporal_median_host(stc_ctx* ctx, const float* in_host, int n, int64_t 
 
 int stc_superresolve_host(stc_ctx* ctx, const float* x_host, const float* bilinear_host, int N, int H, int W, float* out_host) {
   CTX_CHECK();
-  if (!x_host || !bilinear_host || !out_host) STC_FAIL(STC_ERR_ARG, "superresolve: bad argument");
+  if (!x_host || !out_host) STC_FAIL(STC_ERR_ARG, "superresolve: bad argument");
   size_t npx = (size_t)N * H * W;
   DevBuf dx, db, dout;
-  STC_CUDA(cudaMalloc(&dx.p, npx * 40)); STC_CUDA(cudaMalloc(&db.p, npx * 24)); STC_CUDA(cudaMalloc(&dout.p, npx * 24));
+  STC_CUDA(cudaMalloc(&dx.p, npx * 40)); STC_CUDA(cudaMalloc(&dout.p, npx * 24));
   STC_CUDA(cudaMemcpyAsync(dx.p, x_host, npx * 40, cudaMemcpyHostToDevice, ctx->stream));
-  STC_CUDA(cudaMemcpyAsync(db.p, bilinear_host, npx * 24, cudaMemcpyHostToDevice, ctx->stream));
+  if (bilinear_host) {          // NULL: the bilinear input is x[..., 4:] (superresolve_large_tile), no second upload
+    STC_CUDA(cudaMalloc(&db.p, npx * 24));
+    STC_CUDA(cudaMemcpyAsync(db.p, bilinear_host, npx * 24, cudaMemcpyHostToDevice, ctx->stream));
+  }
   int rc = sr_forward_dev(ctx, (const float*)dx.p, (const float*)db.p, N, H, W, (float*)dout.p);
   if (rc) return rc;
   STC_CUDA(cudaMemcpyAsync(out_host, dout.p, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));

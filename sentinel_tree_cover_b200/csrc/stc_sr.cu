@@ -62,7 +62,7 @@ struct SrApply {
   const float4* raw; int64_t raw_plane;
   float4* skip; int64_t skip_plane; int write_skip;
   uint4* dst; int64_t dst_plane;
-  const float* bil; float* out;
+  const float* bil; int bil_stride, bil_off; float* out;   // bilinear input: [.., bil_stride] floats per pixel, band k at bil_off + k
   int N, H, W; int mode;
 };
 
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) sr_apply_kernel(SrApply p) {
     float4 a = p.raw[P], c = p.raw[p.raw_plane + P];
     float t[6] = {a.x, a.y, a.z, a.w, c.x, c.y};
 #pragma unroll
-    for (int k = 0; k < 6; ++k) p.out[idx * 6 + k] = tanhf(t[k]) + p.bil[idx * 6 + k];
+    for (int k = 0; k < 6; ++k) p.out[idx * 6 + k] = tanhf(t[k]) + p.bil[idx * p.bil_stride + p.bil_off + k];
     return;
   }
   uint4 o[4];
@@ -168,12 +168,13 @@ static int sr_conv(stc_ctx* ctx, SrState* s, int layer, const Act& in, int mode)
   return launch_conv(ctx, cp, 1);
 }
 
-static int sr_apply(stc_ctx* ctx, SrState* s, int mode, int write_skip, Act* dst, const float* bil, float* out) {
+static int sr_apply(stc_ctx* ctx, SrState* s, int mode, int write_skip, Act* dst, const float* bil, float* out,
+                    int bil_stride = 6, int bil_off = 0) {
   SrApply ap; memset(&ap, 0, sizeof(ap));
   ap.raw = s->raw.base; ap.raw_plane = s->raw.plane; ap.skip = s->skip.base; ap.skip_plane = s->skip.plane;
   ap.write_skip = write_skip;
   if (dst) { ap.dst = dst->at(0); ap.dst_plane = dst->plane; }
-  ap.bil = bil; ap.out = out; ap.N = s->N; ap.H = s->H; ap.W = s->W; ap.mode = mode;
+  ap.bil = bil; ap.bil_stride = bil_stride; ap.bil_off = bil_off; ap.out = out; ap.N = s->N; ap.H = s->H; ap.W = s->W; ap.mode = mode;
   sr_apply_kernel<<<cdiv((int64_t)s->N * s->H * s->W, 256), 256, 0, ctx->stream>>>(ap);
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -198,6 +199,9 @@ int sr_forward_dev(stc_ctx* ctx, const float* x_dev, const float* bil_dev, int N
   if ((rc = sr_conv(ctx, s, 4, s->Bf, MODE_BIAS))) return rc;
   if ((rc = sr_apply(ctx, s, 1, 0, &s->A, nullptr, nullptr))) return rc;      // c = b + 0.1*d
   if ((rc = sr_conv(ctx, s, 5, s->A, MODE_BIAS))) return rc;
-  if ((rc = sr_apply(ctx, s, 2, 0, nullptr, bil_dev, out_dev))) return rc;
+  // bil_dev == nullptr: the bilinear input is bands 4..9 of x itself (what superresolve_large_tile feeds, :104-105)
+  if (bil_dev) rc = sr_apply(ctx, s, 2, 0, nullptr, bil_dev, out_dev);
+  else rc = sr_apply(ctx, s, 2, 0, nullptr, x_dev, out_dev, 10, 4);
+  if (rc) return rc;
   return STC_OK;
 }
