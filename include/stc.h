@@ -329,6 +329,19 @@ int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const float* dem_h
  *      floats written (or needed if out_host == NULL). --------------------- */
 int64_t stc_debug_read(stc_ctx* ctx, const char* name, float* out_host);
 
+/* ---- region-scale pieces: a region is a grid of R x C overlapping patches
+ *      (P-px windows every `stride` px; the reference mosaics one 6 x 6 km tile at a time, :1515-1641, this is its
+ *      generalisation).  stc_region_gather_dev cuts B patch windows [B,T,P,P,Cc] out of a device-resident canvas
+ *      band [T,Hc,Wc,Cc] (wrap != 0: the canvas is periodic, used to synthesise a region from a small base cube); the
+ *      window origins ys/xs [B] are DEVICE arrays so that the call is asynchronous (the caller validates them);
+ *      stc_region_blend_dev blends patch outputs preds [rows_have,C,S,S] (first grid row r_first of R) into the
+ *      uint8 canvas rows [y0,y1): Gaussian weights gauss [S,S], sum(w * p*100) / sum(w) in row-major patch order,
+ *      uint8 truncation, <= 15 -> 0, uncovered -> 255.  Patch (r,c) covers canvas rows r*stride+margin .. +S. ---- */
+int stc_region_gather_dev(stc_ctx* ctx, const float* canvas_dev, int T, int Hc, int Wc, int Cc, int wrap,
+                          const int32_t* ys_dev, const int32_t* xs_dev, int B, int P, float* out_dev);
+int stc_region_blend_dev(stc_ctx* ctx, const float* preds_dev, int r_first, int rows_have, int R, int C, int S, int stride,
+                         int margin, const float* gauss_host, int y0, int y1, int Wc, uint8_t* out_host);
+
 #ifdef __cplusplus
 }
 #endif

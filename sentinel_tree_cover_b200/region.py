@@ -1,0 +1,108 @@
+"""Region-scale driver: a region is an R x C grid of overlapping patches (168 px
+windows every 58 px: 190 x 190 patches over an 11,130 px canvas for 1 x 1 degree).  Rows of the patch grid are
+block-partitioned over the ranks (shard.shard_range); every rank cuts its patches out of its device-resident canvas
+band, runs the batched forward, and blends the canvas rows it owns.  The only data-path exchange is the halo: a canvas
+row is covered by up to three patch rows, so a rank needs the LAST TWO patch rows of the previous rank (their
+probabilities, 2 x C x S x S floats) -- one all_gather of those blocks.  The blend adds the covering patches of a
+pixel in grid order, so the mosaic is bit-identical for any number of ranks.
+
+Host side only (integers, torch.distributed plumbing); arithmetic is in csrc/stc_region.cu and the model kernels."""
+import ctypes as _C
+
+import numpy as np
+
+from . import api as _api
+from .shard import shard_range
+
+
+def _dev(p, offset=0):
+    """Device pointer (int or ctypes.c_void_p) + byte offset -> ctypes.c_void_p."""
+    base = p.value if isinstance(p, _C.c_void_p) else int(p)
+    return _C.c_void_p(base + int(offset))
+
+
+def canvas_size(n, patch, stride):
+    return (n - 1) * stride + patch
+
+
+def owned_canvas_rows(ra, rb, R, patch, stride):
+    """Canvas rows blended by the rank that owns patch rows [ra, rb): one stride band per patch row, the last rank
+    takes the remainder."""
+    end = canvas_size(R, patch, stride)
+    if ra >= rb:                      # more ranks than patch rows: the trailing ranks own nothing
+        y = end if ra >= R else ra * stride
+        return y, y
+    return ra * stride, (rb * stride if rb < R else end)
+
+
+def halo_rows(ra, S, stride, margin):
+    """First patch row whose output can touch canvas row ra*stride (rows below come from the previous rank)."""
+    a = ra * stride - margin - S
+    first = (a // stride) + 1
+    return max(first, 0)
+
+
+class RegionRunner:
+    """One rank's share of a region.  `canvas_dev` is a device pointer to the rank's canvas band [T, Hband, Wc, Cc]
+    float32 whose first row is canvas row `band_y0` (wrap=True: a periodic base cube instead, origin (0, 0))."""
+
+    def __init__(self, sess, R, C, patch=168, stride=58, rank=0, world=1, batch=256, sigma=36):
+        self.sess, self.R, self.C, self.P, self.stride = sess, R, C, patch, stride
+        self.S, self.margin = patch - 14, 7
+        self.rank, self.world, self.batch, self.sigma = rank, world, batch, sigma
+        self.ra, self.rb = shard_range(R, rank, world)
+        self.Hc, self.Wc = canvas_size(R, patch, stride), canvas_size(C, patch, stride)
+
+    # ---- forward over the rank's patch rows -------------------------------------------------
+    def predict_rows(self, canvas_dev, T, Hband, Wband, Cc, wrap, band_y0, preds_dev):
+        """Fills preds_dev [(rb-ra), C, S, S] float32 (device pointer)."""
+        sess, P, S = self.sess, self.P, self.S
+        n = (self.rb - self.ra) * self.C
+        if n == 0:
+            return 0
+        patch_bytes = T * P * P * Cc * 4
+        idx = np.arange(n)
+        ys = ((self.ra + idx // self.C) * self.stride - band_y0).astype(np.int32)
+        xs = ((idx % self.C) * self.stride).astype(np.int32)
+        if not wrap and (ys.min() < 0 or xs.min() < 0 or ys.max() + P > Hband or xs.max() + P > Wband):
+            raise ValueError("region: a patch window leaves the canvas band")
+        # window origins of ALL batches go to the device once, so the per-batch calls are asynchronous and the host
+        # runs ahead of the GPU (a host hiccup between batches would otherwise idle the device)
+        coords = np.ascontiguousarray(np.concatenate([ys, xs]))
+        d_xy = sess.malloc(coords.nbytes)
+        buf = sess.malloc(min(self.batch, n) * patch_bytes)
+        try:
+            sess.h2d(d_xy, coords)
+            done = 0
+            while done < n:
+                b = min(self.batch, n - done)
+                sess._check(sess.lib.stc_region_gather_dev(sess.h, _dev(canvas_dev), T, Hband, Wband, Cc, int(bool(wrap)),
+                                                           _dev(d_xy, done * 4), _dev(d_xy, (n + done) * 4), b, P, buf))
+                sess.predict_patches_dev(buf, b, P, P, _dev(preds_dev, done * S * S * 4))
+                done += b
+            sess.sync()
+        finally:
+            sess.free(buf); sess.free(d_xy)
+        return n
+
+    # ---- blend of the owned canvas rows -------------------------------------------------------
+    def blend(self, preds_dev, r_first, rows_have):
+        y0, y1 = owned_canvas_rows(self.ra, self.rb, self.R, self.P, self.stride)
+        out = np.empty((y1 - y0, self.Wc), np.uint8)
+        if y1 <= y0:
+            return out, (y0, y1)
+        gauss = np.ascontiguousarray(_api.fspecial_gauss(self.S, self.sigma), np.float32)
+        self.sess._check(self.sess.lib.stc_region_blend_dev(self.sess.h, _dev(preds_dev), int(r_first), int(rows_have), self.R, self.C, self.S,
+                                                            self.stride, self.margin, _api._dptr(gauss), y0, y1, self.Wc, _api._dptr(out)))
+        return out, (y0, y1)
+
+
+def exchange_halo(own_tail, dist, rank, world):
+    """own_tail: torch tensor [2, C, S, S] (the rank's last two patch rows, zero-padded if it owns fewer).  Returns the
+    previous rank's tail (None on rank 0).  One all_gather; NCCL on GPUs, gloo in the CPU tests."""
+    import torch
+    if world == 1:
+        return None
+    got = [torch.empty_like(own_tail) for _ in range(world)]
+    dist.all_gather(got, own_tail)
+    return got[rank - 1] if rank > 0 else None
