@@ -373,23 +373,32 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS + j * N);
         float scale = 1.f;
         if (MODE == MODE_PSCALE_SWISH) scale = pscale(p, yp, xp);
+        uint32_t keep[(MODE == MODE_CAND) ? 16 : 1];     // MODE_CAND (N = 32): this warp's 16 columns, kept from the squeeze pass
         if (MODE == MODE_CAND) {           // 1x1 squeeze over all N channels of the pixel (pb:candidate/convolution_1)
+          static_assert(MODE != MODE_CAND || N == 32, "the candidate epilogue keeps one 16-column half per warp");
+          uint32_t ra[16], rb[16];
+          tmem_ld16_nowait(taddr, ra);
+          tmem_ld16_nowait(taddr + 16, rb);
+          tmem_wait_ld();
           float d = 0.f;
 #pragma unroll
-          for (int c0 = 0; c0 < N; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16_nowait(taddr + c0, r);
-            tmem_wait_ld();
+          for (int i = 0; i < 16; ++i) d = fmaf(__uint_as_float(ra[i]), __ldg(&p.sse_w[dir][i]), d);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) d = fmaf(__uint_as_float(r[i]), __ldg(&p.sse_w[dir][c0 + i]), d);
-          }
+          for (int i = 0; i < 16; ++i) d = fmaf(__uint_as_float(rb[i]), __ldg(&p.sse_w[dir][16 + i]), d);
           scale = fast_sigmoid(d);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) keep[i] = half ? rb[i] : ra[i];      // TMEM is read once (it is shared with the MMAs)
         }
 #pragma unroll
         for (int c0 = 0; c0 < NH; c0 += 16) {
           uint32_t r[16];
-          tmem_ld16_nowait(taddr + cbase + c0, r);
-          tmem_wait_ld();
+          if (MODE == MODE_CAND) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = keep[i];
+          } else {
+            tmem_ld16_nowait(taddr + cbase + c0, r);
+            tmem_wait_ld();
+          }
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -766,7 +775,6 @@ static int launch_simt(stc_ctx* ctx, const ConvParams& p, int ndir) {
 
 int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
   static const int exp_align = getenv("STC_EXP_ALIGN") ? atoi(getenv("STC_EXP_ALIGN")) : 0;
-  static const int occ2 = getenv("STC_CONV_OCC2") ? atoi(getenv("STC_CONV_OCC2")) : 0;   // bit 0: GRU convs, bit 1: N=64 block convs
   // A/B switches (profiling): kernel generation, MMA issuers per CTA, resident weights
   static const int conv_v = getenv("STC_CONV_V") ? atoi(getenv("STC_CONV_V")) : 2;
   static const int conv_iss = getenv("STC_CONV_ISS") ? atoi(getenv("STC_CONV_ISS")) : 1;
@@ -814,6 +822,7 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
   int rc;
   const int g = p.stats[0] ? p.G : 0;
   const int key = (p.N * 100 + g) * 10 + p.mode;
+  rc = STC_OK;
   if (ctx->conv_impl == 1) {
     rc = launch_simt(ctx, p, ndir);
   } else if (conv_v >= 2) {
@@ -836,17 +845,18 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
       default: STC_FAIL(STC_ERR_ARG, "conv: unsupported (N, groups, mode) combination");
     }
 #undef STC_V2
-    if (rc == 1) STC_FAIL(STC_ERR_ARG, "conv: image rows too wide for the shared-memory staging (set STC_CONV_V=1)");
-  } else {
+  }
+  if (ctx->conv_impl != 1 && (conv_v < 2 || rc == 1)) {
+    // first-generation kernel: A/B reference (STC_CONV_V=1) and the fallback for image rows too wide for the one-range staging
     switch (key) {
       case (6400 + 16) * 10 + MODE_PLAIN:                                                                               // GRU gates
-        rc = (occ2 & 1) ? launch_umma<64, 2, 16, MODE_PLAIN, 2>(ctx, p, ndir) : launch_umma<64, 4, 16, MODE_PLAIN>(ctx, p, ndir); break;
+        rc = launch_umma<64, 4, 16, MODE_PLAIN>(ctx, p, ndir); break;
       case (3200 + 8) * 10 + MODE_CAND:                                                                                 // GRU candidate
-        rc = (occ2 & 1) ? launch_umma<32, 2, 8, MODE_CAND, 2>(ctx, p, ndir) : launch_umma<32, 4, 8, MODE_CAND>(ctx, p, ndir); break;
+        rc = launch_umma<32, 4, 8, MODE_CAND>(ctx, p, ndir); break;
       case (6400 + 8) * 10 + MODE_PSCALE_SWISH:                                                                         // conv_median, conv_concat, up3
-        rc = (occ2 & 2) ? launch_umma<64, 2, 8, MODE_PSCALE_SWISH, 2>(ctx, p, ndir) : launch_umma<64, 4, 8, MODE_PSCALE_SWISH>(ctx, p, ndir); break;
+        rc = launch_umma<64, 4, 8, MODE_PSCALE_SWISH>(ctx, p, ndir); break;
       case (6400 + 8) * 10 + MODE_SWISH:                                                                                // out
-        rc = (occ2 & 2) ? launch_umma<64, 2, 8, MODE_SWISH, 2>(ctx, p, ndir) : launch_umma<64, 4, 8, MODE_SWISH>(ctx, p, ndir); break;
+        rc = launch_umma<64, 4, 8, MODE_SWISH>(ctx, p, ndir); break;
       case (12800 + 8) * 10 + MODE_PSCALE_SWISH: rc = launch_umma<128, 2, 8, MODE_PSCALE_SWISH>(ctx, p, ndir); break; // up2, up2_out
       case (12800 + 8) * 10 + MODE_SWISH:        rc = launch_umma<128, 2, 8, MODE_SWISH>(ctx, p, ndir); break;        // conv1
       case (25600 + 8) * 10 + MODE_SWISH:        rc = launch_umma<256, 1, 8, MODE_SWISH>(ctx, p, ndir); break;        // conv2

@@ -452,69 +452,14 @@ struct ApplyParams {
   int Hd, Wd; int mode; int off;  // mode 0 identity(+crop off) 1 maxpool2 2 upsample2 3 head
   const float* head_w; const float* head_b; float* head_out;
   float* feat_out;             // mode 3, optional: the block's sSE output (pb:csse_out_mul/mul) [B,Hd,Wd,C] float32
+  // mode 1, optional second consumer of the same block output: the centre crop [off2, off2 + Hd2)^2 of the un-pooled tensor
+  // (skip connection into a decoder concat buffer), written by the thread that pools the pixel -- the block's raw output
+  // is then read once instead of by two launches
+  uint4* dst2; int64_t dst2_plane; int d2Hp, d2Wp, off2, Hd2;
 };
 
-__global__ void __launch_bounds__(256) block_apply_kernel(ApplyParams p) {
-  extern __shared__ float s_ab[];   // [C] a, [C] b, [C] sse_w
-  float* sa = s_ab; float* sb = s_ab + p.C; float* sw = s_ab + 2 * p.C;
-  const int b = blockIdx.y;
-  const int gs = p.C / 8;
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    gn_affine(p.stats + (int64_t)b * 16, c / gs, p.count, p.gamma[c], p.beta[c], sa[c], sb[c]);
-    sw[c] = p.sse_w[c];
-  }
-  __syncthreads();
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.Hd * p.Wd) return;
-  int yd = idx / p.Wd, xd = idx - yd * p.Wd;
-  int nsrc = (p.mode == 1) ? 4 : 1;
-  int64_t SP[4]; float sv[4];
-  for (int k = 0; k < nsrc; ++k) {
-    int ys, xs;
-    if (p.mode == 1) { ys = 2 * yd + (k >> 1); xs = 2 * xd + (k & 1); }
-    else if (p.mode == 2) { ys = yd >> 1; xs = xd >> 1; }
-    else { ys = yd + p.off; xs = xd + p.off; }
-    SP[k] = ((int64_t)b * p.sHp + ys + p.so) * p.sWp + xs + p.so;
-    float dot = 0.f;
-    for (int c4 = 0; c4 < p.C / 4; ++c4) {
-      float4 v = p.raw[(int64_t)c4 * p.raw_plane + SP[k]];
-      int c = c4 * 4;
-      dot += (v.x * sa[c] + sb[c]) * sw[c] + (v.y * sa[c + 1] + sb[c + 1]) * sw[c + 1] +
-             (v.z * sa[c + 2] + sb[c + 2]) * sw[c + 2] + (v.w * sa[c + 3] + sb[c + 3]) * sw[c + 3];
-    }
-    sv[k] = sigm(dot + p.sse_b[0]);
-  }
-  if (p.mode == 3) {
-    float acc = 0.f;
-    for (int c4 = 0; c4 < p.C / 4; ++c4) {
-      float4 v = p.raw[(int64_t)c4 * p.raw_plane + SP[0]];
-      int c = c4 * 4;
-      acc += (v.x * sa[c] + sb[c]) * sv[0] * p.head_w[c] + (v.y * sa[c + 1] + sb[c + 1]) * sv[0] * p.head_w[c + 1] +
-             (v.z * sa[c + 2] + sb[c + 2]) * sv[0] * p.head_w[c + 2] + (v.w * sa[c + 3] + sb[c + 3]) * sv[0] * p.head_w[c + 3];
-    }
-    p.head_out[((int64_t)b * p.Hd + yd) * p.Wd + xd] = sigm(acc + p.head_b[0]);
-    return;
-  }
-  int64_t DP = ((int64_t)b * p.dHp + yd + 1) * p.dWp + xd + 1;
-  for (int c8 = 0; c8 < p.C / 8; ++c8) {
-    float o[8];
-    for (int k = 0; k < nsrc; ++k) {
-      float4 v0 = p.raw[(int64_t)(2 * c8) * p.raw_plane + SP[k]];
-      float4 v1 = p.raw[(int64_t)(2 * c8 + 1) * p.raw_plane + SP[k]];
-      float t[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int c = c8 * 8 + i;
-        float z = (t[i] * sa[c] + sb[c]) * sv[k];
-        o[i] = (k == 0) ? z : fmaxf(o[i], z);
-      }
-    }
-    p.dst[(int64_t)c8 * p.dst_plane + DP] = pack8(o);
-  }
-}
-
-// Same block tail, compiled per (C, MODE) so that the channel loops unroll and all plane loads of a pixel are in
-// flight at once (the runtime-C loop above keeps one 16-byte load per thread in flight, ~48 % of HBM peak).
+// Compiled per (C, MODE) so that the channel loops unroll and all plane loads of a pixel are in flight at once
+// (a runtime-C loop keeps one 16-byte load per thread in flight: measured ~48 % of HBM peak).
 // The sSE logit is folded to dot(v, a*w) + (sum b*w + bias); for C == 64 the raw values stay in registers
 // between the logit pass and the output pass.
 __device__ __forceinline__ float fast_sigm(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
@@ -600,10 +545,16 @@ __global__ void __launch_bounds__(256, 2) block_apply_t(ApplyParams p) {
       const float4 v0 = KEEP ? keep[2 * c8] : p.raw[(int64_t)(2 * c8) * p.raw_plane + SP[k]];
       const float4 v1 = KEEP ? keep[2 * c8 + 1] : p.raw[(int64_t)(2 * c8 + 1) * p.raw_plane + SP[k]];
       const float t[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float zk[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float z = (t[i] * sa8[i] + sb8[i]) * sv[k];
-        o[i] = (k == 0) ? z : fmaxf(o[i], z);
+        zk[i] = (t[i] * sa8[i] + sb8[i]) * sv[k];
+        o[i] = (k == 0) ? zk[i] : fmaxf(o[i], zk[i]);
+      }
+      if (MODE == 1 && p.dst2) {
+        const int y2 = 2 * yd + (k >> 1) - p.off2, x2 = 2 * xd + (k & 1) - p.off2;
+        if (y2 >= 0 && y2 < p.Hd2 && x2 >= 0 && x2 < p.Hd2)
+          p.dst2[(int64_t)c8 * p.dst2_plane + ((int64_t)b * p.d2Hp + y2 + 1) * p.d2Wp + x2 + 1] = pack8(zk);
       }
     }
     p.dst[(int64_t)c8 * p.dst_plane + DP] = pack8(o);
@@ -879,7 +830,8 @@ static int run_block_conv(stc_ctx* ctx, ModelState* m, int blk, const Act& in, i
 }
 
 static int run_apply(stc_ctx* ctx, ModelState* m, int blk, const Act& src_geo, bool same, int mode, int off,
-                     Act* dst, int dst_chunk_off, int Hd, int B, float* head_out) {
+                     Act* dst, int dst_chunk_off, int Hd, int B, float* head_out,
+                     Act* dst2 = nullptr, int dst2_chunk_off = 0, int off2 = 0, int Hd2 = 0) {
   ApplyParams ap; memset(&ap, 0, sizeof(ap));
   ap.raw = m->rawB.base; ap.raw_plane = (int64_t)((src_geo.Ptot() + 511) / 512 * 512); ap.C = BLK_COUT[blk];
   ap.sHp = src_geo.Hp; ap.sWp = src_geo.Wp; ap.so = same ? 1 : 2;
@@ -889,14 +841,13 @@ static int run_apply(stc_ctx* ctx, ModelState* m, int blk, const Act& src_geo, b
   std::string n = BLK[blk];
   ap.gamma = m->fp[n + ".gamma"]; ap.beta = m->fp[n + ".beta"]; ap.sse_w = m->fp[n + ".sse_w"]; ap.sse_b = m->fp[n + ".sse_b"];
   if (dst) { ap.dst = dst->at(dst_chunk_off); ap.dst_plane = dst->plane; ap.dHp = dst->Hp; ap.dWp = dst->Wp; }
+  if (dst2 && mode == 1) { ap.dst2 = dst2->at(dst2_chunk_off); ap.dst2_plane = dst2->plane; ap.d2Hp = dst2->Hp; ap.d2Wp = dst2->Wp; ap.off2 = off2; ap.Hd2 = Hd2; }
   ap.Hd = Hd; ap.Wd = Hd; ap.mode = mode; ap.off = off;
   ap.head_w = m->fp["head.w"]; ap.head_b = m->fp["head.b"]; ap.head_out = head_out;
   ap.feat_out = (mode == 3) ? ctx->feat_late_chunk : nullptr;
   dim3 grid(cdiv((int64_t)Hd * Hd, 256), B);
-  static const bool old_apply = getenv("STC_APPLY_OLD") != nullptr;      // A/B switch for profiling
   trace_begin(ctx, "block_apply");
-  if (old_apply) block_apply_kernel<<<grid, 256, 3 * ap.C * sizeof(float), ctx->stream>>>(ap);
-  else if (ap.C == 64) launch_apply_c<64>(ap, grid, ctx->stream);
+  if (ap.C == 64) launch_apply_c<64>(ap, grid, ctx->stream);
   else if (ap.C == 128) launch_apply_c<128>(ap, grid, ctx->stream);
   else if (ap.C == 256) launch_apply_c<256>(ap, grid, ctx->stream);
   else STC_FAIL(STC_ERR_ARG, "block tail: unsupported channel count");
@@ -1028,11 +979,10 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
   rc = run_block_conv(ctx, m, 0, xmed, 4, true, B); if (rc) return rc;                       // conv_median
   rc = run_apply(ctx, m, 0, m->CCin, true, 0, 0, &m->CCin, 8, H, B, nullptr); if (rc) return rc;
   rc = run_block_conv(ctx, m, 1, m->CCin, 16, true, B); if (rc) return rc;                   // conv_concat
-  rc = run_apply(ctx, m, 1, m->CCin, true, 1, 0, &m->P1, 0, p1, B, nullptr); if (rc) return rc;
-  rc = run_apply(ctx, m, 1, m->CCin, true, 0, 6, &m->CAT2, 8, u3, B, nullptr); if (rc) return rc;
+  // maxpool -> P1 and the centre crop (skip connection) -> CAT2 from one read of the block's raw output
+  rc = run_apply(ctx, m, 1, m->CCin, true, 1, 0, &m->P1, 0, p1, B, nullptr, &m->CAT2, 8, 6, u3); if (rc) return rc;
   rc = run_block_conv(ctx, m, 2, m->P1, 8, false, B); if (rc) return rc;                     // conv1 (VALID)
-  rc = run_apply(ctx, m, 2, m->P1, false, 1, 0, &m->P2, 0, p2, B, nullptr); if (rc) return rc;
-  rc = run_apply(ctx, m, 2, m->P1, false, 0, 2, &m->CAT1, 16, u2, B, nullptr); if (rc) return rc;
+  rc = run_apply(ctx, m, 2, m->P1, false, 1, 0, &m->P2, 0, p2, B, nullptr, &m->CAT1, 16, 2, u2); if (rc) return rc;
   rc = run_block_conv(ctx, m, 3, m->P2, 16, false, B); if (rc) return rc;                    // conv2 (VALID)
   rc = run_apply(ctx, m, 3, m->P2, false, 2, 0, &m->U2in, 0, u2, B, nullptr); if (rc) return rc;
   rc = run_block_conv(ctx, m, 4, m->U2in, 32, true, B); if (rc) return rc;                   // up2
