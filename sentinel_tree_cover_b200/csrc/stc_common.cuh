@@ -48,7 +48,7 @@ struct ConvParams {
   int vy0, vy1, vx0, vx1;       // valid output range in padded coordinates
   int mode;
   int out_fp16;                 // 1: write fp16 planes of uint4 (8 ch) instead of fp32 float4 planes
-  int exp_align;                // timing experiment (STC_EXP_ALIGN): see stc_conv.cu
+  int exp_flags;                // timing experiments (STC_EXP_FLAGS, results invalid): see stc_conv.cu
 };
 enum { MODE_PLAIN = 0, MODE_PSCALE_SWISH = 1, MODE_SWISH = 2, MODE_CAND = 3,
        MODE_BIAS = 4, MODE_BIAS_RELU = 5 };

@@ -348,8 +348,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per
       mbar_wait(TFULL(as), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
-      // timing experiments (STC_EXP_ALIGN bits, results invalid): 2 = no epilogue work at all, 4 = no global stores
-      for (int j = 0; j < ((working && !(p.exp_align & 2)) ? NT : 0); ++j) {
+      // timing experiments (STC_EXP_FLAGS bits, results invalid): 2 = no epilogue work at all, 4 = no global stores
+      for (int j = 0; j < ((working && !(p.exp_flags & 2)) ? NT : 0); ++j) {
         const int P = p0 + j * 128 + row;
         const bool inb = P < (int)p.Ptot;
         const int Pc = inb ? P : 0;
@@ -415,7 +415,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per
               acc_ss[(c0 + i) / GS] = fmaf(xm, xm, acc_ss[(c0 + i) / GS]);
             }
           }
-          if (inb && !(p.exp_align & 4)) {
+          if (inb && !(p.exp_flags & 4)) {
             if (p.out_fp16) {
               uint4* o = reinterpret_cast<uint4*>(outp) + (int64_t)((cbase + c0) >> 3) * p.out_plane + P;
               o[0] = pack8h(v);
@@ -530,9 +530,9 @@ __global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, in
           const uint64_t bdesc = desc_join(b_lo + (uint32_t)(tap * 2 * N));
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
-            // exp_align (STC_EXP_ALIGN=1, timing experiment only): drop the dx row shift so every
+            // STC_EXP_FLAGS bit 0 (, timing experiment only): drop the dx row shift so every
             // A core matrix starts 128-B aligned -- results are wrong, the MMA rate is what is measured
-            const int dxe = (p.exp_align & 1) ? 0 : dx;
+            const int dxe = (p.exp_flags & 1) ? 0 : dx;
             const uint64_t adesc = desc_join(a_lo + (uint32_t)((dy * 2) * C::R + j * 128 + dxe));
             if (leader) tc_mma_f16(tacc + (uint32_t)(j * N), adesc, bdesc, IDESC, (ks > 0 || tap > 0) ? 1u : 0u);
           }
@@ -774,14 +774,14 @@ static int launch_simt(stc_ctx* ctx, const ConvParams& p, int ndir) {
 }
 
 int launch_conv(stc_ctx* ctx, const ConvParams& p_in, int ndir) {
-  static const int exp_align = getenv("STC_EXP_ALIGN") ? atoi(getenv("STC_EXP_ALIGN")) : 0;
+  static const int exp_flags = getenv("STC_EXP_FLAGS") ? atoi(getenv("STC_EXP_FLAGS")) : 0;
   // A/B switches (profiling): kernel generation, MMA issuers per CTA, resident weights
   static const int conv_v = getenv("STC_CONV_V") ? atoi(getenv("STC_CONV_V")) : 2;
   static const int conv_iss = getenv("STC_CONV_ISS") ? atoi(getenv("STC_CONV_ISS")) : 1;
   static const int conv_wres = getenv("STC_CONV_WRES") ? atoi(getenv("STC_CONV_WRES")) : 1;
   static const int conv_prio = getenv("STC_CONV_PRIO") ? atoi(getenv("STC_CONV_PRIO")) : 1;
   ConvParams p = p_in;
-  p.exp_align = exp_align;
+  p.exp_flags = exp_flags;
   if (p.mode == MODE_CAND && p.N != 32) STC_FAIL(STC_ERR_ARG, "conv: MODE_CAND requires N == 32");
   if (p.G > 16 || (p.G > 0 && p.N % p.G)) STC_FAIL(STC_ERR_ARG, "conv: bad group count");
   cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -156,3 +156,31 @@ def test_uint16_patches_follow_integer_convention(sess):
     y_u = sess.predict_patches(u)
     y_f = sess.predict_patches(mf)
     assert y_u.dtype == np.float32 and np.abs(y_u - y_f).max() < 2e-4
+
+
+def test_wide_rows_use_the_three_segment_kernel(predict_weights):
+    """H = 728: one staged row range (512 + 2*730 + 2 rows x 2 chunks) no longer leaves two pipeline stages in shared
+    memory, so the launcher falls back to the first-generation kernel (three per-dy segments).  Checked against the
+    CUDA-core kernel on the same fp16 operands."""
+    x = P.synth_model_input(1, 728, 24)
+    ys = []
+    for impl in (1, 0):
+        s = StcSession(0, predict_weights=predict_weights, conv_impl=impl)
+        ys.append(s.predict(x))
+        s.close()
+    d = np.abs(ys[0] - ys[1]).max()
+    print("wide rows: umma vs simt", d)
+    assert ys[0].shape == (1, 714, 714) and d < 2e-4
+
+
+def test_kernel_timeline_csv(sess, tmp_path):
+    """stc_trace: one row per kernel of the forward, start <= end, convolutions labelled."""
+    m = P.synth_monthly(2, 44, 3)
+    sess.trace(1)
+    sess.predict_patches(m)
+    path = str(tmp_path / "trace.csv")
+    sess.trace(0, path)
+    rows = [l.strip().split(",") for l in open(path)][1:]
+    labels = {r[0] for r in rows}
+    assert {"front", "conv_gates", "conv_cand", "apply1", "apply2", "block_apply"} <= labels
+    assert all(float(r[2]) <= float(r[3]) for r in rows)
