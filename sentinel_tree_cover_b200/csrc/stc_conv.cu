@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, in
           const uint64_t bdesc = desc_join(b_lo + (uint32_t)(tap * 2 * N));
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
-            // STC_EXP_FLAGS bit 0 (, timing experiment only): drop the dx row shift so every
+            // STC_EXP_FLAGS bit 0 (timing experiment only): drop the dx row shift so every
             // A core matrix starts 128-B aligned -- results are wrong, the MMA rate is what is measured
             const int dxe = (p.exp_flags & 1) ? 0 : dx;
             const uint64_t adesc = desc_join(a_lo + (uint32_t)((dy * 2) * C::R + j * 128 + dxe));
