@@ -407,53 +407,74 @@ __device__ __forceinline__ float np_leaf_sum(const float* a, int n, int pass, fl
   for (; i < n; ++i) res = __fadd_rn(res, g(i));
   return res;
 }
-__device__ float np_combine(const float* leaf, int n) {     // replay of the pairwise recursion over leaf sums (single thread)
-  struct F { int n, stage; float a; };
-  F st[40]; int sp = 0; st[0].n = n; st[0].stage = 0; st[0].a = 0.f;
-  float ret = 0.f; int li = 0;
-  while (sp >= 0) {
-    F& f = st[sp];
-    if (f.n <= 128) { ret = leaf[li++]; --sp; continue; }
-    int n2 = f.n / 2; n2 -= n2 % 8;
-    if (f.stage == 0) { f.stage = 1; ++sp; st[sp].n = n2; st[sp].stage = 0; }
-    else if (f.stage == 1) { f.a = ret; f.stage = 2; ++sp; st[sp].n = f.n - n2; st[sp].stage = 0; }
-    else { ret = __fadd_rn(f.a, ret); --sp; }
-  }
-  return ret;
-}
 // out[t] = {mean, std} as float32 exactly as NumPy computes them (finite inputs; a date whose
 // brightness median is NaN has no valid slot and yields NaN, as np.nanmean / np.nanstd do).
-__global__ void __launch_bounds__(1024) k_np_moments(const float* __restrict__ vals,
-                                                     const int* __restrict__ cnts, int HW, int leaf_cap, int2* __restrict__ leaves,
-                                                     float* __restrict__ leafsum, float* __restrict__ out /*[T][2]*/) {
+// np.add.reduce over a contiguous float32 vector is a recursion: n > 128 splits into (n/2 rounded down to a multiple
+// of 8, rest), leaves use 8 strided accumulators.  The recursion tree depends only on n, so it is built breadth first
+// (one thread per node, block-wide scan per level), every leaf is summed by its own thread, and the inner nodes are
+// combined level by level from the bottom: left + right, NumPy's order, no serial walk (the first version replayed the
+// recursion on one thread: 3.4 ms per launch for 3,800 leaves).  One block per date; node arrays in global memory.
+__global__ void __launch_bounds__(1024) k_np_moments(const float* __restrict__ vals, const int* __restrict__ cnts, int HW, int node_cap,
+                                                     int2* __restrict__ nodes_all, int* __restrict__ child_all, float* __restrict__ val_all,
+                                                     float* __restrict__ out /*[T][2]*/) {
   const int t = blockIdx.x;
   const float* a = vals + (int64_t)t * HW;
-  int2* lv = leaves + (int64_t)t * leaf_cap; float* ls = leafsum + (int64_t)t * leaf_cap;
+  int2* node = nodes_all + (int64_t)t * node_cap;        // (offset, length)
+  int* child = child_all + (int64_t)t * node_cap;        // index of the left child (right = +1), -1 for a leaf
+  float* val = val_all + (int64_t)t * node_cap;
   const int n = cnts[2 * t], nvalid = cnts[2 * t + 1];
-  __shared__ int L; __shared__ float mean_s;
+  __shared__ int lvl_start[40]; __shared__ int n_lvl; __shared__ int wtot[32]; __shared__ int base_s; __shared__ float mean_s;
   if (nvalid == 0) { if (threadIdx.x == 0) { out[2 * t] = nanf(""); out[2 * t + 1] = nanf(""); } return; }
-  if (threadIdx.x == 0) {
-    int2 st[40]; int sp = 0; st[0] = make_int2(0, n); int l = 0;
-    while (sp >= 0) {
-      int2 f = st[sp--];
-      if (f.y <= 128) { lv[l++] = f; continue; }
-      int n2 = f.y / 2; n2 -= n2 % 8;
-      st[++sp] = make_int2(f.x + n2, f.y - n2);
-      st[++sp] = make_int2(f.x, n2);
-    }
-    L = l;
-  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { node[0] = make_int2(0, n); lvl_start[0] = 0; lvl_start[1] = 1; n_lvl = 1; }
   __syncthreads();
+  // ---- breadth-first construction ----
+  for (int d = 0; d < 38; ++d) {
+    const int ls = lvl_start[d], le = lvl_start[d + 1];
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int i0 = ls; i0 < le; i0 += 1024) {
+      const int i = i0 + threadIdx.x;
+      int2 f = make_int2(0, 0);
+      bool inner = false;
+      if (i < le) { f = node[i]; inner = f.y > 128; }
+      const unsigned bal = __ballot_sync(0xffffffffu, inner);
+      if (lane == 0) wtot[wid] = __popc(bal);
+      __syncthreads();
+      int woff = 0;
+      for (int w = 0; w < wid; ++w) woff += wtot[w];
+      if (i < le) {
+        if (inner) {
+          const int c = le + 2 * (base_s + woff + __popc(bal & ((1u << lane) - 1u)));
+          int n2 = f.y / 2; n2 -= n2 % 8;
+          child[i] = c;
+          node[c] = make_int2(f.x, n2);
+          node[c + 1] = make_int2(f.x + n2, f.y - n2);
+        } else child[i] = -1;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { int sum = 0; for (int w = 0; w < 32; ++w) sum += wtot[w]; base_s += sum; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { lvl_start[d + 2] = le + 2 * base_s; if (base_s > 0) n_lvl = d + 2; }
+    __syncthreads();
+    if (base_s == 0) break;
+  }
+  const int total = lvl_start[n_lvl];
   for (int pass = 0; pass < 2; ++pass) {
     const float mean = pass ? mean_s : 0.f;
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
-      const float* q = a + lv[l].x; const int m = lv[l].y;
-      ls[l] = np_leaf_sum(q, m, pass, mean);
-    }
+    for (int i = threadIdx.x; i < total; i += 1024)
+      if (child[i] < 0) val[i] = np_leaf_sum(a + node[i].x, node[i].y, pass, mean);
     __syncthreads();
+    for (int d = n_lvl - 2; d >= 0; --d) {               // the deepest level holds leaves only
+      for (int i = lvl_start[d] + threadIdx.x; i < lvl_start[d + 1]; i += 1024) {
+        const int c = child[i];
+        if (c >= 0) val[i] = __fadd_rn(val[c], val[c + 1]);
+      }
+      __syncthreads();
+    }
     if (threadIdx.x == 0) {
-      float s = np_combine(ls, n);
-      float r = (float)((double)s / (double)nvalid);     // float32 / intp -> float64 divide -> float32
+      const float r = (float)((double)val[0] / (double)nvalid);     // float32 / intp -> float64 divide -> float32
       if (pass == 0) { mean_s = r; out[2 * t] = r; } else out[2 * t + 1] = __fsqrt_rn(r);
     }
     __syncthreads();
@@ -636,7 +657,7 @@ extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const f
     STC_FAIL(STC_ERR_ARG, "cloud_masks: bad argument (1 <= T <= 32)");
   const int HW = H * W; const int64_t N = (int64_t)T * HW;
   Buf d_img, d_dem, d_clm, d_a, d_b, d_c, d_sh, d_cl, d_bc, d_nsr, d_water, d_allref, d_minb4, d_p25, d_minrgb, d_rc, d_thr,
-      d_ci, d_cc, d_cnt, d_win, d_med, d_mom, d_flags, d_all, d_out, d_vals, d_leaves, d_leafsum, d_cnts;
+      d_ci, d_cc, d_cnt, d_win, d_med, d_mom, d_flags, d_all, d_out, d_vals, d_leaves, d_leafsum, d_child, d_cnts;
   STC_CUDA(cudaMalloc(&d_img.p, N * 40)); STC_CUDA(cudaMalloc(&d_dem.p, HW * 4));
   for (Buf* b : {&d_clm, &d_a, &d_b, &d_c, &d_sh, &d_cl, &d_bc, &d_nsr}) STC_CUDA(cudaMalloc(&b->p, N));
   STC_CUDA(cudaMalloc(&d_water.p, HW * 4)); STC_CUDA(cudaMalloc(&d_allref.p, HW * 16)); STC_CUDA(cudaMalloc(&d_minb4.p, HW * 16));
@@ -645,9 +666,9 @@ extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const f
   STC_CUDA(cudaMalloc(&d_cnt.p, 64)); STC_CUDA(cudaMalloc(&d_win.p, 2 * CT_MAX * 4)); STC_CUDA(cudaMalloc(&d_med.p, CT_MAX * 4));
   STC_CUDA(cudaMalloc(&d_mom.p, CT_MAX * 2 * 4)); STC_CUDA(cudaMalloc(&d_flags.p, 2 * CT_MAX * 4)); STC_CUDA(cudaMalloc(&d_all.p, CT_MAX * 4));
   STC_CUDA(cudaMalloc(&d_out.p, N * 4));
-  const int leaf_cap = HW / 32 + 8;
-  STC_CUDA(cudaMalloc(&d_vals.p, N * 4)); STC_CUDA(cudaMalloc(&d_leaves.p, (size_t)T * leaf_cap * 8));
-  STC_CUDA(cudaMalloc(&d_leafsum.p, (size_t)T * leaf_cap * 4)); STC_CUDA(cudaMalloc(&d_cnts.p, CT_MAX * 2 * 4));
+  const int node_cap = 2 * (HW / 56 + 8) + 2;            // a pairwise leaf holds 58..128 values; a binary tree has < 2 x leaves nodes
+  STC_CUDA(cudaMalloc(&d_vals.p, N * 4)); STC_CUDA(cudaMalloc(&d_leaves.p, (size_t)T * node_cap * 8));
+  STC_CUDA(cudaMalloc(&d_leafsum.p, (size_t)T * node_cap * 4)); STC_CUDA(cudaMalloc(&d_child.p, (size_t)T * node_cap * 4)); STC_CUDA(cudaMalloc(&d_cnts.p, CT_MAX * 2 * 4));
   const float* img = (const float*)d_img.p; const float* dem = (const float*)d_dem.p;
   unsigned char *clm = (unsigned char*)d_clm.p, *ta = (unsigned char*)d_a.p, *tb = (unsigned char*)d_b.p, *tc = (unsigned char*)d_c.p,
                 *sh = (unsigned char*)d_sh.p, *cl = (unsigned char*)d_cl.p, *bc = (unsigned char*)d_bc.p, *nsr = (unsigned char*)d_nsr.p;
@@ -670,8 +691,8 @@ extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const f
   std::vector<float> mom_h(2 * CT_MAX); std::vector<int> cnt_h(2 * CT_MAX);
   auto moments = [&](int kind, const float* medb, const int* all_px, bool to_host) -> int {
     k_compact<<<T, 1024, 0, ctx->stream>>>(img, cl, water, medb, all_px, HW, kind, (float*)d_vals.p, (int*)d_cnts.p);
-    k_np_moments<<<T, 1024, 0, ctx->stream>>>((const float*)d_vals.p, (const int*)d_cnts.p, HW, leaf_cap, (int2*)d_leaves.p,
-                                              (float*)d_leafsum.p, (float*)d_mom.p);
+    k_np_moments<<<T, 1024, 0, ctx->stream>>>((const float*)d_vals.p, (const int*)d_cnts.p, HW, node_cap, (int2*)d_leaves.p,
+                                              (int*)d_child.p, (float*)d_leafsum.p, (float*)d_mom.p);
     ctx->launches += 2;
     if (to_host) {
       STC_CUDA(cudaMemcpyAsync(mom_h.data(), d_mom.p, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
