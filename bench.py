@@ -361,6 +361,12 @@ def main():
         flops = conv_flops_per_tile(H) * B * args.steps
         achieved = flops / (conv_ms_single / 1000.0) / 1e12 if conv_ms_single > 0 else None
         roof = gates_roofline(gates_ms, gates_n, min(B, int(os.environ.get("STC_CHUNK", "32"))), peaks)
+        if gates_n_ovl and roof.get("achieved"):
+            # the same launches inside the timed (multi-slot) region: their CUDA-event durations include the kernels of
+            # the other slots that share the SMs, so this is a lower bound on the kernel's own rate
+            ovl = roof["achieved"] * (gates_ms / gates_n) / (gates_ms_ovl / gates_n_ovl)
+            roof["achieved_in_timed_region"] = ovl
+            roof["frac_in_timed_region"] = ovl / roof["peak"]
         if gates_n_ovl:
             roof["note"] += "; timed with every launch alone on the GPU (single-stream pass of the same %d steps, %.2f ms/step); in the " \
                             "production multi-slot schedule the same launches average %.1f us because chunks share the SMs" \
