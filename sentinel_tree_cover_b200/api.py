@@ -641,6 +641,29 @@ def predict_subtile(subtile, sess, op=None, size=None):
     return preds
 
 
+def predict_subtile_monthly(subtile, sess):
+    """Legacy 12-step contract, src/download_and_predict_job_multiyear.py:794-838 (the "12-step x 13-band" signature of
+    BASELINE.json): subtile (13, S+14, S+14, 13) = 12 monthly frames + the median frame, 13 bands (10 S2, DEM, 2 S1).
+    Indices (:812-816), clip / normalise with the 17 constants (:819-820), sess.run with lengths = 12 (:826), squeeze,
+    preds[1:-1, 1:-1] (:831).  All-zero (or negative-sum) input -> int 255 fill of the UNcropped size, like the
+    reference (:834-835 uses SIZE).  The ConvGRU weights do not depend on the sequence length, so the same
+    session serves the quarterly (length 4) and this monthly (length 12) graph."""
+    SIZE = subtile.shape[1] - 14
+    if np.sum(subtile) > 0:
+        if not isinstance(subtile.flat[0], np.floating):
+            assert np.max(subtile) > 1
+            subtile = sess.to_float32(np.ascontiguousarray(subtile).astype(np.uint16, copy=False))
+        sub = np.ascontiguousarray(subtile, np.float32)
+        x = np.empty(sub.shape[:3] + (17,), np.float32)
+        x[..., :13] = sub
+        x[..., 13:] = sess.indices(sub)                       # evi, bi, msavi2, grndvi on the device (bands 0,1,2,3,8)
+        preds = sess.predict(x[np.newaxis], length=sub.shape[0] - 1, normalize=True).squeeze()
+        preds = preds[1:-1, 1:-1]
+    else:
+        preds = np.full((SIZE, SIZE), 255)
+    return preds
+
+
 def float_to_int16(arr, sess, precision=1000):
     """src/download_and_predict_job.py:174-180 (the NaN replacement is in place there too)."""
     return sess.float_to_int16(arr, precision)

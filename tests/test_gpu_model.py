@@ -184,3 +184,20 @@ def test_kernel_timeline_csv(sess, tmp_path):
     labels = {r[0] for r in rows}
     assert {"front", "conv_gates", "conv_cand", "apply1", "apply2", "block_apply"} <= labels
     assert all(float(r[2]) <= float(r[3]) for r in rows)
+
+
+def test_predict_subtile_monthly_legacy_contract(sess, predict_weights):
+    """src/download_and_predict_job_multiyear.py:794-838: (13, S+14, S+14, 13) monthly stack, indices computed inside,
+    12 GRU steps, output preds[1:-1, 1:-1]."""
+    from sentinel_tree_cover_b200.api import predict_subtile_monthly
+    r = np.random.default_rng(12)
+    m = P.synth_monthly(1, 44, 17)[0]                                   # [12, 44, 44, 13]
+    sub = np.concatenate([m, np.median(m, axis=0, keepdims=True)]).astype(np.float32)
+    got = predict_subtile_monthly(sub, sess)
+    x = np.concatenate([sub, P.make_indices(sub)], axis=-1)
+    ref = PredictRef(predict_weights).forward(P.normalize_subtile(x[None].copy(), MIN_ALL, MAX_ALL), length=[12])[0][1:-1, 1:-1]
+    err = np.abs(got - ref).max()
+    print("legacy monthly contract err", err)
+    assert got.shape == (28, 28) and got.dtype == np.float32 and err < TOL
+    z = predict_subtile_monthly(np.zeros((13, 44, 44, 13), np.float32), sess)
+    assert z.shape == (30, 30) and (z == 255).all()
