@@ -634,15 +634,39 @@ struct PyRandom {
   }
   inline uint32_t randbelow(uint32_t n) {
     const int sh = __builtin_clz(n);     // 32 - n.bit_length(), n >= 1
-    // (~10 ns per shuffled element on the host; a variant that examines two candidates with conditional moves instead of
-    //  the unpredictable accept branch measured the same, so the plain _randbelow_with_getrandbits loop stays)
     uint32_t r;
     do { r = next() >> sh; } while (r >= n);
     return r;
   }
+  // random.shuffle: for i = len-1 .. 1: j = _randbelow(i + 1); x[i], x[j] = x[j], x[i].  _randbelow_with_getrandbits
+  // draws k = (i+1).bit_length() bits until the value is <= i, i.e. EVERY draw consumes one generator output and a
+  // rejected draw changes nothing.  The loop below therefore advances one output per iteration and turns the accept test
+  // into arithmetic (a rejected draw swaps x[i] with itself and leaves i alone): no unpredictable branch, ~3x faster than
+  // the textbook rejection loop (the accept rate is 50-100 %).  All i of one power-of-two band share the shift.
   void shuffle(std::vector<int>& x) {
     int* v = x.data();
-    for (size_t i = x.size(); i-- > 1;) { const uint32_t j = randbelow((uint32_t)i + 1); const int t = v[i]; v[i] = v[j]; v[j] = t; }
+    size_t i = x.size();
+    if (i < 2) return;
+    --i;                                   // i = len - 1
+    while (i >= 1) {
+      const int sh = __builtin_clz((uint32_t)i + 1u);
+      const size_t band_lo = (sh == 31) ? 1 : ((size_t)1 << (31 - sh));     // smallest i with the same bit length of i + 1 ... (i+1 >= 2^(31-sh))
+      const size_t lo = band_lo > 1 ? band_lo - 1 : 1;                       // i + 1 >= band_lo  <=>  i >= band_lo - 1
+      while (i >= lo) {
+        if (idx >= 624) regen(); else if (!out_valid) temper_all();
+        int avail = 624 - idx;
+        const uint32_t* o = out + idx;
+        int used = 0;
+        while (used < avail && i >= lo) {
+          const uint32_t r = o[used++] >> sh;
+          const bool ok = r <= (uint32_t)i;
+          const size_t j = ok ? (size_t)r : i;
+          const int t = v[i]; v[i] = v[j]; v[j] = t;
+          i -= ok;
+        }
+        idx += used;
+      }
+    }
   }
 };
 
@@ -788,6 +812,7 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
   CF_SYNC();
   PyRandom rng; memcpy(rng.mt, mt_state, 624 * 4); rng.idx = (int)mt_state[624];
   std::vector<unsigned char> lab;
+  std::vector<int> p2, p20, p40, p60, p80, p100, p98, sample;      // reused across dates: fresh multi-MB vectors page-fault on every date
   double t_gpu1 = 0, t_bucket = 0, t_shuffle = 0, t_gpu2 = 0; long long n_draw = 0;
   for (int d = 0; d < n; ++d) {
     const int c_pos = counts[d * 5], c_zero = counts[d * 5 + 1], c_lt1 = counts[d * 5 + 2], c_one = counts[d * 5 + 3];
@@ -822,33 +847,38 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
     CF_SYNC();
     double tt1 = cf_timing ? cf_now() : 0; t_gpu1 += tt1 - tt0;
     // sampling bookkeeping (:447-497): index lists per stratum, Python random.shuffle, concatenate, shuffle, truncate
-    std::vector<int> p2, p20, p40, p60, p80, p100, p98;
     {
+      // count, size, then fill: the five quintile lists without branches (every row is stored into every list, the cursor
+      // only advances where the stratum bit is set); the 2 % tails p2 / p98 are written ten times per row, which is
+      // np.repeat(..., 10) (:470-471)
       size_t cntb[7] = {0, 0, 0, 0, 0, 0, 0};
       for (int r = 0; r < K; ++r) { const unsigned char m = lab[r]; for (int k = 0; k < 7; ++k) cntb[k] += (m >> k) & 1u; }
-      p2.reserve(cntb[0] * 10); p20.reserve(cntb[1]); p40.reserve(cntb[2]); p60.reserve(cntb[3]); p80.reserve(cntb[4]);
-      p100.reserve(cntb[5]); p98.reserve(cntb[6] * 10);
-    }
-    for (int r = 0; r < K; ++r) {
-      unsigned char m = lab[r];
-      if (m & 1) p2.push_back(r);
-      if (m & 2) p20.push_back(r);
-      if (m & 4) p40.push_back(r);
-      if (m & 8) p60.push_back(r);
-      if (m & 16) p80.push_back(r);
-      if (m & 32) p100.push_back(r);
-      if (m & 64) p98.push_back(r);
+      std::vector<int>* lists[7] = {&p2, &p20, &p40, &p60, &p80, &p100, &p98};
+      const int rep[7] = {10, 1, 1, 1, 1, 1, 10};
+      int* cur[7];
+      for (int k = 0; k < 7; ++k) { lists[k]->resize(cntb[k] * rep[k] + 10); cur[k] = lists[k]->data(); }
+      for (int r = 0; r < K; ++r) {
+        const unsigned char m = lab[r];
+        *cur[1] = r; cur[1] += (m >> 1) & 1u;
+        *cur[2] = r; cur[2] += (m >> 2) & 1u;
+        *cur[3] = r; cur[3] += (m >> 3) & 1u;
+        *cur[4] = r; cur[4] += (m >> 4) & 1u;
+        *cur[5] = r; cur[5] += (m >> 5) & 1u;
+        if (m & 0x41u) {                                   // the 2 % tails: rare, predictable
+          if (m & 1u) { for (int q = 0; q < 10; ++q) cur[0][q] = r; cur[0] += 10; }
+          if (m & 0x40u) { for (int q = 0; q < 10; ++q) cur[6][q] = r; cur[6] += 10; }
+        }
+      }
+      for (int k = 0; k < 7; ++k) lists[k]->resize(cntb[k] * rep[k]);
     }
     for (auto* v : {&p20, &p40, &p60, &p80, &p100})      // p2 / p98 go through np.repeat first, which accepts a 0-d array
       if (v->size() == 1)
         STC_FAIL(STC_ERR_STATE, "remove_clouds: single-element EVI stratum -- the reference raises TypeError (shuffle of a 0-d array)");
-    auto repeat10 = [](std::vector<int>& v) { std::vector<int> o; o.reserve(v.size() * 10); for (int x : v) for (int k = 0; k < 10; ++k) o.push_back(x); v.swap(o); };
-    repeat10(p98); repeat10(p2);
     double tt2 = cf_timing ? cf_now() : 0; t_bucket += tt2 - tt1;
     n_draw += (long long)(p2.size() + p98.size() + p20.size() + p40.size() + p60.size() + p80.size() + p100.size());
     rng.shuffle(p2); rng.shuffle(p98); rng.shuffle(p20); rng.shuffle(p40); rng.shuffle(p60); rng.shuffle(p80); rng.shuffle(p100);
     const size_t n_i = (size_t)(std::min(90000, K) / 5);
-    std::vector<int> sample;
+    sample.clear();
     auto append = [&](const std::vector<int>& v, size_t limit) { sample.insert(sample.end(), v.begin(), v.begin() + std::min(limit, v.size())); };
     append(p2, p2.size()); append(p20, n_i); append(p40, n_i); append(p60, n_i); append(p80, n_i); append(p100, n_i); append(p98, p98.size());
     rng.shuffle(sample);
