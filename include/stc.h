@@ -283,6 +283,11 @@ int stc_binary_dilate_host(stc_ctx* ctx, const uint8_t* in_host, int n, int H, i
  *      stc_last_error. ---- */
 int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H, int W,
                            uint32_t* mt_state, float* areas_out_host, int32_t* to_remove_out_host, float* mosaic_out_host);
+/* Same, for process_tile: when no date has to be removed the cube is clipped to [0, 1] before it is copied back
+ * (np.clip(sentinel2, 0, 1), src/download_and_predict_job.py:996, is the next statement on that path) and
+ * *clipped_out = 1; otherwise the cube comes back unclipped (the masks are recomputed on it first, :972-990). */
+int stc_remove_clouds_clip_host(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H, int W,
+                                uint32_t* mt_state, float* areas_out_host, int32_t* to_remove_out_host, int32_t* clipped_out);
 
 /* ---- exact squared Euclidean distance to the nearest non-zero pixel of `target`, searched
  *      within `radius` (radius^2+1 where none): the capped distance_transform_edt call sites

@@ -113,6 +113,8 @@ SYMBOLS = [
     ("stc_postprocess_subtile_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_remove_clouds_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("stc_remove_clouds_clip_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     ("stc_cloud_masks_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int]),
     ("stc_debug_read", C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p]),
@@ -532,7 +534,7 @@ class StcSession:
         self._check(self.lib.stc_postprocess_subtile_host(self.h, _dptr(p), _dptr(a), _dptr(m), S, F, Cc, _dptr(out)))
         return out
 
-    def remove_clouds(self, tiles, probs, pfcps, mt_state, want_mosaic=False):
+    def remove_clouds(self, tiles, probs, pfcps, mt_state, want_mosaic=False, clip_when_all_kept=False):
         """remove_cloud_and_shadows core (cloud_removal.py:888-973).  tiles: C-contiguous float32 [n,H,W,10],
         rewritten in place.  mt_state: uint32[625] (Python `random.getstate()[1]`), advanced in place.
         Returns (areas [n,H,W] float32, to_remove list[, mosaic [H,W,10]])."""
@@ -551,6 +553,11 @@ class StcSession:
         areas = np.empty((n, H, W), np.float32)
         rem = np.zeros(n, np.int32)
         mosaic = np.empty((H, W, 10), np.float32) if want_mosaic else None
+        if clip_when_all_kept:               # process_tile: fold the np.clip(sentinel2, 0, 1) that follows into the download
+            clipped = C.c_int32(0)
+            self._check(self.lib.stc_remove_clouds_clip_host(self.h, _dptr(tiles), _dptr(p), _dptr(f), n, H, W, _dptr(mt_state),
+                                                             _dptr(areas), _dptr(rem), C.byref(clipped)))
+            return areas, [int(i) for i in np.flatnonzero(rem)], bool(clipped.value)
         self._check(self.lib.stc_remove_clouds_host(self.h, _dptr(tiles), _dptr(p), _dptr(f), n, H, W, _dptr(mt_state), _dptr(areas),
                                                     _dptr(rem), _dptr(mosaic) if want_mosaic else None))
         out = (areas, [int(i) for i in np.flatnonzero(rem)])
@@ -827,7 +834,7 @@ def id_areas_to_interp(tiles, probs, shadows, image_dates, pfcps, sess):
     return sess.feather(a, 15)
 
 
-def remove_cloud_and_shadows(tiles, probs, shadows, image_dates, pfcps, sentinel1, mosaic=None, sess=None):
+def remove_cloud_and_shadows(tiles, probs, shadows, image_dates, pfcps, sentinel1, mosaic=None, sess=None, clip_when_all_kept=False):
     """src/preprocessing/cloud_removal.py:888-973, same arguments and return value
     `(tiles, areas_interpolated, to_remove)`; `tiles` is blended IN PLACE like the reference.
     `shadows`, `image_dates` and `sentinel1` are accepted and unused (the reference body never reads
@@ -849,10 +856,16 @@ def remove_cloud_and_shadows(tiles, probs, shadows, image_dates, pfcps, sentinel
         work = np.ascontiguousarray(tiles, np.float32)
     version, internal, gauss = random.getstate()
     state = np.array(internal, dtype=np.uint32)
-    areas, to_remove = sess.remove_clouds(work, probs, pfcps, state)
+    clipped = False
+    if clip_when_all_kept:       # tile.process_tile: fold the np.clip that follows (:996) into the download; extra return value
+        areas, to_remove, clipped = sess.remove_clouds(work, probs, pfcps, state, clip_when_all_kept=True)
+    else:
+        areas, to_remove = sess.remove_clouds(work, probs, pfcps, state)
     random.setstate((version, tuple(int(v) for v in state), gauss))
     if work is not tiles:
         tiles[...] = work
+    if clip_when_all_kept:
+        return tiles, areas, to_remove, clipped
     return tiles, areas, to_remove
 
 

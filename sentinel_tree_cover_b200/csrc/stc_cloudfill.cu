@@ -683,9 +683,18 @@ __global__ void __launch_bounds__(256) k_count_zero(const unsigned char* __restr
 #define CF_LAUNCH(kern, grid, block, ...) do { kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
 #define CF_SYNC() STC_CUDA(cudaStreamSynchronize(ctx->stream))
 
-extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H,
-                                      int W, uint32_t* mt_state, float* areas_host, int32_t* to_remove_host, float* mosaic_host) {
+namespace {
+__global__ void __launch_bounds__(256) k_clip01(float* __restrict__ x, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = fminf(fmaxf(x[i], 0.f), 1.f);
+}
+}  // namespace
+
+static int remove_clouds_impl(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H,
+                              int W, uint32_t* mt_state, float* areas_host, int32_t* to_remove_host, float* mosaic_host,
+                              int clip_when_all_kept, int32_t* clipped_out) {
   if (!ctx) return STC_ERR_ARG;
+  if (clipped_out) *clipped_out = 0;
   if (!tiles_host || !probs_host || !pfcps_host || !mt_state || !areas_host || !to_remove_host || n < 1 || n > CF_MAX_DATES || H < 3 ||
       W < 3 || mt_state[624] > 624)
     STC_FAIL(STC_ERR_ARG, "remove_clouds: bad argument (1 <= n <= 32, MT19937 state of 624 words + position)");
@@ -925,9 +934,31 @@ extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const flo
   }
   STC_CUDA(cudaGetLastError());
   cf_mark("residual clouds");
+  if (clip_when_all_kept) {
+    // process_tile clips the cube right after this call (src/download_and_predict_job.py:996) unless a fully
+    // interpolated date has to be dropped first (:972-990, the masks are then recomputed on the unclipped cube): doing it
+    // here saves a round trip of the whole cube
+    bool all_kept = true;
+    for (int d = 0; d < n; ++d) all_kept = all_kept && !to_remove_host[d];
+    if (all_kept) {
+      CF_LAUNCH(k_clip01, cdiv(N * 10, 256), 256, tiles, N * 10);
+      if (clipped_out) *clipped_out = 1;
+    }
+  }
   STC_CUDA(cudaMemcpyAsync(tiles_host, tiles, N * 40, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(areas_host, areas, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CF_SYNC();
   cf_mark("download");
   return STC_OK;
+}
+
+extern "C" int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H,
+                                      int W, uint32_t* mt_state, float* areas_host, int32_t* to_remove_host, float* mosaic_host) {
+  return remove_clouds_impl(ctx, tiles_host, probs_host, pfcps_host, n, H, W, mt_state, areas_host, to_remove_host, mosaic_host, 0, nullptr);
+}
+
+extern "C" int stc_remove_clouds_clip_host(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n,
+                                           int H, int W, uint32_t* mt_state, float* areas_host, int32_t* to_remove_host,
+                                           int32_t* clipped_out) {
+  return remove_clouds_impl(ctx, tiles_host, probs_host, pfcps_host, n, H, W, mt_state, areas_host, to_remove_host, nullptr, 1, clipped_out);
 }

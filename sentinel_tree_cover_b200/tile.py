@@ -248,7 +248,8 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
         interp = _api.id_areas_to_interp(sentinel2, cloudshad, cloudshad, image_dates, fcps, sess)   # :917
         if not (isinstance(sentinel2, np.ndarray) and sentinel2.dtype == np.float32 and sentinel2.flags.c_contiguous):
             sentinel2 = np.ascontiguousarray(sentinel2, np.float32)
-        _, interp, to_remove = _api.remove_cloud_and_shadows(sentinel2, cloudshad, cloudshad, image_dates, fcps, None, sess=sess)
+        _, interp, to_remove, clipped = _api.remove_cloud_and_shadows(sentinel2, cloudshad, cloudshad, image_dates, fcps, None, sess=sess,
+                                                                      clip_when_all_kept=True)
         _mark("remove_cloud_and_shadows")
         if len(to_remove) > 0:                                                            # :972-990
             clouds = np.delete(clouds, to_remove, axis=0)
@@ -260,11 +261,13 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
             cloudshad, fcps = masks(False)
             interp = _api.id_areas_to_interp(sentinel2, cloudshad, cloudshad, image_dates, fcps, sess)
     else:
+        clipped = False
         interp = np.zeros((sentinel2.shape[0], sentinel2.shape[1], sentinel2.shape[2]), dtype=np.float32)
         cloudshad = np.zeros((sentinel2.shape[0], sentinel2.shape[1], sentinel2.shape[2]), dtype=np.float32)
 
     dem = divide(dem, 90, sess)                                                           # :995
-    sentinel2 = clip01(sentinel2, sess)                                                   # :996
+    if not clipped:                                                                       # :996 (already done on the device
+        sentinel2 = clip01(sentinel2, sess)                                               #  when remove_clouds kept all dates)
     _mark("clip + dem scale")
     return sentinel2, image_dates, interp, s1, dem, cloudshad, snow
 
