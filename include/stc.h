@@ -286,6 +286,9 @@ int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const float* probs_h
 /* Same, for process_tile: when no date has to be removed the cube is clipped to [0, 1] before it is copied back
  * (np.clip(sentinel2, 0, 1), src/download_and_predict_job.py:996, is the next statement on that path) and
  * *clipped_out = 1; otherwise the cube comes back unclipped (the masks are recomputed on it first, :972-990). */
+/* Test hook (host only, no device): Python's random.shuffle replayed on data[0..n) from the generator state mt_state
+ * (624 MT19937 words + position, `random.getstate()[1]`); the advanced state is written back. */
+int stc_py_shuffle(uint32_t* mt_state, int32_t* data, int64_t n);
 int stc_remove_clouds_clip_host(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H, int W,
                                 uint32_t* mt_state, float* areas_out_host, int32_t* to_remove_out_host, int32_t* clipped_out);
 

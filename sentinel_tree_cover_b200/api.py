@@ -113,6 +113,7 @@ SYMBOLS = [
     ("stc_postprocess_subtile_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_remove_clouds_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("stc_py_shuffle", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     ("stc_remove_clouds_clip_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     ("stc_cloud_masks_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

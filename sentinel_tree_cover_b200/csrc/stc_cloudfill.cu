@@ -962,3 +962,15 @@ extern "C" int stc_remove_clouds_clip_host(stc_ctx* ctx, float* tiles_host, cons
                                            int32_t* clipped_out) {
   return remove_clouds_impl(ctx, tiles_host, probs_host, pfcps_host, n, H, W, mt_state, areas_host, to_remove_host, nullptr, 1, clipped_out);
 }
+
+// Test hook for the host-side generator replay (no device, no context): shuffles data[0..n) exactly like Python's
+// random.shuffle would with the generator state mt_state (624 words + position), and writes the advanced state back.
+extern "C" int stc_py_shuffle(uint32_t* mt_state, int32_t* data, int64_t n) {
+  if (!mt_state || (!data && n > 0) || n < 0 || mt_state[624] > 624) return STC_ERR_ARG;
+  PyRandom rng; memcpy(rng.mt, mt_state, 624 * 4); rng.idx = (int)mt_state[624];
+  std::vector<int> v(data, data + n);
+  rng.shuffle(v);
+  if (n > 0) memcpy(data, v.data(), (size_t)n * 4);
+  memcpy(mt_state, rng.mt, 624 * 4); mt_state[624] = (uint32_t)rng.idx;
+  return STC_OK;
+}

@@ -80,3 +80,23 @@ def test_weight_broadcast_and_sharding_world2_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("OK") == 2
+
+
+def test_python_random_shuffle_replay_matches_cpython():
+    """The cloud-removal fit samples its pixels with Python's global `random` (cloud_removal.py:447-497); the library
+    replays random.shuffle from the generator state on the host (MT19937 block regeneration, branch-free rejection
+    loop).  Host-only entry point: runs without a GPU."""
+    import ctypes as C
+    import random
+    from sentinel_tree_cover_b200 import api
+    lib = api.load_library()
+    random.seed(20240917)
+    for _ in range(411):                                     # land in the middle of a 624-word block
+        random.getrandbits(32)
+    for n in (0, 1, 2, 3, 7, 1024, 1025, 65535, 65536, 65537, 200003):
+        state = np.array(random.getstate()[1], dtype=np.uint32)
+        want = list(range(n)); random.shuffle(want)
+        got = np.arange(n, dtype=np.int32)
+        rc = lib.stc_py_shuffle(state.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), n)
+        assert rc == 0 and got.tolist() == want, n
+        assert tuple(int(v) for v in state) == random.getstate()[1], n      # the generator is left where Python leaves it
