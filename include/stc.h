@@ -347,6 +347,11 @@ int64_t stc_debug_read(stc_ctx* ctx, const char* name, float* out_host);
  *      uint8 truncation, <= 15 -> 0, uncovered -> 255.  Patch (r,c) covers canvas rows r*stride+margin .. +S. ---- */
 int stc_region_gather_dev(stc_ctx* ctx, const float* canvas_dev, int T, int Hc, int Wc, int Cc, int wrap,
                           const int32_t* ys_dev, const int32_t* xs_dev, int B, int P, float* out_dev);
+/* Forward over n patch windows of the canvas (gather + fused front end + model), `batch` windows at a time with the
+ * gather of the next batch overlapped; preds_dev [n, P-14, P-14] float32.  Synchronous (returns when preds_dev is complete). */
+int stc_region_predict_dev(stc_ctx* ctx, const float* canvas_dev, int T, int Hc, int Wc, int Cc, int wrap,
+                           const int32_t* ys_dev, const int32_t* xs_dev, int n, int batch, int P,
+                           const double* min17, const double* max17, float* preds_dev);
 int stc_region_blend_dev(stc_ctx* ctx, const float* preds_dev, int r_first, int rows_have, int R, int C, int S, int stride,
                          int margin, const float* gauss_host, int y0, int y1, int Wc, uint8_t* out_host);
 

@@ -93,6 +93,58 @@ int stc_region_gather_dev(stc_ctx* ctx, const float* canvas_dev, int T, int Hc, 
   return STC_OK;      // asynchronous: the window origins live on the device, nothing to wait for
 }
 
+// Forward over n patch windows of a canvas: gather -> fused front end + model, `batch` windows at a time.  The gather
+// of batch k + 1 runs on its own stream into the second patch buffer while batch k is in the model (the gather alone
+// costs ~10 % of a batch when it is serialised with the forward).
+int stc_region_predict_dev(stc_ctx* ctx, const float* canvas_dev, int T, int Hc, int Wc, int Cc, int wrap,
+                           const int32_t* ys_dev, const int32_t* xs_dev, int n, int batch, int P,
+                           const double* min17, const double* max17, float* preds_dev) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!canvas_dev || !ys_dev || !xs_dev || !preds_dev || !min17 || !max17 || n < 1 || batch < 1 || T != 12 || Cc != 13 || P < 28 || P % 4 ||
+      (!wrap && (P > Hc || P > Wc)))
+    STC_FAIL(STC_ERR_ARG, "region_predict: bad argument (the model front end takes 12 months x 13 bands, P a multiple of 4 >= 28)");
+  if ((int64_t)batch * T > 65535) STC_FAIL(STC_ERR_ARG, "region_predict: at most 65535 patch-months per batch");
+  if (batch > n) batch = n;
+  const size_t patch_elems = (size_t)T * P * P * Cc;
+  const int S = P - 14;
+  float* buf[2] = {nullptr, nullptr};
+  cudaStream_t gs = nullptr; cudaEvent_t eg[2] = {nullptr, nullptr}, ec[2] = {nullptr, nullptr};
+  int rc = STC_OK;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    if (gs) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
+    for (int i = 0; i < 2; ++i) { if (buf[i]) cudaFree(buf[i]); if (eg[i]) cudaEventDestroy(eg[i]); if (ec[i]) cudaEventDestroy(ec[i]); }
+  };
+#define RG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return STC_ERR_CUDA; } } while (0)
+  const int nbuf = n > batch ? 2 : 1;
+  for (int i = 0; i < nbuf; ++i) RG_CUDA(cudaMalloc((void**)&buf[i], (size_t)batch * patch_elems * 4));
+  RG_CUDA(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    RG_CUDA(cudaEventCreateWithFlags(&eg[i], cudaEventDisableTiming));
+    RG_CUDA(cudaEventCreateWithFlags(&ec[i], cudaEventDisableTiming));
+  }
+  // everything already enqueued on the caller's stream (e.g. the upload of the origins) precedes the first gather
+  RG_CUDA(cudaEventRecord(ec[1], ctx->stream));
+  RG_CUDA(cudaStreamWaitEvent(gs, ec[1], 0));
+  int k = 0;
+  for (int done = 0; done < n; done += batch, ++k) {
+    const int b = (n - done) < batch ? (n - done) : batch;
+    const int s = (nbuf == 2) ? (k & 1) : 0;
+    if (k >= nbuf) RG_CUDA(cudaStreamWaitEvent(gs, ec[s], 0));            // the forward that last read this buffer is done
+    dim3 grid(P, b * T);
+    region_gather_kernel<<<grid, 256, 0, gs>>>(canvas_dev, T, Hc, Wc, Cc, wrap, ys_dev + done, xs_dev + done, P, buf[s]);
+    RG_CUDA(cudaGetLastError()); ctx->launches++;
+    RG_CUDA(cudaEventRecord(eg[s], gs));
+    RG_CUDA(cudaStreamWaitEvent(ctx->stream, eg[s], 0));
+    rc = model_predict_patches_dev(ctx, buf[s], b, P, P, min17, max17, preds_dev + (size_t)done * S * S);
+    if (rc) { cleanup(); return rc; }
+    RG_CUDA(cudaEventRecord(ec[s], ctx->stream));
+  }
+#undef RG_CUDA
+  cleanup();
+  return STC_OK;
+}
+
 int stc_region_blend_dev(stc_ctx* ctx, const float* preds_dev, int r_first, int rows_have, int R, int C, int S, int stride, int margin,
                          const float* gauss_host, int y0, int y1, int Wc, uint8_t* out_host) {
   if (!ctx) return STC_ERR_ARG;

@@ -60,29 +60,24 @@ class RegionRunner:
         n = (self.rb - self.ra) * self.C
         if n == 0:
             return 0
-        patch_bytes = T * P * P * Cc * 4
         idx = np.arange(n)
         ys = ((self.ra + idx // self.C) * self.stride - band_y0).astype(np.int32)
         xs = ((idx % self.C) * self.stride).astype(np.int32)
         if not wrap and (ys.min() < 0 or xs.min() < 0 or ys.max() + P > Hband or xs.max() + P > Wband):
             raise ValueError("region: a patch window leaves the canvas band")
-        # window origins of ALL batches go to the device once, so the per-batch calls are asynchronous and the host
-        # runs ahead of the GPU (a host hiccup between batches would otherwise idle the device)
+        # window origins of ALL batches go to the device once, so the batches are enqueued back to back and the host runs
+        # ahead of the GPU (a host hiccup between batches would otherwise idle the device)
         coords = np.ascontiguousarray(np.concatenate([ys, xs]))
         d_xy = sess.malloc(coords.nbytes)
-        buf = sess.malloc(min(self.batch, n) * patch_bytes)
         try:
             sess.h2d(d_xy, coords)
-            done = 0
-            while done < n:
-                b = min(self.batch, n - done)
-                sess._check(sess.lib.stc_region_gather_dev(sess.h, _dev(canvas_dev), T, Hband, Wband, Cc, int(bool(wrap)),
-                                                           _dev(d_xy, done * 4), _dev(d_xy, (n + done) * 4), b, P, buf))
-                sess.predict_patches_dev(buf, b, P, P, _dev(preds_dev, done * S * S * 4))
-                done += b
-            sess.sync()
+            mn, mnp = _api._f64(sess.min_all)
+            mx, mxp = _api._f64(sess.max_all)
+            # one call: per batch a gather on a side stream (overlapping the previous batch's forward) + the forward
+            sess._check(sess.lib.stc_region_predict_dev(sess.h, _dev(canvas_dev), T, Hband, Wband, Cc, int(bool(wrap)),
+                                                        _dev(d_xy), _dev(d_xy, n * 4), n, self.batch, P, mnp, mxp, _dev(preds_dev)))
         finally:
-            sess.free(buf); sess.free(d_xy)
+            sess.free(d_xy)
         return n
 
     # ---- blend of the owned canvas rows -------------------------------------------------------
