@@ -143,6 +143,8 @@ int stc_temporal_median_host(stc_ctx* ctx, const float* in_host, int n, int64_t 
  *      bilinear [N,H,W,6] -> out [N,H,W,6] = pb:Add_2 -------------------- */
 int stc_superresolve_host(stc_ctx* ctx, const float* x_host, const float* bilinear_host,
                           int N, int H, int W, float* out_host);
+/* Device-resident variant (x_dev [N,H,W,10], out_dev [N,H,W,6]; bilinear_dev may be NULL = x[..., 4:]); asynchronous. */
+int stc_superresolve_dev(stc_ctx* ctx, const float* x_dev, const float* bilinear_dev, int N, int H, int W, float* out_dev);
 
 /* ---- Gaussian overlap-blend mosaic, load_mosaic_predictions depth == 1
  *      (src/download_and_predict_job.py:1515-1641).  preds [n,S,S]: subtile predictions as

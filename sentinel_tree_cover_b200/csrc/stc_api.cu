@@ -358,6 +358,12 @@ int stc_temporal_median_host(stc_ctx* ctx, const float* in_host, int n, int64_t 
   return STC_OK;
 }
 
+int stc_superresolve_dev(stc_ctx* ctx, const float* x_dev, const float* bilinear_dev, int N, int H, int W, float* out_dev) {
+  CTX_CHECK();
+  if (!x_dev || !out_dev) STC_FAIL(STC_ERR_ARG, "superresolve: bad argument");
+  return sr_forward_dev(ctx, x_dev, bilinear_dev, N, H, W, out_dev);     // bilinear_dev == NULL: bands 4..9 of x
+}
+
 int stc_superresolve_host(stc_ctx* ctx, const float* x_host, const float* bilinear_host, int N, int H, int W, float* out_host) {
   CTX_CHECK();
   if (!x_host || !out_host) STC_FAIL(STC_ERR_ARG, "superresolve: bad argument");
