@@ -5,7 +5,7 @@ capped at 3072 images).  Per line: ms per call (CUDA events), SURVEY 8d algorith
 measured HBM peak; the super-resolution line also gives TFLOP/s (it is the tensor-bound one: 82,944 FLOP per pixel).
 The cloud pipeline (masks / removal) works on one tile of n dates at a time and has no batch axis: tools/bench_preproc.py.
 Usage (GPU box): python tools/bench_sweep.py [--max 4096]"""
-import argparse, json, os, sys
+import argparse, ctypes, json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
@@ -48,10 +48,10 @@ def main():
             inner = 0
         d_in = sess.malloc(max(24 * inner * 4, 16)); d_out = sess.malloc(max(12 * inner * 4, 16))
         if inner:
-          ms = timed(lambda: sess._check(sess.lib.stc_temporal_matmul_dev(sess.h, d_in, M.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_float)), 24, 12, inner, d_out)), reps)
-          by = (24 + 12) * inner * 4
-          print(json.dumps({"kernel": "K1 regrid+Whittaker+monthly (12x24 operator)", "B": B, "ms": round(ms, 4), "algorithmic_MB": round(by / 1e6, 1),
-                            "GBps": round(by / ms / 1e6, 1), "frac_hbm": round(by / ms / 1e6 / peak, 3)}), flush=True)
+            ms = timed(lambda: sess._check(sess.lib.stc_temporal_matmul_dev(sess.h, d_in, M.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 24, 12, inner, d_out)), reps)
+            by = (24 + 12) * inner * 4
+            print(json.dumps({"kernel": "K1 regrid+Whittaker+monthly (12x24 operator)", "B": B, "ms": round(ms, 4), "algorithmic_MB": round(by / 1e6, 1),
+                              "GBps": round(by / ms / 1e6, 1), "frac_hbm": round(by / ms / 1e6 / peak, 3)}), flush=True)
         sess.free(d_in); sess.free(d_out)
         # ---- assemble: [B,12,H,W,13] -> [B,5,H,W,17]
         if B * px * (12 * 13 + 5 * 17) * 4 > LIMIT:
@@ -69,7 +69,7 @@ def main():
         d_in = sess.malloc(N * px * 40); d_out = sess.malloc(N * px * 24)
         for k in range(0, N, x.shape[0]):
             n = min(x.shape[0], N - k)
-            sess.h2d(__import__("ctypes").c_void_p(d_in.value + k * px * 40), x[:n])
+            sess.h2d(ctypes.c_void_p(d_in.value + k * px * 40), x[:n])
         sess.sync()
         ms = timed(lambda: sess._check(sess.lib.stc_superresolve_dev(sess.h, d_in, None, N, H, H, d_out)), max(2, reps // 2))
         by = N * px * (40 + 24)
