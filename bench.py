@@ -255,7 +255,7 @@ def main():
     from sentinel_tree_cover_b200.api import StcSession
     from sentinel_tree_cover_b200.weights import random_predict_weights
     from sentinel_tree_cover_b200.shard import broadcast_weights
-    from oracle import preproc_ref as P   # synthetic-input generator + cpu_baseline only
+    from sentinel_tree_cover_b200 import synth as P   # seeded synthetic patches
 
     w = random_predict_weights(0) if rank == 0 else None
     if world > 1:

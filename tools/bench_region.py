@@ -41,7 +41,7 @@ def main():
     from sentinel_tree_cover_b200.weights import random_predict_weights
     from sentinel_tree_cover_b200.shard import broadcast_weights
     from sentinel_tree_cover_b200 import region
-    from oracle import preproc_ref as P          # synthetic-input generator (and --verify)
+    from sentinel_tree_cover_b200 import synth as P
     w = random_predict_weights(0) if rank == 0 else None
     if world > 1:
         w = broadcast_weights(w, dist, device=torch.device("cuda", local))

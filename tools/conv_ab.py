@@ -28,7 +28,7 @@ def main():
     a = ap.parse_args()
     from sentinel_tree_cover_b200.api import StcSession
     from sentinel_tree_cover_b200.weights import random_predict_weights
-    from oracle import preproc_ref as P   # synthetic-input generator only
+    from sentinel_tree_cover_b200 import synth as P
     H = 168
     sess = StcSession(0, predict_weights=random_predict_weights(0))
     base = P.synth_monthly(8, H, 2000)
