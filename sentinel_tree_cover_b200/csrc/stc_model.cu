@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256) gru_apply1_kernel(GruParams p) {
 }
 
 // u = sigmoid(GN(g_u)); h~ = u*h + (1-u)*tanh(GN(y)); h = 0.75 h + 0.25 h~ (zoneout, inference)
-__global__ void __launch_bounds__(256) gru_apply2_kernel(GruParams p) {
+__global__ void __launch_bounds__(256, 3) gru_apply2_kernel(GruParams p) {
   const int d = blockIdx.z, b = blockIdx.y;
   __shared__ float ua[32], ub[32], ya[32], yb[32];
   if (threadIdx.x < 32) {
