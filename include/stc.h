@@ -247,6 +247,14 @@ int stc_process_subtiles_host(stc_ctx* ctx, const float* s2q_host, const float* 
                               const int32_t* windows_host, int S, int T, int length, int force_no_data,
                               const double* min17, const double* max17, float* out_host, int32_t* no_data_host);
 
+/* Same with the two --gen_feats taps of the forward (stc_predict_feats_host) for every subtile: early / late
+ * [nt,S,S,64] float32 (src/download_and_predict_job.py:1429-1431). */
+int stc_process_subtiles_feats_host(stc_ctx* ctx, const float* s2q_host, const float* s1q_host, const float* s2med_host,
+                                    const float* s1med_host, const float* dem_host, const int32_t* clear_host, int H, int W, int nt,
+                                    const int32_t* windows_host, int S, int T, int length, int force_no_data,
+                                    const double* min17, const double* max17, float* out_host, int32_t* no_data_host,
+                                    float* early_host, float* late_host);
+
 /* ---- storage codecs and the Sentinel-1 dB transform.
  *      to_float32 (src/tof/tof_downloading.py:64-72): uint16 -> x/65535 float32;
  *      to_int16 (:51-61): trunc(clip(x,0,1)*65535) -> uint16;
@@ -332,6 +340,41 @@ int stc_build_sentinel2_host(stc_ctx* ctx, const float* s2_10_host, const float*
  *      5 +brightness/whiteness, 6 after false-positive removal, 7 after shape clean-up, 8 before haze). ---- */
 int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const float* dem_host, int T, int H, int W,
                          float* clouds_host, uint8_t* fcps_host, uint8_t* stage_host, int stage_id);
+
+/* ---- one whole tile, device-resident: the body of the reference's main loop
+ *      (src/download_and_predict_job.py:1995-2020)  process_tile (:640-997, make_shadow) -> superresolve_large_tile
+ *      (:95-147) -> process_subtiles (:1125-1486, prediction path, length 4) -> load_mosaic_predictions (:1515-1641)
+ *      in ONE call: the raw cubes are uploaded once, the uint8 tile is downloaded once, every intermediate stays in
+ *      pooled device memory and only per-date scalars / integers reach the host, where the reference's control flow on
+ *      scalars is replayed (date screening, retry loops, the regrid / Whittaker operator of the surviving dates, window
+ *      table, mosaic multipliers).  Same device code as the per-stage entry points above.
+ *      s2_10 [n,h10,w10,4], s2_20 [n,h20,w20,6], s1 [12,hs,ws,2] uint16 as stored in raw/s2_10, raw/s2_20, raw/s1
+ *      (x / 65535); dem [hd,wd] float32 (raw/misc/dem); clm [n,h20,w20] uint8 Sen2Cor mask (raw/clouds/cloudmask) or
+ *      NULL; dates [n] day-of-year of the Sentinel-2 images (raw/misc/s2_dates).  Shapes are aligned to (2*h20, 2*w20)
+ *      like adjust_shape (:260-310).  mt_state: Python's MT19937 state (see stc_remove_clouds_host), advanced in place.
+ *      gauss: float32 [size,size] fspecial_gauss(size, 36) (:1489) or NULL (computed here).
+ *      out [out_h,out_w] uint8 with out_h = 2*w20, out_w = 2*h20 (the mosaic's axes are the file axes y, x; :1515-1641);
+ *      layers are blended in ascending (x, y) order (the reference uses its os.listdir order).
+ *      dates_kept [n] / n_kept: the image dates that survived; subtile_preds [nt,size,size] float32 (optional) = the
+ *      per-subtile arrays process_subtiles would have saved, in window-table order (nt = 36).
+ *      Situations in which the reference raises return STC_ERR_STATE with the cause in stc_last_error. ---- */
+int stc_tile_run_host(stc_ctx* ctx, const uint16_t* s2_10_host, int n, int h10, int w10, const uint16_t* s2_20_host, int h20,
+                      int w20, const uint16_t* s1_host, int m1, int hs, int ws, const float* dem_host, int hd, int wd,
+                      const uint8_t* clm_host, const int32_t* dates_host, uint32_t* mt_state, int make_shadow, int superresolve,
+                      int size, int length, const double* min17, const double* max17, const float* gauss_host,
+                      uint8_t* out_host, int out_h, int out_w, int32_t* dates_kept_host, int32_t* n_kept_host,
+                      float* subtile_preds_host);
+/* Host-logic hooks of the tile chain (no device, no context; used by the CPU tests to hold the C++ date / window logic
+ * against the NumPy mirrors regrid.py / windows.py, which are pinned to the reference):
+ *   stc_monthly_operator_plan: G [24,n] = calculate_and_save_best_images weights (src/downloading/utils.py:176-347),
+ *                              M [12,n] = pair-mean . Whittaker . G (whittaker_smoother.py:10-69); either may be NULL.
+ *   stc_subtile_windows_plan : the window tables of process_subtiles (:1295-1317); returns the number of subtiles.
+ *   stc_adjust_shape_plan    : adjust_shape (:260-310) for one axis as out[i] = in[clamp(i + shift, 0, len - 1)]. */
+int stc_monthly_operator_plan(const int32_t* dates, int n, float* G_out, float* M_out);
+int stc_subtile_windows_plan(int Lx, int Ly, int size, int n_rows, int32_t* folder_out, int32_t* array_out, int cap);
+int stc_adjust_shape_plan(int len, int target, int32_t* shift_out, int32_t* out_len);
+/* Device-memory pool statistics (scratch buffers of all entry points are recycled, not cudaMalloc'd per call). */
+int stc_pool_info(stc_ctx* ctx, int64_t* hits, int64_t* misses, int64_t* cached_bytes, int64_t* total_bytes);
 
 /* ---- debug: copy an internal activation buffer of the last stc_predict_*
  *      call to the host as float32 NHWC (interior only).  Names: "ccin",

@@ -109,6 +109,9 @@ SYMBOLS = [
     ("stc_process_subtiles_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p,
                                             C.c_void_p, C.c_void_p]),
+    ("stc_process_subtiles_feats_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("stc_np_sum_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("stc_normalize_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     ("stc_bright_bare_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -121,6 +124,14 @@ SYMBOLS = [
     ("stc_cloud_masks_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int]),
     ("stc_debug_read", C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p]),
+    ("stc_tile_run_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, _f64p, _f64p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    ("stc_monthly_operator_plan", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("stc_subtile_windows_plan", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    ("stc_adjust_shape_plan", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("stc_pool_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 ]
 
 
@@ -565,6 +576,51 @@ class StcSession:
                                                     _dptr(rem), _dptr(mosaic) if want_mosaic else None))
         out = (areas, [int(i) for i in np.flatnonzero(rem)])
         return out + (mosaic,) if want_mosaic else out
+
+    def run_tile(self, s2_10, s2_20, s1, dem, dates, clm=None, make_shadow=True, superresolve=True, size=158, length=4,
+                 return_subtiles=False):
+        """One whole tile on the device (stc_tile_run_host): raw uint16 cubes -> uint8 tree-cover tile, the body of the
+        reference's main loop (src/download_and_predict_job.py:1995-2020).  s2_10 [n,h10,w10,4], s2_20 [n,h20,w20,6],
+        s1 [12,hs,ws,2] uint16 as stored under raw/; dem float32; dates [n] int; clm optional uint8 [n,h20,w20].
+        Python's global `random` state is handed to the library and advanced, as in remove_cloud_and_shadows.
+        Returns (tile uint8 [2*w20, 2*h20], dates_kept[, subtile predictions [36,size,size]])."""
+        import random
+        a10 = np.ascontiguousarray(s2_10, np.uint16); a20 = np.ascontiguousarray(s2_20, np.uint16)
+        a1 = np.ascontiguousarray(s1, np.uint16); d = np.ascontiguousarray(dem, np.float32)
+        dt = np.ascontiguousarray(dates, np.int32)
+        n, h10, w10, c4 = a10.shape
+        n2, h20, w20, c6 = a20.shape
+        m1, hs, ws, c2 = a1.shape
+        if c4 != 4 or c6 != 6 or c2 != 2 or n2 != n or dt.shape != (n,) or d.ndim != 2:
+            raise ValueError("run_tile: shapes %r / %r / %r / %r / %r" % (a10.shape, a20.shape, a1.shape, d.shape, dt.shape))
+        cm = None
+        if clm is not None:
+            cm = np.ascontiguousarray(clm, np.uint8)
+            if cm.shape != (n, h20, w20):
+                raise ValueError("run_tile: Sen2Cor mask %r is not (n, h20, w20)" % (cm.shape,))
+        version, internal, gaussian = random.getstate()
+        state = np.array(internal, dtype=np.uint32)
+        out = np.empty((2 * w20, 2 * h20), np.uint8)
+        kept = np.zeros(n, np.int32)
+        nk = C.c_int32(0)
+        gauss = np.ascontiguousarray(fspecial_gauss(size, 36), np.float32)
+        nt = 36 if size != 222 else 49
+        sub = np.empty((nt, size, size), np.float32) if return_subtiles else None
+        mn, mnp = _f64(self.min_all)
+        mx, mxp = _f64(self.max_all)
+        rc = self.lib.stc_tile_run_host(self.h, _dptr(a10), n, h10, w10, _dptr(a20), h20, w20, _dptr(a1), m1, hs, ws, _dptr(d), d.shape[0],
+                                        d.shape[1], _dptr(cm) if cm is not None else None, _dptr(dt), _dptr(state), int(bool(make_shadow)),
+                                        int(bool(superresolve)), int(size), int(length), mnp, mxp, _dptr(gauss), _dptr(out), out.shape[0],
+                                        out.shape[1], _dptr(kept), C.byref(nk), _dptr(sub) if return_subtiles else None)
+        random.setstate((version, tuple(int(v) for v in state), gaussian))      # the generator advanced even if a later stage failed
+        self._check(rc)
+        kept = kept[:nk.value].copy()
+        return (out, kept, sub) if return_subtiles else (out, kept)
+
+    def pool_info(self):
+        v = [C.c_int64() for _ in range(4)]
+        self._check(self.lib.stc_pool_info(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("hits", "misses", "cached_bytes", "total_bytes"), [x.value for x in v]))
 
     def mosaic(self, preds, xs, ys, out_shape, sigma=36):
         """Gaussian overlap blend of subtile predictions (list/array [n,S,S], the arrays as

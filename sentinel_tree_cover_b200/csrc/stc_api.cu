@@ -47,6 +47,7 @@ void stc_destroy(stc_ctx* ctx) {
     for (int j = 0; j < 2; ++j) if (ctx->ev_lane[i][j]) cudaEventDestroy(ctx->ev_lane[i][j]);
   }
   cudaStreamDestroy(ctx->stream);
+  stc_pool_trim();
   delete ctx;
 }
 
@@ -148,7 +149,7 @@ int stc_trace(stc_ctx* ctx, int enable, const char* csv_path) {
 // ---- helpers for host-buffer variants ------------------------------------------------
 struct DevBuf {
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { if (p) stc_dfree(p); }
 };
 
 int stc_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int W, int length,
@@ -163,7 +164,7 @@ int stc_predict_host(stc_ctx* ctx, const float* x_host, int B, int T, int H, int
   if (!x_host || !out_host || B < 1) STC_FAIL(STC_ERR_ARG, "predict: bad argument");
   size_t nin = (size_t)B * (T + 1) * H * W * 17, nout = (size_t)B * (H - 14) * (W - 14);
   DevBuf din, dout;
-  STC_CUDA(cudaMalloc(&din.p, nin * 4)); STC_CUDA(cudaMalloc(&dout.p, nout * 4));
+  STC_CUDA(stc_dmalloc(&din.p, nin * 4)); STC_CUDA(stc_dmalloc(&dout.p, nout * 4));
   STC_CUDA(cudaMemcpyAsync(din.p, x_host, nin * 4, cudaMemcpyHostToDevice, ctx->stream));
   int rc = model_predict_dev(ctx, (const float*)din.p, B, T, H, W, length, normalize, min17, max17, (float*)dout.p);
   if (rc) return rc;
@@ -179,8 +180,8 @@ int stc_predict_feats_host(stc_ctx* ctx, const float* x_host, int B, int T, int 
   if (!x_host || !early_host || !late_host || B < 1) STC_FAIL(STC_ERR_ARG, "predict_feats: bad argument");
   size_t nin = (size_t)B * (T + 1) * H * W * 17, nout = (size_t)B * (H - 14) * (W - 14);
   DevBuf din, dout, de, dl;
-  STC_CUDA(cudaMalloc(&din.p, nin * 4)); STC_CUDA(cudaMalloc(&dout.p, nout * 4));
-  STC_CUDA(cudaMalloc(&de.p, nout * 64 * 4)); STC_CUDA(cudaMalloc(&dl.p, nout * 64 * 4));
+  STC_CUDA(stc_dmalloc(&din.p, nin * 4)); STC_CUDA(stc_dmalloc(&dout.p, nout * 4));
+  STC_CUDA(stc_dmalloc(&de.p, nout * 64 * 4)); STC_CUDA(stc_dmalloc(&dl.p, nout * 64 * 4));
   STC_CUDA(cudaMemcpyAsync(din.p, x_host, nin * 4, cudaMemcpyHostToDevice, ctx->stream));
   ctx->feat_early_dev = (float*)de.p; ctx->feat_late_dev = (float*)dl.p;
   int rc = model_predict_dev(ctx, (const float*)din.p, B, T, H, W, length, normalize, min17, max17, (float*)dout.p);
@@ -202,7 +203,7 @@ int stc_assemble_host(stc_ctx* ctx, const float* monthly_host, int B, int H, int
   CTX_CHECK();
   size_t nin = (size_t)B * 12 * H * W * 13, nout = (size_t)B * 5 * H * W * 17;
   DevBuf din, dout;
-  STC_CUDA(cudaMalloc(&din.p, nin * 4)); STC_CUDA(cudaMalloc(&dout.p, nout * 4));
+  STC_CUDA(stc_dmalloc(&din.p, nin * 4)); STC_CUDA(stc_dmalloc(&dout.p, nout * 4));
   STC_CUDA(cudaMemcpyAsync(din.p, monthly_host, nin * 4, cudaMemcpyHostToDevice, ctx->stream));
   int rc = pre_assemble_dev(ctx, (const float*)din.p, B, H, W, (float*)dout.p);
   if (rc) return rc;
@@ -216,6 +217,7 @@ int stc_assemble_host(stc_ctx* ctx, const float* monthly_host, int B, int H, int
 static int predict_patches_core(stc_ctx* ctx, const float* monthly, bool host_in, int B, int H, int W,
                                 const double* min17, const double* max17, float* out, bool host_out) {
   if (B < 1 || !monthly || !out || !min17 || !max17) STC_FAIL(STC_ERR_ARG, "predict_patches: bad argument");
+  if (H != W || H % 4 != 0 || H < 28) STC_FAIL(STC_ERR_ARG, "predict_patches: patches must be square, H a multiple of 4 and >= 28");
   const size_t esz = ctx->monthly_u16 ? 2 : 4;      // element size of the monthly patches
   size_t per_in = (size_t)12 * H * W * 13, per_out = (size_t)(H - 14) * (W - 14);
   if (!host_in && !host_out) return model_predict_patches_dev(ctx, monthly, B, H, W, min17, max17, out);
@@ -323,7 +325,7 @@ int stc_temporal_matmul_host(stc_ctx* ctx, const float* in_host, const float* M_
   CTX_CHECK();
   if (!in_host || !M_host || !out_host || inner < 1) STC_FAIL(STC_ERR_ARG, "temporal_matmul: bad argument");
   DevBuf din, dout;
-  STC_CUDA(cudaMalloc(&din.p, (size_t)n_in * inner * 4)); STC_CUDA(cudaMalloc(&dout.p, (size_t)n_out * inner * 4));
+  STC_CUDA(stc_dmalloc(&din.p, (size_t)n_in * inner * 4)); STC_CUDA(stc_dmalloc(&dout.p, (size_t)n_out * inner * 4));
   STC_CUDA(cudaMemcpyAsync(din.p, in_host, (size_t)n_in * inner * 4, cudaMemcpyHostToDevice, ctx->stream));
   int rc = pre_temporal_matmul_dev(ctx, (const float*)din.p, M_host, n_in, n_out, inner, (float*)dout.p);
   if (rc) return rc;
@@ -336,7 +338,7 @@ int stc_indices_host(stc_ctx* ctx, const float* in_host, int64_t npix, int C, fl
   CTX_CHECK();
   if (!in_host || !out_host || npix < 1) STC_FAIL(STC_ERR_ARG, "indices: bad argument");
   DevBuf din, dout;
-  STC_CUDA(cudaMalloc(&din.p, (size_t)npix * C * 4)); STC_CUDA(cudaMalloc(&dout.p, (size_t)npix * 16));
+  STC_CUDA(stc_dmalloc(&din.p, (size_t)npix * C * 4)); STC_CUDA(stc_dmalloc(&dout.p, (size_t)npix * 16));
   STC_CUDA(cudaMemcpyAsync(din.p, in_host, (size_t)npix * C * 4, cudaMemcpyHostToDevice, ctx->stream));
   int rc = pre_indices_dev(ctx, (const float*)din.p, npix, C, (float*)dout.p);
   if (rc) return rc;
@@ -349,7 +351,7 @@ int stc_temporal_median_host(stc_ctx* ctx, const float* in_host, int n, int64_t 
   CTX_CHECK();
   if (!in_host || !out_host || inner < 1) STC_FAIL(STC_ERR_ARG, "temporal_median: bad argument");
   DevBuf din, dout;
-  STC_CUDA(cudaMalloc(&din.p, (size_t)n * inner * 4)); STC_CUDA(cudaMalloc(&dout.p, (size_t)inner * 4));
+  STC_CUDA(stc_dmalloc(&din.p, (size_t)n * inner * 4)); STC_CUDA(stc_dmalloc(&dout.p, (size_t)inner * 4));
   STC_CUDA(cudaMemcpyAsync(din.p, in_host, (size_t)n * inner * 4, cudaMemcpyHostToDevice, ctx->stream));
   int rc = pre_temporal_median_dev(ctx, (const float*)din.p, n, inner, (float*)dout.p);
   if (rc) return rc;
@@ -369,10 +371,10 @@ int stc_superresolve_host(stc_ctx* ctx, const float* x_host, const float* biline
   if (!x_host || !out_host) STC_FAIL(STC_ERR_ARG, "superresolve: bad argument");
   size_t npx = (size_t)N * H * W;
   DevBuf dx, db, dout;
-  STC_CUDA(cudaMalloc(&dx.p, npx * 40)); STC_CUDA(cudaMalloc(&dout.p, npx * 24));
+  STC_CUDA(stc_dmalloc(&dx.p, npx * 40)); STC_CUDA(stc_dmalloc(&dout.p, npx * 24));
   STC_CUDA(cudaMemcpyAsync(dx.p, x_host, npx * 40, cudaMemcpyHostToDevice, ctx->stream));
   if (bilinear_host) {          // NULL: the bilinear input is x[..., 4:] (superresolve_large_tile), no second upload
-    STC_CUDA(cudaMalloc(&db.p, npx * 24));
+    STC_CUDA(stc_dmalloc(&db.p, npx * 24));
     STC_CUDA(cudaMemcpyAsync(db.p, bilinear_host, npx * 24, cudaMemcpyHostToDevice, ctx->stream));
   }
   int rc = sr_forward_dev(ctx, (const float*)dx.p, (const float*)db.p, N, H, W, (float*)dout.p);
@@ -386,7 +388,7 @@ int stc_superresolve_host(stc_ctx* ctx, const float* x_host, const float* biline
 static int mosaic_upload(stc_ctx* ctx, const float* preds, const int32_t* xs, const int32_t* ys, const int32_t* placed,
                          int n, int S, DevBuf& dp, DevBuf& dx, DevBuf& dy, DevBuf& dpl) {
   size_t np_ = (size_t)n * S * S * 4;
-  STC_CUDA(cudaMalloc(&dp.p, np_)); STC_CUDA(cudaMalloc(&dx.p, n * 4)); STC_CUDA(cudaMalloc(&dy.p, n * 4)); STC_CUDA(cudaMalloc(&dpl.p, n * 4));
+  STC_CUDA(stc_dmalloc(&dp.p, np_)); STC_CUDA(stc_dmalloc(&dx.p, n * 4)); STC_CUDA(stc_dmalloc(&dy.p, n * 4)); STC_CUDA(stc_dmalloc(&dpl.p, n * 4));
   STC_CUDA(cudaMemcpyAsync(dp.p, preds, np_, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(dx.p, xs, n * 4, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(dy.p, ys, n * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -401,7 +403,7 @@ int stc_mosaic_diffs_host(stc_ctx* ctx, const float* preds_host, const int32_t* 
   DevBuf dp, dx, dy, dpl, dr;
   int rc = mosaic_upload(ctx, preds_host, xs, ys, placed, n, S, dp, dx, dy, dpl); if (rc) return rc;
   size_t bytes = (size_t)n * S * S * 4;
-  STC_CUDA(cudaMalloc(&dr.p, bytes));
+  STC_CUDA(stc_dmalloc(&dr.p, bytes));
   rc = pre_gauss_mosaic_dev(ctx, (const float*)dp.p, (const int*)dx.p, (const int*)dy.p, (const int*)dpl.p, nullptr, nullptr,
                             (float*)dr.p, 0, n, S, 0, 0, nullptr, nullptr);
   if (rc) return rc;
@@ -417,8 +419,8 @@ int stc_gauss_mosaic_host(stc_ctx* ctx, const float* preds_host, const int32_t* 
     STC_FAIL(STC_ERR_ARG, "gauss_mosaic: bad argument");
   DevBuf dp, dx, dy, dpl, dg, dm, dt, dout;
   int rc = mosaic_upload(ctx, preds_host, xs, ys, placed, n, S, dp, dx, dy, dpl); if (rc) return rc;
-  STC_CUDA(cudaMalloc(&dg.p, (size_t)S * S * 4)); STC_CUDA(cudaMalloc(&dm.p, n * 4));
-  STC_CUDA(cudaMalloc(&dt.p, (size_t)out_h * out_w)); STC_CUDA(cudaMalloc(&dout.p, (size_t)out_h * out_w));
+  STC_CUDA(stc_dmalloc(&dg.p, (size_t)S * S * 4)); STC_CUDA(stc_dmalloc(&dm.p, n * 4));
+  STC_CUDA(stc_dmalloc(&dt.p, (size_t)out_h * out_w)); STC_CUDA(stc_dmalloc(&dout.p, (size_t)out_h * out_w));
   STC_CUDA(cudaMemcpyAsync(dg.p, gauss_host, (size_t)S * S * 4, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(dm.p, mult_host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
   rc = pre_gauss_mosaic_dev(ctx, (const float*)dp.p, (const int*)dx.p, (const int*)dy.p, (const int*)dpl.p, (const float*)dg.p,
@@ -436,8 +438,8 @@ int stc_feature_mosaic_host(stc_ctx* ctx, const int16_t* feats_host, const int32
     STC_FAIL(STC_ERR_ARG, "feature_mosaic: bad argument");
   DevBuf df, dx, dy, dg, dout;
   const size_t nf = (size_t)n * S * S * D, no = (size_t)D * out_h * out_w;
-  STC_CUDA(cudaMalloc(&df.p, nf * 2)); STC_CUDA(cudaMalloc(&dx.p, n * 4)); STC_CUDA(cudaMalloc(&dy.p, n * 4));
-  STC_CUDA(cudaMalloc(&dg.p, (size_t)S * S * 4)); STC_CUDA(cudaMalloc(&dout.p, no * 2));
+  STC_CUDA(stc_dmalloc(&df.p, nf * 2)); STC_CUDA(stc_dmalloc(&dx.p, n * 4)); STC_CUDA(stc_dmalloc(&dy.p, n * 4));
+  STC_CUDA(stc_dmalloc(&dg.p, (size_t)S * S * 4)); STC_CUDA(stc_dmalloc(&dout.p, no * 2));
   STC_CUDA(cudaMemcpyAsync(df.p, feats_host, nf * 2, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(dx.p, xs, n * 4, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(dy.p, ys, n * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -446,6 +448,15 @@ int stc_feature_mosaic_host(stc_ctx* ctx, const int16_t* feats_host, const int32
   if (rc) return rc;
   STC_CUDA(cudaMemcpyAsync(out_host, dout.p, no * 2, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+int stc_pool_info(stc_ctx* ctx, int64_t* hits, int64_t* misses, int64_t* cached_bytes, int64_t* total_bytes) {
+  CTX_CHECK();
+  size_t c = 0, t = 0;
+  stc_pool_stats(hits, misses, &c, &t);
+  if (cached_bytes) *cached_bytes = (int64_t)c;
+  if (total_bytes) *total_bytes = (int64_t)t;
   return STC_OK;
 }
 

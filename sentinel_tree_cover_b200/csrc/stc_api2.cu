@@ -5,7 +5,7 @@ int pre_edt_sq_dev(stc_ctx* ctx, const unsigned char* target_dev, int n, int H, 
 namespace {
 struct DevBuf2 {
   void* p = nullptr;
-  ~DevBuf2() { if (p) cudaFree(p); }
+  ~DevBuf2() { if (p) stc_dfree(p); }
 };
 }
 
@@ -16,8 +16,8 @@ int stc_feather_host(stc_ctx* ctx, const float* masks_host, int n, int H, int W,
   if (!masks_host || !out_host || n < 1 || H < 1 || W < 1) STC_FAIL(STC_ERR_ARG, "feather: bad argument");
   size_t bytes = (size_t)n * H * W * 4;
   DevBuf2 din, da, db, ds, dout;
-  STC_CUDA(cudaMalloc(&din.p, bytes)); STC_CUDA(cudaMalloc(&da.p, bytes)); STC_CUDA(cudaMalloc(&db.p, bytes));
-  STC_CUDA(cudaMalloc(&ds.p, n * 4)); STC_CUDA(cudaMalloc(&dout.p, bytes));
+  STC_CUDA(stc_dmalloc(&din.p, bytes)); STC_CUDA(stc_dmalloc(&da.p, bytes)); STC_CUDA(stc_dmalloc(&db.p, bytes));
+  STC_CUDA(stc_dmalloc(&ds.p, n * 4)); STC_CUDA(stc_dmalloc(&dout.p, bytes));
   STC_CUDA(cudaMemcpyAsync(din.p, masks_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   int rc = pre_feather_dev(ctx, (const float*)din.p, n, H, W, closing_size, (float*)da.p, (float*)db.p, (float*)ds.p, (float*)dout.p);
   if (rc) return rc;
@@ -32,7 +32,7 @@ int stc_binary_dilate_host(stc_ctx* ctx, const uint8_t* in_host, int n, int H, i
   if (!in_host || !out_host || n < 1 || H < 1 || W < 1) STC_FAIL(STC_ERR_ARG, "binary_dilate: bad argument");
   size_t bytes = (size_t)n * H * W;
   DevBuf2 din, dout;
-  STC_CUDA(cudaMalloc(&din.p, bytes)); STC_CUDA(cudaMalloc(&dout.p, bytes));
+  STC_CUDA(stc_dmalloc(&din.p, bytes)); STC_CUDA(stc_dmalloc(&dout.p, bytes));
   STC_CUDA(cudaMemcpyAsync(din.p, in_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   int rc = pre_binary_dilate_dev(ctx, (const unsigned char*)din.p, n, H, W, iterations, connectivity, (unsigned char*)dout.p);
   if (rc) return rc;
@@ -46,7 +46,7 @@ int stc_edt_sq_host(stc_ctx* ctx, const uint8_t* target_host, int n, int H, int 
   if (!target_host || !out_host || n < 1 || H < 1 || W < 1) STC_FAIL(STC_ERR_ARG, "edt_sq: bad argument");
   size_t px = (size_t)n * H * W;
   DevBuf2 din, dout;
-  STC_CUDA(cudaMalloc(&din.p, px)); STC_CUDA(cudaMalloc(&dout.p, px * 4));
+  STC_CUDA(stc_dmalloc(&din.p, px)); STC_CUDA(stc_dmalloc(&dout.p, px * 4));
   STC_CUDA(cudaMemcpyAsync(din.p, target_host, px, cudaMemcpyHostToDevice, ctx->stream));
   int rc = pre_edt_sq_dev(ctx, (const unsigned char*)din.p, n, H, W, radius, (int*)dout.p);
   if (rc) return rc;

@@ -16,7 +16,7 @@
 
 namespace {
 
-struct Buf { void* p = nullptr; ~Buf() { if (p) cudaFree(p); } };
+struct Buf { void* p = nullptr; ~Buf() { if (p) stc_dfree(p); } };
 
 // ---------------------------------------------------------------------------------------------
 // generic spatial primitives on [T][H][W] uint8 masks
@@ -650,30 +650,28 @@ void maskop_dilate(stc_ctx* ctx, const unsigned char* in, unsigned char* out, in
 
 #define LAUNCH1D(kern, n, ...) do { kern<<<cdiv((n), 256), 256, 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
 
-extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const float* dem_host, int T, int H, int W,
-                                    float* clouds_host, uint8_t* fcps_host, uint8_t* stage_host, int stage_id) {
+// Device-resident core: img_dev [T,H,W,10] float32, dem_dev [H,W]; clouds_dev [T,H,W] float32, fcps_dev [T,H,W] uint8.
+// Returns with its kernels enqueued on ctx->stream (it synchronises internally where the reference's control flow needs
+// scalars on the host: the adaptive threshold loop, the plausibility tests, the haze flags).
+int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int H, int W, float* clouds_dev, unsigned char* fcps_dev,
+                    uint8_t* stage_host, int stage_id) {
   if (!ctx) return STC_ERR_ARG;
-  if (!img_host || !dem_host || !clouds_host || !fcps_host || T < 1 || T > CT_MAX || H < 3 || W < 3)
+  if (!img || !dem || !clouds_dev || !fcps_dev || T < 1 || T > CT_MAX || H < 3 || W < 3)
     STC_FAIL(STC_ERR_ARG, "cloud_masks: bad argument (1 <= T <= 32)");
   const int HW = H * W; const int64_t N = (int64_t)T * HW;
-  Buf d_img, d_dem, d_clm, d_a, d_b, d_c, d_sh, d_cl, d_bc, d_nsr, d_water, d_allref, d_minb4, d_p25, d_minrgb, d_rc, d_thr,
-      d_ci, d_cc, d_cnt, d_win, d_med, d_mom, d_flags, d_all, d_out, d_vals, d_leaves, d_leafsum, d_child, d_cnts;
-  STC_CUDA(cudaMalloc(&d_img.p, N * 40)); STC_CUDA(cudaMalloc(&d_dem.p, HW * 4));
-  for (Buf* b : {&d_clm, &d_a, &d_b, &d_c, &d_sh, &d_cl, &d_bc, &d_nsr}) STC_CUDA(cudaMalloc(&b->p, N));
-  STC_CUDA(cudaMalloc(&d_water.p, HW * 4)); STC_CUDA(cudaMalloc(&d_allref.p, HW * 16)); STC_CUDA(cudaMalloc(&d_minb4.p, HW * 16));
-  STC_CUDA(cudaMalloc(&d_p25.p, HW * 12)); STC_CUDA(cudaMalloc(&d_minrgb.p, HW * 12)); STC_CUDA(cudaMalloc(&d_rc.p, HW * 12));
-  STC_CUDA(cudaMalloc(&d_thr.p, HW * 4)); STC_CUDA(cudaMalloc(&d_ci.p, HW)); STC_CUDA(cudaMalloc(&d_cc.p, HW));
-  STC_CUDA(cudaMalloc(&d_cnt.p, 64)); STC_CUDA(cudaMalloc(&d_win.p, 2 * CT_MAX * 4)); STC_CUDA(cudaMalloc(&d_med.p, CT_MAX * 4));
-  STC_CUDA(cudaMalloc(&d_mom.p, CT_MAX * 2 * 4)); STC_CUDA(cudaMalloc(&d_flags.p, 2 * CT_MAX * 4)); STC_CUDA(cudaMalloc(&d_all.p, CT_MAX * 4));
-  STC_CUDA(cudaMalloc(&d_out.p, N * 4));
+  Buf d_clm, d_a, d_b, d_c, d_sh, d_cl, d_bc, d_nsr, d_water, d_allref, d_minb4, d_p25, d_minrgb, d_rc, d_thr,
+      d_ci, d_cc, d_cnt, d_win, d_med, d_mom, d_flags, d_all, d_vals, d_leaves, d_leafsum, d_child, d_cnts;
+  for (Buf* b : {&d_clm, &d_a, &d_b, &d_c, &d_sh, &d_cl, &d_bc, &d_nsr}) STC_CUDA(stc_dmalloc(&b->p, N));
+  STC_CUDA(stc_dmalloc(&d_water.p, HW * 4)); STC_CUDA(stc_dmalloc(&d_allref.p, HW * 16)); STC_CUDA(stc_dmalloc(&d_minb4.p, HW * 16));
+  STC_CUDA(stc_dmalloc(&d_p25.p, HW * 12)); STC_CUDA(stc_dmalloc(&d_minrgb.p, HW * 12)); STC_CUDA(stc_dmalloc(&d_rc.p, HW * 12));
+  STC_CUDA(stc_dmalloc(&d_thr.p, HW * 4)); STC_CUDA(stc_dmalloc(&d_ci.p, HW)); STC_CUDA(stc_dmalloc(&d_cc.p, HW));
+  STC_CUDA(stc_dmalloc(&d_cnt.p, 64)); STC_CUDA(stc_dmalloc(&d_win.p, 2 * CT_MAX * 4)); STC_CUDA(stc_dmalloc(&d_med.p, CT_MAX * 4));
+  STC_CUDA(stc_dmalloc(&d_mom.p, CT_MAX * 2 * 4)); STC_CUDA(stc_dmalloc(&d_flags.p, 2 * CT_MAX * 4)); STC_CUDA(stc_dmalloc(&d_all.p, CT_MAX * 4));
   const int node_cap = 2 * (HW / 56 + 8) + 2;            // a pairwise leaf holds 58..128 values; a binary tree has < 2 x leaves nodes
-  STC_CUDA(cudaMalloc(&d_vals.p, N * 4)); STC_CUDA(cudaMalloc(&d_leaves.p, (size_t)T * node_cap * 8));
-  STC_CUDA(cudaMalloc(&d_leafsum.p, (size_t)T * node_cap * 4)); STC_CUDA(cudaMalloc(&d_child.p, (size_t)T * node_cap * 4)); STC_CUDA(cudaMalloc(&d_cnts.p, CT_MAX * 2 * 4));
-  const float* img = (const float*)d_img.p; const float* dem = (const float*)d_dem.p;
+  STC_CUDA(stc_dmalloc(&d_vals.p, N * 4)); STC_CUDA(stc_dmalloc(&d_leaves.p, (size_t)T * node_cap * 8));
+  STC_CUDA(stc_dmalloc(&d_leafsum.p, (size_t)T * node_cap * 4)); STC_CUDA(stc_dmalloc(&d_child.p, (size_t)T * node_cap * 4)); STC_CUDA(stc_dmalloc(&d_cnts.p, CT_MAX * 2 * 4));
   unsigned char *clm = (unsigned char*)d_clm.p, *ta = (unsigned char*)d_a.p, *tb = (unsigned char*)d_b.p, *tc = (unsigned char*)d_c.p,
                 *sh = (unsigned char*)d_sh.p, *cl = (unsigned char*)d_cl.p, *bc = (unsigned char*)d_bc.p, *nsr = (unsigned char*)d_nsr.p;
-  STC_CUDA(cudaMemcpyAsync(d_img.p, img_host, N * 40, cudaMemcpyHostToDevice, ctx->stream));
-  STC_CUDA(cudaMemcpyAsync(d_dem.p, dem_host, HW * 4, cudaMemcpyHostToDevice, ctx->stream));
   StaticRefs sr{(float*)d_water.p, (float*)d_allref.p, (float*)d_minb4.p, (float*)d_p25.p, (float*)d_minrgb.p};
   const float* water = sr.water;
   auto dilate = [&](const unsigned char* in, unsigned char* out, int64_t frames, int k, int conn, int inv_in, int inv_out, int three_d) {
@@ -830,7 +828,7 @@ extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const f
   }
   LAUNCH1D(k_or, N, cl, sh, cl, N);
   dilate(nsr, tc, T, 2, 1, 0, 0, 1);                                            // fcps = dilate3d(max(0, nsr), 2)
-  STC_CUDA(cudaMemcpyAsync(fcps_host, tc, N, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(fcps_dev, tc, N, cudaMemcpyDeviceToDevice, ctx->stream));
 
   // ---- H: dark-blue shadow recovery (:1638-1648) ----
   {
@@ -866,8 +864,26 @@ extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const f
       }
     }
   }
-  LAUNCH1D(k_to_float, N, cl, (float*)d_out.p, N);
+  LAUNCH1D(k_to_float, N, cl, clouds_dev, N);
   STC_CUDA(cudaGetLastError());
+  return STC_OK;
+}
+
+extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const float* dem_host, int T, int H, int W,
+                                    float* clouds_host, uint8_t* fcps_host, uint8_t* stage_host, int stage_id) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!img_host || !dem_host || !clouds_host || !fcps_host || T < 1 || T > CT_MAX || H < 3 || W < 3)
+    STC_FAIL(STC_ERR_ARG, "cloud_masks: bad argument (1 <= T <= 32)");
+  const int64_t N = (int64_t)T * H * W;
+  Buf d_img, d_dem, d_out, d_fcps;
+  STC_CUDA(stc_dmalloc(&d_img.p, N * 40)); STC_CUDA(stc_dmalloc(&d_dem.p, (size_t)H * W * 4));
+  STC_CUDA(stc_dmalloc(&d_out.p, N * 4)); STC_CUDA(stc_dmalloc(&d_fcps.p, N));
+  STC_CUDA(cudaMemcpyAsync(d_img.p, img_host, N * 40, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(d_dem.p, dem_host, (size_t)H * W * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = cloud_masks_dev(ctx, (const float*)d_img.p, (const float*)d_dem.p, T, H, W, (float*)d_out.p, (unsigned char*)d_fcps.p,
+                           stage_host, stage_id);
+  if (rc) return rc;
+  STC_CUDA(cudaMemcpyAsync(fcps_host, d_fcps.p, N, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(clouds_host, d_out.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
   return STC_OK;

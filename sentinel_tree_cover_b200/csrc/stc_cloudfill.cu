@@ -33,7 +33,7 @@ namespace {
 
 struct DBuf {
   void* p = nullptr;
-  ~DBuf() { if (p) cudaFree(p); }
+  ~DBuf() { if (p) stc_dfree(p); }
   template <typename T> T* as() { return (T*)p; }
 };
 
@@ -686,16 +686,18 @@ __global__ void __launch_bounds__(256) k_count_zero(const unsigned char* __restr
 namespace {
 __global__ void __launch_bounds__(256) k_clip01(float* __restrict__ x, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) x[i] = fminf(fmaxf(x[i], 0.f), 1.f);
+  if (i < n) { const float v = x[i]; x[i] = isnan(v) ? v : fminf(fmaxf(v, 0.f), 1.f); }     // np.clip keeps NaN
 }
 }  // namespace
 
-static int remove_clouds_impl(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H,
-                              int W, uint32_t* mt_state, float* areas_host, int32_t* to_remove_host, float* mosaic_host,
-                              int clip_when_all_kept, int32_t* clipped_out) {
+// Device-resident core: tiles [n,H,W,10] float32 (blended in place), probs [n,H,W] float32, pfcps [>= H*W] uint8 (date 0 is read),
+// areas [n,H,W] float32 out, mosaic_out [H,W,10] optional -- all device pointers; mt_state / to_remove / clipped_out on the host.
+int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const unsigned char* pfcps_dev, int n, int H,
+                      int W, uint32_t* mt_state, float* areas, int32_t* to_remove_host, float* mosaic_out_dev,
+                      int clip_when_all_kept, int32_t* clipped_out) {
   if (!ctx) return STC_ERR_ARG;
   if (clipped_out) *clipped_out = 0;
-  if (!tiles_host || !probs_host || !pfcps_host || !mt_state || !areas_host || !to_remove_host || n < 1 || n > CF_MAX_DATES || H < 3 ||
+  if (!tiles || !probs_dev || !pfcps_dev || !mt_state || !areas || !to_remove_host || n < 1 || n > CF_MAX_DATES || H < 3 ||
       W < 3 || mt_state[624] > 624)
     STC_FAIL(STC_ERR_ARG, "remove_clouds: bad argument (1 <= n <= 32, MT19937 state of 624 words + position)");
   const int HW = H * W; const int64_t N = (int64_t)n * HW;
@@ -710,31 +712,26 @@ static int remove_clouds_impl(stc_ctx* ctx, float* tiles_host, const float* prob
     fprintf(stderr, "[remove_clouds] %-34s %8.1f ms\n", what, t - cf_t);
     cf_t = t;
   };
-  DBuf d_tiles, d_areas, d_probs, d_ta, d_tb, d_sums, d_water0, d_water1, d_flag, d_u8a, d_u8b, d_pf, d_ref, d_pos, d_src_rows,
+  DBuf d_ta, d_tb, d_sums, d_water0, d_water1, d_flag, d_u8a, d_u8b, d_pf, d_ref, d_pos, d_src_rows,
       d_ref_rows, d_mosaic, d_div, d_snow, d_rowsrc, d_evi, d_lab, d_sample, d_partial, d_gram, d_coef, d_status, d_jobs, d_q, d_qout,
-      d_sd, d_params, d_cnt, d_counts, d_pfall;
+      d_sd, d_params, d_cnt, d_counts;
   const int gram_blocks = 296;
-  STC_CUDA(cudaMalloc(&d_tiles.p, N * 40)); STC_CUDA(cudaMalloc(&d_areas.p, N * 4)); STC_CUDA(cudaMalloc(&d_probs.p, N * 4));
-  STC_CUDA(cudaMalloc(&d_ta.p, N * 4)); STC_CUDA(cudaMalloc(&d_tb.p, N * 4)); STC_CUDA(cudaMalloc(&d_sums.p, CF_MAX_DATES * 4));
-  for (DBuf* b : {&d_water0, &d_water1, &d_flag, &d_u8a, &d_u8b, &d_pf}) STC_CUDA(cudaMalloc(&b->p, HW));
-  STC_CUDA(cudaMalloc(&d_pfall.p, N));
-  STC_CUDA(cudaMalloc(&d_ref.p, (int64_t)HW * 40)); STC_CUDA(cudaMalloc(&d_pos.p, (int64_t)HW * 4));
-  STC_CUDA(cudaMalloc(&d_src_rows.p, (int64_t)HW * 40)); STC_CUDA(cudaMalloc(&d_ref_rows.p, (int64_t)HW * 40));
-  STC_CUDA(cudaMalloc(&d_mosaic.p, (int64_t)HW * 40)); STC_CUDA(cudaMalloc(&d_div.p, (int64_t)HW * 4)); STC_CUDA(cudaMalloc(&d_snow.p, (int64_t)HW * 4));
-  STC_CUDA(cudaMalloc(&d_rowsrc.p, (int64_t)HW * 12)); STC_CUDA(cudaMalloc(&d_evi.p, (int64_t)HW * 12)); STC_CUDA(cudaMalloc(&d_lab.p, (int64_t)HW * 3));
-  STC_CUDA(cudaMalloc(&d_sample.p, (int64_t)HW * 12));
-  STC_CUDA(cudaMalloc(&d_partial.p, (size_t)gram_blocks * GRAM_N * 8)); STC_CUDA(cudaMalloc(&d_gram.p, GRAM_N * 8));
-  STC_CUDA(cudaMalloc(&d_coef.p, 10 * NF * 8)); STC_CUDA(cudaMalloc(&d_status.p, 64));
-  STC_CUDA(cudaMalloc(&d_jobs.p, 32 * sizeof(SelectJob))); STC_CUDA(cudaMalloc(&d_q.p, 32 * 8)); STC_CUDA(cudaMalloc(&d_qout.p, 32 * 4));
-  STC_CUDA(cudaMalloc(&d_sd.p, 32 * 4)); STC_CUDA(cudaMalloc(&d_params.p, 32 * 4)); STC_CUDA(cudaMalloc(&d_cnt.p, 64));
-  STC_CUDA(cudaMalloc(&d_counts.p, CF_MAX_DATES * 5 * 4));
-  float* tiles = d_tiles.as<float>(); float* areas = d_areas.as<float>(); float* mosaic = d_mosaic.as<float>();
+  STC_CUDA(stc_dmalloc(&d_ta.p, N * 4)); STC_CUDA(stc_dmalloc(&d_tb.p, N * 4)); STC_CUDA(stc_dmalloc(&d_sums.p, CF_MAX_DATES * 4));
+  for (DBuf* b : {&d_water0, &d_water1, &d_flag, &d_u8a, &d_u8b, &d_pf}) STC_CUDA(stc_dmalloc(&b->p, HW));
+  STC_CUDA(stc_dmalloc(&d_ref.p, (int64_t)HW * 40)); STC_CUDA(stc_dmalloc(&d_pos.p, (int64_t)HW * 4));
+  STC_CUDA(stc_dmalloc(&d_src_rows.p, (int64_t)HW * 40)); STC_CUDA(stc_dmalloc(&d_ref_rows.p, (int64_t)HW * 40));
+  STC_CUDA(stc_dmalloc(&d_mosaic.p, (int64_t)HW * 40)); STC_CUDA(stc_dmalloc(&d_div.p, (int64_t)HW * 4)); STC_CUDA(stc_dmalloc(&d_snow.p, (int64_t)HW * 4));
+  STC_CUDA(stc_dmalloc(&d_rowsrc.p, (int64_t)HW * 12)); STC_CUDA(stc_dmalloc(&d_evi.p, (int64_t)HW * 12)); STC_CUDA(stc_dmalloc(&d_lab.p, (int64_t)HW * 3));
+  STC_CUDA(stc_dmalloc(&d_sample.p, (int64_t)HW * 12));
+  STC_CUDA(stc_dmalloc(&d_partial.p, (size_t)gram_blocks * GRAM_N * 8)); STC_CUDA(stc_dmalloc(&d_gram.p, GRAM_N * 8));
+  STC_CUDA(stc_dmalloc(&d_coef.p, 10 * NF * 8)); STC_CUDA(stc_dmalloc(&d_status.p, 64));
+  STC_CUDA(stc_dmalloc(&d_jobs.p, 32 * sizeof(SelectJob))); STC_CUDA(stc_dmalloc(&d_q.p, 32 * 8)); STC_CUDA(stc_dmalloc(&d_qout.p, 32 * 4));
+  STC_CUDA(stc_dmalloc(&d_sd.p, 32 * 4)); STC_CUDA(stc_dmalloc(&d_params.p, 32 * 4)); STC_CUDA(stc_dmalloc(&d_cnt.p, 64));
+  STC_CUDA(stc_dmalloc(&d_counts.p, CF_MAX_DATES * 5 * 4));
+  float* mosaic = d_mosaic.as<float>();
   unsigned char *water0 = d_water0.as<unsigned char>(), *water1 = d_water1.as<unsigned char>(), *flag = d_flag.as<unsigned char>(),
                 *u8a = d_u8a.as<unsigned char>(), *u8b = d_u8b.as<unsigned char>(), *pf = d_pf.as<unsigned char>();
   int* cnt = d_cnt.as<int>();
-  STC_CUDA(cudaMemcpyAsync(tiles, tiles_host, N * 40, cudaMemcpyHostToDevice, ctx->stream));
-  STC_CUDA(cudaMemcpyAsync(d_probs.p, probs_host, N * 4, cudaMemcpyHostToDevice, ctx->stream));
-  STC_CUDA(cudaMemcpyAsync(d_pfall.p, pfcps_host, N, cudaMemcpyHostToDevice, ctx->stream));
 
   auto run_quantiles = [&](const std::vector<SelectJob>& jobs, const std::vector<double>& q, int median_mode, float* out_dev) -> int {
     STC_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(SelectJob), cudaMemcpyHostToDevice, ctx->stream));
@@ -747,7 +744,7 @@ static int remove_clouds_impl(stc_ctx* ctx, float* tiles_host, const float* prob
 
   cf_mark("alloc + upload");
   // ---- 1. feather the masks (:908-921, closing size 20) ----
-  if ((rc = pre_feather_dev(ctx, d_probs.as<float>(), n, H, W, 20, d_ta.as<float>(), d_tb.as<float>(), d_sums.as<float>(), areas))) return rc;
+  if ((rc = pre_feather_dev(ctx, probs_dev, n, H, W, 20, d_ta.as<float>(), d_tb.as<float>(), d_sums.as<float>(), areas))) return rc;
 
   cf_mark("feather");
   // ---- 2. cloud-free mosaic (:578-699) ----
@@ -765,12 +762,12 @@ static int remove_clouds_impl(stc_ctx* ctx, float* tiles_host, const float* prob
   // behind it, exactly reproducing the sequential loop.
   DBuf d_refall, d_flagall, d_posall, d_srcall, d_refrowsall, d_Ks, d_medall, d_sdall, d_paramsall, d_jobsall;
   const int64_t slab = (int64_t)HW * 10;
-  STC_CUDA(cudaMalloc(&d_refall.p, (size_t)n * slab * 4)); STC_CUDA(cudaMalloc(&d_srcall.p, (size_t)n * slab * 4));
-  STC_CUDA(cudaMalloc(&d_refrowsall.p, (size_t)n * slab * 4));
-  STC_CUDA(cudaMalloc(&d_flagall.p, (size_t)n * HW)); STC_CUDA(cudaMalloc(&d_posall.p, (size_t)n * HW * 4));
-  STC_CUDA(cudaMalloc(&d_Ks.p, CF_MAX_DATES * 4)); STC_CUDA(cudaMalloc(&d_medall.p, CF_MAX_DATES * 20 * 4));
-  STC_CUDA(cudaMalloc(&d_sdall.p, CF_MAX_DATES * 20 * 4)); STC_CUDA(cudaMalloc(&d_paramsall.p, CF_MAX_DATES * 20 * 4));
-  STC_CUDA(cudaMalloc(&d_jobsall.p, CF_MAX_DATES * 20 * sizeof(SelectJob)));
+  STC_CUDA(stc_dmalloc(&d_refall.p, (size_t)n * slab * 4)); STC_CUDA(stc_dmalloc(&d_srcall.p, (size_t)n * slab * 4));
+  STC_CUDA(stc_dmalloc(&d_refrowsall.p, (size_t)n * slab * 4));
+  STC_CUDA(stc_dmalloc(&d_flagall.p, (size_t)n * HW)); STC_CUDA(stc_dmalloc(&d_posall.p, (size_t)n * HW * 4));
+  STC_CUDA(stc_dmalloc(&d_Ks.p, CF_MAX_DATES * 4)); STC_CUDA(stc_dmalloc(&d_medall.p, CF_MAX_DATES * 20 * 4));
+  STC_CUDA(stc_dmalloc(&d_sdall.p, CF_MAX_DATES * 20 * 4)); STC_CUDA(stc_dmalloc(&d_paramsall.p, CF_MAX_DATES * 20 * 4));
+  STC_CUDA(stc_dmalloc(&d_jobsall.p, CF_MAX_DATES * 20 * sizeof(SelectJob)));
   int land_px = 0;
   STC_CUDA(cudaMemcpyAsync(&land_px, cnt + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<int> Ks(n, 0);
@@ -807,7 +804,7 @@ static int remove_clouds_impl(stc_ctx* ctx, float* tiles_host, const float* prob
     start = f + 1;
   }
   CF_LAUNCH(k_mosaic_final, cdiv((int64_t)HW * 10, 128), 128, tiles, d_div.as<float>(), n, HW, mosaic);
-  if (mosaic_host) STC_CUDA(cudaMemcpyAsync(mosaic_host, mosaic, (int64_t)HW * 40, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mosaic_out_dev) STC_CUDA(cudaMemcpyAsync(mosaic_out_dev, mosaic, (int64_t)HW * 40, cudaMemcpyDeviceToDevice, ctx->stream));
 
   cf_mark("mosaic");
   // ---- 3. per-date alignment and blending (:939-959, :316-575) ----
@@ -913,7 +910,7 @@ static int remove_clouds_impl(stc_ctx* ctx, float* tiles_host, const float* prob
 
   cf_mark("per-date alignment + blend");
   // ---- 4. residual clouds in the mosaic (:703-732) ----
-  maskop_dilate(ctx, d_pfall.as<unsigned char>(), pf, 1, H, W, 10, 1, 0, 0, 0);      // pfcps[0] (single frame when n == 1)
+  maskop_dilate(ctx, pfcps_dev, pf, 1, H, W, 10, 1, 0, 0, 0);      // pfcps[0] (single frame when n == 1)
   STC_CUDA(cudaMemsetAsync(cnt, 0, 8, ctx->stream));
   CF_LAUNCH(k_only_one, cdiv(HW, 256), 256, areas, pf, n, HW, u8a, cnt);
   int only_cnt = 0;
@@ -945,10 +942,30 @@ static int remove_clouds_impl(stc_ctx* ctx, float* tiles_host, const float* prob
       if (clipped_out) *clipped_out = 1;
     }
   }
-  STC_CUDA(cudaMemcpyAsync(tiles_host, tiles, N * 40, cudaMemcpyDeviceToHost, ctx->stream));
-  STC_CUDA(cudaMemcpyAsync(areas_host, areas, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return STC_OK;
+}
+
+static int remove_clouds_impl(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H,
+                              int W, uint32_t* mt_state, float* areas_host, int32_t* to_remove_host, float* mosaic_host,
+                              int clip_when_all_kept, int32_t* clipped_out) {
+  if (!ctx) return STC_ERR_ARG;
+  if (!tiles_host || !probs_host || !pfcps_host || !areas_host || n < 1 || n > CF_MAX_DATES || H < 3 || W < 3)
+    STC_FAIL(STC_ERR_ARG, "remove_clouds: bad argument (1 <= n <= 32, MT19937 state of 624 words + position)");
+  const int64_t N = (int64_t)n * H * W;
+  DBuf d_tiles, d_areas, d_probs, d_pfall, d_mosaic;
+  STC_CUDA(stc_dmalloc(&d_tiles.p, N * 40)); STC_CUDA(stc_dmalloc(&d_areas.p, N * 4)); STC_CUDA(stc_dmalloc(&d_probs.p, N * 4));
+  STC_CUDA(stc_dmalloc(&d_pfall.p, N));
+  if (mosaic_host) STC_CUDA(stc_dmalloc(&d_mosaic.p, (size_t)H * W * 40));
+  STC_CUDA(cudaMemcpyAsync(d_tiles.p, tiles_host, N * 40, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(d_probs.p, probs_host, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(d_pfall.p, pfcps_host, N, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = remove_clouds_dev(ctx, d_tiles.as<float>(), d_probs.as<float>(), d_pfall.as<unsigned char>(), n, H, W, mt_state,
+                             d_areas.as<float>(), to_remove_host, mosaic_host ? d_mosaic.as<float>() : nullptr, clip_when_all_kept, clipped_out);
+  if (rc) return rc;
+  if (mosaic_host) STC_CUDA(cudaMemcpyAsync(mosaic_host, d_mosaic.p, (size_t)H * W * 40, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(tiles_host, d_tiles.p, N * 40, cudaMemcpyDeviceToHost, ctx->stream));
+  STC_CUDA(cudaMemcpyAsync(areas_host, d_areas.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CF_SYNC();
-  cf_mark("download");
   return STC_OK;
 }
 

@@ -44,8 +44,20 @@ __global__ void __launch_bounds__(256) float_to_int16_kernel(const float* __rest
   out[i] = (int16_t)__fmul_rn(v, precision);
 }
 
+// ---- device-level launchers (shared with stc_tile.cu) ----
+int codec_to_float32_dev(stc_ctx* ctx, const uint16_t* in_dev, int64_t n, float* out_dev) {
+  to_float32_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n);
+  STC_CUDA(cudaGetLastError()); ctx->launches++;
+  return STC_OK;
+}
+int codec_convert_to_db_dev(stc_ctx* ctx, const float* in_dev, int64_t n, float min_db, float* out_dev) {
+  convert_to_db_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n, min_db);
+  STC_CUDA(cudaGetLastError()); ctx->launches++;
+  return STC_OK;
+}
+
 namespace {
-struct Buf { void* p = nullptr; ~Buf() { if (p) cudaFree(p); } };
+struct Buf { void* p = nullptr; ~Buf() { if (p) stc_dfree(p); } };
 }
 
 extern "C" {
@@ -54,7 +66,7 @@ int stc_to_float32_host(stc_ctx* ctx, const uint16_t* in_host, int64_t n, float*
   if (!ctx) return STC_ERR_ARG;
   if (!in_host || !out_host || n < 1) STC_FAIL(STC_ERR_ARG, "to_float32: bad argument");
   Buf a, b;
-  STC_CUDA(cudaMalloc(&a.p, n * 2)); STC_CUDA(cudaMalloc(&b.p, n * 4));
+  STC_CUDA(stc_dmalloc(&a.p, n * 2)); STC_CUDA(stc_dmalloc(&b.p, n * 4));
   STC_CUDA(cudaMemcpyAsync(a.p, in_host, n * 2, cudaMemcpyHostToDevice, ctx->stream));
   to_float32_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, ctx->stream>>>((const uint16_t*)a.p, (float*)b.p, n);
   STC_CUDA(cudaGetLastError()); ctx->launches++;
@@ -67,7 +79,7 @@ int stc_to_uint16_host(stc_ctx* ctx, const float* in_host, int64_t n, uint16_t* 
   if (!ctx) return STC_ERR_ARG;
   if (!in_host || !out_host || n < 1) STC_FAIL(STC_ERR_ARG, "to_uint16: bad argument");
   Buf a, b;
-  STC_CUDA(cudaMalloc(&a.p, n * 4)); STC_CUDA(cudaMalloc(&b.p, n * 2));
+  STC_CUDA(stc_dmalloc(&a.p, n * 4)); STC_CUDA(stc_dmalloc(&b.p, n * 2));
   STC_CUDA(cudaMemcpyAsync(a.p, in_host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
   to_uint16_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (uint16_t*)b.p, n);
   STC_CUDA(cudaGetLastError()); ctx->launches++;
@@ -80,7 +92,7 @@ int stc_float_to_int16_host(stc_ctx* ctx, const float* in_host, int64_t n, int p
   if (!ctx) return STC_ERR_ARG;
   if (!in_host || !out_host || n < 1 || precision < 1) STC_FAIL(STC_ERR_ARG, "float_to_int16: bad argument");
   Buf a, b;
-  STC_CUDA(cudaMalloc(&a.p, n * 4)); STC_CUDA(cudaMalloc(&b.p, n * 2));
+  STC_CUDA(stc_dmalloc(&a.p, n * 4)); STC_CUDA(stc_dmalloc(&b.p, n * 2));
   STC_CUDA(cudaMemcpyAsync(a.p, in_host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
   // np.clip(float32 array, python float, python float): the bounds are float64 scalars cast to float32
   float_to_int16_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (int16_t*)b.p, n, (float)(-32768.0 / precision),
@@ -95,7 +107,7 @@ int stc_convert_to_db_host(stc_ctx* ctx, const float* in_host, int64_t n, float 
   if (!ctx) return STC_ERR_ARG;
   if (!in_host || !out_host || n < 1 || !(min_db > 0.f)) STC_FAIL(STC_ERR_ARG, "convert_to_db: bad argument");
   Buf a, b;
-  STC_CUDA(cudaMalloc(&a.p, n * 4)); STC_CUDA(cudaMalloc(&b.p, n * 4));
+  STC_CUDA(stc_dmalloc(&a.p, n * 4)); STC_CUDA(stc_dmalloc(&b.p, n * 4));
   STC_CUDA(cudaMemcpyAsync(a.p, in_host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
   convert_to_db_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (float*)b.p, n, min_db);
   STC_CUDA(cudaGetLastError()); ctx->launches++;

@@ -103,6 +103,21 @@ struct stc_ctx {
 
 #define STC_FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
 
+// GroupNorm statistics slots (sum, sum of squares per sample and group) hold 64-bit FIXED-POINT integers (2^-24 units)
+// inside the double-typed buffers: integer atomics are associative, so the totals do not depend on the order in which
+// warps and CTAs arrive -- identical inputs give identical bytes, run to run.  Together with sample-aligned conv tiles
+// (every partial sum covers the same pixels of a sample wherever the sample sits in the batch) the result is also
+// independent of the batch position and of the number of CTAs.  Range: |sum| < 2^39 = 5e11.
+#ifdef __CUDACC__
+#define STC_STAT_SCALE 16777216.0
+__device__ __forceinline__ void stat_add(double* slot, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)__double2ll_rn((double)v * STC_STAT_SCALE));
+}
+__device__ __forceinline__ double stat_get(const double* slot) {
+  return (double)(*reinterpret_cast<const long long*>(slot)) * (1.0 / STC_STAT_SCALE);
+}
+#endif
+
 // timeline helpers: bracket one launch on ctx->stream
 static inline void trace_begin(stc_ctx* ctx, const char* label) {
   if (!ctx->trace_on) return;
@@ -117,6 +132,22 @@ static inline void trace_end(stc_ctx* ctx) {
 }
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- device-memory pool (stc_pool.cu): per-call scratch buffers are recycled instead of cudaMalloc'd / cudaFree'd ----
+cudaError_t stc_dmalloc(void** p, size_t bytes);
+cudaError_t stc_dfree(void* p);
+template <typename T> static inline cudaError_t stc_dmalloc(T** p, size_t bytes) { return stc_dmalloc((void**)p, bytes); }
+void stc_pool_trim();
+void stc_pool_stats(int64_t* hits, int64_t* misses, size_t* cached_bytes, size_t* total_bytes);
+// RAII scratch buffer from the pool
+struct PoolBuf {
+  void* p = nullptr;
+  PoolBuf() = default;
+  PoolBuf(const PoolBuf&) = delete; PoolBuf& operator=(const PoolBuf&) = delete;
+  ~PoolBuf() { if (p) stc_dfree(p); }
+  cudaError_t alloc(size_t bytes) { if (p) { stc_dfree(p); p = nullptr; } return stc_dmalloc(&p, bytes); }
+  template <typename T> T* as() const { return (T*)p; }
+};
 
 // model entry points implemented in stc_model.cu
 int model_finalize_weights(stc_ctx* ctx);

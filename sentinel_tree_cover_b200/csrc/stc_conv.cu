@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(ConvParams p) {
   if (p.stats[dir] && tid < 2 * p.G * 2) {
     int slot = tid / (2 * p.G), rem = tid - slot * 2 * p.G;
     float v = ((float*)sStat)[slot * 32 + rem];
-    if (b0 + slot < p.B && v != 0.f) atomicAdd(&p.stats[dir][(int64_t)(b0 + slot) * p.G * 2 + rem], (double)v);
+    if (b0 + slot < p.B && v != 0.f) stat_add(&p.stats[dir][(int64_t)(b0 + slot) * p.G * 2 + rem], v);
   }
 }
 
@@ -305,7 +305,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // Epilogue shared by both tcgen05 kernels: warps 2-9, TMEM -> registers -> global, fused MODE arithmetic and
 // GroupNorm partial sums.  `tile` is the global super-tile index (dir = tile / tiles_per_dir).
 template <int N, int NT, int G, int MODE>
-__device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per_dir, int tile_begin, int tile_end,
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per_dir, int tps, int tile_begin, int tile_end,
                                               uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int warp, int lane) {
   constexpr int ACC_COLS = NT * N;
   auto TFULL = [&](int s) { return tfull0 + 8u * s; };
@@ -325,16 +325,17 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per
     float acc_s[GA], acc_ss[GA];
 #pragma unroll
     for (int g = 0; g < GA; ++g) { acc_s[g] = 0.f; acc_ss[g] = 0.f; }
-    int cur_b = -1, cur_dir = 0;
-    auto flush_warp = [&]() {
-      if (G == 0 || cur_b < 0) return;
-      double* st = p.stats[cur_dir] + ((int64_t)cur_b * G + half * GA) * 2;
+    // one flush per super-tile: warp-shuffle reduction of the lane partials, then fixed-point integer atomics (stat_add).
+    // Tiles are sample-aligned, so a partial covers the same pixels in the same order wherever the sample sits.
+    auto flush_warp = [&](int b, int dir) {
+      if (G == 0) return;
+      double* st = p.stats[dir] + ((int64_t)b * G + half * GA) * 2;
 #pragma unroll
       for (int g = 0; g < GA; ++g) {
         float s = acc_s[g], ss = acc_ss[g];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-        if (lane == 0) { atomicAdd(st + 2 * g, (double)s); atomicAdd(st + 2 * g + 1, (double)ss); }
+        if (lane == 0) { stat_add(st + 2 * g, s); stat_add(st + 2 * g + 1, ss); }
         acc_s[g] = 0.f; acc_ss[g] = 0.f;
       }
     };
@@ -342,7 +343,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per
     for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const int as = it & 1;
       const int dir = tile / tiles_per_dir;
-      const int p0 = (tile - dir * tiles_per_dir) * (NT * 128);
+      const int tl = tile - dir * tiles_per_dir;
+      const int tb = tl / tps;                                  // the sample this super-tile belongs to
+      const int k0 = (tl - tb * tps) * (NT * 128);              // first row of the tile inside the sample
+      const int p0 = tb * hw + k0;
       const bool has_stats = (G > 0) && (p.stats[dir] != nullptr);
       float* const outp = reinterpret_cast<float*>(p.out[dir]);
       mbar_wait(TFULL(as), (uint32_t)(it >> 1) & 1u);
@@ -350,26 +354,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per
 #pragma unroll 1
       // timing experiments (STC_EXP_FLAGS bits, results invalid): 2 = no epilogue work at all, 4 = no global stores
       for (int j = 0; j < ((working && !(p.exp_flags & 2)) ? NT : 0); ++j) {
+        const int rem_raw = k0 + j * 128 + row;
+        const bool inb = rem_raw < hw;                           // rows past the sample's end belong to the next sample's tiles
         const int P = p0 + j * 128 + row;
-        const bool inb = P < (int)p.Ptot;
-        const int Pc = inb ? P : 0;
-        const int b = Pc / hw;
-        const int rem = Pc - b * hw;
+        const int rem = inb ? rem_raw : 0;
         const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
         const bool valid = inb && (yp >= p.vy0 && yp < p.vy1 && xp >= p.vx0 && xp < p.vx1);
-        bool per_lane_flush = false;
-        if (has_stats) {
-          const unsigned mk = __ballot_sync(0xffffffffu, inb);
-          if (mk) {
-            const int bw = __shfl_sync(0xffffffffu, b, __ffs(mk) - 1);
-            const bool uniform = __all_sync(0xffffffffu, !inb || b == bw);
-            if (uniform) {
-              if (bw != cur_b || dir != cur_dir) { flush_warp(); cur_b = bw; cur_dir = dir; }
-            } else {              // the warp's 32 pixels straddle two samples (once per sample boundary)
-              flush_warp(); cur_b = -1; per_lane_flush = true;
-            }
-          }
-        }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS + j * N);
         float scale = 1.f;
         if (MODE == MODE_PSCALE_SWISH) scale = pscale(p, yp, xp);
@@ -427,20 +417,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per
             }
           }
         }
-        if (G > 0 && per_lane_flush) {
-          double* st = p.stats[dir] + ((int64_t)b * G + half * GA) * 2;
-#pragma unroll
-          for (int g = 0; g < GA; ++g) {
-            if (valid) { atomicAdd(st + 2 * g, (double)acc_s[g]); atomicAdd(st + 2 * g + 1, (double)acc_ss[g]); }
-            acc_s[g] = 0.f; acc_ss[g] = 0.f;
-          }
-        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(TEMPTY(as));
+      if (lane == 0) mbar_arrive(TEMPTY(as));                    // the accumulator stage is free again; the statistics follow
+      if (has_stats && working) flush_warp(tb, dir);
     }
-    flush_warp();
   }
 }
 
@@ -448,10 +430,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per
 // G GroupNorm groups whose (sum, sumsq) the epilogue accumulates (0 = none), MODE the fused
 // epilogue.  320 threads: warp 0 bulk-copy producer, warp 1 TMEM allocator + MMA issuer,
 // warps 2-9 epilogue (TMEM lane quarter = warp%4, column half = (warp-2)/4).
-// Statistics live in per-lane registers across the CTA's contiguous run of tiles and are
-// flushed (shuffle reduction + fp64 atomics) only when the sample changes.
+// Statistics live in per-lane registers for one (sample-aligned) super-tile and are flushed per tile: shuffle
+// reduction + 64-bit fixed-point integer atomics (order independent, see stat_add in stc_common.cuh).
 template <int N, int NT, int G, int MODE, int OCC = 1>
-__global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, int tiles_per_dir, int total_tiles, int tiles_per_cta) {
+__global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, int tiles_per_dir, int total_tiles, int tiles_per_cta, int tps) {
   using C = UmmaCfg<N, NT, OCC>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -488,7 +470,8 @@ __global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, in
       int stage = 0; uint32_t phase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int dir = tile / tiles_per_dir;
-        const int64_t p0 = (int64_t)(tile - dir * tiles_per_dir) * (NT * 128);
+        const int tl = tile - dir * tiles_per_dir, tb = tl / tps;
+        const int64_t p0 = (int64_t)tb * (p.Hp * p.Wp) + (int64_t)(tl - tb * tps) * (NT * 128);       // sample-aligned super-tiles
         for (int ks = 0; ks < Ksteps; ++ks) {
           const uint4* src; int64_t plane; int c;
           if (ks < p.k0steps) { src = p.a0[dir]; plane = p.a0_plane; c = 2 * ks; }
@@ -544,7 +527,7 @@ __global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, in
       }
     }
   } else {
-    conv_epilogue<N, NT, G, MODE>(p, tiles_per_dir, tile_begin, tile_end, tmem_base, TFULL(0), TEMPTY(0), warp, lane);
+    conv_epilogue<N, NT, G, MODE>(p, tiles_per_dir, tps, tile_begin, tile_end, tmem_base, TFULL(0), TEMPTY(0), warp, lane);
   }
   // ---- teardown ----
   tc_fence_before();
@@ -573,7 +556,7 @@ __global__ void __launch_bounds__(320, OCC) conv3x3_umma_kernel(ConvParams p, in
 // ======================================================================================
 template <int N, int NT, int G, int MODE, bool WRES>
 __global__ void __launch_bounds__(352, 2) conv3x3_umma2_kernel(ConvParams p, int tiles_per_dir, int ndir, int tiles_per_cta,
-                                                                int RU, int stages, int iss) {
+                                                                int RU, int stages, int iss, int tps) {
   constexpr int B_BYTES = 9 * 2 * N * 16;
   constexpr int ACC_COLS = NT * N;
   constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
@@ -627,7 +610,8 @@ __global__ void __launch_bounds__(352, 2) conv3x3_umma2_kernel(ConvParams p, int
       }
       int stage = 0; uint32_t phase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int64_t p0 = (int64_t)(tile - dir * tiles_per_dir) * (NT * 128);
+        const int tl = tile - dir * tiles_per_dir, tb = tl / tps;
+        const int64_t p0 = (int64_t)tb * (p.Hp * p.Wp) + (int64_t)(tl - tb * tps) * (NT * 128);       // sample-aligned super-tiles
         for (int ks = 0; ks < Ksteps; ++ks) {
           const uint4* src; int64_t plane; int c;
           if (ks < p.k0steps) { src = p.a0[dir]; plane = p.a0_plane; c = 2 * ks; }
@@ -687,7 +671,7 @@ __global__ void __launch_bounds__(352, 2) conv3x3_umma2_kernel(ConvParams p, int
       }
     }
   } else {
-    conv_epilogue<N, NT, G, MODE>(p, tiles_per_dir, tile_begin, tile_end, tmem_base, TFULL(0), TEMPTY(0), warp, lane);
+    conv_epilogue<N, NT, G, MODE>(p, tiles_per_dir, tps, tile_begin, tile_end, tmem_base, TFULL(0), TEMPTY(0), warp, lane);
   }
   // ---- teardown ----
   tc_fence_before();
@@ -710,13 +694,14 @@ static int launch_umma(stc_ctx* ctx, const ConvParams& p, int ndir) {
     configured = true;
   }
   if (p.Ptot >= (1ll << 31) - 1024) STC_FAIL(STC_ERR_ARG, "conv: pixel space exceeds 2^31");
-  int tiles_per_dir = cdiv(p.Ptot, NT * 128);
+  const int tps = cdiv((int64_t)p.Hp * p.Wp, NT * 128);        // super-tiles per sample (sample-aligned, see conv_epilogue)
+  int tiles_per_dir = tps * p.B;
   int total = tiles_per_dir * ndir;
   const int slots = ctx->num_sms * OCC;
   int grid = total < slots ? total : slots;
   int tiles_per_cta = cdiv(total, grid);
   grid = cdiv(total, tiles_per_cta);
-  kern<<<grid, 320, C::SMEM_BYTES, ctx->stream>>>(p, tiles_per_dir, total, tiles_per_cta);
+  kern<<<grid, 320, C::SMEM_BYTES, ctx->stream>>>(p, tiles_per_dir, total, tiles_per_cta, tps);
   STC_CUDA(cudaGetLastError());
   return STC_OK;
 }
@@ -744,13 +729,14 @@ static int launch_umma2(stc_ctx* ctx, const ConvParams& p, int ndir, int iss_req
   if (WRES && stages < 3) return launch_umma2<N, NT, G, MODE, false>(ctx, p, ndir, iss_req);   // budget too small for resident weights
   if (stages < 2) return 1;                        // caller reports the geometry as unsupported
   const int smem_bytes = w_bytes + stages * stage_bytes + 256;
-  const int tiles_per_dir = cdiv(p.Ptot, NT * 128);
+  const int tps = cdiv((int64_t)p.Hp * p.Wp, NT * 128);        // super-tiles per sample (sample-aligned, see conv_epilogue)
+  const int tiles_per_dir = tps * p.B;
   int per_dir = ctx->num_sms / ndir;               // CTAs per direction
   if (per_dir > tiles_per_dir) per_dir = tiles_per_dir;
   const int tiles_per_cta = cdiv(tiles_per_dir, per_dir);
   per_dir = cdiv(tiles_per_dir, tiles_per_cta);
   const int iss = (NT >= 2 && iss_req >= 2) ? 2 : 1;
-  kern<<<per_dir * ndir, 352, smem_bytes, ctx->stream>>>(p, tiles_per_dir, ndir, tiles_per_cta, RU, stages, iss);
+  kern<<<per_dir * ndir, 352, smem_bytes, ctx->stream>>>(p, tiles_per_dir, ndir, tiles_per_cta, RU, stages, iss, tps);
   STC_CUDA(cudaGetLastError());
   return STC_OK;
 }

@@ -78,7 +78,7 @@ extern "C" int stc_missing_px_host(stc_ctx* ctx, const float* arr_host, int n, i
   if (!arr_host || !bad_px_host || !nan_vals_host || n < 1 || H < 1 || W < 1 || C < 1) STC_FAIL(STC_ERR_ARG, "missing_px: bad argument");
   const int64_t bytes = (int64_t)n * H * W * C * 4;
   float* d = nullptr; int* cnt = nullptr;
-  STC_CUDA(cudaMalloc(&d, bytes)); STC_CUDA(cudaMalloc(&cnt, 2 * n * 4));
+  STC_CUDA(stc_dmalloc(&d, bytes)); STC_CUDA(stc_dmalloc(&cnt, 2 * n * 4));
   cudaMemcpyAsync(d, arr_host, bytes, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemsetAsync(cnt, 0, 2 * n * 4, ctx->stream);
   k_missing_counts<<<dim3(cdiv((int64_t)H * W, 256), n), 256, 0, ctx->stream>>>(d, H * W, C, cnt, cnt + n);
@@ -86,7 +86,7 @@ extern "C" int stc_missing_px_host(stc_ctx* ctx, const float* arr_host, int n, i
   cudaMemcpyAsync(bad_px_host, cnt, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
   cudaMemcpyAsync(nan_vals_host, cnt + n, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d); cudaFree(cnt);
+  stc_dfree(d); stc_dfree(cnt);
   STC_CUDA(e);
   STC_CUDA(cudaGetLastError());
   return STC_OK;
@@ -98,7 +98,7 @@ extern "C" int stc_median_fill_host(stc_ctx* ctx, float* arr_host, int n, int H,
     STC_FAIL(STC_ERR_ARG, "median_fill: bad argument (1 <= n <= 96)");
   const int64_t cols = (int64_t)H * W * C, bytes = cols * n * 4;
   float* d = nullptr; int* cnt = nullptr;
-  STC_CUDA(cudaMalloc(&d, bytes)); STC_CUDA(cudaMalloc(&cnt, 2 * n * 4));
+  STC_CUDA(stc_dmalloc(&d, bytes)); STC_CUDA(stc_dmalloc(&cnt, 2 * n * 4));
   cudaMemcpyAsync(d, arr_host, bytes, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemsetAsync(cnt, 0, 2 * n * 4, ctx->stream);
   k_median_fill<<<cdiv(cols, 128), 128, 0, ctx->stream>>>(d, n, cols);
@@ -107,7 +107,7 @@ extern "C" int stc_median_fill_host(stc_ctx* ctx, float* arr_host, int n, int H,
   cudaMemcpyAsync(arr_host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
   cudaMemcpyAsync(nan_vals_host, cnt + n, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d); cudaFree(cnt);
+  stc_dfree(d); stc_dfree(cnt);
   STC_CUDA(e);
   STC_CUDA(cudaGetLastError());
   return STC_OK;
@@ -191,20 +191,27 @@ __global__ void __launch_bounds__(256) k_build_sentinel2(const float* __restrict
 
 }  // namespace
 
+int interp_build_sentinel2_dev(stc_ctx* ctx, const float* s2_10_dev, const float* s2_20_dev, int n, int h, int w, float* out_dev) {
+  const int64_t px = (int64_t)n * 4 * h * w;
+  k_build_sentinel2<<<cdiv(px, 256), 256, 0, ctx->stream>>>(s2_10_dev, s2_20_dev, n, h, w, out_dev);
+  STC_CUDA(cudaGetLastError()); ctx->launches++;
+  return STC_OK;
+}
+
 extern "C" int stc_build_sentinel2_host(stc_ctx* ctx, const float* s2_10_host, const float* s2_20_host, int n, int h, int w,
                                         float* out_host) {
   if (!ctx) return STC_ERR_ARG;
   if (!s2_10_host || !s2_20_host || !out_host || n < 1 || h < 2 || w < 2) STC_FAIL(STC_ERR_ARG, "build_sentinel2: bad argument");
   const int64_t px = (int64_t)n * 4 * h * w;
   float *d10 = nullptr, *d20 = nullptr, *dout = nullptr;
-  STC_CUDA(cudaMalloc(&d10, px * 16)); STC_CUDA(cudaMalloc(&d20, (int64_t)n * h * w * 24)); STC_CUDA(cudaMalloc(&dout, px * 40));
+  STC_CUDA(stc_dmalloc(&d10, px * 16)); STC_CUDA(stc_dmalloc(&d20, (int64_t)n * h * w * 24)); STC_CUDA(stc_dmalloc(&dout, px * 40));
   cudaMemcpyAsync(d10, s2_10_host, px * 16, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(d20, s2_20_host, (int64_t)n * h * w * 24, cudaMemcpyHostToDevice, ctx->stream);
   k_build_sentinel2<<<cdiv(px, 256), 256, 0, ctx->stream>>>(d10, d20, n, h, w, dout);
   ctx->launches++;
   cudaMemcpyAsync(out_host, dout, px * 40, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d10); cudaFree(d20); cudaFree(dout);
+  stc_dfree(d10); stc_dfree(d20); stc_dfree(dout);
   STC_CUDA(e);
   STC_CUDA(cudaGetLastError());
   return STC_OK;

@@ -42,8 +42,8 @@ __device__ __forceinline__ void unpack8(uint4 u, float* v) {
 // pb:*_norm/{moments,add,Sqrt,truediv,mul,add_1}: biased variance, eps inside the sqrt.
 __device__ __forceinline__ void gn_affine(const double* st /*[G][2]*/, int g, float count, float gamma, float beta,
                                           float& a, float& b) {
-  double mean = st[2 * g] / (double)count;
-  double var = st[2 * g + 1] / (double)count - mean * mean;
+  double mean = stat_get(st + 2 * g) / (double)count;
+  double var = stat_get(st + 2 * g + 1) / (double)count - mean * mean;
   if (var < 0.0) var = 0.0;
   float rstd = (float)(1.0 / sqrt(var + (double)GN_EPS));
   a = rstd * gamma;
@@ -1056,6 +1056,7 @@ int model_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int
   if (H != W) STC_FAIL(STC_ERR_ARG, "predict: H must equal W");
   if (H % 4 != 0 || H < 28) STC_FAIL(STC_ERR_ARG, "predict: H must be a multiple of 4 and >= 28");
   if (T < 1 || T > 12 || length < 1) STC_FAIL(STC_ERR_ARG, "predict: bad T/length");
+  if (length > T) STC_FAIL(STC_ERR_ARG, "predict: length exceeds the number of sequence frames (the backward direction would read past them)");
   if (normalize && (!min17 || !max17)) STC_FAIL(STC_ERR_ARG, "predict: normalize needs min/max");
   return run_chunks(ctx, x_dev, nullptr, B, T, H, length, normalize, min17, max17, out_dev);
 }

@@ -12,7 +12,7 @@ int pre_edt_sq_dev(stc_ctx* ctx, const unsigned char* target_dev, int n, int H, 
 
 namespace {
 
-struct PBuf { void* p = nullptr; ~PBuf() { if (p) cudaFree(p); } template <typename T> T* as() { return (T*)p; } };
+struct PBuf { void* p = nullptr; ~PBuf() { if (p) stc_dfree(p); } template <typename T> T* as() { return (T*)p; } };
 
 // ---- np.sum of contiguous float32 segments, NumPy's pairwise order (see stc_cloud.cu k_np_moments) ----
 // mode 0: x          mode 1: x < 255 ? x*100 : x  (the in-place scaling of :1570 before the sum of :1573)
@@ -163,13 +163,23 @@ int bright_bare_dev(stc_ctx* ctx, const float* img_dev, int F, int H, int W, int
 
 }  // namespace
 
+// device core of stc_np_sum_host: data_dev [nseg, len] -> sum_dev [nseg] float32, valid_dev [nseg] int32
+int post_np_sum_dev(stc_ctx* ctx, const float* data_dev, int nseg, int len, int mode, float* sum_dev, int* valid_dev) {
+  const int leaf_cap = len / 32 + 8;
+  PBuf lv, ls;
+  STC_CUDA(stc_dmalloc(&lv.p, (size_t)nseg * leaf_cap * 8)); STC_CUDA(stc_dmalloc(&ls.p, (size_t)nseg * leaf_cap * 4));
+  k_np_sum_seg<<<nseg, 1024, 0, ctx->stream>>>(data_dev, len, mode, leaf_cap, lv.as<int2>(), ls.as<float>(), sum_dev, valid_dev);
+  STC_CUDA(cudaGetLastError()); ctx->launches++;
+  return STC_OK;
+}
+
 extern "C" int stc_np_sum_host(stc_ctx* ctx, const float* data_host, int nseg, int len, int mode, float* sum_host, int32_t* valid_host) {
   if (!ctx) return STC_ERR_ARG;
   if (!data_host || !sum_host || nseg < 1 || len < 1 || mode < 0 || mode > 2) STC_FAIL(STC_ERR_ARG, "np_sum: bad argument");
   const int leaf_cap = len / 32 + 8;
   PBuf d, lv, ls, so, vo;
-  STC_CUDA(cudaMalloc(&d.p, (size_t)nseg * len * 4)); STC_CUDA(cudaMalloc(&lv.p, (size_t)nseg * leaf_cap * 8));
-  STC_CUDA(cudaMalloc(&ls.p, (size_t)nseg * leaf_cap * 4)); STC_CUDA(cudaMalloc(&so.p, nseg * 4)); STC_CUDA(cudaMalloc(&vo.p, nseg * 4));
+  STC_CUDA(stc_dmalloc(&d.p, (size_t)nseg * len * 4)); STC_CUDA(stc_dmalloc(&lv.p, (size_t)nseg * leaf_cap * 8));
+  STC_CUDA(stc_dmalloc(&ls.p, (size_t)nseg * leaf_cap * 4)); STC_CUDA(stc_dmalloc(&so.p, nseg * 4)); STC_CUDA(stc_dmalloc(&vo.p, nseg * 4));
   STC_CUDA(cudaMemcpyAsync(d.p, data_host, (size_t)nseg * len * 4, cudaMemcpyHostToDevice, ctx->stream));
   k_np_sum_seg<<<nseg, 1024, 0, ctx->stream>>>(d.as<float>(), len, mode, leaf_cap, lv.as<int2>(), ls.as<float>(), so.as<float>(), vo.as<int>());
   ctx->launches++;
@@ -189,7 +199,7 @@ extern "C" int stc_normalize_host(stc_ctx* ctx, float* x_host, int64_t npx, int 
     p.mid[c] = (float)((maxs[c] + mins[c]) / 2); p.half[c] = (float)((maxs[c] - mins[c]) / 2);
   }
   PBuf d;
-  STC_CUDA(cudaMalloc(&d.p, (size_t)npx * C * 4));
+  STC_CUDA(stc_dmalloc(&d.p, (size_t)npx * C * 4));
   STC_CUDA(cudaMemcpyAsync(d.p, x_host, (size_t)npx * C * 4, cudaMemcpyHostToDevice, ctx->stream));
   k_normalize<<<cdiv(npx * C, 256), 256, 0, ctx->stream>>>(d.as<float>(), npx * C, C, p);
   ctx->launches++;
@@ -204,8 +214,8 @@ extern "C" int stc_bright_bare_host(stc_ctx* ctx, const float* img_host, int F, 
   if (!img_host || !ramp_host || F < 1 || H < 15 || W < 15 || C < 9) STC_FAIL(STC_ERR_ARG, "bright_bare: bad argument");
   PBuf img, a, b, d2, ramp;
   const size_t bytes = (size_t)F * H * W * C * 4;
-  STC_CUDA(cudaMalloc(&img.p, bytes)); STC_CUDA(cudaMalloc(&a.p, H * W)); STC_CUDA(cudaMalloc(&b.p, H * W));
-  STC_CUDA(cudaMalloc(&d2.p, (size_t)H * W * 4)); STC_CUDA(cudaMalloc(&ramp.p, (size_t)(H - 14) * (W - 14) * 8));
+  STC_CUDA(stc_dmalloc(&img.p, bytes)); STC_CUDA(stc_dmalloc(&a.p, H * W)); STC_CUDA(stc_dmalloc(&b.p, H * W));
+  STC_CUDA(stc_dmalloc(&d2.p, (size_t)H * W * 4)); STC_CUDA(stc_dmalloc(&ramp.p, (size_t)(H - 14) * (W - 14) * 8));
   STC_CUDA(cudaMemcpyAsync(img.p, img_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   int rc = bright_bare_dev(ctx, img.as<float>(), F, H, W, C, a.as<unsigned char>(), b.as<unsigned char>(), d2.as<int>(), ramp.as<double>());
   if (rc) return rc;
@@ -245,10 +255,10 @@ extern "C" int stc_postprocess_subtile_host(stc_ctx* ctx, const float* preds_hos
   const int H = S + 14, Hm = S + 2;
   PBuf img, a, b, d2, ramp, preds, mc, na, nb, vote, out;
   const size_t bytes = (size_t)F * H * H * C * 4;
-  STC_CUDA(cudaMalloc(&img.p, bytes)); STC_CUDA(cudaMalloc(&a.p, H * H)); STC_CUDA(cudaMalloc(&b.p, H * H));
-  STC_CUDA(cudaMalloc(&d2.p, (size_t)H * H * 4)); STC_CUDA(cudaMalloc(&ramp.p, (size_t)S * S * 8));
-  STC_CUDA(cudaMalloc(&preds.p, (size_t)S * S * 4)); STC_CUDA(cudaMalloc(&mc.p, (size_t)H * H * 4));
-  STC_CUDA(cudaMalloc(&na.p, Hm * Hm)); STC_CUDA(cudaMalloc(&nb.p, Hm * Hm)); STC_CUDA(cudaMalloc(&vote.p, 256)); STC_CUDA(cudaMalloc(&out.p, (size_t)S * S * 4));
+  STC_CUDA(stc_dmalloc(&img.p, bytes)); STC_CUDA(stc_dmalloc(&a.p, H * H)); STC_CUDA(stc_dmalloc(&b.p, H * H));
+  STC_CUDA(stc_dmalloc(&d2.p, (size_t)H * H * 4)); STC_CUDA(stc_dmalloc(&ramp.p, (size_t)S * S * 8));
+  STC_CUDA(stc_dmalloc(&preds.p, (size_t)S * S * 4)); STC_CUDA(stc_dmalloc(&mc.p, (size_t)H * H * 4));
+  STC_CUDA(stc_dmalloc(&na.p, Hm * Hm)); STC_CUDA(stc_dmalloc(&nb.p, Hm * Hm)); STC_CUDA(stc_dmalloc(&vote.p, 256)); STC_CUDA(stc_dmalloc(&out.p, (size_t)S * S * 4));
   STC_CUDA(cudaMemcpyAsync(img.p, img_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(preds.p, preds_host, (size_t)S * S * 4, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(mc.p, min_clear_host, (size_t)H * H * 4, cudaMemcpyHostToDevice, ctx->stream));

@@ -9,6 +9,7 @@
 //   indices_kernel         : make_indices (src/download_and_predict_job.py:998-1006)
 //   temporal_median_kernel : np.median(axis=0) (:1152-1160)
 #include "stc_common.cuh"
+#include <cstring>
 
 #include "stc_indices.cuh"
 
@@ -62,14 +63,15 @@ int pre_assemble_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W
 }
 
 // ---- out[o][i] = sum_n M[o][n] * in[n][i] ----------------------------------------------
-__constant__ float c_M[32 * 32];
+// The operator travels as a kernel parameter (constant bank, 4 KB): no __constant__ upload, no stream synchronisation per call.
+struct TMat { float m[32 * 32]; };
 
 // NMAX = compile-time bound on n_in (8 / 16 / 24 / 32): the date loop is fully unrolled over NMAX with a uniform
 // `n < n_in` guard, so the n_in x VEC inputs of a thread live in registers.  (A runtime-length loop indexes the array
 // dynamically, which puts it in local memory: measured 1.65 TB/s = 25 % of the HBM peak for n = 24.)
 template <int VEC, int NMAX>
 __global__ void __launch_bounds__(256) temporal_matmul_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                              int n_in, int n_out, int64_t inner) {
+                                                              int n_in, int n_out, int64_t inner, const __grid_constant__ TMat Mk) {
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (i >= inner) return;
   float v[NMAX][VEC];
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(256) temporal_matmul_kernel(const float* __res
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) {
       if (n < n_in) {                      // same sequential fma order over the dates as before
-        const float m = c_M[o * 32 + n];
+        const float m = Mk.m[o * 32 + n];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[k] = fmaf(m, v[n][k], acc[k]);
       }
@@ -105,26 +107,24 @@ __global__ void __launch_bounds__(256) temporal_matmul_kernel(const float* __res
 }
 
 template <int VEC>
-static void launch_temporal_matmul(const float* in_dev, float* out_dev, int n_in, int n_out, int64_t inner, cudaStream_t st) {
+static void launch_temporal_matmul(const float* in_dev, float* out_dev, int n_in, int n_out, int64_t inner, const TMat& Mk, cudaStream_t st) {
   const int grid = cdiv(inner / VEC + (inner % VEC ? 1 : 0), 256);
-  if (n_in <= 8) temporal_matmul_kernel<VEC, 8><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner);
-  else if (n_in <= 16) temporal_matmul_kernel<VEC, 16><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner);
-  else if (n_in <= 24) temporal_matmul_kernel<VEC, 24><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner);
-  else temporal_matmul_kernel<VEC, 32><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner);
+  if (n_in <= 8) temporal_matmul_kernel<VEC, 8><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk);
+  else if (n_in <= 16) temporal_matmul_kernel<VEC, 16><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk);
+  else if (n_in <= 24) temporal_matmul_kernel<VEC, 24><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk);
+  else temporal_matmul_kernel<VEC, 32><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk);
 }
 
 int pre_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_host, int n_in, int n_out, int64_t inner,
                             float* out_dev) {
   if (n_in < 1 || n_in > 32 || n_out < 1 || n_out > 32) STC_FAIL(STC_ERR_ARG, "temporal_matmul: n_in/n_out must be in 1..32");
-  float Mp[32 * 32] = {0};
+  TMat Mk; memset(&Mk, 0, sizeof(Mk));
   for (int o = 0; o < n_out; ++o)
-    for (int n = 0; n < n_in; ++n) Mp[o * 32 + n] = M_host[o * n_in + n];
-  STC_CUDA(cudaMemcpyToSymbolAsync(c_M, Mp, sizeof(Mp), 0, cudaMemcpyHostToDevice, ctx->stream));
+    for (int n = 0; n < n_in; ++n) Mk.m[o * 32 + n] = M_host[o * n_in + n];
   bool vec = (inner % 4 == 0) && (((uintptr_t)in_dev & 15) == 0) && (((uintptr_t)out_dev & 15) == 0);
-  if (vec) launch_temporal_matmul<4>(in_dev, out_dev, n_in, n_out, inner, ctx->stream);
-  else launch_temporal_matmul<1>(in_dev, out_dev, n_in, n_out, inner, ctx->stream);
+  if (vec) launch_temporal_matmul<4>(in_dev, out_dev, n_in, n_out, inner, Mk, ctx->stream);
+  else launch_temporal_matmul<1>(in_dev, out_dev, n_in, n_out, inner, Mk, ctx->stream);
   STC_CUDA(cudaGetLastError());
-  STC_CUDA(cudaStreamSynchronize(ctx->stream));  // Mp is a stack buffer
   ctx->launches++;
   return STC_OK;
 }

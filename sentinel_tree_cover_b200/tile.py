@@ -83,40 +83,29 @@ def max_masked(a, b, zero, sess):
     return a
 
 
+def _axis_plan(length, target):
+    """One axis of adjust_shape (:260-310) as (shift, out_len): out[i] = in[clip(i + shift, 0, length - 1)].
+    Padding is 'edge' padding, i.e. an index clamp; the reference's rules for how much it pads or crops (and the cases
+    in which it leaves the axis one pixel off) are reproduced, see csrc/stc_tile.cu: tilehost::adjust_axis."""
+    shift, out_len = _api.C.c_int32(0), _api.C.c_int32(0)
+    rc = _api.load_library().stc_adjust_shape_plan(int(length), int(target), _api.C.byref(shift), _api.C.byref(out_len))
+    if rc != 0:
+        raise ValueError("adjust_shape: bad axis length %r / target %r" % (length, target))
+    return shift.value, out_len.value
+
+
 def adjust_shape(arr, width, height):
-    """:260-310 -- pad ('edge') or centre-crop axes 1/2 to (width, height); pure data movement."""
-    arr = arr[:, :, :, np.newaxis] if len(arr.shape) == 3 else arr
-    arr = arr[np.newaxis, :, :, np.newaxis] if len(arr.shape) == 2 else arr
-    if arr.shape[1] < width:
-        pad_amt = (width - arr.shape[1]) // 2
-        if pad_amt == 0:
-            arr = np.pad(arr, ((0, 0), (1, pad_amt), (0, 0), (0, 0)), 'edge')
-        else:
-            arr = np.pad(arr, ((0, 0), (pad_amt, pad_amt), (0, 0), (0, 0)), 'edge')
-    if arr.shape[2] < height:
-        pad_amt = (height - arr.shape[2]) // 2
-        if pad_amt == 0:
-            arr = np.pad(arr, ((0, 0), (0, 0), (1, 0), (0, 0)), 'edge')
-        else:
-            arr = np.pad(arr, ((0, 0), (0, 0), (pad_amt, pad_amt), (0, 0)), 'edge')
-    if arr.shape[1] > width:
-        pad_amt = (arr.shape[1] - width) // 2
-        even = (arr.shape[1] - width) % 2 == 0
-        if pad_amt == 0:
-            arr = arr[:, 1:, ...]
-        elif even:
-            arr = arr[:, int(pad_amt):-int(pad_amt), ...]
-        else:
-            arr = arr[:, int(np.floor(pad_amt / 2)):-int(np.ceil(pad_amt / 2)), ...]
-    if arr.shape[2] > height:
-        pad_amt = (arr.shape[2] - height) // 2
-        even = (arr.shape[2] - height) % 2 == 0
-        if pad_amt == 0:
-            arr = arr[:, :, 1:, :]
-        elif even:
-            arr = arr[:, :, int(pad_amt):-int(pad_amt), ...]
-        else:
-            arr = arr[:, :, int(np.floor(pad_amt / 2)):-int(np.ceil(pad_amt / 2)), ...]
+    """:260-310 -- pad ('edge') or centre-crop axes 1 / 2 to (width, height): a gather along each axis with clamped
+    indices (the device chain runs the same plan as a kernel, stc_tile.cu: k_adjust)."""
+    if arr.ndim == 3:
+        arr = arr[:, :, :, np.newaxis]
+    elif arr.ndim == 2:
+        arr = arr[np.newaxis, :, :, np.newaxis]
+    for axis, target in ((1, width), (2, height)):
+        shift, out_len = _axis_plan(arr.shape[axis], target)
+        if shift != 0 or out_len != arr.shape[axis]:
+            idx = np.clip(np.arange(out_len) + shift, 0, arr.shape[axis] - 1)
+            arr = np.take(arr, idx, axis=axis)
     return arr.squeeze()
 
 
@@ -217,12 +206,10 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
         nonlocal clm
         cloudshad, fcps = _api.identify_clouds_shadows(sentinel2, dem, bbx, sess)
         if clm is not None:
-            try:
+            if clm.shape == np.asarray(fcps).shape == np.asarray(cloudshad).shape:       # the reference's try/except guards a shape mismatch
                 if first:
                     clm[fcps] = 0.                                                        # :843 (in place: later rounds see it)
-                cloudshad = max_masked(cloudshad, clm, None, sess)                        # :844 / :874 / ...
-            except Exception:
-                pass
+                cloudshad = max_masked(cloudshad, clm, None, sess)                        # :844 / :874 / ...; libstc errors propagate
         return cloudshad, fcps
 
     def frac_gt0(a):
@@ -369,111 +356,36 @@ def process_subtiles(x, y, s2=None, dates=None, interp=None, s1=None, dem=None, 
     clear_all = count_lt_axis0(interp, 0.33, sess)                                        # np.sum(interp < 0.33, axis=0), whole tile
     _mark("quarterly medians + counts")
 
-    if fused and not gen_feats and not os.environ.get("STC_TILE_HOST_GATHER"):
-        # window table only (integers); gather, stacks, no-image test, forward and post-filters run on the device
-        table = np.zeros((len(tiles_folder), 12), np.int32)
-        outputs = []
-        for t in range(len(tiles_folder)):
-            start_x, start_y, nr, nc = [int(v) for v in tiles_array[t]]
-            folder_x, folder_y = tiles_folder[t][0], tiles_folder[t][1]
-            nr = min(start_x + nr, s2.shape[1]) - start_x
-            nc = min(start_y + nc, s2.shape[2]) - start_y
-            row = [start_x, start_y, nr, nc, 0, 0, 0, 0, 0, 0, 0, 0]
-            if nc == SIZE + 7:                                   # :1369-1377 (second array axis)
-                pad_u = 7 if start_y == 0 else 0
-                pad_d = 7 if start_y != 0 else 0
-                row[6], row[7] = pad_u, pad_d
-                row[10], row[11] = pad_u, pad_d
-            if nr == SIZE + 7:                                   # :1378-1388 (first array axis); min_clear is padded with
-                pad_l = 7 if start_x == 0 else 0                 # (pad_u, pad_d) there -- whatever those variables hold
-                pad_r = 7 if start_x != 0 else 0
-                row[4], row[5] = pad_l, pad_r
-                row[8], row[9] = pad_u, pad_d                    # NameError in the reference too if never set
-            table[t] = row
-            outputs.append(f"{path}{str(folder_y)}/{str(folder_x)}.npy")
-        out = np.empty((len(table), SIZE, SIZE), np.float32)
-        flags = np.zeros(len(table), np.int32)
-        mn, mnp = _api._f64(sess.min_all)
-        mx, mxp = _api._f64(sess.max_all)
-        dem32 = np.ascontiguousarray(dem, np.float32)
-        s2m = np.ascontiguousarray(s2_median[0]); s1m = np.ascontiguousarray(s1_median[0])
-        _check(sess, sess.lib.stc_process_subtiles_host(sess.h, _ptr(s2), _ptr(s1), _ptr(s2m), _ptr(s1m), _ptr(dem32), _ptr(clear_all),
-                                                        s2.shape[1], s2.shape[2], len(table), _ptr(table), SIZE, length, length,
-                                                        int(len(dates) < 2), mnp, mxp, _ptr(out), _ptr(flags)))
-        _mark("gather + forward + post-filters (device)")
-        for i in range(len(table)):
-            os.makedirs(os.path.realpath(os.path.dirname(outputs[i])), exist_ok=True)
-            np.save(outputs[i], out[i])
-        _mark("save")
-        return
-
-    stacks, clears, outputs, no_data = [], [], [], []
-    for t in range(len(tiles_folder)):
-        tile_folder, tile_array = tiles_folder[t], tiles_array[t]
-        start_x, start_y = tile_array[0], tile_array[1]
-        folder_x, folder_y = tile_folder[0], tile_folder[1]
-        end_x, end_y = start_x + tile_array[2], start_y + tile_array[3]
-        subtile = np.copy(s2[:, start_x:end_x, start_y:end_y, :])
-        subtile_median_s2 = np.copy(s2_median[:, start_x:end_x, start_y:end_y, :])
-        subtile_median_s1 = np.copy(s1_median[:, start_x:end_x, start_y:end_y, :])
-        dem_subtile = dem[np.newaxis, start_x:end_x, start_y:end_y]
-        s1_subtile = np.copy(s1[:, start_x:end_x, start_y:end_y, :])
-        min_clear = clear_all[start_x:end_x, start_y:end_y]
-        no_images = bool(np.percentile(min_clear, 50) < 1)                                # :1357 (scalar decision)
-        # :1369-1388 edge padding; pad_u / pad_d deliberately keep their value from earlier iterations, as the
-        # reference's second block reads them for the x-direction pad of min_clear
-        if subtile.shape[2] == SIZE + 7:
-            pad_u = 7 if start_y == 0 else 0
-            pad_d = 7 if start_y != 0 else 0
-            subtile = np.pad(subtile, ((0, 0), (0, 0), (pad_u, pad_d), (0, 0)), 'reflect')
-            s1_subtile = np.pad(s1_subtile, ((0, 0), (0, 0), (pad_u, pad_d), (0, 0)), 'reflect')
-            dem_subtile = np.pad(dem_subtile, ((0, 0), (0, 0), (pad_u, pad_d)), 'reflect')
-            subtile_median_s2 = np.pad(subtile_median_s2, ((0, 0), (0, 0), (pad_u, pad_d), (0, 0)), 'reflect')
-            subtile_median_s1 = np.pad(subtile_median_s1, ((0, 0), (0, 0), (pad_u, pad_d), (0, 0)), 'reflect')
-            min_clear = np.pad(min_clear, ((0, 0), (pad_u, pad_d)), 'reflect')
-        if subtile.shape[1] == SIZE + 7:
-            pad_l = 7 if start_x == 0 else 0
-            pad_r = 7 if start_x != 0 else 0
-            subtile = np.pad(subtile, ((0, 0), (pad_l, pad_r), (0, 0), (0, 0)), 'reflect')
-            s1_subtile = np.pad(s1_subtile, ((0, 0), (pad_l, pad_r), (0, 0), (0, 0)), 'reflect')
-            dem_subtile = np.pad(dem_subtile, ((0, 0), (pad_l, pad_r), (0, 0)), 'reflect')
-            subtile_median_s2 = np.pad(subtile_median_s2, ((0, 0), (pad_l, pad_r), (0, 0), (0, 0)), 'reflect')
-            subtile_median_s1 = np.pad(subtile_median_s1, ((0, 0), (pad_l, pad_r), (0, 0), (0, 0)), 'reflect')
-            min_clear = np.pad(min_clear, ((pad_u, pad_d), (0, 0)), 'reflect')
-        subtile_all = np.zeros((length + 1, SIZE + 14, SIZE + 14, 17), dtype=np.float32)   # :1391-1401 (copies only)
-        subtile_all[:-1, ..., :10] = subtile[..., :10]
-        subtile_all[:-1, ..., 11:13] = s1_subtile
-        subtile_all[:-1, ..., 13:] = subtile[..., 10:]
-        subtile_all[:, ..., 10] = dem_subtile.repeat(length + 1, axis=0)
-        subtile_all[-1, ..., :10] = subtile_median_s2[..., :10]
-        subtile_all[-1, ..., 11:13] = subtile_median_s1
-        subtile_all[-1, ..., 13:] = subtile_median_s2[..., 10:]
-        no_images = True if len(dates) < 2 else no_images
-        stacks.append(subtile_all); clears.append(min_clear); no_data.append(no_images)
-        outputs.append(f"{path}{str(folder_y)}/{str(folder_x)}.npy")
-
-    _mark("window slicing / padding")
-    # one call: normalisation + batched forward + post-filters on the device for every subtile of the tile
-    batch = np.stack(stacks)
-    clear = np.ascontiguousarray(np.stack(clears), np.float32)
-    flags = np.ascontiguousarray(np.array(no_data, dtype=np.int32))
-    if batch.shape[1:] != (length + 1, SIZE + 14, SIZE + 14, 17) or clear.shape[1:] != (SIZE + 14, SIZE + 14):
-        raise ValueError("subtile stacks %r / clear-image maps %r do not have the expected geometry" % (batch.shape, clear.shape))
-    out = np.empty((len(stacks), SIZE, SIZE), np.float32)
+    # window table only (integers); gather, stacks, no-image test, forward and post-filters run on the device
+    # (oracle/subtiles_ref.host_gather_stacks is the statement-by-statement NumPy restatement the tests compare against)
+    if s2.shape[0] != length or s1.shape[0] != length:
+        raise ValueError("process_subtiles: %d / %d composite frames for length %d" % (s2.shape[0], s1.shape[0], length))
+    table = subtile_table(tiles_array, s2.shape[1], s2.shape[2], SIZE)
+    outputs = [f"{path}{str(tf[1])}/{str(tf[0])}.npy" for tf in tiles_folder]
+    out = np.empty((len(table), SIZE, SIZE), np.float32)
+    flags = np.zeros(len(table), np.int32)
     mn, mnp = _api._f64(sess.min_all)
     mx, mxp = _api._f64(sess.max_all)
-    _check(sess, sess.lib.stc_predict_postprocess_host(sess.h, _ptr(batch), _ptr(clear), _ptr(flags), len(stacks), length, SIZE + 14, length,
-                                                       mnp, mxp, _ptr(out)))
-    _mark("forward + post-filters (fused)")
-    for i in range(len(stacks)):
+    s2 = np.ascontiguousarray(s2, np.float32); s1 = np.ascontiguousarray(s1, np.float32)
+    dem32 = np.ascontiguousarray(dem, np.float32)
+    s2m = np.ascontiguousarray(s2_median[0], np.float32); s1m = np.ascontiguousarray(s1_median[0], np.float32)
+    args = (sess.h, _ptr(s2), _ptr(s1), _ptr(s2m), _ptr(s1m), _ptr(dem32), _ptr(clear_all), s2.shape[1], s2.shape[2], len(table), _ptr(table),
+            SIZE, length, length, int(len(dates) < 2), mnp, mxp, _ptr(out), _ptr(flags))
+    if gen_feats:
+        early = np.empty((len(table), SIZE, SIZE, 64), np.float32)
+        late = np.empty((len(table), SIZE, SIZE, 64), np.float32)
+        _check(sess, sess.lib.stc_process_subtiles_feats_host(*args, _ptr(early), _ptr(late)))
+    else:
+        _check(sess, sess.lib.stc_process_subtiles_host(*args))
+    _mark("gather + forward + post-filters (device)")
+    for i in range(len(table)):
         os.makedirs(os.path.realpath(os.path.dirname(outputs[i])), exist_ok=True)
         np.save(outputs[i], out[i])
     _mark("save")
     if gen_feats:                                                                         # :1429-1446
-        live = [i for i in range(len(stacks)) if not no_data[i]]
+        live = [i for i in range(len(table)) if not flags[i]]
         if live:
-            _, early, late = sess.predict_feats(batch[live], length=length, normalize=True)
-            both = sess.float_to_int16(np.concatenate([early[..., :32], late[..., :32]], axis=-1))
+            both = sess.float_to_int16(np.concatenate([early[live][..., :32], late[live][..., :32]], axis=-1))
             root = f'{local_path}{str(x)}/{str(y)}/'
             for k, i in enumerate(live):
                 out_f = outputs[i].replace(path, root + "feats/")
@@ -482,3 +394,55 @@ def process_subtiles(x, y, s2=None, dates=None, interp=None, s1=None, dem=None, 
             os.makedirs(os.path.realpath(root + "raw/feats/"), exist_ok=True)
             os.makedirs(os.path.realpath(root + "ard/"), exist_ok=True)
         _mark("features")
+
+
+def subtile_table(tiles_array, H, W, SIZE):
+    """The integer description of the subtile loop's slicing and edge padding (:1345-1388) that the device gather
+    consumes: per subtile (row0, col0, rows, cols, data pads rows-before/after, cols-before/after, min_clear pads in the
+    same order).  The reference pads min_clear in its first-axis block with the (pad_u, pad_d) of the second-axis block --
+    whatever those loop variables currently hold -- which is kept."""
+    table = np.zeros((len(tiles_array), 12), np.int32)
+    pad_u = pad_d = None
+    for t, (start_x, start_y, nr, nc) in enumerate(np.asarray(tiles_array).astype(int).tolist()):
+        nr = min(start_x + nr, H) - start_x
+        nc = min(start_y + nc, W) - start_y
+        row = table[t]
+        row[:4] = (start_x, start_y, nr, nc)
+        if nc == SIZE + 7:                                       # second array axis (:1369-1377)
+            pad_u, pad_d = (7, 0) if start_y == 0 else (0, 7)
+            row[6:8] = (pad_u, pad_d)
+            row[10:12] = (pad_u, pad_d)
+        if nr == SIZE + 7:                                       # first array axis (:1378-1388)
+            if pad_u is None:
+                raise NameError("pad_u")                         # the reference reads the variable before any assignment here
+            row[4:6] = (7, 0) if start_x == 0 else (0, 7)
+            row[8:10] = (pad_u, pad_d)
+    return table
+
+
+def run_tile(x, y, local_path, sess, bbx=None, loader=None, exists=os.path.exists, make_shadow=True, size=158, length=4,
+             return_subtiles=False):
+    """The body of the reference's main loop for one tile (:1995-2020) in ONE device-resident call
+    (StcSession.run_tile -> stc_tile_run_host): raw/*.hkl arrays -> uint8 tree-cover tile.  Same file naming and
+    `loader` / `exists` stand-ins as process_tile.  `bbx` is accepted and unused (see api.identify_clouds_shadows)."""
+    del bbx
+    load = loader or _default_loader
+    x = str(int(x)); y = str(int(y))
+    folder = f"{local_path}{x}/{y}/"
+    tile_idx = f'{x}X{y}Y'
+    cloud_mask_file = f'{folder}raw/clouds/cloudmask_{tile_idx}.hkl'
+    clm = np.asarray(load(cloud_mask_file)) if exists(cloud_mask_file) else None
+    s1 = np.asarray(load(f'{folder}raw/s1/{tile_idx}.hkl'))
+    s2_10 = np.asarray(load(f'{folder}raw/s2_10/{tile_idx}.hkl'))
+    s2_20 = np.asarray(load(f'{folder}raw/s2_20/{tile_idx}.hkl'))
+    for name, a in (("s1", s1), ("s2_10", s2_10), ("s2_20", s2_20)):
+        if not (np.issubdtype(a.dtype, np.integer) and a.min() >= 0 and a.max() <= 65535):
+            raise ValueError("run_tile: raw/%s is not a uint16-range integer array; use process_tile for float storage" % name)
+    dem = np.asarray(load(f'{folder}raw/misc/dem_{tile_idx}.hkl'), np.float32)
+    dates = np.asarray(load(f'{folder}raw/misc/s2_dates_{tile_idx}.hkl'))
+    if s2_10.ndim == 3:
+        s2_10 = s2_10[np.newaxis]
+    if s2_20.ndim == 3:
+        s2_20 = s2_20[np.newaxis]
+    return sess.run_tile(s2_10, s2_20, s1, dem, dates, clm=None if clm is None else (clm != 0), make_shadow=make_shadow, size=size,
+                         length=length, return_subtiles=return_subtiles)

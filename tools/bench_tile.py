@@ -37,7 +37,20 @@ def main():
         res.append({"process_tile_ms": round(d[0], 1), "superresolve_ms": round(d[1], 1), "process_subtiles_ms": round(d[2], 1),
                     "mosaic_ms": round(d[3], 1), "total_ms": round(float(d.sum()), 1), "dates_kept": int(len(dates)),
                     "out_shape": list(out.shape), "out_dtype": str(out.dtype), "tree_cover_mean": round(float(out[out <= 100].mean()), 2)})
-    print(json.dumps({"tile": "618x618, %d dates, synthetic raw (uint16 S2/S1, f32 DEM)" % args.n, "runs": res}), flush=True)
+    # the same tile through the device-resident chain (ONE C call: stc_tile_run_host)
+    raw = store.raw
+    pin = {k: sess.pinned_empty(raw[k].shape, raw[k].dtype) for k in ("s2_10", "s2_20", "s1", "dem")}
+    for k in pin:
+        pin[k][...] = raw[k]
+    chain = []
+    for rep in range(args.reps + 1):
+        random.seed(4)
+        t0 = time.perf_counter()
+        out2, kept = sess.run_tile(pin["s2_10"], pin["s2_20"], pin["s1"], pin["dem"], raw["s2_dates"])
+        chain.append(round((time.perf_counter() - t0) * 1e3, 1))
+    print(json.dumps({"tile": "618x618, %d dates, synthetic raw (uint16 S2/S1, f32 DEM)" % args.n, "runs": res,
+                      "chain_ms": chain, "chain_equals_mirrors": bool(np.array_equal(out2, out)), "chain_dates_kept": int(len(kept)),
+                      "pool": sess.pool_info()}), flush=True)
 
 
 if __name__ == "__main__":
