@@ -25,6 +25,26 @@ sys.path.insert(0, ROOT)
 H = 168
 BATCH = 256
 METRIC = "tiles/sec (12-step 168x168x13 S1+S2 patches)"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def workload_config(batch):
+    """The one `config` object both arms print (the driver compares them)."""
+    return {"workload": "configs[1]: batch=256 tiles, 12-step S1+S2 stack, assemble+normalize+ConvGRU/U-Net forward",
+            "patch": [12, H, H, 13], "batch_per_gpu": batch, "weights": "random-init, released architecture",
+            "l2": "inputs (%.1f GB/step) exceed L2; no flush needed" % (batch * 12 * H * H * 13 * 4 / 1e9),
+            "parallelism": "tiles sharded, one process per GPU, one NCCL weight broadcast"}
+
+
+def committed_traffic(kernel_key):
+    """DRAM read+write bytes per launch of `kernel_key` from the committed ncu capture (profiles/r02_traffic.json, written
+    by tools/summarize_dram.py from an `ncu --set full` run of this very command); None when no capture is committed."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        e = d["kernels"][kernel_key]
+        return float(e["dram_bytes_per_launch"]), d.get("source", "profiles/r02_traffic.json")
+    except Exception:
+        return None, None
 
 
 def conv_flops_per_tile(Hin, T=4):
@@ -47,10 +67,10 @@ def gates_roofline(total_ms, n_launch, chunk, peaks):
     avg_s = total_ms / n_launch / 1000.0
     achieved = flops_avg / avg_s / 1e12
     return {"bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"],
-            "traffic": 398.0e6,
+            "traffic": committed_traffic("conv_gates")[0],
             "kernel": "conv3x3_umma2_kernel<64,4,16,PLAIN,WRES> (ConvGRU gates)",
             "note": "avg of %d launches: %.1f us; algorithmic %.3e FLOP/launch (%d tiles x 2 directions); peak = %s sustained "
-                    "bf16/fp16 dense; traffic = dram read+write per launch from ncu (profiles/r01_f_summary.md: 213 MB + 185 MB; "
+                    "bf16/fp16 dense; traffic = dram read+write per launch from the committed ncu capture (profiles/r02_traffic.json; "
                     "algorithmic 202 + 231 MB); structural ceiling of this formulation: an M128 x N64 x K16 tcgen05.mma with both "
                     "operands in shared memory retires every 48 clk (operand reads, profiles/r01_umma_microbench5.txt) = 67%% of the "
                     "dense rate, times 49/64 useful K and 168^2/170^2 useful rows = 50%% of the burst peak"
@@ -72,9 +92,9 @@ def hbm_roofline(trace_csv, chunk, peaks):
     avg_s = sum(durs) / len(durs) / 1000.0
     achieved = bytes_avg / avg_s / 1e9
     return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
-            "traffic": 734.0e6, "kernel": "gru_apply2_kernel (ConvGRU gating + state update)",
+            "traffic": committed_traffic("gru_apply2")[0], "kernel": "gru_apply2_kernel (ConvGRU gating + state update)",
             "note": "avg of %d launches: %.1f us; algorithmic %.3e B/launch (%d tiles x 2 directions); peak = %s HBM copy "
-                    "bandwidth; traffic = dram read+write per launch from ncu (profiles/r01_f_summary.md: 411 MB + 323 MB)"
+                    "bandwidth; traffic = dram read+write per launch from the committed ncu capture (profiles/r02_traffic.json)"
                     % (len(durs), 1e6 * avg_s, bytes_avg, chunk, peaks["src"])}
 
 
@@ -190,10 +210,6 @@ def cpu_reference_tiles_per_s(n_tiles, seed=1234):
     from oracle.model_ref import PredictRef
     from sentinel_tree_cover_b200.api import MIN_ALL, MAX_ALL
     from sentinel_tree_cover_b200.weights import random_predict_weights
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can.
-    # torch's own default (physical cores) is left alone; only a forced single thread is raised.
-    if torch.get_num_threads() == 1:
-        torch.set_num_threads(_host_cores())
     _log("cpu baseline: %d tiles on %d threads" % (n_tiles, torch.get_num_threads()))
     model = PredictRef(random_predict_weights(0))
     m = P.synth_monthly(1, H, seed)
@@ -205,29 +221,155 @@ def cpu_reference_tiles_per_s(n_tiles, seed=1234):
     return n_tiles / dt, torch.get_num_threads(), dt
 
 
+def cpu_reference_tile_chain(n_dates=12, px=206):
+    """CPU leg of `tile_chain`: the oracle ports of every stage of the per-tile loop body on a px x px cut-out with
+    n_dates dates (oracle/chain_ref.py); a 618-px tile is (618/px)^2 such samples."""
+    import torch
+    from oracle import chain_ref
+    from sentinel_tree_cover_b200.api import MIN_ALL, MAX_ALL
+    from sentinel_tree_cover_b200.weights import load_npz
+    t, nwin = chain_ref.run_sample(n_dates, px, 5, load_npz(os.path.join(GOLD, "weights_predict_172.npz")),
+                                   load_npz(os.path.join(GOLD, "weights_superresolve.npz")), MIN_ALL, MAX_ALL)
+    scale = (618.0 / px) ** 2
+    total = sum(t.values())
+    return {"value": 1.0 / (total * scale), "unit": "tiles/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "one %dx%d px cut-out with %d dates and %d of the 36 subtile windows (%.1f s; a 618x618 tile = %.1f such samples): "
+                      "NumPy/SciPy ports of identify_clouds_shadows, remove_cloud_and_shadows, smooth_large_tile + torch-CPU "
+                      "restatements of the two frozen graphs" % (px, px, n_dates, nwin, total, scale),
+            "stage_seconds": {k: round(v, 3) for k, v in t.items()}}
+
+
+def _clean_thread_env():
+    """torchrun exports OMP_NUM_THREADS=1 before the interpreter starts, which pins oneDNN/OpenMP to one thread for the life
+    of the process (torch.set_num_threads afterwards only reaches part of the stack: round 1 printed 0.22 tiles/s on
+    '32 cores').  The CPU legs therefore run in a child process whose environment has no thread caps."""
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        env.pop(k, None)
+    env["STC_BENCH_CHILD"] = "1"
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID", "GROUP_RANK", "LOCAL_WORLD_SIZE",
+              "ROLE_RANK", "ROLE_WORLD_SIZE"):
+        env.pop(k, None)
+    return env
+
+
+def cpu_leg(kind, arg):
+    """Run one CPU leg ('patches' or 'chain') in a clean child process and return its JSON."""
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-leg", kind, "--cpu-arg", str(arg)], env=_clean_thread_env(),
+                         capture_output=True, text=True, timeout=900)
+    for ln in out.stdout.splitlines()[::-1]:
+        if ln.startswith("{"):
+            return json.loads(ln)
+    raise RuntimeError("cpu leg %s failed: %s" % (kind, out.stderr[-400:]))
+
+
+def run_cpu_leg(kind, arg):
+    if kind == "patches":                      # arg = "tiles" or "tiles x steps": one line, per-step values
+        parts = [int(v) for v in str(arg).split("x")]
+        n, steps = parts[0], (parts[1] if len(parts) > 1 else 1)
+        vals, secs, cores = [], [], 1
+        for _ in range(steps):
+            v, cores, dt = cpu_reference_tiles_per_s(n)
+            vals.append(v); secs.append(dt)
+        print(json.dumps({"value": float(np.mean(vals)), "values": vals, "cores": cores, "seconds": float(np.sum(secs)), "tiles": n,
+                          "steps": steps}), flush=True)
+    else:
+        print(json.dumps(cpu_reference_tile_chain(int(str(arg).split("x")[0]))), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n = 4
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_tiles_per_s(1)
-    vals = []
-    t_all = 0.0
-    for _ in range(args.steps):
-        v, cores, dt = cpu_reference_tiles_per_s(n)
-        vals.append(v); t_all += dt
+    r = cpu_leg("patches", "%dx%d" % (n, args.steps + min(args.warmup, 1)))      # one child process; its first step is the warm-up
+    vals = r["values"][min(args.warmup, 1):]
+    cores = r["cores"]
     value = float(np.mean(vals))
+    t_all = sum(n / v for v in vals)
     line = {"metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * t_all / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "configs[1]: batch=256 tiles, 12-step S1+S2 stack, assemble+normalize+ConvGRU/U-Net forward",
-                       "patch": [12, H, H, 13]},
+            "config": workload_config(args.batch),
             "cpu_baseline": {"value": value, "unit": "tiles/s", "cores": cores, "kind": "port",
                              "sample": "%d tiles per step (batch 1 each) of the 256-tile workload; torch-CPU restatement of the frozen graph "
                                        "(TensorFlow unavailable) + NumPy preprocessing" % n},
             "e2e": {"value": value, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_tile_chain:
+        try:
+            line["tile_chain"] = {"n12": cpu_leg("chain", 12)}
+        except Exception as e:             # the headline line must still print
+            line["tile_chain"] = {"error": str(e)[:200]}
     print(json.dumps(line), flush=True)
+
+
+def tile_chain_bench(sess, rank, world, barrier, peaks, reps):
+    """The whole per-tile loop body of the reference (download_and_predict_job.py:1995-2020) through ONE C call
+    (stc_tile_run_host): raw uint16 S2 10 m / 20 m + S1 cubes and the DEM in pinned host memory -> uint8 618x618 tree-cover
+    tile in host memory.  Wall clock around the synchronous call, H2D / D2H inside; every rank runs its own tile."""
+    import random
+    from sentinel_tree_cover_b200.synth import synth_raw_tile
+    out = {}
+    for n in (12, 24):
+        raw = synth_raw_tile(91 + rank, n=n, h=309, w=309)
+        pin = {k: sess.pinned_empty(raw[k].shape, raw[k].dtype) for k in ("s2_10", "s2_20", "s1", "dem")}
+        for k in pin:
+            pin[k][...] = raw[k]
+        for _ in range(2):
+            random.seed(4)
+            tile_u8, kept = sess.run_tile(pin["s2_10"], pin["s2_20"], pin["s1"], pin["dem"], raw["s2_dates"])
+        barrier()
+        l0 = sess.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            random.seed(4)
+            tile_u8, kept = sess.run_tile(pin["s2_10"], pin["s2_20"], pin["s1"], pin["dem"], raw["s2_dates"])
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        out["n%d" % n] = {"ms_per_tile": ms, "launches_per_tile": (sess.launch_count() - l0) // reps, "dates_kept": int(len(kept)),
+                          "h2d_bytes_per_tile": int(sum(pin[k].nbytes for k in pin)), "d2h_bytes_per_tile": int(tile_u8.nbytes),
+                          "tree_cover_mean": float(tile_u8[tile_u8 <= 100].mean()) if (tile_u8 <= 100).any() else None}
+        # one more tile with CUDA events around every kernel launch (stc_trace; not timed above)
+        csv_path = os.path.join(ROOT, "gpurun_out", "tile_trace_n%d_rank%d.csv" % (n, rank))
+        sess.trace(1)
+        random.seed(4)
+        sess.run_tile(pin["s2_10"], pin["s2_20"], pin["s1"], pin["dem"], raw["s2_dates"])
+        sess.trace(0, csv_path)
+        out["n%d" % n]["kernels"] = chain_kernel_table(csv_path, n, 618 * 618, peaks)
+    return out
+
+
+# algorithmic bytes per launch of the streaming kernels of the chain (SURVEY 8d: what one pass must read and write, f32),
+# as a function of (n dates, px pixels, launches of that kernel per tile)
+CHAIN_BYTES = {
+    "temporal_matmul_kernel": lambda n, px, k: (n + 12) * px * 14 * 4 / k,          # K1: n dates in, 12 months out, 14 channels over its launches
+    "sr_apply_kernel": None,
+    "k_cloud_refs": lambda n, px, k: (5 * 3 + 1 + 3) * px * 4,                       # <= 5-date window of 3 bands + shadow mask in, 3 refs out
+    "k_build_sentinel2": lambda n, px, k: n * px * (4 + 6 / 4.0 + 10) * 4,           # 10 m + 20 m stacks in, 10-band cube out
+    "k_mosaic_ref": lambda n, px, k: (n * px * 11 + n * px * 10) * 4 / k,
+    "indices_kernel": lambda n, px, k: n * px * (10 + 4) * 4 / k,
+}
+
+
+def chain_kernel_table(csv_path, n, px, peaks, top=12):
+    """Per-kernel totals of one traced tile: launches, summed CUDA-event time, share of the summed kernel time, and for the
+    streaming kernels in CHAIN_BYTES the achieved fraction of the measured HBM peak."""
+    import csv
+    tot = {}
+    for r in csv.DictReader(open(csv_path)):
+        d = float(r["end_ms"]) - float(r["start_ms"])
+        e = tot.setdefault(r["label"], [0, 0.0])
+        e[0] += 1; e[1] += d
+    all_ms = sum(v[1] for v in tot.values()) or 1.0
+    rows = []
+    for name, (k, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:top]:
+        row = {"kernel": name, "launches": k, "ms": round(ms, 3), "share": round(ms / all_ms, 3)}
+        f = CHAIN_BYTES.get(name)
+        if f:
+            gbs = f(n, px, k) * k / (ms / 1e3) / 1e9
+            row["hbm_gbs"] = round(gbs, 1); row["hbm_frac"] = round(gbs / peaks["hbm"], 3)
+        rows.append(row)
+    return {"sum_kernel_ms": round(all_ms, 2), "top": rows}
 
 
 def main():
@@ -238,7 +380,13 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tile-chain", action="store_true")
+    ap.add_argument("--tile-reps", type=int, default=5)
+    ap.add_argument("--cpu-leg", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-arg", default="8", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_leg:
+        return run_cpu_leg(args.cpu_leg, args.cpu_arg)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -261,6 +409,10 @@ def main():
     if world > 1:
         w = broadcast_weights(w, dist, device=torch.device("cuda", local))   # one NCCL broadcast at startup
     sess = StcSession(local, predict_weights=w)
+    chain_sess = None
+    if not args.no_tile_chain:          # the tile chain runs the RELEASED weights (its outputs are compared with goldens in tests/)
+        chain_sess = StcSession(local, predict_weights=os.path.join(GOLD, "weights_predict_172.npz"),
+                                superresolve_weights=os.path.join(GOLD, "weights_superresolve.npz"))
     B = args.batch
     Ho = H - 14
     # synthetic patches: 16 distinct seeded tiles tiled up to the batch (generation cost only)
@@ -348,6 +500,18 @@ def main():
     ms_u16 = max(ms_u16, (time.perf_counter() - t0) * 1000.0)
     sampler.stop_flag = True                 # clocks / throttle reasons were sampled across all three timed regions
     sampler.join(timeout=2)
+    chain = None
+    if chain_sess is not None:
+        _log("uint16 e2e done; whole-tile chain")
+        chain = tile_chain_bench(chain_sess, rank, world, barrier, measured_peaks(), args.tile_reps)
+        ct = torch.tensor([chain["n12"]["ms_per_tile"], chain["n24"]["ms_per_tile"]], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+        for k, v in zip(("n12", "n24"), ct.tolist()):
+            chain[k]["ms_per_tile"] = v
+            chain[k]["tiles_per_s"] = world * 1000.0 / v
+            chain[k]["subtile_patches_per_s"] = 36 * world * 1000.0 / v
+        chain_sess.close()
 
     t = torch.tensor([ms, ms_e2e, ms_u16], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -374,11 +538,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16", "data": "synthetic",
-                "config": {"workload": "configs[1]: batch=256 tiles, 12-step S1+S2 stack, assemble+normalize+ConvGRU/U-Net forward",
-                           "patch": [12, H, H, 13], "batch_per_gpu": B, "weights": "random-init, released architecture",
-                           "l2": "inputs (%.1f GB/step) exceed L2; no flush needed" % (nbytes_in / 1e9),
-                           "parallelism": "tiles sharded, one process per GPU, one NCCL weight broadcast",
-                           "conv_impl": "tcgen05" if os.environ.get("STC_CONV_IMPL", "0") == "0" else "simt"},
+                "config": workload_config(B),
                 "e2e": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": nbytes_out,
                         "ms_per_step": ms_e2e_max / args.steps},
                 "e2e_u16": {"value": tiles / (ms_u16_max / 1000.0), "unit": "tiles/s", "h2d_bytes_per_step": nbytes_in // 2,
@@ -396,11 +556,24 @@ def main():
                                      % (flops / args.steps, conv_launches_single, conv_ms_single / args.steps, ms_single / args.steps,
                                         ms / args.steps, conv_ms / args.steps, peaks["src"])},
                 "clocks": sampler.summary(), "checksum": checksum}
-        if not args.no_cpu_baseline:
-            v, cores, dt = cpu_reference_tiles_per_s(8)
-            line["cpu_baseline"] = {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port",
+        if chain is not None:
+            chain["note"] = ("whole per-tile loop body (process_tile -> superresolve_large_tile -> process_subtiles -> "
+                             "load_mosaic_predictions, download_and_predict_job.py:1995-2020) through ONE C call, stc_tile_run_host: raw "
+                             "uint16 618x618 cubes in pinned host memory -> uint8 tile; wall clock incl. H2D/D2H; released weights; one "
+                             "tile per rank; `kernels` = CUDA-event time of every launch of one extra traced tile")
+            line["tile_chain"] = chain
+        # rank 0 at N = 1 only (the spec's cpu_baseline rule); a child process so that no thread cap of this process applies
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_leg("patches", 8)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "tiles/s", "cores": r["cores"], "kind": "port",
                                     "sample": "8 tiles (batch 1 each, %.1f s) of the same workload; torch-CPU restatement of the frozen "
-                                              "graph (TensorFlow unavailable) + NumPy preprocessing" % dt}
+                                              "graph (TensorFlow unavailable) + NumPy preprocessing" % r["seconds"]}
+            if chain is not None:
+                try:
+                    chain["cpu_baseline"] = cpu_leg("chain", 12)
+                    chain["n12"]["vs_cpu_baseline"] = chain["n12"]["tiles_per_s"] / chain["cpu_baseline"]["value"]
+                except Exception as e:
+                    chain["cpu_baseline"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     sess.free(d_in); sess.free(d_out)
     sess.close()

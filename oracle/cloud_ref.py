@@ -260,27 +260,4 @@ def identify_clouds_shadows(img, dem, stages=False):
     return clouds, fcps
 
 
-def synth_cloudy_cube(T, H, W, seed):
-    """Sentinel-2-like cube [T,H,W,10] with vegetation/soil/water spectra, Gaussian-blob clouds
-    (+0.3..0.6 on every band) and displaced shadows (x0.3), plus a DEM [H,W]."""
-    r = np.random.default_rng(seed)
-    veg = np.array([0.035, 0.06, 0.045, 0.30, 0.10, 0.22, 0.28, 0.32, 0.17, 0.08], np.float32)
-    soil = np.array([0.09, 0.12, 0.15, 0.25, 0.18, 0.21, 0.23, 0.26, 0.30, 0.24], np.float32)
-    wat = np.array([0.05, 0.06, 0.04, 0.02, 0.03, 0.025, 0.02, 0.02, 0.01, 0.008], np.float32)
-    yy, xx = np.mgrid[0:H, 0:W]
-    mix = 0.5 + 0.5 * np.sin(xx / 17.0) * np.cos(yy / 23.0)
-    base = veg[None, None] * mix[..., None] + soil[None, None] * (1 - mix[..., None])
-    lake = (yy - H * 0.7) ** 2 + (xx - W * 0.25) ** 2 < (min(H, W) * 0.12) ** 2
-    base[lake] = wat
-    cube = np.repeat(base[None], T, 0) * (1 + 0.08 * np.sin(2 * np.pi * np.arange(T) / T))[:, None, None, None]
-    cube = cube + r.normal(0, 0.004, cube.shape)
-    for t in range(T):
-        for _ in range(r.integers(0, 3)):
-            cy, cx, s = r.integers(0, H), r.integers(0, W), r.uniform(5, 14)
-            blob = np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * s * s))
-            cube[t] += (r.uniform(0.3, 0.6) * (blob > 0.4))[..., None]
-            sy, sx = cy + int(1.5 * s), cx + int(1.2 * s)
-            sh = np.exp(-((yy - sy) ** 2 + (xx - sx) ** 2) / (2 * s * s)) > 0.45
-            cube[t][sh] *= 0.3
-    dem = (40 * (0.5 + 0.5 * np.sin(xx / 31.0 + yy / 47.0))).astype(np.float32)
-    return np.clip(cube, 0.001, 0.999).astype(np.float32), dem
+from sentinel_tree_cover_b200.synth import synth_cloudy_cube  # noqa: E402,F401  (seeded generator shared with bench.py)

@@ -71,6 +71,7 @@ class GraphInterpreter:
         self.dtype = dtype
         self.memo = {}
         self.feeds = {}
+        self.visited = {}          # node name -> op type, every node _compute ran (all runs, all loop iterations)
         if threads:
             torch.set_num_threads(threads)
         # while-loop frames, identified by the name prefix up to ".../while/"
@@ -86,6 +87,20 @@ class GraphInterpreter:
         self.frames = {k: None for k in self.frames}   # while-loop results are per run
         self.feeds = {k: np.asarray(v) for k, v in feeds.items()}
         return self._eval(fetch, None)
+
+    def ancestors(self, fetch):
+        """Every node the fetch depends on through data edges (static reachability, control edges excluded)."""
+        seen, stack = set(), [_split_name(fetch)[0]]
+        while stack:
+            n = stack.pop()
+            if n in seen:
+                continue
+            seen.add(n)
+            for r in self.nodes[n]["inputs"]:
+                m, _ = _split_name(r)
+                if m is not None and m not in seen:
+                    stack.append(m)
+        return seen
 
     def _frame_of(self, name):
         for p in self.frames:
@@ -145,6 +160,7 @@ class GraphInterpreter:
     def _compute(self, n, it):
         op, name, a = n["op"], n["name"], n["attr"]
         ins = [r for r in n["inputs"] if not r.startswith("^")]
+        self.visited[name] = op
 
         if op == "Const":
             v = a["value"]

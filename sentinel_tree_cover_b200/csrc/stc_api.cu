@@ -41,6 +41,9 @@ void stc_destroy(stc_ctx* ctx) {
     if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
   }
   if (ctx->stage_out) cudaFree(ctx->stage_out);
+  if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
+  if (ctx->stage_ring) cudaFreeHost(ctx->stage_ring);
+  if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->aux_ev[0]); cudaEventDestroy(ctx->aux_ev[1]); }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (int i = 0; i < stc_ctx::MAX_SLOTS; ++i) {
     if (ctx->hi_stream[i]) cudaStreamDestroy(ctx->hi_stream[i]);

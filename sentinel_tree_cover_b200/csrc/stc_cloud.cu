@@ -644,11 +644,11 @@ static CloudWin cloud_window(int t, int T) {
 // shared with stc_cloudfill.cu: binary dilation / erosion-by-dilation on [frames][H][W] uint8 masks
 void maskop_dilate(stc_ctx* ctx, const unsigned char* in, unsigned char* out, int frames, int H, int W, int k, int conn, int inv_in,
                    int inv_out, int three_d) {
-  k_dilate<<<cdiv((int64_t)frames * H * W, 256), 256, 0, ctx->stream>>>(in, out, frames, H, W, k, conn, inv_in, inv_out, three_d);
+  { TraceScope ts_(ctx, "k_dilate"); k_dilate<<<cdiv((int64_t)frames * H * W, 256), 256, 0, ctx->stream>>>(in, out, frames, H, W, k, conn, inv_in, inv_out, three_d); }
   ctx->launches++;
 }
 
-#define LAUNCH1D(kern, n, ...) do { kern<<<cdiv((n), 256), 256, 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
+#define LAUNCH1D(kern, n, ...) do { TraceScope ts_(ctx, #kern); kern<<<cdiv((n), 256), 256, 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
 
 // Device-resident core: img_dev [T,H,W,10] float32, dem_dev [H,W]; clouds_dev [T,H,W] float32, fcps_dev [T,H,W] uint8.
 // Returns with its kernels enqueued on ctx->stream (it synchronises internally where the reference's control flow needs
@@ -675,7 +675,7 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   StaticRefs sr{(float*)d_water.p, (float*)d_allref.p, (float*)d_minb4.p, (float*)d_p25.p, (float*)d_minrgb.p};
   const float* water = sr.water;
   auto dilate = [&](const unsigned char* in, unsigned char* out, int64_t frames, int k, int conn, int inv_in, int inv_out, int three_d) {
-    k_dilate<<<cdiv(frames * HW, 256), 256, 0, ctx->stream>>>(in, out, (int)frames, H, W, k, conn, inv_in, inv_out, three_d);
+    { TraceScope ts_(ctx, "k_dilate"); k_dilate<<<cdiv(frames * HW, 256), 256, 0, ctx->stream>>>(in, out, (int)frames, H, W, k, conn, inv_in, inv_out, three_d); }
     ctx->launches++;
   };
   auto dump = [&](int id, const unsigned char* src) -> int {     // stage taps for the tests
@@ -688,9 +688,9 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   // NumPy-exact float32 {mean, std} of f_kind over the clear pixels of every date -> mom_h[t*2..], cnt_h[t*2..]
   std::vector<float> mom_h(2 * CT_MAX); std::vector<int> cnt_h(2 * CT_MAX);
   auto moments = [&](int kind, const float* medb, const int* all_px, bool to_host) -> int {
-    k_compact<<<T, 1024, 0, ctx->stream>>>(img, cl, water, medb, all_px, HW, kind, (float*)d_vals.p, (int*)d_cnts.p);
-    k_np_moments<<<T, 1024, 0, ctx->stream>>>((const float*)d_vals.p, (const int*)d_cnts.p, HW, node_cap, (int2*)d_leaves.p,
-                                              (int*)d_child.p, (float*)d_leafsum.p, (float*)d_mom.p);
+    { TraceScope ts_(ctx, "k_compact"); k_compact<<<T, 1024, 0, ctx->stream>>>(img, cl, water, medb, all_px, HW, kind, (float*)d_vals.p, (int*)d_cnts.p); }
+    { TraceScope ts_(ctx, "k_np_moments"); k_np_moments<<<T, 1024, 0, ctx->stream>>>((const float*)d_vals.p, (const int*)d_cnts.p, HW, node_cap, (int2*)d_leaves.p,
+                                              (int*)d_child.p, (float*)d_leafsum.p, (float*)d_mom.p); }
     ctx->launches += 2;
     if (to_host) {
       STC_CUDA(cudaMemcpyAsync(mom_h.data(), d_mom.p, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -705,7 +705,7 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   LAUNCH1D(k_hollstein, N, img, ta, N);
   dilate(ta, tb, T, 2, 1, 1, 1, 0);
   dilate(tb, clm, T, 10, 1, 0, 0, 0);
-  k_static_refs<<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, clm, T, HW, sr); ctx->launches++;
+  { TraceScope ts_(ctx, "k_static_refs"); k_static_refs<<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, clm, T, HW, sr); } ctx->launches++;
   if ((rc_ = dump(1, clm))) return rc_;
 
   // ---- B: shadows ----
@@ -713,15 +713,15 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
     int wl[2 * CT_MAX];
     for (int t = 0; t < T; ++t) shadow_window(t, T, wl[t], wl[CT_MAX + t]);
     STC_CUDA(cudaMemcpyAsync(d_win.p, wl, sizeof(wl), cudaMemcpyHostToDevice, ctx->stream));
-    k_shadow_candidates<<<dim3(cdiv(HW, 128), T), 128, 0, ctx->stream>>>(img, clm, dem, sr, T, HW, (const int*)d_win.p,
-                                                                         (const int*)d_win.p + CT_MAX, ta);
+    { TraceScope ts_(ctx, "k_shadow_candidates"); k_shadow_candidates<<<dim3(cdiv(HW, 128), T), 128, 0, ctx->stream>>>(img, clm, dem, sr, T, HW, (const int*)d_win.p,
+                                                                         (const int*)d_win.p + CT_MAX, ta); }
     ctx->launches++;
     STC_CUDA(cudaStreamSynchronize(ctx->stream));   // wl is a stack buffer
     if ((rc_ = dump(2, ta))) return rc_;
     dilate(ta, tb, T, 2, 1, 1, 1, 0);
     dilate(tb, tc, T, 3, 1, 0, 0, 0);
     STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
-    k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tc, HW, (int*)d_all.p); ctx->launches++;
+    { TraceScope ts_(ctx, "k_count_dates"); k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tc, HW, (int*)d_all.p); } ctx->launches++;
     LAUNCH1D(k_edt_grow, N, tc, sh, T, H, W, 5, (const int*)d_all.p);
     if ((rc_ = dump(3, sh))) return rc_;
   }
@@ -729,7 +729,7 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   // ---- C: clouds ----
   for (int t = 0; t < T; ++t) {
     CloudWin w = cloud_window(t, T);
-    k_cloud_refs<<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, sh, sr, T, HW, t, w, (float*)d_rc.p, (float*)d_thr.p, (unsigned char*)d_ci.p);
+    { TraceScope ts_(ctx, "k_cloud_refs"); k_cloud_refs<<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, sh, sr, T, HW, t, w, (float*)d_rc.p, (float*)d_thr.p, (unsigned char*)d_ci.p); }
     ctx->launches++;
     int cnt[2] = {0, 0};
     STC_CUDA(cudaMemsetAsync(d_cnt.p, 0, 8, ctx->stream));
@@ -754,17 +754,17 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
 
   // ---- D: brightness z-score + whiteness ----
   {
-    k_masked_median<<<T, 1024, 0, ctx->stream>>>(img, cl, sh, HW, (float*)d_med.p); ctx->launches++;
+    { TraceScope ts_(ctx, "k_masked_median"); k_masked_median<<<T, 1024, 0, ctx->stream>>>(img, cl, sh, HW, (float*)d_med.p); } ctx->launches++;
     // `if np.sum(clouds[i] < 0.90)`: select clear pixels when any exists, else every pixel
     int allpx[CT_MAX];
     STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
-    k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(cl, HW, (int*)d_all.p); ctx->launches++;
+    { TraceScope ts_(ctx, "k_count_dates"); k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(cl, HW, (int*)d_all.p); } ctx->launches++;
     STC_CUDA(cudaMemcpyAsync(allpx, d_all.p, T * 4, cudaMemcpyDeviceToHost, ctx->stream));
     STC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int t = 0; t < T; ++t) allpx[t] = (allpx[t] == HW);
     STC_CUDA(cudaMemcpyAsync(d_all.p, allpx, T * 4, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc_ = moments(0, (const float*)d_med.p, (const int*)d_all.p, false))) return rc_;
-    k_bright_clouds<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(img, water, (const float*)d_med.p, (const float*)d_mom.p, T, HW, bc);
+    { TraceScope ts_(ctx, "k_bright_clouds"); k_bright_clouds<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(img, water, (const float*)d_med.p, (const float*)d_mom.p, T, HW, bc); }
     ctx->launches++;
     LAUNCH1D(k_bright_merge, HW, img, bc, T, HW, cl);
     STC_CUDA(cudaStreamSynchronize(ctx->stream));   // allpx is a stack buffer
@@ -774,7 +774,7 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   // ---- E: false positives ----
   LAUNCH1D(k_nsr, N, img, ta, N);
   dilate(ta, nsr, T, 3, 1, 0, 0, 1);                                            // 3-D dilation (:1518)
-  k_fp1<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(img, water, T, HW, nsr, cl, ta); ctx->launches++;
+  { TraceScope ts_(ctx, "k_fp1"); k_fp1<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(img, water, T, HW, nsr, cl, ta); } ctx->launches++;
   dilate(ta, tb, T, 10, 1, 0, 0, 0);
   LAUNCH1D(k_clear_where, N, cl, tb, N);
   LAUNCH1D(k_winsum_lt, N, cl, ta, T, H, W, 5);
@@ -782,8 +782,8 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   LAUNCH1D(k_dark, N, img, ta, N);
   dilate(ta, tb, T, 3, 1, 0, 0, 0);
   STC_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * CT_MAX * 4, ctx->stream));
-  k_any01<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tb, HW, (int*)d_flags.p); ctx->launches++;
-  k_zero_rows<<<dim3(cdiv(W, 256), T), 256, 0, ctx->stream>>>(cl, (const int*)d_flags.p, H, W); ctx->launches++;
+  { TraceScope ts_(ctx, "k_any01"); k_any01<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tb, HW, (int*)d_flags.p); } ctx->launches++;
+  { TraceScope ts_(ctx, "k_zero_rows"); k_zero_rows<<<dim3(cdiv(W, 256), T), 256, 0, ctx->stream>>>(cl, (const int*)d_flags.p, H, W); } ctx->launches++;
   if ((rc_ = dump(6, cl))) return rc_;
 
   // ---- F: shape clean-up (pfcps == 0: no urban clouds) ----
@@ -793,7 +793,7 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   dilate(tb, ta, T, 5, 1, 0, 0, 0);
   LAUNCH1D(k_or, N, cl, ta, tb, N);
   STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
-  k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tb, HW, (int*)d_all.p); ctx->launches++;
+  { TraceScope ts_(ctx, "k_count_dates"); k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tb, HW, (int*)d_all.p); } ctx->launches++;
   LAUNCH1D(k_edt_grow, N, tb, cl, T, H, W, 3, (const int*)d_all.p);
   if ((rc_ = dump(7, cl))) return rc_;
 

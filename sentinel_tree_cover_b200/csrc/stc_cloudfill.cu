@@ -16,6 +16,7 @@
 // NumPy's float32 lerp).  The regression is float64 with a different summation order than
 // LAPACK/BLAS: filled pixels agree to ~1e-6 relative (tests/test_cloud_fill.py: rtol 1e-4).
 #include "stc_common.cuh"
+#include "stc_select.cuh"
 #include <chrono>
 #include <cstdio>
 #include <algorithm>
@@ -152,70 +153,22 @@ __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ t
   ref_rows_all[slab + (int64_t)r * 10 + c] = ref_all[slab + idx];
 }
 
-// exact k-th order statistics of a strided float32 column by MSB-first radix select; one block per (matrix, column)
-struct SelectJob { const float* data; int64_t stride; int n; int k; };
-__device__ float block_radix_select(const float* __restrict__ data, int64_t stride, int n, int k) {
-  __shared__ int hist[256]; __shared__ unsigned prefix; __shared__ int kth;
-  if (threadIdx.x == 0) { prefix = 0; kth = k; }
-  __syncthreads();
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    const unsigned pre = prefix;
-    const unsigned mask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      unsigned u = __float_as_uint(data[(int64_t)i * stride]); u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
-      if ((u & mask) == (pre & mask)) atomicAdd(&hist[(u >> shift) & 255], 1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int kk = kth, b = 0;
-      while (b < 255 && kk >= hist[b]) { kk -= hist[b]; ++b; }
-      kth = kk; prefix = pre | ((unsigned)b << shift);
-    }
-    __syncthreads();
-  }
-  unsigned u = prefix; u ^= (u >> 31) ? 0x80000000u : 0xffffffffu;
-  __syncthreads();
-  return __uint_as_float(u);
-}
-// the order statistic of rank k+1 given a = rank k: a again if more than k+1 values are <= a, else min(x > a)
-__device__ float block_next_stat(const float* __restrict__ data, int64_t stride, int n, float a, int k) {
-  __shared__ int cnt_le; __shared__ unsigned min_gt;
-  if (threadIdx.x == 0) { cnt_le = 0; min_gt = 0xffffffffu; }
-  __syncthreads();
-  unsigned ka = __float_as_uint(a); ka ^= (ka >> 31) ? 0xffffffffu : 0x80000000u;
-  int c = 0; unsigned mn = 0xffffffffu;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    unsigned u = __float_as_uint(data[(int64_t)i * stride]); u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
-    if (u <= ka) ++c; else if (u < mn) mn = u;
-  }
-  for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); unsigned t = __shfl_xor_sync(0xffffffffu, mn, o); mn = t < mn ? t : mn; }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt_le, c); atomicMin(&min_gt, mn); }
-  __syncthreads();
-  float b;
-  if (cnt_le >= k + 2) b = a;
-  else { unsigned u = min_gt; u ^= (u >> 31) ? 0x80000000u : 0xffffffffu; b = __uint_as_float(u); }
-  __syncthreads();
-  return b;
-}
-// quantile q of each job's column with NumPy's float32 lerp (np.median's even case is (a+b)/2, which differs from
-// a + (b-a)*0.5 in float32, so the median has its own flag)
-__global__ void __launch_bounds__(1024) k_quantile(const SelectJob* __restrict__ jobs, const double* __restrict__ q, int median_mode,
-                                                   float* __restrict__ out) {
-  const SelectJob j = jobs[blockIdx.x];
-  if (j.n <= 0) { if (threadIdx.x == 0) out[blockIdx.x] = nanf(""); return; }
-  if (median_mode) {
-    float a = block_radix_select(j.data, j.stride, j.n, (j.n - 1) / 2);
-    float b = (j.n & 1) ? a : block_next_stat(j.data, j.stride, j.n, a, (j.n - 1) / 2);
-    if (threadIdx.x == 0) out[blockIdx.x] = (j.n & 1) ? a : __fdiv_rn(__fadd_rn(a, b), 2.f);
-    return;
-  }
+// np.median / np.percentile from the (x_(k), x_(k+1)) pairs of select_ranks_dev: NumPy's even-length median is (a + b) / 2,
+// its percentile the float32 lerp between the two neighbouring order statistics.
+struct QSpec { int slot; int n; double q; int median; };
+__global__ void __launch_bounds__(128) k_quantile_finish(const float* __restrict__ pairs, const QSpec* __restrict__ specs, int nspec,
+                                                         float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nspec) return;
+  const QSpec s = specs[i];
+  if (s.n <= 0) { out[i] = nanf(""); return; }
+  const float a = pairs[2 * s.slot];
+  float b = pairs[2 * s.slot + 1];
+  if (s.median) { out[i] = (s.n & 1) ? a : __fdiv_rn(__fadd_rn(a, b), 2.f); return; }
   int lo; float g;
-  np_quantile_pos(j.n, q[blockIdx.x], lo, g);
-  float a = block_radix_select(j.data, j.stride, j.n, lo);
-  float b = (lo + 1 < j.n && g != 0.f) ? block_next_stat(j.data, j.stride, j.n, a, lo) : a;
-  if (threadIdx.x == 0) out[blockIdx.x] = np_lerp(a, b, g);
+  np_quantile_pos(s.n, s.q, lo, g);
+  if (!(lo + 1 < s.n && g != 0.f)) b = a;
+  out[i] = np_lerp(a, b, g);
 }
 
 // np.nanstd(rows, axis=0) of a [K][10] float32 matrix: NumPy reduces axis 0 row by row, i.e. each column is a
@@ -391,19 +344,54 @@ __global__ void __launch_bounds__(256) k_collect_rows(const float* __restrict__ 
 }
 
 // stratum bits of every row against the six EVI percentiles b = {2,20,40,60,80,98} (:455-467)
-__global__ void __launch_bounds__(256) k_strata(const float* __restrict__ evi, const float* __restrict__ b, int K, unsigned char* __restrict__ lab) {
+__global__ void __launch_bounds__(256) k_strata(const float* __restrict__ evi, const float* __restrict__ b, int K, unsigned char* __restrict__ lab,
+                                                int* __restrict__ counts /*[7], zeroed*/) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= K) return;
-  float e = evi[r];
   unsigned char m = 0;
-  if (e < b[0]) m |= 1;                       // p2
-  if (e < b[1]) m |= 2;                       // p20
-  if (e >= b[1] && e < b[2]) m |= 4;          // p40
-  if (e >= b[2] && e < b[3]) m |= 8;          // p60
-  if (e >= b[3] && e < b[4]) m |= 16;         // p80
-  if (e >= b[4]) m |= 32;                     // p100
-  if (e >= b[5]) m |= 64;                     // p98
-  lab[r] = m;
+  if (r < K) {
+    float e = evi[r];
+    if (e < b[0]) m |= 1;                       // p2
+    if (e < b[1]) m |= 2;                       // p20
+    if (e >= b[1] && e < b[2]) m |= 4;          // p40
+    if (e >= b[2] && e < b[3]) m |= 8;          // p60
+    if (e >= b[3] && e < b[4]) m |= 16;         // p80
+    if (e >= b[4]) m |= 32;                     // p100
+    if (e >= b[5]) m |= 64;                     // p98
+    lab[r] = m;
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    unsigned bal = __ballot_sync(0xffffffffu, (m >> k) & 1);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(counts + k, __popc(bal));
+  }
+}
+// Index lists of the seven strata of one date, rows in ascending order (np.argwhere), the two 2 % tails repeated ten
+// times per row (np.repeat(.., 10), :468-471).  One block per (stratum, date): order-preserving compaction.
+struct BucketJob { const unsigned char* lab; int K; int* out[7]; };
+__global__ void __launch_bounds__(1024) k_bucket_lists(const BucketJob* __restrict__ jobs) {
+  const BucketJob j = jobs[blockIdx.y];
+  const int k = blockIdx.x, rep = (k == 0 || k == 6) ? 10 : 1;
+  int* out = j.out[k];
+  __shared__ int wtot[32]; __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int r0 = 0; r0 < j.K; r0 += 1024) {
+    const int r = r0 + threadIdx.x;
+    const bool f = r < j.K && ((j.lab[r] >> k) & 1);
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) wtot[wid] = __popc(bal);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { const int c = wtot[w]; if (w < wid) woff += c; tot += c; }
+    if (f) {
+      const int pos = (base + woff + __popc(bal & ((1u << lane) - 1u))) * rep;
+      for (int q = 0; q < rep; ++q) out[pos + q] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base += tot;
+    __syncthreads();
+  }
 }
 
 // float64 Gram sums over the sampled rows.  Features u_j = [mosaic bands, snow], c_j = clip(u_j, 0.005, 1)
@@ -643,9 +631,9 @@ struct PyRandom {
   // rejected draw changes nothing.  The loop below therefore advances one output per iteration and turns the accept test
   // into arithmetic (a rejected draw swaps x[i] with itself and leaves i alone): no unpredictable branch, ~3x faster than
   // the textbook rejection loop (the accept rate is 50-100 %).  All i of one power-of-two band share the shift.
-  void shuffle(std::vector<int>& x) {
-    int* v = x.data();
-    size_t i = x.size();
+  void shuffle(std::vector<int>& x) { shuffle(x.data(), x.size()); }
+  void shuffle(int* v, size_t len) {
+    size_t i = len;
     if (i < 2) return;
     --i;                                   // i = len - 1
     while (i >= 1) {
@@ -680,7 +668,7 @@ __global__ void __launch_bounds__(256) k_count_zero(const unsigned char* __restr
 }
 }  // namespace
 
-#define CF_LAUNCH(kern, grid, block, ...) do { kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
+#define CF_LAUNCH(kern, grid, block, ...) do { TraceScope ts_(ctx, #kern); kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
 #define CF_SYNC() STC_CUDA(cudaStreamSynchronize(ctx->stream))
 
 namespace {
@@ -713,7 +701,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
     cf_t = t;
   };
   DBuf d_ta, d_tb, d_sums, d_water0, d_water1, d_flag, d_u8a, d_u8b, d_pf, d_ref, d_pos, d_src_rows,
-      d_ref_rows, d_mosaic, d_div, d_snow, d_rowsrc, d_evi, d_lab, d_sample, d_partial, d_gram, d_coef, d_status, d_jobs, d_q, d_qout,
+      d_ref_rows, d_mosaic, d_div, d_snow, d_partial, d_gram, d_coef, d_status, d_qout,
       d_sd, d_params, d_cnt, d_counts;
   const int gram_blocks = 296;
   STC_CUDA(stc_dmalloc(&d_ta.p, N * 4)); STC_CUDA(stc_dmalloc(&d_tb.p, N * 4)); STC_CUDA(stc_dmalloc(&d_sums.p, CF_MAX_DATES * 4));
@@ -721,11 +709,9 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   STC_CUDA(stc_dmalloc(&d_ref.p, (int64_t)HW * 40)); STC_CUDA(stc_dmalloc(&d_pos.p, (int64_t)HW * 4));
   STC_CUDA(stc_dmalloc(&d_src_rows.p, (int64_t)HW * 40)); STC_CUDA(stc_dmalloc(&d_ref_rows.p, (int64_t)HW * 40));
   STC_CUDA(stc_dmalloc(&d_mosaic.p, (int64_t)HW * 40)); STC_CUDA(stc_dmalloc(&d_div.p, (int64_t)HW * 4)); STC_CUDA(stc_dmalloc(&d_snow.p, (int64_t)HW * 4));
-  STC_CUDA(stc_dmalloc(&d_rowsrc.p, (int64_t)HW * 12)); STC_CUDA(stc_dmalloc(&d_evi.p, (int64_t)HW * 12)); STC_CUDA(stc_dmalloc(&d_lab.p, (int64_t)HW * 3));
-  STC_CUDA(stc_dmalloc(&d_sample.p, (int64_t)HW * 12));
   STC_CUDA(stc_dmalloc(&d_partial.p, (size_t)gram_blocks * GRAM_N * 8)); STC_CUDA(stc_dmalloc(&d_gram.p, GRAM_N * 8));
   STC_CUDA(stc_dmalloc(&d_coef.p, 10 * NF * 8)); STC_CUDA(stc_dmalloc(&d_status.p, 64));
-  STC_CUDA(stc_dmalloc(&d_jobs.p, 32 * sizeof(SelectJob))); STC_CUDA(stc_dmalloc(&d_q.p, 32 * 8)); STC_CUDA(stc_dmalloc(&d_qout.p, 32 * 4));
+  STC_CUDA(stc_dmalloc(&d_qout.p, 32 * 4));
   STC_CUDA(stc_dmalloc(&d_sd.p, 32 * 4)); STC_CUDA(stc_dmalloc(&d_params.p, 32 * 4)); STC_CUDA(stc_dmalloc(&d_cnt.p, 64));
   STC_CUDA(stc_dmalloc(&d_counts.p, CF_MAX_DATES * 5 * 4));
   float* mosaic = d_mosaic.as<float>();
@@ -733,11 +719,25 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
                 *u8a = d_u8a.as<unsigned char>(), *u8b = d_u8b.as<unsigned char>(), *pf = d_pf.as<unsigned char>();
   int* cnt = d_cnt.as<int>();
 
-  auto run_quantiles = [&](const std::vector<SelectJob>& jobs, const std::vector<double>& q, int median_mode, float* out_dev) -> int {
-    STC_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(SelectJob), cudaMemcpyHostToDevice, ctx->stream));
-    if (!median_mode) STC_CUDA(cudaMemcpyAsync(d_q.p, q.data(), q.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CF_LAUNCH(k_quantile, (int)jobs.size(), 1024, d_jobs.as<SelectJob>(), d_q.as<double>(), median_mode, out_dev);
-    CF_SYNC();      // jobs / q are host vectors
+  // out_dev[i] = the median / percentile described by specs[i]; every (job, column) slot serves one spec.  Asynchronous.
+  auto run_select = [&](const std::vector<SelJob>& jobs, const std::vector<QSpec>& specs, float* out_dev) -> int {
+    const int nj = (int)jobs.size(), ns = (int)specs.size();
+    std::vector<int> ks((size_t)nj * SEL_MAX_COLS, 0);
+    for (const QSpec& sp : specs) {
+      if (sp.n <= 0) continue;
+      if (sp.median) ks[sp.slot] = (sp.n - 1) / 2;
+      else { int lo; float g; np_quantile_pos(sp.n, sp.q, lo, g); ks[sp.slot] = lo; }
+    }
+    DBuf d_ks, d_pairs, d_specs;
+    STC_CUDA(stc_dmalloc(&d_ks.p, ks.size() * 4)); STC_CUDA(stc_dmalloc(&d_pairs.p, ks.size() * 8)); STC_CUDA(stc_dmalloc(&d_specs.p, (size_t)ns * sizeof(QSpec)));
+    const void* hk = ctx_stage(ctx, ks.data(), ks.size() * 4);
+    const void* hs = ctx_stage(ctx, specs.data(), (size_t)ns * sizeof(QSpec));
+    if (!hk || !hs) STC_FAIL(STC_ERR_NOMEM, "remove_clouds: pinned staging");
+    STC_CUDA(cudaMemcpyAsync(d_ks.p, hk, ks.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    STC_CUDA(cudaMemcpyAsync(d_specs.p, hs, (size_t)ns * sizeof(QSpec), cudaMemcpyHostToDevice, ctx->stream));
+    int rcs = select_ranks_dev(ctx, jobs.data(), nj, d_ks.as<int>(), d_pairs.as<float>());
+    if (rcs) return rcs;
+    CF_LAUNCH(k_quantile_finish, cdiv(ns, 128), 128, d_pairs.as<float>(), d_specs.as<QSpec>(), ns, out_dev);
     return STC_OK;
   };
   int rc;
@@ -760,14 +760,13 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   // stays in date order (float32 sum order).  A date that cannot be aligned (<= 1000 usable pixels) sets its weights to 1
   // (:679-680), which changes the reference images of the LATER dates: the batch is then cut at that date and restarted
   // behind it, exactly reproducing the sequential loop.
-  DBuf d_refall, d_flagall, d_posall, d_srcall, d_refrowsall, d_Ks, d_medall, d_sdall, d_paramsall, d_jobsall;
+  DBuf d_refall, d_flagall, d_posall, d_srcall, d_refrowsall, d_Ks, d_medall, d_sdall, d_paramsall;
   const int64_t slab = (int64_t)HW * 10;
   STC_CUDA(stc_dmalloc(&d_refall.p, (size_t)n * slab * 4)); STC_CUDA(stc_dmalloc(&d_srcall.p, (size_t)n * slab * 4));
   STC_CUDA(stc_dmalloc(&d_refrowsall.p, (size_t)n * slab * 4));
   STC_CUDA(stc_dmalloc(&d_flagall.p, (size_t)n * HW)); STC_CUDA(stc_dmalloc(&d_posall.p, (size_t)n * HW * 4));
   STC_CUDA(stc_dmalloc(&d_Ks.p, CF_MAX_DATES * 4)); STC_CUDA(stc_dmalloc(&d_medall.p, CF_MAX_DATES * 20 * 4));
   STC_CUDA(stc_dmalloc(&d_sdall.p, CF_MAX_DATES * 20 * 4)); STC_CUDA(stc_dmalloc(&d_paramsall.p, CF_MAX_DATES * 20 * 4));
-  STC_CUDA(stc_dmalloc(&d_jobsall.p, CF_MAX_DATES * 20 * sizeof(SelectJob)));
   int land_px = 0;
   STC_CUDA(cudaMemcpyAsync(&land_px, cnt + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<int> Ks(n, 0);
@@ -785,19 +784,29 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       const int cv = f - start;
       CF_LAUNCH(k_gather_rows, dim3(cdiv(slab, 256), cv), 256, tiles, d_refall.as<float>(), d_posall.as<int>(), HW, start,
                 d_srcall.as<float>(), d_refrowsall.as<float>());
-      std::vector<SelectJob> jobs;
+      // np.nanstd's column chains are sequential by definition (k_col_std: 20 warps per date, ~3 ms): they run on a side
+      // stream next to the medians, which use the whole GPU
+      if (!ctx->aux_stream) {
+        STC_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        STC_CUDA(cudaEventCreateWithFlags(&ctx->aux_ev[0], cudaEventDisableTiming)); STC_CUDA(cudaEventCreateWithFlags(&ctx->aux_ev[1], cudaEventDisableTiming));
+      }
+      STC_CUDA(cudaEventRecord(ctx->aux_ev[0], ctx->stream));
+      STC_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
+      { k_col_std<<<dim3(2, cv), 320, 0, ctx->aux_stream>>>(d_srcall.as<float>(), d_refrowsall.as<float>(), slab, d_Ks.as<int>(), start, d_sdall.as<float>()); }
+      ctx->launches++;
+      STC_CUDA(cudaEventRecord(ctx->aux_ev[1], ctx->aux_stream));
+      std::vector<SelJob> jobs; std::vector<QSpec> specs;
       for (int i = start; i < f; ++i)
-        for (int mm = 0; mm < 2; ++mm)
-          for (int c = 0; c < 10; ++c)
-            jobs.push_back({(mm ? d_refrowsall.as<float>() : d_srcall.as<float>()) + (int64_t)i * slab + c, 10, Ks[i], 0});
-      STC_CUDA(cudaMemcpyAsync(d_jobsall.p, jobs.data(), jobs.size() * sizeof(SelectJob), cudaMemcpyHostToDevice, ctx->stream));
-      CF_LAUNCH(k_quantile, (int)jobs.size(), 1024, d_jobsall.as<SelectJob>(), (const double*)nullptr, 1, d_medall.as<float>() + start * 20);
-      CF_LAUNCH(k_col_std, dim3(2, cv), 320, d_srcall.as<float>(), d_refrowsall.as<float>(), slab, d_Ks.as<int>(), start, d_sdall.as<float>());
+        for (int mm = 0; mm < 2; ++mm) {
+          jobs.push_back(SelJob{(mm ? d_refrowsall.as<float>() : d_srcall.as<float>()) + (int64_t)i * slab, Ks[i], 10, 10});
+          for (int c = 0; c < 10; ++c) specs.push_back(QSpec{(int)(jobs.size() - 1) * SEL_MAX_COLS + c, Ks[i], 0.0, 1});
+        }
+      if ((rc = run_select(jobs, specs, d_medall.as<float>() + start * 20))) return rc;
+      STC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1], 0));
       CF_LAUNCH(k_scale_params, cv, 32, d_medall.as<float>() + start * 20, d_sdall.as<float>() + start * 20, d_paramsall.as<float>() + start * 20);
       for (int i = start; i < f; ++i)
         CF_LAUNCH(k_mosaic_accum, cdiv(slab, 256), 256, tiles + (int64_t)i * slab, areas + (int64_t)i * HW, water0,
                   d_paramsall.as<float>() + i * 20, HW, mosaic);
-      CF_SYNC();                                             // `jobs` is a host vector
     }
     if (f < n && land_px > 0)
       CF_LAUNCH(k_fill_f, cdiv(HW, 256), 256, areas + (int64_t)f * HW, (int64_t)HW, 1.f);      // interp[i] = 1. (:679-680)
@@ -817,95 +826,138 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   STC_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, n * 20, cudaMemcpyDeviceToHost, ctx->stream));
   CF_SYNC();
   PyRandom rng; memcpy(rng.mt, mt_state, 624 * 4); rng.idx = (int)mt_state[624];
-  std::vector<unsigned char> lab;
-  std::vector<int> p2, p20, p40, p60, p80, p100, p98, sample;      // reused across dates: fresh multi-MB vectors page-fault on every date
-  double t_gpu1 = 0, t_bucket = 0, t_shuffle = 0, t_gpu2 = 0; long long n_draw = 0;
+  // ---- 3a. everything about the per-date fits that does NOT depend on the blending of earlier dates, for all dates at once:
+  //      the clear-land rows of a date's window [lo, hi) (weights == 0: the blend never touches them), their EVI, the six EVI
+  //      percentiles, the stratum bits and the seven ordered index lists (:421-471).  One synchronisation for the stratum
+  //      sizes, one for the lists; the lists land in pinned host memory.
+  struct FitJob { int d, lo, hi, K; int64_t row0; int cnt[7]; int64_t list0[7]; };
+  std::vector<FitJob> fits;
+  std::vector<int> fit_of(n, -1);
+  int64_t total_rows = 0;
   for (int d = 0; d < n; ++d) {
     const int c_pos = counts[d * 5], c_zero = counts[d * 5 + 1], c_lt1 = counts[d * 5 + 2], c_one = counts[d * 5 + 3];
     to_remove_host[d] = (c_one == HW);
-    if (!(c_pos > 0 && c_zero > 0)) {
-      if (c_pos > 0)      // no clear pixel at all: the interpolated array stays the raw mosaic
-        CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, (const float*)nullptr,
-                  d_coef.as<double>(), 0, HW);
-      continue;
-    }
+    if (!(c_pos > 0 && c_zero > 0)) continue;
     if (!((double)c_lt1 / (double)HW > 0.01))
       STC_FAIL(STC_ERR_STATE, "remove_clouds: date with <= 1% non-saturated pixels -- the reference raises UnboundLocalError here (cloud_removal.py:575)");
-    int lo, hi;
-    if (c_zero > 40000) { lo = d; hi = d + 1; }
-    else { lo = (d == n - 1) ? std::max(d - 2, 0) : std::max(d - 1, 0); hi = std::min(d + 2, n); }
-    double tt0 = cf_timing ? cf_now() : 0;
-    CF_LAUNCH(k_snow_mean, cdiv(HW, 256), 256, tiles, n, HW, d_snow.as<float>());
-    int K = 0;
-    for (int t = lo; t < hi; ++t) {
-      CF_LAUNCH(k_collect_rows, cdiv(HW, 256), 256, tiles, d_posall.as<int>() + (int64_t)t * HW, HW, t, K, d_rowsrc.as<int>(), d_evi.as<float>());
-      K += counts[t * 5 + 4];
-    }
-    if (K < 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: no clear land pixel to fit on -- the reference fails in np.percentile here");
-    {
-      std::vector<SelectJob> jobs(6, SelectJob{d_evi.as<float>(), 1, K, 0});
-      std::vector<double> q = {2 / 100.0, 20 / 100.0, 40 / 100.0, 60 / 100.0, 80 / 100.0, 98 / 100.0};
-      if ((rc = run_quantiles(jobs, q, 0, d_qout.as<float>()))) return rc;
-    }
-    CF_LAUNCH(k_strata, cdiv(K, 256), 256, d_evi.as<float>(), d_qout.as<float>(), K, d_lab.as<unsigned char>());
-    lab.resize(K);
-    STC_CUDA(cudaMemcpyAsync(lab.data(), d_lab.p, K, cudaMemcpyDeviceToHost, ctx->stream));
-    CF_SYNC();
-    double tt1 = cf_timing ? cf_now() : 0; t_gpu1 += tt1 - tt0;
-    // sampling bookkeeping (:447-497): index lists per stratum, Python random.shuffle, concatenate, shuffle, truncate
-    {
-      // count, size, then fill: the five quintile lists without branches (every row is stored into every list, the cursor
-      // only advances where the stratum bit is set); the 2 % tails p2 / p98 are written ten times per row, which is
-      // np.repeat(..., 10) (:470-471)
-      size_t cntb[7] = {0, 0, 0, 0, 0, 0, 0};
-      for (int r = 0; r < K; ++r) { const unsigned char m = lab[r]; for (int k = 0; k < 7; ++k) cntb[k] += (m >> k) & 1u; }
-      std::vector<int>* lists[7] = {&p2, &p20, &p40, &p60, &p80, &p100, &p98};
-      const int rep[7] = {10, 1, 1, 1, 1, 1, 10};
-      int* cur[7];
-      for (int k = 0; k < 7; ++k) { lists[k]->resize(cntb[k] * rep[k] + 10); cur[k] = lists[k]->data(); }
-      for (int r = 0; r < K; ++r) {
-        const unsigned char m = lab[r];
-        *cur[1] = r; cur[1] += (m >> 1) & 1u;
-        *cur[2] = r; cur[2] += (m >> 2) & 1u;
-        *cur[3] = r; cur[3] += (m >> 3) & 1u;
-        *cur[4] = r; cur[4] += (m >> 4) & 1u;
-        *cur[5] = r; cur[5] += (m >> 5) & 1u;
-        if (m & 0x41u) {                                   // the 2 % tails: rare, predictable
-          if (m & 1u) { for (int q = 0; q < 10; ++q) cur[0][q] = r; cur[0] += 10; }
-          if (m & 0x40u) { for (int q = 0; q < 10; ++q) cur[6][q] = r; cur[6] += 10; }
-        }
-      }
-      for (int k = 0; k < 7; ++k) lists[k]->resize(cntb[k] * rep[k]);
-    }
-    for (auto* v : {&p20, &p40, &p60, &p80, &p100})      // p2 / p98 go through np.repeat first, which accepts a 0-d array
-      if (v->size() == 1)
-        STC_FAIL(STC_ERR_STATE, "remove_clouds: single-element EVI stratum -- the reference raises TypeError (shuffle of a 0-d array)");
-    double tt2 = cf_timing ? cf_now() : 0; t_bucket += tt2 - tt1;
-    n_draw += (long long)(p2.size() + p98.size() + p20.size() + p40.size() + p60.size() + p80.size() + p100.size());
-    rng.shuffle(p2); rng.shuffle(p98); rng.shuffle(p20); rng.shuffle(p40); rng.shuffle(p60); rng.shuffle(p80); rng.shuffle(p100);
-    const size_t n_i = (size_t)(std::min(90000, K) / 5);
-    sample.clear();
-    auto append = [&](const std::vector<int>& v, size_t limit) { sample.insert(sample.end(), v.begin(), v.begin() + std::min(limit, v.size())); };
-    append(p2, p2.size()); append(p20, n_i); append(p40, n_i); append(p60, n_i); append(p80, n_i); append(p100, n_i); append(p98, p98.size());
-    rng.shuffle(sample);
-    if ((int)sample.size() > K) sample.resize(K);
-    const int S = (int)sample.size();
-    double tt3 = cf_timing ? cf_now() : 0; t_shuffle += tt3 - tt2;
-    STC_CUDA(cudaMemcpyAsync(d_sample.p, sample.data(), (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
-    const int gb = std::min(gram_blocks, cdiv(S, GRAM_ROWS));
-    CF_LAUNCH(k_gram, gb, 640, tiles, mosaic, d_snow.as<float>(), d_rowsrc.as<int>(), d_sample.as<int>(), S, HW, d_partial.as<double>());
-    CF_LAUNCH(k_gram_reduce, 1, 640, d_partial.as<double>(), gb, d_gram.as<double>());
-    CF_LAUNCH(k_nnls, 1, 32, d_gram.as<double>(), S, d_coef.as<double>(), d_status.as<int>());
-    int status[10];
-    STC_CUDA(cudaMemcpyAsync(status, d_status.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
-    CF_SYNC();      // also keeps `sample` alive until uploaded
-    for (int b = 0; b < 10; ++b)
-      if (status[b] != 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: NNLS did not converge (scipy.optimize.nnls raises RuntimeError)");
-    CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, d_snow.as<float>(),
-              d_coef.as<double>(), 1, HW);
-    if (cf_timing) t_gpu2 += cf_now() - tt3;
+    FitJob f; f.d = d;
+    if (c_zero > 40000) { f.lo = d; f.hi = d + 1; }
+    else { f.lo = (d == n - 1) ? std::max(d - 2, 0) : std::max(d - 1, 0); f.hi = std::min(d + 2, n); }
+    f.K = 0;
+    for (int t = f.lo; t < f.hi; ++t) f.K += counts[t * 5 + 4];
+    if (f.K < 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: no clear land pixel to fit on -- the reference fails in np.percentile here");
+    f.row0 = total_rows; total_rows += f.K;
+    fit_of[d] = (int)fits.size(); fits.push_back(f);
   }
-  if (cf_timing) fprintf(stderr, "[remove_clouds]   per-date: gpu(collect..strata) %.1f, buckets %.1f, shuffles %.1f (%lld elements), gpu(gram..nnls) %.1f ms\n", t_gpu1, t_bucket, t_shuffle, n_draw, t_gpu2);
+  const int nf = (int)fits.size();
+  DBuf d_rows_all, d_evi_all, d_lab_all, d_fqout, d_fcnt, d_lists, d_bjobs, d_sample_all, d_status_all;
+  int* pin_lists = nullptr;
+  if (nf > 0) {
+    STC_CUDA(stc_dmalloc(&d_rows_all.p, (size_t)total_rows * 4)); STC_CUDA(stc_dmalloc(&d_evi_all.p, (size_t)total_rows * 4));
+    STC_CUDA(stc_dmalloc(&d_lab_all.p, (size_t)total_rows));
+    STC_CUDA(stc_dmalloc(&d_fqout.p, (size_t)nf * 6 * 4)); STC_CUDA(stc_dmalloc(&d_fcnt.p, (size_t)nf * 7 * 4));
+    STC_CUDA(stc_dmalloc(&d_status_all.p, (size_t)nf * 10 * 4));
+    std::vector<SelJob> jobs; std::vector<QSpec> specs;
+    const double qs[6] = {2 / 100.0, 20 / 100.0, 40 / 100.0, 60 / 100.0, 80 / 100.0, 98 / 100.0};
+    for (const FitJob& f : fits) {
+      int K = 0;
+      for (int t = f.lo; t < f.hi; ++t) {
+        CF_LAUNCH(k_collect_rows, cdiv(HW, 256), 256, tiles, d_posall.as<int>() + (int64_t)t * HW, HW, t, (int)(f.row0 + K), d_rows_all.as<int>(), d_evi_all.as<float>());
+        K += counts[t * 5 + 4];
+      }
+      for (int k = 0; k < 6; ++k) {
+        jobs.push_back(SelJob{d_evi_all.as<float>() + f.row0, f.K, 1, 1});
+        specs.push_back(QSpec{(int)(jobs.size() - 1) * SEL_MAX_COLS, f.K, qs[k], 0});
+      }
+    }
+    if ((rc = run_select(jobs, specs, d_fqout.as<float>()))) return rc;
+    STC_CUDA(cudaMemsetAsync(d_fcnt.p, 0, (size_t)nf * 7 * 4, ctx->stream));
+    for (int j = 0; j < nf; ++j)
+      CF_LAUNCH(k_strata, cdiv(fits[j].K, 256), 256, d_evi_all.as<float>() + fits[j].row0, d_fqout.as<float>() + 6 * j, fits[j].K,
+                d_lab_all.as<unsigned char>() + fits[j].row0, d_fcnt.as<int>() + 7 * j);
+    std::vector<int> h_cnt((size_t)nf * 7);
+    STC_CUDA(cudaMemcpyAsync(h_cnt.data(), d_fcnt.p, (size_t)nf * 7 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CF_SYNC();
+    int64_t total_list = 0;
+    const int rep[7] = {10, 1, 1, 1, 1, 1, 10};
+    for (int j = 0; j < nf; ++j)
+      for (int k = 0; k < 7; ++k) { fits[j].cnt[k] = h_cnt[(size_t)j * 7 + k] * rep[k]; fits[j].list0[k] = total_list; total_list += fits[j].cnt[k]; }
+    for (const FitJob& f : fits)
+      for (int k = 1; k <= 5; ++k)                          // p2 / p98 go through np.repeat first, which accepts a 0-d array
+        if (f.cnt[k] == 1)
+          STC_FAIL(STC_ERR_STATE, "remove_clouds: single-element EVI stratum -- the reference raises TypeError (shuffle of a 0-d array)");
+    STC_CUDA(stc_dmalloc(&d_lists.p, (size_t)std::max<int64_t>(total_list, 1) * 4)); STC_CUDA(stc_dmalloc(&d_bjobs.p, (size_t)nf * sizeof(BucketJob)));
+    std::vector<BucketJob> bj(nf);
+    for (int j = 0; j < nf; ++j) {
+      bj[j].lab = d_lab_all.as<unsigned char>() + fits[j].row0; bj[j].K = fits[j].K;
+      for (int k = 0; k < 7; ++k) bj[j].out[k] = d_lists.as<int>() + fits[j].list0[k];
+    }
+    STC_CUDA(cudaMemcpyAsync(d_bjobs.p, bj.data(), (size_t)nf * sizeof(BucketJob), cudaMemcpyHostToDevice, ctx->stream));
+    CF_LAUNCH(k_bucket_lists, dim3(7, nf), 1024, d_bjobs.as<BucketJob>());
+    // pinned host scratch: the lists, then (behind them) one sample slot per date
+    int64_t sample_cap = 0;
+    std::vector<int64_t> sample0(nf);
+    for (int j = 0; j < nf; ++j) {
+      const int64_t n_i = std::min(90000, fits[j].K) / 5;
+      int64_t cap = (int64_t)fits[j].cnt[0] + fits[j].cnt[6];
+      for (int k = 1; k <= 5; ++k) cap += std::min<int64_t>(n_i, fits[j].cnt[k]);
+      sample0[j] = sample_cap; sample_cap += cap;
+    }
+    pin_lists = (int*)ctx_pinned(ctx, (size_t)(total_list + sample_cap + 16) * 4);
+    if (!pin_lists) STC_FAIL(STC_ERR_NOMEM, "remove_clouds: pinned host scratch");
+    STC_CUDA(stc_dmalloc(&d_sample_all.p, (size_t)std::max<int64_t>(sample_cap, 1) * 4));
+    STC_CUDA(cudaMemcpyAsync(pin_lists, d_lists.p, (size_t)total_list * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CF_SYNC();                                             // bj is a host vector; the lists are on the host now
+    cf_mark("fit rows, strata, index lists (all dates)");
+    // ---- 3b. in date order: Python's random.shuffle replayed on the host for date d while the device still works on date
+    //      d - 1 (launches are asynchronous; nothing below synchronises), then Gram sums, NNLS and the blend of date d.
+    int* pin_samples = pin_lists + total_list;
+    double t_shuffle = 0; long long n_draw = 0;
+    for (int d = 0; d < n; ++d) {
+      const int j = fit_of[d];
+      if (j < 0) {
+        if (counts[d * 5] > 0 && !(counts[d * 5 + 1] > 0))    // no clear pixel at all: the interpolated array stays the raw mosaic
+          CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, (const float*)nullptr,
+                    d_coef.as<double>(), 0, HW);
+        continue;
+      }
+      const FitJob& f = fits[j];
+      const double tt0 = cf_timing ? cf_now() : 0;
+      int* L[7]; for (int k = 0; k < 7; ++k) L[k] = pin_lists + f.list0[k];
+      // :472-478 shuffle order p2, p98, p20, p40, p60, p80, p100
+      rng.shuffle(L[0], f.cnt[0]); rng.shuffle(L[6], f.cnt[6]);
+      for (int k = 1; k <= 5; ++k) rng.shuffle(L[k], f.cnt[k]);
+      const size_t n_i = (size_t)(std::min(90000, f.K) / 5);
+      int* smp = pin_samples + sample0[j];
+      size_t S = 0;
+      auto append = [&](int k, size_t limit) { const size_t c = std::min(limit, (size_t)f.cnt[k]); memcpy(smp + S, L[k], c * 4); S += c; };
+      append(0, (size_t)f.cnt[0]); for (int k = 1; k <= 5; ++k) append(k, n_i); append(6, (size_t)f.cnt[6]);   // [p2, p20, p40, p60, p80, p100, p98]
+      rng.shuffle(smp, S);
+      if (S > (size_t)f.K) S = (size_t)f.K;
+      for (int k = 0; k < 7; ++k) n_draw += f.cnt[k];
+      if (cf_timing) t_shuffle += cf_now() - tt0;
+      int* d_smp = d_sample_all.as<int>() + sample0[j];
+      STC_CUDA(cudaMemcpyAsync(d_smp, smp, S * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CF_LAUNCH(k_snow_mean, cdiv(HW, 256), 256, tiles, n, HW, d_snow.as<float>());
+      const int gb = std::min(gram_blocks, cdiv((int64_t)S, GRAM_ROWS));
+      CF_LAUNCH(k_gram, gb, 640, tiles, mosaic, d_snow.as<float>(), d_rows_all.as<int>() + f.row0, d_smp, (int)S, HW, d_partial.as<double>());
+      CF_LAUNCH(k_gram_reduce, 1, 640, d_partial.as<double>(), gb, d_gram.as<double>());
+      CF_LAUNCH(k_nnls, 1, 32, d_gram.as<double>(), (int)S, d_coef.as<double>(), d_status_all.as<int>() + 10 * j);
+      CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, d_snow.as<float>(),
+                d_coef.as<double>(), 1, HW);
+    }
+    std::vector<int> status((size_t)nf * 10);
+    STC_CUDA(cudaMemcpyAsync(status.data(), d_status_all.p, (size_t)nf * 40, cudaMemcpyDeviceToHost, ctx->stream));
+    CF_SYNC();
+    if (cf_timing) fprintf(stderr, "[remove_clouds]   host shuffles %.1f ms (%lld elements, overlapped with the device)\n", t_shuffle, n_draw);
+    for (int v : status)
+      if (v != 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: NNLS did not converge (scipy.optimize.nnls raises RuntimeError)");
+  } else {
+    for (int d = 0; d < n; ++d)
+      if (counts[d * 5] > 0 && !(counts[d * 5 + 1] > 0))
+        CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, (const float*)nullptr,
+                  d_coef.as<double>(), 0, HW);
+  }
   memcpy(mt_state, rng.mt, 624 * 4); mt_state[624] = (uint32_t)rng.idx;
 
   cf_mark("per-date alignment + blend");
@@ -922,8 +974,9 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
     float* blue = d_src_rows.as<float>(); float* red = d_ref_rows.as<float>();
     CF_LAUNCH(k_gather_br, cdiv(HW, 256), 256, mosaic, d_pos.as<int>(), HW, blue, red);
     const int K2 = HW - only_cnt;
-    std::vector<SelectJob> jobs = {SelectJob{blue, 1, K2, 0}, SelectJob{red, 1, K2, 0}};
-    if ((rc = run_quantiles(jobs, {99 / 100.0, 99 / 100.0}, 0, d_qout.as<float>()))) return rc;
+    std::vector<SelJob> jobs = {SelJob{blue, K2, 1, 1}, SelJob{red, K2, 1, 1}};
+    std::vector<QSpec> specs = {QSpec{0, K2, 99 / 100.0, 0}, QSpec{SEL_MAX_COLS, K2, 99 / 100.0, 0}};
+    if ((rc = run_select(jobs, specs, d_qout.as<float>()))) return rc;
     CF_LAUNCH(k_mosaic_clouds, cdiv(HW, 256), 256, mosaic, u8a, pf, d_qout.as<float>(), HW, u8b);
     maskop_dilate(ctx, u8b, flag, 1, H, W, 3, 1, 1, 0, 0);
     maskop_dilate(ctx, flag, u8b, 1, H, W, 8, 1, 1, 0, 0);

@@ -46,12 +46,12 @@ __global__ void __launch_bounds__(256) float_to_int16_kernel(const float* __rest
 
 // ---- device-level launchers (shared with stc_tile.cu) ----
 int codec_to_float32_dev(stc_ctx* ctx, const uint16_t* in_dev, int64_t n, float* out_dev) {
-  to_float32_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n);
+  { TraceScope ts_(ctx, "to_float32_kernel"); to_float32_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   return STC_OK;
 }
 int codec_convert_to_db_dev(stc_ctx* ctx, const float* in_dev, int64_t n, float min_db, float* out_dev) {
-  convert_to_db_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n, min_db);
+  { TraceScope ts_(ctx, "convert_to_db_kernel"); convert_to_db_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n, min_db); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   return STC_OK;
 }
@@ -68,7 +68,7 @@ int stc_to_float32_host(stc_ctx* ctx, const uint16_t* in_host, int64_t n, float*
   Buf a, b;
   STC_CUDA(stc_dmalloc(&a.p, n * 2)); STC_CUDA(stc_dmalloc(&b.p, n * 4));
   STC_CUDA(cudaMemcpyAsync(a.p, in_host, n * 2, cudaMemcpyHostToDevice, ctx->stream));
-  to_float32_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, ctx->stream>>>((const uint16_t*)a.p, (float*)b.p, n);
+  { TraceScope ts_(ctx, "to_float32_kernel"); to_float32_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, ctx->stream>>>((const uint16_t*)a.p, (float*)b.p, n); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(out_host, b.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -81,7 +81,7 @@ int stc_to_uint16_host(stc_ctx* ctx, const float* in_host, int64_t n, uint16_t* 
   Buf a, b;
   STC_CUDA(stc_dmalloc(&a.p, n * 4)); STC_CUDA(stc_dmalloc(&b.p, n * 2));
   STC_CUDA(cudaMemcpyAsync(a.p, in_host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-  to_uint16_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (uint16_t*)b.p, n);
+  { TraceScope ts_(ctx, "to_uint16_kernel"); to_uint16_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (uint16_t*)b.p, n); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(out_host, b.p, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -95,8 +95,8 @@ int stc_float_to_int16_host(stc_ctx* ctx, const float* in_host, int64_t n, int p
   STC_CUDA(stc_dmalloc(&a.p, n * 4)); STC_CUDA(stc_dmalloc(&b.p, n * 2));
   STC_CUDA(cudaMemcpyAsync(a.p, in_host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
   // np.clip(float32 array, python float, python float): the bounds are float64 scalars cast to float32
-  float_to_int16_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (int16_t*)b.p, n, (float)(-32768.0 / precision),
-                                                              (float)(32767.0 / precision), (float)precision);
+  { TraceScope ts_(ctx, "float_to_int16_kernel"); float_to_int16_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (int16_t*)b.p, n, (float)(-32768.0 / precision),
+                                                              (float)(32767.0 / precision), (float)precision); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(out_host, b.p, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -109,7 +109,7 @@ int stc_convert_to_db_host(stc_ctx* ctx, const float* in_host, int64_t n, float 
   Buf a, b;
   STC_CUDA(stc_dmalloc(&a.p, n * 4)); STC_CUDA(stc_dmalloc(&b.p, n * 4));
   STC_CUDA(cudaMemcpyAsync(a.p, in_host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-  convert_to_db_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (float*)b.p, n, min_db);
+  { TraceScope ts_(ctx, "convert_to_db_kernel"); convert_to_db_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)a.p, (float*)b.p, n, min_db); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(out_host, b.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
+#include <cstring>
 #include <map>
 #include <vector>
 #include "../../include/stc.h"
@@ -90,7 +91,35 @@ struct stc_ctx {
   float* feat_early_chunk = nullptr; float* feat_late_chunk = nullptr;
   int monthly_u16 = 0;        // the monthly patches of the current call are uint16 (x/65535), not float32
   void* sr = nullptr;         // SuperresState*
+  // grow-only pinned host scratch (index lists of the cloud-removal sampling stage, small result blocks)
+  void* pin_buf = nullptr; size_t pin_bytes = 0;
+  // pinned ring for small host -> device tables (job lists, window tables): cudaMemcpyAsync from it is truly asynchronous
+  char* stage_ring = nullptr; size_t stage_pos = 0;
+  // side stream for latency-bound kernels that occupy a few SMs next to GPU-wide work (forked / joined with events)
+  cudaStream_t aux_stream = nullptr; cudaEvent_t aux_ev[2] = {nullptr, nullptr};
 };
+static constexpr size_t STC_STAGE_RING = 8u << 20;
+// copy `bytes` of host data into the pinned ring and return the pinned address (valid until the ring wraps: 8 MB of tables)
+static inline const void* ctx_stage(stc_ctx* ctx, const void* src, size_t bytes) {
+  if (bytes > STC_STAGE_RING / 4) return nullptr;
+  if (!ctx->stage_ring && cudaMallocHost((void**)&ctx->stage_ring, STC_STAGE_RING) != cudaSuccess) { ctx->stage_ring = nullptr; return nullptr; }
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (ctx->stage_pos + need > STC_STAGE_RING) ctx->stage_pos = 0;
+  char* dst = ctx->stage_ring + ctx->stage_pos;
+  ctx->stage_pos += need;
+  memcpy(dst, src, bytes);
+  return dst;
+}
+// pinned host scratch of at least `bytes` (contents are not preserved across calls that grow it)
+static inline void* ctx_pinned(stc_ctx* ctx, size_t bytes) {
+  if (ctx->pin_bytes < bytes) {
+    if (ctx->pin_buf) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pin_buf); ctx->pin_buf = nullptr; ctx->pin_bytes = 0; }
+    size_t want = bytes + bytes / 4;
+    if (cudaMallocHost(&ctx->pin_buf, want) != cudaSuccess) { ctx->pin_buf = nullptr; return nullptr; }
+    ctx->pin_bytes = want;
+  }
+  return ctx->pin_buf;
+}
 
 #define STC_CUDA(call)                                                              \
   do {                                                                              \
@@ -130,6 +159,13 @@ static inline void trace_end(stc_ctx* ctx) {
   if (!ctx->trace_on || ctx->trace.empty()) return;
   cudaEventRecord(ctx->trace.back().b, ctx->stream);
 }
+
+// RAII bracket around one launch statement: `{ TraceScope ts_(ctx, "kernel"); kernel<<<...>>>(...); }`
+struct TraceScope {
+  stc_ctx* c;
+  TraceScope(stc_ctx* ctx, const char* label) : c(ctx) { trace_begin(ctx, label); }
+  ~TraceScope() { trace_end(c); }
+};
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

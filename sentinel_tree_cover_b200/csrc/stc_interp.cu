@@ -61,13 +61,13 @@ __global__ void __launch_bounds__(128) k_median_fill(float* __restrict__ arr, in
 
 // device-level entry points shared with stc_tilefuse.cu
 int interp_missing_counts_dev(stc_ctx* ctx, const float* arr_dev, int n, int HW, int C, int* bad_px_dev, int* nan_vals_dev) {
-  k_missing_counts<<<dim3(cdiv((int64_t)HW, 256), n), 256, 0, ctx->stream>>>(arr_dev, HW, C, bad_px_dev, nan_vals_dev);
+  { TraceScope ts_(ctx, "k_missing_counts"); k_missing_counts<<<dim3(cdiv((int64_t)HW, 256), n), 256, 0, ctx->stream>>>(arr_dev, HW, C, bad_px_dev, nan_vals_dev); }
   ctx->launches++;
   return STC_OK;
 }
 int interp_median_fill_dev(stc_ctx* ctx, float* arr_dev, int n, int64_t cols) {
   if (n > FILL_MAX_DATES) STC_FAIL(STC_ERR_ARG, "median_fill: more than 96 dates");
-  k_median_fill<<<cdiv(cols, 128), 128, 0, ctx->stream>>>(arr_dev, n, cols);
+  { TraceScope ts_(ctx, "k_median_fill"); k_median_fill<<<cdiv(cols, 128), 128, 0, ctx->stream>>>(arr_dev, n, cols); }
   ctx->launches++;
   return STC_OK;
 }
@@ -81,7 +81,7 @@ extern "C" int stc_missing_px_host(stc_ctx* ctx, const float* arr_host, int n, i
   STC_CUDA(stc_dmalloc(&d, bytes)); STC_CUDA(stc_dmalloc(&cnt, 2 * n * 4));
   cudaMemcpyAsync(d, arr_host, bytes, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemsetAsync(cnt, 0, 2 * n * 4, ctx->stream);
-  k_missing_counts<<<dim3(cdiv((int64_t)H * W, 256), n), 256, 0, ctx->stream>>>(d, H * W, C, cnt, cnt + n);
+  { TraceScope ts_(ctx, "k_missing_counts"); k_missing_counts<<<dim3(cdiv((int64_t)H * W, 256), n), 256, 0, ctx->stream>>>(d, H * W, C, cnt, cnt + n); }
   ctx->launches++;
   cudaMemcpyAsync(bad_px_host, cnt, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
   cudaMemcpyAsync(nan_vals_host, cnt + n, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -101,8 +101,8 @@ extern "C" int stc_median_fill_host(stc_ctx* ctx, float* arr_host, int n, int H,
   STC_CUDA(stc_dmalloc(&d, bytes)); STC_CUDA(stc_dmalloc(&cnt, 2 * n * 4));
   cudaMemcpyAsync(d, arr_host, bytes, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemsetAsync(cnt, 0, 2 * n * 4, ctx->stream);
-  k_median_fill<<<cdiv(cols, 128), 128, 0, ctx->stream>>>(d, n, cols);
-  k_missing_counts<<<dim3(cdiv((int64_t)H * W, 256), n), 256, 0, ctx->stream>>>(d, H * W, C, cnt, cnt + n);
+  { TraceScope ts_(ctx, "k_median_fill"); k_median_fill<<<cdiv(cols, 128), 128, 0, ctx->stream>>>(d, n, cols); }
+  { TraceScope ts_(ctx, "k_missing_counts"); k_missing_counts<<<dim3(cdiv((int64_t)H * W, 256), n), 256, 0, ctx->stream>>>(d, H * W, C, cnt, cnt + n); }
   ctx->launches += 2;
   cudaMemcpyAsync(arr_host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
   cudaMemcpyAsync(nan_vals_host, cnt + n, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) k_build_sentinel2(const float* __restrict
 
 int interp_build_sentinel2_dev(stc_ctx* ctx, const float* s2_10_dev, const float* s2_20_dev, int n, int h, int w, float* out_dev) {
   const int64_t px = (int64_t)n * 4 * h * w;
-  k_build_sentinel2<<<cdiv(px, 256), 256, 0, ctx->stream>>>(s2_10_dev, s2_20_dev, n, h, w, out_dev);
+  { TraceScope ts_(ctx, "k_build_sentinel2"); k_build_sentinel2<<<cdiv(px, 256), 256, 0, ctx->stream>>>(s2_10_dev, s2_20_dev, n, h, w, out_dev); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   return STC_OK;
 }
@@ -207,7 +207,7 @@ extern "C" int stc_build_sentinel2_host(stc_ctx* ctx, const float* s2_10_host, c
   STC_CUDA(stc_dmalloc(&d10, px * 16)); STC_CUDA(stc_dmalloc(&d20, (int64_t)n * h * w * 24)); STC_CUDA(stc_dmalloc(&dout, px * 40));
   cudaMemcpyAsync(d10, s2_10_host, px * 16, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(d20, s2_20_host, (int64_t)n * h * w * 24, cudaMemcpyHostToDevice, ctx->stream);
-  k_build_sentinel2<<<cdiv(px, 256), 256, 0, ctx->stream>>>(d10, d20, n, h, w, dout);
+  { TraceScope ts_(ctx, "k_build_sentinel2"); k_build_sentinel2<<<cdiv(px, 256), 256, 0, ctx->stream>>>(d10, d20, n, h, w, dout); }
   ctx->launches++;
   cudaMemcpyAsync(out_host, dout, px * 40, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) edt_sq_kernel(const unsigned char* __rest
 
 int pre_edt_sq_dev(stc_ctx* ctx, const unsigned char* target_dev, int n, int H, int W, int radius, int* out_dev) {
   if (radius < 1 || radius > 64) STC_FAIL(STC_ERR_ARG, "edt_sq: radius must be in 1..64");
-  edt_sq_kernel<<<cdiv((int64_t)n * H * W, 256), 256, 0, ctx->stream>>>(target_dev, out_dev, n, H, W, radius);
+  { TraceScope ts_(ctx, "edt_sq_kernel"); edt_sq_kernel<<<cdiv((int64_t)n * H * W, 256), 256, 0, ctx->stream>>>(target_dev, out_dev, n, H, W, radius); }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;
@@ -123,15 +123,15 @@ int pre_feather_dev(stc_ctx* ctx, const float* mask_dev, int n, int H, int W, in
   if (size < 1 || size > 64) STC_FAIL(STC_ERR_ARG, "feather: closing size must be in 1..64");
   int64_t tot = (int64_t)n * H * W;
   int grid = cdiv(tot, 256);
-  date_sum_kernel<<<n, 256, 0, ctx->stream>>>(mask_dev, sums_dev, H * W);
-  edt_feather_kernel<<<grid, 256, 0, ctx->stream>>>(mask_dev, sums_dev, tmp_a, n, H, W);
+  { TraceScope ts_(ctx, "date_sum_kernel"); date_sum_kernel<<<n, 256, 0, ctx->stream>>>(mask_dev, sums_dev, H * W); }
+  { TraceScope ts_(ctx, "edt_feather_kernel"); edt_feather_kernel<<<grid, 256, 0, ctx->stream>>>(mask_dev, sums_dev, tmp_a, n, H, W); }
   int dlo, dhi, elo, ehi;
   if (size & 1) { dlo = elo = -(size / 2); dhi = ehi = size / 2; }
   else { dlo = -(size / 2 - 1); dhi = size / 2; elo = -(size / 2); ehi = size / 2 - 1; }
-  window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_a, sums_dev, tmp_b, n, H, W, dlo, dhi, 0, 1);
-  window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_b, sums_dev, tmp_a, n, H, W, dlo, dhi, 1, 1);
-  window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_a, sums_dev, tmp_b, n, H, W, elo, ehi, 0, 0);
-  window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_b, sums_dev, out_dev, n, H, W, elo, ehi, 1, 0);
+  { TraceScope ts_(ctx, "window_reduce_kernel"); window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_a, sums_dev, tmp_b, n, H, W, dlo, dhi, 0, 1); }
+  { TraceScope ts_(ctx, "window_reduce_kernel"); window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_b, sums_dev, tmp_a, n, H, W, dlo, dhi, 1, 1); }
+  { TraceScope ts_(ctx, "window_reduce_kernel"); window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_a, sums_dev, tmp_b, n, H, W, elo, ehi, 0, 0); }
+  { TraceScope ts_(ctx, "window_reduce_kernel"); window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_b, sums_dev, out_dev, n, H, W, elo, ehi, 1, 0); }
   STC_CUDA(cudaGetLastError());
   ctx->launches += 6;
   return STC_OK;
@@ -140,7 +140,7 @@ int pre_feather_dev(stc_ctx* ctx, const float* mask_dev, int n, int H, int W, in
 int pre_binary_dilate_dev(stc_ctx* ctx, const unsigned char* in_dev, int n, int H, int W, int iterations, int conn,
                           unsigned char* out_dev) {
   if (iterations < 1 || iterations > 64 || (conn != 1 && conn != 2)) STC_FAIL(STC_ERR_ARG, "binary_dilate: bad iterations/connectivity");
-  binary_dilate_kernel<<<cdiv((int64_t)n * H * W, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n, H, W, iterations, conn);
+  { TraceScope ts_(ctx, "binary_dilate_kernel"); binary_dilate_kernel<<<cdiv((int64_t)n * H * W, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n, H, W, iterations, conn); }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;

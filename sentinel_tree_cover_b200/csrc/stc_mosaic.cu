@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(128) mosaic_feats_kernel(const short* feats, c
 int pre_feature_mosaic_dev(stc_ctx* ctx, const short* feats_dev, const int* xs_dev, const int* ys_dev, const float* gauss_dev,
                            int n, int S, int D, int Hc, int Wc, short* out_dev) {
   if (n < 1 || n > 64) STC_FAIL(STC_ERR_ARG, "feature mosaic: 1..64 subtiles supported");
-  mosaic_feats_kernel<<<cdiv((int64_t)Hc * Wc, 128), 128, 0, ctx->stream>>>(feats_dev, xs_dev, ys_dev, gauss_dev, n, S, D, Hc, Wc, out_dev);
+  { TraceScope ts_(ctx, "mosaic_feats_kernel"); mosaic_feats_kernel<<<cdiv((int64_t)Hc * Wc, 128), 128, 0, ctx->stream>>>(feats_dev, xs_dev, ys_dev, gauss_dev, n, S, D, Hc, Wc, out_dev); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   return STC_OK;
 }
@@ -166,12 +166,12 @@ int pre_gauss_mosaic_dev(stc_ctx* ctx, const float* preds_dev, const int* xs_dev
   if (n < 1 || n > 64) STC_FAIL(STC_ERR_ARG, "mosaic: 1..64 subtiles supported");
   MosaicParams p{preds_dev, xs_dev, ys_dev, placed_dev, gauss_dev, mult_dev, n, S, Hc, Wc};
   if (stage == 0) {
-    mosaic_ratio_kernel<<<n, 256, 0, ctx->stream>>>(p, diffs_dev);
+    { TraceScope ts_(ctx, "mosaic_ratio_kernel"); mosaic_ratio_kernel<<<n, 256, 0, ctx->stream>>>(p, diffs_dev); }
     STC_CUDA(cudaGetLastError()); ctx->launches++;
   } else {
-    mosaic_blend_kernel<<<cdiv((int64_t)Hc * Wc, 128), 128, 0, ctx->stream>>>(p, tmp_dev);
+    { TraceScope ts_(ctx, "mosaic_blend_kernel"); mosaic_blend_kernel<<<cdiv((int64_t)Hc * Wc, 128), 128, 0, ctx->stream>>>(p, tmp_dev); }
     STC_CUDA(cudaGetLastError()); ctx->launches++;
-    mosaic_dilate_kernel<<<cdiv((int64_t)Hc * Wc, 256), 256, 0, ctx->stream>>>(tmp_dev, out_dev, Hc, Wc, 10);
+    { TraceScope ts_(ctx, "mosaic_dilate_kernel"); mosaic_dilate_kernel<<<cdiv((int64_t)Hc * Wc, 256), 256, 0, ctx->stream>>>(tmp_dev, out_dev, Hc, Wc, 10); }
     STC_CUDA(cudaGetLastError()); ctx->launches++;
   }
   return STC_OK;

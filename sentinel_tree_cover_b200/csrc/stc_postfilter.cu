@@ -151,12 +151,12 @@ __global__ void __launch_bounds__(256) k_attenuate_round(const float* __restrict
 int bright_bare_dev(stc_ctx* ctx, const float* img_dev, int F, int H, int W, int C, unsigned char* a, unsigned char* b, int* d2,
                     double* ramp_dev) {
   const int HW = H * W;
-  k_bright_candidates<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(img_dev, F, HW, C, a);
+  { TraceScope ts_(ctx, "k_bright_candidates"); k_bright_candidates<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(img_dev, F, HW, C, a); }
   maskop_dilate(ctx, a, b, 1, H, W, 2, 1, 1, 0, 0);      // binary_dilation(1 - bright, 2)
   maskop_dilate(ctx, b, a, 1, H, W, 1, 1, 1, 0, 0);      // binary_dilation(1 - that, 1)
   int rc = pre_edt_sq_dev(ctx, a, 1, H, W, 3, d2);
   if (rc) return rc;
-  k_ramp_crop<<<cdiv((H - 14) * (W - 14), 256), 256, 0, ctx->stream>>>(d2, H, W, 7, ramp_dev);
+  { TraceScope ts_(ctx, "k_ramp_crop"); k_ramp_crop<<<cdiv((H - 14) * (W - 14), 256), 256, 0, ctx->stream>>>(d2, H, W, 7, ramp_dev); }
   ctx->launches += 2;
   return STC_OK;
 }
@@ -168,7 +168,7 @@ int post_np_sum_dev(stc_ctx* ctx, const float* data_dev, int nseg, int len, int 
   const int leaf_cap = len / 32 + 8;
   PBuf lv, ls;
   STC_CUDA(stc_dmalloc(&lv.p, (size_t)nseg * leaf_cap * 8)); STC_CUDA(stc_dmalloc(&ls.p, (size_t)nseg * leaf_cap * 4));
-  k_np_sum_seg<<<nseg, 1024, 0, ctx->stream>>>(data_dev, len, mode, leaf_cap, lv.as<int2>(), ls.as<float>(), sum_dev, valid_dev);
+  { TraceScope ts_(ctx, "k_np_sum_seg"); k_np_sum_seg<<<nseg, 1024, 0, ctx->stream>>>(data_dev, len, mode, leaf_cap, lv.as<int2>(), ls.as<float>(), sum_dev, valid_dev); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   return STC_OK;
 }
@@ -181,7 +181,7 @@ extern "C" int stc_np_sum_host(stc_ctx* ctx, const float* data_host, int nseg, i
   STC_CUDA(stc_dmalloc(&d.p, (size_t)nseg * len * 4)); STC_CUDA(stc_dmalloc(&lv.p, (size_t)nseg * leaf_cap * 8));
   STC_CUDA(stc_dmalloc(&ls.p, (size_t)nseg * leaf_cap * 4)); STC_CUDA(stc_dmalloc(&so.p, nseg * 4)); STC_CUDA(stc_dmalloc(&vo.p, nseg * 4));
   STC_CUDA(cudaMemcpyAsync(d.p, data_host, (size_t)nseg * len * 4, cudaMemcpyHostToDevice, ctx->stream));
-  k_np_sum_seg<<<nseg, 1024, 0, ctx->stream>>>(d.as<float>(), len, mode, leaf_cap, lv.as<int2>(), ls.as<float>(), so.as<float>(), vo.as<int>());
+  { TraceScope ts_(ctx, "k_np_sum_seg"); k_np_sum_seg<<<nseg, 1024, 0, ctx->stream>>>(d.as<float>(), len, mode, leaf_cap, lv.as<int2>(), ls.as<float>(), so.as<float>(), vo.as<int>()); }
   ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(sum_host, so.p, nseg * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (valid_host) STC_CUDA(cudaMemcpyAsync(valid_host, vo.p, nseg * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -201,7 +201,7 @@ extern "C" int stc_normalize_host(stc_ctx* ctx, float* x_host, int64_t npx, int 
   PBuf d;
   STC_CUDA(stc_dmalloc(&d.p, (size_t)npx * C * 4));
   STC_CUDA(cudaMemcpyAsync(d.p, x_host, (size_t)npx * C * 4, cudaMemcpyHostToDevice, ctx->stream));
-  k_normalize<<<cdiv(npx * C, 256), 256, 0, ctx->stream>>>(d.as<float>(), npx * C, C, p);
+  { TraceScope ts_(ctx, "k_normalize"); k_normalize<<<cdiv(npx * C, 256), 256, 0, ctx->stream>>>(d.as<float>(), npx * C, C, p); }
   ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(x_host, d.p, (size_t)npx * C * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -236,11 +236,11 @@ int post_subtile_dev(stc_ctx* ctx, const float* preds_dev, const float* img_dev,
   int blocks = 0, bs = 0, thresh = 0;
   if (S == 158) { blocks = 4; bs = 40; thresh = 400; }         // sum > 40*40*0.25
   else if (S == 142) { blocks = 9; bs = 16; thresh = 192; }    // sum > 16*16*0.75
-  k_lt1<<<cdiv(Hm * Hm, 256), 256, 0, ctx->stream>>>(mc_dev, H, H, 6, na);
+  { TraceScope ts_(ctx, "k_lt1"); k_lt1<<<cdiv(Hm * Hm, 256), 256, 0, ctx->stream>>>(mc_dev, H, H, 6, na); }
   maskop_dilate(ctx, na, nb, 1, Hm, Hm, 6, 2, 1, 1, 0);   // 1 - dilate(1 - x, 3x3, 6)
   maskop_dilate(ctx, nb, na, 1, Hm, Hm, 6, 2, 0, 0, 0);   // dilate(.., 3x3, 6)
-  if (blocks) k_block_vote<<<dim3(blocks, blocks), 256, 0, ctx->stream>>>(na, blocks, bs, thresh, vote);
-  k_attenuate_round<<<cdiv(S * S, 256), 256, 0, ctx->stream>>>(preds_dev, ramp, blocks ? vote : nullptr, S, blocks, bs, out_dev);
+  if (blocks) { TraceScope ts_(ctx, "k_block_vote"); k_block_vote<<<dim3(blocks, blocks), 256, 0, ctx->stream>>>(na, blocks, bs, thresh, vote); }
+  { TraceScope ts_(ctx, "k_attenuate_round"); k_attenuate_round<<<cdiv(S * S, 256), 256, 0, ctx->stream>>>(preds_dev, ramp, blocks ? vote : nullptr, S, blocks, bs, out_dev); }
   ctx->launches += 3;
   return STC_OK;
 }

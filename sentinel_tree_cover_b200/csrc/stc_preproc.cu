@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const float* __restrict__
 
 int pre_assemble_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W, float* out_dev) {
   int64_t n = (int64_t)B * H * W;
-  assemble_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(monthly_dev, out_dev, B, H * W);
+  { TraceScope ts_(ctx, "assemble_kernel"); assemble_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(monthly_dev, out_dev, B, H * W); }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;
@@ -109,10 +109,10 @@ __global__ void __launch_bounds__(256) temporal_matmul_kernel(const float* __res
 template <int VEC>
 static void launch_temporal_matmul(const float* in_dev, float* out_dev, int n_in, int n_out, int64_t inner, const TMat& Mk, cudaStream_t st) {
   const int grid = cdiv(inner / VEC + (inner % VEC ? 1 : 0), 256);
-  if (n_in <= 8) temporal_matmul_kernel<VEC, 8><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk);
-  else if (n_in <= 16) temporal_matmul_kernel<VEC, 16><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk);
-  else if (n_in <= 24) temporal_matmul_kernel<VEC, 24><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk);
-  else temporal_matmul_kernel<VEC, 32><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk);
+  if (n_in <= 8) { temporal_matmul_kernel<VEC, 8><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk); }
+  else if (n_in <= 16) { temporal_matmul_kernel<VEC, 16><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk); }
+  else if (n_in <= 24) { temporal_matmul_kernel<VEC, 24><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk); }
+  else { temporal_matmul_kernel<VEC, 32><<<grid, 256, 0, st>>>(in_dev, out_dev, n_in, n_out, inner, Mk); }
 }
 
 int pre_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_host, int n_in, int n_out, int64_t inner,
@@ -122,8 +122,9 @@ int pre_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_ho
   for (int o = 0; o < n_out; ++o)
     for (int n = 0; n < n_in; ++n) Mk.m[o * 32 + n] = M_host[o * n_in + n];
   bool vec = (inner % 4 == 0) && (((uintptr_t)in_dev & 15) == 0) && (((uintptr_t)out_dev & 15) == 0);
-  if (vec) launch_temporal_matmul<4>(in_dev, out_dev, n_in, n_out, inner, Mk, ctx->stream);
-  else launch_temporal_matmul<1>(in_dev, out_dev, n_in, n_out, inner, Mk, ctx->stream);
+  { TraceScope ts_(ctx, "temporal_matmul_kernel");
+    if (vec) launch_temporal_matmul<4>(in_dev, out_dev, n_in, n_out, inner, Mk, ctx->stream);
+    else launch_temporal_matmul<1>(in_dev, out_dev, n_in, n_out, inner, Mk, ctx->stream); }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) indices_kernel(const float* __restrict__ 
 
 int pre_indices_dev(stc_ctx* ctx, const float* in_dev, int64_t npix, int C, float* out_dev) {
   if (C < 10) STC_FAIL(STC_ERR_ARG, "indices: need at least 10 bands");
-  indices_kernel<<<cdiv(npix, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, npix, C);
+  { TraceScope ts_(ctx, "indices_kernel"); indices_kernel<<<cdiv(npix, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, npix, C); }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) temporal_median_kernel(const float* __res
 
 int pre_temporal_median_dev(stc_ctx* ctx, const float* in_dev, int n, int64_t inner, float* out_dev) {
   if (n < 1 || n > 32) STC_FAIL(STC_ERR_ARG, "temporal_median: n must be in 1..32");
-  temporal_median_kernel<<<cdiv(inner, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n, inner);
+  { TraceScope ts_(ctx, "temporal_median_kernel"); temporal_median_kernel<<<cdiv(inner, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n, inner); }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;

@@ -175,7 +175,7 @@ static int sr_apply(stc_ctx* ctx, SrState* s, int mode, int write_skip, Act* dst
   ap.write_skip = write_skip;
   if (dst) { ap.dst = dst->at(0); ap.dst_plane = dst->plane; }
   ap.bil = bil; ap.bil_stride = bil_stride; ap.bil_off = bil_off; ap.out = out; ap.N = s->N; ap.H = s->H; ap.W = s->W; ap.mode = mode;
-  sr_apply_kernel<<<cdiv((int64_t)s->N * s->H * s->W, 256), 256, 0, ctx->stream>>>(ap);
+  { TraceScope ts_(ctx, "sr_apply_kernel"); sr_apply_kernel<<<cdiv((int64_t)s->N * s->H * s->W, 256), 256, 0, ctx->stream>>>(ap); }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;
@@ -186,7 +186,7 @@ int sr_forward_dev(stc_ctx* ctx, const float* x_dev, const float* bil_dev, int N
   if (!s || !s->ready) STC_FAIL(STC_ERR_STATE, "superresolve: weights not finalized");
   if (H < 3 || W < 3 || N < 1) STC_FAIL(STC_ERR_ARG, "superresolve: bad shape");
   int rc = sr_plan(ctx, s, N, H, W); if (rc) return rc;
-  sr_prep_kernel<<<cdiv((int64_t)N * H * W, 256), 256, 0, ctx->stream>>>(x_dev, N, H, W, s->X.at(0), s->X.plane);
+  { TraceScope ts_(ctx, "sr_prep_kernel"); sr_prep_kernel<<<cdiv((int64_t)N * H * W, 256), 256, 0, ctx->stream>>>(x_dev, N, H, W, s->X.at(0), s->X.plane); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
   if ((rc = sr_conv(ctx, s, 0, s->X, MODE_BIAS_RELU))) return rc;
   if ((rc = sr_apply(ctx, s, 0, 1, &s->A, nullptr, nullptr))) return rc;      // a (skip = a)

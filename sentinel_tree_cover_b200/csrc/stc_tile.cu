@@ -362,7 +362,7 @@ struct TimeMarks {
 };
 
 #define TL_CHECK(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
-#define TL_LAUNCH(kern, n, ...) do { kern<<<cdiv((n), 256), 256, 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
+#define TL_LAUNCH(kern, n, ...) do { TraceScope ts_(ctx, #kern); kern<<<cdiv((n), 256), 256, 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
 
 // np.delete(x, idx, axis=0) on a device array of `n` slabs: the kept slabs move down in order
 int compact_slabs(stc_ctx* ctx, void* base, size_t slab_bytes, int n, const std::vector<int>& keep) {
@@ -464,7 +464,7 @@ extern "C" int stc_tile_run_host(stc_ctx* ctx, const uint16_t* s2_10_host, int n
     if (ay.out_len != H || ax.out_len != W) STC_FAIL(STC_ERR_ARG, "tile_run: Sentinel-1 shape cannot be aligned to the 10 m grid (adjust_shape leaves a mismatch; the reference fails in its slicing)");
     STC_CUDA(S.s1.alloc((size_t)m1 * HW * 8));
     const int64_t tot = (int64_t)m1 * HW * 2;
-    k_adjust<float><<<cdiv(tot, 256), 256, 0, ctx->stream>>>(s1raw.as<float>(), hs, ws, 2, S.s1.as<float>(), H, W, ay.shift, ax.shift, tot); ctx->launches++;
+    { TraceScope ts_(ctx, "k_adjust"); k_adjust<float><<<cdiv(tot, 256), 256, 0, ctx->stream>>>(s1raw.as<float>(), hs, ws, 2, S.s1.as<float>(), H, W, ay.shift, ax.shift, tot); } ctx->launches++;
   }
   // DEM: 5 x 5 median filter (:713), adjust_shape
   {
@@ -474,7 +474,7 @@ extern "C" int stc_tile_run_host(stc_ctx* ctx, const uint16_t* s2_10_host, int n
     const AxisPlan ay = tilehost::adjust_axis(hd, H), ax = tilehost::adjust_axis(wd, W);
     if (ay.out_len != H || ax.out_len != W) STC_FAIL(STC_ERR_ARG, "tile_run: DEM shape cannot be aligned to the 10 m grid (adjust_shape)");
     STC_CUDA(S.dem.alloc((size_t)HW * 4));
-    k_adjust<float><<<cdiv(HW, 256), 256, 0, ctx->stream>>>(dmed.as<float>(), hd, wd, 1, S.dem.as<float>(), H, W, ay.shift, ax.shift, HW); ctx->launches++;
+    { TraceScope ts_(ctx, "k_adjust"); k_adjust<float><<<cdiv(HW, 256), 256, 0, ctx->stream>>>(dmed.as<float>(), hd, wd, 1, S.dem.as<float>(), H, W, ay.shift, ax.shift, HW); } ctx->launches++;
   }
   // Sentinel-2: adjust_shape of the 10 m bands (pure data movement, done on the uint16 samples), decode, 20 m -> 10 m stack
   {
@@ -484,7 +484,7 @@ extern "C" int stc_tile_run_host(stc_ctx* ctx, const uint16_t* s2_10_host, int n
     if (h10 != H || w10 != W) {
       STC_CUDA(u10adj.alloc((size_t)n * HW * 8));
       const int64_t tot = (int64_t)n * HW * 4;
-      k_adjust<uint16_t><<<cdiv(tot, 256), 256, 0, ctx->stream>>>(src10, h10, w10, 4, u10adj.as<uint16_t>(), H, W, ay.shift, ax.shift, tot); ctx->launches++;
+      { TraceScope ts_(ctx, "k_adjust"); k_adjust<uint16_t><<<cdiv(tot, 256), 256, 0, ctx->stream>>>(src10, h10, w10, 4, u10adj.as<uint16_t>(), H, W, ay.shift, ax.shift, tot); } ctx->launches++;
       src10 = u10adj.as<uint16_t>();
     }
     STC_CUDA(f10.alloc((size_t)n * HW * 16)); STC_CUDA(f20.alloc((size_t)n20 * 4)); STC_CUDA(S.s2.alloc((size_t)n * HW * 40));
@@ -600,12 +600,12 @@ extern "C" int stc_tile_run_host(stc_ctx* ctx, const uint16_t* s2_10_host, int n
       STC_CUDA(wins.alloc(wl.size() * sizeof(SrWin)));
       STC_CUDA(cudaMemcpyAsync(wins.p, wl.data(), wl.size() * sizeof(SrWin), cudaMemcpyHostToDevice, ctx->stream));
       STC_CUDA(gat.alloc((size_t)nw * S.n * P * P * 40)); STC_CUDA(res.alloc((size_t)nw * S.n * P * P * 24));
-      k_sr_gather<<<dim3(cdiv(P * P, 256), S.n, nw), 256, 0, ctx->stream>>>(S.s2.as<float>(), band.as<float>(), wins.as<SrWin>(), S.n, H, W, band_rows,
-                                                                            wsz, gat.as<float>());
+      { TraceScope ts_(ctx, "k_sr_gather"); k_sr_gather<<<dim3(cdiv(P * P, 256), S.n, nw), 256, 0, ctx->stream>>>(S.s2.as<float>(), band.as<float>(), wins.as<SrWin>(), S.n, H, W, band_rows,
+                                                                            wsz, gat.as<float>()); }
       ctx->launches++;
       TL_CHECK(sr_forward_dev(ctx, gat.as<float>(), nullptr, nw * S.n, P, P, res.as<float>()));
-      k_sr_scatter<<<dim3(cdiv(wsz * wsz, 256), S.n, nw), 256, 0, ctx->stream>>>(res.as<float>(), wins.as<SrWin>(), S.n, H, W, band_rows, wsz,
-                                                                                 S.s2.as<float>(), band.as<float>());
+      { TraceScope ts_(ctx, "k_sr_scatter"); k_sr_scatter<<<dim3(cdiv(wsz * wsz, 256), S.n, nw), 256, 0, ctx->stream>>>(res.as<float>(), wins.as<SrWin>(), S.n, H, W, band_rows, wsz,
+                                                                                 S.s2.as<float>(), band.as<float>()); }
       ctx->launches++;
       STC_CUDA(cudaStreamSynchronize(ctx->stream));          // wl is a host vector
       return STC_OK;

@@ -56,7 +56,7 @@ int tf_s2_medians_dev(stc_ctx* ctx, float* s2, int n, int H, int W, float* media
   for (int t = 0; t < n; ++t) nans += h[n + t];
   *nan_total_host = nans;
   if (nans) {            // interpolate_na_vals: NaN -> 0 (the reference fills in place), then the counts see the zeros
-    k_nan_to_zero<<<cdiv(px * 10, 256), 256, 0, ctx->stream>>>(s2, px * 10); ctx->launches++;
+    { TraceScope ts_(ctx, "k_nan_to_zero"); k_nan_to_zero<<<cdiv(px * 10, 256), 256, 0, ctx->stream>>>(s2, px * 10); } ctx->launches++;
     STC_CUDA(cudaMemsetAsync(cnt.p, 0, 2 * n * 4, ctx->stream));
     TF_CHECK(interp_missing_counts_dev(ctx, s2, n, HW, 10, cnt.as<int>(), cnt.as<int>() + n));
     STC_CUDA(cudaMemcpyAsync(h.data(), cnt.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -66,7 +66,7 @@ int tf_s2_medians_dev(stc_ctx* ctx, float* s2, int n, int H, int W, float* media
   TF_CHECK(pre_temporal_median_dev(ctx, s2, n, (int64_t)HW * 10, m10.as<float>()));
   TF_CHECK(pre_indices_dev(ctx, s2, px, 10, idx.as<float>()));
   TF_CHECK(pre_temporal_median_dev(ctx, idx.as<float>(), n, (int64_t)HW * 4, m4.as<float>()));
-  k_concat_channels<<<cdiv((int64_t)HW * 14, 256), 256, 0, ctx->stream>>>(m10.as<float>(), 10, m4.as<float>(), 4, HW, median14_dev); ctx->launches++;
+  { TraceScope ts_(ctx, "k_concat_channels"); k_concat_channels<<<cdiv((int64_t)HW * 14, 256), 256, 0, ctx->stream>>>(m10.as<float>(), 10, m4.as<float>(), 4, HW, median14_dev); } ctx->launches++;
   STC_CUDA(cudaGetLastError());
   return STC_OK;
 }
@@ -95,7 +95,7 @@ int tf_smooth_quarterly_dev(stc_ctx* ctx, float* s2, int n, int H, int W, const 
   TF_CHECK(pre_indices_dev(ctx, s2, px, 10, idx.as<float>()));                         // make_indices :998
   TF_CHECK(pre_temporal_matmul_dev(ctx, s2, M_host, n, 12, (int64_t)HW * 10, sm10.as<float>()));
   TF_CHECK(pre_temporal_matmul_dev(ctx, idx.as<float>(), M_host, n, 12, (int64_t)HW * 4, sm4.as<float>()));
-  k_concat_channels<<<cdiv((int64_t)12 * HW * 14, 256), 256, 0, ctx->stream>>>(sm10.as<float>(), 10, sm4.as<float>(), 4, (int64_t)12 * HW, sm14p);
+  { TraceScope ts_(ctx, "k_concat_channels"); k_concat_channels<<<cdiv((int64_t)12 * HW * 14, 256), 256, 0, ctx->stream>>>(sm10.as<float>(), 10, sm4.as<float>(), 4, (int64_t)12 * HW, sm14p); }
   ctx->launches++;
   if (s2_quarterly_dev)
     for (int k = 0; k < 4; ++k)
@@ -172,7 +172,7 @@ extern "C" int stc_predict_postprocess_host(stc_ctx* ctx, const float* x_host, c
   TF_CHECK(model_predict_dev(ctx, x.as<float>(), B, T, H, H, length, 1, min17, max17, preds.as<float>()));
   for (int i = 0; i < B; ++i) {
     float* p = preds.as<float>() + (size_t)i * S * S;
-    if (no_data_host[i]) { k_fill_value<<<cdiv(S * S, 256), 256, 0, ctx->stream>>>(p, (int64_t)S * S, 255.f); ctx->launches++; }   // np.full((SIZE, SIZE), 255)
+    if (no_data_host[i]) { { TraceScope ts_(ctx, "k_fill_value"); k_fill_value<<<cdiv(S * S, 256), 256, 0, ctx->stream>>>(p, (int64_t)S * S, 255.f); } ctx->launches++; }   // np.full((SIZE, SIZE), 255)
     TF_CHECK(post_subtile_dev(ctx, p, x.as<float>() + per * i, mc.as<float>() + (size_t)i * H * H, S, T + 1, 17, a.as<unsigned char>(),
                               b.as<unsigned char>(), d2.as<int>(), ramp.as<double>(), na.as<unsigned char>(), nb.as<unsigned char>(),
                               vote.as<unsigned char>(), out.as<float>() + (size_t)i * S * S));
@@ -283,16 +283,16 @@ int tf_process_subtiles_dev(stc_ctx* ctx, const float* s2q, const float* s1q, co
   STC_CUDA(stc_dmalloc(&vote.p, 256));
   static_assert(sizeof(Win) == 48, "window table layout");
   STC_CUDA(cudaMemcpyAsync(win.p, windows_host, (size_t)nt * 48, cudaMemcpyHostToDevice, ctx->stream));
-  k_gather_subtiles<<<dim3(cdiv(P * P, 256), T + 1, nt), 256, 0, ctx->stream>>>(s2q, s1q, s2m, s1m, dem, win.as<Win>(), T, H, W, P, x.as<float>());
-  k_gather_clear<<<dim3(cdiv(P * P, 256), nt), 256, 0, ctx->stream>>>(clr, win.as<Win>(), W, P, mc.as<float>());
-  k_no_image_test<<<nt, 256, 0, ctx->stream>>>(clr, win.as<Win>(), W, force_no_data, flags.as<int>());
+  { TraceScope ts_(ctx, "k_gather_subtiles"); k_gather_subtiles<<<dim3(cdiv(P * P, 256), T + 1, nt), 256, 0, ctx->stream>>>(s2q, s1q, s2m, s1m, dem, win.as<Win>(), T, H, W, P, x.as<float>()); }
+  { TraceScope ts_(ctx, "k_gather_clear"); k_gather_clear<<<dim3(cdiv(P * P, 256), nt), 256, 0, ctx->stream>>>(clr, win.as<Win>(), W, P, mc.as<float>()); }
+  { TraceScope ts_(ctx, "k_no_image_test"); k_no_image_test<<<nt, 256, 0, ctx->stream>>>(clr, win.as<Win>(), W, force_no_data, flags.as<int>()); }
   ctx->launches += 3;
   STC_CUDA(cudaStreamSynchronize(ctx->stream));      // the caller's window table may go away
   ctx->feat_early_dev = early_dev; ctx->feat_late_dev = late_dev;       // --gen_feats taps [nt,S,S,64] (optional)
   const int rc_fwd = model_predict_dev(ctx, x.as<float>(), nt, T, P, P, length, 1, min17, max17, preds.as<float>());
   ctx->feat_early_dev = ctx->feat_late_dev = nullptr;
   if (rc_fwd) return rc_fwd;
-  k_fill_if<<<dim3(cdiv(S * S, 256), nt), 256, 0, ctx->stream>>>(preds.as<float>(), flags.as<int>(), S * S, 255.f); ctx->launches++;
+  { TraceScope ts_(ctx, "k_fill_if"); k_fill_if<<<dim3(cdiv(S * S, 256), nt), 256, 0, ctx->stream>>>(preds.as<float>(), flags.as<int>(), S * S, 255.f); } ctx->launches++;
   for (int i = 0; i < nt; ++i)
     TF_CHECK(post_subtile_dev(ctx, preds.as<float>() + (size_t)i * S * S, x.as<float>() + per * i, mc.as<float>() + (size_t)i * P * P, S, T + 1, 17,
                               a.as<unsigned char>(), b.as<unsigned char>(), d2.as<int>(), ramp.as<double>(), na.as<unsigned char>(),

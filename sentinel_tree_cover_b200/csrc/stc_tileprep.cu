@@ -149,40 +149,40 @@ __global__ void __launch_bounds__(256) k_max_masked(float* __restrict__ a, const
 
 // ---- device-level launchers (shared with stc_tile.cu: the device-resident tile chain) ----
 int tp_s1_fill_dev(stc_ctx* ctx, float* s1_dev, int m, int len) {
-  k_s1_fill<<<m, 1024, 0, ctx->stream>>>(s1_dev, len); ctx->launches++;
+  { TraceScope ts_(ctx, "k_s1_fill"); k_s1_fill<<<m, 1024, 0, ctx->stream>>>(s1_dev, len); } ctx->launches++;
   return STC_OK;
 }
 int tp_median5_dev(stc_ctx* ctx, const float* in_dev, int H, int W, float* out_dev) {
-  k_median5<<<cdiv(H * W, 256), 256, 0, ctx->stream>>>(in_dev, H, W, out_dev); ctx->launches++;
+  { TraceScope ts_(ctx, "k_median5"); k_median5<<<cdiv(H * W, 256), 256, 0, ctx->stream>>>(in_dev, H, W, out_dev); } ctx->launches++;
   return STC_OK;
 }
 int tp_clm_pairs_dev(stc_ctx* ctx, float* clm_dev, int n, int HW) {
-  k_clm_pairs<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(clm_dev, n, HW); ctx->launches++;
+  { TraceScope ts_(ctx, "k_clm_pairs"); k_clm_pairs<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(clm_dev, n, HW); } ctx->launches++;
   return STC_OK;
 }
 // per_date_dev [n] int32 (zeroed here), low_tmp / snow_dev [HW] uint8
 int tp_snow_dev(stc_ctx* ctx, const float* s2_dev, int n, int H, int W, int* per_date_dev, unsigned char* low_tmp, unsigned char* snow_dev) {
   const int HW = H * W;
   STC_CUDA(cudaMemsetAsync(per_date_dev, 0, n * 4, ctx->stream));
-  k_snow<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(s2_dev, n, HW, per_date_dev, low_tmp); ctx->launches++;
+  { TraceScope ts_(ctx, "k_snow"); k_snow<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(s2_dev, n, HW, per_date_dev, low_tmp); } ctx->launches++;
   maskop_dilate(ctx, low_tmp, snow_dev, 1, H, W, 2, 1, 0, 1, 0);     // 1 - binary_dilation(snow < 0.7, 2)
   return STC_OK;
 }
 int tp_count_gt_dev(stc_ctx* ctx, const float* data_dev, int nseg, int len, float thresh, int* counts_dev) {
   STC_CUDA(cudaMemsetAsync(counts_dev, 0, nseg * 4, ctx->stream));
-  k_count_gt<<<dim3(cdiv(len, 256), nseg), 256, 0, ctx->stream>>>(data_dev, len, thresh, counts_dev); ctx->launches++;
+  { TraceScope ts_(ctx, "k_count_gt"); k_count_gt<<<dim3(cdiv(len, 256), nseg), 256, 0, ctx->stream>>>(data_dev, len, thresh, counts_dev); } ctx->launches++;
   return STC_OK;
 }
 int tp_elementwise_dev(stc_ctx* ctx, float* x_dev, int64_t n, int mode, float a, float b) {
-  k_elementwise<<<cdiv(n, 256), 256, 0, ctx->stream>>>(x_dev, n, mode, a, b); ctx->launches++;
+  { TraceScope ts_(ctx, "k_elementwise"); k_elementwise<<<cdiv(n, 256), 256, 0, ctx->stream>>>(x_dev, n, mode, a, b); } ctx->launches++;
   return STC_OK;
 }
 int tp_max_masked_dev(stc_ctx* ctx, float* a_dev, const float* b_dev, const unsigned char* zero_dev, int64_t n) {
-  k_max_masked<<<cdiv(n, 256), 256, 0, ctx->stream>>>(a_dev, b_dev, zero_dev, n); ctx->launches++;
+  { TraceScope ts_(ctx, "k_max_masked"); k_max_masked<<<cdiv(n, 256), 256, 0, ctx->stream>>>(a_dev, b_dev, zero_dev, n); } ctx->launches++;
   return STC_OK;
 }
 int tp_count_lt_axis0_dev(stc_ctx* ctx, const float* data_dev, int n, int64_t len, float thresh, int* out_dev) {
-  k_count_lt_axis0<<<cdiv(len, 256), 256, 0, ctx->stream>>>(data_dev, n, len, thresh, out_dev); ctx->launches++;
+  { TraceScope ts_(ctx, "k_count_lt_axis0"); k_count_lt_axis0<<<cdiv(len, 256), 256, 0, ctx->stream>>>(data_dev, n, len, thresh, out_dev); } ctx->launches++;
   return STC_OK;
 }
 
@@ -194,7 +194,7 @@ extern "C" int stc_s1_fill_host(stc_ctx* ctx, float* s1_host, int m, int H, int 
   const int len = H * W * C; TBuf d;
   STC_CUDA(stc_dmalloc(&d.p, (size_t)m * len * 4));
   STC_CUDA(cudaMemcpyAsync(d.p, s1_host, (size_t)m * len * 4, cudaMemcpyHostToDevice, ctx->stream));
-  k_s1_fill<<<m, 1024, 0, ctx->stream>>>(d.as<float>(), len); ctx->launches++;
+  { TraceScope ts_(ctx, "k_s1_fill"); k_s1_fill<<<m, 1024, 0, ctx->stream>>>(d.as<float>(), len); } ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(s1_host, d.p, (size_t)m * len * 4, cudaMemcpyDeviceToHost, ctx->stream));
   TP_FINISH();
 }
@@ -205,7 +205,7 @@ extern "C" int stc_median_filter5_host(stc_ctx* ctx, const float* in_host, int H
   TBuf a, b;
   STC_CUDA(stc_dmalloc(&a.p, (size_t)H * W * 4)); STC_CUDA(stc_dmalloc(&b.p, (size_t)H * W * 4));
   STC_CUDA(cudaMemcpyAsync(a.p, in_host, (size_t)H * W * 4, cudaMemcpyHostToDevice, ctx->stream));
-  k_median5<<<cdiv(H * W, 256), 256, 0, ctx->stream>>>(a.as<float>(), H, W, b.as<float>()); ctx->launches++;
+  { TraceScope ts_(ctx, "k_median5"); k_median5<<<cdiv(H * W, 256), 256, 0, ctx->stream>>>(a.as<float>(), H, W, b.as<float>()); } ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(out_host, b.p, (size_t)H * W * 4, cudaMemcpyDeviceToHost, ctx->stream));
   TP_FINISH();
 }
@@ -216,7 +216,7 @@ extern "C" int stc_clm_pairs_host(stc_ctx* ctx, float* clm_host, int n, int H, i
   TBuf d; const size_t bytes = (size_t)n * H * W * 4;
   STC_CUDA(stc_dmalloc(&d.p, bytes));
   STC_CUDA(cudaMemcpyAsync(d.p, clm_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  k_clm_pairs<<<cdiv(H * W, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, H * W); ctx->launches++;
+  { TraceScope ts_(ctx, "k_clm_pairs"); k_clm_pairs<<<cdiv(H * W, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, H * W); } ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(clm_host, d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   TP_FINISH();
 }
@@ -228,7 +228,7 @@ extern "C" int stc_snow_host(stc_ctx* ctx, const float* s2_host, int n, int H, i
   STC_CUDA(stc_dmalloc(&d.p, (size_t)n * HW * 40)); STC_CUDA(stc_dmalloc(&cnt.p, n * 4)); STC_CUDA(stc_dmalloc(&a.p, HW)); STC_CUDA(stc_dmalloc(&b.p, HW));
   STC_CUDA(cudaMemcpyAsync(d.p, s2_host, (size_t)n * HW * 40, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemsetAsync(cnt.p, 0, n * 4, ctx->stream));
-  k_snow<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, HW, cnt.as<int>(), a.as<unsigned char>()); ctx->launches++;
+  { TraceScope ts_(ctx, "k_snow"); k_snow<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, HW, cnt.as<int>(), a.as<unsigned char>()); } ctx->launches++;
   maskop_dilate(ctx, a.as<unsigned char>(), b.as<unsigned char>(), 1, H, W, 2, 1, 0, 1, 0);     // 1 - binary_dilation(snow < 0.7, 2)
   STC_CUDA(cudaMemcpyAsync(per_date_host, cnt.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(snow_host, b.p, HW, cudaMemcpyDeviceToHost, ctx->stream));
@@ -242,7 +242,7 @@ extern "C" int stc_count_gt_host(stc_ctx* ctx, const float* data_host, int nseg,
   STC_CUDA(stc_dmalloc(&d.p, (size_t)nseg * len * 4)); STC_CUDA(stc_dmalloc(&cnt.p, nseg * 4));
   STC_CUDA(cudaMemcpyAsync(d.p, data_host, (size_t)nseg * len * 4, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemsetAsync(cnt.p, 0, nseg * 4, ctx->stream));
-  k_count_gt<<<dim3(cdiv(len, 256), nseg), 256, 0, ctx->stream>>>(d.as<float>(), len, thresh, cnt.as<int>()); ctx->launches++;
+  { TraceScope ts_(ctx, "k_count_gt"); k_count_gt<<<dim3(cdiv(len, 256), nseg), 256, 0, ctx->stream>>>(d.as<float>(), len, thresh, cnt.as<int>()); } ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(counts_host, cnt.p, nseg * 4, cudaMemcpyDeviceToHost, ctx->stream));
   TP_FINISH();
 }
@@ -253,7 +253,7 @@ extern "C" int stc_elementwise_host(stc_ctx* ctx, float* x_host, int64_t n, int 
   TBuf d;
   STC_CUDA(stc_dmalloc(&d.p, (size_t)n * 4));
   STC_CUDA(cudaMemcpyAsync(d.p, x_host, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-  k_elementwise<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, mode, a, b); ctx->launches++;
+  { TraceScope ts_(ctx, "k_elementwise"); k_elementwise<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, mode, a, b); } ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(x_host, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   TP_FINISH();
 }
@@ -266,7 +266,7 @@ extern "C" int stc_max_masked_host(stc_ctx* ctx, float* a_host, const float* b_h
   STC_CUDA(cudaMemcpyAsync(a.p, a_host, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(b.p, b_host, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
   if (zero_host) { STC_CUDA(stc_dmalloc(&z.p, (size_t)n)); STC_CUDA(cudaMemcpyAsync(z.p, zero_host, (size_t)n, cudaMemcpyHostToDevice, ctx->stream)); }
-  k_max_masked<<<cdiv(n, 256), 256, 0, ctx->stream>>>(a.as<float>(), b.as<float>(), zero_host ? z.as<unsigned char>() : nullptr, n); ctx->launches++;
+  { TraceScope ts_(ctx, "k_max_masked"); k_max_masked<<<cdiv(n, 256), 256, 0, ctx->stream>>>(a.as<float>(), b.as<float>(), zero_host ? z.as<unsigned char>() : nullptr, n); } ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(a_host, a.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   TP_FINISH();
 }
@@ -277,7 +277,7 @@ extern "C" int stc_count_lt_axis0_host(stc_ctx* ctx, const float* data_host, int
   TBuf d, o;
   STC_CUDA(stc_dmalloc(&d.p, (size_t)n * len * 4)); STC_CUDA(stc_dmalloc(&o.p, (size_t)len * 4));
   STC_CUDA(cudaMemcpyAsync(d.p, data_host, (size_t)n * len * 4, cudaMemcpyHostToDevice, ctx->stream));
-  k_count_lt_axis0<<<cdiv(len, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, len, thresh, o.as<int>()); ctx->launches++;
+  { TraceScope ts_(ctx, "k_count_lt_axis0"); k_count_lt_axis0<<<cdiv(len, 256), 256, 0, ctx->stream>>>(d.as<float>(), n, len, thresh, o.as<int>()); } ctx->launches++;
   STC_CUDA(cudaMemcpyAsync(out_host, o.p, (size_t)len * 4, cudaMemcpyDeviceToHost, ctx->stream));
   TP_FINISH();
 }

@@ -201,3 +201,49 @@ def test_predict_subtile_monthly_legacy_contract(sess, predict_weights):
     assert got.shape == (28, 28) and got.dtype == np.float32 and err < TOL
     z = predict_subtile_monthly(np.zeros((13, 44, 44, 13), np.float32), sess)
     assert z.shape == (30, 30) and (z == 255).all()
+
+
+def test_uint16_wire_format_vs_f32_oracle_on_original_floats(sess, predict_weights):
+    """The uint16 patch transport (x/65535, predict_subtile :345-347) against the float32 ORACLE evaluated on the
+    ORIGINAL, un-quantised floats: quantisation (<= 7.6e-6 per input value) plus fp16 tensor-core error together must stay
+    within the 1e-3 budget."""
+    m = P.synth_monthly(3, 76, 43)
+    u = np.clip(np.rint(m * 65535.0), 0, 65535).astype(np.uint16)
+    y_u = sess.predict_patches(u)
+    ref = PredictRef(predict_weights).forward(P.normalize_subtile(P.assemble(m), MIN_ALL, MAX_ALL))
+    err = np.abs(y_u - ref)
+    print("u16 wire vs f32 oracle on original floats: max", err.max(), "mean", err.mean())
+    assert err.max() < TOL
+
+
+def test_predictions_are_bit_identical_run_to_run_and_across_batch_positions(sess):
+    """GroupNorm statistics are accumulated as 64-bit fixed-point integers per sample-aligned tile: the same patch gives
+    the same bytes whichever batch slot it sits in and however the blocks are scheduled (the reference is deterministic)."""
+    m = P.synth_monthly(5, 44, 44)
+    a = sess.predict_patches(m)
+    b = sess.predict_patches(m)
+    assert np.array_equal(a, b)
+    perm = np.array([3, 0, 4, 1, 2])
+    c = sess.predict_patches(np.ascontiguousarray(m[perm]))
+    assert np.array_equal(c, a[perm])
+    big = np.ascontiguousarray(np.concatenate([m] * 9)[:40])          # crosses the 32-tile chunk boundary
+    d = sess.predict_patches(big)
+    assert np.array_equal(d[:5], a) and np.array_equal(d[35:40], a)
+
+
+@pytest.mark.parametrize("size", [76, 124, 172, 220])
+def test_gpu_matches_real_tensorflow_golden_when_present(size):
+    """tests/golden/model_tf_<size>.npz (tools/make_golden_tf.py, a machine with TensorFlow): real Session.run outputs."""
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "model_tf_%d.npz" % size)
+    if not os.path.exists(path):
+        pytest.skip("no TensorFlow golden committed")
+    g = np.load(path)
+    w = {k[2:]: g[k] for k in g.files if k.startswith("w/")}
+    s = StcSession(0, predict_weights=w)
+    x = P.synth_model_input(int(g["batch"]), size, int(g["seed"]))
+    for b in range(int(g["batch"])):
+        y = s.predict(x[b:b + 1], length=int(g["length"][b]))[0]
+        assert np.abs(y - g["y"][b]).max() < TOL
+    s.close()
