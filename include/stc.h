@@ -297,7 +297,8 @@ int stc_remove_clouds_host(stc_ctx* ctx, float* tiles_host, const float* probs_h
  * (np.clip(sentinel2, 0, 1), src/download_and_predict_job.py:996, is the next statement on that path) and
  * *clipped_out = 1; otherwise the cube comes back unclipped (the masks are recomputed on it first, :972-990). */
 /* Test hook (host only, no device): Python's random.shuffle replayed on data[0..n) from the generator state mt_state
- * (624 MT19937 words + position, `random.getstate()[1]`); the advanced state is written back. */
+ * (624 MT19937 words + position, `random.getstate()[1]`); the advanced state is written back.  data == NULL walks the
+ * generator through the same draws without shuffling anything (the state a following shuffle would start from). */
 int stc_py_shuffle(uint32_t* mt_state, int32_t* data, int64_t n);
 int stc_remove_clouds_clip_host(stc_ctx* ctx, float* tiles_host, const float* probs_host, const uint8_t* pfcps_host, int n, int H, int W,
                                 uint32_t* mt_state, float* areas_out_host, int32_t* to_remove_out_host, int32_t* clipped_out);
@@ -340,6 +341,15 @@ int stc_build_sentinel2_host(stc_ctx* ctx, const float* s2_10_host, const float*
  *      5 +brightness/whiteness, 6 after false-positive removal, 7 after shape clean-up, 8 before haze). ---- */
 int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const float* dem_host, int T, int H, int W,
                          float* clouds_host, uint8_t* fcps_host, uint8_t* stage_host, int stage_id);
+/* Ancillary rasters of the tile whose masks are computed next (replaces the file reads of
+ * src/preprocessing/cloud_removal.py:735-771: mask_nonurban_areas("urbanmask.tif", ...) inside detect_pfcp :1131-1135 and
+ * adjust_cloudmask_in_forests("forestmask.tif", ...) :1254-1257).  Reading the .tif window is the caller's I/O; the arrays
+ * come in at tile resolution, uint8 0/1: forest [H,W] = the function's return value; urban_core / urban_near [H,W] = the
+ * two resized rasters of mask_nonurban_areas (dilated once :745-747; dilated five more times :751-752).  NULL = that
+ * raster is absent (the reference's except-branch: zeros).  The masks stay set until replaced and apply to
+ * stc_cloud_masks_host / stc_tile_run_host calls with the same H, W. */
+int stc_set_ancillary_masks_host(stc_ctx* ctx, const uint8_t* forest_host, const uint8_t* urban_core_host, const uint8_t* urban_near_host,
+                                 int H, int W);
 
 /* ---- one whole tile, device-resident: the body of the reference's main loop
  *      (src/download_and_predict_job.py:1995-2020)  process_tile (:640-997, make_shadow) -> superresolve_large_tile

@@ -41,6 +41,7 @@ void stc_destroy(stc_ctx* ctx) {
     if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
   }
   if (ctx->stage_out) cudaFree(ctx->stage_out);
+  for (unsigned char* p : {ctx->anc_forest, ctx->anc_urban_core, ctx->anc_urban_near}) if (p) cudaFree(p);
   if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
   if (ctx->stage_ring) cudaFreeHost(ctx->stage_ring);
   if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->aux_ev[0]); cudaEventDestroy(ctx->aux_ev[1]); }

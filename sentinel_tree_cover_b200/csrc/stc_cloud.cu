@@ -7,6 +7,7 @@
 // temporal stages; spatial stages are windowed searches with SciPy's border semantics.
 // Stage-by-stage parity is checked against oracle/cloud_ref.py (tests/test_cloud_masks.py).
 #include "stc_common.cuh"
+#include "stc_select.cuh"
 #include <cmath>
 #include <cstring>
 #include <algorithm>
@@ -21,53 +22,8 @@ struct Buf { void* p = nullptr; ~Buf() { if (p) stc_dfree(p); } };
 // ---------------------------------------------------------------------------------------------
 // generic spatial primitives on [T][H][W] uint8 masks
 // ---------------------------------------------------------------------------------------------
-// out = inv_out ^ (exists q within L1 (conn 1) / Linf (conn 2) radius k of p, in-image, with (in[q] != 0) ^ inv_in)
-// three_d: the L1 ball also spans the date axis (scipy binary_dilation on a 3-D array, 3-D cross).
-__global__ void __launch_bounds__(256) k_dilate(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int T, int H,
-                                                int W, int k, int conn, int inv_in, int inv_out, int three_d) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)T * H * W) return;
-  int x = (int)(idx % W); int64_t r = idx / W; int y = (int)(r % H); int t = (int)(r / H);
-  unsigned char hit = 0;
-  int dt0 = three_d ? -k : 0, dt1 = three_d ? k : 0;
-  for (int dt = dt0; dt <= dt1 && !hit; ++dt) {
-    int tt = t + dt; if (tt < 0 || tt >= T) continue;
-    int kk = k - abs(dt);
-    const unsigned char* m = in + (int64_t)tt * H * W;
-    for (int dy = -kk; dy <= kk && !hit; ++dy) {
-      int yy = y + dy; if (yy < 0 || yy >= H) continue;
-      int span = conn == 1 ? kk - abs(dy) : kk;
-      for (int dx = -span; dx <= span; ++dx) {
-        int xx = x + dx; if (xx < 0 || xx >= W) continue;
-        if ((m[(int64_t)yy * W + xx] != 0) ^ inv_in) { hit = 1; break; }
-      }
-    }
-  }
-  out[idx] = hit ^ inv_out;
-}
-
-// out = exists non-zero pixel of `in` within Euclidean distance <= radius  (1 - (edt(1 - in) > radius)).
-// A frame with no non-zero pixel has no background for scipy's distance_transform_edt, which then
-// measures from the virtual site (row -1, column 0): d^2 = (y+1)^2 + x^2 (scipy 1.x feature-transform
-// initialisation; pinned by tests/test_cloud_masks.py against the reference run in this image).
-__global__ void __launch_bounds__(256) k_edt_grow(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int T, int H,
-                                                  int W, int radius, const int* __restrict__ frame_count) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)T * H * W) return;
-  int x = (int)(idx % W); int64_t r = idx / W; int y = (int)(r % H); int t = (int)(r / H);
-  const unsigned char* m = in + (int64_t)t * H * W;
-  const int r2 = radius * radius;
-  if (frame_count[t] == 0) { out[idx] = ((y + 1) * (y + 1) + x * x) <= r2; return; }
-  unsigned char hit = 0;
-  for (int dy = -radius; dy <= radius && !hit; ++dy) {
-    int yy = y + dy; if (yy < 0 || yy >= H) continue;
-    for (int dx = -radius; dx <= radius; ++dx) {
-      int xx = x + dx; if (xx < 0 || xx >= W) continue;
-      if (dx * dx + dy * dy <= r2 && m[(int64_t)yy * W + xx]) { hit = 1; break; }
-    }
-  }
-  out[idx] = hit;
-}
+// binary dilation / erosion-by-dilation and the capped Euclidean grow are the separable passes of stc_morph.cu
+// (morph_dilate_dev, morph_edt_grow_dev)
 
 // 3x3 window sum with np.pad(mode='reflect') borders (cloud_removal.py:1244-1249, windowsize 3)
 __device__ __forceinline__ int winsum3(const unsigned char* m, int y, int x, int H, int W) {
@@ -204,71 +160,96 @@ __global__ void __launch_bounds__(128) k_shadow_candidates(const float* __restri
 // ---------------------------------------------------------------------------------------------
 struct CloudWin { int others_lo, others_hi; int close[3]; int nclose; };
 
-// per pixel of date t: ri_upper (3), ri_close (3), close_thresh; clouds_i; all from registers
+// Per pixel, ALL dates in one pass: the T x 3 visible-band references are loaded once into registers and every date's
+// ri_upper (3), ri_close (3), close_thresh and clouds_i are produced from them (round 1 launched this per date and
+// re-read the whole cube T times: 9.6 GB of DRAM traffic at T = 24).  forest: optional [HW] 0/1 mask (ESA WorldCover
+// forest, cloud_removal.py:1254-1257), nullptr = no forest anywhere.
+struct CloudWinAll { CloudWin w[CT_MAX]; };
 __global__ void __launch_bounds__(128) k_cloud_refs(const float* __restrict__ img, const unsigned char* __restrict__ shadows,
-                                                    StaticRefs s, int T, int HW, int t, CloudWin w,
-                                                    float* __restrict__ rc_out /*[HW][3]*/, float* __restrict__ thr_out /*[HW]*/,
-                                                    unsigned char* __restrict__ ci_out /*[HW]*/) {
+                                                    StaticRefs s, const unsigned char* __restrict__ forest, int T, int HW,
+                                                    const __grid_constant__ CloudWinAll wins,
+                                                    float* __restrict__ rc_out /*[T][HW][3]*/, float* __restrict__ thr_out /*[T][HW]*/,
+                                                    unsigned char* __restrict__ ci_out /*[T][HW]*/, int* __restrict__ ci_count /*[T]*/) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
+  const bool live = p < HW;
+  if (!live) p = HW - 1;                              // keep the warp whole for the ballots below
   float ref[CT_MAX][3];
+  float own[3];
   for (int tt = 0; tt < T; ++tt) {
     const float* q = img + ((int64_t)tt * HW + p) * 10;
     bool shd = (T > 2) && shadows[(int64_t)tt * HW + p];
     for (int k = 0; k < 3; ++k) ref[tt][k] = shd ? nanf("") : q[k];
   }
-  float up[3], rc[3];
-  if (T > 2) {
-    for (int k = 0; k < 3; ++k) {
-      float m = nanf("");
-      for (int tt = w.others_lo; tt < w.others_hi; ++tt) { float x = ref[tt][k]; if (!isnan(x)) m = isnan(m) ? x : fminf(m, x); }
-      up[k] = m;
-    }
-    if (isnan(up[0])) for (int k = 0; k < 3; ++k) up[k] = s.p25[p * 3 + k];
-    for (int k = 0; k < 3; ++k) {
-      float m = nanf("");
-      for (int c = 0; c < w.nclose; ++c) { int ci_ = w.close[c]; if (ci_ < 0) ci_ += T;   /* Python negative index */
-        float x = ref[ci_][k]; if (!isnan(x)) m = isnan(m) ? x : fminf(m, x); }
-      rc[k] = m;
-    }
-    // progressive widening (:1385-1394): the image-level `any NaN` test only bounds the number of
-    // rounds; per pixel the value is the first widened window that holds a valid date
-    int lo_i = w.close[0], hi_i = w.close[w.nclose - 1];
-    for (int it = 0; it < 10; ++it) {
-      lo_i = lo_i - 1 > 0 ? lo_i - 1 : 0; hi_i = hi_i + 1 < T ? hi_i + 1 : T;
+  const bool in_forest = forest && forest[p] == 1;
+  for (int t = 0; t < T; ++t) {
+    const CloudWin& w = wins.w[t];
+    float up[3], rc[3];
+    if (T > 2) {
       for (int k = 0; k < 3; ++k) {
-        if (!isnan(rc[k])) continue;
         float m = nanf("");
-        for (int tt = lo_i; tt < hi_i; ++tt) { if (tt == t) continue; float x = ref[tt][k]; if (!isnan(x)) m = isnan(m) ? x : fminf(m, x); }
+        for (int tt = w.others_lo; tt < w.others_hi; ++tt) { float x = ref[tt][k]; if (!isnan(x)) m = isnan(m) ? x : fminf(m, x); }
+        up[k] = m;
+      }
+      if (isnan(up[0])) for (int k = 0; k < 3; ++k) up[k] = s.p25[p * 3 + k];
+      for (int k = 0; k < 3; ++k) {
+        float m = nanf("");
+        for (int c = 0; c < w.nclose; ++c) { int ci_ = w.close[c]; if (ci_ < 0) ci_ += T;   /* Python negative index */
+          float x = ref[ci_][k]; if (!isnan(x)) m = isnan(m) ? x : fminf(m, x); }
         rc[k] = m;
       }
+      // progressive widening (:1385-1394): the image-level `any NaN` test only bounds the number of
+      // rounds; per pixel the value is the first widened window that holds a valid date
+      int lo_i = w.close[0], hi_i = w.close[w.nclose - 1];
+      for (int it = 0; it < 10; ++it) {
+        lo_i = lo_i - 1 > 0 ? lo_i - 1 : 0; hi_i = hi_i + 1 < T ? hi_i + 1 : T;
+        for (int k = 0; k < 3; ++k) {
+          if (!isnan(rc[k])) continue;
+          float m = nanf("");
+          for (int tt = lo_i; tt < hi_i; ++tt) { if (tt == t) continue; float x = ref[tt][k]; if (!isnan(x)) m = isnan(m) ? x : fminf(m, x); }
+          rc[k] = m;
+        }
+      }
+      for (int k = 0; k < 3; ++k) if (isnan(rc[k])) rc[k] = s.minrgb[p * 3 + k];
+    } else {
+      for (int k = 0; k < 3; ++k) { float m = INFINITY; for (int tt = 0; tt < T; ++tt) m = fminf(m, ref[tt][k]); rc[k] = m; up[k] = m; }
     }
-    for (int k = 0; k < 3; ++k) if (isnan(rc[k])) rc[k] = s.minrgb[p * 3 + k];
-  } else {
-    for (int k = 0; k < 3; ++k) { float m = INFINITY; for (int tt = 0; tt < T; ++tt) m = fminf(m, ref[tt][k]); rc[k] = m; up[k] = m; }
+    float thr = __fadd_rn(__fdiv_rn(__fdiv_rn(rc[0], 0.02f), 100.f), 0.005f);
+    thr = fminf(thr, 0.10f); thr = fmaxf(thr, 0.05f);
+    if (in_forest) thr = __fsub_rn(thr, 0.02f);       // close_thresh[forest_mask == 1] -= 0.02 (:1415)
+    thr = fmaxf(thr, 0.04f);
+    { const float* q = img + ((int64_t)t * HW + p) * 10; own[0] = q[0]; own[1] = q[1]; own[2] = q[2]; }     // L1 hit: read above
+    const bool ci = (__fsub_rn(own[0], up[0]) > 0.08f) && (__fsub_rn(own[1], up[1]) > 0.08f) && (__fsub_rn(own[2], up[2]) > 0.07f);
+    const unsigned bal = __ballot_sync(0xffffffffu, live && ci);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(ci_count + t, __popc(bal));
+    if (live) {
+      const int64_t i = (int64_t)t * HW + p;
+      ci_out[i] = ci;
+      rc_out[i * 3 + 0] = rc[0]; rc_out[i * 3 + 1] = rc[1]; rc_out[i * 3 + 2] = rc[2];
+      thr_out[i] = thr;
+    }
   }
-  float thr = __fadd_rn(__fdiv_rn(__fdiv_rn(rc[0], 0.02f), 100.f), 0.005f);
-  thr = fminf(thr, 0.10f); thr = fmaxf(thr, 0.05f); thr = fmaxf(thr, 0.04f);   // forest mask == 0 here
-  const float* x = img + ((int64_t)t * HW + p) * 10;
-  ci_out[p] = (__fsub_rn(x[0], up[0]) > 0.08f) && (__fsub_rn(x[1], up[1]) > 0.08f) && (__fsub_rn(x[2], up[2]) > 0.07f);
-  rc_out[p * 3 + 0] = rc[0]; rc_out[p * 3 + 1] = rc[1]; rc_out[p * 3 + 2] = rc[2];
-  thr_out[p] = thr;
 }
 
-// clouds_close for one modifier value (float32 arithmetic of `thr + mod + 0.01`), + counts
-__global__ void __launch_bounds__(256) k_cloud_close(const float* __restrict__ img, int HW, int t, const float* __restrict__ rc,
-                                                     const float* __restrict__ thr, float mod, unsigned char* __restrict__ cc,
-                                                     int* __restrict__ count) {
+// clouds_close of every still-active date for its current modifier (float32 arithmetic of `thr + mod + 0.01`), + counts
+struct CloseMods { float mod[CT_MAX]; int active[CT_MAX]; };
+__global__ void __launch_bounds__(256) k_cloud_close(const float* __restrict__ img, int HW, const float* __restrict__ rc_all,
+                                                     const float* __restrict__ thr_all, const __grid_constant__ CloseMods m,
+                                                     unsigned char* __restrict__ cc_all, int* __restrict__ count /*[T]*/) {
+  const int t = blockIdx.y;
+  if (!m.active[t]) return;
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned char v = 0;
   if (p < HW) {
-    const float* x = img + ((int64_t)t * HW + p) * 10;
-    float a = __fadd_rn(__fadd_rn(thr[p], mod), 0.01f), b = __fadd_rn(thr[p], mod);
-    v = (__fsub_rn(x[0], rc[p * 3]) > a) && (__fsub_rn(x[1], rc[p * 3 + 1]) > a) && (__fsub_rn(x[2], rc[p * 3 + 2]) > b);
-    cc[p] = v;
+    const int64_t i = (int64_t)t * HW + p;
+    const float* x = img + i * 10;
+    const float* rc = rc_all + i * 3;
+    const float mod = m.mod[t];
+    float a = __fadd_rn(__fadd_rn(thr_all[i], mod), 0.01f), b = __fadd_rn(thr_all[i], mod);
+    v = (__fsub_rn(x[0], rc[0]) > a) && (__fsub_rn(x[1], rc[1]) > a) && (__fsub_rn(x[2], rc[2]) > b);
+    cc_all[i] = v;
   }
   unsigned bal = __ballot_sync(0xffffffffu, v);
-  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count + t, __popc(bal));
 }
 
 __global__ void __launch_bounds__(256) k_count(const unsigned char* __restrict__ m, int n, int* __restrict__ count) {
@@ -285,12 +266,21 @@ __global__ void __launch_bounds__(256) k_count_dates(const unsigned char* __rest
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count + t, __popc(bal));
 }
 
-// cc &= (sum rgb < 0.75)
-__global__ void __launch_bounds__(256) k_cc_bright(const float* __restrict__ img, int HW, int t, unsigned char* __restrict__ cc) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
-  const float* x = img + ((int64_t)t * HW + p) * 10;
-  cc[p] = cc[p] && (__fadd_rn(__fadd_rn(x[0], x[1]), x[2]) < 0.75f);
+// cc &= (sum rgb < 0.75), every date
+__global__ void __launch_bounds__(256) k_cc_bright(const float* __restrict__ img, int64_t N, unsigned char* __restrict__ cc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* x = img + i * 10;
+  cc[i] = cc[i] && (__fadd_rn(__fadd_rn(x[0], x[1]), x[2]) < 0.75f);
+}
+// clouds = max(clouds_i, clouds_close) where clouds_close is the eroded version outside forest (:1443-1447)
+__global__ void __launch_bounds__(256) k_clouds_join(const unsigned char* __restrict__ ci, const unsigned char* __restrict__ cc,
+                                                     const unsigned char* __restrict__ cc_eroded, const unsigned char* __restrict__ forest,
+                                                     int HW, int64_t N, unsigned char* __restrict__ clouds) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const bool in_forest = forest && forest[i % HW] != 0;
+  clouds[i] = ci[i] | (in_forest ? cc[i] : cc_eroded[i]);
 }
 __global__ void __launch_bounds__(256) k_or(const unsigned char* a, const unsigned char* b, unsigned char* o, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,52 +290,35 @@ __global__ void __launch_bounds__(256) k_or(const unsigned char* a, const unsign
 // ---------------------------------------------------------------------------------------------
 // stage D: brightness z-score clouds (:1458-1481) and whiteness filter (:1484-1492)
 // ---------------------------------------------------------------------------------------------
-// exact k-th order statistics of the positive float32 values selected by (clouds==0 && shadows==0),
-// one block per date, MSB-first radix select on the bit patterns
-__global__ void __launch_bounds__(1024) k_masked_median(const float* __restrict__ img, const unsigned char* __restrict__ clouds,
-                                                        const unsigned char* __restrict__ shadows, int HW, float* __restrict__ med) {
-  const int t = blockIdx.x;
-  __shared__ int hist[256]; __shared__ unsigned prefix; __shared__ int kth; __shared__ int total;
-  __shared__ float found[2];
-  auto value = [&](int p, bool& ok) {
-    ok = !clouds[(int64_t)t * HW + p] && !shadows[(int64_t)t * HW + p];
-    const float* x = img + ((int64_t)t * HW + p) * 10;
-    return __fadd_rn(__fadd_rn(x[0], x[1]), x[2]);
-  };
-  if (threadIdx.x == 0) total = 0;
-  __syncthreads();
-  int local = 0;
-  for (int p = threadIdx.x; p < HW; p += blockDim.x) { bool ok; float v = value(p, ok); if (ok && !isnan(v)) ++local; }
-  atomicAdd(&total, local);
-  __syncthreads();
-  const int n = total;
-  if (n == 0) { if (threadIdx.x == 0) med[t] = nanf(""); return; }
-  for (int which = 0; which < 2; ++which) {
-    if (threadIdx.x == 0) { prefix = 0; kth = (which == 0) ? (n - 1) / 2 : n / 2; }
-    __syncthreads();
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-      __syncthreads();
-      const unsigned pre = prefix;
-      const unsigned mask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
-      for (int p = threadIdx.x; p < HW; p += blockDim.x) {
-        bool ok; float v = value(p, ok);
-        if (!ok || isnan(v)) continue;
-        unsigned u = __float_as_uint(v); u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;   // order-preserving key
-        if ((u & mask) == (pre & mask)) atomicAdd(&hist[(u >> shift) & 255], 1);
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int k = kth, b = 0;
-        while (k >= hist[b]) { k -= hist[b]; ++b; }
-        kth = k; prefix = pre | ((unsigned)b << shift);
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) { unsigned u = prefix; u ^= (u >> 31) ? 0x80000000u : 0xffffffffu; found[which] = __uint_as_float(u); }
-    __syncthreads();
+// np.nanmedian of the brightness (B2 + B3 + B4) over the pixels with clouds == 0 && shadows == 0 of every date: the
+// selected values (others: NaN, which sorts last) go through the GPU-wide radix select of stc_select.cu -- round 1 ran
+// one block per date (24 blocks on 148 SMs, 3.2 ms).
+__global__ void __launch_bounds__(256) k_bright_vals(const float* __restrict__ img, const unsigned char* __restrict__ clouds,
+                                                     const unsigned char* __restrict__ shadows, int HW, float* __restrict__ vals,
+                                                     int* __restrict__ nvalid) {
+  const int t = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false; float v = 0.f;
+  if (p < HW) {
+    const int64_t i = (int64_t)t * HW + p;
+    ok = !clouds[i] && !shadows[i];
+    const float* x = img + i * 10;
+    v = __fadd_rn(__fadd_rn(x[0], x[1]), x[2]);
+    ok = ok && !isnan(v);
+    vals[i] = ok ? v : __uint_as_float(0x7fc00000u);
   }
-  if (threadIdx.x == 0) med[t] = (n & 1) ? found[0] : __fmul_rn(__fadd_rn(found[0], found[1]), 0.5f);
+  const unsigned bal = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(nvalid + t, __popc(bal));
+}
+__global__ void k_median_ks(const int* __restrict__ nvalid, int T, int* __restrict__ ks) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) ks[t * SEL_MAX_COLS] = nvalid[t] > 0 ? (nvalid[t] - 1) / 2 : 0;
+}
+__global__ void k_median_finish(const float* __restrict__ pairs, const int* __restrict__ nvalid, int T, float* __restrict__ med) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int n = nvalid[t];
+  const float a = pairs[(t * SEL_MAX_COLS) * 2], b = pairs[(t * SEL_MAX_COLS) * 2 + 1];
+  med[t] = n == 0 ? nanf("") : (n & 1) ? a : __fmul_rn(__fadd_rn(a, b), 0.5f);
 }
 
 // ---- NumPy-exact float32 mean / std of a masked selection ------------------------------------
@@ -356,44 +329,82 @@ __global__ void __launch_bounds__(1024) k_masked_median(const float* __restrict_
 // combined in recursion order.
 // kind 0: brightness ratio over clouds==0 (or every pixel when all_px[t]); NaN -> 0 and not counted
 // kind 1: 1/blue over clouds==0      kind 2: mean rgb over clouds==0     kind 3: ptp(rgb) over clouds==0
-__global__ void __launch_bounds__(1024) k_compact(const float* __restrict__ img, const unsigned char* __restrict__ clouds,
-                                                  const float* __restrict__ water, const float* __restrict__ medb,
-                                                  const int* __restrict__ all_px, int HW, int kind, float* __restrict__ vals,
-                                                  int* __restrict__ cnts /*[T][2]: slots, valid*/) {
-  const int t = blockIdx.x;
-  __shared__ int wtot[32]; __shared__ int base; __shared__ int nvalid;
-  if (threadIdx.x == 0) { base = 0; nvalid = 0; }
-  __syncthreads();
+// The selection of one date is compacted in row-major order by all SMs: per 1024-pixel chunk the selected / valid counts
+// (k_compact_count), an exclusive scan of the chunk counts per date (k_compact_scan), and the ordered scatter
+// (k_compact_scatter).  Round 1 walked each date with ONE block (24 blocks on 148 SMs, 0.8 ms per call).
+__device__ __forceinline__ bool compact_value(const float* __restrict__ img, const unsigned char* __restrict__ clouds,
+                                              const float* __restrict__ water, const float* __restrict__ medb, bool everything, int HW,
+                                              int kind, int t, int p, float& v, bool& valid) {
+  valid = false; v = 0.f;
+  if (p >= HW) return false;
+  const bool sel = everything || !clouds[(int64_t)t * HW + p];
+  if (!sel) return false;
+  const float* x = img + ((int64_t)t * HW + p) * 10;
+  if (kind == 0) { float r = __fdiv_rn(__fadd_rn(__fadd_rn(x[0], x[1]), x[2]), medb[t]); v = (water[p] > 0.f) ? 1.f : r; }
+  else if (kind == 1) v = __fdiv_rn(1.f, x[0]);
+  else if (kind == 2) v = __fdiv_rn(__fadd_rn(__fadd_rn(x[0], x[1]), x[2]), 3.f);
+  else v = __fsub_rn(fmaxf(fmaxf(x[0], x[1]), x[2]), fminf(fminf(x[0], x[1]), x[2]));
+  valid = true;
+  if (kind == 0 && isnan(v)) { v = 0.f; valid = false; }
+  return true;
+}
+__global__ void __launch_bounds__(1024) k_compact_count(const float* __restrict__ img, const unsigned char* __restrict__ clouds,
+                                                        const float* __restrict__ water, const float* __restrict__ medb,
+                                                        const int* __restrict__ all_px, int HW, int kind, int2* __restrict__ chunk_cnt) {
+  const int t = blockIdx.y, p = blockIdx.x * 1024 + threadIdx.x;
   const bool everything = (kind == 0) && all_px && all_px[t];
+  float v; bool valid;
+  const bool sel = compact_value(img, clouds, water, medb, everything, HW, kind, t, p, v, valid);
+  __shared__ int s_sel, s_val;
+  if (threadIdx.x == 0) { s_sel = 0; s_val = 0; }
+  __syncthreads();
+  const unsigned bal = __ballot_sync(0xffffffffu, sel), balv = __ballot_sync(0xffffffffu, valid);
+  if ((threadIdx.x & 31) == 0) { if (bal) atomicAdd(&s_sel, __popc(bal)); if (balv) atomicAdd(&s_val, __popc(balv)); }
+  __syncthreads();
+  if (threadIdx.x == 0) chunk_cnt[(int64_t)t * gridDim.x + blockIdx.x] = make_int2(s_sel, s_val);
+}
+__global__ void __launch_bounds__(1024) k_compact_scan(const int2* __restrict__ chunk_cnt, int chunks, int* __restrict__ chunk_base,
+                                                       int* __restrict__ cnts /*[T][2]: slots, valid*/) {
+  const int t = blockIdx.x;
+  __shared__ int wtot[32]; __shared__ int carry, vsum;
+  if (threadIdx.x == 0) { carry = 0; vsum = 0; }
+  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int p0 = 0; p0 < HW; p0 += 1024) {
-    const int p = p0 + threadIdx.x;
-    bool sel = false; float v = 0.f; bool valid = false;
-    if (p < HW) {
-      sel = everything || !clouds[(int64_t)t * HW + p];
-      if (sel) {
-        const float* x = img + ((int64_t)t * HW + p) * 10;
-        if (kind == 0) { float r = __fdiv_rn(__fadd_rn(__fadd_rn(x[0], x[1]), x[2]), medb[t]); v = (water[p] > 0.f) ? 1.f : r; }
-        else if (kind == 1) v = __fdiv_rn(1.f, x[0]);
-        else if (kind == 2) v = __fdiv_rn(__fadd_rn(__fadd_rn(x[0], x[1]), x[2]), 3.f);
-        else v = __fsub_rn(fmaxf(fmaxf(x[0], x[1]), x[2]), fminf(fminf(x[0], x[1]), x[2]));
-        valid = true;
-        if (kind == 0 && isnan(v)) { v = 0.f; valid = false; }
-      }
-    }
-    unsigned bal = __ballot_sync(0xffffffffu, sel);
-    unsigned balv = __ballot_sync(0xffffffffu, valid);
-    if (lane == 0) wtot[wid] = __popc(bal);
+  for (int c0 = 0; c0 < chunks; c0 += 1024) {
+    const int c = c0 + threadIdx.x;
+    const int2 v = c < chunks ? chunk_cnt[(int64_t)t * chunks + c] : make_int2(0, 0);
+    int incl = v.x;
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    int vs = v.y;
+    for (int o = 16; o > 0; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
+    if (lane == 31) wtot[wid] = incl;
+    if (lane == 0 && vs) atomicAdd(&vsum, vs);
     __syncthreads();
     int woff = 0;
     for (int w = 0; w < wid; ++w) woff += wtot[w];
-    if (sel) vals[(int64_t)t * HW + base + woff + __popc(bal & ((1u << lane) - 1u))] = v;
-    if (lane == 0 && balv) atomicAdd(&nvalid, __popc(balv));
+    if (c < chunks) chunk_base[(int64_t)t * chunks + c] = carry + woff + incl - v.x;
     __syncthreads();
-    if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 32; ++w) s += wtot[w]; base += s; }
+    if (threadIdx.x == 0) { int sum = 0; for (int w = 0; w < 32; ++w) sum += wtot[w]; carry += sum; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { cnts[2 * t] = base; cnts[2 * t + 1] = nvalid; }
+  if (threadIdx.x == 0) { cnts[2 * t] = carry; cnts[2 * t + 1] = vsum; }
+}
+__global__ void __launch_bounds__(1024) k_compact_scatter(const float* __restrict__ img, const unsigned char* __restrict__ clouds,
+                                                          const float* __restrict__ water, const float* __restrict__ medb,
+                                                          const int* __restrict__ all_px, int HW, int kind,
+                                                          const int* __restrict__ chunk_base, float* __restrict__ vals) {
+  const int t = blockIdx.y, p = blockIdx.x * 1024 + threadIdx.x;
+  const bool everything = (kind == 0) && all_px && all_px[t];
+  float v; bool valid;
+  const bool sel = compact_value(img, clouds, water, medb, everything, HW, kind, t, p, v, valid);
+  __shared__ int wtot[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, sel);
+  if (lane == 0) wtot[wid] = __popc(bal);
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < wid; ++w) woff += wtot[w];
+  if (sel) vals[(int64_t)t * HW + chunk_base[(int64_t)t * gridDim.x + blockIdx.x] + woff + __popc(bal & ((1u << lane) - 1u))] = v;
 }
 
 __device__ __forceinline__ float np_leaf_sum(const float* a, int n, int pass, float mean) {
@@ -644,8 +655,7 @@ static CloudWin cloud_window(int t, int T) {
 // shared with stc_cloudfill.cu: binary dilation / erosion-by-dilation on [frames][H][W] uint8 masks
 void maskop_dilate(stc_ctx* ctx, const unsigned char* in, unsigned char* out, int frames, int H, int W, int k, int conn, int inv_in,
                    int inv_out, int three_d) {
-  { TraceScope ts_(ctx, "k_dilate"); k_dilate<<<cdiv((int64_t)frames * H * W, 256), 256, 0, ctx->stream>>>(in, out, frames, H, W, k, conn, inv_in, inv_out, three_d); }
-  ctx->launches++;
+  morph_dilate_dev(ctx, in, out, frames, H, W, k, conn, inv_in, inv_out, three_d);
 }
 
 #define LAUNCH1D(kern, n, ...) do { TraceScope ts_(ctx, #kern); kern<<<cdiv((n), 256), 256, 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
@@ -653,14 +663,15 @@ void maskop_dilate(stc_ctx* ctx, const unsigned char* in, unsigned char* out, in
 // Device-resident core: img_dev [T,H,W,10] float32, dem_dev [H,W]; clouds_dev [T,H,W] float32, fcps_dev [T,H,W] uint8.
 // Returns with its kernels enqueued on ctx->stream (it synchronises internally where the reference's control flow needs
 // scalars on the host: the adaptive threshold loop, the plausibility tests, the haze flags).
-int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int H, int W, float* clouds_dev, unsigned char* fcps_dev,
+int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int H, int W, const unsigned char* forest_dev,
+                    const unsigned char* urban_core_dev, const unsigned char* urban_near_dev, float* clouds_dev, unsigned char* fcps_dev,
                     uint8_t* stage_host, int stage_id) {
   if (!ctx) return STC_ERR_ARG;
   if (!img || !dem || !clouds_dev || !fcps_dev || T < 1 || T > CT_MAX || H < 3 || W < 3)
     STC_FAIL(STC_ERR_ARG, "cloud_masks: bad argument (1 <= T <= 32)");
   const int HW = H * W; const int64_t N = (int64_t)T * HW;
   Buf d_clm, d_a, d_b, d_c, d_sh, d_cl, d_bc, d_nsr, d_water, d_allref, d_minb4, d_p25, d_minrgb, d_rc, d_thr,
-      d_ci, d_cc, d_cnt, d_win, d_med, d_mom, d_flags, d_all, d_vals, d_leaves, d_leafsum, d_child, d_cnts;
+      d_ci, d_cc, d_cnt, d_win, d_med, d_mom, d_flags, d_all, d_vals, d_leaves, d_leafsum, d_child, d_cnts, d_ccnt, d_cbase;
   for (Buf* b : {&d_clm, &d_a, &d_b, &d_c, &d_sh, &d_cl, &d_bc, &d_nsr}) STC_CUDA(stc_dmalloc(&b->p, N));
   STC_CUDA(stc_dmalloc(&d_water.p, HW * 4)); STC_CUDA(stc_dmalloc(&d_allref.p, HW * 16)); STC_CUDA(stc_dmalloc(&d_minb4.p, HW * 16));
   STC_CUDA(stc_dmalloc(&d_p25.p, HW * 12)); STC_CUDA(stc_dmalloc(&d_minrgb.p, HW * 12)); STC_CUDA(stc_dmalloc(&d_rc.p, HW * 12));
@@ -668,15 +679,16 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   STC_CUDA(stc_dmalloc(&d_cnt.p, 64)); STC_CUDA(stc_dmalloc(&d_win.p, 2 * CT_MAX * 4)); STC_CUDA(stc_dmalloc(&d_med.p, CT_MAX * 4));
   STC_CUDA(stc_dmalloc(&d_mom.p, CT_MAX * 2 * 4)); STC_CUDA(stc_dmalloc(&d_flags.p, 2 * CT_MAX * 4)); STC_CUDA(stc_dmalloc(&d_all.p, CT_MAX * 4));
   const int node_cap = 2 * (HW / 56 + 8) + 2;            // a pairwise leaf holds 58..128 values; a binary tree has < 2 x leaves nodes
+  STC_CUDA(stc_dmalloc(&d_ccnt.p, (size_t)T * cdiv(HW, 1024) * 8)); STC_CUDA(stc_dmalloc(&d_cbase.p, (size_t)T * cdiv(HW, 1024) * 4));
   STC_CUDA(stc_dmalloc(&d_vals.p, N * 4)); STC_CUDA(stc_dmalloc(&d_leaves.p, (size_t)T * node_cap * 8));
   STC_CUDA(stc_dmalloc(&d_leafsum.p, (size_t)T * node_cap * 4)); STC_CUDA(stc_dmalloc(&d_child.p, (size_t)T * node_cap * 4)); STC_CUDA(stc_dmalloc(&d_cnts.p, CT_MAX * 2 * 4));
   unsigned char *clm = (unsigned char*)d_clm.p, *ta = (unsigned char*)d_a.p, *tb = (unsigned char*)d_b.p, *tc = (unsigned char*)d_c.p,
                 *sh = (unsigned char*)d_sh.p, *cl = (unsigned char*)d_cl.p, *bc = (unsigned char*)d_bc.p, *nsr = (unsigned char*)d_nsr.p;
   StaticRefs sr{(float*)d_water.p, (float*)d_allref.p, (float*)d_minb4.p, (float*)d_p25.p, (float*)d_minrgb.p};
   const float* water = sr.water;
+  const unsigned char* forest = forest_dev;            // [HW] 0/1 or nullptr (no forestmask.tif: zeros, :1256-1257)
   auto dilate = [&](const unsigned char* in, unsigned char* out, int64_t frames, int k, int conn, int inv_in, int inv_out, int three_d) {
-    { TraceScope ts_(ctx, "k_dilate"); k_dilate<<<cdiv(frames * HW, 256), 256, 0, ctx->stream>>>(in, out, (int)frames, H, W, k, conn, inv_in, inv_out, three_d); }
-    ctx->launches++;
+    morph_dilate_dev(ctx, in, out, (int)frames, H, W, k, conn, inv_in, inv_out, three_d);
   };
   auto dump = [&](int id, const unsigned char* src) -> int {     // stage taps for the tests
     if (stage_host && stage_id == id) {
@@ -688,7 +700,11 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   // NumPy-exact float32 {mean, std} of f_kind over the clear pixels of every date -> mom_h[t*2..], cnt_h[t*2..]
   std::vector<float> mom_h(2 * CT_MAX); std::vector<int> cnt_h(2 * CT_MAX);
   auto moments = [&](int kind, const float* medb, const int* all_px, bool to_host) -> int {
-    { TraceScope ts_(ctx, "k_compact"); k_compact<<<T, 1024, 0, ctx->stream>>>(img, cl, water, medb, all_px, HW, kind, (float*)d_vals.p, (int*)d_cnts.p); }
+    const int chunks = cdiv(HW, 1024);
+    { TraceScope ts_(ctx, "k_compact_count"); k_compact_count<<<dim3(chunks, T), 1024, 0, ctx->stream>>>(img, cl, water, medb, all_px, HW, kind, (int2*)d_ccnt.p); }
+    { TraceScope ts_(ctx, "k_compact_scan"); k_compact_scan<<<T, 1024, 0, ctx->stream>>>((const int2*)d_ccnt.p, chunks, (int*)d_cbase.p, (int*)d_cnts.p); }
+    { TraceScope ts_(ctx, "k_compact_scatter"); k_compact_scatter<<<dim3(chunks, T), 1024, 0, ctx->stream>>>(img, cl, water, medb, all_px, HW, kind, (const int*)d_cbase.p, (float*)d_vals.p); }
+    ctx->launches += 2;
     { TraceScope ts_(ctx, "k_np_moments"); k_np_moments<<<T, 1024, 0, ctx->stream>>>((const float*)d_vals.p, (const int*)d_cnts.p, HW, node_cap, (int2*)d_leaves.p,
                                               (int*)d_child.p, (float*)d_leafsum.p, (float*)d_mom.p); }
     ctx->launches += 2;
@@ -722,39 +738,65 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
     dilate(tb, tc, T, 3, 1, 0, 0, 0);
     STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
     { TraceScope ts_(ctx, "k_count_dates"); k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tc, HW, (int*)d_all.p); } ctx->launches++;
-    LAUNCH1D(k_edt_grow, N, tc, sh, T, H, W, 5, (const int*)d_all.p);
+    if ((rc_ = morph_edt_grow_dev(ctx, tc, sh, T, H, W, 5, (const int*)d_all.p))) return rc_;
     if ((rc_ = dump(3, sh))) return rc_;
   }
 
-  // ---- C: clouds ----
-  for (int t = 0; t < T; ++t) {
-    CloudWin w = cloud_window(t, T);
-    { TraceScope ts_(ctx, "k_cloud_refs"); k_cloud_refs<<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, sh, sr, T, HW, t, w, (float*)d_rc.p, (float*)d_thr.p, (unsigned char*)d_ci.p); }
+  // ---- C: clouds, all dates per launch; the adaptive threshold loop (:1425-1440) advances every still-active date per round ----
+  {
+    Buf d_rcall, d_thrall, d_ciall, d_ccall, d_cnti, d_cntc;
+    STC_CUDA(stc_dmalloc(&d_rcall.p, N * 12)); STC_CUDA(stc_dmalloc(&d_thrall.p, N * 4)); STC_CUDA(stc_dmalloc(&d_ciall.p, N));
+    STC_CUDA(stc_dmalloc(&d_ccall.p, N)); STC_CUDA(stc_dmalloc(&d_cnti.p, CT_MAX * 4)); STC_CUDA(stc_dmalloc(&d_cntc.p, CT_MAX * 4));
+    CloudWinAll wins; memset(&wins, 0, sizeof(wins));
+    for (int t = 0; t < T; ++t) wins.w[t] = cloud_window(t, T);
+    STC_CUDA(cudaMemsetAsync(d_cnti.p, 0, CT_MAX * 4, ctx->stream));
+    { TraceScope ts_(ctx, "k_cloud_refs"); k_cloud_refs<<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, sh, sr, forest, T, HW, wins, (float*)d_rcall.p, (float*)d_thrall.p,
+                                                                    (unsigned char*)d_ciall.p, (int*)d_cnti.p); }
     ctx->launches++;
-    int cnt[2] = {0, 0};
-    STC_CUDA(cudaMemsetAsync(d_cnt.p, 0, 8, ctx->stream));
-    LAUNCH1D(k_count, HW, (const unsigned char*)d_ci.p, HW, (int*)d_cnt.p);
-    double mean_i = 0.0, mean_c = 1.0, mod = 0.0;
-    bool first = true;
-    while ((mean_c - mean_i) > 0.075) {
-      STC_CUDA(cudaMemsetAsync((int*)d_cnt.p + 1, 0, 4, ctx->stream));
-      LAUNCH1D(k_cloud_close, HW, img, HW, t, (const float*)d_rc.p, (const float*)d_thr.p, (float)mod, (unsigned char*)d_cc.p, (int*)d_cnt.p + 1);
-      STC_CUDA(cudaMemcpyAsync(cnt, d_cnt.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    int cnt_i[CT_MAX], cnt_c[CT_MAX];
+    STC_CUDA(cudaMemcpyAsync(cnt_i, d_cnti.p, T * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CloseMods cm; memset(&cm, 0, sizeof(cm));
+    double mod[CT_MAX];
+    for (int t = 0; t < T; ++t) { cm.active[t] = 1; mod[t] = 0.0; }
+    bool any = true;
+    while (any) {
+      for (int t = 0; t < T; ++t) cm.mod[t] = (float)mod[t];
+      STC_CUDA(cudaMemsetAsync(d_cntc.p, 0, CT_MAX * 4, ctx->stream));
+      { TraceScope ts_(ctx, "k_cloud_close"); k_cloud_close<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(img, HW, (const float*)d_rcall.p, (const float*)d_thrall.p, cm,
+                                                                                  (unsigned char*)d_ccall.p, (int*)d_cntc.p); }
+      ctx->launches++;
+      STC_CUDA(cudaMemcpyAsync(cnt_c, d_cntc.p, T * 4, cudaMemcpyDeviceToHost, ctx->stream));
       STC_CUDA(cudaStreamSynchronize(ctx->stream));
-      mean_i = (double)cnt[0] / HW; mean_c = (double)cnt[1] / HW;
-      mod += 0.0025; first = false;
-      if (mod > 10.0) STC_FAIL(STC_ERR_STATE, "cloud_masks: threshold loop did not converge");
+      any = false;
+      for (int t = 0; t < T; ++t) {
+        if (!cm.active[t]) continue;
+        const double mean_i = (double)cnt_i[t] / HW, mean_c = (double)cnt_c[t] / HW;
+        mod[t] += 0.0025;
+        if (!((mean_c - mean_i) > 0.075)) cm.active[t] = 0; else any = true;
+        if (mod[t] > 10.0) STC_FAIL(STC_ERR_STATE, "cloud_masks: threshold loop did not converge");
+      }
     }
-    (void)first;
-    LAUNCH1D(k_cc_bright, HW, img, HW, t, (unsigned char*)d_cc.p);
-    dilate((const unsigned char*)d_cc.p, ta, 1, 2, 1, 1, 1, 0);                 // erode 2 (forest mask == 0 everywhere)
-    LAUNCH1D(k_or, HW, (const unsigned char*)d_ci.p, ta, cl + (int64_t)t * HW, (int64_t)HW);
+    LAUNCH1D(k_cc_bright, N, img, N, (unsigned char*)d_ccall.p);
+    dilate((const unsigned char*)d_ccall.p, ta, T, 2, 1, 1, 1, 0);              // erode 2 (applies outside forest)
+    LAUNCH1D(k_clouds_join, N, (const unsigned char*)d_ciall.p, (const unsigned char*)d_ccall.p, ta, forest, HW, N, cl);
   }
   if ((rc_ = dump(4, cl))) return rc_;
 
   // ---- D: brightness z-score + whiteness ----
   {
-    { TraceScope ts_(ctx, "k_masked_median"); k_masked_median<<<T, 1024, 0, ctx->stream>>>(img, cl, sh, HW, (float*)d_med.p); } ctx->launches++;
+    {
+      Buf d_nv, d_ks, d_pairs;
+      STC_CUDA(stc_dmalloc(&d_nv.p, CT_MAX * 4)); STC_CUDA(stc_dmalloc(&d_ks.p, (size_t)T * SEL_MAX_COLS * 4)); STC_CUDA(stc_dmalloc(&d_pairs.p, (size_t)T * SEL_MAX_COLS * 8));
+      STC_CUDA(cudaMemsetAsync(d_nv.p, 0, CT_MAX * 4, ctx->stream));
+      STC_CUDA(cudaMemsetAsync(d_ks.p, 0, (size_t)T * SEL_MAX_COLS * 4, ctx->stream));
+      { TraceScope ts_(ctx, "k_bright_vals"); k_bright_vals<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(img, cl, sh, HW, (float*)d_vals.p, (int*)d_nv.p); }
+      k_median_ks<<<1, 32, 0, ctx->stream>>>((const int*)d_nv.p, T, (int*)d_ks.p);
+      std::vector<SelJob> jobs(T);
+      for (int t = 0; t < T; ++t) jobs[t] = SelJob{(const float*)d_vals.p + (int64_t)t * HW, HW, 1, 1};
+      if ((rc_ = select_ranks_dev(ctx, jobs.data(), T, (const int*)d_ks.p, (float*)d_pairs.p))) return rc_;
+      k_median_finish<<<1, 32, 0, ctx->stream>>>((const float*)d_pairs.p, (const int*)d_nv.p, T, (float*)d_med.p);
+      ctx->launches += 3;
+    }
     // `if np.sum(clouds[i] < 0.90)`: select clear pixels when any exists, else every pixel
     int allpx[CT_MAX];
     STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
@@ -794,7 +836,7 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   LAUNCH1D(k_or, N, cl, ta, tb, N);
   STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
   { TraceScope ts_(ctx, "k_count_dates"); k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tb, HW, (int*)d_all.p); } ctx->launches++;
-  LAUNCH1D(k_edt_grow, N, tb, cl, T, H, W, 3, (const int*)d_all.p);
+  if ((rc_ = morph_edt_grow_dev(ctx, tb, cl, T, H, W, 3, (const int*)d_all.p))) return rc_;
   if ((rc_ = dump(7, cl))) return rc_;
 
   // ---- G: shadow plausibility (:1617-1626), per date on scalar means ----
@@ -808,12 +850,8 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
     // np.mean of a float32 0/1 array: exact for these sizes
     float ms = (float)((double)c2[0] / HW), mc = (float)((double)c2[1] / HW);
     auto restrict_far = [&]() -> int {
-      const unsigned char* src = cl + (int64_t)t * HW; unsigned char* dst = ta;
-      for (int it = 0; it < 5; ++it) {                                          // 50 cross iterations = 5 x L1 radius 10
-        dilate(src, dst, 1, 10, 1, 0, 0, 0);
-        src = dst; dst = (dst == ta) ? tb : ta;
-      }
-      LAUNCH1D(k_and_or_dem, HW, sh + (int64_t)t * HW, src, dem, HW);
+      dilate(cl + (int64_t)t * HW, ta, 1, 50, 1, 0, 0, 0);                      // 50 cross iterations = L1 radius 50
+      LAUNCH1D(k_and_or_dem, HW, sh + (int64_t)t * HW, ta, dem, HW);
       return STC_OK;
     };
     if (ms > (mc + 0.3f) && mc < 0.3f) restrict_far();
@@ -880,11 +918,42 @@ extern "C" int stc_cloud_masks_host(stc_ctx* ctx, const float* img_host, const f
   STC_CUDA(stc_dmalloc(&d_out.p, N * 4)); STC_CUDA(stc_dmalloc(&d_fcps.p, N));
   STC_CUDA(cudaMemcpyAsync(d_img.p, img_host, N * 40, cudaMemcpyHostToDevice, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(d_dem.p, dem_host, (size_t)H * W * 4, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = cloud_masks_dev(ctx, (const float*)d_img.p, (const float*)d_dem.p, T, H, W, (float*)d_out.p, (unsigned char*)d_fcps.p,
+  const bool anc = ctx->anc_H == H && ctx->anc_W == W;
+  int rc = cloud_masks_dev(ctx, (const float*)d_img.p, (const float*)d_dem.p, T, H, W, anc ? ctx->anc_forest : nullptr,
+                           anc ? ctx->anc_urban_core : nullptr, anc ? ctx->anc_urban_near : nullptr, (float*)d_out.p, (unsigned char*)d_fcps.p,
                            stage_host, stage_id);
   if (rc) return rc;
   STC_CUDA(cudaMemcpyAsync(fcps_host, d_fcps.p, N, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaMemcpyAsync(clouds_host, d_out.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return STC_OK;
+}
+
+
+// Ancillary rasters for the masks of the tile that follows (cloud_removal.py:1131-1135 `urbanmask.tif`, :1254-1257
+// `forestmask.tif`): the caller reads the raster windows (I/O) and passes them at tile resolution -- forest [H,W] 0/1 =
+// adjust_cloudmask_in_forests(...), urban_core / urban_near [H,W] 0/1 = the two resized rasters of mask_nonurban_areas
+// (:745-753: dilated once, dilated five more times).  NULL pointers clear a mask; masks stay set until replaced and are
+// used by stc_cloud_masks_host / stc_tile_run_host calls whose H, W match.
+extern "C" int stc_set_ancillary_masks_host(stc_ctx* ctx, const uint8_t* forest_host, const uint8_t* urban_core_host,
+                                            const uint8_t* urban_near_host, int H, int W) {
+  if (!ctx) return STC_ERR_ARG;
+  if ((!urban_core_host) != (!urban_near_host)) STC_FAIL(STC_ERR_ARG, "ancillary masks: urban_core and urban_near come together");
+  if ((forest_host || urban_core_host) && (H < 3 || W < 3)) STC_FAIL(STC_ERR_ARG, "ancillary masks: bad shape");
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (unsigned char** p : {&ctx->anc_forest, &ctx->anc_urban_core, &ctx->anc_urban_near}) { if (*p) { cudaFree(*p); *p = nullptr; } }
+  ctx->anc_H = ctx->anc_W = 0;
+  if (!forest_host && !urban_core_host) return STC_OK;
+  const size_t HW = (size_t)H * W;
+  auto up = [&](const uint8_t* src, unsigned char** dst) -> int {
+    if (!src) return STC_OK;
+    STC_CUDA(cudaMalloc((void**)dst, HW));
+    STC_CUDA(cudaMemcpyAsync(*dst, src, HW, cudaMemcpyHostToDevice, ctx->stream));
+    return STC_OK;
+  };
+  int rc;
+  if ((rc = up(forest_host, &ctx->anc_forest)) || (rc = up(urban_core_host, &ctx->anc_urban_core)) || (rc = up(urban_near_host, &ctx->anc_urban_near))) return rc;
+  STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->anc_H = H; ctx->anc_W = W;
   return STC_OK;
 }

@@ -17,7 +17,12 @@
 // LAPACK/BLAS: filled pixels agree to ~1e-6 relative (tests/test_cloud_fill.py: rtol 1e-4).
 #include "stc_common.cuh"
 #include "stc_select.cuh"
+#include "stc_pyrandom.h"
 #include <chrono>
+#include <atomic>
+#include <thread>
+#include <memory>
+#include <sched.h>
 #include <cstdio>
 #include <algorithm>
 #include <cmath>
@@ -113,28 +118,55 @@ __global__ void __launch_bounds__(128) k_mosaic_ref(const float* __restrict__ ti
 
 // order-preserving compaction positions of a flag image: pos[p] = rank of p among flagged pixels; total -> *count
 // (single block; HW <= a few 100k)
-__global__ void __launch_bounds__(1024) k_scan_flags(const unsigned char* __restrict__ flag_all, int HW, int* __restrict__ pos_all,
-                                                     int* __restrict__ count) {
-  __shared__ int wtot[32]; __shared__ int base;
-  const unsigned char* flag = flag_all + (int64_t)blockIdx.x * HW;       // one block per flag image
-  int* pos = pos_all + (int64_t)blockIdx.x * HW;
-  if (threadIdx.x == 0) base = 0;
+// Three GPU-wide passes: flags per 1024-pixel chunk counted, chunk counts scanned per image, positions written (round 1
+// walked every image with one block: 0.33 ms per call on 12-24 of 148 SMs).
+__global__ void __launch_bounds__(1024) k_flag_chunk_count(const unsigned char* __restrict__ flag_all, int HW, int* __restrict__ chunk_cnt) {
+  const int p = blockIdx.x * 1024 + threadIdx.x;
+  const bool f = p < HW && flag_all[(int64_t)blockIdx.y * HW + p];
+  __shared__ int tot;
+  if (threadIdx.x == 0) tot = 0;
+  __syncthreads();
+  const unsigned bal = __ballot_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&tot, __popc(bal));
+  __syncthreads();
+  if (threadIdx.x == 0) chunk_cnt[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(1024) k_flag_chunk_scan(int* __restrict__ chunk_cnt /* in: counts, out: exclusive bases */, int chunks,
+                                                          int* __restrict__ count) {
+  int* c = chunk_cnt + (int64_t)blockIdx.x * chunks;
+  __shared__ int wtot[32]; __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int p0 = 0; p0 < HW; p0 += 1024) {
-    const int p = p0 + threadIdx.x;
-    const bool f = p < HW && flag[p];
-    unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) wtot[wid] = __popc(bal);
+  for (int c0 = 0; c0 < chunks; c0 += 1024) {
+    const int i = c0 + threadIdx.x;
+    const int v = i < chunks ? c[i] : 0;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) wtot[wid] = incl;
     __syncthreads();
     int woff = 0;
     for (int w = 0; w < wid; ++w) woff += wtot[w];
-    if (p < HW) pos[p] = f ? base + woff + __popc(bal & ((1u << lane) - 1u)) : -1;
+    if (i < chunks) c[i] = carry + woff + incl - v;
     __syncthreads();
-    if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 32; ++w) s += wtot[w]; base += s; }
+    if (threadIdx.x == 0) { int sum = 0; for (int w = 0; w < 32; ++w) sum += wtot[w]; carry += sum; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) count[blockIdx.x] = base;
+  if (threadIdx.x == 0) count[blockIdx.x] = carry;
+}
+__global__ void __launch_bounds__(1024) k_flag_positions(const unsigned char* __restrict__ flag_all, int HW, const int* __restrict__ chunk_base,
+                                                         int* __restrict__ pos_all) {
+  const int p = blockIdx.x * 1024 + threadIdx.x;
+  const bool f = p < HW && flag_all[(int64_t)blockIdx.y * HW + p];
+  __shared__ int wtot[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) wtot[wid] = __popc(bal);
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < wid; ++w) woff += wtot[w];
+  if (p < HW)
+    pos_all[(int64_t)blockIdx.y * HW + p] = f ? chunk_base[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] + woff + __popc(bal & ((1u << lane) - 1u)) : -1;
 }
 
 // gather the flagged rows of date i = i0 + blockIdx.y and of its reference image into per-date slabs:
@@ -585,79 +617,6 @@ __global__ void __launch_bounds__(256) k_add_clip(float* __restrict__ areas, con
   areas[i] = v > 1.f ? 1.f : v;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Python's random.shuffle on the MT19937 state handed over by the caller (CPython Lib/random.py:
-// shuffle -> _randbelow_with_getrandbits -> getrandbits(k) = genrand_uint32() >> (32 - k))
-// ---------------------------------------------------------------------------------------------
-struct PyRandom {
-  // CPython's MT19937 (Modules/_randommodule.c): `mt` is the untempered state Python exports with getstate(), `idx` its
-  // position.  The replay of random.shuffle over ~1e6-element index lists per date is the one long host loop of
-  // remove_clouds, so a whole block of 624 outputs is regenerated and tempered at once (three modulo-free loops the
-  // compiler vectorises) and next() only reads the buffer.
-  uint32_t mt[624]; int idx;
-  uint32_t out[624]; bool out_valid = false;
-  static inline uint32_t twist(uint32_t u, uint32_t v, uint32_t m) {
-    const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
-    return m ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
-  }
-  void temper_all() {
-    for (int k = 0; k < 624; ++k) {
-      uint32_t y = mt[k];
-      y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
-      out[k] = y;
-    }
-    out_valid = true;
-  }
-  void regen() {
-    for (int k = 0; k < 227; ++k) mt[k] = twist(mt[k], mt[k + 1], mt[k + 397]);
-    for (int k = 227; k < 623; ++k) mt[k] = twist(mt[k], mt[k + 1], mt[k - 227]);
-    mt[623] = twist(mt[623], mt[0], mt[396]);
-    temper_all();
-    idx = 0;
-  }
-  inline uint32_t next() {
-    if (idx >= 624) regen();
-    else if (!out_valid) temper_all();
-    return out[idx++];
-  }
-  inline uint32_t randbelow(uint32_t n) {
-    const int sh = __builtin_clz(n);     // 32 - n.bit_length(), n >= 1
-    uint32_t r;
-    do { r = next() >> sh; } while (r >= n);
-    return r;
-  }
-  // random.shuffle: for i = len-1 .. 1: j = _randbelow(i + 1); x[i], x[j] = x[j], x[i].  _randbelow_with_getrandbits
-  // draws k = (i+1).bit_length() bits until the value is <= i, i.e. EVERY draw consumes one generator output and a
-  // rejected draw changes nothing.  The loop below therefore advances one output per iteration and turns the accept test
-  // into arithmetic (a rejected draw swaps x[i] with itself and leaves i alone): no unpredictable branch, ~3x faster than
-  // the textbook rejection loop (the accept rate is 50-100 %).  All i of one power-of-two band share the shift.
-  void shuffle(std::vector<int>& x) { shuffle(x.data(), x.size()); }
-  void shuffle(int* v, size_t len) {
-    size_t i = len;
-    if (i < 2) return;
-    --i;                                   // i = len - 1
-    while (i >= 1) {
-      const int sh = __builtin_clz((uint32_t)i + 1u);
-      const size_t band_lo = (sh == 31) ? 1 : ((size_t)1 << (31 - sh));     // smallest i with the same bit length of i + 1 ... (i+1 >= 2^(31-sh))
-      const size_t lo = band_lo > 1 ? band_lo - 1 : 1;                       // i + 1 >= band_lo  <=>  i >= band_lo - 1
-      while (i >= lo) {
-        if (idx >= 624) regen(); else if (!out_valid) temper_all();
-        int avail = 624 - idx;
-        const uint32_t* o = out + idx;
-        int used = 0;
-        while (used < avail && i >= lo) {
-          const uint32_t r = o[used++] >> sh;
-          const bool ok = r <= (uint32_t)i;
-          const size_t j = ok ? (size_t)r : i;
-          const int t = v[i]; v[i] = v[j]; v[j] = t;
-          i -= ok;
-        }
-        idx += used;
-      }
-    }
-  }
-};
-
 }  // namespace
 
 namespace {
@@ -671,12 +630,32 @@ __global__ void __launch_bounds__(256) k_count_zero(const unsigned char* __restr
 #define CF_LAUNCH(kern, grid, block, ...) do { TraceScope ts_(ctx, #kern); kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
 #define CF_SYNC() STC_CUDA(cudaStreamSynchronize(ctx->stream))
 
+// pos[img][p] = rank of pixel p among the flagged pixels of image img (row-major), -1 when not flagged; count[img] = flagged pixels
+static int scan_flags_dev(stc_ctx* ctx, const unsigned char* flags, int nimg, int HW, int* pos, int* count) {
+  const int chunks = cdiv(HW, 1024);
+  PoolBuf cc;
+  STC_CUDA(cc.alloc((size_t)nimg * chunks * 4));
+  CF_LAUNCH(k_flag_chunk_count, dim3(chunks, nimg), 1024, flags, HW, cc.as<int>());
+  CF_LAUNCH(k_flag_chunk_scan, nimg, 1024, cc.as<int>(), chunks, count);
+  CF_LAUNCH(k_flag_positions, dim3(chunks, nimg), 1024, flags, HW, cc.as<int>(), pos);
+  return STC_OK;
+}
+
 namespace {
 __global__ void __launch_bounds__(256) k_clip01(float* __restrict__ x, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const float v = x[i]; x[i] = isnan(v) ? v : fminf(fmaxf(v, 0.f), 1.f); }     // np.clip keeps NaN
 }
 }  // namespace
+
+// worker threads for the shuffle replay: STC_HOST_THREADS, else a quarter of the cores this process may run on (2..8)
+static int host_threads() {
+  if (const char* e = getenv("STC_HOST_THREADS")) { const int v = atoi(e); if (v >= 1) return std::min(v, 64); }
+  cpu_set_t set; CPU_ZERO(&set);
+  int n = 4;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set) / 4;
+  return std::max(2, std::min(n, 8));
+}
 
 // Device-resident core: tiles [n,H,W,10] float32 (blended in place), probs [n,H,W] float32, pfcps [>= H*W] uint8 (date 0 is read),
 // areas [n,H,W] float32 out, mosaic_out [H,W,10] optional -- all device pointers; mt_state / to_remove / clipped_out on the host.
@@ -747,6 +726,188 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   if ((rc = pre_feather_dev(ctx, probs_dev, n, H, W, 20, d_ta.as<float>(), d_tb.as<float>(), d_sums.as<float>(), areas))) return rc;
 
   cf_mark("feather");
+  // ---- state of the per-date fits (phase 3), declared here because phase 3a may run inside the mosaic phase (see below) ----
+  struct FitJob { int d, lo, hi, K; int64_t row0; int cnt[7]; int64_t list0[7]; };
+  struct ShufTask { int j; int k; uint32_t mt[624]; int idx; };            // k in 0..6: list k; k == 7: the sample
+  std::vector<int> counts(n * 5);
+  PyRandom rng; rng.import_state(mt_state, (int)mt_state[624]);
+  std::vector<FitJob> fits;
+  std::vector<int> fit_of(n, -1);
+  int64_t total_rows = 0;
+  int nf = 0;
+  DBuf d_rows_all, d_evi_all, d_lab_all, d_fqout, d_fcnt, d_lists, d_bjobs, d_sample_all, d_status_all, d_flag3, d_pos3, d_K3;
+  int* pin_lists = nullptr; int* pin_samples = nullptr;
+  std::vector<int64_t> sample0;
+  std::vector<ShufTask> tasks;
+  std::atomic<size_t> published{0};
+  std::vector<size_t> S_of;
+  double tt0 = 0, t_skip = 0;
+  long long n_draw = 0;
+  std::unique_ptr<std::atomic<int>[]> lists_done, sample_done;
+  std::atomic<size_t> next_task{0};
+  std::vector<std::thread> pool;
+  const int nthreads = host_threads();
+  struct Joiner { std::vector<std::thread>& p; ~Joiner() { for (auto& t : p) if (t.joinable()) t.join(); } } joiner{pool};
+  bool fits_ready = false;
+  // Phase 3a + the host-side shuffle replay.  Nothing here depends on the mosaic VALUES: the fit rows are the clear land
+  // pixels (weights == 0, never blended), their EVI comes from the untouched cube.  It does depend on the weights, which
+  // the mosaic phase changes only when a date has <= 1000 usable pixels (:679-680).  So when the first pass over the
+  // dates shows that no date is in that case, this runs INSIDE the mosaic phase and the generator walk + the shuffles
+  // (10-20 ms of host work) overlap the mosaic kernels; otherwise it runs after the mosaic, as the reference orders it.
+  auto prepare_fits = [&]() -> int {
+    STC_CUDA(stc_dmalloc(&d_flag3.p, (size_t)n * HW)); STC_CUDA(stc_dmalloc(&d_pos3.p, (size_t)n * HW * 4)); STC_CUDA(stc_dmalloc(&d_K3.p, CF_MAX_DATES * 4));
+    CF_LAUNCH(k_water_of_median, cdiv(HW, 128), 128, tiles, n, HW, water1);
+    STC_CUDA(cudaMemsetAsync(d_counts.p, 0, CF_MAX_DATES * 5 * 4, ctx->stream));
+    CF_LAUNCH(k_area_counts, dim3(cdiv(HW, 256), n), 256, areas, water1, HW, d_counts.as<int>());
+    CF_LAUNCH(k_flag_clear_land, dim3(cdiv(HW, 256), n), 256, areas, water1, HW, d_flag3.as<unsigned char>());
+    if ((rc = scan_flags_dev(ctx, d_flag3.as<unsigned char>(), n, HW, d_pos3.as<int>(), d_K3.as<int>()))) return rc;
+    STC_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, n * 20, cudaMemcpyDeviceToHost, ctx->stream));
+    CF_SYNC();
+    // ---- 3a. everything about the per-date fits that does NOT depend on the blending of earlier dates, for all dates at once:
+    //      the clear-land rows of a date's window [lo, hi) (weights == 0: the blend never touches them), their EVI, the six EVI
+    //      percentiles, the stratum bits and the seven ordered index lists (:421-471).  One synchronisation for the stratum
+    //      sizes, one for the lists; the lists land in pinned host memory.
+    for (int d = 0; d < n; ++d) {
+      const int c_pos = counts[d * 5], c_zero = counts[d * 5 + 1], c_lt1 = counts[d * 5 + 2], c_one = counts[d * 5 + 3];
+      to_remove_host[d] = (c_one == HW);
+      if (!(c_pos > 0 && c_zero > 0)) continue;
+      if (!((double)c_lt1 / (double)HW > 0.01))
+        STC_FAIL(STC_ERR_STATE, "remove_clouds: date with <= 1% non-saturated pixels -- the reference raises UnboundLocalError here (cloud_removal.py:575)");
+      FitJob f; f.d = d;
+      if (c_zero > 40000) { f.lo = d; f.hi = d + 1; }
+      else { f.lo = (d == n - 1) ? std::max(d - 2, 0) : std::max(d - 1, 0); f.hi = std::min(d + 2, n); }
+      f.K = 0;
+      for (int t = f.lo; t < f.hi; ++t) f.K += counts[t * 5 + 4];
+      if (f.K < 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: no clear land pixel to fit on -- the reference fails in np.percentile here");
+      f.row0 = total_rows; total_rows += f.K;
+      fit_of[d] = (int)fits.size(); fits.push_back(f);
+    }
+    nf = (int)fits.size();
+    if (nf > 0) {
+      STC_CUDA(stc_dmalloc(&d_rows_all.p, (size_t)total_rows * 4)); STC_CUDA(stc_dmalloc(&d_evi_all.p, (size_t)total_rows * 4));
+      STC_CUDA(stc_dmalloc(&d_lab_all.p, (size_t)total_rows));
+      STC_CUDA(stc_dmalloc(&d_fqout.p, (size_t)nf * 6 * 4)); STC_CUDA(stc_dmalloc(&d_fcnt.p, (size_t)nf * 7 * 4));
+      STC_CUDA(stc_dmalloc(&d_status_all.p, (size_t)nf * 10 * 4));
+      std::vector<SelJob> jobs; std::vector<QSpec> specs;
+      const double qs[6] = {2 / 100.0, 20 / 100.0, 40 / 100.0, 60 / 100.0, 80 / 100.0, 98 / 100.0};
+      for (const FitJob& f : fits) {
+        int K = 0;
+        for (int t = f.lo; t < f.hi; ++t) {
+          CF_LAUNCH(k_collect_rows, cdiv(HW, 256), 256, tiles, d_pos3.as<int>() + (int64_t)t * HW, HW, t, (int)(f.row0 + K), d_rows_all.as<int>(), d_evi_all.as<float>());
+          K += counts[t * 5 + 4];
+        }
+        for (int k = 0; k < 6; ++k) {
+          jobs.push_back(SelJob{d_evi_all.as<float>() + f.row0, f.K, 1, 1});
+          specs.push_back(QSpec{(int)(jobs.size() - 1) * SEL_MAX_COLS, f.K, qs[k], 0});
+        }
+      }
+      if ((rc = run_select(jobs, specs, d_fqout.as<float>()))) return rc;
+      STC_CUDA(cudaMemsetAsync(d_fcnt.p, 0, (size_t)nf * 7 * 4, ctx->stream));
+      for (int j = 0; j < nf; ++j)
+        CF_LAUNCH(k_strata, cdiv(fits[j].K, 256), 256, d_evi_all.as<float>() + fits[j].row0, d_fqout.as<float>() + 6 * j, fits[j].K,
+                  d_lab_all.as<unsigned char>() + fits[j].row0, d_fcnt.as<int>() + 7 * j);
+      std::vector<int> h_cnt((size_t)nf * 7);
+      STC_CUDA(cudaMemcpyAsync(h_cnt.data(), d_fcnt.p, (size_t)nf * 7 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CF_SYNC();
+      int64_t total_list = 0;
+      const int rep[7] = {10, 1, 1, 1, 1, 1, 10};
+      for (int j = 0; j < nf; ++j)
+        for (int k = 0; k < 7; ++k) { fits[j].cnt[k] = h_cnt[(size_t)j * 7 + k] * rep[k]; fits[j].list0[k] = total_list; total_list += fits[j].cnt[k]; }
+      for (const FitJob& f : fits)
+        for (int k = 1; k <= 5; ++k)                          // p2 / p98 go through np.repeat first, which accepts a 0-d array
+          if (f.cnt[k] == 1)
+            STC_FAIL(STC_ERR_STATE, "remove_clouds: single-element EVI stratum -- the reference raises TypeError (shuffle of a 0-d array)");
+      STC_CUDA(stc_dmalloc(&d_lists.p, (size_t)std::max<int64_t>(total_list, 1) * 4)); STC_CUDA(stc_dmalloc(&d_bjobs.p, (size_t)nf * sizeof(BucketJob)));
+      std::vector<BucketJob> bj(nf);
+      for (int j = 0; j < nf; ++j) {
+        bj[j].lab = d_lab_all.as<unsigned char>() + fits[j].row0; bj[j].K = fits[j].K;
+        for (int k = 0; k < 7; ++k) bj[j].out[k] = d_lists.as<int>() + fits[j].list0[k];
+      }
+      STC_CUDA(cudaMemcpyAsync(d_bjobs.p, bj.data(), (size_t)nf * sizeof(BucketJob), cudaMemcpyHostToDevice, ctx->stream));
+      CF_LAUNCH(k_bucket_lists, dim3(7, nf), 1024, d_bjobs.as<BucketJob>());
+      // pinned host scratch: the lists, then (behind them) one sample slot per date
+      int64_t sample_cap = 0;
+      sample0.assign(nf, 0);
+      for (int j = 0; j < nf; ++j) {
+        const int64_t n_i = std::min(90000, fits[j].K) / 5;
+        int64_t cap = (int64_t)fits[j].cnt[0] + fits[j].cnt[6];
+        for (int k = 1; k <= 5; ++k) cap += std::min<int64_t>(n_i, fits[j].cnt[k]);
+        sample0[j] = sample_cap; sample_cap += cap;
+      }
+      pin_lists = (int*)ctx_pinned(ctx, (size_t)(total_list + sample_cap + 16) * 4);
+      if (!pin_lists) STC_FAIL(STC_ERR_NOMEM, "remove_clouds: pinned host scratch");
+      STC_CUDA(stc_dmalloc(&d_sample_all.p, (size_t)std::max<int64_t>(sample_cap, 1) * 4));
+      STC_CUDA(cudaMemcpyAsync(pin_lists, d_lists.p, (size_t)total_list * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CF_SYNC();                                             // bj is a host vector; the lists are on the host now
+      cf_mark("fit rows, strata, index lists (all dates)");
+      // ---- 3b. in date order: Python's random.shuffle replayed on the host for date d while the device still works on date
+      //      d - 1 (launches are asynchronous; nothing below synchronises), then Gram sums, NNLS and the blend of date d.
+      pin_samples = pin_lists + total_list;
+      // Python's random.shuffle, replayed on the host: 8 shuffles per date (:472-496) whose swaps are dependent random
+      // memory accesses (~3.5 ns per element, ~0.5 M elements per date).  The generator is first walked through all of
+      // them WITHOUT data (skip_shuffle) to record the state each one starts from; the shuffles themselves then run on
+      // worker threads (they touch disjoint lists; a date's sample shuffle waits for its seven list shuffles), and the
+      // device work of date d is enqueued as soon as that date's sample is ready.
+      tasks.resize((size_t)nf * 8);
+      S_of.assign(nf, 0);
+      for (int j = 0; j < nf; ++j) {
+        const FitJob& f = fits[j];
+        const size_t n_i = (size_t)(std::min(90000, f.K) / 5);
+        size_t S = (size_t)f.cnt[0] + (size_t)f.cnt[6];
+        for (int k = 1; k <= 5; ++k) S += std::min(n_i, (size_t)f.cnt[k]);
+        S_of[j] = S;
+      }
+      tt0 = cf_timing ? cf_now() : 0;
+      auto walker = [&, this_n = n]() {
+        size_t ti = 0;
+        for (int d = 0; d < n; ++d) {
+          const int j = fit_of[d];
+          if (j < 0) continue;
+          const FitJob& f = fits[j];
+          const int order[8] = {0, 6, 1, 2, 3, 4, 5, 7};                        // :472-478 shuffle order p2, p98, p20 ... p100, then the sample
+          for (int q = 0; q < 8; ++q) {
+            ShufTask& t = tasks[ti];
+            t.j = j; t.k = order[q]; rng.export_state(t.mt, &t.idx);
+            published.store(++ti, std::memory_order_release);
+            const size_t len = order[q] < 7 ? (size_t)f.cnt[order[q]] : S_of[j];
+            rng.skip_shuffle(len);
+            n_draw += (long long)len;
+          }
+        }
+        if (cf_timing) t_skip = cf_now() - tt0;
+      };
+      lists_done.reset(new std::atomic<int>[nf]); sample_done.reset(new std::atomic<int>[nf]);
+      for (int j = 0; j < nf; ++j) { lists_done[j].store(0); sample_done[j].store(0); }
+      auto worker = [&]() {
+        PyRandom r;
+        for (;;) {
+          const size_t ti = next_task.fetch_add(1);
+          if (ti >= tasks.size()) return;
+          while (published.load(std::memory_order_acquire) <= ti) std::this_thread::yield();
+          const ShufTask& t = tasks[ti];
+          const FitJob& f = fits[t.j];
+          r.import_state(t.mt, t.idx);
+          if (t.k < 7) {
+            r.shuffle(pin_lists + f.list0[t.k], (size_t)f.cnt[t.k]);
+            lists_done[t.j].fetch_add(1, std::memory_order_release);
+          } else {
+            while (lists_done[t.j].load(std::memory_order_acquire) < 7) std::this_thread::yield();   // earlier tasks: already taken by a worker
+            const size_t n_i = (size_t)(std::min(90000, f.K) / 5);
+            int* smp = pin_samples + sample0[t.j];
+            size_t S = 0;
+            auto append = [&](int k, size_t limit) { const size_t c = std::min(limit, (size_t)f.cnt[k]); memcpy(smp + S, pin_lists + f.list0[k], c * 4); S += c; };
+            append(0, (size_t)f.cnt[0]); for (int k = 1; k <= 5; ++k) append(k, n_i); append(6, (size_t)f.cnt[6]);   // [p2, p20, p40, p60, p80, p100, p98]
+            r.shuffle(smp, S);
+            sample_done[t.j].store(1, std::memory_order_release);
+          }
+        }
+      };
+      pool.emplace_back(walker);
+      for (int q = 0; q < nthreads; ++q) pool.emplace_back(worker);
+    }
+    fits_ready = true;
+    return STC_OK;
+    };
   // ---- 2. cloud-free mosaic (:578-699) ----
   CF_LAUNCH(k_mosaic_prep, cdiv(HW, 128), 128, tiles, areas, n, HW, u8a, d_div.as<float>());
   maskop_dilate(ctx, u8a, u8b, 1, H, W, 2, 1, 1, 0, 0);          // dilate(1 - water, 2)
@@ -774,12 +935,13 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   while (start < n) {
     const int m = n - start;
     CF_LAUNCH(k_mosaic_ref, dim3(cdiv(HW, 128), m), 128, tiles, areas, water0, n, HW, start, d_refall.as<float>(), d_flagall.as<unsigned char>());
-    CF_LAUNCH(k_scan_flags, m, 1024, d_flagall.as<unsigned char>() + (int64_t)start * HW, HW, d_posall.as<int>() + (int64_t)start * HW,
-              d_Ks.as<int>() + start);
+    if ((rc = scan_flags_dev(ctx, d_flagall.as<unsigned char>() + (int64_t)start * HW, m, HW, d_posall.as<int>() + (int64_t)start * HW,
+                             d_Ks.as<int>() + start))) return rc;
     STC_CUDA(cudaMemcpyAsync(Ks.data() + start, d_Ks.as<int>() + start, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CF_SYNC();
     int f = start;
     while (f < n && Ks[f] > 1000) ++f;                       // dates [start, f) are final
+    if (start == 0 && f == n && !fits_ready && (rc = prepare_fits())) return rc;      // no weight changes ahead: overlap (see prepare_fits)
     if (f > start) {
       const int cv = f - start;
       CF_LAUNCH(k_gather_rows, dim3(cdiv(slab, 256), cv), 256, tiles, d_refall.as<float>(), d_posall.as<int>(), HW, start,
@@ -817,102 +979,8 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
 
   cf_mark("mosaic");
   // ---- 3. per-date alignment and blending (:939-959, :316-575) ----
-  CF_LAUNCH(k_water_of_median, cdiv(HW, 128), 128, tiles, n, HW, water1);
-  STC_CUDA(cudaMemsetAsync(d_counts.p, 0, CF_MAX_DATES * 5 * 4, ctx->stream));
-  CF_LAUNCH(k_area_counts, dim3(cdiv(HW, 256), n), 256, areas, water1, HW, d_counts.as<int>());
-  CF_LAUNCH(k_flag_clear_land, dim3(cdiv(HW, 256), n), 256, areas, water1, HW, d_flagall.as<unsigned char>());
-  CF_LAUNCH(k_scan_flags, n, 1024, d_flagall.as<unsigned char>(), HW, d_posall.as<int>(), d_Ks.as<int>());
-  std::vector<int> counts(n * 5);
-  STC_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, n * 20, cudaMemcpyDeviceToHost, ctx->stream));
-  CF_SYNC();
-  PyRandom rng; memcpy(rng.mt, mt_state, 624 * 4); rng.idx = (int)mt_state[624];
-  // ---- 3a. everything about the per-date fits that does NOT depend on the blending of earlier dates, for all dates at once:
-  //      the clear-land rows of a date's window [lo, hi) (weights == 0: the blend never touches them), their EVI, the six EVI
-  //      percentiles, the stratum bits and the seven ordered index lists (:421-471).  One synchronisation for the stratum
-  //      sizes, one for the lists; the lists land in pinned host memory.
-  struct FitJob { int d, lo, hi, K; int64_t row0; int cnt[7]; int64_t list0[7]; };
-  std::vector<FitJob> fits;
-  std::vector<int> fit_of(n, -1);
-  int64_t total_rows = 0;
-  for (int d = 0; d < n; ++d) {
-    const int c_pos = counts[d * 5], c_zero = counts[d * 5 + 1], c_lt1 = counts[d * 5 + 2], c_one = counts[d * 5 + 3];
-    to_remove_host[d] = (c_one == HW);
-    if (!(c_pos > 0 && c_zero > 0)) continue;
-    if (!((double)c_lt1 / (double)HW > 0.01))
-      STC_FAIL(STC_ERR_STATE, "remove_clouds: date with <= 1% non-saturated pixels -- the reference raises UnboundLocalError here (cloud_removal.py:575)");
-    FitJob f; f.d = d;
-    if (c_zero > 40000) { f.lo = d; f.hi = d + 1; }
-    else { f.lo = (d == n - 1) ? std::max(d - 2, 0) : std::max(d - 1, 0); f.hi = std::min(d + 2, n); }
-    f.K = 0;
-    for (int t = f.lo; t < f.hi; ++t) f.K += counts[t * 5 + 4];
-    if (f.K < 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: no clear land pixel to fit on -- the reference fails in np.percentile here");
-    f.row0 = total_rows; total_rows += f.K;
-    fit_of[d] = (int)fits.size(); fits.push_back(f);
-  }
-  const int nf = (int)fits.size();
-  DBuf d_rows_all, d_evi_all, d_lab_all, d_fqout, d_fcnt, d_lists, d_bjobs, d_sample_all, d_status_all;
-  int* pin_lists = nullptr;
+  if (!fits_ready && (rc = prepare_fits())) return rc;
   if (nf > 0) {
-    STC_CUDA(stc_dmalloc(&d_rows_all.p, (size_t)total_rows * 4)); STC_CUDA(stc_dmalloc(&d_evi_all.p, (size_t)total_rows * 4));
-    STC_CUDA(stc_dmalloc(&d_lab_all.p, (size_t)total_rows));
-    STC_CUDA(stc_dmalloc(&d_fqout.p, (size_t)nf * 6 * 4)); STC_CUDA(stc_dmalloc(&d_fcnt.p, (size_t)nf * 7 * 4));
-    STC_CUDA(stc_dmalloc(&d_status_all.p, (size_t)nf * 10 * 4));
-    std::vector<SelJob> jobs; std::vector<QSpec> specs;
-    const double qs[6] = {2 / 100.0, 20 / 100.0, 40 / 100.0, 60 / 100.0, 80 / 100.0, 98 / 100.0};
-    for (const FitJob& f : fits) {
-      int K = 0;
-      for (int t = f.lo; t < f.hi; ++t) {
-        CF_LAUNCH(k_collect_rows, cdiv(HW, 256), 256, tiles, d_posall.as<int>() + (int64_t)t * HW, HW, t, (int)(f.row0 + K), d_rows_all.as<int>(), d_evi_all.as<float>());
-        K += counts[t * 5 + 4];
-      }
-      for (int k = 0; k < 6; ++k) {
-        jobs.push_back(SelJob{d_evi_all.as<float>() + f.row0, f.K, 1, 1});
-        specs.push_back(QSpec{(int)(jobs.size() - 1) * SEL_MAX_COLS, f.K, qs[k], 0});
-      }
-    }
-    if ((rc = run_select(jobs, specs, d_fqout.as<float>()))) return rc;
-    STC_CUDA(cudaMemsetAsync(d_fcnt.p, 0, (size_t)nf * 7 * 4, ctx->stream));
-    for (int j = 0; j < nf; ++j)
-      CF_LAUNCH(k_strata, cdiv(fits[j].K, 256), 256, d_evi_all.as<float>() + fits[j].row0, d_fqout.as<float>() + 6 * j, fits[j].K,
-                d_lab_all.as<unsigned char>() + fits[j].row0, d_fcnt.as<int>() + 7 * j);
-    std::vector<int> h_cnt((size_t)nf * 7);
-    STC_CUDA(cudaMemcpyAsync(h_cnt.data(), d_fcnt.p, (size_t)nf * 7 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CF_SYNC();
-    int64_t total_list = 0;
-    const int rep[7] = {10, 1, 1, 1, 1, 1, 10};
-    for (int j = 0; j < nf; ++j)
-      for (int k = 0; k < 7; ++k) { fits[j].cnt[k] = h_cnt[(size_t)j * 7 + k] * rep[k]; fits[j].list0[k] = total_list; total_list += fits[j].cnt[k]; }
-    for (const FitJob& f : fits)
-      for (int k = 1; k <= 5; ++k)                          // p2 / p98 go through np.repeat first, which accepts a 0-d array
-        if (f.cnt[k] == 1)
-          STC_FAIL(STC_ERR_STATE, "remove_clouds: single-element EVI stratum -- the reference raises TypeError (shuffle of a 0-d array)");
-    STC_CUDA(stc_dmalloc(&d_lists.p, (size_t)std::max<int64_t>(total_list, 1) * 4)); STC_CUDA(stc_dmalloc(&d_bjobs.p, (size_t)nf * sizeof(BucketJob)));
-    std::vector<BucketJob> bj(nf);
-    for (int j = 0; j < nf; ++j) {
-      bj[j].lab = d_lab_all.as<unsigned char>() + fits[j].row0; bj[j].K = fits[j].K;
-      for (int k = 0; k < 7; ++k) bj[j].out[k] = d_lists.as<int>() + fits[j].list0[k];
-    }
-    STC_CUDA(cudaMemcpyAsync(d_bjobs.p, bj.data(), (size_t)nf * sizeof(BucketJob), cudaMemcpyHostToDevice, ctx->stream));
-    CF_LAUNCH(k_bucket_lists, dim3(7, nf), 1024, d_bjobs.as<BucketJob>());
-    // pinned host scratch: the lists, then (behind them) one sample slot per date
-    int64_t sample_cap = 0;
-    std::vector<int64_t> sample0(nf);
-    for (int j = 0; j < nf; ++j) {
-      const int64_t n_i = std::min(90000, fits[j].K) / 5;
-      int64_t cap = (int64_t)fits[j].cnt[0] + fits[j].cnt[6];
-      for (int k = 1; k <= 5; ++k) cap += std::min<int64_t>(n_i, fits[j].cnt[k]);
-      sample0[j] = sample_cap; sample_cap += cap;
-    }
-    pin_lists = (int*)ctx_pinned(ctx, (size_t)(total_list + sample_cap + 16) * 4);
-    if (!pin_lists) STC_FAIL(STC_ERR_NOMEM, "remove_clouds: pinned host scratch");
-    STC_CUDA(stc_dmalloc(&d_sample_all.p, (size_t)std::max<int64_t>(sample_cap, 1) * 4));
-    STC_CUDA(cudaMemcpyAsync(pin_lists, d_lists.p, (size_t)total_list * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CF_SYNC();                                             // bj is a host vector; the lists are on the host now
-    cf_mark("fit rows, strata, index lists (all dates)");
-    // ---- 3b. in date order: Python's random.shuffle replayed on the host for date d while the device still works on date
-    //      d - 1 (launches are asynchronous; nothing below synchronises), then Gram sums, NNLS and the blend of date d.
-    int* pin_samples = pin_lists + total_list;
-    double t_shuffle = 0; long long n_draw = 0;
     for (int d = 0; d < n; ++d) {
       const int j = fit_of[d];
       if (j < 0) {
@@ -922,20 +990,10 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
         continue;
       }
       const FitJob& f = fits[j];
-      const double tt0 = cf_timing ? cf_now() : 0;
-      int* L[7]; for (int k = 0; k < 7; ++k) L[k] = pin_lists + f.list0[k];
-      // :472-478 shuffle order p2, p98, p20, p40, p60, p80, p100
-      rng.shuffle(L[0], f.cnt[0]); rng.shuffle(L[6], f.cnt[6]);
-      for (int k = 1; k <= 5; ++k) rng.shuffle(L[k], f.cnt[k]);
-      const size_t n_i = (size_t)(std::min(90000, f.K) / 5);
+      while (!sample_done[j].load(std::memory_order_acquire)) std::this_thread::yield();
       int* smp = pin_samples + sample0[j];
-      size_t S = 0;
-      auto append = [&](int k, size_t limit) { const size_t c = std::min(limit, (size_t)f.cnt[k]); memcpy(smp + S, L[k], c * 4); S += c; };
-      append(0, (size_t)f.cnt[0]); for (int k = 1; k <= 5; ++k) append(k, n_i); append(6, (size_t)f.cnt[6]);   // [p2, p20, p40, p60, p80, p100, p98]
-      rng.shuffle(smp, S);
+      size_t S = S_of[j];
       if (S > (size_t)f.K) S = (size_t)f.K;
-      for (int k = 0; k < 7; ++k) n_draw += f.cnt[k];
-      if (cf_timing) t_shuffle += cf_now() - tt0;
       int* d_smp = d_sample_all.as<int>() + sample0[j];
       STC_CUDA(cudaMemcpyAsync(d_smp, smp, S * 4, cudaMemcpyHostToDevice, ctx->stream));
       CF_LAUNCH(k_snow_mean, cdiv(HW, 256), 256, tiles, n, HW, d_snow.as<float>());
@@ -946,10 +1004,12 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, d_snow.as<float>(),
                 d_coef.as<double>(), 1, HW);
     }
+    for (auto& t : pool) t.join();
+    if (cf_timing) fprintf(stderr, "[remove_clouds]   generator walk %.1f ms (%lld elements), shuffles on %d host threads, all enqueued after %.1f ms\n",
+                           t_skip, n_draw, nthreads, cf_now() - tt0);
     std::vector<int> status((size_t)nf * 10);
     STC_CUDA(cudaMemcpyAsync(status.data(), d_status_all.p, (size_t)nf * 40, cudaMemcpyDeviceToHost, ctx->stream));
     CF_SYNC();
-    if (cf_timing) fprintf(stderr, "[remove_clouds]   host shuffles %.1f ms (%lld elements, overlapped with the device)\n", t_shuffle, n_draw);
     for (int v : status)
       if (v != 1) STC_FAIL(STC_ERR_STATE, "remove_clouds: NNLS did not converge (scipy.optimize.nnls raises RuntimeError)");
   } else {
@@ -958,7 +1018,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
         CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, (const float*)nullptr,
                   d_coef.as<double>(), 0, HW);
   }
-  memcpy(mt_state, rng.mt, 624 * 4); mt_state[624] = (uint32_t)rng.idx;
+  { int idx_out = 0; rng.export_state(mt_state, &idx_out); mt_state[624] = (uint32_t)idx_out; }
 
   cf_mark("per-date alignment + blend");
   // ---- 4. residual clouds in the mosaic (:703-732) ----
@@ -970,7 +1030,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   CF_SYNC();
   if (only_cnt != HW) {
     CF_LAUNCH(k_not, cdiv(HW, 256), 256, u8a, flag, HW);
-    CF_LAUNCH(k_scan_flags, 1, 1024, flag, HW, d_pos.as<int>(), cnt);
+    if ((rc = scan_flags_dev(ctx, flag, 1, HW, d_pos.as<int>(), cnt))) return rc;
     float* blue = d_src_rows.as<float>(); float* red = d_ref_rows.as<float>();
     CF_LAUNCH(k_gather_br, cdiv(HW, 256), 256, mosaic, d_pos.as<int>(), HW, blue, red);
     const int K2 = HW - only_cnt;
@@ -1036,11 +1096,10 @@ extern "C" int stc_remove_clouds_clip_host(stc_ctx* ctx, float* tiles_host, cons
 // Test hook for the host-side generator replay (no device, no context): shuffles data[0..n) exactly like Python's
 // random.shuffle would with the generator state mt_state (624 words + position), and writes the advanced state back.
 extern "C" int stc_py_shuffle(uint32_t* mt_state, int32_t* data, int64_t n) {
-  if (!mt_state || (!data && n > 0) || n < 0 || mt_state[624] > 624) return STC_ERR_ARG;
-  PyRandom rng; memcpy(rng.mt, mt_state, 624 * 4); rng.idx = (int)mt_state[624];
-  std::vector<int> v(data, data + n);
-  rng.shuffle(v);
-  if (n > 0) memcpy(data, v.data(), (size_t)n * 4);
-  memcpy(mt_state, rng.mt, 624 * 4); mt_state[624] = (uint32_t)rng.idx;
+  if (!mt_state || n < 0 || mt_state[624] > 624) return STC_ERR_ARG;
+  PyRandom rng; rng.import_state(mt_state, (int)mt_state[624]);
+  if (!data) rng.skip_shuffle((size_t)n);        // generator walk only (what remove_clouds does before it farms the shuffles out)
+  else rng.shuffle(data, (size_t)n);
+  int idx_out = 0; rng.export_state(mt_state, &idx_out); mt_state[624] = (uint32_t)idx_out;
   return STC_OK;
 }

@@ -95,6 +95,10 @@ struct stc_ctx {
   void* pin_buf = nullptr; size_t pin_bytes = 0;
   // pinned ring for small host -> device tables (job lists, window tables): cudaMemcpyAsync from it is truly asynchronous
   char* stage_ring = nullptr; size_t stage_pos = 0;
+  // ancillary rasters of the current tile (stc_set_ancillary_masks_host): ESA WorldCover forest / urban masks at tile
+  // resolution, [anc_H * anc_W] uint8 on the device, nullptr = absent (the reference's fallback when the .tif is missing)
+  unsigned char* anc_forest = nullptr; unsigned char* anc_urban_core = nullptr; unsigned char* anc_urban_near = nullptr;
+  int anc_H = 0, anc_W = 0;
   // side stream for latency-bound kernels that occupy a few SMs next to GPU-wide work (forked / joined with events)
   cudaStream_t aux_stream = nullptr; cudaEvent_t aux_ev[2] = {nullptr, nullptr};
 };
@@ -210,6 +214,11 @@ int pre_feature_mosaic_dev(stc_ctx* ctx, const short* feats_dev, const int* xs_d
                            int n, int S, int D, int Hc, int Wc, short* out_dev);
 int pre_feather_dev(stc_ctx* ctx, const float* mask_dev, int n, int H, int W, int size, float* tmp_a, float* tmp_b,
                     float* sums_dev, float* out_dev);
+// separable morphology (stc_morph.cu): row distance by warp ballots + one column pass
+int morph_rowdist_dev(stc_ctx* ctx, const void* in, int src_kind, int64_t rows, int W, int cap, unsigned char* g);
+int morph_dilate_dev(stc_ctx* ctx, const unsigned char* in, unsigned char* out, int frames, int H, int W, int k, int conn, int inv_in,
+                     int inv_out, int three_d);
+int morph_edt_grow_dev(stc_ctx* ctx, const unsigned char* in, unsigned char* out, int T, int H, int W, int radius, const int* frame_count_dev);
 int pre_binary_dilate_dev(stc_ctx* ctx, const unsigned char* in_dev, int n, int H, int W, int iterations, int conn,
                           unsigned char* out_dev);
 int model_forward_slot(stc_ctx* ctx, int slot, const float* monthly_dev, int nb, int Bc, int H,

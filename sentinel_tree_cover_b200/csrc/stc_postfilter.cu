@@ -88,9 +88,11 @@ __global__ void __launch_bounds__(256) k_normalize(float* __restrict__ x, int64_
 }
 
 // ---- bright bare surfaces ----
+// blockIdx.y = image of the batch: img [nimg][F][HW][C], out [nimg][HW]
 __global__ void __launch_bounds__(256) k_bright_candidates(const float* __restrict__ img, int F, int HW, int C, unsigned char* __restrict__ out) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
+  img += (int64_t)blockIdx.y * F * HW * C; out += (int64_t)blockIdx.y * HW;
   int cnt = 0;
   for (int f = 0; f < F; ++f) {
     const float* x = img + ((int64_t)f * HW + p) * C;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(256) k_ramp_crop(const int* __restrict__ d2, i
   const int Ho = H - 2 * crop, Wo = W - 2 * crop;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Ho * Wo) return;
+  d2 += (int64_t)blockIdx.y * H * W; out += (int64_t)blockIdx.y * Ho * Wo;
   int y = i / Wo + crop, x = i % Wo + crop;
   double d = sqrt((double)d2[y * W + x]);
   if (d > 3.0) d = 3.0;
@@ -122,10 +125,12 @@ __global__ void __launch_bounds__(256) k_lt1(const float* __restrict__ m, int Hm
   const int Ho = Hm - 2 * crop, Wo = Wm - 2 * crop;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Ho * Wo) return;
+  m += (int64_t)blockIdx.y * Hm * Wm; out += (int64_t)blockIdx.y * Ho * Wo;
   out[i] = m[(i / Wo + crop) * Wm + (i % Wo + crop)] < 1.f;
 }
-__global__ void k_block_vote(const unsigned char* __restrict__ m, int blocks, int bs, int thresh, unsigned char* __restrict__ vote) {
+__global__ void k_block_vote(const unsigned char* __restrict__ m, int64_t mstride, int blocks, int bs, int thresh, unsigned char* __restrict__ vote) {
   const int by = blockIdx.y, bx = blockIdx.x, side = blocks * bs;
+  m += (int64_t)blockIdx.z * mstride; vote += (int64_t)blockIdx.z * 256;
   __shared__ int s;
   if (threadIdx.x == 0) s = 0;
   __syncthreads();
@@ -140,6 +145,8 @@ __global__ void __launch_bounds__(256) k_attenuate_round(const float* __restrict
                                                          float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S * S) return;
+  preds += (int64_t)blockIdx.y * S * S; ramp += (int64_t)blockIdx.y * S * S; out += (int64_t)blockIdx.y * S * S;
+  if (vote) vote += (int64_t)blockIdx.y * 256;
   const int y = i / S, x = i % S;
   float p = preds[i];
   if (vote && vote[((y + 1) / bs) * blocks + (x + 1) / bs]) p = 255.f;       // votes expanded to blocks, cropped by 1 (:1465-1466)
@@ -148,15 +155,16 @@ __global__ void __launch_bounds__(256) k_attenuate_round(const float* __restrict
   out[i] = (float)v;
 }
 
-int bright_bare_dev(stc_ctx* ctx, const float* img_dev, int F, int H, int W, int C, unsigned char* a, unsigned char* b, int* d2,
+// nimg images at once: img [nimg][F][H][W][C]; scratch a, b [nimg][H*W] u8, d2 [nimg][H*W] int; ramp [nimg][(H-14)*(W-14)] double
+int bright_bare_dev(stc_ctx* ctx, const float* img_dev, int nimg, int F, int H, int W, int C, unsigned char* a, unsigned char* b, int* d2,
                     double* ramp_dev) {
   const int HW = H * W;
-  { TraceScope ts_(ctx, "k_bright_candidates"); k_bright_candidates<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(img_dev, F, HW, C, a); }
-  maskop_dilate(ctx, a, b, 1, H, W, 2, 1, 1, 0, 0);      // binary_dilation(1 - bright, 2)
-  maskop_dilate(ctx, b, a, 1, H, W, 1, 1, 1, 0, 0);      // binary_dilation(1 - that, 1)
-  int rc = pre_edt_sq_dev(ctx, a, 1, H, W, 3, d2);
+  { TraceScope ts_(ctx, "k_bright_candidates"); k_bright_candidates<<<dim3(cdiv(HW, 256), nimg), 256, 0, ctx->stream>>>(img_dev, F, HW, C, a); }
+  maskop_dilate(ctx, a, b, nimg, H, W, 2, 1, 1, 0, 0);      // binary_dilation(1 - bright, 2)
+  maskop_dilate(ctx, b, a, nimg, H, W, 1, 1, 1, 0, 0);      // binary_dilation(1 - that, 1)
+  int rc = pre_edt_sq_dev(ctx, a, nimg, H, W, 3, d2);
   if (rc) return rc;
-  { TraceScope ts_(ctx, "k_ramp_crop"); k_ramp_crop<<<cdiv((H - 14) * (W - 14), 256), 256, 0, ctx->stream>>>(d2, H, W, 7, ramp_dev); }
+  { TraceScope ts_(ctx, "k_ramp_crop"); k_ramp_crop<<<dim3(cdiv((H - 14) * (W - 14), 256), nimg), 256, 0, ctx->stream>>>(d2, H, W, 7, ramp_dev); }
   ctx->launches += 2;
   return STC_OK;
 }
@@ -217,7 +225,7 @@ extern "C" int stc_bright_bare_host(stc_ctx* ctx, const float* img_host, int F, 
   STC_CUDA(stc_dmalloc(&img.p, bytes)); STC_CUDA(stc_dmalloc(&a.p, H * W)); STC_CUDA(stc_dmalloc(&b.p, H * W));
   STC_CUDA(stc_dmalloc(&d2.p, (size_t)H * W * 4)); STC_CUDA(stc_dmalloc(&ramp.p, (size_t)(H - 14) * (W - 14) * 8));
   STC_CUDA(cudaMemcpyAsync(img.p, img_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = bright_bare_dev(ctx, img.as<float>(), F, H, W, C, a.as<unsigned char>(), b.as<unsigned char>(), d2.as<int>(), ramp.as<double>());
+  int rc = bright_bare_dev(ctx, img.as<float>(), 1, F, H, W, C, a.as<unsigned char>(), b.as<unsigned char>(), d2.as<int>(), ramp.as<double>());
   if (rc) return rc;
   STC_CUDA(cudaMemcpyAsync(ramp_host, ramp.p, (size_t)(H - 14) * (W - 14) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -225,24 +233,30 @@ extern "C" int stc_bright_bare_host(stc_ctx* ctx, const float* img_host, int F, 
   return STC_OK;
 }
 
-// device-level post-filter of one subtile (all pointers on the device); scratch: a,b [H*H] u8, d2 [H*H] int, ramp [S*S] double,
-// na,nb [(S+2)^2] u8, vote [256] u8
-int post_subtile_dev(stc_ctx* ctx, const float* preds_dev, const float* img_dev, const float* mc_dev, int S, int F, int C,
-                     unsigned char* a, unsigned char* b, int* d2, double* ramp, unsigned char* na, unsigned char* nb, unsigned char* vote,
-                     float* out_dev) {
+// device-level post-filter of nimg subtiles in one pass per kernel (all pointers on the device): preds / out [nimg][S*S],
+// img [nimg][F][H][H][C], mc [nimg][H*H]; scratch per image: a, b [H*H] u8, d2 [H*H] int, ramp [S*S] double, na, nb [(S+2)^2] u8,
+// vote [256] u8.  (Round 1 looped over the 36 subtiles of a tile: 288 launches of 6-10 us.)
+int post_subtiles_dev(stc_ctx* ctx, const float* preds_dev, const float* img_dev, const float* mc_dev, int nimg, int S, int F, int C,
+                      unsigned char* a, unsigned char* b, int* d2, double* ramp, unsigned char* na, unsigned char* nb, unsigned char* vote,
+                      float* out_dev) {
   const int H = S + 14, Hm = S + 2;
-  int rc = bright_bare_dev(ctx, img_dev, F, H, H, C, a, b, d2, ramp);
+  int rc = bright_bare_dev(ctx, img_dev, nimg, F, H, H, C, a, b, d2, ramp);
   if (rc) return rc;
   int blocks = 0, bs = 0, thresh = 0;
   if (S == 158) { blocks = 4; bs = 40; thresh = 400; }         // sum > 40*40*0.25
   else if (S == 142) { blocks = 9; bs = 16; thresh = 192; }    // sum > 16*16*0.75
-  { TraceScope ts_(ctx, "k_lt1"); k_lt1<<<cdiv(Hm * Hm, 256), 256, 0, ctx->stream>>>(mc_dev, H, H, 6, na); }
-  maskop_dilate(ctx, na, nb, 1, Hm, Hm, 6, 2, 1, 1, 0);   // 1 - dilate(1 - x, 3x3, 6)
-  maskop_dilate(ctx, nb, na, 1, Hm, Hm, 6, 2, 0, 0, 0);   // dilate(.., 3x3, 6)
-  if (blocks) { TraceScope ts_(ctx, "k_block_vote"); k_block_vote<<<dim3(blocks, blocks), 256, 0, ctx->stream>>>(na, blocks, bs, thresh, vote); }
-  { TraceScope ts_(ctx, "k_attenuate_round"); k_attenuate_round<<<cdiv(S * S, 256), 256, 0, ctx->stream>>>(preds_dev, ramp, blocks ? vote : nullptr, S, blocks, bs, out_dev); }
+  { TraceScope ts_(ctx, "k_lt1"); k_lt1<<<dim3(cdiv(Hm * Hm, 256), nimg), 256, 0, ctx->stream>>>(mc_dev, H, H, 6, na); }
+  maskop_dilate(ctx, na, nb, nimg, Hm, Hm, 6, 2, 1, 1, 0);   // 1 - dilate(1 - x, 3x3, 6)
+  maskop_dilate(ctx, nb, na, nimg, Hm, Hm, 6, 2, 0, 0, 0);   // dilate(.., 3x3, 6)
+  if (blocks) { TraceScope ts_(ctx, "k_block_vote"); k_block_vote<<<dim3(blocks, blocks, nimg), 256, 0, ctx->stream>>>(na, (int64_t)Hm * Hm, blocks, bs, thresh, vote); }
+  { TraceScope ts_(ctx, "k_attenuate_round"); k_attenuate_round<<<dim3(cdiv(S * S, 256), nimg), 256, 0, ctx->stream>>>(preds_dev, ramp, blocks ? vote : nullptr, S, blocks, bs, out_dev); }
   ctx->launches += 3;
   return STC_OK;
+}
+int post_subtile_dev(stc_ctx* ctx, const float* preds_dev, const float* img_dev, const float* mc_dev, int S, int F, int C,
+                     unsigned char* a, unsigned char* b, int* d2, double* ramp, unsigned char* na, unsigned char* nb, unsigned char* vote,
+                     float* out_dev) {
+  return post_subtiles_dev(ctx, preds_dev, img_dev, mc_dev, 1, S, F, C, a, b, d2, ramp, na, nb, vote, out_dev);
 }
 
 // preds [S,S] float32; img [F,S+14,S+14,C] (the subtile stack before normalisation); min_clear [S+14,S+14] float32

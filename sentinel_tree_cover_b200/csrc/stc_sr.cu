@@ -7,14 +7,22 @@
 
 int pack_and_upload_conv(stc_ctx* ctx, const float* w, int Cin, int Cout, const std::vector<int>& chanmap, int Npad, uint4** dptr);
 
-struct SrState {
-  uint4* w[6] = {nullptr};
-  float* bias = nullptr;      // 6 x 32 floats (out layer padded to 16)
+// activation arena of one (N, H, W) launch shape; superresolve_large_tile alternates between two shapes per tile (all
+// windows but one, then the overlapping corner window), so the last few plans are kept instead of cudaFree / cudaMalloc /
+// memset of a 2.5 GB arena on every switch (that was 5-15 ms of the 6-23 ms the stage took)
+struct SrPlan {
   void* arena = nullptr; size_t arena_bytes = 0;
   int N = 0, H = 0, W = 0;
   Act X, A, Bf;               // 10->16 ch input (2 chunks), two 32-ch ping-pong activations
   Raw raw, skip;              // conv output (32 ch), fp32 skip path (32 ch)
+  uint64_t last_use = 0;
+};
+struct SrState : SrPlan {
+  uint4* w[6] = {nullptr};
+  float* bias = nullptr;      // 6 x 32 floats (out layer padded to 16)
   bool ready = false;
+  std::vector<SrPlan> cache;  // plans not in use (the current one lives in the base class)
+  uint64_t tick = 0;
 };
 
 __device__ __forceinline__ uint4 sr_pack8(const float* v) {
@@ -130,12 +138,25 @@ void sr_destroy(stc_ctx* ctx) {
   if (!s) return;
   for (int i = 0; i < 6; ++i) cudaFree(s->w[i]);
   cudaFree(s->bias); cudaFree(s->arena);
+  for (auto& pl : s->cache) cudaFree(pl.arena);
   delete s; ctx->sr = nullptr;
 }
 
 static int sr_plan(stc_ctx* ctx, SrState* s, int N, int H, int W) {
+  s->last_use = ++s->tick;
   if (s->arena && s->N == N && s->H == H && s->W == W) return STC_OK;
-  if (s->arena) { cudaFree(s->arena); s->arena = nullptr; }
+  if (s->arena) { s->cache.push_back(*static_cast<SrPlan*>(s)); s->arena = nullptr; }
+  for (size_t i = 0; i < s->cache.size(); ++i)
+    if (s->cache[i].N == N && s->cache[i].H == H && s->cache[i].W == W) {
+      *static_cast<SrPlan*>(s) = s->cache[i]; s->cache.erase(s->cache.begin() + i); s->last_use = s->tick;
+      return STC_OK;
+    }
+  while (s->cache.size() > 3) {                      // keep at most 3 idle plans: drop the least recently used
+    size_t lru = 0;
+    for (size_t i = 1; i < s->cache.size(); ++i) if (s->cache[i].last_use < s->cache[lru].last_use) lru = i;
+    STC_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(s->cache[lru].arena); s->cache.erase(s->cache.begin() + lru);
+  }
   int Hp = H + 2, Wp = W + 2;
   int64_t P = (int64_t)N * Hp * Wp;
   int guard = ((Wp + 2 + 544 + 7) / 8) * 8;

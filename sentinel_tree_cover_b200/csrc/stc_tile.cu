@@ -30,7 +30,8 @@ int tp_max_masked_dev(stc_ctx* ctx, float* a_dev, const float* b_dev, const unsi
 int tp_count_lt_axis0_dev(stc_ctx* ctx, const float* data_dev, int n, int64_t len, float thresh, int* out_dev);
 int interp_build_sentinel2_dev(stc_ctx* ctx, const float* s2_10_dev, const float* s2_20_dev, int n, int h, int w, float* out_dev);
 int interp_missing_counts_dev(stc_ctx* ctx, const float* arr_dev, int n, int HW, int C, int* bad_px_dev, int* nan_vals_dev);
-int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int H, int W, float* clouds_dev, unsigned char* fcps_dev,
+int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int H, int W, const unsigned char* forest_dev,
+                    const unsigned char* urban_core_dev, const unsigned char* urban_near_dev, float* clouds_dev, unsigned char* fcps_dev,
                     uint8_t* stage_host, int stage_id);
 int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const unsigned char* pfcps_dev, int n, int H, int W,
                       uint32_t* mt_state, float* areas, int32_t* to_remove_host, float* mosaic_out_dev, int clip_when_all_kept,
@@ -390,7 +391,9 @@ struct TileState {
 // cloud_removal.identify_clouds_shadows + the Sen2Cor merge (:840-846, 872-876, ...)
 int tile_masks(stc_ctx* ctx, TileState& S, bool first) {
   const int64_t N = (int64_t)S.n * S.H * S.W;
-  TL_CHECK(cloud_masks_dev(ctx, S.s2.as<float>(), S.dem.as<float>(), S.n, S.H, S.W, S.cloudshad.as<float>(), S.fcps.as<unsigned char>(), nullptr, 0));
+  const bool anc = ctx->anc_H == S.H && ctx->anc_W == S.W;
+  TL_CHECK(cloud_masks_dev(ctx, S.s2.as<float>(), S.dem.as<float>(), S.n, S.H, S.W, anc ? ctx->anc_forest : nullptr, anc ? ctx->anc_urban_core : nullptr,
+                           anc ? ctx->anc_urban_near : nullptr, S.cloudshad.as<float>(), S.fcps.as<unsigned char>(), nullptr, 0));
   if (S.have_clm) {
     if (first) TL_LAUNCH(k_zero_where, N, S.clm.as<float>(), S.fcps.as<unsigned char>(), N);      // clm[fcps] = 0.
     TL_CHECK(tp_max_masked_dev(ctx, S.cloudshad.as<float>(), S.clm.as<float>(), nullptr, N));      // np.maximum(cloudshad, clm)

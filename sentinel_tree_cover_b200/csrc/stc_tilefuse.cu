@@ -8,6 +8,9 @@
 
 int interp_missing_counts_dev(stc_ctx* ctx, const float* arr_dev, int n, int HW, int C, int* bad_px_dev, int* nan_vals_dev);
 int interp_median_fill_dev(stc_ctx* ctx, float* arr_dev, int n, int64_t cols);
+int post_subtiles_dev(stc_ctx* ctx, const float* preds_dev, const float* img_dev, const float* mc_dev, int nimg, int S, int F, int C,
+                      unsigned char* a, unsigned char* b, int* d2, double* ramp, unsigned char* na, unsigned char* nb, unsigned char* vote,
+                      float* out_dev);
 int post_subtile_dev(stc_ctx* ctx, const float* preds_dev, const float* img_dev, const float* mc_dev, int S, int F, int C,
                      unsigned char* a, unsigned char* b, int* d2, double* ramp, unsigned char* na, unsigned char* nb, unsigned char* vote,
                      float* out_dev);
@@ -278,9 +281,9 @@ int tf_process_subtiles_dev(stc_ctx* ctx, const float* s2q, const float* s1q, co
   const size_t per = (size_t)(T + 1) * P * P * 17;
   STC_CUDA(stc_dmalloc(&win.p, (size_t)nt * sizeof(Win))); STC_CUDA(stc_dmalloc(&x.p, per * nt * 4)); STC_CUDA(stc_dmalloc(&mc.p, (size_t)nt * P * P * 4));
   STC_CUDA(stc_dmalloc(&flags.p, nt * 4)); STC_CUDA(stc_dmalloc(&preds.p, (size_t)nt * S * S * 4));
-  STC_CUDA(stc_dmalloc(&a.p, P * P)); STC_CUDA(stc_dmalloc(&b.p, P * P)); STC_CUDA(stc_dmalloc(&d2.p, (size_t)P * P * 4));
-  STC_CUDA(stc_dmalloc(&ramp.p, (size_t)S * S * 8)); STC_CUDA(stc_dmalloc(&na.p, (S + 2) * (S + 2))); STC_CUDA(stc_dmalloc(&nb.p, (S + 2) * (S + 2)));
-  STC_CUDA(stc_dmalloc(&vote.p, 256));
+  STC_CUDA(stc_dmalloc(&a.p, (size_t)nt * P * P)); STC_CUDA(stc_dmalloc(&b.p, (size_t)nt * P * P)); STC_CUDA(stc_dmalloc(&d2.p, (size_t)nt * P * P * 4));
+  STC_CUDA(stc_dmalloc(&ramp.p, (size_t)nt * S * S * 8)); STC_CUDA(stc_dmalloc(&na.p, (size_t)nt * (S + 2) * (S + 2)));
+  STC_CUDA(stc_dmalloc(&nb.p, (size_t)nt * (S + 2) * (S + 2))); STC_CUDA(stc_dmalloc(&vote.p, (size_t)nt * 256));
   static_assert(sizeof(Win) == 48, "window table layout");
   STC_CUDA(cudaMemcpyAsync(win.p, windows_host, (size_t)nt * 48, cudaMemcpyHostToDevice, ctx->stream));
   { TraceScope ts_(ctx, "k_gather_subtiles"); k_gather_subtiles<<<dim3(cdiv(P * P, 256), T + 1, nt), 256, 0, ctx->stream>>>(s2q, s1q, s2m, s1m, dem, win.as<Win>(), T, H, W, P, x.as<float>()); }
@@ -293,10 +296,8 @@ int tf_process_subtiles_dev(stc_ctx* ctx, const float* s2q, const float* s1q, co
   ctx->feat_early_dev = ctx->feat_late_dev = nullptr;
   if (rc_fwd) return rc_fwd;
   { TraceScope ts_(ctx, "k_fill_if"); k_fill_if<<<dim3(cdiv(S * S, 256), nt), 256, 0, ctx->stream>>>(preds.as<float>(), flags.as<int>(), S * S, 255.f); } ctx->launches++;
-  for (int i = 0; i < nt; ++i)
-    TF_CHECK(post_subtile_dev(ctx, preds.as<float>() + (size_t)i * S * S, x.as<float>() + per * i, mc.as<float>() + (size_t)i * P * P, S, T + 1, 17,
-                              a.as<unsigned char>(), b.as<unsigned char>(), d2.as<int>(), ramp.as<double>(), na.as<unsigned char>(),
-                              nb.as<unsigned char>(), vote.as<unsigned char>(), out_dev + (size_t)i * S * S));
+  TF_CHECK(post_subtiles_dev(ctx, preds.as<float>(), x.as<float>(), mc.as<float>(), nt, S, T + 1, 17, a.as<unsigned char>(), b.as<unsigned char>(),
+                             d2.as<int>(), ramp.as<double>(), na.as<unsigned char>(), nb.as<unsigned char>(), vote.as<unsigned char>(), out_dev));
   STC_CUDA(cudaMemcpyAsync(no_data_host, flags.p, nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
   STC_CUDA(cudaStreamSynchronize(ctx->stream));
   STC_CUDA(cudaGetLastError());

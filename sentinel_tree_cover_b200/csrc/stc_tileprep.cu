@@ -3,6 +3,8 @@
 // median filter, the Sen2Cor consecutive-date rule, the snow mask, per-date threshold counts, clip / scale.
 // All HBM-bound single-pass kernels.
 #include "stc_common.cuh"
+#include "stc_select.cuh"
+#include <vector>
 
 void maskop_dilate(stc_ctx* ctx, const unsigned char* in, unsigned char* out, int frames, int H, int W, int k, int conn, int inv_in,
                    int inv_out, int three_d);
@@ -11,48 +13,16 @@ namespace {
 
 struct TBuf { void* p = nullptr; ~TBuf() { if (p) stc_dfree(p); } template <typename T> T* as() { return (T*)p; } };
 
-// ---- exact median of every contiguous float32 segment (np.median of a 1-D array), one block per segment ----
-__device__ float seg_radix_select(const float* __restrict__ data, int n, int k) {
-  __shared__ int hist[256]; __shared__ unsigned prefix; __shared__ int kth;
-  if (threadIdx.x == 0) { prefix = 0; kth = k; }
-  __syncthreads();
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    const unsigned pre = prefix;
-    const unsigned mask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      unsigned u = __float_as_uint(data[i]); u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
-      if ((u & mask) == (pre & mask)) atomicAdd(&hist[(u >> shift) & 255], 1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int kk = kth, b = 0;
-      while (b < 255 && kk >= hist[b]) { kk -= hist[b]; ++b; }
-      kth = kk; prefix = pre | ((unsigned)b << shift);
-    }
-    __syncthreads();
-  }
-  unsigned u = prefix; u ^= (u >> 31) ? 0x80000000u : 0xffffffffu;
-  __syncthreads();
-  return __uint_as_float(u);
-}
-// s1_i[s1_i == 1] = np.median(s1_i[s1_i < 65535]) (:702-705): the median runs over ALL values of the date
-// (both polarisations; every value is < 65535 after the /65535 scaling), then replaces the saturated ones
-__global__ void __launch_bounds__(1024) k_s1_fill(float* __restrict__ s1, int len) {
-  float* a = s1 + (int64_t)blockIdx.x * len;
-  __shared__ int any_one;
-  if (threadIdx.x == 0) any_one = 0;
-  __syncthreads();
-  int f = 0;
-  for (int i = threadIdx.x; i < len; i += blockDim.x) f |= (a[i] == 1.0f);
-  if (f) any_one = 1;
-  __syncthreads();
-  if (!any_one) return;
-  float lo = seg_radix_select(a, len, (len - 1) / 2);
-  float hi = (len & 1) ? lo : seg_radix_select(a, len, len / 2);
-  const float med = (len & 1) ? lo : __fdiv_rn(__fadd_rn(lo, hi), 2.f);
-  for (int i = threadIdx.x; i < len; i += blockDim.x) if (a[i] == 1.0f) a[i] = med;
+// s1_i[s1_i == 1] = np.median(s1_i[s1_i < 65535]) (:702-705): the median runs over ALL values of the date (both
+// polarisations; every value is < 65535 after the /65535 scaling), then replaces the saturated ones.  The per-date
+// medians come from the GPU-wide radix select (stc_select.cu); round 1 ran one block per date (12 blocks, 1.5 ms).
+__global__ void __launch_bounds__(256) k_s1_fill(float* __restrict__ s1, int len, const float* __restrict__ pairs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  float* a = s1 + (int64_t)blockIdx.y * len;
+  if (a[i] != 1.0f) return;
+  const float lo = pairs[blockIdx.y * SEL_MAX_COLS * 2], hi = pairs[blockIdx.y * SEL_MAX_COLS * 2 + 1];
+  a[i] = (len & 1) ? lo : __fdiv_rn(__fadd_rn(lo, hi), 2.f);
 }
 
 // scipy.ndimage.median_filter(dem, size=5), mode='reflect' (d c b a | a b c d): rank 12 of the 25 window values
@@ -149,7 +119,18 @@ __global__ void __launch_bounds__(256) k_max_masked(float* __restrict__ a, const
 
 // ---- device-level launchers (shared with stc_tile.cu: the device-resident tile chain) ----
 int tp_s1_fill_dev(stc_ctx* ctx, float* s1_dev, int m, int len) {
-  { TraceScope ts_(ctx, "k_s1_fill"); k_s1_fill<<<m, 1024, 0, ctx->stream>>>(s1_dev, len); } ctx->launches++;
+  if (m < 1 || len < 1) return STC_OK;
+  std::vector<SelJob> jobs(m);
+  std::vector<int> ks((size_t)m * SEL_MAX_COLS, 0);
+  for (int t = 0; t < m; ++t) { jobs[t] = SelJob{s1_dev + (int64_t)t * len, len, 1, 1}; ks[(size_t)t * SEL_MAX_COLS] = (len - 1) / 2; }
+  PoolBuf d_ks, d_pairs;
+  STC_CUDA(d_ks.alloc(ks.size() * 4)); STC_CUDA(d_pairs.alloc(ks.size() * 8));
+  const void* hk = ctx_stage(ctx, ks.data(), ks.size() * 4);
+  if (!hk) STC_FAIL(STC_ERR_NOMEM, "s1_fill: pinned staging");
+  STC_CUDA(cudaMemcpyAsync(d_ks.p, hk, ks.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = select_ranks_dev(ctx, jobs.data(), m, d_ks.as<int>(), d_pairs.as<float>());
+  if (rc) return rc;
+  { TraceScope ts_(ctx, "k_s1_fill"); k_s1_fill<<<dim3(cdiv(len, 256), m), 256, 0, ctx->stream>>>(s1_dev, len, d_pairs.as<float>()); } ctx->launches++;
   return STC_OK;
 }
 int tp_median5_dev(stc_ctx* ctx, const float* in_dev, int H, int W, float* out_dev) {
@@ -194,7 +175,7 @@ extern "C" int stc_s1_fill_host(stc_ctx* ctx, float* s1_host, int m, int H, int 
   const int len = H * W * C; TBuf d;
   STC_CUDA(stc_dmalloc(&d.p, (size_t)m * len * 4));
   STC_CUDA(cudaMemcpyAsync(d.p, s1_host, (size_t)m * len * 4, cudaMemcpyHostToDevice, ctx->stream));
-  { TraceScope ts_(ctx, "k_s1_fill"); k_s1_fill<<<m, 1024, 0, ctx->stream>>>(d.as<float>(), len); } ctx->launches++;
+  { int rc = tp_s1_fill_dev(ctx, d.as<float>(), m, len); if (rc) return rc; }
   STC_CUDA(cudaMemcpyAsync(s1_host, d.p, (size_t)m * len * 4, cudaMemcpyDeviceToHost, ctx->stream));
   TP_FINISH();
 }

@@ -93,9 +93,13 @@ def test_python_random_shuffle_replay_matches_cpython():
     random.seed(20240917)
     for _ in range(411):                                     # land in the middle of a 624-word block
         random.getrandbits(32)
-    for n in (0, 1, 2, 3, 7, 1024, 1025, 65535, 65536, 65537, 200003):
+    for n in (0, 1, 2, 3, 7, 31, 32, 33, 34, 63, 64, 65, 100, 1024, 1025, 65535, 65536, 65537, 200003, 1300001):
         state = np.array(random.getstate()[1], dtype=np.uint32)
+        skip = state.copy()
         want = list(range(n)); random.shuffle(want)
+        # data == NULL: the generator walk alone (what lets the shuffles run on worker threads) ends in the same state
+        assert lib.stc_py_shuffle(skip.ctypes.data_as(C.c_void_p), None, n) == 0
+        assert tuple(int(v) for v in skip) == random.getstate()[1], ("skip", n)
         got = np.arange(n, dtype=np.int32)
         rc = lib.stc_py_shuffle(state.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), n)
         assert rc == 0 and got.tolist() == want, n
