@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE (oracle) -- NumPy/SciPy restatement of the multi-temporal cloud / shadow
 mask, /root/reference/src/preprocessing/cloud_removal.py:1215-1677 (`identify_clouds_shadows`),
-for the configuration the reference tree actually runs in: `urbanmask.tif` / `forestmask.tif`
-are absent, so the forest mask and the potential-false-positive (urban) masks are all zero
-(:1131-1135, :1254-1257).  Pinned against the reference function itself executed through
-oracle/refshim.py (tests/test_cloud_masks.py).  Tests only; never imported by the product.
+both for the configuration the reference tree runs in as shipped (`urbanmask.tif` / `forestmask.tif` absent: the forest
+mask and the potential-false-positive (urban) masks are all zero, :1131-1135, :1254-1257) and with the two ancillary
+rasters given as arrays (`forest`, `urban=(core, near)`: what adjust_cloudmask_in_forests :758-771 returns and the two
+resized rasters of mask_nonurban_areas :735-755), including the Fmask-4 parallax test of detect_pfcp (:1109-1212).
+Pinned against the reference function itself executed through oracle/refshim.py (tests/test_cloud_masks.py; with the
+rasters: the two loader functions monkey-patched to return seeded arrays).  Tests only; never imported by the product.
 
 The function returns the final (clouds, fcps) and, with `stages=True`, the intermediate
 arrays the CUDA pipeline is checked against stage by stage.
@@ -55,14 +57,81 @@ def cloud_windows(t, T):
     return others, close
 
 
-def identify_clouds_shadows(img, dem, stages=False):
+def nn_resize_index(n_out, n_in):
+    """Source index of every output sample of an order-0 resize (scipy.ndimage.zoom(order=0, grid_mode=True,
+    mode='nearest'), the stand-in for skimage.transform.resize(..., 0)): the same map in every column / row."""
+    from scipy.ndimage import zoom
+    return zoom(np.arange(n_in, dtype=np.float64), n_out / float(n_in), order=0, mode="nearest", grid_mode=True, prefilter=False).astype(np.int64)
+
+
+def rasters_to_masks(forest_rst, urban_rst, shape):
+    """What the reference derives from the two ESA WorldCover windows (cloud_removal.py:735-771): forest = dilate 2 ->
+    resize; urban core = dilate 1 -> resize; urban near = dilate 5 more -> resize.  Returns uint8 (forest, core, near)."""
+    def rs(a):
+        return a[nn_resize_index(shape[0], a.shape[0])][:, nn_resize_index(shape[1], a.shape[1])]
+    forest = rs(dil(forest_rst, iterations=2)).astype(np.uint8) if forest_rst is not None else None
+    core = near = None
+    if urban_rst is not None:
+        r1 = dil(urban_rst, iterations=1)
+        core = rs(r1).astype(np.uint8)
+        near = rs(dil(r1, iterations=5)).astype(np.uint8)
+    return forest, core, near
+
+
+def detect_pfcp(arr, dem, urban):
+    """cloud_removal.py:1109-1212 with the urban raster given as (core, near) masks (None: the except-branch, zeros)."""
+    from scipy import ndimage, signal
+    T, H, W, _ = arr.shape
+    ndvi = (arr[..., 3] - arr[..., 2]) / (arr[..., 3] + arr[..., 2])
+    ndbi = (arr[..., 8] - arr[..., 3]) / (arr[..., 8] + arr[..., 3])
+    ndwi = np.median((arr[..., 1] - arr[..., 3]) / (arr[..., 1] + arr[..., 3]), axis=0)
+    pfps = np.median(np.logical_and(ndbi > 0, ndbi > ndvi), axis=0)
+    pfps = pfps * (ndwi < 0)
+    if urban is None:
+        pfps = np.zeros_like(dem)
+    else:
+        core, near = urban
+        pfps[core == 1] = 1.
+        pfps[near == 0] = 0.
+    pfps[(dem / 90) > 0.10] = 0.
+    pfps = np.tile(pfps[np.newaxis], (T, 1, 1))
+    cdis = np.zeros((T, H, W), np.float32)
+    H2, W2 = H + H % 2, W + W % 2
+    ru, cu = nn_resize_index(H2, H), nn_resize_index(W2, W)
+    rd, cd = nn_resize_index(H, H2), nn_resize_index(W, W2)
+    mean_op = np.ones((7, 7)) / 49
+
+    def var7(x):
+        return signal.convolve2d(x ** 2, mean_op, mode="same", boundary="symm") - signal.convolve2d(x, mean_op, mode="same", boundary="symm") ** 2
+
+    for t in range(T):
+        def pool(b, blur):
+            x = np.copy(arr[t, ..., b])
+            if (H % 2 + W % 2) > 0:
+                x = x[ru][:, cu]
+            if blur:
+                x = ndimage.gaussian_filter(x, sigma=0.5, truncate=3)
+            return np.mean(x.reshape(H2 // 2, 2, W2 // 2, 2), axis=(1, 3))
+        b8, b8a, b7 = pool(3, True), pool(7, False), pool(6, False)
+        r8a, r8a7 = var7(b8 / b8a), var7(b7 / b8a)
+        cdi = (r8a7 - r8a) / (r8a7 + r8a)
+        pf = (cdi >= -0.4).repeat(2, axis=0).repeat(2, axis=1)[rd][:, cd]
+        cdis[t] = pf * (ndvi[t] < 0.4)
+    s2 = np.ones((3, 3), bool)
+    for t in range(T):
+        cdis[t] = dil(cdis[t], iterations=6, structure=s2)
+        pfps[t] = dil(pfps[t], iterations=6, structure=s2)
+    return pfps * cdis, pfps
+
+
+def identify_clouds_shadows(img, dem, stages=False, forest=None, urban=None):
     img = np.asarray(img, np.float32)
     T, H, W, _ = img.shape
     st = {}
     with np.errstate(all="ignore"):
         ndwi = (img[..., 1] - img[..., 3]) / (img[..., 1] + img[..., 3])
         water = np.nanmedian(ndwi, axis=0)
-        forest = np.zeros_like(dem)
+        forest = np.zeros_like(dem) if forest is None else np.asarray(forest)
         # Hollstein "okay" cloud mask (:1230-1242)
         clm = (img[..., 7] > 0.166) * (img[..., 1] > 0.28) * (img[..., 5] / img[..., 8] < 4.292)
         for t in range(T):
@@ -179,8 +248,18 @@ def identify_clouds_shadows(img, dem, stages=False):
         st["clouds_bright"] = clouds.copy()
 
         # ---- false-positive removal (:1497-1551); fcps == 0 without an urban mask ----
-        fcps = np.zeros((T, H, W), np.float32)
-        pfcps = np.zeros((T, H, W), np.float32)
+        if urban is None:                      # pfps == 0 (:1133-1135), so fcps == 0 whatever the parallax test says
+            fcps, pfcps = np.zeros((T, H, W)), np.zeros((T, H, W))
+        else:
+            fcps, pfcps = detect_pfcp(img, dem, urban)
+        st["fcps0"], st["pfcps0"] = (fcps > 0).astype(np.uint8), (pfcps > 0).astype(np.uint8)
+        for t in range(T):
+            lo, hi = max(t - 1, 0), min(t + 2, T)
+            bmin = np.min(img[lo:hi, ..., :3], axis=(0, 3))
+            isnt = ((np.mean(img[t, ..., :3], axis=-1) - bmin) < 0.4)
+            rm = np.logical_and(fcps[t] > 0, isnt)
+            clouds[t][rm] = 0.
+            shadows[t][rm] = 0.
         nsr = (img[..., 3] / (img[..., 8] + 0.01)) < 0.75
         nsr = dil(nsr, iterations=3)          # note: 3-D dilation over (T,H,W) with the 3-D cross (:1518)
         for t in range(T):

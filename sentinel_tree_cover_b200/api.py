@@ -486,10 +486,27 @@ class StcSession:
         return out
 
     CLOUD_STAGES = {"clm": 1, "shadows_raw": 2, "shadows_clean": 3, "clouds_raw": 4, "clouds_bright": 5,
-                    "clouds_fp": 6, "clouds_shape": 7, "clouds_pre_haze": 8}
+                    "clouds_fp": 6, "clouds_shape": 7, "clouds_pre_haze": 8, "fcps0": 9}
+
+    def set_ancillary_masks(self, forest=None, urban=None, shape=None):
+        """ESA WorldCover rasters of the tile whose masks are computed next (stc_set_ancillary_masks_host): `forest` [H,W]
+        0/1 = what adjust_cloudmask_in_forests returns (cloud_removal.py:758-771), `urban` = (core, near) [H,W] 0/1 = the two
+        resized rasters of mask_nonurban_areas (:735-755); see ancillary_masks_from_rasters.  None clears a mask (the
+        reference's behaviour when the .tif is missing).  They apply to cloud_masks / run_tile calls of the same H, W."""
+        f = None if forest is None else np.ascontiguousarray(np.asarray(forest) != 0, np.uint8)
+        c = n = None
+        if urban is not None:
+            c = np.ascontiguousarray(np.asarray(urban[0]) != 0, np.uint8)
+            n = np.ascontiguousarray(np.asarray(urban[1]) != 0, np.uint8)
+        shp = shape or (f.shape if f is not None else (c.shape if c is not None else (0, 0)))
+        for m in (f, c, n):
+            if m is not None and m.shape != tuple(shp):
+                raise ValueError("ancillary mask shape %r is not %r" % (m.shape, tuple(shp)))
+        self._check(self.lib.stc_set_ancillary_masks_host(self.h, _dptr(f) if f is not None else None, _dptr(c) if c is not None else None,
+                                                          _dptr(n) if n is not None else None, int(shp[0]), int(shp[1])))
 
     def cloud_masks(self, img, dem, stage=None):
-        """identify_clouds_shadows (cloud_removal.py:1215-1677), no forest/urban mask rasters.
+        """identify_clouds_shadows (cloud_removal.py:1215-1677) with the ancillary rasters last given to set_ancillary_masks.
         img [T,H,W,>=10] float32 reflectance, dem [H,W] -> (clouds float32 [T,H,W], fcps bool [T,H,W]);
         with `stage` (a CLOUD_STAGES name) also returns that intermediate uint8 mask (test tap)."""
         a = np.ascontiguousarray(np.asarray(img)[..., :10], np.float32)
@@ -860,14 +877,50 @@ def process_sentinel_1_tile(sentinel1, dates, sess):
     return sess.temporal_matmul(sentinel1, M)
 
 
-def identify_clouds_shadows(img, dem, bbx, sess):
+def _nn_index(n_out, n_in):
+    """Source index of an order-0 resize (skimage.transform.resize(x, shape, 0)): nearest sample to (i + .5) n_in / n_out - .5."""
+    k = np.floor((np.arange(n_out) + 0.5) * (n_in / float(n_out)) - 0.5 + 0.5).astype(np.int64)
+    return np.clip(k, 0, n_in - 1)
+
+
+def _dilate_cross(a, k):
+    """k iterations of the 4-connected binary dilation with border_value 0 (tiny host rasters only)."""
+    a = np.asarray(a) != 0
+    for _ in range(k):
+        p = np.pad(a, 1)
+        a = p[1:-1, 1:-1] | p[:-2, 1:-1] | p[2:, 1:-1] | p[1:-1, :-2] | p[1:-1, 2:]
+    return a
+
+
+def ancillary_masks_from_rasters(forest_rst, urban_rst, shape):
+    """What the reference derives from the two raster WINDOWS it reads with rasterio (the read itself is the caller's I/O):
+    forest = dilate 2 -> order-0 resize to the tile (adjust_cloudmask_in_forests, cloud_removal.py:758-771); urban core =
+    dilate 1 -> resize, urban near = dilate 5 more -> resize (mask_nonurban_areas, :735-755).  A ~40 x 40 raster: host NumPy.
+    Returns (forest, (core, near)) ready for StcSession.set_ancillary_masks; None in -> None out."""
+    def rs(a):
+        return np.ascontiguousarray(a[_nn_index(shape[0], a.shape[0])][:, _nn_index(shape[1], a.shape[1])], np.uint8)
+    forest = rs(_dilate_cross(forest_rst, 2)) if forest_rst is not None else None
+    urban = None
+    if urban_rst is not None:
+        r1 = _dilate_cross(urban_rst, 1)
+        urban = (rs(r1), rs(_dilate_cross(r1, 5)))
+    return forest, urban
+
+
+def identify_clouds_shadows(img, dem, bbx, sess, forest_mask=None, urban_mask=None):
     """src/preprocessing/cloud_removal.py:1215-1677, same arguments and return value
-    `(clouds float32 [T,H,W], fcps bool [T,H,W])`.  `bbx` only positions the optional
-    forestmask.tif / urbanmask.tif rasters, which this tree does not ship (:1131-1135, :1254-1257),
-    so it is accepted and unused: forest and urban masks are zero, exactly the reference's
-    behaviour when those files are absent.  Runs entirely on the GPU (stc_cloud_masks_host)."""
+    `(clouds float32 [T,H,W], fcps bool [T,H,W])`.  The reference uses `bbx` only to cut the windows of
+    forestmask.tif / urbanmask.tif (:1131-1135, :1254-1257) and falls back to zeros when the files are absent (they are
+    not shipped with the tree); here the caller passes the arrays instead: `forest_mask` [H,W] and `urban_mask` =
+    (core, near) [H,W] as produced by ancillary_masks_from_rasters.  Both None = the reference's fallback.
+    Runs entirely on the GPU (stc_cloud_masks_host)."""
     del bbx
-    return sess.cloud_masks(img, dem)
+    H, W = np.asarray(dem).shape
+    sess.set_ancillary_masks(forest_mask, urban_mask, (H, W))
+    try:
+        return sess.cloud_masks(img, dem)
+    finally:
+        sess.set_ancillary_masks(None, None)
 
 
 def identify_bright_bare_surfaces(img, sess):

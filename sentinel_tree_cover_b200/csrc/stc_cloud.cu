@@ -9,6 +9,8 @@
 #include "stc_common.cuh"
 #include "stc_select.cuh"
 #include <cmath>
+int pfcp_detect_dev(stc_ctx* ctx, const float* img, const float* dem, const unsigned char* urban_core, const unsigned char* urban_near, int T,
+                    int H, int W, unsigned char* fcps_out, unsigned char* pfps_out);
 #include <cstring>
 #include <algorithm>
 #include <vector>
@@ -581,8 +583,45 @@ __global__ void __launch_bounds__(256) k_zero_rows(unsigned char* __restrict__ c
   if (flags[2 * t + 1] && H > 1) clouds[((int64_t)t * H + 1) * W + x] = 0;
 }
 
+// clouds / shadows of date t are cleared where fcps > 0 and the pixel is not much brighter than its darkest neighbour date
+// (:1500-1511)
+__global__ void __launch_bounds__(256) k_fcps_remove(const float* __restrict__ img, const unsigned char* __restrict__ fcps, int T, int HW,
+                                                     unsigned char* __restrict__ clouds, unsigned char* __restrict__ shadows) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x; const int t = blockIdx.y;
+  if (p >= HW) return;
+  const int64_t i = (int64_t)t * HW + p;
+  if (!fcps[i]) return;
+  const int lo = t - 1 > 0 ? t - 1 : 0, hi = t + 2 < T ? t + 2 : T;
+  float bmin = INFINITY;
+  for (int tt = lo; tt < hi; ++tt) { const float* q = img + ((int64_t)tt * HW + p) * 10; bmin = fminf(bmin, fminf(fminf(q[0], q[1]), q[2])); }
+  const float* x = img + i * 10;
+  const float bi = __fdiv_rn(__fadd_rn(__fadd_rn(x[0], x[1]), x[2]), 3.f);
+  if (__fsub_rn(bi, bmin) < 0.4f) { clouds[i] = 0; shadows[i] = 0; }
+}
+// brightness_threshold * (1 - forest_mask) (:1549)
+__global__ void __launch_bounds__(256) k_clear_forest(unsigned char* __restrict__ m, const unsigned char* __restrict__ forest, int HW, int64_t N) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N && forest[i % HW] != 0) m[i] = 0;       // 1 - forest is 0 where forest == 1 (the raster is 0/1)
+}
+// urban / non-urban split of the eroded clouds (:1592-1597): pf5 [HW] is the dilated potential-false-positive mask
+__global__ void __launch_bounds__(256) k_split_urban(const unsigned char* __restrict__ c, const unsigned char* __restrict__ pf5, int HW, int64_t N,
+                                                     unsigned char* __restrict__ urban, unsigned char* __restrict__ nonurban) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const bool u = pf5[i % HW] != 0;
+  urban[i] = c[i] && u; nonurban[i] = c[i] && !u;
+}
+// clouds = non_urban + urban (:1612) is 2 where both are set; the 2s only matter for the image means of the next two
+// stages (they are clipped at :1649), so they are kept as a second mask: clouds = a | b, two = a & b
+__global__ void __launch_bounds__(256) k_sum_masks(const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, int64_t N,
+                                                   unsigned char* __restrict__ clouds, unsigned char* __restrict__ two) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  clouds[i] = a[i] | b[i]; two[i] = a[i] & b[i];
+}
+
 // ---------------------------------------------------------------------------------------------
-// stage F: shape clean-up (:1590-1612) with pfcps == 0
+// stage F: shape clean-up (:1590-1612)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_split_size(const unsigned char* __restrict__ c, unsigned char* __restrict__ large,
                                                     unsigned char* __restrict__ small, int T, int H, int W) {
@@ -814,6 +853,17 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   }
 
   // ---- E: false positives ----
+  const bool urban = urban_core_dev && urban_near_dev;      // no urbanmask.tif: pfps == 0 -> fcps == 0 (:1133-1135)
+  Buf d_fc0, d_pf, d_pf5, d_two;
+  if (urban) {
+    STC_CUDA(stc_dmalloc(&d_fc0.p, N)); STC_CUDA(stc_dmalloc(&d_pf.p, HW)); STC_CUDA(stc_dmalloc(&d_pf5.p, HW)); STC_CUDA(stc_dmalloc(&d_two.p, N));
+    if ((rc_ = pfcp_detect_dev(ctx, img, dem, urban_core_dev, urban_near_dev, T, H, W, (unsigned char*)d_fc0.p, (unsigned char*)d_pf.p))) return rc_;
+    if ((rc_ = dump(9, (const unsigned char*)d_fc0.p))) return rc_;
+    { TraceScope ts_(ctx, "k_fcps_remove"); k_fcps_remove<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(img, (const unsigned char*)d_fc0.p, T, HW, cl, sh); }
+    ctx->launches++;
+  } else if (stage_host && stage_id == 9) {
+    memset(stage_host, 0, (size_t)N);
+  }
   LAUNCH1D(k_nsr, N, img, ta, N);
   dilate(ta, nsr, T, 3, 1, 0, 0, 1);                                            // 3-D dilation (:1518)
   { TraceScope ts_(ctx, "k_fp1"); k_fp1<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(img, water, T, HW, nsr, cl, ta); } ctx->launches++;
@@ -823,13 +873,22 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   STC_CUDA(cudaMemcpyAsync(cl, ta, N, cudaMemcpyDeviceToDevice, ctx->stream));
   LAUNCH1D(k_dark, N, img, ta, N);
   dilate(ta, tb, T, 3, 1, 0, 0, 0);
+  if (forest) LAUNCH1D(k_clear_forest, N, tb, forest, HW, N);
   STC_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * CT_MAX * 4, ctx->stream));
   { TraceScope ts_(ctx, "k_any01"); k_any01<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tb, HW, (int*)d_flags.p); } ctx->launches++;
   { TraceScope ts_(ctx, "k_zero_rows"); k_zero_rows<<<dim3(cdiv(W, 256), T), 256, 0, ctx->stream>>>(cl, (const int*)d_flags.p, H, W); } ctx->launches++;
   if ((rc_ = dump(6, cl))) return rc_;
 
-  // ---- F: shape clean-up (pfcps == 0: no urban clouds) ----
+  // ---- F: shape clean-up: urban clouds eroded by 3, the others grown by size (:1590-1612) ----
   dilate(cl, ta, T, 1, 1, 1, 1, 0);                                             // erode 1
+  Buf d_urb;
+  if (urban) {
+    STC_CUDA(stc_dmalloc(&d_urb.p, N));
+    dilate((const unsigned char*)d_pf.p, (unsigned char*)d_pf5.p, 1, 5, 1, 0, 0, 0);      // pfcps[i] dilated 5 (the same raster for every date)
+    LAUNCH1D(k_split_urban, N, ta, (const unsigned char*)d_pf5.p, HW, N, tb, tc);          // tb = urban, tc = non-urban
+    dilate(tb, (unsigned char*)d_urb.p, T, 3, 1, 1, 1, 0);                                // urban clouds: erode 3
+    STC_CUDA(cudaMemcpyAsync(ta, tc, N, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
   LAUNCH1D(k_split_size, N, ta, tb, tc, T, H, W);                               // tb = large, tc = small
   dilate(tc, cl, T, 1, 1, 0, 0, 0);
   dilate(tb, ta, T, 5, 1, 0, 0, 0);
@@ -837,6 +896,10 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
   { TraceScope ts_(ctx, "k_count_dates"); k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>(tb, HW, (int*)d_all.p); } ctx->launches++;
   if ((rc_ = morph_edt_grow_dev(ctx, tb, cl, T, H, W, 3, (const int*)d_all.p))) return rc_;
+  if (urban) {
+    STC_CUDA(cudaMemcpyAsync(ta, cl, N, cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH1D(k_sum_masks, N, ta, (const unsigned char*)d_urb.p, N, cl, (unsigned char*)d_two.p);
+  }
   if ((rc_ = dump(7, cl))) return rc_;
 
   // ---- G: shadow plausibility (:1617-1626), per date on scalar means ----
@@ -845,6 +908,7 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
     STC_CUDA(cudaMemsetAsync(d_cnt.p, 0, 8, ctx->stream));
     LAUNCH1D(k_count, HW, sh + (int64_t)t * HW, HW, (int*)d_cnt.p);
     LAUNCH1D(k_count, HW, cl + (int64_t)t * HW, HW, (int*)d_cnt.p + 1);
+    if (urban) LAUNCH1D(k_count, HW, (const unsigned char*)d_two.p + (int64_t)t * HW, HW, (int*)d_cnt.p + 1);     // value-2 pixels count twice
     STC_CUDA(cudaMemcpyAsync(c2, d_cnt.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     STC_CUDA(cudaStreamSynchronize(ctx->stream));
     // np.mean of a float32 0/1 array: exact for these sizes
@@ -865,14 +929,22 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
     }
   }
   LAUNCH1D(k_or, N, cl, sh, cl, N);
-  dilate(nsr, tc, T, 2, 1, 0, 0, 1);                                            // fcps = dilate3d(max(0, nsr), 2)
+  if (urban) { LAUNCH1D(k_or, N, nsr, (const unsigned char*)d_fc0.p, ta, N); dilate(ta, tc, T, 2, 1, 0, 0, 1); }   // fcps = dilate3d(max(fcps, nsr), 2)
+  else dilate(nsr, tc, T, 2, 1, 0, 0, 1);                                       // fcps == 0
   STC_CUDA(cudaMemcpyAsync(fcps_dev, tc, N, cudaMemcpyDeviceToDevice, ctx->stream));
+  int two_cnt[CT_MAX] = {0};                                                    // pixels where clouds == 2 (urban + grown non-urban cloud)
+  if (urban) {
+    STC_CUDA(cudaMemsetAsync(d_all.p, 0, CT_MAX * 4, ctx->stream));
+    { TraceScope ts_(ctx, "k_count_dates"); k_count_dates<<<dim3(cdiv(HW, 256), T), 256, 0, ctx->stream>>>((const unsigned char*)d_two.p, HW, (int*)d_all.p); } ctx->launches++;
+    STC_CUDA(cudaMemcpyAsync(two_cnt, d_all.p, T * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    STC_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
 
   // ---- H: dark-blue shadow recovery (:1638-1648) ----
   {
     if ((rc_ = moments(1, nullptr, nullptr, true))) return rc_;
     for (int t = 0; t < T; ++t) {
-      float frac = (float)((double)(HW - cnt_h[2 * t]) / HW);                   // np.mean(clouds[t]) as float32
+      float frac = (float)((double)(HW - cnt_h[2 * t] + two_cnt[t]) / HW);      // np.mean(clouds[t]) as float32 (a 2 counts twice)
       if (!(frac < 0.9f)) continue;
       volatile float two_sd = 2.f * mom_h[2 * t + 1];
       float ref = mom_h[2 * t] + two_sd;

@@ -17,9 +17,10 @@ def synth_monthly(B, H, seed, W=None):
     return np.ascontiguousarray(np.concatenate([s2, dem, s1], -1), np.float32)
 
 
-def synth_cloudy_cube(T, H, W, seed):
+def synth_cloudy_cube(T, H, W, seed, urban=False):
     """Sentinel-2-like cube [T,H,W,10] with vegetation/soil/water spectra, Gaussian-blob clouds
-    (+0.3..0.6 on every band) and displaced shadows (x0.3), plus a DEM [H,W]."""
+    (+0.3..0.6 on every band) and displaced shadows (x0.3), plus a DEM [H,W].
+    urban=True adds a built-up block (NDBI > 0, NDBI > NDVI) with bright roofs that look like small clouds."""
     r = np.random.default_rng(seed)
     veg = np.array([0.035, 0.06, 0.045, 0.30, 0.10, 0.22, 0.28, 0.32, 0.17, 0.08], np.float32)
     soil = np.array([0.09, 0.12, 0.15, 0.25, 0.18, 0.21, 0.23, 0.26, 0.30, 0.24], np.float32)
@@ -29,6 +30,11 @@ def synth_cloudy_cube(T, H, W, seed):
     base = veg[None, None] * mix[..., None] + soil[None, None] * (1 - mix[..., None])
     lake = (yy - H * 0.7) ** 2 + (xx - W * 0.25) ** 2 < (min(H, W) * 0.12) ** 2
     base[lake] = wat
+    if urban:
+        town = (np.abs(yy - H * 0.3) < H * 0.16) & (np.abs(xx - W * 0.65) < W * 0.2)
+        base[town] = np.array([0.10, 0.12, 0.16, 0.20, 0.19, 0.20, 0.21, 0.22, 0.28, 0.24], np.float32)
+        roofs = town & (((yy // 3) % 5 == 0) & ((xx // 3) % 4 == 0))
+        base[roofs] += 0.22
     cube = np.repeat(base[None], T, 0) * (1 + 0.08 * np.sin(2 * np.pi * np.arange(T) / T))[:, None, None, None]
     cube = cube + r.normal(0, 0.004, cube.shape)
     for t in range(T):

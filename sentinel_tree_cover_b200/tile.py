@@ -114,7 +114,8 @@ def _default_loader(path):
     return hkl.load(path)
 
 
-def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, loader=None, exists=os.path.exists):
+def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, loader=None, exists=os.path.exists,
+                 forest_mask=None, urban_mask=None):
     """:640-997, same arguments and return tuple
     `(sentinel2, image_dates, interp, s1, dem, cloudshad, snow)`."""
     if sess is None:
@@ -204,7 +205,7 @@ def process_tile(x, y, data, local_path, bbx, make_shadow=False, sess=None, load
 
     def masks(first):
         nonlocal clm
-        cloudshad, fcps = _api.identify_clouds_shadows(sentinel2, dem, bbx, sess)
+        cloudshad, fcps = _api.identify_clouds_shadows(sentinel2, dem, bbx, sess, forest_mask=forest_mask, urban_mask=urban_mask)
         if clm is not None:
             if clm.shape == np.asarray(fcps).shape == np.asarray(cloudshad).shape:       # the reference's try/except guards a shape mismatch
                 if first:
