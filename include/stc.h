@@ -410,6 +410,13 @@ int stc_region_predict_dev(stc_ctx* ctx, const float* canvas_dev, int T, int Hc,
 int stc_region_blend_dev(stc_ctx* ctx, const float* preds_dev, int r_first, int rows_have, int R, int C, int S, int stride,
                          int margin, const float* gauss_host, int y0, int y1, int Wc, uint8_t* out_host);
 
+/* ---- seam re-segmentation pass (src/resegment_tiles_wide.py) ----
+ * align_subtile_histograms(array) :284-345: arr [T,H,W,C] float32 (a border subtile: right edge of a tile | left edge of its
+ * neighbour), transformed in place: per time step and band the two column halves (split at `half` = (SIZE + 14) // 2) are
+ * rescaled to their common mean / standard deviation (non-water pixels), kept only where that shrinks the jump across
+ * column `seam_col` = SIZE // 2 + 7.  applied_out [T] (optional): 1 where the transform was kept. */
+int stc_align_histograms_host(stc_ctx* ctx, float* arr_host, int T, int H, int W, int C, int half, int seam_col, int32_t* applied_out);
+
 #ifdef __cplusplus
 }
 #endif

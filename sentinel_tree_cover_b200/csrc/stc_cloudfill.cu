@@ -53,11 +53,19 @@ __device__ __forceinline__ float np_median_small(float* v, int n) {
   return (n & 1) ? v[n >> 1] : __fdiv_rn(__fadd_rn(v[(n >> 1) - 1], v[n >> 1]), 2.f);
 }
 // NumPy's float32 linear-interpolation quantile between two neighbouring order statistics
-__device__ __host__ inline void np_quantile_pos(int n, double q, int& lo, float& g) {
-  double vi = (double)n * q + (1.0 + q * (-1.0)) - 1.0;       // _compute_virtual_index(n, q, alpha=1, beta=1)
-  if (vi < 0) vi = 0;
-  double fl = floor(vi);
-  lo = (int)fl; g = (float)(vi - fl);
+// Position of the `pct`-th percentile among n sorted float32 values exactly as np.percentile(a, pct) computes it for a
+// float32 array (NumPy 2.x): q = float32(pct) / float32(100) (percentile divides by a.dtype.type(100)), virtual index =
+// (n - 1) * q in FLOAT32 (method 'linear': lambda n, q: (n - 1) * q on a 0-d float32 array), gamma = index - floor(index).
+// For n in the 10^4..10^5 range the float32 index carries only 7-9 fractional bits, so gamma differs from the exact
+// fraction in the 3rd-5th digit; the float64 formula used before this was 1 ulp off on ~25 % of the EVI percentiles
+// (found with the T = 8, 96 x 104 case of tests/test_resegment.py: a boundary pixel changed stratum).
+__device__ __host__ inline void np_quantile_pos(int n, double pct, int& lo, float& g) {
+  volatile float q = (float)pct / 100.f;
+  volatile float vi = (float)(n - 1) * q;
+  float v = vi;
+  if (v < 0.f) v = 0.f;
+  const float fl = floorf(v);
+  lo = (int)fl; g = v - fl;
   if (lo >= n - 1) { lo = n - 1; g = 0.f; }
 }
 __device__ __forceinline__ float np_lerp(float a, float b, float g) {
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ t
 
 // np.median / np.percentile from the (x_(k), x_(k+1)) pairs of select_ranks_dev: NumPy's even-length median is (a + b) / 2,
 // its percentile the float32 lerp between the two neighbouring order statistics.
-struct QSpec { int slot; int n; double q; int median; };
+struct QSpec { int slot; int n; double q /* percentile, 0..100 */; int median; };
 __global__ void __launch_bounds__(128) k_quantile_finish(const float* __restrict__ pairs, const QSpec* __restrict__ specs, int nspec,
                                                          float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(128) k_mosaic_final(const float* __restrict__ 
   for (int t = 0; t < n; ++t) { v[t] = tiles[(int64_t)t * HW * 10 + idx]; mn = fminf(mn, v[t]); mx = fmaxf(mx, v[t]); }
   if (isnan(m)) {
     isortf(v, n);
-    int lo; float g; np_quantile_pos(n, 10.0 / 100.0, lo, g);
+    int lo; float g; np_quantile_pos(n, 10.0, lo, g);
     m = np_lerp(v[lo], v[lo + 1 < n ? lo + 1 : n - 1], g);
   }
   m = fmaxf(m, mn); m = fminf(m, mx);
@@ -789,7 +797,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       STC_CUDA(stc_dmalloc(&d_fqout.p, (size_t)nf * 6 * 4)); STC_CUDA(stc_dmalloc(&d_fcnt.p, (size_t)nf * 7 * 4));
       STC_CUDA(stc_dmalloc(&d_status_all.p, (size_t)nf * 10 * 4));
       std::vector<SelJob> jobs; std::vector<QSpec> specs;
-      const double qs[6] = {2 / 100.0, 20 / 100.0, 40 / 100.0, 60 / 100.0, 80 / 100.0, 98 / 100.0};
+      const double qs[6] = {2, 20, 40, 60, 80, 98};           // percentiles (np_quantile_pos divides by 100 in float32)
       for (const FitJob& f : fits) {
         int K = 0;
         for (int t = f.lo; t < f.hi; ++t) {
@@ -1001,6 +1009,18 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       CF_LAUNCH(k_gram, gb, 640, tiles, mosaic, d_snow.as<float>(), d_rows_all.as<int>() + f.row0, d_smp, (int)S, HW, d_partial.as<double>());
       CF_LAUNCH(k_gram_reduce, 1, 640, d_partial.as<double>(), gb, d_gram.as<double>());
       CF_LAUNCH(k_nnls, 1, 32, d_gram.as<double>(), (int)S, d_coef.as<double>(), d_status_all.as<int>() + 10 * j);
+      if (getenv("STC_CF_DEBUG")) {                        // test aid: fit inputs / coefficients of every date on stderr
+        double hc[10 * NF]; int hs[6] = {0}; int hr[6] = {0}; float hq[6] = {0};
+        cudaMemcpyAsync(hq, d_fqout.as<float>() + 6 * j, sizeof(hq), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(hc, d_coef.p, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(hr, d_rows_all.as<int>() + f.row0, sizeof(int) * (f.K < 6 ? f.K : 6), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        for (int q = 0; q < 6 && q < (int)S; ++q) hs[q] = smp[q];
+        fprintf(stderr, "[cf_debug] date %d window [%d,%d) K %d S %zu sample %d %d %d %d %d %d rows %d %d %d %d %d %d cnt %d %d %d %d %d %d %d\n", d, f.lo, f.hi, f.K, S,
+                hs[0], hs[1], hs[2], hs[3], hs[4], hs[5], hr[0], hr[1], hr[2], hr[3], hr[4], hr[5], f.cnt[0], f.cnt[1], f.cnt[2], f.cnt[3], f.cnt[4], f.cnt[5], f.cnt[6]);
+        fprintf(stderr, "[cf_debug]   evi percentiles %.9g %.9g %.9g %.9g %.9g %.9g\n", hq[0], hq[1], hq[2], hq[3], hq[4], hq[5]);
+        for (int b = 0; b < 10; b += 8) { fprintf(stderr, "[cf_debug]   band %d coef", b); for (int q = 0; q < NF; ++q) fprintf(stderr, " %.6g", hc[b * NF + q]); fprintf(stderr, "\n"); }
+      }
       CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, d_snow.as<float>(),
                 d_coef.as<double>(), 1, HW);
     }
@@ -1035,7 +1055,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
     CF_LAUNCH(k_gather_br, cdiv(HW, 256), 256, mosaic, d_pos.as<int>(), HW, blue, red);
     const int K2 = HW - only_cnt;
     std::vector<SelJob> jobs = {SelJob{blue, K2, 1, 1}, SelJob{red, K2, 1, 1}};
-    std::vector<QSpec> specs = {QSpec{0, K2, 99 / 100.0, 0}, QSpec{SEL_MAX_COLS, K2, 99 / 100.0, 0}};
+    std::vector<QSpec> specs = {QSpec{0, K2, 99.0, 0}, QSpec{SEL_MAX_COLS, K2, 99.0, 0}};
     if ((rc = run_select(jobs, specs, d_qout.as<float>()))) return rc;
     CF_LAUNCH(k_mosaic_clouds, cdiv(HW, 256), 256, mosaic, u8a, pf, d_qout.as<float>(), HW, u8b);
     maskop_dilate(ctx, u8b, flag, 1, H, W, 3, 1, 1, 0, 0);
