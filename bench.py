@@ -342,16 +342,17 @@ def tile_chain_bench(sess, rank, world, barrier, peaks, reps):
 # algorithmic bytes per launch of the streaming kernels of the chain (what one pass must read and write, f32),
 # as a function of (n dates, px pixels, launches of that kernel per tile)
 CHAIN_BYTES = {
-    "temporal_matmul_kernel": lambda n, px, k: (n + 12) * px * 14 * 4 / k,          # K1: n dates in, 12 months out, 14 channels over its launches
+    "temporal_matmul_kernel": lambda n, px, k: (n + 12) * px * 14 * 4 / k,          # K1 unfused: n dates in, 12 months out, 14 channels over its launches
+    "smooth_fused_kernel": lambda n, px, k: (n * 10 + 4 * 14) * px * 4,             # K1 fused: n x 10 bands in, 4 quarterly x 14 channels out
     "sr_apply_kernel": None,
-    "k_cloud_refs": lambda n, px, k: (5 * 3 + 1 + 3) * px * 4,                       # <= 5-date window of 3 bands + shadow mask in, 3 refs out
+    "k_cloud_refs": lambda n, px, k: (n * (3 * 4 + 1) + n * (3 * 4 + 4 + 1)) * px,  # all dates in one pass: 3 bands + shadow mask in, refs + threshold + flag out
     "k_build_sentinel2": lambda n, px, k: n * px * (4 + 6 / 4.0 + 10) * 4,           # 10 m + 20 m stacks in, 10-band cube out
     "k_mosaic_ref": lambda n, px, k: (n * px * 11 + n * px * 10) * 4 / k,
     "indices_kernel": lambda n, px, k: n * px * (10 + 4) * 4 / k,
 }
 
 
-def chain_kernel_table(csv_path, n, px, peaks, top=12):
+def chain_kernel_table(csv_path, n, px, peaks, top=14):
     """Per-kernel totals of one traced tile: launches, summed CUDA-event time, share of the summed kernel time, and for the
     streaming kernels in CHAIN_BYTES the achieved fraction of the measured HBM peak."""
     import csv
@@ -362,9 +363,12 @@ def chain_kernel_table(csv_path, n, px, peaks, top=12):
         e[0] += 1; e[1] += d
     all_ms = sum(v[1] for v in tot.values()) or 1.0
     rows = []
-    for name, (k, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:top]:
-        row = {"kernel": name, "launches": k, "ms": round(ms, 3), "share": round(ms / all_ms, 3)}
+    ranked = sorted(tot.items(), key=lambda kv: -kv[1][1])
+    for i, (name, (k, ms)) in enumerate(ranked):
         f = CHAIN_BYTES.get(name)
+        if i >= top and not f:
+            continue
+        row = {"kernel": name, "launches": k, "ms": round(ms, 3), "share": round(ms / all_ms, 3)}
         if f:
             gbs = f(n, px, k) * k / (ms / 1e3) / 1e9
             row["hbm_gbs"] = round(gbs, 1); row["hbm_frac"] = round(gbs / peaks["hbm"], 3)
@@ -486,7 +490,7 @@ def main():
     checksum = float(host_out.astype(np.float64).sum())
     # ---- same, with the patches in the reference's uint16 storage convention (x/65535) ----
     _log("e2e done; uint16 e2e")
-    host_u16 = sess.pinned_empty((B, 12, H, H, 13), np.uint16)
+    host_u16 = sess.pinned_empty((B, 12, H, H, 13), np.uint16, write_combined=bool(int(os.environ.get("STC_BENCH_WC", "0"))))
     for i in range(B):
         host_u16[i] = np.clip(np.rint(host_in[i] * 65535.0), 0, 65535).astype(np.uint16)
     sess.predict_patches(host_u16, out=host_out)
@@ -535,15 +539,21 @@ def main():
             roof["note"] += "; timed with every launch alone on the GPU (single-stream pass of the same %d steps, %.2f ms/step); in the " \
                             "production multi-slot schedule the same launches average %.1f us because chunks share the SMs" \
                             % (args.steps, ms_single / args.steps, 1e3 * gates_ms_ovl / gates_n_ovl)
+        e2e_u16 = tiles / (ms_u16_max / 1000.0)
         line = {"metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16", "data": "synthetic",
                 "config": workload_config(B),
-                "e2e": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": nbytes_out,
-                        "ms_per_step": ms_e2e_max / args.steps},
-                "e2e_u16": {"value": tiles / (ms_u16_max / 1000.0), "unit": "tiles/s", "h2d_bytes_per_step": nbytes_in // 2,
-                            "d2h_bytes_per_step": nbytes_out, "ms_per_step": ms_u16_max / args.steps,
-                            "note": "same call with uint16 patches (reference integer convention x/65535, predict_subtile :345-347)"},
+                # end to end through the host-buffer C-ABI call in the reference's storage format: uint16 patches
+                # (to_int16 / to_float32, src/tof/tof_downloading.py:51-72; predict_subtile :345-347 divides integer input by
+                # 65535).  tests/test_gpu_model.py::test_uint16_wire_format_vs_f32_oracle_on_original_floats holds this path to
+                # 1e-3 against the float32 oracle evaluated on the ORIGINAL floats.
+                "e2e": {"value": e2e_u16, "unit": "tiles/s", "h2d_bytes_per_step": nbytes_in // 2, "d2h_bytes_per_step": nbytes_out,
+                        "ms_per_step": ms_u16_max / args.steps, "wire_format": "uint16 patches [B,12,H,W,13] (x/65535), float32 maps back",
+                        "h2d_gbs_per_rank": (nbytes_in // 2) / (ms_u16_max / args.steps / 1000.0) / 1e9},
+                "e2e_f32": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": nbytes_out,
+                            "ms_per_step": ms_e2e_max / args.steps, "h2d_gbs_per_rank": nbytes_in / (ms_e2e_max / args.steps / 1000.0) / 1e9,
+                            "note": "same call with float32 patches (twice the bytes over PCIe)"},
                 "gpu_launches": int(launches),
                 "roofline": roof,
                 "roofline_hbm": hbm_roofline(trace_csv, min(B, int(os.environ.get("STC_CHUNK", "32"))), peaks),

@@ -54,7 +54,9 @@ int stc_finalize_weights(stc_ctx* ctx, int which);
 /* ---- device memory helpers (so the host side needs no CUDA binding) ---- */
 int stc_malloc(stc_ctx* ctx, size_t bytes, void** dptr);
 int stc_free(stc_ctx* ctx, void* dptr);
-int stc_malloc_host(stc_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+int stc_malloc_host(stc_ctx* ctx, size_t bytes, void** hptr);
+/* same, with cudaHostAllocWriteCombined when write_combined != 0 (upload-only staging buffers) */
+int stc_malloc_host_flags(stc_ctx* ctx, size_t bytes, int write_combined, void** hptr); /* pinned */
 int stc_free_host(stc_ctx* ctx, void* hptr);
 int stc_h2d(stc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int stc_d2h(stc_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);

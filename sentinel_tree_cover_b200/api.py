@@ -119,6 +119,7 @@ SYMBOLS = [
     ("stc_remove_clouds_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     ("stc_py_shuffle", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    ("stc_malloc_host_flags", C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     ("stc_align_histograms_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("stc_set_ancillary_masks_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     ("stc_remove_clouds_clip_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
@@ -238,10 +239,13 @@ class StcSession:
     def free(self, p):
         self._check(self.lib.stc_free(self.h, p))
 
-    def pinned_empty(self, shape, dtype=np.float32):
+    def pinned_empty(self, shape, dtype=np.float32, write_combined=False):
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
         p = C.c_void_p()
-        self._check(self.lib.stc_malloc_host(self.h, n, C.byref(p)))
+        if write_combined:
+            self._check(self.lib.stc_malloc_host_flags(self.h, n, 1, C.byref(p)))
+        else:
+            self._check(self.lib.stc_malloc_host(self.h, n, C.byref(p)))
         buf = (C.c_char * n).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
         self._pins = getattr(self, '_pins', [])

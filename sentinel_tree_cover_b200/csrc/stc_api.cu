@@ -82,6 +82,13 @@ int stc_finalize_weights(stc_ctx* ctx, int which) {
 int stc_malloc(stc_ctx* ctx, size_t bytes, void** dptr) { CTX_CHECK(); cudaSetDevice(ctx->device); STC_CUDA(cudaMalloc(dptr, bytes)); return STC_OK; }
 int stc_free(stc_ctx* ctx, void* dptr) { CTX_CHECK(); STC_CUDA(cudaStreamSynchronize(ctx->stream)); STC_CUDA(cudaFree(dptr)); return STC_OK; }
 int stc_malloc_host(stc_ctx* ctx, size_t bytes, void** hptr) { CTX_CHECK(); STC_CUDA(cudaMallocHost(hptr, bytes)); return STC_OK; }
+// write_combined != 0: cudaHostAllocWriteCombined (upload-only buffers: the DMA engine reads them without snooping the CPU caches,
+// the host must only write them sequentially and never read them back)
+int stc_malloc_host_flags(stc_ctx* ctx, size_t bytes, int write_combined, void** hptr) {
+  CTX_CHECK();
+  STC_CUDA(cudaHostAlloc(hptr, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  return STC_OK;
+}
 int stc_free_host(stc_ctx* ctx, void* hptr) { CTX_CHECK(); STC_CUDA(cudaFreeHost(hptr)); return STC_OK; }
 int stc_h2d(stc_ctx* ctx, void* dst, const void* src, size_t bytes) {
   CTX_CHECK(); STC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); return STC_OK;

@@ -205,6 +205,7 @@ int launch_conv(stc_ctx* ctx, const ConvParams& p, int ndir);
 // preprocessing (stc_preproc.cu)
 int pre_assemble_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W, float* out_dev);
 int pre_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_host, int n_in, int n_out, int64_t inner, float* out_dev);
+int pre_smooth_fused_dev(stc_ctx* ctx, const float* s2_dev, const float* M_host, int n, int64_t HW, float* monthly_dev, float* quarterly_dev);
 int pre_indices_dev(stc_ctx* ctx, const float* in_dev, int64_t npix, int C, float* out_dev);
 int pre_temporal_median_dev(stc_ctx* ctx, const float* in_dev, int n, int64_t inner, float* out_dev);
 int pre_gauss_mosaic_dev(stc_ctx* ctx, const float* preds_dev, const int* xs_dev, const int* ys_dev, const int* placed_dev,

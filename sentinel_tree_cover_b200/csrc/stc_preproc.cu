@@ -9,6 +9,7 @@
 //   indices_kernel         : make_indices (src/download_and_predict_job.py:998-1006)
 //   temporal_median_kernel : np.median(axis=0) (:1152-1160)
 #include "stc_common.cuh"
+#include <algorithm>
 #include <cstring>
 
 #include "stc_indices.cuh"
@@ -125,6 +126,117 @@ int pre_temporal_matmul_dev(stc_ctx* ctx, const float* in_dev, const float* M_ho
   { TraceScope ts_(ctx, "temporal_matmul_kernel");
     if (vec) launch_temporal_matmul<4>(in_dev, out_dev, n_in, n_out, inner, Mk, ctx->stream);
     else launch_temporal_matmul<1>(in_dev, out_dev, n_in, n_out, inner, Mk, ctx->stream); }
+  STC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return STC_OK;
+}
+
+// ---- K1 fused: indices -> date regridding + Whittaker + monthly mean (one 12 x n operator) -> quarterly medians ----------
+// smooth_large_tile (src/download_and_predict_job.py:1057-1096) + the quarterly composites of process_subtiles (:1274-1278) in
+// ONE pass over the cube: s2 [n][HW][10] float32 is read exactly once, the 4 index channels are formed on the fly, the
+// 14 x 12 monthly values of a pixel live in registers, and only what the caller needs is written (monthly [12][HW][14] and /
+// or quarterly [4][HW][14]).  Algorithmic bytes per pixel: 40 n in, 56 x (12 and / or 4) out -- the unfused chain (indices,
+// two products, a channel interleave, four medians: 9 launches) moved 2.6x that through HBM.
+// Staging: a CTA owns tiles of FS_PX consecutive pixels; for a tile the n rows of FS_PX x 40 B (contiguous in the
+// [n][HW][10] layout) are fetched by cp.async.bulk into one of two shared-memory stages, completion on an mbarrier
+// (expect_tx = n x FS_PX x 40), so the copy of tile k + 1 runs under the arithmetic of tile k and no thread issues a
+// global load.  FS_PX x 14 threads: thread (px, ch) reads its band (ch < 10) or recomputes its index (ch >= 10) per date.
+// Arithmetic order = the unfused kernels (sequential fmaf over the dates from 0, exact index forms, insertion-sort median
+// of 3): bit-identical results, which tests/test_tile_chain.py relies on (chain vs stage-by-stage mirrors).
+constexpr int FS_PX = 32;
+__device__ __forceinline__ uint32_t fs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fs_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__global__ void __launch_bounds__(FS_PX * 14) smooth_fused_kernel(const float* __restrict__ s2, int n, int64_t HW, const __grid_constant__ TMat Mk,
+                                                                  float* __restrict__ monthly /*[12][HW][14] or null*/,
+                                                                  float* __restrict__ quarterly /*[4][HW][14] or null*/) {
+  extern __shared__ __align__(128) float fs_smem[];                  // 2 stages x [n][FS_PX][10]
+  __shared__ __align__(8) uint64_t bars[2];
+  const int tid = threadIdx.x, px = tid / 14, ch = tid - px * 14;
+  const int64_t ntiles = (HW + FS_PX - 1) / FS_PX;
+  const uint32_t stage_floats = (uint32_t)n * FS_PX * 10;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fs_smem_u32(&bars[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fs_smem_u32(&bars[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int64_t tile, int stage) {                        // thread 0: n bulk copies of one tile into `stage`
+    const int64_t p0 = tile * FS_PX;
+    const int npx = (int)((HW - p0) < FS_PX ? (HW - p0) : FS_PX);
+    const uint32_t row_bytes = (uint32_t)npx * 40u;
+    const uint32_t bar = fs_smem_u32(&bars[stage]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t)n) : "memory");
+    for (int t = 0; t < n; ++t) {
+      const uint32_t dst = fs_smem_u32(fs_smem + (size_t)stage * stage_floats + (size_t)t * FS_PX * 10);
+      const float* src = s2 + ((int64_t)t * HW + p0) * 10;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
+    }
+  };
+  int64_t tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) issue(tile, 0);
+  uint32_t phase[2] = {0, 0};
+  int stage = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int64_t next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) issue(next, stage ^ 1);           // the other stage was released by the barrier below
+    fs_mbar_wait(fs_smem_u32(&bars[stage]), phase[stage]);
+    phase[stage] ^= 1;
+    const float* sm = fs_smem + (size_t)stage * stage_floats;
+    const int64_t p = tile * FS_PX + px;
+    if (p < HW) {
+      float acc[12];
+#pragma unroll
+      for (int o = 0; o < 12; ++o) acc[o] = 0.f;
+      for (int t = 0; t < n; ++t) {
+        const float* x = sm + ((size_t)t * FS_PX + px) * 10;
+        float v;
+        if (ch < 10) v = x[ch];
+        else if (ch == 10) v = idx_evi(x[0], x[1], x[2], x[3]);
+        else if (ch == 11) v = idx_bi(x[0], x[2], x[3], x[8]);
+        else if (ch == 12) v = idx_msavi2(x[2], x[3]);
+        else v = idx_grndvi(x[1], x[2], x[3]);
+#pragma unroll
+        for (int o = 0; o < 12; ++o) acc[o] = fmaf(Mk.m[o * 32 + t], v, acc[o]);
+      }
+      if (monthly) {
+#pragma unroll
+        for (int o = 0; o < 12; ++o) monthly[((int64_t)o * HW + p) * 14 + ch] = acc[o];
+      }
+      if (quarterly) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float m3[3] = {acc[3 * k], acc[3 * k + 1], acc[3 * k + 2]};
+          quarterly[((int64_t)k * HW + p) * 14 + ch] = median_n<3>(m3, 3);
+        }
+      }
+    }
+    __syncthreads();                                                 // every thread is done with `stage` before it is refilled
+    stage ^= 1;
+  }
+}
+
+int pre_smooth_fused_dev(stc_ctx* ctx, const float* s2_dev, const float* M_host, int n, int64_t HW, float* monthly_dev, float* quarterly_dev) {
+  if (n < 1 || n > 32) STC_FAIL(STC_ERR_ARG, "smooth_fused: n must be in 1..32");
+  if (((uintptr_t)s2_dev & 15) != 0 || (HW * 40) % 16 != 0) STC_FAIL(STC_ERR_ARG, "smooth_fused: the cube must be 16-byte aligned per date");
+  TMat Mk; memset(&Mk, 0, sizeof(Mk));
+  for (int o = 0; o < 12; ++o)
+    for (int t = 0; t < n; ++t) Mk.m[o * 32 + t] = M_host[o * n + t];
+  const size_t smem = (size_t)2 * n * FS_PX * 40;
+  static bool attr_set = false;
+  if (!attr_set) { STC_CUDA(cudaFuncSetAttribute(smooth_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * FS_PX * 40)); attr_set = true; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t ntiles = (HW + FS_PX - 1) / FS_PX;
+  const int per_sm = smem <= 36 * 1024 ? 4 : smem <= 56 * 1024 ? 3 : 2;          // resident CTAs by shared memory (448 threads each)
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sms * per_sm);
+  { TraceScope ts_(ctx, "smooth_fused_kernel");
+    smooth_fused_kernel<<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev); }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;

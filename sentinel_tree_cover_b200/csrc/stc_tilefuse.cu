@@ -91,18 +91,24 @@ int tf_smooth_quarterly_dev(stc_ctx* ctx, float* s2, int n, int H, int W, const 
     STC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int t = 0; t < n; ++t) if (nan_after_host[t] > 0) return STC_OK;      // caller drops the NaN dates and retries (:1048-1053)
   }
-  STC_CUDA(stc_dmalloc(&idx.p, px * 16)); STC_CUDA(stc_dmalloc(&sm10.p, (size_t)12 * HW * 40));
-  STC_CUDA(stc_dmalloc(&sm4.p, (size_t)12 * HW * 16));
-  float* sm14p = s2_monthly_dev;
-  if (!sm14p) { STC_CUDA(stc_dmalloc(&sm14.p, (size_t)12 * HW * 56)); sm14p = sm14.as<float>(); }
-  TF_CHECK(pre_indices_dev(ctx, s2, px, 10, idx.as<float>()));                         // make_indices :998
-  TF_CHECK(pre_temporal_matmul_dev(ctx, s2, M_host, n, 12, (int64_t)HW * 10, sm10.as<float>()));
-  TF_CHECK(pre_temporal_matmul_dev(ctx, idx.as<float>(), M_host, n, 12, (int64_t)HW * 4, sm4.as<float>()));
-  { TraceScope ts_(ctx, "k_concat_channels"); k_concat_channels<<<cdiv((int64_t)12 * HW * 14, 256), 256, 0, ctx->stream>>>(sm10.as<float>(), 10, sm4.as<float>(), 4, (int64_t)12 * HW, sm14p); }
-  ctx->launches++;
-  if (s2_quarterly_dev)
-    for (int k = 0; k < 4; ++k)
-      TF_CHECK(pre_temporal_median_dev(ctx, sm14p + (size_t)3 * k * HW * 14, 3, (int64_t)HW * 14, s2_quarterly_dev + (size_t)k * HW * 14));
+  if ((((uintptr_t)s2) & 15) == 0 && ((int64_t)HW * 40) % 16 == 0) {
+    // one fused pass (pre_smooth_fused_dev): indices, the 12 x n operator on all 14 channels, quarterly medians
+    TF_CHECK(pre_smooth_fused_dev(ctx, s2, M_host, n, (int64_t)HW, s2_monthly_dev, s2_quarterly_dev));
+  } else {
+    // odd pixel count: the bulk copies of the fused kernel need 16-byte aligned date slabs -> separate kernels (same arithmetic)
+    STC_CUDA(stc_dmalloc(&idx.p, px * 16)); STC_CUDA(stc_dmalloc(&sm10.p, (size_t)12 * HW * 40));
+    STC_CUDA(stc_dmalloc(&sm4.p, (size_t)12 * HW * 16));
+    float* sm14p = s2_monthly_dev;
+    if (!sm14p) { STC_CUDA(stc_dmalloc(&sm14.p, (size_t)12 * HW * 56)); sm14p = sm14.as<float>(); }
+    TF_CHECK(pre_indices_dev(ctx, s2, px, 10, idx.as<float>()));                         // make_indices :998
+    TF_CHECK(pre_temporal_matmul_dev(ctx, s2, M_host, n, 12, (int64_t)HW * 10, sm10.as<float>()));
+    TF_CHECK(pre_temporal_matmul_dev(ctx, idx.as<float>(), M_host, n, 12, (int64_t)HW * 4, sm4.as<float>()));
+    { TraceScope ts_(ctx, "k_concat_channels"); k_concat_channels<<<cdiv((int64_t)12 * HW * 14, 256), 256, 0, ctx->stream>>>(sm10.as<float>(), 10, sm4.as<float>(), 4, (int64_t)12 * HW, sm14p); }
+    ctx->launches++;
+    if (s2_quarterly_dev)
+      for (int k = 0; k < 4; ++k)
+        TF_CHECK(pre_temporal_median_dev(ctx, sm14p + (size_t)3 * k * HW * 14, 3, (int64_t)HW * 14, s2_quarterly_dev + (size_t)k * HW * 14));
+  }
   if (s1_dev) {
     if (s1_quarterly_dev)
       for (int k = 0; k < 4; ++k)

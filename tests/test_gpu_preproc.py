@@ -75,3 +75,27 @@ def test_np_sum_matches_numpy_pairwise(sess):
             want = np.array([np.nanmean(b[i]) for i in range(3)], np.float32)
         got = (s.astype(np.float64) / v).astype(np.float32)
         assert np.array_equal(got, want, equal_nan=True), ln
+
+
+def test_fused_smoothing_kernel_is_bit_identical_to_the_separate_kernels(sess):
+    """smooth_fused_kernel (bulk-copy staged, one pass: indices + 12 x n operator + quarterly medians) against the separate
+    kernels it replaces (indices, temporal_matmul on bands and indices, median of 3): same arithmetic order -> same bits.
+    Even pixel count -> fused path; odd -> the fallback (separate kernels) behind the same entry point."""
+    import ctypes as C
+    from sentinel_tree_cover_b200 import api, regrid
+    r = np.random.default_rng(12)
+    for (n, H, W) in ((9, 46, 40), (24, 33, 64), (5, 31, 29)):
+        s2 = r.uniform(0.01, 0.6, (n, H, W, 10)).astype(np.float32)
+        dates = np.sort(r.choice(np.arange(5, 360), n, replace=False))
+        M = np.ascontiguousarray(regrid.monthly_operator(dates)[0], np.float32)
+        monthly = np.empty((12, H, W, 14), np.float32); quarterly = np.empty((4, H, W, 14), np.float32)
+        nan_after = np.zeros(n, np.int32)
+        s2c = s2.copy()
+        sess._check(sess.lib.stc_smooth_quarterly_host(sess.h, api._dptr(s2c), n, H, W, api._dptr(M), None, api._dptr(monthly), api._dptr(quarterly),
+                                                       None, None, api._dptr(nan_after)))
+        bands = sess.temporal_matmul(s2, M)
+        idx = sess.temporal_matmul(sess.indices(s2), M)
+        want = np.concatenate([bands, idx], -1)
+        assert np.array_equal(monthly, want), (n, H, W, float(np.abs(monthly - want).max()))
+        wq = np.stack([np.median(want[3 * k:3 * k + 3], axis=0) for k in range(4)])
+        assert np.array_equal(quarterly, wq), (n, H, W)

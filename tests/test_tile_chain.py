@@ -114,7 +114,9 @@ def _mirror_chain(sess, store, root, seed):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [dict(seed=21, n=8, h=170, w=170, with_clm=False, ragged=False),
-                                  dict(seed=22, n=7, h=172, w=166, with_clm=True, ragged=True)])
+                                  dict(seed=22, n=7, h=172, w=166, with_clm=True, ragged=True),
+                                  dict(seed=91, n=12, h=309, w=309, with_clm=False, ragged=False)],      # the 618 x 618 px production size
+                         ids=["340px", "ragged", "618px"])
 def test_gpu_tile_chain_matches_stage_mirrors(sess, tmp_path, case):
     from sentinel_tree_cover_b200 import windows
     raw = tile_ref.synth_raw_tile(case["seed"], n=case["n"], h=case["h"], w=case["w"], with_clm=case["with_clm"], ragged=case["ragged"])
