@@ -386,6 +386,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tile-chain", action="store_true")
     ap.add_argument("--tile-reps", type=int, default=5)
+    ap.add_argument("--config", default="patches", choices=["patches", "region"],
+                    help="patches = BASELINE configs[1] (default, the metric's workload); region = configs[3], the 1x1 degree mosaic")
+    ap.add_argument("--region-rows", type=int, default=190)
+    ap.add_argument("--region-cols", type=int, default=190)
+    ap.add_argument("--region-periodic", action="store_true")
     ap.add_argument("--cpu-leg", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--cpu-arg", default="8", help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -393,6 +398,14 @@ def main():
         return run_cpu_leg(args.cpu_leg, args.cpu_arg)
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "region":
+        from sentinel_tree_cover_b200 import region_bench
+        region_bench.run(args.region_rows, args.region_cols, 168, 58, args.batch, periodic=args.region_periodic,
+                         steps=max(1, min(args.steps, 3)), warmup=args.warmup)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+        return
 
     import torch
     rank = int(os.environ.get("RANK", "0"))

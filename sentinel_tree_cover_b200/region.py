@@ -92,12 +92,25 @@ class RegionRunner:
         return out, (y0, y1)
 
 
-def exchange_halo(own_tail, dist, rank, world):
-    """own_tail: torch tensor [2, C, S, S] (the rank's last two patch rows, zero-padded if it owns fewer).  Returns the
-    previous rank's tail (None on rank 0).  One all_gather; NCCL on GPUs, gloo in the CPU tests."""
+def exchange_halo(own_tail, dist, rank, world, spans=None, need=None):
+    """own_tail: torch tensor [2, C, S, S] = the rank's LAST two patch rows (row rb-2 in slot 0, rb-1 in slot 1; a rank that
+    owns a single row puts it in slot 1, a rank that owns none sends zeros).  One all_gather (NCCL on GPUs, gloo in the CPU
+    tests).  With `spans` = [(ra, rb)] of every rank and `need` = (first, ra), returns a tensor [ra - first, C, S, S] holding
+    the patch rows first .. ra-1 picked by GLOBAL row index from whichever rank owns them (the previous rank may own fewer
+    than two rows when there are more ranks than half the patch rows); raises if a needed row is in nobody's tail.
+    Without `spans` (old call): the previous rank's tail as is (None on rank 0)."""
     import torch
     if world == 1:
         return None
     got = [torch.empty_like(own_tail) for _ in range(world)]
     dist.all_gather(got, own_tail)
-    return got[rank - 1] if rank > 0 else None
+    if spans is None:
+        return got[rank - 1] if rank > 0 else None
+    first, ra = need
+    rows = []
+    for g in range(first, ra):
+        owner = next((r for r, (a, b) in enumerate(spans) if a <= g < b), None)
+        if owner is None or g < spans[owner][1] - 2:
+            raise RuntimeError("region halo: patch row %d is not among the last two rows of its owner (rank %r)" % (g, owner))
+        rows.append(got[owner][2 - (spans[owner][1] - g)])
+    return torch.stack(rows) if rows else own_tail[:0]

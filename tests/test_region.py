@@ -54,7 +54,7 @@ _WORKER = textwrap.dedent('''
     from sentinel_tree_cover_b200.shard import shard_range
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    R, C, patch, stride = 7, 3, 44, 16
+    R, C, patch, stride = %(R)d, 3, 44, 16
     S, margin = patch - 14, 7
     full = np.random.default_rng(5).uniform(0.05, 0.95, (R, C, S, S)).astype(np.float32)
     ra, rb = shard_range(R, rank, world)
@@ -62,9 +62,10 @@ _WORKER = textwrap.dedent('''
     tail = np.zeros((2, C, S, S), np.float32)
     k = min(2, rb - ra)
     if k: tail[2 - k:] = own[-k:]
-    prev = region.exchange_halo(torch.from_numpy(tail), dist, rank, world)
     first = region.halo_rows(ra, S, stride, margin)
-    have = own if prev is None or ra == first else np.concatenate([prev.numpy()[2 - (ra - first):], own])
+    spans = [shard_range(R, r, world) for r in range(world)]
+    halo = region.exchange_halo(torch.from_numpy(tail), dist, rank, world, spans=spans, need=(first, ra))
+    have = own if halo is None or ra == first else np.concatenate([halo.numpy(), own])
     # blend the owned rows from `have` only: embed into a zero grid (rows outside [first, rb) never touch owned rows)
     grid = np.zeros_like(full); grid[first:rb] = have
     y0, y1 = region.owned_canvas_rows(ra, rb, R, patch, stride)
@@ -80,12 +81,15 @@ _WORKER = textwrap.dedent('''
 ''')
 
 
-def test_halo_exchange_world2_gloo(tmp_path):
+@pytest.mark.parametrize("world,R", [(2, 7), (3, 4)], ids=["world2", "world3_single_row_ranks"])
+def test_halo_exchange_gloo(tmp_path, world, R):
+    """world 3 over 4 patch rows: shards [0,2) [2,3) [3,4) -- the last rank needs rows 1 and 2, which sit in the tails of TWO
+    different ranks (the previous rank owns a single row): the halo is assembled by global row index."""
     script = tmp_path / "worker.py"
-    script.write_text(_WORKER % {"root": ROOT})
+    script.write_text(_WORKER % {"root": ROOT, "R": R})
     env = dict(os.environ, OMP_NUM_THREADS="1")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29571", str(script)], capture_output=True, text=True, timeout=300, env=env)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", str(29571 + world), str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and "REGION-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 

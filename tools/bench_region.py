@@ -1,24 +1,11 @@
-"""Region-scale run (BASELINE configs[3]): R x C overlapping 168-px patches every 58 px (190 x 190 =
-36,100 patches over an 11,130 px canvas for 1 x 1 degree), patch rows sharded over the GPUs of one box, Gaussian
-overlap-blend mosaic -> uint8 canvas on rank 0.
-
-  python tools/bench_region.py [--rows 190 --cols 190] [--verify]
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_region.py ...
-
-Synthetic input: the canvas is a periodic repetition of one seeded 12 x 232 x 232 x 13 cube held on the device (a real
-11,130^2 x 12 x 13 float32 canvas is 77 GB); patches are cut out of it by the same gather kernel a resident canvas band
-would use.  One JSON line on stdout (rank 0): tiles/s over gather + forward + halo exchange + blend + gather of the
-canvas bands (wall clock between barriers, max over ranks), phase times, a checksum of the canvas."""
+"""CLI of the region-scale run (sentinel_tree_cover_b200/region_bench.py; also reachable as `bench.py --config region`).
+  python tools/bench_region.py [--rows 190 --cols 190] [--periodic] [--verify]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_region.py ..."""
 import argparse
-import json
 import os
 import sys
-import time
 
-import numpy as np
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def main():
@@ -28,99 +15,23 @@ def main():
     ap.add_argument("--patch", type=int, default=168)
     ap.add_argument("--stride", type=int, default=58)
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--periodic", action="store_true", help="round-1 input: one 232-px cube addressed modulo its size")
     ap.add_argument("--verify", action="store_true", help="rank 0 checks its first canvas rows against the NumPy oracle blend")
     a = ap.parse_args()
-    import torch
-    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from sentinel_tree_cover_b200.api import StcSession
-    from sentinel_tree_cover_b200.weights import random_predict_weights
-    from sentinel_tree_cover_b200.shard import broadcast_weights
-    from sentinel_tree_cover_b200 import region
-    from sentinel_tree_cover_b200 import synth as P
-    w = random_predict_weights(0) if rank == 0 else None
-    if world > 1:
-        w = broadcast_weights(w, dist, device=torch.device("cuda", local))
-    sess = StcSession(local, predict_weights=w)
-    R, C, patch, stride = a.rows, a.cols, a.patch, a.stride
-    S = patch - 14
-    rr = region.RegionRunner(sess, R, C, patch, stride, rank, world, batch=a.batch)
-    base = np.ascontiguousarray(P.synth_monthly(1, 232, 4000)[0])
-    d_base = sess.malloc(base.nbytes); sess.h2d(d_base, base); sess.sync()
-    first = region.halo_rows(rr.ra, S, stride, 7)
-    n_halo = rr.ra - first
-    preds = torch.zeros((n_halo + (rr.rb - rr.ra), C, S, S), dtype=torch.float32, device="cuda")
-    own_ptr = preds.data_ptr() + n_halo * C * S * S * 4
+    from sentinel_tree_cover_b200 import region_bench
 
-    def barrier():
-        sess.sync(); torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-
-    # warm-up: one batch through the same path (allocations, first launches)
-    warm = region.RegionRunner(sess, 1, min(C, a.batch), patch, stride, 0, 1, batch=a.batch)
-    tmp = torch.empty((1, min(C, a.batch), S, S), dtype=torch.float32, device="cuda")
-    warm.predict_rows(d_base, 12, 232, 232, 13, True, 0, tmp.data_ptr())
-    barrier()
-    if os.environ.get("STC_REGION_TRACE"):
-        sess.trace(1)
-    t0 = time.perf_counter()
-    rr.predict_rows(d_base, 12, 232, 232, 13, True, 0, own_ptr)
-    if os.environ.get("STC_REGION_TRACE"):
-        sess.trace(0, os.environ["STC_REGION_TRACE"])
-    torch.cuda.synchronize(); t1 = time.perf_counter()
-    if world > 1:
-        tail = torch.zeros((2, C, S, S), dtype=torch.float32, device="cuda")
-        k = min(2, rr.rb - rr.ra)
-        if k:
-            tail[2 - k:] = preds[preds.shape[0] - k:]
-        prev = region.exchange_halo(tail, dist, rank, world)
-        if n_halo:
-            preds[:n_halo] = prev[2 - n_halo:]
-    torch.cuda.synchronize(); t2 = time.perf_counter()
-    band, (y0, y1) = rr.blend(preds.data_ptr(), first, preds.shape[0])
-    t3 = time.perf_counter()
-    if world > 1:
-        # bands differ in height (the last rank takes the remainder): pad to the tallest, one NCCL all_gather of uint8
-        spans = [region.owned_canvas_rows(*region.shard_range(R, r, world), R, patch, stride) for r in range(world)]
-        hmax = max(b - a for a, b in spans)
-        mine = torch.zeros((hmax, rr.Wc), dtype=torch.uint8, device="cuda")
-        mine[:band.shape[0]] = torch.from_numpy(band).cuda()
-        allb = torch.empty((world, hmax, rr.Wc), dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(allb, mine)
-        canvas = np.concatenate([allb[r, :spans[r][1] - spans[r][0]].cpu().numpy() for r in range(world)]) if rank == 0 else None
-    else:
-        canvas = band
-    t4 = time.perf_counter()
-    times = torch.tensor([t4 - t0, t1 - t0, t2 - t1, t3 - t2, t4 - t3], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        tt = [float(v) for v in times.cpu()]
-        line = {"metric": "tiles/sec (1x1 degree region, %d x %d patches of %d px every %d px, overlap-blend mosaic)" % (R, C, patch, stride),
-                "value": R * C / tt[0], "unit": "tiles/s", "n_gpus": world, "tiles": R * C, "seconds": tt[0],
-                "phases_s": {"gather+forward": tt[1], "halo exchange": tt[2], "blend": tt[3], "canvas gather": tt[4]},
-                "canvas": list(canvas.shape), "canvas_checksum": int(canvas.astype(np.int64).sum()),
-                "nodata_px": int((canvas == 255).sum()), "data": "synthetic (periodic 232 px base cube)", "scaling": "strong",
-                "note": "the blend is bit-identical for any rank count GIVEN the probabilities; the probabilities themselves differ by "
-                        "rounding flips between runs (fp64 atomics of the GroupNorm sums depend on batch composition), so checksums "
-                        "of different rank counts agree to ~1e-6 relative, not exactly"}
-        if a.verify:
-            from oracle import region_ref as RR
-            nv = min(6, rr.rb - rr.ra)
-            host = preds[n_halo:n_halo + nv].cpu().numpy()
-            want = RR.blend_region(host, stride)
-            rows = (nv - 2) * stride if nv > 2 else 0            # rows fully determined by the first nv patch rows
-            ok = bool(rows == 0 or np.array_equal(canvas[:rows], want[:rows]))
-            line["verify"] = {"rows_checked": rows, "bit_exact_vs_oracle": ok}
-        print(json.dumps(line), flush=True)
-    sess.free(d_base); sess.close()
-    if dist is not None:
-        dist.barrier(); dist.destroy_process_group()
+    def verify(first_rows, canvas_u8, stride):
+        """rank 0's first patch rows blended by the NumPy oracle: the canvas rows they fully determine must be identical"""
+        import numpy as np
+        from oracle import region_ref as RR
+        nv = first_rows.shape[0]
+        want = RR.blend_region(first_rows, stride)
+        rows_ok = (nv - 2) * stride if nv > 2 else 0
+        return {"rows_checked": rows_ok, "bit_exact_vs_oracle": bool(rows_ok == 0 or np.array_equal(canvas_u8[:rows_ok], want[:rows_ok]))}
+    region_bench.run(a.rows, a.cols, a.patch, a.stride, a.batch, periodic=a.periodic, verify_fn=verify if a.verify else None)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
