@@ -174,6 +174,26 @@ class ClockSampler(threading.Thread):
 _T0 = time.time()
 
 
+def numa_interleave_pinned():
+    """Spread the pages of the pinned staging buffers allocated AFTER this call over all NUMA nodes of the host
+    (set_mempolicy(MPOL_INTERLEAVE) through the raw syscall: no numactl / libnuma dependency).  On the 8-GPU boxes every GPU
+    hangs off NUMA node 0 and every rank allocates there by default, so all H2D DMA reads hit one socket's memory
+    controllers (measured ceiling ~181 GB/s aggregate whatever the wire format).  Returns the number of nodes used (0 = policy
+    not changed)."""
+    import ctypes
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        if len(nodes) < 2:
+            return 0
+        mask = ctypes.c_ulong(sum(1 << n for n in nodes))
+        libc = ctypes.CDLL(None, use_errno=True)
+        SYS_set_mempolicy, MPOL_INTERLEAVE = 238, 3                      # x86-64
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_INTERLEAVE, ctypes.byref(mask), ctypes.c_ulong(max(nodes) + 2))
+        return len(nodes) if rc == 0 else 0
+    except Exception:
+        return 0
+
+
 def _log(msg):
     print("[bench %6.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
 
@@ -426,6 +446,7 @@ def main():
     if world > 1:
         w = broadcast_weights(w, dist, device=torch.device("cuda", local))   # one NCCL broadcast at startup
     sess = StcSession(local, predict_weights=w)
+    numa_nodes = numa_interleave_pinned() if os.environ.get("STC_BENCH_INTERLEAVE", "1") == "1" else 0
     chain_sess = None
     if not args.no_tile_chain:          # the tile chain runs the RELEASED weights (its outputs are compared with goldens in tests/)
         chain_sess = StcSession(local, predict_weights=os.path.join(GOLD, "weights_predict_172.npz"),
@@ -563,6 +584,7 @@ def main():
                 # 1e-3 against the float32 oracle evaluated on the ORIGINAL floats.
                 "e2e": {"value": e2e_u16, "unit": "tiles/s", "h2d_bytes_per_step": nbytes_in // 2, "d2h_bytes_per_step": nbytes_out,
                         "ms_per_step": ms_u16_max / args.steps, "wire_format": "uint16 patches [B,12,H,W,13] (x/65535), float32 maps back",
+                        "pinned_pages": ("interleaved over %d NUMA nodes" % numa_nodes) if numa_nodes else "default policy (one NUMA node)",
                         "h2d_gbs_per_rank": (nbytes_in // 2) / (ms_u16_max / args.steps / 1000.0) / 1e9},
                 "e2e_f32": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": nbytes_out,
                             "ms_per_step": ms_e2e_max / args.steps, "h2d_gbs_per_rank": nbytes_in / (ms_e2e_max / args.steps / 1000.0) / 1e9,

@@ -151,14 +151,23 @@ __device__ __forceinline__ void fs_mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 }
+// NMAX = compile-time bound on n (8 / 16 / 24 / 32) so that the date loop unrolls: the operator is then read as immediate
+// constant-bank operands of the FFMAs (a runtime-indexed M costs one LDC per FFMA) and a thread's n inputs sit in registers.
+// Two phases per tile keep every warp convergent: (A) the 4 indices of the FS_PX x n (pixel, date) pairs, one pair per thread
+// (32 consecutive threads = 32 pixels of one date: same code path), into shared memory; (B) thread (px, ch) gathers its n
+// values (band from the staged rows, index from phase A) and forms the 12 months.  The first version let each (px, ch) thread
+// recompute its own index inside the date loop: every warp ran the band path and all four index paths serially (IEEE divisions),
+// 0.87 ms at n = 24, instruction-bound at 8 % of the HBM peak.
+template <int NMAX>
 __global__ void __launch_bounds__(FS_PX * 14) smooth_fused_kernel(const float* __restrict__ s2, int n, int64_t HW, const __grid_constant__ TMat Mk,
                                                                   float* __restrict__ monthly /*[12][HW][14] or null*/,
                                                                   float* __restrict__ quarterly /*[4][HW][14] or null*/) {
-  extern __shared__ __align__(128) float fs_smem[];                  // 2 stages x [n][FS_PX][10]
+  extern __shared__ __align__(128) float fs_smem[];                  // 2 stages x [n][FS_PX][10], then the index tile [n][FS_PX][4]
   __shared__ __align__(8) uint64_t bars[2];
   const int tid = threadIdx.x, px = tid / 14, ch = tid - px * 14;
   const int64_t ntiles = (HW + FS_PX - 1) / FS_PX;
   const uint32_t stage_floats = (uint32_t)n * FS_PX * 10;
+  float4* idx_sm = reinterpret_cast<float4*>(fs_smem + 2 * (size_t)stage_floats);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fs_smem_u32(&bars[0])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fs_smem_u32(&bars[1])));
@@ -188,21 +197,32 @@ __global__ void __launch_bounds__(FS_PX * 14) smooth_fused_kernel(const float* _
     fs_mbar_wait(fs_smem_u32(&bars[stage]), phase[stage]);
     phase[stage] ^= 1;
     const float* sm = fs_smem + (size_t)stage * stage_floats;
-    const int64_t p = tile * FS_PX + px;
-    if (p < HW) {
+    const int64_t p0 = tile * FS_PX;
+    const int npx = (int)((HW - p0) < FS_PX ? (HW - p0) : FS_PX);
+    // ---- phase A: indices of every (date, pixel) of the tile ----
+    for (int i = tid; i < n * FS_PX; i += FS_PX * 14) {
+      const int q = i & (FS_PX - 1);
+      if (q < npx) {
+        const float* x = sm + (size_t)i * 10;
+        idx_sm[i] = make_float4(idx_evi(x[0], x[1], x[2], x[3]), idx_bi(x[0], x[2], x[3], x[8]), idx_msavi2(x[2], x[3]), idx_grndvi(x[1], x[2], x[3]));
+      }
+    }
+    __syncthreads();
+    // ---- phase B: 12 months (and the quarterly medians) of channel ch of pixel px ----
+    if (px < npx) {
+      const int64_t p = p0 + px;
+      float v[NMAX];
+#pragma unroll
+      for (int t = 0; t < NMAX; ++t)
+        v[t] = (t < n) ? (ch < 10 ? sm[((size_t)t * FS_PX + px) * 10 + ch] : reinterpret_cast<const float*>(idx_sm)[((size_t)t * FS_PX + px) * 4 + (ch - 10)]) : 0.f;
       float acc[12];
 #pragma unroll
-      for (int o = 0; o < 12; ++o) acc[o] = 0.f;
-      for (int t = 0; t < n; ++t) {
-        const float* x = sm + ((size_t)t * FS_PX + px) * 10;
-        float v;
-        if (ch < 10) v = x[ch];
-        else if (ch == 10) v = idx_evi(x[0], x[1], x[2], x[3]);
-        else if (ch == 11) v = idx_bi(x[0], x[2], x[3], x[8]);
-        else if (ch == 12) v = idx_msavi2(x[2], x[3]);
-        else v = idx_grndvi(x[1], x[2], x[3]);
+      for (int o = 0; o < 12; ++o) {
+        float a = 0.f;
 #pragma unroll
-        for (int o = 0; o < 12; ++o) acc[o] = fmaf(Mk.m[o * 32 + t], v, acc[o]);
+        for (int t = 0; t < NMAX; ++t)
+          if (t < n) a = fmaf(Mk.m[o * 32 + t], v[t], a);            // same sequential fma order over the dates as temporal_matmul_kernel
+        acc[o] = a;
       }
       if (monthly) {
 #pragma unroll
@@ -216,7 +236,7 @@ __global__ void __launch_bounds__(FS_PX * 14) smooth_fused_kernel(const float* _
         }
       }
     }
-    __syncthreads();                                                 // every thread is done with `stage` before it is refilled
+    __syncthreads();                                                 // every thread is done with `stage` and the index tile
     stage ^= 1;
   }
 }
@@ -227,16 +247,26 @@ int pre_smooth_fused_dev(stc_ctx* ctx, const float* s2_dev, const float* M_host,
   TMat Mk; memset(&Mk, 0, sizeof(Mk));
   for (int o = 0; o < 12; ++o)
     for (int t = 0; t < n; ++t) Mk.m[o * 32 + t] = M_host[o * n + t];
-  const size_t smem = (size_t)2 * n * FS_PX * 40;
+  const size_t smem = (size_t)2 * n * FS_PX * 40 + (size_t)n * FS_PX * 16;
   static bool attr_set = false;
-  if (!attr_set) { STC_CUDA(cudaFuncSetAttribute(smooth_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * FS_PX * 40)); attr_set = true; }
+  if (!attr_set) {
+    const int cap = 2 * 32 * FS_PX * 40 + 32 * FS_PX * 16;
+    STC_CUDA(cudaFuncSetAttribute(smooth_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    STC_CUDA(cudaFuncSetAttribute(smooth_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    STC_CUDA(cudaFuncSetAttribute(smooth_fused_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    STC_CUDA(cudaFuncSetAttribute(smooth_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    attr_set = true;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (HW + FS_PX - 1) / FS_PX;
-  const int per_sm = smem <= 36 * 1024 ? 4 : smem <= 56 * 1024 ? 3 : 2;          // resident CTAs by shared memory (448 threads each)
+  const int per_sm = smem <= 50 * 1024 ? 4 : smem <= 72 * 1024 ? 3 : 2;          // resident CTAs by shared memory (448 threads each)
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sms * per_sm);
   { TraceScope ts_(ctx, "smooth_fused_kernel");
-    smooth_fused_kernel<<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev); }
+    if (n <= 8) smooth_fused_kernel<8><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev);
+    else if (n <= 16) smooth_fused_kernel<16><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev);
+    else if (n <= 24) smooth_fused_kernel<24><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev);
+    else smooth_fused_kernel<32><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev); }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;
