@@ -82,7 +82,11 @@ int stc_trace(stc_ctx* ctx, int enable, const char* csv_path);
  *      x: frames 0..T-1 sequence, frame T the median frame (pb:strided_slice,
  *      pb:strided_slice_1).  `length` is the uniform sequence length
  *      (np.full(B, args.length), :354).  If normalize != 0, normalize_subtile
- *      (:316-325) is applied first with min17/max17.  out: [B,H-14,W-14]. ---- */
+ *      (:316-325) is applied first with min17/max17.  out: [B,H-14,W-14].
+ *      Limits (STC_ERR_ARG otherwise): H == W (the released graphs are square: 76 / 124 / 172 / 220), H a multiple of 4,
+ *      H >= 28, 1 <= length <= T.  The patch entry points (stc_predict_patches_*) take 12 months x 13 bands, H == W.
+ *      Date-axis limit of the preprocessing entry points: n <= 32 dates per tile (registers hold a pixel's time series;
+ *      the reference has no limit, its date selection leaves <= 24). ---- */
 int stc_predict_host(stc_ctx* ctx, const float* x_host, int B, int T, int H, int W, int length,
                      int normalize, const double* min17, const double* max17, float* out_host);
 /* Same forward, additionally returning the two feature taps of the --gen_feats path

@@ -161,16 +161,15 @@ __device__ __forceinline__ void fs_mbar_wait(uint32_t bar, uint32_t parity) {
 template <int NMAX>
 __global__ void __launch_bounds__(FS_PX * 14) smooth_fused_kernel(const float* __restrict__ s2, int n, int64_t HW, const __grid_constant__ TMat Mk,
                                                                   float* __restrict__ monthly /*[12][HW][14] or null*/,
-                                                                  float* __restrict__ quarterly /*[4][HW][14] or null*/) {
-  extern __shared__ __align__(128) float fs_smem[];                  // 2 stages x [n][FS_PX][10], then the index tile [n][FS_PX][4]
-  __shared__ __align__(8) uint64_t bars[2];
+                                                                  float* __restrict__ quarterly /*[4][HW][14] or null*/, int stages) {
+  extern __shared__ __align__(128) float fs_smem[];                  // `stages` x [n][FS_PX][10], then the index tile [n][FS_PX][4]
+  __shared__ __align__(8) uint64_t bars[4];
   const int tid = threadIdx.x, px = tid / 14, ch = tid - px * 14;
   const int64_t ntiles = (HW + FS_PX - 1) / FS_PX;
   const uint32_t stage_floats = (uint32_t)n * FS_PX * 10;
-  float4* idx_sm = reinterpret_cast<float4*>(fs_smem + 2 * (size_t)stage_floats);
+  float4* idx_sm = reinterpret_cast<float4*>(fs_smem + (size_t)stages * stage_floats);
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fs_smem_u32(&bars[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fs_smem_u32(&bars[1])));
+    for (int q = 0; q < stages; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fs_smem_u32(&bars[q])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -188,14 +187,17 @@ __global__ void __launch_bounds__(FS_PX * 14) smooth_fused_kernel(const float* _
     }
   };
   int64_t tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) issue(tile, 0);
-  uint32_t phase[2] = {0, 0};
+  if (tid == 0)                                                      // prologue: stages - 1 tiles in flight (copy latency > one tile's arithmetic at small n)
+    for (int q = 0; q < stages - 1; ++q)
+      if (tile + (int64_t)q * gridDim.x < ntiles) issue(tile + (int64_t)q * gridDim.x, q);
+  uint32_t phase_bits = 0;
   int stage = 0;
   for (; tile < ntiles; tile += gridDim.x) {
-    const int64_t next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) issue(next, stage ^ 1);           // the other stage was released by the barrier below
-    fs_mbar_wait(fs_smem_u32(&bars[stage]), phase[stage]);
-    phase[stage] ^= 1;
+    const int64_t ahead = tile + (int64_t)(stages - 1) * gridDim.x;
+    const int astage = stage == 0 ? stages - 1 : stage - 1;          // the stage consumed in the previous iteration (released by its barrier)
+    if (tid == 0 && ahead < ntiles) issue(ahead, astage);
+    fs_mbar_wait(fs_smem_u32(&bars[stage]), (phase_bits >> stage) & 1u);
+    phase_bits ^= 1u << stage;
     const float* sm = fs_smem + (size_t)stage * stage_floats;
     const int64_t p0 = tile * FS_PX;
     const int npx = (int)((HW - p0) < FS_PX ? (HW - p0) : FS_PX);
@@ -231,13 +233,16 @@ __global__ void __launch_bounds__(FS_PX * 14) smooth_fused_kernel(const float* _
       if (quarterly) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          float m3[3] = {acc[3 * k], acc[3 * k + 1], acc[3 * k + 2]};
-          quarterly[((int64_t)k * HW + p) * 14 + ch] = median_n<3>(m3, 3);
+          const float a0 = acc[3 * k], a1 = acc[3 * k + 1], a2 = acc[3 * k + 2];
+          float md;
+          if (a0 == a0 && a1 == a1 && a2 == a2) md = med3(a0, a1, a2);          // min / max network: registers only
+          else { float m3[3] = {a0, a1, a2}; md = median_n<3>(m3, 3); }          // NaN present: the insertion sort's order (same as the separate kernel)
+          quarterly[((int64_t)k * HW + p) * 14 + ch] = md;
         }
       }
     }
     __syncthreads();                                                 // every thread is done with `stage` and the index tile
-    stage ^= 1;
+    stage = stage + 1 == stages ? 0 : stage + 1;
   }
 }
 
@@ -247,10 +252,13 @@ int pre_smooth_fused_dev(stc_ctx* ctx, const float* s2_dev, const float* M_host,
   TMat Mk; memset(&Mk, 0, sizeof(Mk));
   for (int o = 0; o < 12; ++o)
     for (int t = 0; t < n; ++t) Mk.m[o * 32 + t] = M_host[o * n + t];
-  const size_t smem = (size_t)2 * n * FS_PX * 40 + (size_t)n * FS_PX * 16;
+  const size_t stage_bytes = (size_t)n * FS_PX * 40, idx_bytes = (size_t)n * FS_PX * 16;
+  int stages = (int)((100 * 1024 - idx_bytes) / stage_bytes);                 // two CTAs per SM (registers) share ~227 KB
+  stages = stages < 2 ? 2 : (stages > 4 ? 4 : stages);
+  const size_t smem = stages * stage_bytes + idx_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    const int cap = 2 * 32 * FS_PX * 40 + 32 * FS_PX * 16;
+    const int cap = 4 * 32 * FS_PX * 40 + 32 * FS_PX * 16;
     STC_CUDA(cudaFuncSetAttribute(smooth_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     STC_CUDA(cudaFuncSetAttribute(smooth_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     STC_CUDA(cudaFuncSetAttribute(smooth_fused_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
@@ -260,13 +268,20 @@ int pre_smooth_fused_dev(stc_ctx* ctx, const float* s2_dev, const float* M_host,
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (HW + FS_PX - 1) / FS_PX;
-  const int per_sm = smem <= 50 * 1024 ? 4 : smem <= 72 * 1024 ? 3 : 2;          // resident CTAs by shared memory (448 threads each)
-  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sms * per_sm);
+  int per_sm = 2;                                             // resident CTAs per SM (registers: 61 x 448 -> 2; shared memory at small n allows more)
+  {
+    cudaError_t e = n <= 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smooth_fused_kernel<8>, FS_PX * 14, smem)
+                  : n <= 16 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smooth_fused_kernel<16>, FS_PX * 14, smem)
+                  : n <= 24 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smooth_fused_kernel<24>, FS_PX * 14, smem)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smooth_fused_kernel<32>, FS_PX * 14, smem);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  }
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sms * per_sm);          // one wave of persistent CTAs
   { TraceScope ts_(ctx, "smooth_fused_kernel");
-    if (n <= 8) smooth_fused_kernel<8><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev);
-    else if (n <= 16) smooth_fused_kernel<16><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev);
-    else if (n <= 24) smooth_fused_kernel<24><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev);
-    else smooth_fused_kernel<32><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev); }
+    if (n <= 8) smooth_fused_kernel<8><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev, stages);
+    else if (n <= 16) smooth_fused_kernel<16><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev, stages);
+    else if (n <= 24) smooth_fused_kernel<24><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev, stages);
+    else smooth_fused_kernel<32><<<grid, FS_PX * 14, smem, ctx->stream>>>(s2_dev, n, HW, Mk, monthly_dev, quarterly_dev, stages); }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;

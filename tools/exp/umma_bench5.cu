@@ -112,8 +112,9 @@ static void sweep(long long* d) {
 int main() {
   long long* d; cudaMalloc(&d, 148 * 4 * 8);
   sweep<32>(d); sweep<64>(d); sweep<128>(d);
-  run<256, 1>(1, 0, 0, 8320, "aligned", d);
-  run<256, 1>(1, 170, 1, 13696, "v2", d);
+  // N = 256 rows removed: this harness sizes one shared-memory B tile for N <= 128 (32 * N bytes per K-step overflows the
+  // staging area at N = 256 -> illegal address, the last line of the round-1 log); the production kernel's N = 256 instantiation
+  // (conv2) has its own geometry and is measured in profiles/r02_launches_bench.md instead.
   run<16, 4>(1, 0, 0, 8320, "aligned", d);
   run<16, 4>(1, 170, 1, 13696, "v2", d);
   return 0;
