@@ -96,11 +96,11 @@ def test_adjust_shape_plan_matches_reference():
             assert np.array_equal(got2, want2), (L, target)
 
 
-def _mirror_chain(sess, store, root, seed):
+def _mirror_chain(sess, store, root, seed, forest=None, urban=None):
     from sentinel_tree_cover_b200 import api, tile
     random.seed(seed)
     s2, dates, interp, s1, dem, cloudshad, snow = tile.process_tile(1, 2, None, "/nonexistent/", [0, 0, 1, 1], make_shadow=True, sess=sess,
-                                                                    loader=store.load, exists=store.exists)
+                                                                    loader=store.load, exists=store.exists, forest_mask=forest, urban_mask=urban)
     s2 = api.superresolve_large_tile(np.ascontiguousarray(s2), sess)
     tile.process_subtiles(1, 2, s2, dates, interp, s1, dem, sess, [0, 0, 1, 1], 158, None, local_path=root, length=4)
     path = root + "1/2/processed/"
@@ -151,3 +151,30 @@ def test_gpu_tile_chain_is_repeatable_and_pooled(sess):
     assert np.array_equal(a, b) and np.array_equal(ka, kb)
     assert after["misses"] == before["misses"], (before, after)
     assert 0 < (a <= 100).mean() <= 1
+
+
+@pytest.mark.gpu
+def test_gpu_tile_chain_with_ancillary_rasters_matches_stage_mirrors(sess, tmp_path):
+    """The forest / urban rasters set on the session (stc_set_ancillary_masks_host) reach the cloud masks of the one-call chain
+    exactly as they reach the stage mirror (process_tile(forest_mask=, urban_mask=)), and they change the result."""
+    from sentinel_tree_cover_b200 import api
+    raw = tile_ref.synth_raw_tile(25, n=7, h=170, w=170)
+    store = tile_ref.FakeStore(raw)
+    H = W = 340
+    r = np.random.default_rng(8)
+    frst = np.zeros((22, 22), bool); frst[:9] = True
+    urb = np.zeros((22, 22), bool); urb[4:10, 10:18] = r.random((6, 8)) < 0.7
+    forest, urban = api.ancillary_masks_from_rasters(frst, urb, (H, W))
+    want, want_dates, _, want_state = _mirror_chain(sess, store, str(tmp_path) + "/a/", 4, forest, urban)
+    plain, _, _, _ = _mirror_chain(sess, store, str(tmp_path) + "/b/", 4)
+    sess.set_ancillary_masks(forest, urban, (H, W))
+    try:
+        random.seed(4)
+        got, kept = sess.run_tile(raw["s2_10"], raw["s2_20"], raw["s1"], raw["dem"], raw["s2_dates"])
+    finally:
+        sess.set_ancillary_masks(None, None)
+    assert np.array_equal(kept, want_dates) and random.getstate() == want_state
+    assert np.array_equal(got, want)
+    random.seed(4)
+    again, _ = sess.run_tile(raw["s2_10"], raw["s2_20"], raw["s1"], raw["dem"], raw["s2_dates"])
+    assert np.array_equal(again, plain)                              # masks cleared: back to the shipped configuration
