@@ -423,6 +423,13 @@ int stc_region_blend_dev(stc_ctx* ctx, const float* preds_dev, int r_first, int 
  * column `seam_col` = SIZE // 2 + 7.  applied_out [T] (optional): 1 where the transform was kept. */
 int stc_align_histograms_host(stc_ctx* ctx, float* arr_host, int T, int H, int W, int C, int half, int seam_col, int32_t* applied_out);
 
+/* ---- exact order statistics (the building block under every np.median / np.percentile of the path:
+ * cloud_removal.py:455-467, 598-677, 1458-1481; download_and_predict_job.py:702-705) ----
+ * data: row-major [rows][ld] float32, the first `cols` (<= 16) entries of a row are the columns.  For every column c:
+ * out[2c] = the value of 0-based rank ks[c] in sorted order, out[2c + 1] = the value of rank ks[c] + 1 (repeats out[2c] at
+ * the last rank).  NaN sorts last.  Bit-exact (the values are elements of the input); three passes over the data. */
+int stc_order_stats_host(stc_ctx* ctx, const float* data, int64_t rows, int cols, int64_t ld, const int32_t* ks, float* out);
+
 #ifdef __cplusplus
 }
 #endif

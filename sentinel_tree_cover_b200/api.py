@@ -121,6 +121,7 @@ SYMBOLS = [
     ("stc_py_shuffle", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     ("stc_malloc_host_flags", C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     ("stc_align_histograms_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("stc_order_stats_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     ("stc_set_ancillary_masks_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     ("stc_remove_clouds_clip_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
@@ -413,6 +414,21 @@ class StcSession:
             self._check(self.lib.stc_superresolve_host(self.h, _dptr(x), _dptr(b), N, H, W, _dptr(out)))
         return out
 
+
+    def order_stats(self, data, ks):
+        """Exact order statistics of the columns of `data` [rows, cols<=16] float32 (any row stride): returns [cols, 2] =
+        the values of 0-based rank ks[c] and ks[c] + 1 in sorted order (NaN last).  np.median / np.percentile are one
+        interpolation away from these (stc_order_stats_host)."""
+        a = np.asarray(data, np.float32)
+        if a.ndim == 1:
+            a = a[:, None]
+        if a.strides[1] != 4 or a.strides[0] % 4 or a.strides[0] < 4 * a.shape[1]:
+            a = np.ascontiguousarray(a)
+        rows, cols = a.shape
+        k = np.ascontiguousarray(np.broadcast_to(np.asarray(ks, np.int32), (cols,)))
+        out = np.empty((cols, 2), np.float32)
+        self._check(self.lib.stc_order_stats_host(self.h, C.c_void_p(a.ctypes.data), rows, cols, a.strides[0] // 4, _dptr(k), _dptr(out)))
+        return out
 
     def to_float32(self, arr_u16):
         a = np.ascontiguousarray(arr_u16, np.uint16)

@@ -93,35 +93,40 @@ __global__ void __launch_bounds__(128) k_mosaic_prep(const float* __restrict__ t
   divisor[p] = d;
 }
 
-// reference image of date i = i0 + blockIdx.y: mean of the other dates over pixels usable for both (:598-616);
-// ref / flag are per-date slabs ([n][HW][10], [n][HW]) so that all dates run in one launch
-__global__ void __launch_bounds__(128) k_mosaic_ref(const float* __restrict__ tiles, const float* __restrict__ areas,
+// Reference image of every date i >= i0: mean of the OTHER dates over the pixels usable for both (:598-616), summed in date
+// order.  One thread per (pixel, band) keeps the band's values of all dates in registers and forms the n ordered sums from
+// them, so the cube is read once (the per-date version re-read it for every date: n^2 * HW * 40 bytes, 1.7 ms at n = 24).
+// ref / flag are per-date slabs ([n][HW][10], [n][HW]).
+__global__ void __launch_bounds__(256) k_mosaic_ref(const float* __restrict__ tiles, const float* __restrict__ areas,
                                                     const unsigned char* __restrict__ water, int n, int HW, int i0,
                                                     float* __restrict__ ref_all, unsigned char* __restrict__ flag_all) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
-  const int i = i0 + blockIdx.y;
-  float* ref = ref_all + (int64_t)i * HW * 10;
-  unsigned char* flag = flag_all + (int64_t)i * HW;
-  bool ok = (areas[(int64_t)i * HW + p] < 0.25f) && !water[p];
-  float s[10]; float cnt = 0.f;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)HW * 10) return;
+  const int p = (int)(e / 10), c = (int)(e - (int64_t)p * 10);
+  float x[CF_MAX_DATES];
+  unsigned use = 0, lowa = 0;                       // bit b: areas[b] < 1 (contributes), areas[b] < 0.25 (gets a reference)
 #pragma unroll
-  for (int c = 0; c < 10; ++c) s[c] = 0.f;
-  if (ok) {
-    for (int b = 0; b < n; ++b) {
-      if (b == i || !(areas[(int64_t)b * HW + p] < 1.f)) continue;
-      const float* x = tiles + ((int64_t)b * HW + p) * 10;
-#pragma unroll
-      for (int c = 0; c < 10; ++c) s[c] = __fadd_rn(s[c], x[c]);
-      cnt = __fadd_rn(cnt, 1.f);
+  for (int b = 0; b < CF_MAX_DATES; ++b) {
+    x[b] = 0.f;
+    if (b < n) {
+      x[b] = tiles[(int64_t)b * HW * 10 + e];
+      const float a = areas[(int64_t)b * HW + p];
+      use |= (a < 1.f) ? (1u << b) : 0u;
+      lowa |= (a < 0.25f) ? (1u << b) : 0u;
     }
   }
-  ok = ok && cnt > 0.f;
-  if (ok) {
+  const bool land = !water[p];
+  for (int i = i0; i < n; ++i) {
+    const unsigned others = use & ~(1u << i);
+    const bool ok = land && ((lowa >> i) & 1u) && others;
+    if (ok) {
+      float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < 10; ++c) ref[(int64_t)p * 10 + c] = __fdiv_rn(s[c], cnt);
+      for (int b = 0; b < CF_MAX_DATES; ++b) if ((others >> b) & 1u) s = __fadd_rn(s, x[b]);
+      ref_all[(int64_t)i * HW * 10 + e] = __fdiv_rn(s, (float)__popc(others));
+    }
+    if (c == 0) flag_all[(int64_t)i * HW + p] = ok;
   }
-  flag[p] = ok;
 }
 
 // order-preserving compaction positions of a flag image: pos[p] = rank of p among flagged pixels; total -> *count
@@ -348,11 +353,20 @@ __device__ __forceinline__ float snow_prob(const float* x) {
   if (__fdiv_rn(x[0], x[2]) < 0.75f) p = 0.f;
   return p;
 }
-__global__ void __launch_bounds__(256) k_snow_mean(const float* __restrict__ tiles, int n, int HW, float* __restrict__ snow) {
+// Mean snow probability over the dates (:505-511), recomputed for every fitted date because the blend of the previous date
+// changed its tile.  The per-date probabilities are kept as planes sp[t][p]: k_snow_planes fills them once, the blend
+// refreshes the pixels it rewrites, and the per-date mean adds n floats per pixel in date order instead of re-reading the
+// whole cube (same float32 sum order, identical results).
+__global__ void __launch_bounds__(256) k_snow_planes(const float* __restrict__ tiles, int n, int HW, float* __restrict__ sp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * HW) return;
+  sp[i] = snow_prob(tiles + i * 10);
+}
+__global__ void __launch_bounds__(256) k_snow_mean(const float* __restrict__ sp, int n, int HW, float* __restrict__ snow) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   float s = 0.f;
-  for (int t = 0; t < n; ++t) { float v = snow_prob(tiles + ((int64_t)t * HW + p) * 10); s = t ? __fadd_rn(s, v) : v; }
+  for (int t = 0; t < n; ++t) { float v = sp[(int64_t)t * HW + p]; s = t ? __fadd_rn(s, v) : v; }
   snow[p] = (float)((double)s / (double)n);
 }
 
@@ -436,51 +450,111 @@ __global__ void __launch_bounds__(1024) k_bucket_lists(const BucketJob* __restri
 
 // float64 Gram sums over the sampled rows.  Features u_j = [mosaic bands, snow], c_j = clip(u_j, 0.005, 1)
 // for j < 10 (c_10 = u_10), targets y_b = tile bands of the row's (date, pixel).
-// acc layout (583 doubles): UU[11][11], CU[11][11] (c_j * u_k), CC[11][11], UY[11][10], CY[11][10].
+// gram layout (583 doubles): UU[11][11], CU[11][11] (c_j * u_k), CC[11][11], UY[11][10], CY[11][10].
+//
+// Two kernels.  k_gram_rows follows the sample -> row -> (date, pixel) indirection once, with the whole GPU, and writes the
+// row z = [u0..u10 | c0..c9 | y0..y9 | 0] (32 floats) of every sampled row.  k_gram then forms z_a * z_b for a < 24, all b:
+// one WARP per partial sum, each lane a 6 x 4 register tile (5 shared-memory loads per 24 FMAs; the round-1 kernel spent its
+// time on two loads and two float->double conversions per FMA: 206 us per date).  Every entry is still accumulated in row
+// order over the warp's 64-row groups (group g of partial b = rows [64 (b + g P), +64)), and the P partials are added in
+// order, so the sums do not depend on the schedule.
 #define GRAM_N (3 * NF * NF + 2 * NF * 10)
 #define GRAM_ROWS 64
-__global__ void __launch_bounds__(640) k_gram(const float* __restrict__ tiles, const float* __restrict__ mosaic, const float* __restrict__ snow,
-                                              const int* __restrict__ rowsrc, const int* __restrict__ sample, int S, int HW,
-                                              double* __restrict__ partial /*[grid][GRAM_N]*/) {
-  __shared__ float u[GRAM_ROWS][NF], c[GRAM_ROWS][NF], y[GRAM_ROWS][10];
-  const int q = threadIdx.x;
-  int kind = -1, j = 0, k = 0;
-  if (q < 3 * NF * NF) { kind = q / (NF * NF); j = (q % (NF * NF)) / NF; k = q % NF; }
-  else if (q < GRAM_N) { int r = q - 3 * NF * NF; kind = 3 + r / (NF * 10); j = (r % (NF * 10)) / 10; k = r % 10; }
-  double acc = 0.0;
-  for (int s0 = blockIdx.x * GRAM_ROWS; s0 < S; s0 += gridDim.x * GRAM_ROWS) {
-    const int rows = (S - s0) < GRAM_ROWS ? (S - s0) : GRAM_ROWS;
-    __syncthreads();
-    for (int e = threadIdx.x; e < rows * 21; e += blockDim.x) {
-      int r = e / 21, f = e % 21;
-      int src = rowsrc[sample[s0 + r]];
-      int p = src % HW;
-      if (f < 10) { float v = mosaic[(int64_t)p * 10 + f]; u[r][f] = v; c[r][f] = fminf(fmaxf(v, 0.005f), 1.f); }
-      else if (f == 10) { float v = snow[p]; u[r][10] = v; c[r][10] = v; }
-      else y[r][f - 11] = tiles[(int64_t)src * 10 + (f - 11)];
+#define GRAM_ZW 32                      // floats per staged row
+#define GRAM_PA 24                      // a-side entries computed per row (21 needed)
+#define GRAM_P (GRAM_PA * GRAM_ZW)      // products per partial
+__global__ void __launch_bounds__(256) k_gram_rows(const float* __restrict__ tiles, const float* __restrict__ mosaic, const float* __restrict__ snow,
+                                                   const int* __restrict__ rowsrc, const int* __restrict__ sample, int S, int HW,
+                                                   float* __restrict__ Z /*[S][32]*/) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t s = e >> 5;
+  const int f = (int)(e & 31);
+  if (s >= S) return;
+  const int src = rowsrc[sample[s]];
+  const int p = src % HW;
+  float v = 0.f;
+  if (f < 10) v = mosaic[(int64_t)p * 10 + f];
+  else if (f == 10) v = snow[p];
+  else if (f < 21) v = fminf(fmaxf(mosaic[(int64_t)p * 10 + (f - 11)], 0.005f), 1.f);
+  else if (f < 31) v = tiles[(int64_t)src * 10 + (f - 21)];
+  Z[e] = v;
+}
+__global__ void __launch_bounds__(64) k_gram(const float* __restrict__ Z, int S, int nparts, double* __restrict__ partial /*[nparts][GRAM_P]*/) {
+  __shared__ __align__(16) double zs[2][32][GRAM_ZW];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int part = blockIdx.x * 2 + w;
+  if (part >= nparts) return;                       // warps are independent: only __syncwarp below
+  double (*zz)[GRAM_ZW] = zs[w];
+  const int a0 = (lane >> 3) * 6, b0 = (lane & 7) * 4;
+  double acc[6][4];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  // sub-batches of 32 rows; the next one is in flight (registers) while this one is multiplied
+  float4 pre[8];
+  auto rows_of = [&](int t, int64_t& s) { s = ((int64_t)part + (int64_t)(t >> 1) * nparts) * GRAM_ROWS + (t & 1) * 32; const int64_t left = (int64_t)S - s; return (int)(left < 32 ? (left < 0 ? 0 : left) : 32); };
+  auto fetch = [&](int64_t s, int rr) {
+    const float4* src = reinterpret_cast<const float4*>(Z + s * GRAM_ZW);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int i = lane + 32 * k; pre[k] = (i < rr * 8) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f); }
+  };
+  int t = 0; int64_t s; int rr = rows_of(0, s);
+  if (rr > 0) fetch(s, rr);
+  while (rr > 0) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = lane + 32 * k, r = i >> 3, c = (i & 7) * 4;
+      *reinterpret_cast<double2*>(&zz[r][c]) = make_double2((double)pre[k].x, (double)pre[k].y);
+      *reinterpret_cast<double2*>(&zz[r][c + 2]) = make_double2((double)pre[k].z, (double)pre[k].w);
     }
-    __syncthreads();
-    if (kind >= 0) {
-      for (int r = 0; r < rows; ++r) {
-        double a, b;
-        switch (kind) {
-          case 0: a = u[r][j]; b = u[r][k]; break;
-          case 1: a = c[r][j]; b = u[r][k]; break;
-          case 2: a = c[r][j]; b = c[r][k]; break;
-          case 3: a = u[r][j]; b = y[r][k]; break;
-          default: a = c[r][j]; b = y[r][k]; break;
-        }
-        acc += a * b;
-      }
+    __syncwarp();
+    const int cur = rr;
+    // the second half of a 64-row group may be empty while later groups are not needed either: S is the global end
+    ++t; rr = rows_of(t, s);
+    if (rr == 0 && (t & 1)) { ++t; rr = rows_of(t, s); }
+    if (rr > 0) fetch(s, rr);
+#pragma unroll 2
+    for (int r = 0; r < cur; ++r) {
+      double a[6], b[4];
+      const double2 a01 = *reinterpret_cast<const double2*>(&zz[r][a0]), a23 = *reinterpret_cast<const double2*>(&zz[r][a0 + 2]),
+                    a45 = *reinterpret_cast<const double2*>(&zz[r][a0 + 4]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&zz[r][b0]), b23 = *reinterpret_cast<const double2*>(&zz[r][b0 + 2]);
+      a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y; a[4] = a45.x; a[5] = a45.y;
+      b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);       // the product of two floats is exact in double
     }
   }
-  if (kind >= 0) partial[(int64_t)blockIdx.x * GRAM_N + q] = acc;
+  double* out = partial + (int64_t)part * GRAM_P;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[(a0 + i) * GRAM_ZW + b0 + j] = acc[i][j];
 }
-__global__ void __launch_bounds__(640) k_gram_reduce(const double* __restrict__ partial, int nblk, double* __restrict__ gram) {
-  int q = threadIdx.x;
+// gram[q] = sum over the partials, in order; q -> (a, b) of the staged row (c_10 is u_10)
+__global__ void __launch_bounds__(640) k_gram_reduce(const double* __restrict__ partial, int nparts, double* __restrict__ gram) {
+  const int q = threadIdx.x;
   if (q >= GRAM_N) return;
+  int kind, j, k;
+  if (q < 3 * NF * NF) { kind = q / (NF * NF); j = (q % (NF * NF)) / NF; k = q % NF; }
+  else { const int r = q - 3 * NF * NF; kind = 3 + r / (NF * 10); j = (r % (NF * 10)) / 10; k = r % 10; }
+  const int cj = j < 10 ? 11 + j : 10, ck = k < 10 ? 11 + k : 10;      // position of c_j / c_k in the staged row
+  int a, b;
+  switch (kind) {
+    case 0: a = j; b = k; break;                 // u_j u_k
+    case 1: a = cj; b = k; break;                // c_j u_k
+    case 2: a = cj; b = ck; break;               // c_j c_k
+    case 3: a = j; b = 21 + k; break;            // u_j y_k
+    default: a = cj; b = 21 + k; break;          // c_j y_k
+  }
+  const double* src = partial + a * GRAM_ZW + b;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += partial[(int64_t)b * GRAM_N + q];
+#pragma unroll 8
+  for (int p = 0; p < nparts; ++p) s += src[(int64_t)p * GRAM_P];
   gram[q] = s;
 }
 
@@ -558,7 +632,7 @@ __global__ void k_nnls(const double* __restrict__ gram, int S, double* __restric
 // tiles[d] = tiles[d]*(1-a) + fill*a with fill = regression prediction from [mosaic, snow] (use_coef) or the mosaic itself
 __global__ void __launch_bounds__(256) k_predict_blend(float* __restrict__ tiles_d, const float* __restrict__ area_d,
                                                        const float* __restrict__ mosaic, const float* __restrict__ snow,
-                                                       const double* __restrict__ coef, int use_coef, int HW) {
+                                                       const double* __restrict__ coef, int use_coef, int HW, float* __restrict__ sp_d) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   const float a = area_d[p];
@@ -578,6 +652,7 @@ __global__ void __launch_bounds__(256) k_predict_blend(float* __restrict__ tiles
     float* x = tiles_d + (int64_t)p * 10 + b;
     *x = __fadd_rn(__fmul_rn(*x, om), __fmul_rn(fill, a));
   }
+  if (sp_d) sp_d[p] = snow_prob(tiles_d + (int64_t)p * 10);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -688,7 +763,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
     cf_t = t;
   };
   DBuf d_ta, d_tb, d_sums, d_water0, d_water1, d_flag, d_u8a, d_u8b, d_pf, d_ref, d_pos, d_src_rows,
-      d_ref_rows, d_mosaic, d_div, d_snow, d_partial, d_gram, d_coef, d_status, d_qout,
+      d_ref_rows, d_mosaic, d_div, d_snow, d_partial, d_gramz, d_gram, d_coef, d_status, d_qout,
       d_sd, d_params, d_cnt, d_counts;
   const int gram_blocks = 296;
   STC_CUDA(stc_dmalloc(&d_ta.p, N * 4)); STC_CUDA(stc_dmalloc(&d_tb.p, N * 4)); STC_CUDA(stc_dmalloc(&d_sums.p, CF_MAX_DATES * 4));
@@ -696,7 +771,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   STC_CUDA(stc_dmalloc(&d_ref.p, (int64_t)HW * 40)); STC_CUDA(stc_dmalloc(&d_pos.p, (int64_t)HW * 4));
   STC_CUDA(stc_dmalloc(&d_src_rows.p, (int64_t)HW * 40)); STC_CUDA(stc_dmalloc(&d_ref_rows.p, (int64_t)HW * 40));
   STC_CUDA(stc_dmalloc(&d_mosaic.p, (int64_t)HW * 40)); STC_CUDA(stc_dmalloc(&d_div.p, (int64_t)HW * 4)); STC_CUDA(stc_dmalloc(&d_snow.p, (int64_t)HW * 4));
-  STC_CUDA(stc_dmalloc(&d_partial.p, (size_t)gram_blocks * GRAM_N * 8)); STC_CUDA(stc_dmalloc(&d_gram.p, GRAM_N * 8));
+  STC_CUDA(stc_dmalloc(&d_partial.p, (size_t)gram_blocks * GRAM_P * 8)); STC_CUDA(stc_dmalloc(&d_gram.p, GRAM_N * 8));
   STC_CUDA(stc_dmalloc(&d_coef.p, 10 * NF * 8)); STC_CUDA(stc_dmalloc(&d_status.p, 64));
   STC_CUDA(stc_dmalloc(&d_qout.p, 32 * 4));
   STC_CUDA(stc_dmalloc(&d_sd.p, 32 * 4)); STC_CUDA(stc_dmalloc(&d_params.p, 32 * 4)); STC_CUDA(stc_dmalloc(&d_cnt.p, 64));
@@ -738,6 +813,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   struct FitJob { int d, lo, hi, K; int64_t row0; int cnt[7]; int64_t list0[7]; };
   struct ShufTask { int j; int k; uint32_t mt[624]; int idx; };            // k in 0..6: list k; k == 7: the sample
   std::vector<int> counts(n * 5);
+  PyRandomProducer rng_ahead;                     // generates the walk's outputs on its own thread (stc_pyrandom.h); outlives rng's last use
   PyRandom rng; rng.import_state(mt_state, (int)mt_state[624]);
   std::vector<FitJob> fits;
   std::vector<int> fit_of(n, -1);
@@ -865,9 +941,15 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
         for (int k = 1; k <= 5; ++k) S += std::min(n_i, (size_t)f.cnt[k]);
         S_of[j] = S;
       }
+      {
+        size_t s_max = 1;
+        for (int j = 0; j < nf; ++j) s_max = std::max(s_max, std::min(S_of[j], (size_t)fits[j].K));
+        STC_CUDA(stc_dmalloc(&d_gramz.p, s_max * GRAM_ZW * 4));
+      }
       tt0 = cf_timing ? cf_now() : 0;
       auto walker = [&, this_n = n]() {
         size_t ti = 0;
+        rng.attach(&rng_ahead);
         for (int d = 0; d < n; ++d) {
           const int j = fit_of[d];
           if (j < 0) continue;
@@ -942,7 +1024,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   int start = 0;
   while (start < n) {
     const int m = n - start;
-    CF_LAUNCH(k_mosaic_ref, dim3(cdiv(HW, 128), m), 128, tiles, areas, water0, n, HW, start, d_refall.as<float>(), d_flagall.as<unsigned char>());
+    CF_LAUNCH(k_mosaic_ref, cdiv((int64_t)HW * 10, 256), 256, tiles, areas, water0, n, HW, start, d_refall.as<float>(), d_flagall.as<unsigned char>());
     if ((rc = scan_flags_dev(ctx, d_flagall.as<unsigned char>() + (int64_t)start * HW, m, HW, d_posall.as<int>() + (int64_t)start * HW,
                              d_Ks.as<int>() + start))) return rc;
     STC_CUDA(cudaMemcpyAsync(Ks.data() + start, d_Ks.as<int>() + start, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -989,12 +1071,16 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   // ---- 3. per-date alignment and blending (:939-959, :316-575) ----
   if (!fits_ready && (rc = prepare_fits())) return rc;
   if (nf > 0) {
+    DBuf d_sp;
+    STC_CUDA(stc_dmalloc(&d_sp.p, (size_t)n * HW * 4));
+    float* sp = d_sp.as<float>();
+    CF_LAUNCH(k_snow_planes, cdiv((int64_t)n * HW, 256), 256, tiles, n, HW, sp);
     for (int d = 0; d < n; ++d) {
       const int j = fit_of[d];
       if (j < 0) {
         if (counts[d * 5] > 0 && !(counts[d * 5 + 1] > 0))    // no clear pixel at all: the interpolated array stays the raw mosaic
           CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, (const float*)nullptr,
-                    d_coef.as<double>(), 0, HW);
+                    d_coef.as<double>(), 0, HW, sp + (int64_t)d * HW);
         continue;
       }
       const FitJob& f = fits[j];
@@ -1004,9 +1090,11 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       if (S > (size_t)f.K) S = (size_t)f.K;
       int* d_smp = d_sample_all.as<int>() + sample0[j];
       STC_CUDA(cudaMemcpyAsync(d_smp, smp, S * 4, cudaMemcpyHostToDevice, ctx->stream));
-      CF_LAUNCH(k_snow_mean, cdiv(HW, 256), 256, tiles, n, HW, d_snow.as<float>());
+      CF_LAUNCH(k_snow_mean, cdiv(HW, 256), 256, sp, n, HW, d_snow.as<float>());
       const int gb = std::min(gram_blocks, cdiv((int64_t)S, GRAM_ROWS));
-      CF_LAUNCH(k_gram, gb, 640, tiles, mosaic, d_snow.as<float>(), d_rows_all.as<int>() + f.row0, d_smp, (int)S, HW, d_partial.as<double>());
+      CF_LAUNCH(k_gram_rows, cdiv((int64_t)S * GRAM_ZW, 256), 256, tiles, mosaic, d_snow.as<float>(), d_rows_all.as<int>() + f.row0, d_smp, (int)S, HW,
+                d_gramz.as<float>());
+      CF_LAUNCH(k_gram, cdiv(gb, 2), 64, d_gramz.as<float>(), (int)S, gb, d_partial.as<double>());
       CF_LAUNCH(k_gram_reduce, 1, 640, d_partial.as<double>(), gb, d_gram.as<double>());
       CF_LAUNCH(k_nnls, 1, 32, d_gram.as<double>(), (int)S, d_coef.as<double>(), d_status_all.as<int>() + 10 * j);
       if (getenv("STC_CF_DEBUG")) {                        // test aid: fit inputs / coefficients of every date on stderr
@@ -1022,7 +1110,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
         for (int b = 0; b < 10; b += 8) { fprintf(stderr, "[cf_debug]   band %d coef", b); for (int q = 0; q < NF; ++q) fprintf(stderr, " %.6g", hc[b * NF + q]); fprintf(stderr, "\n"); }
       }
       CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, d_snow.as<float>(),
-                d_coef.as<double>(), 1, HW);
+                d_coef.as<double>(), 1, HW, sp + (int64_t)d * HW);
     }
     for (auto& t : pool) t.join();
     if (cf_timing) fprintf(stderr, "[remove_clouds]   generator walk %.1f ms (%lld elements), shuffles on %d host threads, all enqueued after %.1f ms\n",
@@ -1036,9 +1124,9 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
     for (int d = 0; d < n; ++d)
       if (counts[d * 5] > 0 && !(counts[d * 5 + 1] > 0))
         CF_LAUNCH(k_predict_blend, cdiv(HW, 256), 256, tiles + (int64_t)d * HW * 10, areas + (int64_t)d * HW, mosaic, (const float*)nullptr,
-                  d_coef.as<double>(), 0, HW);
+                  d_coef.as<double>(), 0, HW, (float*)nullptr);
   }
-  { int idx_out = 0; rng.export_state(mt_state, &idx_out); mt_state[624] = (uint32_t)idx_out; }
+  { int idx_out = 0; rng.export_state(mt_state, &idx_out); mt_state[624] = (uint32_t)idx_out; rng_ahead.stop(); }
 
   cf_mark("per-date alignment + blend");
   // ---- 4. residual clouds in the mosaic (:703-732) ----
@@ -1117,8 +1205,9 @@ extern "C" int stc_remove_clouds_clip_host(stc_ctx* ctx, float* tiles_host, cons
 // random.shuffle would with the generator state mt_state (624 words + position), and writes the advanced state back.
 extern "C" int stc_py_shuffle(uint32_t* mt_state, int32_t* data, int64_t n) {
   if (!mt_state || n < 0 || mt_state[624] > 624) return STC_ERR_ARG;
+  PyRandomProducer ahead;
   PyRandom rng; rng.import_state(mt_state, (int)mt_state[624]);
-  if (!data) rng.skip_shuffle((size_t)n);        // generator walk only (what remove_clouds does before it farms the shuffles out)
+  if (!data) { rng.attach(&ahead); rng.skip_shuffle((size_t)n); }     // generator walk only, fed by the producer thread: what remove_clouds does before it farms the shuffles out
   else rng.shuffle(data, (size_t)n);
   int idx_out = 0; rng.export_state(mt_state, &idx_out); mt_state[624] = (uint32_t)idx_out;
   return STC_OK;

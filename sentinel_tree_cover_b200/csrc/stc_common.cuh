@@ -50,6 +50,14 @@ struct ConvParams {
   int mode;
   int out_fp16;                 // 1: write fp16 planes of uint4 (8 ch) instead of fp32 float4 planes
   int exp_flags;                // timing experiments (STC_EXP_FLAGS, results invalid): see stc_conv.cu
+  // Fused DSen2 epilogues (MODE_BIAS / MODE_BIAS_RELU, tcgen05 kernels only; all null = plain raw output).  The network has
+  // no normalisation between its convolutions, so the layer's next fp16 activation (with its reflect border), the fp32
+  // residual and the final tanh + bilinear sum are produced straight from the accumulator instead of by a second pass over
+  // an fp32 copy (stc_sr.cu).
+  uint4* act16; int64_t act16_plane;       // fp16 activation of the valid outputs; border pixels mirrored from the interior
+  float4* skip; int64_t skip_plane;        // fp32 residual planes
+  int skip_mode;                           // 1: skip = x;  2: x = skip + 0.1 x, skip = x
+  float* sr_out; const float* sr_bil; int sr_bil_stride, sr_bil_off;   // N = 16: out[px][k] = tanh(x_k) + bil[px][off + k], k < 6
 };
 enum { MODE_PLAIN = 0, MODE_PSCALE_SWISH = 1, MODE_SWISH = 2, MODE_CAND = 3,
        MODE_BIAS = 4, MODE_BIAS_RELU = 5 };

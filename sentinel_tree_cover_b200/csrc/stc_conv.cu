@@ -405,7 +405,50 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, int tiles_per
               acc_ss[(c0 + i) / GS] = fmaf(xm, xm, acc_ss[(c0 + i) / GS]);
             }
           }
-          if (inb && !(p.exp_flags & 4)) {
+          if ((MODE == MODE_BIAS || MODE == MODE_BIAS_RELU) && (p.act16 || p.sr_out)) {
+            // fused DSen2 epilogues (see ConvParams): only valid outputs are stored
+            if (valid && p.sr_out) {
+              const int Ww = p.vx1 - p.vx0;
+              const int64_t px = ((int64_t)tb * (p.vy1 - p.vy0) + (yp - p.vy0)) * Ww + (xp - p.vx0);
+              if (cbase + c0 == 0) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) p.sr_out[px * 6 + k] = tanhf(v[k]) + p.sr_bil[px * p.sr_bil_stride + p.sr_bil_off + k];
+              }
+            } else if (valid) {
+              const int cq = (cbase + c0) >> 2;
+              if (p.skip_mode == 2) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                  float4* sp = p.skip + (int64_t)(cq + qd) * p.skip_plane + P;
+                  const float4 s = *sp;
+                  v[4 * qd] = fmaf(0.1f, v[4 * qd], s.x); v[4 * qd + 1] = fmaf(0.1f, v[4 * qd + 1], s.y);
+                  v[4 * qd + 2] = fmaf(0.1f, v[4 * qd + 2], s.z); v[4 * qd + 3] = fmaf(0.1f, v[4 * qd + 3], s.w);
+                  *sp = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                }
+              } else if (p.skip_mode == 1) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd)
+                  p.skip[(int64_t)(cq + qd) * p.skip_plane + P] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+              }
+              const uint4 o0 = pack8h(v), o1 = pack8h(v + 8);
+              uint4* const a16 = p.act16 + (int64_t)((cbase + c0) >> 3) * p.act16_plane;
+              const int64_t sample0 = (int64_t)tb * hw;
+              const int ym = (yp == 2) ? 0 : -1, yM = (yp == p.Hp - 3) ? p.Hp - 1 : -1;      // reflect pad 1: row 0 <- row 2, row Hp-1 <- row Hp-3
+              const int xm = (xp == 2) ? 0 : -1, xM = (xp == p.Wp - 3) ? p.Wp - 1 : -1;
+#pragma unroll
+              for (int iy = 0; iy < 3; ++iy) {
+                const int yy = iy == 0 ? yp : iy == 1 ? ym : yM;
+                if (yy < 0) continue;
+#pragma unroll
+                for (int ix = 0; ix < 3; ++ix) {
+                  const int xx = ix == 0 ? xp : ix == 1 ? xm : xM;
+                  if (xx < 0) continue;
+                  const int64_t Pm = sample0 + (int64_t)yy * p.Wp + xx;
+                  a16[Pm] = o0; a16[p.act16_plane + Pm] = o1;
+                }
+              }
+            }
+          } else if (inb && !(p.exp_flags & 4)) {
             if (p.out_fp16) {
               uint4* o = reinterpret_cast<uint4*>(outp) + (int64_t)((cbase + c0) >> 3) * p.out_plane + P;
               o[0] = pack8h(v);

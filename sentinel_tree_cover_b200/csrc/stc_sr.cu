@@ -177,7 +177,9 @@ static int sr_plan(stc_ctx* ctx, SrState* s, int N, int H, int W) {
   return STC_OK;
 }
 
-static int sr_conv(stc_ctx* ctx, SrState* s, int layer, const Act& in, int mode) {
+// dst / skip_mode / out: the fused epilogues (ConvParams); all null = raw fp32 output for sr_apply_kernel
+static int sr_conv(stc_ctx* ctx, SrState* s, int layer, const Act& in, int mode, Act* dst = nullptr, int skip_mode = 0,
+                   float* out = nullptr, const float* bil = nullptr, int bil_stride = 0, int bil_off = 0) {
   ConvParams cp; memset(&cp, 0, sizeof(cp));
   cp.a0[0] = in.at(0); cp.a0_plane = in.plane; cp.k0steps = in.chunks / 2;
   cp.w[0] = s->w[layer]; cp.out[0] = s->raw.base; cp.out_plane = s->raw.plane;
@@ -186,6 +188,8 @@ static int sr_conv(stc_ctx* ctx, SrState* s, int layer, const Act& in, int mode)
   cp.B = in.B; cp.Hp = in.Hp; cp.Wp = in.Wp; cp.Ptot = in.Ptot();
   cp.vy0 = 1; cp.vy1 = in.Hp - 1; cp.vx0 = 1; cp.vx1 = in.Wp - 1;
   cp.mode = mode;
+  if (dst) { cp.act16 = dst->at(0); cp.act16_plane = dst->plane; cp.skip = s->skip.base; cp.skip_plane = s->skip.plane; cp.skip_mode = skip_mode; }
+  if (out) { cp.sr_out = out; cp.sr_bil = bil; cp.sr_bil_stride = bil_stride; cp.sr_bil_off = bil_off; }
   return launch_conv(ctx, cp, 1);
 }
 
@@ -209,6 +213,22 @@ int sr_forward_dev(stc_ctx* ctx, const float* x_dev, const float* bil_dev, int N
   int rc = sr_plan(ctx, s, N, H, W); if (rc) return rc;
   { TraceScope ts_(ctx, "sr_prep_kernel"); sr_prep_kernel<<<cdiv((int64_t)N * H * W, 256), 256, 0, ctx->stream>>>(x_dev, N, H, W, s->X.at(0), s->X.plane); }
   STC_CUDA(cudaGetLastError()); ctx->launches++;
+  // Fused route (tcgen05 kernels): every convolution writes what the next one reads -- the fp16 activation with its reflect
+  // border, the fp32 residual, and at the end tanh + bilinear -- from its accumulator.  The separate fp32 round trip
+  // (sr_apply_kernel, below) moved 2.4x the bytes; it stays for the SIMT reference kernels (conv_impl 1) and as the A/B
+  // reference (STC_SR_FUSE=0): both routes give identical bits (tests/test_gpu_preproc.py).
+  const char* fuse_s = getenv("STC_SR_FUSE");                   // read per call: the A/B test flips it
+  const bool fuse_env = !(fuse_s && atoi(fuse_s) == 0);
+  if (fuse_env && ctx->conv_impl != 1) {
+    if ((rc = sr_conv(ctx, s, 0, s->X, MODE_BIAS_RELU, &s->A, 1))) return rc;         // a (skip = a)
+    if ((rc = sr_conv(ctx, s, 1, s->A, MODE_BIAS_RELU, &s->Bf, 0))) return rc;
+    if ((rc = sr_conv(ctx, s, 2, s->Bf, MODE_BIAS, &s->A, 2))) return rc;             // b = a + 0.1*c
+    if ((rc = sr_conv(ctx, s, 3, s->A, MODE_BIAS_RELU, &s->Bf, 0))) return rc;
+    if ((rc = sr_conv(ctx, s, 4, s->Bf, MODE_BIAS, &s->A, 2))) return rc;             // c = b + 0.1*d
+    // bil_dev == nullptr: the bilinear input is bands 4..9 of x itself (what superresolve_large_tile feeds, :104-105)
+    if (bil_dev) return sr_conv(ctx, s, 5, s->A, MODE_BIAS, nullptr, 0, out_dev, bil_dev, 6, 0);
+    return sr_conv(ctx, s, 5, s->A, MODE_BIAS, nullptr, 0, out_dev, x_dev, 10, 4);
+  }
   if ((rc = sr_conv(ctx, s, 0, s->X, MODE_BIAS_RELU))) return rc;
   if ((rc = sr_apply(ctx, s, 0, 1, &s->A, nullptr, nullptr))) return rc;      // a (skip = a)
   if ((rc = sr_conv(ctx, s, 1, s->A, MODE_BIAS_RELU))) return rc;

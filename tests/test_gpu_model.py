@@ -127,6 +127,22 @@ def test_superresolve_vs_graph_golden(sess, sr_weights):
     assert eq < 6e-4
 
 
+def test_superresolve_fused_epilogues_equal_separate_passes(sess, monkeypatch):
+    """The convolutions of the super-resolution network write the next layer's fp16 activation (with its reflect border), the
+    fp32 residual and the final tanh + bilinear sum from their accumulators; STC_SR_FUSE=0 keeps the round-1 route (fp32 raw
+    output + one elementwise pass per layer).  Same arithmetic, same bits -- also for odd sizes and a batch."""
+    r = np.random.default_rng(12)
+    for shape in [(3, 118, 118, 10), (1, 37, 53, 10), (2, 3, 3, 10), (5, 206, 206, 10)]:
+        x = r.uniform(0, 0.6, shape).astype(np.float32)
+        monkeypatch.setenv("STC_SR_FUSE", "0")
+        want = sess.superresolve(x, x[..., 4:])
+        want2 = sess.superresolve(x)
+        monkeypatch.delenv("STC_SR_FUSE")
+        got = sess.superresolve(x, x[..., 4:])
+        got2 = sess.superresolve(x)
+        assert np.array_equal(got, want) and np.array_equal(got2, want2), shape
+
+
 def test_full_size_properties(sess):
     """BASELINE size (168 -> 154), batch 8: size-independent properties."""
     m = P.synth_monthly(8, 168, 77)

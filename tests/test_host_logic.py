@@ -104,3 +104,25 @@ def test_python_random_shuffle_replay_matches_cpython():
         rc = lib.stc_py_shuffle(state.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), n)
         assert rc == 0 and got.tolist() == want, n
         assert tuple(int(v) for v in state) == random.getstate()[1], n      # the generator is left where Python leaves it
+
+
+@pytest.mark.parametrize("isa", ["0", "1"])
+def test_generator_walk_on_every_instruction_set(isa):
+    """The data-less walk (skip_shuffle) has an AVX-512, an AVX2 and a scalar scan; the default run takes the widest the
+    machine has.  STC_PYRANDOM_ISA caps it, so the other two are walked here in a child process."""
+    code = r'''
+import ctypes as C, random, numpy as np
+from sentinel_tree_cover_b200 import api
+lib = api.load_library()
+random.seed(77)
+for _ in range(100): random.getrandbits(32)
+for n in (5, 255, 256, 257, 4095, 4096, 16384, 70001, 600000):
+    skip = np.array(random.getstate()[1], dtype=np.uint32)
+    want = list(range(n)); random.shuffle(want)
+    assert lib.stc_py_shuffle(skip.ctypes.data_as(C.c_void_p), None, n) == 0
+    assert tuple(int(v) for v in skip) == random.getstate()[1], n
+print("OK")
+'''
+    env = dict(os.environ, STC_PYRANDOM_ISA=isa, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
