@@ -420,31 +420,74 @@ __global__ void __launch_bounds__(256) k_strata(const float* __restrict__ evi, c
   }
 }
 // Index lists of the seven strata of one date, rows in ascending order (np.argwhere), the two 2 % tails repeated ten
-// times per row (np.repeat(.., 10), :468-471).  One block per (stratum, date): order-preserving compaction.
-struct BucketJob { const unsigned char* lab; int K; int* out[7]; };
-__global__ void __launch_bounds__(1024) k_bucket_lists(const BucketJob* __restrict__ jobs) {
+// times per row (np.repeat(.., 10), :468-471).  Order-preserving compaction in three GPU-wide steps (the first version
+// walked each list with one block: 84-168 blocks of serial 1024-row rounds, 0.5-0.9 ms): per-block stratum counts, a scan
+// of the block counts per (date, stratum), then every block places its rows.
+struct BucketJob { const unsigned char* lab; int K; int* out[7]; int* chunk; /* [blocks][7]: counts, then exclusive bases */ };
+#define BL_ROWS 1024                     // rows per block: 256 threads x 4 consecutive rows
+__device__ __forceinline__ void bucket_thread_counts(const BucketJob& j, int r0, unsigned char (&lab)[4], int (&c)[7]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) lab[q] = (r0 + q < j.K) ? j.lab[r0 + q] : (unsigned char)0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) c[k] = ((lab[0] >> k) & 1) + ((lab[1] >> k) & 1) + ((lab[2] >> k) & 1) + ((lab[3] >> k) & 1);
+}
+__global__ void __launch_bounds__(256) k_bucket_count(const BucketJob* __restrict__ jobs) {
   const BucketJob j = jobs[blockIdx.y];
-  const int k = blockIdx.x, rep = (k == 0 || k == 6) ? 10 : 1;
-  int* out = j.out[k];
-  __shared__ int wtot[32]; __shared__ int base;
-  if (threadIdx.x == 0) base = 0;
+  if ((int64_t)blockIdx.x * BL_ROWS >= j.K) return;
+  unsigned char lab[4]; int c[7];
+  bucket_thread_counts(j, blockIdx.x * BL_ROWS + threadIdx.x * 4, lab, c);
+  __shared__ int tot[7];
+  if (threadIdx.x < 7) tot[threadIdx.x] = 0;
   __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    int v = c[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&tot[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) j.chunk[blockIdx.x * 7 + threadIdx.x] = tot[threadIdx.x];
+}
+__global__ void __launch_bounds__(224) k_bucket_scan(const BucketJob* __restrict__ jobs) {      // one warp per (date, stratum)
+  const BucketJob j = jobs[blockIdx.x];
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blocks = (j.K + BL_ROWS - 1) / BL_ROWS;
+  int running = 0;
+  for (int c0 = 0; c0 < blocks; c0 += 32) {
+    const int v = (c0 + lane < blocks) ? j.chunk[(c0 + lane) * 7 + k] : 0;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (c0 + lane < blocks) j.chunk[(c0 + lane) * 7 + k] = running + incl - v;
+    running += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+__global__ void __launch_bounds__(256) k_bucket_scatter(const BucketJob* __restrict__ jobs) {
+  const BucketJob j = jobs[blockIdx.y];
+  if ((int64_t)blockIdx.x * BL_ROWS >= j.K) return;
+  const int r0 = blockIdx.x * BL_ROWS + threadIdx.x * 4;
+  unsigned char lab[4]; int c[7];
+  bucket_thread_counts(j, r0, lab, c);
+  __shared__ int wtot[8][7];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int r0 = 0; r0 < j.K; r0 += 1024) {
-    const int r = r0 + threadIdx.x;
-    const bool f = r < j.K && ((j.lab[r] >> k) & 1);
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) wtot[wid] = __popc(bal);
-    __syncthreads();
-    int woff = 0, tot = 0;
-    for (int w = 0; w < 32; ++w) { const int c = wtot[w]; if (w < wid) woff += c; tot += c; }
-    if (f) {
-      const int pos = (base + woff + __popc(bal & ((1u << lane) - 1u))) * rep;
-      for (int q = 0; q < rep; ++q) out[pos + q] = r;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) base += tot;
-    __syncthreads();
+  int excl[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    int incl = c[k];
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    excl[k] = incl - c[k];
+    if (lane == 31) wtot[wid][k] = incl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    if (!c[k]) continue;
+    int pos = j.chunk[blockIdx.x * 7 + k] + excl[k];
+    for (int w = 0; w < wid; ++w) pos += wtot[w][k];
+    const int rep = (k == 0 || k == 6) ? 10 : 1;
+    int* out = j.out[k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if ((lab[q] >> k) & 1) { for (int t = 0; t < rep; ++t) out[pos * rep + t] = r0 + q; ++pos; }
   }
 }
 
@@ -583,7 +626,7 @@ __device__ bool solve_sym(const double* G, const double* r, const bool* P, doubl
   }
   return true;
 }
-__global__ void k_nnls(const double* __restrict__ gram, int S, double* __restrict__ coef /*[10][NF]*/, int* __restrict__ status) {
+__global__ void k_nnls_serial(const double* __restrict__ gram, int S, double* __restrict__ coef /*[10][NF]*/, int* __restrict__ status) {
   const int band = threadIdx.x;
   if (band >= 10) return;
   const double *UU = gram, *CU = gram + NF * NF, *CC = gram + 2 * NF * NF, *UY = gram + 3 * NF * NF, *CY = UY + NF * 10;
@@ -627,6 +670,99 @@ __global__ void k_nnls(const double* __restrict__ gram, int S, double* __restric
   }
   for (int j = 0; j < NF; ++j) coef[band * NF + j] = x[j];
   status[band] = st;
+}
+
+// The same algorithm, one WARP per band: the O(m^3) elimination of every solve runs over the lanes (each element update is
+// the same fused multiply-add with the same operands, so the bits do not change), the O(m) bookkeeping is done by lane j
+// for entry j with exact warp reductions (min / max / ballot), and only the back substitution -- a sum whose order
+// matters -- stays on one lane.  107 -> ~30 us per date; k_nnls_serial above is kept as the A/B reference
+// (STC_NNLS_SERIAL=1, tests/test_cloud_fill.py).
+struct NnlsShared { double G[NF * NF], A[NF][NF + 1], r[NF], x[NF], s[NF], f[NF]; int id[NF]; };
+__device__ bool solve_sym_warp(NnlsShared& sh, unsigned P, int lane) {
+  const int m = __popc(P);
+  if (lane < NF) sh.s[lane] = 0.0;
+  if (lane < m) sh.id[lane] = __fns(P, 0, lane + 1);
+  __syncwarp();
+  for (int e = lane; e < m * (m + 1); e += 32) {
+    const int a = e / (m + 1), b = e - a * (m + 1);
+    sh.A[a][b] = (b < m) ? sh.G[sh.id[a] * NF + sh.id[b]] : sh.r[sh.id[a]];
+  }
+  __syncwarp();
+  for (int col = 0; col < m; ++col) {
+    int piv = col; double best = fabs(sh.A[col][col]);                  // every lane: the same <= 11 broadcast reads
+    for (int a = col + 1; a < m; ++a) { const double v = fabs(sh.A[a][col]); if (v > best) { best = v; piv = a; } }
+    if (best == 0.0) return false;
+    if (piv != col && lane >= col && lane <= m) { const double t = sh.A[col][lane]; sh.A[col][lane] = sh.A[piv][lane]; sh.A[piv][lane] = t; }
+    __syncwarp();
+    if (lane > col && lane < m) sh.f[lane] = sh.A[lane][col] / sh.A[col][col];
+    __syncwarp();
+    const int wdt = m - col;                                            // columns col+1 .. m (column col is never read again)
+    for (int e = lane; e < (m - col - 1) * wdt; e += 32) {
+      const int a = col + 1 + e / wdt, b = col + 1 + e % wdt;
+      sh.A[a][b] = fma(-sh.f[a], sh.A[col][b], sh.A[a][b]);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    for (int a = m - 1; a >= 0; --a) {
+      double t = sh.A[a][m];
+      for (int b = a + 1; b < m; ++b) t = fma(-sh.A[a][b], sh.s[sh.id[b]], t);
+      sh.s[sh.id[a]] = t / sh.A[a][a];
+    }
+  }
+  __syncwarp();
+  return true;
+}
+__global__ void __launch_bounds__(320) k_nnls(const double* __restrict__ gram, int S, double* __restrict__ coef /*[10][NF]*/, int* __restrict__ status) {
+  __shared__ NnlsShared shs[10];
+  const int band = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  NnlsShared& sh = shs[band];
+  const double *UU = gram, *CU = gram + NF * NF, *CC = gram + 2 * NF * NF, *UY = gram + 3 * NF * NF, *CY = UY + NF * 10;
+  for (int e = lane; e < NF * NF; e += 32) {
+    const int j = e / NF, k = e - j * NF;
+    const bool cj = j < band, ck = k < band;
+    sh.G[e] = (cj && ck) ? CC[j * NF + k] : cj ? CU[j * NF + k] : ck ? CU[k * NF + j] : UU[j * NF + k];
+  }
+  const bool mine = lane < NF;
+  double r = 0.0, x = 0.0, w = 0.0;
+  if (mine) { r = (lane < band) ? CY[lane * 10 + band] : UY[lane * 10 + band]; sh.r[lane] = r; sh.x[lane] = 0.0; w = r; }
+  __syncwarp();
+  const double tol = 10.0 * (double)(S > NF ? S : NF) * 2.220446049250313e-16;
+  const int maxiter = 3 * NF;
+  const unsigned ALL = (1u << NF) - 1u, FULL = 0xffffffffu;
+  unsigned P = 0;
+  int iter = 0, st = 1;
+  while (true) {
+    if (P == ALL) break;
+    const bool free_j = mine && !((P >> lane) & 1u);
+    if (!__any_sync(FULL, free_j && w > tol)) break;
+    // argmax over j of (P[j] ? 0 : w[j]), first maximum
+    const double v = mine ? (free_j ? w : 0.0) : -INFINITY;
+    double mx = v;
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+    const unsigned hit = __ballot_sync(FULL, mine && v == mx);
+    const int kbest = hit ? (__ffs(hit) - 1) : 0;
+    P |= 1u << kbest;
+    if (!solve_sym_warp(sh, P, lane)) { st = -2; break; }
+    while (iter < maxiter) {
+      const bool in_p = mine && ((P >> lane) & 1u);
+      const double sj = mine ? sh.s[lane] : 0.0;
+      if (!__any_sync(FULL, in_p && sj < 0)) break;                     // min over P of s is not negative
+      ++iter;
+      double al = (in_p && sj < 0) ? x / (x - sj) : INFINITY;
+      for (int o = 16; o > 0; o >>= 1) al = fmin(al, __shfl_xor_sync(FULL, al, o));
+      if (mine) { x *= (1 - al); x = fma(al, sj, x); }
+      P &= ~__ballot_sync(FULL, mine && x <= tol);
+      if (!solve_sym_warp(sh, P, lane)) { st = -2; break; }
+    }
+    if (st < 0) break;
+    if (mine) { x = sh.s[lane]; sh.x[lane] = x; }
+    __syncwarp();
+    if (mine) { double t = r; for (int k = 0; k < NF; ++k) t = fma(-sh.G[lane * NF + k], sh.x[k], t); w = t; }
+    if (iter == maxiter) { st = -1; break; }
+  }
+  if (mine) coef[band * NF + lane] = x;
+  if (lane == 0) status[band] = st;
 }
 
 // tiles[d] = tiles[d]*(1-a) + fill*a with fill = regression prediction from [mosaic, snow] (use_coef) or the mosaic itself
@@ -731,13 +867,18 @@ __global__ void __launch_bounds__(256) k_clip01(float* __restrict__ x, int64_t n
 }
 }  // namespace
 
-// worker threads for the shuffle replay: STC_HOST_THREADS, else a quarter of the cores this process may run on (2..8)
+// Worker threads for the shuffle replay: STC_HOST_THREADS, else this process' share of the cores it may run on (the ranks
+// of one node divide them: LOCAL_WORLD_SIZE, set by torchrun) minus the three threads that are busy anyway (the caller, the
+// generator walk and its producer); 2..12.  The shuffles are ~60 ms of CPU time for a 24-date tile, and a date's device
+// work cannot be enqueued before its sample is shuffled, so too few workers put the host on the critical path.
 static int host_threads() {
   if (const char* e = getenv("STC_HOST_THREADS")) { const int v = atoi(e); if (v >= 1) return std::min(v, 64); }
   cpu_set_t set; CPU_ZERO(&set);
-  int n = 4;
-  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set) / 4;
-  return std::max(2, std::min(n, 8));
+  int cores = 8;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+  int ranks = 1;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v >= 1) ranks = v; }
+  return std::max(2, std::min(cores / ranks - 3, 12));
 }
 
 // Device-resident core: tiles [n,H,W,10] float32 (blended in place), probs [n,H,W] float32, pfcps [>= H*W] uint8 (date 0 is read),
@@ -819,7 +960,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   std::vector<int> fit_of(n, -1);
   int64_t total_rows = 0;
   int nf = 0;
-  DBuf d_rows_all, d_evi_all, d_lab_all, d_fqout, d_fcnt, d_lists, d_bjobs, d_sample_all, d_status_all, d_flag3, d_pos3, d_K3;
+  DBuf d_rows_all, d_evi_all, d_lab_all, d_fqout, d_fcnt, d_lists, d_bjobs, d_bchunk, d_sample_all, d_status_all, d_flag3, d_pos3, d_K3;
   int* pin_lists = nullptr; int* pin_samples = nullptr;
   std::vector<int64_t> sample0;
   std::vector<ShufTask> tasks;
@@ -902,13 +1043,23 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
           if (f.cnt[k] == 1)
             STC_FAIL(STC_ERR_STATE, "remove_clouds: single-element EVI stratum -- the reference raises TypeError (shuffle of a 0-d array)");
       STC_CUDA(stc_dmalloc(&d_lists.p, (size_t)std::max<int64_t>(total_list, 1) * 4)); STC_CUDA(stc_dmalloc(&d_bjobs.p, (size_t)nf * sizeof(BucketJob)));
+      int max_blocks = 1;
+      for (int j = 0; j < nf; ++j) max_blocks = std::max(max_blocks, cdiv(fits[j].K, BL_ROWS));
+      STC_CUDA(stc_dmalloc(&d_bchunk.p, (size_t)nf * max_blocks * 7 * 4));
       std::vector<BucketJob> bj(nf);
       for (int j = 0; j < nf; ++j) {
         bj[j].lab = d_lab_all.as<unsigned char>() + fits[j].row0; bj[j].K = fits[j].K;
         for (int k = 0; k < 7; ++k) bj[j].out[k] = d_lists.as<int>() + fits[j].list0[k];
+        bj[j].chunk = d_bchunk.as<int>() + (size_t)j * max_blocks * 7;
       }
-      STC_CUDA(cudaMemcpyAsync(d_bjobs.p, bj.data(), (size_t)nf * sizeof(BucketJob), cudaMemcpyHostToDevice, ctx->stream));
-      CF_LAUNCH(k_bucket_lists, dim3(7, nf), 1024, d_bjobs.as<BucketJob>());
+      {
+        const void* staged = ctx_stage(ctx, bj.data(), (size_t)nf * sizeof(BucketJob));
+        if (!staged) STC_FAIL(STC_ERR_NOMEM, "remove_clouds: pinned staging");
+        STC_CUDA(cudaMemcpyAsync(d_bjobs.p, staged, (size_t)nf * sizeof(BucketJob), cudaMemcpyHostToDevice, ctx->stream));
+      }
+      CF_LAUNCH(k_bucket_count, dim3(max_blocks, nf), 256, d_bjobs.as<BucketJob>());
+      CF_LAUNCH(k_bucket_scan, nf, 224, d_bjobs.as<BucketJob>());
+      CF_LAUNCH(k_bucket_scatter, dim3(max_blocks, nf), 256, d_bjobs.as<BucketJob>());
       // pinned host scratch: the lists, then (behind them) one sample slot per date
       int64_t sample_cap = 0;
       sample0.assign(nf, 0);
@@ -921,8 +1072,23 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       pin_lists = (int*)ctx_pinned(ctx, (size_t)(total_list + sample_cap + 16) * 4);
       if (!pin_lists) STC_FAIL(STC_ERR_NOMEM, "remove_clouds: pinned host scratch");
       STC_CUDA(stc_dmalloc(&d_sample_all.p, (size_t)std::max<int64_t>(sample_cap, 1) * 4));
-      STC_CUDA(cudaMemcpyAsync(pin_lists, d_lists.p, (size_t)total_list * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CF_SYNC();                                             // bj is a host vector; the lists are on the host now
+      // The lists (4 MB per date) travel on their own stream, one event per date: the compute stream goes on with the mosaic,
+      // the generator walk below needs only the list LENGTHS and starts now, and a worker waits for its date's event.
+      if (!ctx->d2h_stream) {
+        STC_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        STC_CUDA(cudaEventCreateWithFlags(&ctx->d2h_fork, cudaEventDisableTiming));
+      }
+      while ((int)ctx->d2h_events.size() < nf) {
+        cudaEvent_t e; STC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->d2h_events.push_back(e);
+      }
+      STC_CUDA(cudaEventRecord(ctx->d2h_fork, ctx->stream));
+      STC_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->d2h_fork, 0));
+      for (int j = 0; j < nf; ++j) {
+        const int64_t a = fits[j].list0[0], b = fits[j].list0[6] + fits[j].cnt[6];
+        if (b > a) STC_CUDA(cudaMemcpyAsync(pin_lists + a, d_lists.as<int>() + a, (size_t)(b - a) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        STC_CUDA(cudaEventRecord(ctx->d2h_events[j], ctx->d2h_stream));
+      }
       cf_mark("fit rows, strata, index lists (all dates)");
       // ---- 3b. in date order: Python's random.shuffle replayed on the host for date d while the device still works on date
       //      d - 1 (launches are asynchronous; nothing below synchronises), then Gram sums, NNLS and the blend of date d.
@@ -976,6 +1142,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
           while (published.load(std::memory_order_acquire) <= ti) std::this_thread::yield();
           const ShufTask& t = tasks[ti];
           const FitJob& f = fits[t.j];
+          while (cudaEventQuery(ctx->d2h_events[t.j]) == cudaErrorNotReady) std::this_thread::yield();      // the date's lists are on the host
           r.import_state(t.mt, t.idx);
           if (t.k < 7) {
             r.shuffle(pin_lists + f.list0[t.k], (size_t)f.cnt[t.k]);
@@ -1071,6 +1238,8 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   // ---- 3. per-date alignment and blending (:939-959, :316-575) ----
   if (!fits_ready && (rc = prepare_fits())) return rc;
   if (nf > 0) {
+    const char* nnls_env = getenv("STC_NNLS_SERIAL");                  // A/B reference, read per call
+    const bool nnls_serial = nnls_env && atoi(nnls_env) == 1;
     DBuf d_sp;
     STC_CUDA(stc_dmalloc(&d_sp.p, (size_t)n * HW * 4));
     float* sp = d_sp.as<float>();
@@ -1096,7 +1265,8 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
                 d_gramz.as<float>());
       CF_LAUNCH(k_gram, cdiv(gb, 2), 64, d_gramz.as<float>(), (int)S, gb, d_partial.as<double>());
       CF_LAUNCH(k_gram_reduce, 1, 640, d_partial.as<double>(), gb, d_gram.as<double>());
-      CF_LAUNCH(k_nnls, 1, 32, d_gram.as<double>(), (int)S, d_coef.as<double>(), d_status_all.as<int>() + 10 * j);
+      if (nnls_serial) CF_LAUNCH(k_nnls_serial, 1, 32, d_gram.as<double>(), (int)S, d_coef.as<double>(), d_status_all.as<int>() + 10 * j);
+      else CF_LAUNCH(k_nnls, 1, 320, d_gram.as<double>(), (int)S, d_coef.as<double>(), d_status_all.as<int>() + 10 * j);
       if (getenv("STC_CF_DEBUG")) {                        // test aid: fit inputs / coefficients of every date on stderr
         double hc[10 * NF]; int hs[6] = {0}; int hr[6] = {0}; float hq[6] = {0};
         cudaMemcpyAsync(hq, d_fqout.as<float>() + 6 * j, sizeof(hq), cudaMemcpyDeviceToHost, ctx->stream);

@@ -109,6 +109,8 @@ struct stc_ctx {
   int anc_H = 0, anc_W = 0;
   // side stream for latency-bound kernels that occupy a few SMs next to GPU-wide work (forked / joined with events)
   cudaStream_t aux_stream = nullptr; cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+  // remove_clouds: the per-date index lists go to the host on their own stream, one event per date (stc_cloudfill.cu)
+  cudaStream_t d2h_stream = nullptr; cudaEvent_t d2h_fork = nullptr; std::vector<cudaEvent_t> d2h_events;
 };
 static constexpr size_t STC_STAGE_RING = 8u << 20;
 // copy `bytes` of host data into the pinned ring and return the pinned address (valid until the ring wraps: 8 MB of tables)

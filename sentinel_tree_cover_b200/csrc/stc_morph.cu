@@ -177,21 +177,48 @@ __global__ void __launch_bounds__(256) k_any_positive(const float* __restrict__ 
   if (__any_sync(0xffffffffu, pos) && (threadIdx.x & 31) == 0) atomicOr(flags + blockIdx.y, 1);
 }
 
-// separable flat max/min filter along one axis with SciPy 'reflect' boundary
-__global__ void __launch_bounds__(256) window_reduce_kernel(const float* __restrict__ in, const int* __restrict__ sums,
-                                                            float* __restrict__ out, int n, int H, int W, int lo, int hi,
-                                                            int axis, int is_max) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)n * H * W) return;
-  int x = (int)(idx % W); int64_t r = idx / W; int y = (int)(r % H); int d = (int)(r / H);
+// Flat 2-D max / min filter over the window [lo, hi] x [lo, hi] with SciPy 'reflect' boundary: one block per 64 x 16 output
+// tile, the tile and its halo staged once in shared memory (the boundary folded in there), then the column pass and the row
+// pass from shared memory.  The per-axis kernel of the first version read `hi - lo + 1` global values per pixel and pass and computed a
+// reflected index for each of them: 0.1-0.2 ms per pass on a 12-24 date tile, 1.3-2.5 ms per tile for the three featherings.
+#define W2_TX 64
+#define W2_TY 16
+template <bool IS_MAX>
+__global__ void __launch_bounds__(256) k_window2d(const float* __restrict__ in, const int* __restrict__ flags, float* __restrict__ out,
+                                                  int H, int W, int lo, int hi) {
+  extern __shared__ float w2_sm[];
+  const int d = blockIdx.z, x0 = blockIdx.x * W2_TX, y0 = blockIdx.y * W2_TY;
   const float* m = in + (int64_t)d * H * W;
-  if (sums && !sums[d]) { out[idx] = m[(int64_t)y * W + x]; return; }
-  float v = is_max ? -INFINITY : INFINITY;
-  for (int k = lo; k <= hi; ++k) {
-    float t = axis == 0 ? m[(int64_t)reflect_index(y + k, H) * W + x] : m[(int64_t)y * W + reflect_index(x + k, W)];
-    v = is_max ? fmaxf(v, t) : fminf(v, t);
+  float* o = out + (int64_t)d * H * W;
+  if (flags && !flags[d]) {                                         // date without any mask: the closing is skipped
+    for (int e = threadIdx.x; e < W2_TX * W2_TY; e += blockDim.x) {
+      const int x = x0 + e % W2_TX, y = y0 + e / W2_TX;
+      if (x < W && y < H) o[(int64_t)y * W + x] = m[(int64_t)y * W + x];
+    }
+    return;
   }
-  out[idx] = v;
+  const int span = hi - lo, SW = W2_TX + span, SH = W2_TY + span;
+  float* a = w2_sm;                 // [SH][SW] input tile + halo
+  float* b = w2_sm + SH * SW;       // [W2_TY][SW] after the column pass
+  for (int e = threadIdx.x; e < SH * SW; e += blockDim.x) {
+    const int r = e / SW, c = e - r * SW;
+    a[e] = m[(int64_t)reflect_index(y0 + lo + r, H) * W + reflect_index(x0 + lo + c, W)];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < W2_TY * SW; e += blockDim.x) {
+    const int r = e / SW, c = e - r * SW;
+    float v = a[r * SW + c];
+    for (int k = 1; k <= span; ++k) { const float t = a[(r + k) * SW + c]; v = IS_MAX ? fmaxf(v, t) : fminf(v, t); }
+    b[e] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < W2_TY * W2_TX; e += blockDim.x) {
+    const int r = e / W2_TX, c = e - r * W2_TX;
+    if (x0 + c >= W || y0 + r >= H) continue;
+    float v = b[r * SW + c];
+    for (int k = 1; k <= span; ++k) { const float t = b[r * SW + c + k]; v = IS_MAX ? fmaxf(v, t) : fminf(v, t); }
+    o[(int64_t)(y0 + r) * W + x0 + c] = v;
+  }
 }
 
 int pre_edt_sq_dev(stc_ctx* ctx, const unsigned char* target_dev, int n, int H, int W, int radius, int* out_dev) {
@@ -223,12 +250,21 @@ int pre_feather_dev(stc_ctx* ctx, const float* mask_dev, int n, int H, int W, in
   int dlo, dhi, elo, ehi;
   if (size & 1) { dlo = elo = -(size / 2); dhi = ehi = size / 2; }
   else { dlo = -(size / 2 - 1); dhi = size / 2; elo = -(size / 2); ehi = size / 2 - 1; }
-  { TraceScope ts_(ctx, "window_reduce_kernel"); window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_a, flags, tmp_b, n, H, W, dlo, dhi, 0, 1); }
-  { TraceScope ts_(ctx, "window_reduce_kernel"); window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_b, flags, tmp_a, n, H, W, dlo, dhi, 1, 1); }
-  { TraceScope ts_(ctx, "window_reduce_kernel"); window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_a, flags, tmp_b, n, H, W, elo, ehi, 0, 0); }
-  { TraceScope ts_(ctx, "window_reduce_kernel"); window_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(tmp_b, flags, out_dev, n, H, W, elo, ehi, 1, 0); }
+  {
+    // grey closing = max filter, then min filter (window <= 64: <= 50 KB of shared memory)
+    const dim3 g2(cdiv(W, W2_TX), cdiv(H, W2_TY), n);
+    auto smem_of = [](int span) { return (size_t)((W2_TY + span) * (W2_TX + span) + W2_TY * (W2_TX + span)) * 4; };
+    static bool configured = false;
+    if (!configured) {
+      STC_CUDA(cudaFuncSetAttribute(k_window2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(63)));
+      STC_CUDA(cudaFuncSetAttribute(k_window2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(63)));
+      configured = true;
+    }
+    { TraceScope ts_(ctx, "k_window2d"); k_window2d<true><<<g2, 256, smem_of(dhi - dlo), ctx->stream>>>(tmp_a, flags, tmp_b, H, W, dlo, dhi); }
+    { TraceScope ts_(ctx, "k_window2d"); k_window2d<false><<<g2, 256, smem_of(ehi - elo), ctx->stream>>>(tmp_b, flags, out_dev, H, W, elo, ehi); }
+  }
   STC_CUDA(cudaGetLastError());
-  ctx->launches += 6;
+  ctx->launches += 4;
   return STC_OK;
 }
 

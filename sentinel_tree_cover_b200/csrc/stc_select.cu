@@ -24,7 +24,7 @@
 namespace {
 
 constexpr int SEL_BINS = 2048;            // bins of the widest digit
-constexpr int SEL_ITERS = 256;            // elements per thread, block and pass
+constexpr int SEL_ITERS = 128;            // elements per thread, block and pass
 
 struct SelState { unsigned prefix; int kth; int cnt_le; unsigned min_gt; };
 
@@ -36,7 +36,7 @@ __device__ __forceinline__ float sel_unkey(unsigned u) {
   u ^= (u >> 31) ? 0x80000000u : 0xffffffffu;
   return __uint_as_float(u);
 }
-__host__ __device__ __forceinline__ int sel_stride(int cols) { return (256 / cols) * cols; }    // active threads = elements per iteration
+__host__ __device__ __forceinline__ int sel_stride(int cols) { return (512 / cols) * cols; }    // active threads = elements per iteration
 
 __global__ void __launch_bounds__(256) k_sel_init(const int* __restrict__ ks, SelState* __restrict__ st, int* __restrict__ hist, int total) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,9 +45,13 @@ __global__ void __launch_bounds__(256) k_sel_init(const int* __restrict__ ks, Se
   for (int64_t q = i + (int64_t)gridDim.x * blockDim.x; q < (int64_t)total * SEL_BINS; q += (int64_t)gridDim.x * blockDim.x) hist[q] = 0;
 }
 
-// digit = (key >> shift) & (nbins - 1); keys must match the job column's prefix in the bits above the digit
+// digit = (key >> shift) & (nbins - 1); keys must match the job column's prefix in the bits above the digit.
+// 512 threads, eight independent loads in flight per thread: with one load per thread and iteration the pass ran at
+// 1-2 TB/s (latency-bound: 80 KB of histogram per block leave room for two blocks per SM).
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_UNROLL = 8;
 template <bool LAST>
-__global__ void __launch_bounds__(256) k_sel_hist(const SelJob* __restrict__ jobs, SelState* __restrict__ st, int* __restrict__ hist, int shift, int nbins) {
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_hist(const SelJob* __restrict__ jobs, SelState* __restrict__ st, int* __restrict__ hist, int shift, int nbins) {
   const SelJob j = jobs[blockIdx.y];
   const int S = sel_stride(j.cols);
   const int64_t total = (int64_t)j.rows * j.cols;
@@ -59,6 +63,7 @@ __global__ void __launch_bounds__(256) k_sel_hist(const SelJob* __restrict__ job
   for (int i = threadIdx.x; i < j.cols * nbins; i += blockDim.x) h[i] = 0;
   if (threadIdx.x < j.cols) { pre[threadIdx.x] = st[blockIdx.y * SEL_MAX_COLS + threadIdx.x].prefix; mn[threadIdx.x] = 0xffffffffu; }
   __syncthreads();
+  const unsigned lanes = __ballot_sync(0xffffffffu, (int)threadIdx.x < S);       // the warp's lanes that work (all but the block's last few)
   if ((int)threadIdx.x < S) {
     const int c = (int)threadIdx.x % j.cols;         // e0 and S are multiples of cols: the column never changes
     const int hi_shift = shift + (LAST ? 10 : 11);   // bits above the digit (the digit of the last pass is 10 bits wide)
@@ -68,11 +73,29 @@ __global__ void __launch_bounds__(256) k_sel_hist(const SelJob* __restrict__ job
     const unsigned dmask = (unsigned)nbins - 1u;
     const float* src = j.data + (j.ld == j.cols ? e0 + threadIdx.x : ((e0 + threadIdx.x) / j.cols) * (int64_t)j.ld + c);
     const int64_t step = (j.ld == j.cols) ? S : (int64_t)(S / j.cols) * j.ld;
-    for (int64_t e = e0 + threadIdx.x; e < e1; e += S, src += step) {
-      const unsigned u = sel_key(*src);
-      const unsigned top = (hi_shift >= 32) ? 0u : (u >> hi_shift);
-      if (top == want) atomicAdd(&hc[(u >> shift) & dmask], 1);
-      else if (LAST && top > want && u < above) above = u;
+    // a single column puts all lanes of a warp on the same few bins in the first pass: lanes with equal digits are merged
+    const bool merge = j.cols <= 2;
+    const int rounds = (int)((e1 - e0 + (int64_t)S * SEL_UNROLL - 1) / ((int64_t)S * SEL_UNROLL));      // the same for every thread
+    int64_t e = e0 + threadIdx.x;
+    for (int k = 0; k < rounds; ++k, e += (int64_t)S * SEL_UNROLL, src += step * SEL_UNROLL) {
+      unsigned u[SEL_UNROLL];
+#pragma unroll
+      for (int q = 0; q < SEL_UNROLL; ++q) u[q] = (e + (int64_t)q * S < e1) ? sel_key(src[q * step]) : 0u;
+#pragma unroll
+      for (int q = 0; q < SEL_UNROLL; ++q) {
+        const bool in = e + (int64_t)q * S < e1;
+        const unsigned top = (hi_shift >= 32) ? 0u : (u[q] >> hi_shift);
+        const bool hit = in && top == want;
+        const int bin = (int)((u[q] >> shift) & dmask);
+        if (merge) {
+          const unsigned act = __ballot_sync(lanes, hit);
+          if (hit) {
+            const unsigned peers = __match_any_sync(act, c * nbins + bin);
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hc[bin], __popc(peers));
+          }
+        } else if (hit) atomicAdd(&hc[bin], 1);
+        if (LAST && in && top > want && u[q] < above) above = u[q];
+      }
     }
     if (LAST && above != 0xffffffffu) atomicMin(&mn[c], above);
   }
@@ -177,10 +200,10 @@ int select_ranks_dev(stc_ctx* ctx, const SelJob* jobs_host, int njobs, const int
     const int shift = pass == 0 ? 21 : pass == 1 ? 10 : 0, nbins = pass == 2 ? 1024 : 2048;
     const size_t smem = (size_t)max_cols * nbins * 4;
     if (pass < 2) {
-      { TraceScope ts_(ctx, "k_sel_hist"); k_sel_hist<false><<<grid, 256, smem, ctx->stream>>>(jobs.as<SelJob>(), st.as<SelState>(), hist.as<int>(), shift, nbins); }
+      { TraceScope ts_(ctx, "k_sel_hist"); k_sel_hist<false><<<grid, SEL_THREADS, smem, ctx->stream>>>(jobs.as<SelJob>(), st.as<SelState>(), hist.as<int>(), shift, nbins); }
       { TraceScope ts_(ctx, "k_sel_pick"); k_sel_pick<false><<<pick_blocks, 256, 0, ctx->stream>>>(jobs.as<SelJob>(), st.as<SelState>(), hist.as<int>(), ks_dev, shift, nbins, njobs); }
     } else {
-      { TraceScope ts_(ctx, "k_sel_hist"); k_sel_hist<true><<<grid, 256, smem, ctx->stream>>>(jobs.as<SelJob>(), st.as<SelState>(), hist.as<int>(), shift, nbins); }
+      { TraceScope ts_(ctx, "k_sel_hist"); k_sel_hist<true><<<grid, SEL_THREADS, smem, ctx->stream>>>(jobs.as<SelJob>(), st.as<SelState>(), hist.as<int>(), shift, nbins); }
       { TraceScope ts_(ctx, "k_sel_pick"); k_sel_pick<true><<<pick_blocks, 256, 0, ctx->stream>>>(jobs.as<SelJob>(), st.as<SelState>(), hist.as<int>(), ks_dev, shift, nbins, njobs); }
     }
   }

@@ -95,6 +95,27 @@ def test_gpu_remove_clouds_vs_oracle(sess, case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", [(6, 230, 220, 42, 11), (9, 120, 100, 46, 12)])
+def test_gpu_warp_parallel_nnls_equals_the_serial_solver(sess, case, monkeypatch):
+    """k_nnls (one warp per band, the elimination spread over the lanes) against k_nnls_serial (one thread per band, the
+    direct transcription of scipy.optimize.nnls' Lawson-Hanson loop): the same operations on the same operands, so the
+    blended tiles are bit-identical."""
+    T, H, W, seed, rseed = case
+    img, clouds, fcps = _inputs(T, H, W, seed)
+    outs = []
+    for serial in ("1", "0"):
+        monkeypatch.setenv("STC_NNLS_SERIAL", serial)
+        random.seed(rseed)
+        state = np.array(random.getstate()[1], dtype=np.uint32)
+        tiles = np.copy(img)
+        areas, rm = sess.remove_clouds(tiles, clouds, fcps, state)
+        outs.append((tiles, areas, rm, state))
+    assert (outs[0][0] != img).any()                                  # the fit did change pixels
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+    assert np.array_equal(outs[0][3], outs[1][3])
+
+
+@pytest.mark.gpu
 def test_gpu_remove_clouds_no_clouds_is_identity(sess):
     img, _ = cloud_ref.synth_cloudy_cube(5, 64, 64, 50)
     tiles = np.copy(img)
