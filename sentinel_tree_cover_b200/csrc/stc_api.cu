@@ -48,6 +48,8 @@ void stc_destroy(stc_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->d2h_stream) { cudaStreamDestroy(ctx->d2h_stream); cudaEventDestroy(ctx->d2h_fork); }
   for (cudaEvent_t e : ctx->d2h_events) cudaEventDestroy(e);
+  if (ctx->smp_stream) cudaStreamDestroy(ctx->smp_stream);
+  for (cudaEvent_t e : ctx->smp_events) cudaEventDestroy(e);
   for (int i = 0; i < stc_ctx::MAX_SLOTS; ++i) {
     if (ctx->hi_stream[i]) cudaStreamDestroy(ctx->hi_stream[i]);
     for (int j = 0; j < 2; ++j) if (ctx->ev_lane[i][j]) cudaEventDestroy(ctx->ev_lane[i][j]);

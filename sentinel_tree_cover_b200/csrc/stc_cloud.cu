@@ -640,18 +640,22 @@ __global__ void __launch_bounds__(256) k_and_or_dem(unsigned char* __restrict__ 
   if (p >= HW) return;
   if (!(near[p] || dem[p] >= 30.f)) shadows[p] = 0;
 }
-// dark-blue shadow candidates of one date: 1/B2 > ref && B8A < 0.17
-__global__ void __launch_bounds__(256) k_darkblue(const float* __restrict__ img, int HW, int t, float ref, unsigned char* __restrict__ o) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
+// dark-blue shadow candidates: 1/B2 > ref && B8A < 0.17 (:1638-1648)
+// all dates in one launch (blockIdx.y = date): inactive dates (np.mean(clouds) >= 0.9, :1641) give an empty candidate mask,
+// which the opening that follows leaves empty and the final OR ignores -- the same as skipping the date
+__global__ void __launch_bounds__(256) k_darkblue_all(const float* __restrict__ img, int HW, const float* __restrict__ refs,
+                                                      const int* __restrict__ active, unsigned char* __restrict__ o) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
   if (p >= HW) return;
   const float* x = img + ((int64_t)t * HW + p) * 10;
-  o[p] = (__fdiv_rn(1.f, x[0]) > ref) && (x[7] < 0.17f);
+  o[(int64_t)t * HW + p] = active[t] && (__fdiv_rn(1.f, x[0]) > refs[t]) && (x[7] < 0.17f);
 }
-__global__ void __launch_bounds__(256) k_or_nowater(unsigned char* __restrict__ clouds, const unsigned char* __restrict__ s,
-                                                    const float* __restrict__ water, int HW) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_or_nowater_all(unsigned char* __restrict__ clouds, const unsigned char* __restrict__ s,
+                                                        const float* __restrict__ water, int HW) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
-  if (s[p] && !(water[p] > 0.f)) clouds[p] = 1;
+  const int64_t i = (int64_t)blockIdx.y * HW + p;
+  if (s[i] && !(water[p] > 0.f)) clouds[i] = 1;
 }
 __global__ void __launch_bounds__(256) k_fill(unsigned char* p, int64_t n, unsigned char v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -903,29 +907,42 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   if ((rc_ = dump(7, cl))) return rc_;
 
   // ---- G: shadow plausibility (:1617-1626), per date on scalar means ----
-  for (int t = 0; t < T; ++t) {
-    int c2[2] = {0, 0};
-    STC_CUDA(cudaMemsetAsync(d_cnt.p, 0, 8, ctx->stream));
-    LAUNCH1D(k_count, HW, sh + (int64_t)t * HW, HW, (int*)d_cnt.p);
-    LAUNCH1D(k_count, HW, cl + (int64_t)t * HW, HW, (int*)d_cnt.p + 1);
-    if (urban) LAUNCH1D(k_count, HW, (const unsigned char*)d_two.p + (int64_t)t * HW, HW, (int*)d_cnt.p + 1);     // value-2 pixels count twice
-    STC_CUDA(cudaMemcpyAsync(c2, d_cnt.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  {
+    // the counts of every date in three launches and ONE synchronisation (the first version counted, copied and synchronised
+    // date by date: 3 n launches and n round trips); a date's shadows change only through its own restrict_far
+    Buf d_g;
+    STC_CUDA(stc_dmalloc(&d_g.p, 2 * CT_MAX * 4));
+    int* g_sh = (int*)d_g.p; int* g_cl = g_sh + CT_MAX;
+    STC_CUDA(cudaMemsetAsync(d_g.p, 0, 2 * CT_MAX * 4, ctx->stream));
+    const dim3 gd(cdiv(HW, 256), T);
+    { TraceScope ts_(ctx, "k_count_dates"); k_count_dates<<<gd, 256, 0, ctx->stream>>>(sh, HW, g_sh); } ctx->launches++;
+    { TraceScope ts_(ctx, "k_count_dates"); k_count_dates<<<gd, 256, 0, ctx->stream>>>(cl, HW, g_cl); } ctx->launches++;
+    if (urban) { TraceScope ts_(ctx, "k_count_dates"); k_count_dates<<<gd, 256, 0, ctx->stream>>>((const unsigned char*)d_two.p, HW, g_cl); ctx->launches++; }   // value-2 pixels count twice
+    int cnt_g[2 * CT_MAX];
+    STC_CUDA(cudaMemcpyAsync(cnt_g, d_g.p, 2 * CT_MAX * 4, cudaMemcpyDeviceToHost, ctx->stream));
     STC_CUDA(cudaStreamSynchronize(ctx->stream));
-    // np.mean of a float32 0/1 array: exact for these sizes
-    float ms = (float)((double)c2[0] / HW), mc = (float)((double)c2[1] / HW);
-    auto restrict_far = [&]() -> int {
-      dilate(cl + (int64_t)t * HW, ta, 1, 50, 1, 0, 0, 0);                      // 50 cross iterations = L1 radius 50
-      LAUNCH1D(k_and_or_dem, HW, sh + (int64_t)t * HW, ta, dem, HW);
-      return STC_OK;
-    };
-    if (ms > (mc + 0.3f) && mc < 0.3f) restrict_far();
-    if (mc < 0.05f) {
-      STC_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4, ctx->stream));
-      LAUNCH1D(k_count, HW, sh + (int64_t)t * HW, HW, (int*)d_cnt.p);
-      STC_CUDA(cudaMemcpyAsync(c2, d_cnt.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      STC_CUDA(cudaStreamSynchronize(ctx->stream));
-      float ms2 = (float)((double)c2[0] / HW);
-      if ((ms2 / mc) > 3.f) restrict_far();                                     // mc == 0: inf > 3 (or nan: false), as NumPy
+    for (int t = 0; t < T; ++t) {
+      // np.mean of a float32 0/1 array: exact for these sizes
+      const float ms = (float)((double)cnt_g[t] / HW), mc = (float)((double)cnt_g[CT_MAX + t] / HW);
+      auto restrict_far = [&]() -> int {
+        dilate(cl + (int64_t)t * HW, ta, 1, 50, 1, 0, 0, 0);                      // 50 cross iterations = L1 radius 50
+        LAUNCH1D(k_and_or_dem, HW, sh + (int64_t)t * HW, ta, dem, HW);
+        return STC_OK;
+      };
+      const bool far1 = ms > (mc + 0.3f) && mc < 0.3f;
+      if (far1) restrict_far();
+      if (mc < 0.05f) {
+        float ms2 = ms;
+        if (far1) {                                                               // the shadows of this date just changed: count again
+          int c1 = 0;
+          STC_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4, ctx->stream));
+          LAUNCH1D(k_count, HW, sh + (int64_t)t * HW, HW, (int*)d_cnt.p);
+          STC_CUDA(cudaMemcpyAsync(&c1, d_cnt.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+          STC_CUDA(cudaStreamSynchronize(ctx->stream));
+          ms2 = (float)((double)c1 / HW);
+        }
+        if ((ms2 / mc) > 3.f) restrict_far();                                     // mc == 0: inf > 3 (or nan: false), as NumPy
+      }
     }
   }
   LAUNCH1D(k_or, N, cl, sh, cl, N);
@@ -943,15 +960,27 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   // ---- H: dark-blue shadow recovery (:1638-1648) ----
   {
     if ((rc_ = moments(1, nullptr, nullptr, true))) return rc_;
+    // every date in one launch per step (6 n small launches before)
+    struct { float ref[CT_MAX]; int active[CT_MAX]; } db;
+    memset(&db, 0, sizeof(db));
+    bool any_db = false;
     for (int t = 0; t < T; ++t) {
       float frac = (float)((double)(HW - cnt_h[2 * t] + two_cnt[t]) / HW);      // np.mean(clouds[t]) as float32 (a 2 counts twice)
       if (!(frac < 0.9f)) continue;
       volatile float two_sd = 2.f * mom_h[2 * t + 1];
-      float ref = mom_h[2 * t] + two_sd;
-      LAUNCH1D(k_darkblue, HW, img, HW, t, ref, ta);
-      dilate(ta, tb, 1, 2, 1, 1, 1, 0);
-      dilate(tb, ta, 1, 2, 1, 0, 0, 0);
-      LAUNCH1D(k_or_nowater, HW, cl + (int64_t)t * HW, ta, water, HW);
+      db.ref[t] = mom_h[2 * t] + two_sd; db.active[t] = 1; any_db = true;
+    }
+    if (any_db) {
+      Buf d_db;
+      STC_CUDA(stc_dmalloc(&d_db.p, sizeof(db)));
+      const void* staged = ctx_stage(ctx, &db, sizeof(db));
+      if (!staged) STC_FAIL(STC_ERR_NOMEM, "cloud_masks: pinned staging");
+      STC_CUDA(cudaMemcpyAsync(d_db.p, staged, sizeof(db), cudaMemcpyHostToDevice, ctx->stream));
+      const dim3 gd(cdiv(HW, 256), T);
+      { TraceScope ts_(ctx, "k_darkblue_all"); k_darkblue_all<<<gd, 256, 0, ctx->stream>>>(img, HW, (const float*)d_db.p, (const int*)((const char*)d_db.p + sizeof(db.ref)), ta); } ctx->launches++;
+      dilate(ta, tb, T, 2, 1, 1, 1, 0);
+      dilate(tb, ta, T, 2, 1, 0, 0, 0);
+      { TraceScope ts_(ctx, "k_or_nowater_all"); k_or_nowater_all<<<gd, 256, 0, ctx->stream>>>(cl, ta, water, HW); } ctx->launches++;
     }
     if ((rc_ = dump(8, cl))) return rc_;
   }

@@ -273,15 +273,23 @@ __global__ void k_scale_params(const float* __restrict__ med_all, const float* _
   params[10 + c] = __fsub_rn(med[10 + c], __fmul_rn(med[c], mult));
 }
 
-__global__ void __launch_bounds__(256) k_mosaic_accum(const float* __restrict__ tiles_i, const float* __restrict__ area_i,
-                                                      const unsigned char* __restrict__ water, const float* __restrict__ params,
-                                                      int HW, float* __restrict__ mosaic) {
+// mosaic += (1 - area_i) * aligned(tiles_i) for the dates [i0, i1), in date order (float32 sum order) -- one pass: the
+// running sum stays in a register (a launch per date re-read and re-wrote the 15 MB mosaic every time)
+__global__ void __launch_bounds__(256) k_mosaic_accum(const float* __restrict__ tiles, const float* __restrict__ areas,
+                                                      const unsigned char* __restrict__ water, const float* __restrict__ params_all,
+                                                      int HW, int i0, int i1, float* __restrict__ mosaic) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)HW * 10) return;
   int p = (int)(idx / 10), c = (int)(idx % 10);
-  float x = tiles_i[idx];
-  if (!water[p]) x = __fadd_rn(__fmul_rn(x, params[c]), params[10 + c]);
-  mosaic[idx] = __fadd_rn(mosaic[idx], __fmul_rn(__fsub_rn(1.f, area_i[p]), x));
+  const bool land = !water[p];
+  float m = mosaic[idx];
+  for (int i = i0; i < i1; ++i) {
+    float x = tiles[(int64_t)i * HW * 10 + idx];
+    const float* params = params_all + i * 20;
+    if (land) x = __fadd_rn(__fmul_rn(x, params[c]), params[10 + c]);
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(1.f, areas[(int64_t)i * HW + p]), x));
+  }
+  mosaic[idx] = m;
 }
 
 __global__ void __launch_bounds__(128) k_mosaic_final(const float* __restrict__ tiles, const float* __restrict__ divisor, int n, int HW,
@@ -413,11 +421,17 @@ __global__ void __launch_bounds__(256) k_strata(const float* __restrict__ evi, c
     if (e >= b[5]) m |= 64;                     // p98
     lab[r] = m;
   }
+  // block totals first: one global atomic per stratum and block (one per warp made 150,000 atomics on seven addresses: 33 us)
+  __shared__ int tot[7];
+  if (threadIdx.x < 7) tot[threadIdx.x] = 0;
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
     unsigned bal = __ballot_sync(0xffffffffu, (m >> k) & 1);
-    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(counts + k, __popc(bal));
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&tot[k], __popc(bal));
   }
+  __syncthreads();
+  if (threadIdx.x < 7 && tot[threadIdx.x]) atomicAdd(counts + threadIdx.x, tot[threadIdx.x]);
 }
 // Index lists of the seven strata of one date, rows in ascending order (np.argwhere), the two 2 % tails repeated ten
 // times per row (np.repeat(.., 10), :468-471).  Order-preserving compaction in three GPU-wide steps (the first version
@@ -596,7 +610,7 @@ __global__ void __launch_bounds__(640) k_gram_reduce(const double* __restrict__ 
   }
   const double* src = partial + a * GRAM_ZW + b;
   double s = 0.0;
-#pragma unroll 8
+#pragma unroll 32
   for (int p = 0; p < nparts; ++p) s += src[(int64_t)p * GRAM_P];
   gram[q] = s;
 }
@@ -1078,12 +1092,16 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
         STC_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
         STC_CUDA(cudaEventCreateWithFlags(&ctx->d2h_fork, cudaEventDisableTiming));
       }
+      if (!ctx->smp_stream) STC_CUDA(cudaStreamCreateWithFlags(&ctx->smp_stream, cudaStreamNonBlocking));
       while ((int)ctx->d2h_events.size() < nf) {
         cudaEvent_t e; STC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->d2h_events.push_back(e);
+        STC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->smp_events.push_back(e);
       }
       STC_CUDA(cudaEventRecord(ctx->d2h_fork, ctx->stream));
       STC_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->d2h_fork, 0));
+      STC_CUDA(cudaStreamWaitEvent(ctx->smp_stream, ctx->d2h_fork, 0));      // d_sample_all comes from the stream-ordered pool
       for (int j = 0; j < nf; ++j) {
         const int64_t a = fits[j].list0[0], b = fits[j].list0[6] + fits[j].cnt[6];
         if (b > a) STC_CUDA(cudaMemcpyAsync(pin_lists + a, d_lists.as<int>() + a, (size_t)(b - a) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
@@ -1136,6 +1154,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       for (int j = 0; j < nf; ++j) { lists_done[j].store(0); sample_done[j].store(0); }
       auto worker = [&]() {
         PyRandom r;
+        cudaSetDevice(ctx->device);                          // event queries and the sample upload below are CUDA calls of this thread
         for (;;) {
           const size_t ti = next_task.fetch_add(1);
           if (ti >= tasks.size()) return;
@@ -1155,7 +1174,11 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
             auto append = [&](int k, size_t limit) { const size_t c = std::min(limit, (size_t)f.cnt[k]); memcpy(smp + S, pin_lists + f.list0[k], c * 4); S += c; };
             append(0, (size_t)f.cnt[0]); for (int k = 1; k <= 5; ++k) append(k, n_i); append(6, (size_t)f.cnt[6]);   // [p2, p20, p40, p60, p80, p100, p98]
             r.shuffle(smp, S);
-            sample_done[t.j].store(1, std::memory_order_release);
+            // the upload starts here, next to the device work of the earlier dates; the compute stream waits on the event
+            const size_t up = std::min(S, (size_t)f.K);
+            const cudaError_t ce = cudaMemcpyAsync(d_sample_all.as<int>() + sample0[t.j], smp, up * 4, cudaMemcpyHostToDevice, ctx->smp_stream);
+            const cudaError_t ee = cudaEventRecord(ctx->smp_events[t.j], ctx->smp_stream);
+            sample_done[t.j].store((ce == cudaSuccess && ee == cudaSuccess) ? 1 : -1, std::memory_order_release);
           }
         }
       };
@@ -1223,9 +1246,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       if ((rc = run_select(jobs, specs, d_medall.as<float>() + start * 20))) return rc;
       STC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1], 0));
       CF_LAUNCH(k_scale_params, cv, 32, d_medall.as<float>() + start * 20, d_sdall.as<float>() + start * 20, d_paramsall.as<float>() + start * 20);
-      for (int i = start; i < f; ++i)
-        CF_LAUNCH(k_mosaic_accum, cdiv(slab, 256), 256, tiles + (int64_t)i * slab, areas + (int64_t)i * HW, water0,
-                  d_paramsall.as<float>() + i * 20, HW, mosaic);
+      CF_LAUNCH(k_mosaic_accum, cdiv(slab, 256), 256, tiles, areas, water0, d_paramsall.as<float>(), HW, start, f, mosaic);
     }
     if (f < n && land_px > 0)
       CF_LAUNCH(k_fill_f, cdiv(HW, 256), 256, areas + (int64_t)f * HW, (int64_t)HW, 1.f);      // interp[i] = 1. (:679-680)
@@ -1253,12 +1274,14 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
         continue;
       }
       const FitJob& f = fits[j];
-      while (!sample_done[j].load(std::memory_order_acquire)) std::this_thread::yield();
+      int sdone;
+      while (!(sdone = sample_done[j].load(std::memory_order_acquire))) std::this_thread::yield();
+      if (sdone < 0) STC_FAIL(STC_ERR_CUDA, "remove_clouds: sample upload failed");
       int* smp = pin_samples + sample0[j];
       size_t S = S_of[j];
       if (S > (size_t)f.K) S = (size_t)f.K;
       int* d_smp = d_sample_all.as<int>() + sample0[j];
-      STC_CUDA(cudaMemcpyAsync(d_smp, smp, S * 4, cudaMemcpyHostToDevice, ctx->stream));
+      STC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->smp_events[j], 0));
       CF_LAUNCH(k_snow_mean, cdiv(HW, 256), 256, sp, n, HW, d_snow.as<float>());
       const int gb = std::min(gram_blocks, cdiv((int64_t)S, GRAM_ROWS));
       CF_LAUNCH(k_gram_rows, cdiv((int64_t)S * GRAM_ZW, 256), 256, tiles, mosaic, d_snow.as<float>(), d_rows_all.as<int>() + f.row0, d_smp, (int)S, HW,

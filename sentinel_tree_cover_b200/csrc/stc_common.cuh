@@ -111,6 +111,8 @@ struct stc_ctx {
   cudaStream_t aux_stream = nullptr; cudaEvent_t aux_ev[2] = {nullptr, nullptr};
   // remove_clouds: the per-date index lists go to the host on their own stream, one event per date (stc_cloudfill.cu)
   cudaStream_t d2h_stream = nullptr; cudaEvent_t d2h_fork = nullptr; std::vector<cudaEvent_t> d2h_events;
+  // ... and the shuffled sample of a date comes back on a third one, issued by the worker thread that finished it
+  cudaStream_t smp_stream = nullptr; std::vector<cudaEvent_t> smp_events;
 };
 static constexpr size_t STC_STAGE_RING = 8u << 20;
 // copy `bytes` of host data into the pinned ring and return the pinned address (valid until the ring wraps: 8 MB of tables)

@@ -12,6 +12,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=12)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--trace", default=None, help="CSV path: one more chain tile with CUDA events around every kernel launch")
     args = ap.parse_args()
     from oracle import tile_ref                       # synthetic raw tile only
     from sentinel_tree_cover_b200 import api, tile
@@ -50,6 +51,18 @@ def main():
         chain.append(round((time.perf_counter() - t0) * 1e3, 1))
     if not res:
         out = out2                         # --reps 0: the chain alone (profiling runs)
+    if args.trace:
+        sess.trace(1)
+        random.seed(4)
+        sess.run_tile(pin["s2_10"], pin["s2_20"], pin["s1"], pin["dem"], raw["s2_dates"])
+        sess.trace(0, args.trace)
+        tot = {}
+        import csv
+        for r in csv.DictReader(open(args.trace)):
+            e = tot.setdefault(r["label"], [0, 0.0]); e[0] += 1; e[1] += float(r["end_ms"]) - float(r["start_ms"])
+        print("kernel table (launches, ms, us/launch), sum %.2f ms" % sum(v[1] for v in tot.values()), file=sys.stderr)
+        for name, (k, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:40]:
+            print("  %-28s %4d %8.3f %8.1f" % (name, k, ms, ms / k * 1e3), file=sys.stderr)
     print(json.dumps({"tile": "618x618, %d dates, synthetic raw (uint16 S2/S1, f32 DEM)" % args.n, "runs": res,
                       "chain_ms": chain, "chain_equals_mirrors": bool(np.array_equal(out2, out)),
                       "chain_vs_mirrors_differing_px": int((out2 != out).sum()), "chain_vs_mirrors_max_abs": int(np.abs(out2.astype(int) - out.astype(int)).max()),
