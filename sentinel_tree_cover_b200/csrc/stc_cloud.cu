@@ -8,6 +8,7 @@
 // Stage-by-stage parity is checked against oracle/cloud_ref.py (tests/test_cloud_masks.py).
 #include "stc_common.cuh"
 #include "stc_select.cuh"
+#include "stc_sortnet.cuh"
 #include <cmath>
 int pfcp_detect_dev(stc_ctx* ctx, const float* img, const float* dem, const unsigned char* urban_core, const unsigned char* urban_near, int T,
                     int H, int W, unsigned char* fcps_out, unsigned char* pfps_out);
@@ -78,10 +79,8 @@ __global__ void __launch_bounds__(256) k_hollstein(const float* __restrict__ img
   clm[i] = (p[7] > 0.166f) && (p[1] > 0.28f) && (__fdiv_rn(p[5], p[8]) < 4.292f);
 }
 
-__global__ void __launch_bounds__(128) k_static_refs(const float* __restrict__ img, const unsigned char* __restrict__ clm, int T, int HW,
-                                                     StaticRefs o) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
+// one pixel by insertion sorts (the reference transcription): the route for pixels holding a NaN / infinity
+__device__ void static_refs_px(const float* __restrict__ img, const unsigned char* __restrict__ clm, int T, int HW, int p, const StaticRefs& o) {
   float v[CT_MAX];
   // water = nanmedian_t (B3 - B8)/(B3 + B8)
   int n = 0;
@@ -114,10 +113,81 @@ __global__ void __launch_bounds__(128) k_static_refs(const float* __restrict__ i
     o.minrgb[p * 3 + k] = mn;
   }
 }
+// The same statistics with the dates of a pixel in registers and sorting networks of N >= T slots (stc_sortnet.cuh): the
+// seven bands the stage uses are loaded once per date, the eight sorts per pixel cost 8 x 240 compare-exchanges at N = 32.
+template <int N>
+__global__ void __launch_bounds__(128) k_static_refs(const float* __restrict__ img, const unsigned char* __restrict__ clm, int T, int HW,
+                                                     StaticRefs o) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  // bands 0, 1, 2, 3, 7, 8 of every date (b[.][t]), Hollstein flags as a bit mask
+  float b0[N], b1[N], b2[N], b3[N], b7[N], b8[N];
+  unsigned cloudy = 0; bool ok = true;
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    b0[t] = b1[t] = b2[t] = b3[t] = b7[t] = b8[t] = INFINITY;
+    if (t < T) {
+      const float* q = img + ((int64_t)t * HW + p) * 10;
+      b0[t] = q[0]; b1[t] = q[1]; b2[t] = q[2]; b3[t] = q[3]; b7[t] = q[7]; b8[t] = q[8];
+      ok = ok && net_ok(b0[t]) && net_ok(b1[t]) && net_ok(b2[t]) && net_ok(b3[t]) && net_ok(b7[t]) && net_ok(b8[t]);
+      if (clm[(int64_t)t * HW + p]) cloudy |= 1u << t;
+    }
+  }
+  float v[N];
+  int n = 0;
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    float x = INFINITY;
+    if (t < T) {
+      x = __fdiv_rn(__fsub_rn(b1[t], b3[t]), __fadd_rn(b1[t], b3[t]));
+      if (isnan(x)) x = INFINITY; else { ++n; ok = ok && net_ok(x); }
+    }
+    v[t] = x;
+  }
+  if (!ok) { static_refs_px(img, clm, T, HW, p, o); return; }
+  sort_net<N>(v);
+  o.water[p] = net_median<N>(v, n);
+  const int nn = T - __popc(cloudy);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float (&bk)[N] = k == 0 ? b0 : k == 1 ? b1 : k == 2 ? b7 : b8;
+    float mn = INFINITY;
+#pragma unroll
+    for (int t = 0; t < N; ++t) { if (t < T) mn = fminf(mn, bk[t]); v[t] = (t < T && !((cloudy >> t) & 1u)) ? bk[t] : INFINITY; }
+    float r;
+    if (nn > 0) { sort_net<N>(v); r = net_median<N>(v, nn); }
+    else {                                                      // every date flagged: np.median over all dates (:1303-1304)
+#pragma unroll
+      for (int t = 0; t < N; ++t) v[t] = bk[t];
+      sort_net<N>(v); r = net_median<N>(v, T);
+    }
+    o.allref[p * 4 + k] = r;
+    o.minb4[p * 4 + k] = mn;
+  }
+  // np.percentile(a, 25, axis=0): positions as in percentile25_sorted
+  const double vi = 0.25 * (double)(T - 1);
+  const int lo = (int)floor(vi);
+  const float g = (float)(vi - (double)lo);
+  const int hi = lo + 1 < T ? lo + 1 : T - 1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float (&bk)[N] = k == 0 ? b0 : k == 1 ? b1 : b2;
+    float mn = INFINITY;
+#pragma unroll
+    for (int t = 0; t < N; ++t) { if (t < T) mn = fminf(mn, bk[t]); v[t] = bk[t]; }
+    sort_net<N>(v);
+    const float a = net_pick<N>(v, lo), bb = net_pick<N>(v, hi);
+    const float d = __fsub_rn(bb, a);
+    o.p25[p * 3 + k] = (g >= 0.5f) ? __fsub_rn(bb, __fmul_rn(d, __fsub_rn(1.f, g))) : __fadd_rn(a, __fmul_rn(d, g));
+    o.minrgb[p * 3 + k] = mn;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // stage B: per-date shadow candidates (:1265-1324)
 // ---------------------------------------------------------------------------------------------
+// N >= the longest date window: the window's values sit in registers and are sorted by a network (stc_sortnet.cuh)
+template <int N>
 __global__ void __launch_bounds__(128) k_shadow_candidates(const float* __restrict__ img, const unsigned char* __restrict__ clm,
                                                            const float* __restrict__ dem, StaticRefs s, int T, int HW,
                                                            const int* __restrict__ win_lo, const int* __restrict__ win_hi,
@@ -126,19 +196,40 @@ __global__ void __launch_bounds__(128) k_shadow_candidates(const float* __restri
   const int t = blockIdx.y;
   if (p >= HW) return;
   const int lo = win_lo[t], hi = win_hi[t];
-  const int bsel[4] = {0, 1, 7, 8};
   float rmed[4], rmax[4];
+  unsigned use = 0;                                   // window dates that are not Hollstein-flagged
+#pragma unroll
+  for (int i = 0; i < N; ++i) if (lo + i < hi && !clm[(int64_t)(lo + i) * HW + p]) use |= 1u << i;
+  const int n = __popc(use);
+  bool ok = true;
+#pragma unroll
   for (int k = 0; k < 4; ++k) {
-    float v[CT_MAX]; int n = 0; float mx = -INFINITY;
-    for (int tt = lo; tt < hi; ++tt) {
-      if (clm[(int64_t)tt * HW + p]) continue;
-      float x = img[((int64_t)tt * HW + p) * 10 + bsel[k]];
-      v[n++] = x; mx = fmaxf(mx, x);
+    const int band = k == 0 ? 0 : k == 1 ? 1 : k == 2 ? 7 : 8;
+    float v[N]; float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float x = INFINITY;
+      if ((use >> i) & 1u) { x = img[((int64_t)(lo + i) * HW + p) * 10 + band]; ok = ok && net_ok(x); mx = fmaxf(mx, x); }
+      v[i] = x;
     }
-    isort(v, n);
-    float m = median_sorted(v, n);
+    sort_net<N>(v);
     rmax[k] = n ? mx : nanf("");
-    rmed[k] = isnan(m) ? s.minb4[p * 4 + k] : m;
+    rmed[k] = n ? net_median<N>(v, n) : s.minb4[p * 4 + k];
+  }
+  if (!ok) {                                          // a NaN / infinity in the window: the insertion-sort transcription
+    const int bsel[4] = {0, 1, 7, 8};
+    for (int k = 0; k < 4; ++k) {
+      float v[CT_MAX]; int nn = 0; float mx = -INFINITY;
+      for (int tt = lo; tt < hi; ++tt) {
+        if (clm[(int64_t)tt * HW + p]) continue;
+        float x = img[((int64_t)tt * HW + p) * 10 + bsel[k]];
+        v[nn++] = x; mx = fmaxf(mx, x);
+      }
+      isort(v, nn);
+      float m = median_sorted(v, nn);
+      rmax[k] = nn ? mx : nanf("");
+      rmed[k] = isnan(m) ? s.minb4[p * 4 + k] : m;
+    }
   }
   const float* x = img + ((int64_t)t * HW + p) * 10;
   const float water = s.water[p];
@@ -764,18 +855,32 @@ int cloud_masks_dev(stc_ctx* ctx, const float* img, const float* dem, int T, int
   LAUNCH1D(k_hollstein, N, img, ta, N);
   dilate(ta, tb, T, 2, 1, 1, 1, 0);
   dilate(tb, clm, T, 10, 1, 0, 0, 0);
-  { TraceScope ts_(ctx, "k_static_refs"); k_static_refs<<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, clm, T, HW, sr); } ctx->launches++;
+  {
+    TraceScope ts_(ctx, "k_static_refs");
+    if (T <= 8) k_static_refs<8><<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, clm, T, HW, sr);
+    else if (T <= 16) k_static_refs<16><<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, clm, T, HW, sr);
+    else k_static_refs<32><<<cdiv(HW, 128), 128, 0, ctx->stream>>>(img, clm, T, HW, sr);
+  }
+  ctx->launches++;
   if ((rc_ = dump(1, clm))) return rc_;
 
   // ---- B: shadows ----
   {
     int wl[2 * CT_MAX];
-    for (int t = 0; t < T; ++t) shadow_window(t, T, wl[t], wl[CT_MAX + t]);
-    STC_CUDA(cudaMemcpyAsync(d_win.p, wl, sizeof(wl), cudaMemcpyHostToDevice, ctx->stream));
-    { TraceScope ts_(ctx, "k_shadow_candidates"); k_shadow_candidates<<<dim3(cdiv(HW, 128), T), 128, 0, ctx->stream>>>(img, clm, dem, sr, T, HW, (const int*)d_win.p,
-                                                                         (const int*)d_win.p + CT_MAX, ta); }
+    int wmax = 1;
+    for (int t = 0; t < T; ++t) { shadow_window(t, T, wl[t], wl[CT_MAX + t]); wmax = std::max(wmax, wl[CT_MAX + t] - wl[t]); }
+    const void* staged = ctx_stage(ctx, wl, sizeof(wl));
+    if (!staged) STC_FAIL(STC_ERR_NOMEM, "cloud_masks: pinned staging");
+    STC_CUDA(cudaMemcpyAsync(d_win.p, staged, sizeof(wl), cudaMemcpyHostToDevice, ctx->stream));
+    {
+      TraceScope ts_(ctx, "k_shadow_candidates");
+      const dim3 gs(cdiv(HW, 128), T);
+      const int* wlo = (const int*)d_win.p; const int* whi = wlo + CT_MAX;
+      if (wmax <= 8) k_shadow_candidates<8><<<gs, 128, 0, ctx->stream>>>(img, clm, dem, sr, T, HW, wlo, whi, ta);
+      else if (wmax <= 16) k_shadow_candidates<16><<<gs, 128, 0, ctx->stream>>>(img, clm, dem, sr, T, HW, wlo, whi, ta);
+      else k_shadow_candidates<32><<<gs, 128, 0, ctx->stream>>>(img, clm, dem, sr, T, HW, wlo, whi, ta);
+    }
     ctx->launches++;
-    STC_CUDA(cudaStreamSynchronize(ctx->stream));   // wl is a stack buffer
     if ((rc_ = dump(2, ta))) return rc_;
     dilate(ta, tb, T, 2, 1, 1, 1, 0);
     dilate(tb, tc, T, 3, 1, 0, 0, 0);

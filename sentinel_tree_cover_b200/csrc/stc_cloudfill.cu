@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(128) k_water_of_median(const float* __restrict
 }
 
 // counts[t] = {#a>0, #a==0, #a<1, #a==1, #(a==0 && !water)}
-__global__ void __launch_bounds__(256) k_area_counts(const float* __restrict__ areas, const unsigned char* __restrict__ water, int HW,
+__global__ void __launch_bounds__(1024) k_area_counts(const float* __restrict__ areas, const unsigned char* __restrict__ water, int HW,
                                                      int* __restrict__ counts) {
   const int t = blockIdx.y; int p = blockIdx.x * blockDim.x + threadIdx.x;
   float a = p < HW ? areas[(int64_t)t * HW + p] : -1.f;
@@ -339,13 +339,19 @@ __global__ void __launch_bounds__(256) k_area_counts(const float* __restrict__ a
   unsigned b0 = __ballot_sync(0xffffffffu, in && a > 0.f), b1 = __ballot_sync(0xffffffffu, in && a == 0.f),
            b2 = __ballot_sync(0xffffffffu, in && a < 1.f), b3 = __ballot_sync(0xffffffffu, in && a == 1.f),
            b4 = __ballot_sync(0xffffffffu, in && a == 0.f && !water[p < HW ? p : 0]);
+  // block totals in shared memory, then five global atomics per block (one set per warp serialised on 5 n addresses: 0.28-0.52 ms)
+  __shared__ int tot[5];
+  if (threadIdx.x < 5) tot[threadIdx.x] = 0;
+  __syncthreads();
   if ((threadIdx.x & 31) == 0) {
-    if (b0) atomicAdd(counts + t * 5 + 0, __popc(b0));
-    if (b1) atomicAdd(counts + t * 5 + 1, __popc(b1));
-    if (b2) atomicAdd(counts + t * 5 + 2, __popc(b2));
-    if (b3) atomicAdd(counts + t * 5 + 3, __popc(b3));
-    if (b4) atomicAdd(counts + t * 5 + 4, __popc(b4));
+    if (b0) atomicAdd(&tot[0], __popc(b0));
+    if (b1) atomicAdd(&tot[1], __popc(b1));
+    if (b2) atomicAdd(&tot[2], __popc(b2));
+    if (b3) atomicAdd(&tot[3], __popc(b3));
+    if (b4) atomicAdd(&tot[4], __popc(b4));
   }
+  __syncthreads();
+  if (threadIdx.x < 5 && tot[threadIdx.x]) atomicAdd(counts + t * 5 + threadIdx.x, tot[threadIdx.x]);
 }
 
 // snow probability of one pixel-date (:348-370), float32 as NumPy evaluates it
@@ -997,7 +1003,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
     STC_CUDA(stc_dmalloc(&d_flag3.p, (size_t)n * HW)); STC_CUDA(stc_dmalloc(&d_pos3.p, (size_t)n * HW * 4)); STC_CUDA(stc_dmalloc(&d_K3.p, CF_MAX_DATES * 4));
     CF_LAUNCH(k_water_of_median, cdiv(HW, 128), 128, tiles, n, HW, water1);
     STC_CUDA(cudaMemsetAsync(d_counts.p, 0, CF_MAX_DATES * 5 * 4, ctx->stream));
-    CF_LAUNCH(k_area_counts, dim3(cdiv(HW, 256), n), 256, areas, water1, HW, d_counts.as<int>());
+    CF_LAUNCH(k_area_counts, dim3(cdiv(HW, 1024), n), 1024, areas, water1, HW, d_counts.as<int>());
     CF_LAUNCH(k_flag_clear_land, dim3(cdiv(HW, 256), n), 256, areas, water1, HW, d_flag3.as<unsigned char>());
     if ((rc = scan_flags_dev(ctx, d_flag3.as<unsigned char>(), n, HW, d_pos3.as<int>(), d_K3.as<int>()))) return rc;
     STC_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, n * 20, cudaMemcpyDeviceToHost, ctx->stream));

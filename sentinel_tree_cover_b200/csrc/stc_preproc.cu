@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "stc_indices.cuh"
+#include "stc_sortnet.cuh"
 
 // monthly [B,12,H,W,13] -> out [B,5,H,W,17]
 __global__ void __launch_bounds__(128) assemble_kernel(const float* __restrict__ in, float* __restrict__ out,
@@ -306,17 +307,40 @@ int pre_indices_dev(stc_ctx* ctx, const float* in_dev, int64_t npix, int C, floa
 }
 
 // ---- temporal median ----------------------------------------------------------------------
+// N >= n slots in registers, sorted by a network (stc_sortnet.cuh); a column holding a NaN / infinity takes the insertion sort,
+// whose placement of NaN the callers rely on (interpolate_na_vals goldens)
+template <int N>
 __global__ void __launch_bounds__(256) temporal_median_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int64_t inner) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= inner) return;
-  float v[32];
-  for (int t = 0; t < n; ++t) v[t] = in[(int64_t)t * inner + i];
-  out[i] = median_n<32>(v, n);
+  float v[N];
+  bool ok = true;
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    float x = INFINITY;
+    if (t < n) { x = in[(int64_t)t * inner + i]; ok = ok && net_ok(x); }
+    v[t] = x;
+  }
+  if (!ok) {
+    float w[32];
+    for (int t = 0; t < n; ++t) w[t] = in[(int64_t)t * inner + i];
+    out[i] = median_n<32>(w, n);
+    return;
+  }
+  sort_net<N>(v);
+  out[i] = net_median<N>(v, n);
 }
 
 int pre_temporal_median_dev(stc_ctx* ctx, const float* in_dev, int n, int64_t inner, float* out_dev) {
   if (n < 1 || n > 32) STC_FAIL(STC_ERR_ARG, "temporal_median: n must be in 1..32");
-  { TraceScope ts_(ctx, "temporal_median_kernel"); temporal_median_kernel<<<cdiv(inner, 256), 256, 0, ctx->stream>>>(in_dev, out_dev, n, inner); }
+  {
+    TraceScope ts_(ctx, "temporal_median_kernel");
+    const int grid = cdiv(inner, 256);
+    if (n <= 4) temporal_median_kernel<4><<<grid, 256, 0, ctx->stream>>>(in_dev, out_dev, n, inner);
+    else if (n <= 8) temporal_median_kernel<8><<<grid, 256, 0, ctx->stream>>>(in_dev, out_dev, n, inner);
+    else if (n <= 16) temporal_median_kernel<16><<<grid, 256, 0, ctx->stream>>>(in_dev, out_dev, n, inner);
+    else temporal_median_kernel<32><<<grid, 256, 0, ctx->stream>>>(in_dev, out_dev, n, inner);
+  }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;
