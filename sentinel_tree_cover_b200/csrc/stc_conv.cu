@@ -786,7 +786,13 @@ static int launch_umma2(stc_ctx* ctx, const ConvParams& p, int ndir, int iss_req
   constexpr int B_BYTES = 9 * 2 * N * 16;
   // Shared-memory budget: leave room (default 64 KB + registers; measured best of 131/163/195/227) for blocks of the HBM-bound elementwise kernels of the
   // other chunk to be co-resident with the persistent conv CTA (STC_CONV_SMEM_KB, A/B switch).
-  static const int SMEM_MAX = (getenv("STC_CONV_SMEM_KB") ? atoi(getenv("STC_CONV_SMEM_KB")) : 163) * 1024;
+  static const int SMEM_MAX_1 = (getenv("STC_CONV_SMEM_KB") ? atoi(getenv("STC_CONV_SMEM_KB")) : 163) * 1024;
+  // The DSen2 convolutions (32 input channels: two K-steps, 18 small MMAs per sub-tile) are bound by their loads and stores,
+  // not by the tensor pipe: two CTAs per SM (each with half the shared-memory budget and 256 of the 512 TMEM columns) keep
+  // twice the copies and epilogue stores in flight.  STC_SR_OCC=1 restores one CTA per SM (A/B).
+  static const int sr_occ = getenv("STC_SR_OCC") ? atoi(getenv("STC_SR_OCC")) : 2;
+  const bool two_ctas = (MODE == MODE_BIAS || MODE == MODE_BIAS_RELU) && N <= 32 && sr_occ >= 2;
+  const int SMEM_MAX = two_ctas ? std::min(SMEM_MAX_1, 104 * 1024) : SMEM_MAX_1;
   static bool configured = false;
   auto kern = conv3x3_umma2_kernel<N, NT, G, MODE, WRES>;
   if (!configured) {
@@ -805,7 +811,7 @@ static int launch_umma2(stc_ctx* ctx, const ConvParams& p, int ndir, int iss_req
   const int smem_bytes = w_bytes + stages * stage_bytes + 256;
   const int tps = cdiv((int64_t)p.Hp * p.Wp, NT * 128);        // super-tiles per sample (sample-aligned, see conv_epilogue)
   const int tiles_per_dir = tps * p.B;
-  int per_dir = ctx->num_sms / ndir;               // CTAs per direction
+  int per_dir = (two_ctas ? 2 * ctx->num_sms : ctx->num_sms) / ndir;               // CTAs per direction
   if (per_dir > tiles_per_dir) per_dir = tiles_per_dir;
   const int tiles_per_cta = cdiv(tiles_per_dir, per_dir);
   per_dir = cdiv(tiles_per_dir, tiles_per_cta);
