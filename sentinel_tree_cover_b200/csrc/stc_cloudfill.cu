@@ -515,20 +515,23 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const BucketJob* __restr
 // for j < 10 (c_10 = u_10), targets y_b = tile bands of the row's (date, pixel).
 // gram layout (583 doubles): UU[11][11], CU[11][11] (c_j * u_k), CC[11][11], UY[11][10], CY[11][10].
 //
-// Two kernels.  k_gram_rows follows the sample -> row -> (date, pixel) indirection once, with the whole GPU, and writes the
-// row z = [u0..u10 | c0..c9 | y0..y9 | 0] (32 floats) of every sampled row.  k_gram then forms z_a * z_b for a < 24, all b:
-// one WARP per partial sum, each lane a 6 x 4 register tile (5 shared-memory loads per 24 FMAs; the round-1 kernel spent its
-// time on two loads and two float->double conversions per FMA: 206 us per date).  Every entry is still accumulated in row
-// order over the warp's 64-row groups (group g of partial b = rows [64 (b + g P), +64)), and the P partials are added in
-// order, so the sums do not depend on the schedule.
+// k_gram_rows follows the sample -> row -> (date, pixel) indirection once, with the whole GPU, and writes the row
+// z = [u0..u10 | c0..c9 | y0..y9 | 0] (32 floats) of every sampled row.  k_gram then forms z_a * z_b for a < 24, all b, from
+// register tiles (5 shared-memory loads per 12 FMAs; the round-1 kernel spent its time on two loads and two float->double
+// conversions per FMA: 206 us per date).  Every entry is still accumulated in row order over its partial's 64-row groups
+// (group g of partial b = rows [64 (b + g P), +64)), and the P partials are added in order, so the sums do not depend on
+// the schedule and are the ones the first version produced.
 #define GRAM_N (3 * NF * NF + 2 * NF * 10)
 #define GRAM_ROWS 64
 #define GRAM_ZW 32                      // floats per staged row
 #define GRAM_PA 24                      // a-side entries computed per row (21 needed)
 #define GRAM_P (GRAM_PA * GRAM_ZW)      // products per partial
-__global__ void __launch_bounds__(256) k_gram_rows(const float* __restrict__ tiles, const float* __restrict__ mosaic, const float* __restrict__ snow,
+// Everything of a row except the snow feature is known before the per-date loop starts (the rows are clear land, weights == 0,
+// which no blend touches; the mosaic is final), so this gather runs AHEAD on the sample stream; k_gram_snow then drops the one
+// value that depends on the blends of the earlier dates into slot 10.
+__global__ void __launch_bounds__(256) k_gram_rows(const float* __restrict__ tiles, const float* __restrict__ mosaic,
                                                    const int* __restrict__ rowsrc, const int* __restrict__ sample, int S, int HW,
-                                                   float* __restrict__ Z /*[S][32]*/) {
+                                                   float* __restrict__ Z /*[S][32]*/, int* __restrict__ pix /*[S]*/) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t s = e >> 5;
   const int f = (int)(e & 31);
@@ -537,64 +540,66 @@ __global__ void __launch_bounds__(256) k_gram_rows(const float* __restrict__ til
   const int p = src % HW;
   float v = 0.f;
   if (f < 10) v = mosaic[(int64_t)p * 10 + f];
-  else if (f == 10) v = snow[p];
+  else if (f == 10) pix[s] = p;
   else if (f < 21) v = fminf(fmaxf(mosaic[(int64_t)p * 10 + (f - 11)], 0.005f), 1.f);
   else if (f < 31) v = tiles[(int64_t)src * 10 + (f - 21)];
   Z[e] = v;
 }
-__global__ void __launch_bounds__(64) k_gram(const float* __restrict__ Z, int S, int nparts, double* __restrict__ partial /*[nparts][GRAM_P]*/) {
-  __shared__ __align__(16) double zs[2][32][GRAM_ZW];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int part = blockIdx.x * 2 + w;
-  if (part >= nparts) return;                       // warps are independent: only __syncwarp below
-  double (*zz)[GRAM_ZW] = zs[w];
-  const int a0 = (lane >> 3) * 6, b0 = (lane & 7) * 4;
-  double acc[6][4];
+__global__ void __launch_bounds__(256) k_gram_snow(const float* __restrict__ snow, const int* __restrict__ pix, int S, float* __restrict__ Z) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < S) Z[(int64_t)s * GRAM_ZW + 10] = snow[pix[s]];
+}
+// One partial sum = two warps (a-rows 0..11 and 12..23 of the 24 x 32 products, a 3 x 4 register tile per lane) sharing the
+// staged rows; two partials per block.  The pair synchronises on a named barrier, rows are double-buffered in shared memory and
+// the next sub-batch is already in registers while this one is multiplied.
+__global__ void __launch_bounds__(128) k_gram(const float* __restrict__ Z, int S, int nparts, double* __restrict__ partial /*[nparts][GRAM_P]*/) {
+  __shared__ __align__(16) double zs[2][2][32][GRAM_ZW];
+  const int q = threadIdx.x >> 6, t64 = threadIdx.x & 63, h = t64 >> 5, lane = threadIdx.x & 31;
+  const int part = blockIdx.x * 2 + q;
+  if (part >= nparts) return;                       // both warps of the pair leave together: the pair's barrier is never half-used
+  const int a0 = 12 * h + (lane >> 3) * 3, b0 = (lane & 7) * 4;
+  double acc[3][4];
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  // sub-batches of 32 rows; the next one is in flight (registers) while this one is multiplied
-  float4 pre[8];
+  float4 pre[4];
   auto rows_of = [&](int t, int64_t& s) { s = ((int64_t)part + (int64_t)(t >> 1) * nparts) * GRAM_ROWS + (t & 1) * 32; const int64_t left = (int64_t)S - s; return (int)(left < 32 ? (left < 0 ? 0 : left) : 32); };
   auto fetch = [&](int64_t s, int rr) {
     const float4* src = reinterpret_cast<const float4*>(Z + s * GRAM_ZW);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { const int i = lane + 32 * k; pre[k] = (i < rr * 8) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int k = 0; k < 4; ++k) { const int i = t64 + 64 * k; pre[k] = (i < rr * 8) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f); }
   };
-  int t = 0; int64_t s; int rr = rows_of(0, s);
+  int t = 0, buf = 0; int64_t s; int rr = rows_of(0, s);
   if (rr > 0) fetch(s, rr);
   while (rr > 0) {
-    __syncwarp();
+    double (*zz)[GRAM_ZW] = zs[q][buf];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = lane + 32 * k, r = i >> 3, c = (i & 7) * 4;
+    for (int k = 0; k < 4; ++k) {
+      const int i = t64 + 64 * k, r = i >> 3, c = (i & 7) * 4;
       *reinterpret_cast<double2*>(&zz[r][c]) = make_double2((double)pre[k].x, (double)pre[k].y);
       *reinterpret_cast<double2*>(&zz[r][c + 2]) = make_double2((double)pre[k].z, (double)pre[k].w);
     }
-    __syncwarp();
+    asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
     const int cur = rr;
-    // the second half of a 64-row group may be empty while later groups are not needed either: S is the global end
     ++t; rr = rows_of(t, s);
     if (rr == 0 && (t & 1)) { ++t; rr = rows_of(t, s); }
     if (rr > 0) fetch(s, rr);
-#pragma unroll 2
+#pragma unroll 4
     for (int r = 0; r < cur; ++r) {
-      double a[6], b[4];
-      const double2 a01 = *reinterpret_cast<const double2*>(&zz[r][a0]), a23 = *reinterpret_cast<const double2*>(&zz[r][a0 + 2]),
-                    a45 = *reinterpret_cast<const double2*>(&zz[r][a0 + 4]);
+      const double a[3] = {zz[r][a0], zz[r][a0 + 1], zz[r][a0 + 2]};
       const double2 b01 = *reinterpret_cast<const double2*>(&zz[r][b0]), b23 = *reinterpret_cast<const double2*>(&zz[r][b0 + 2]);
-      a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y; a[4] = a45.x; a[5] = a45.y;
-      b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
+      const double b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-      for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);       // the product of two floats is exact in double
     }
+    buf ^= 1;
   }
   double* out = partial + (int64_t)part * GRAM_P;
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) out[(a0 + i) * GRAM_ZW + b0 + j] = acc[i][j];
 }
@@ -924,7 +929,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
     cf_t = t;
   };
   DBuf d_ta, d_tb, d_sums, d_water0, d_water1, d_flag, d_u8a, d_u8b, d_pf, d_ref, d_pos, d_src_rows,
-      d_ref_rows, d_mosaic, d_div, d_snow, d_partial, d_gramz, d_gram, d_coef, d_status, d_qout,
+      d_ref_rows, d_mosaic, d_div, d_snow, d_partial, d_gramz, d_pix, d_gram, d_coef, d_status, d_qout,
       d_sd, d_params, d_cnt, d_counts;
   const int gram_blocks = 296;
   STC_CUDA(stc_dmalloc(&d_ta.p, N * 4)); STC_CUDA(stc_dmalloc(&d_tb.p, N * 4)); STC_CUDA(stc_dmalloc(&d_sums.p, CF_MAX_DATES * 4));
@@ -985,7 +990,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   std::vector<int64_t> sample0;
   std::vector<ShufTask> tasks;
   std::atomic<size_t> published{0};
-  std::vector<size_t> S_of;
+  std::vector<size_t> S_of, zoff;
   double tt0 = 0, t_skip = 0;
   long long n_draw = 0;
   std::unique_ptr<std::atomic<int>[]> lists_done, sample_done;
@@ -1132,9 +1137,12 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
         S_of[j] = S;
       }
       {
-        size_t s_max = 1;
-        for (int j = 0; j < nf; ++j) s_max = std::max(s_max, std::min(S_of[j], (size_t)fits[j].K));
-        STC_CUDA(stc_dmalloc(&d_gramz.p, s_max * GRAM_ZW * 4));
+        // staged rows of every date (k_gram_rows runs ahead of the per-date chain, so each date keeps its own)
+        zoff.assign(nf, 0);
+        size_t s_tot = 0;
+        for (int j = 0; j < nf; ++j) { zoff[j] = s_tot; s_tot += std::min(S_of[j], (size_t)fits[j].K); }
+        STC_CUDA(stc_dmalloc(&d_gramz.p, std::max<size_t>(s_tot, 1) * GRAM_ZW * 4));
+        STC_CUDA(stc_dmalloc(&d_pix.p, std::max<size_t>(s_tot, 1) * 4));
       }
       tt0 = cf_timing ? cf_now() : 0;
       auto walker = [&, this_n = n]() {
@@ -1183,8 +1191,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
             // the upload starts here, next to the device work of the earlier dates; the compute stream waits on the event
             const size_t up = std::min(S, (size_t)f.K);
             const cudaError_t ce = cudaMemcpyAsync(d_sample_all.as<int>() + sample0[t.j], smp, up * 4, cudaMemcpyHostToDevice, ctx->smp_stream);
-            const cudaError_t ee = cudaEventRecord(ctx->smp_events[t.j], ctx->smp_stream);
-            sample_done[t.j].store((ce == cudaSuccess && ee == cudaSuccess) ? 1 : -1, std::memory_order_release);
+            sample_done[t.j].store(ce == cudaSuccess ? 1 : -1, std::memory_order_release);
           }
         }
       };
@@ -1271,6 +1278,8 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
     STC_CUDA(stc_dmalloc(&d_sp.p, (size_t)n * HW * 4));
     float* sp = d_sp.as<float>();
     CF_LAUNCH(k_snow_planes, cdiv((int64_t)n * HW, 256), 256, tiles, n, HW, sp);
+    STC_CUDA(cudaEventRecord(ctx->d2h_fork, ctx->stream));                 // the mosaic is final: the sample stream may gather rows
+    STC_CUDA(cudaStreamWaitEvent(ctx->smp_stream, ctx->d2h_fork, 0));
     for (int d = 0; d < n; ++d) {
       const int j = fit_of[d];
       if (j < 0) {
@@ -1287,12 +1296,21 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       size_t S = S_of[j];
       if (S > (size_t)f.K) S = (size_t)f.K;
       int* d_smp = d_sample_all.as<int>() + sample0[j];
-      STC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->smp_events[j], 0));
+      float* Zj = d_gramz.as<float>() + zoff[j] * GRAM_ZW;
+      int* pixj = d_pix.as<int>() + zoff[j];
+      {
+        // the snow-independent part of the rows: on the sample stream, behind the upload the worker enqueued there, next to the
+        // chain of the earlier dates on the compute stream
+        cudaStream_t keep = ctx->stream; ctx->stream = ctx->smp_stream;
+        CF_LAUNCH(k_gram_rows, cdiv((int64_t)S * GRAM_ZW, 256), 256, tiles, mosaic, d_rows_all.as<int>() + f.row0, d_smp, (int)S, HW, Zj, pixj);
+        ctx->stream = keep;
+        STC_CUDA(cudaEventRecord(ctx->smp_events[j], ctx->smp_stream));
+        STC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->smp_events[j], 0));
+      }
       CF_LAUNCH(k_snow_mean, cdiv(HW, 256), 256, sp, n, HW, d_snow.as<float>());
+      CF_LAUNCH(k_gram_snow, cdiv((int64_t)S, 256), 256, d_snow.as<float>(), pixj, (int)S, Zj);
       const int gb = std::min(gram_blocks, cdiv((int64_t)S, GRAM_ROWS));
-      CF_LAUNCH(k_gram_rows, cdiv((int64_t)S * GRAM_ZW, 256), 256, tiles, mosaic, d_snow.as<float>(), d_rows_all.as<int>() + f.row0, d_smp, (int)S, HW,
-                d_gramz.as<float>());
-      CF_LAUNCH(k_gram, cdiv(gb, 2), 64, d_gramz.as<float>(), (int)S, gb, d_partial.as<double>());
+      CF_LAUNCH(k_gram, cdiv(gb, 2), 128, Zj, (int)S, gb, d_partial.as<double>());
       CF_LAUNCH(k_gram_reduce, 1, 640, d_partial.as<double>(), gb, d_gram.as<double>());
       if (nnls_serial) CF_LAUNCH(k_nnls_serial, 1, 32, d_gram.as<double>(), (int)S, d_coef.as<double>(), d_status_all.as<int>() + 10 * j);
       else CF_LAUNCH(k_nnls, 1, 320, d_gram.as<double>(), (int)S, d_coef.as<double>(), d_status_all.as<int>() + 10 * j);

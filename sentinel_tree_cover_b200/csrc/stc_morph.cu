@@ -84,6 +84,54 @@ __global__ void __launch_bounds__(256) k_dilate_col(const unsigned char* __restr
   out[idx] = (unsigned char)(hit ^ inv_out);
 }
 
+// The same column pass for larger radii (2-D balls only) as two one-sided running minima instead of a (2k + 1)-entry search:
+// the L1 ball holds a set pixel iff min over yy of g[yy] + |yy - y| <= k (g = k + 1 where the row has none within k), and that
+// minimum is min(forward scan, backward scan) of d <- min(g, d + 1); the Linf ball is the same with g' = (g <= k ? 0 : inf).
+// One thread per (frame, 64-row segment, column), each scan started k rows outside the segment: 2 + k / 16 steps per pixel
+// instead of 2k + 1 (the k = 32 and k = 50 dilations of the cloud stage took 0.09-0.24 ms each on a 24-date tile).
+#define DCS_SEG 64
+__global__ void __launch_bounds__(128) k_dilate_col_scan(const unsigned char* __restrict__ g, unsigned char* __restrict__ out, int T, int H, int W,
+                                                         int k, int conn, int inv_out) {
+  const int segs = (H + DCS_SEG - 1) / DCS_SEG;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)T * segs * W) return;
+  const int x = (int)(idx % W); const int64_t r = idx / W; const int seg = (int)(r % segs); const int t = (int)(r / segs);
+  const unsigned char* gg = g + (int64_t)t * H * W + x;
+  unsigned char* oo = out + (int64_t)t * H * W + x;
+  const int ys = seg * DCS_SEG, ye = min(ys + DCS_SEG, H);
+  const bool linf = conn != 1;
+  int d = 255;
+  for (int yy = max(ys - k, 0); yy < ye; ++yy) {
+    int gv = gg[(int64_t)yy * W];
+    if (linf) gv = gv <= k ? 0 : 255;
+    d = min(gv, d + 1);
+    if (yy >= ys) oo[(int64_t)yy * W] = (unsigned char)min(d, 255);
+  }
+  d = 255;
+  for (int yy = min(ye - 1 + k, H - 1); yy >= ys; --yy) {
+    int gv = gg[(int64_t)yy * W];
+    if (linf) gv = gv <= k ? 0 : 255;
+    d = min(gv, d + 1);
+    if (yy < ye) {
+      const int best = min(d, (int)oo[(int64_t)yy * W]);
+      oo[(int64_t)yy * W] = (unsigned char)((best <= k ? 1 : 0) ^ inv_out);
+    }
+  }
+}
+static void launch_dilate_col(stc_ctx* ctx, const unsigned char* g, unsigned char* out, int frames, int H, int W, int k, int conn, int inv_out,
+                              int three_d) {
+  const int64_t N = (int64_t)frames * H * W;
+  if (!three_d && k >= 6) {
+    const int64_t work = (int64_t)frames * ((H + DCS_SEG - 1) / DCS_SEG) * W;
+    TraceScope ts_(ctx, "k_dilate_col_scan");
+    k_dilate_col_scan<<<cdiv(work, 128), 128, 0, ctx->stream>>>(g, out, frames, H, W, k, conn, inv_out);
+  } else {
+    TraceScope ts_(ctx, "k_dilate_col");
+    k_dilate_col<<<cdiv(N, 256), 256, 0, ctx->stream>>>(g, out, frames, H, W, k, conn, inv_out, three_d);
+  }
+  ctx->launches++;
+}
+
 // shared by stc_cloud.cu / stc_cloudfill.cu / the host wrapper below; radii above 32 are done as successive balls
 // (an L1 / Linf ball of radius a + b is the ball of radius a dilated by the ball of radius b)
 int morph_dilate_dev(stc_ctx* ctx, const unsigned char* in, unsigned char* out, int frames, int H, int W, int k, int conn, int inv_in,
@@ -96,14 +144,12 @@ int morph_dilate_dev(stc_ctx* ctx, const unsigned char* in, unsigned char* out, 
     if (!tmp.p) STC_CUDA(tmp.alloc((size_t)N));
     int rc = morph_rowdist_dev(ctx, src, inv ? 1 : 0, (int64_t)frames * H, W, 32, g.as<unsigned char>());
     if (rc) return rc;
-    { TraceScope ts_(ctx, "k_dilate_col"); k_dilate_col<<<cdiv(N, 256), 256, 0, ctx->stream>>>(g.as<unsigned char>(), tmp.as<unsigned char>(), frames, H, W, 32, conn, 0, three_d); }
-    ctx->launches++;
+    launch_dilate_col(ctx, g.as<unsigned char>(), tmp.as<unsigned char>(), frames, H, W, 32, conn, 0, three_d);
     src = tmp.as<unsigned char>(); inv = 0; k -= 32;
   }
   int rc = morph_rowdist_dev(ctx, src, inv ? 1 : 0, (int64_t)frames * H, W, k, g.as<unsigned char>());
   if (rc) return rc;
-  { TraceScope ts_(ctx, "k_dilate_col"); k_dilate_col<<<cdiv(N, 256), 256, 0, ctx->stream>>>(g.as<unsigned char>(), out, frames, H, W, k, conn, inv_out, three_d); }
-  ctx->launches++;
+  launch_dilate_col(ctx, g.as<unsigned char>(), out, frames, H, W, k, conn, inv_out, three_d);
   STC_CUDA(cudaGetLastError());
   return STC_OK;
 }
