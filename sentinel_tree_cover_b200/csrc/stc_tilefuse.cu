@@ -213,21 +213,18 @@ __global__ void __launch_bounds__(256) k_gather_subtiles(const float* __restrict
                                                          const float* __restrict__ s2med, const float* __restrict__ s1med,
                                                          const float* __restrict__ dem, const Win* __restrict__ wins, int T, int H, int W,
                                                          int P, float* __restrict__ x) {
+  // one thread per output float: the 68-byte pixel records are written coalesced (a thread per pixel scattered its 17 stores)
   const int t = blockIdx.z, f = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * P) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P * P * 17) return;
+  const int i = e / 17, k = e - i * 17;
   const Win w = wins[t];
   const int r = w.r0 + reflect_idx(i / P, w.pr0, w.nr), c = w.c0 + reflect_idx(i % P, w.pc0, w.nc);
   const int64_t px = (int64_t)r * W + c;
   const float* b14 = (f < T) ? s2q + ((int64_t)f * H * W + px) * 14 : s2med + px * 14;
   const float* b2 = (f < T) ? s1q + ((int64_t)f * H * W + px) * 2 : s1med + px * 2;
-  float* o = x + ((((int64_t)t * (T + 1) + f) * P * P) + i) * 17;
-#pragma unroll
-  for (int k = 0; k < 10; ++k) o[k] = b14[k];
-  o[10] = dem[px];
-  o[11] = b2[0]; o[12] = b2[1];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) o[13 + k] = b14[10 + k];
+  const float v = k < 10 ? b14[k] : k == 10 ? dem[px] : k < 13 ? b2[k - 11] : b14[k - 3];
+  x[(((int64_t)t * (T + 1) + f) * P * P) * 17 + e] = v;
 }
 // min_clear maps [nt][P][P] (float32) with their own pads + the no-image test on the UNPADDED window (:1355-1357):
 // np.percentile(min_clear, 50) < 1  <=>  both middle order statistics average below 1 (integers >= 0)
@@ -292,7 +289,7 @@ int tf_process_subtiles_dev(stc_ctx* ctx, const float* s2q, const float* s1q, co
   STC_CUDA(stc_dmalloc(&nb.p, (size_t)nt * (S + 2) * (S + 2))); STC_CUDA(stc_dmalloc(&vote.p, (size_t)nt * 256));
   static_assert(sizeof(Win) == 48, "window table layout");
   STC_CUDA(cudaMemcpyAsync(win.p, windows_host, (size_t)nt * 48, cudaMemcpyHostToDevice, ctx->stream));
-  { TraceScope ts_(ctx, "k_gather_subtiles"); k_gather_subtiles<<<dim3(cdiv(P * P, 256), T + 1, nt), 256, 0, ctx->stream>>>(s2q, s1q, s2m, s1m, dem, win.as<Win>(), T, H, W, P, x.as<float>()); }
+  { TraceScope ts_(ctx, "k_gather_subtiles"); k_gather_subtiles<<<dim3(cdiv(P * P * 17, 256), T + 1, nt), 256, 0, ctx->stream>>>(s2q, s1q, s2m, s1m, dem, win.as<Win>(), T, H, W, P, x.as<float>()); }
   { TraceScope ts_(ctx, "k_gather_clear"); k_gather_clear<<<dim3(cdiv(P * P, 256), nt), 256, 0, ctx->stream>>>(clr, win.as<Win>(), W, P, mc.as<float>()); }
   { TraceScope ts_(ctx, "k_no_image_test"); k_no_image_test<<<nt, 256, 0, ctx->stream>>>(clr, win.as<Win>(), W, force_no_data, flags.as<int>()); }
   ctx->launches += 3;
