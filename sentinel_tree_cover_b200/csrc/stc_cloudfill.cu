@@ -603,13 +603,18 @@ __global__ void __launch_bounds__(128) k_gram(const float* __restrict__ Z, int S
 #pragma unroll
     for (int j = 0; j < 4; ++j) out[(a0 + i) * GRAM_ZW + b0 + j] = acc[i][j];
 }
-// gram[q] = sum over the partials, in order; q -> (a, b) of the staged row (c_10 is u_10)
-__global__ void __launch_bounds__(640) k_gram_reduce(const double* __restrict__ partial, int nparts, double* __restrict__ gram) {
-  const int q = threadIdx.x;
-  if (q >= GRAM_N) return;
+// gram[q] = sum over the partials, in order; q -> (a, b) of the staged row (c_10 is u_10).  Eight lanes per entry: each
+// loads its 37 consecutive partials at once (all loads in flight), then the running sum walks through the eight lanes in
+// order -- the same chain of additions as a serial loop, without waiting for 296 loads one batch after the other.
+#define GRAM_PARTS 296
+#define GRAM_PER ((GRAM_PARTS + 7) / 8)
+__global__ void __launch_bounds__(256) k_gram_reduce(const double* __restrict__ partial, int nparts, double* __restrict__ gram) {
+  const int q = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7, lane = threadIdx.x & 31;
+  const bool valid = q < GRAM_N;
+  const int qq = valid ? q : 0;
   int kind, j, k;
-  if (q < 3 * NF * NF) { kind = q / (NF * NF); j = (q % (NF * NF)) / NF; k = q % NF; }
-  else { const int r = q - 3 * NF * NF; kind = 3 + r / (NF * 10); j = (r % (NF * 10)) / 10; k = r % 10; }
+  if (qq < 3 * NF * NF) { kind = qq / (NF * NF); j = (qq % (NF * NF)) / NF; k = qq % NF; }
+  else { const int r = qq - 3 * NF * NF; kind = 3 + r / (NF * 10); j = (r % (NF * 10)) / 10; k = r % 10; }
   const int cj = j < 10 ? 11 + j : 10, ck = k < 10 ? 11 + k : 10;      // position of c_j / c_k in the staged row
   int a, b;
   switch (kind) {
@@ -620,18 +625,20 @@ __global__ void __launch_bounds__(640) k_gram_reduce(const double* __restrict__ 
     default: a = cj; b = 21 + k; break;          // c_j y_k
   }
   const double* src = partial + a * GRAM_ZW + b;
-  // sixteen loads in flight, then the sixteen additions in order (a plain loop waited for every load: 21-30 us)
+  const int p0 = sub * GRAM_PER, p1 = min(p0 + GRAM_PER, nparts);
+  double v[GRAM_PER];
+#pragma unroll
+  for (int i = 0; i < GRAM_PER; ++i) v[i] = (p0 + i < p1) ? src[(int64_t)(p0 + i) * GRAM_P] : 0.0;
   double s = 0.0;
-  int p0 = 0;
-  for (; p0 + 16 <= nparts; p0 += 16) {
-    double v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = src[(int64_t)(p0 + i) * GRAM_P];
+  for (int turn = 0; turn < 8; ++turn) {
+    if (sub == turn) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += v[i];
+      for (int i = 0; i < GRAM_PER; ++i) if (p0 + i < p1) s += v[i];
+    }
+    s = __shfl_sync(0xffffffffu, s, (lane & ~7) + turn);
   }
-  for (; p0 < nparts; ++p0) s += src[(int64_t)p0 * GRAM_P];
-  gram[q] = s;
+  if (sub == 0 && valid) gram[q] = s;
 }
 
 // Lawson-Hanson NNLS on the normal equations, as scipy.optimize.nnls does (AtA, Atb in float64,
@@ -939,7 +946,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   DBuf d_ta, d_tb, d_sums, d_water0, d_water1, d_flag, d_u8a, d_u8b, d_pf, d_ref, d_pos, d_src_rows,
       d_ref_rows, d_mosaic, d_div, d_snow, d_partial, d_gramz, d_pix, d_gram, d_coef, d_status, d_qout,
       d_sd, d_params, d_cnt, d_counts;
-  const int gram_blocks = 296;
+  const int gram_blocks = GRAM_PARTS;
   STC_CUDA(stc_dmalloc(&d_ta.p, N * 4)); STC_CUDA(stc_dmalloc(&d_tb.p, N * 4)); STC_CUDA(stc_dmalloc(&d_sums.p, CF_MAX_DATES * 4));
   for (DBuf* b : {&d_water0, &d_water1, &d_flag, &d_u8a, &d_u8b, &d_pf}) STC_CUDA(stc_dmalloc(&b->p, HW));
   STC_CUDA(stc_dmalloc(&d_ref.p, (int64_t)HW * 40)); STC_CUDA(stc_dmalloc(&d_pos.p, (int64_t)HW * 4));
@@ -1319,7 +1326,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       CF_LAUNCH(k_gram_snow, cdiv((int64_t)S, 256), 256, d_snow.as<float>(), pixj, (int)S, Zj);
       const int gb = std::min(gram_blocks, cdiv((int64_t)S, GRAM_ROWS));
       CF_LAUNCH(k_gram, cdiv(gb, 2), 128, Zj, (int)S, gb, d_partial.as<double>());
-      CF_LAUNCH(k_gram_reduce, 1, 640, d_partial.as<double>(), gb, d_gram.as<double>());
+      CF_LAUNCH(k_gram_reduce, cdiv(GRAM_N, 32), 256, d_partial.as<double>(), gb, d_gram.as<double>());
       if (nnls_serial) CF_LAUNCH(k_nnls_serial, 1, 32, d_gram.as<double>(), (int)S, d_coef.as<double>(), d_status_all.as<int>() + 10 * j);
       else CF_LAUNCH(k_nnls, 1, 320, d_gram.as<double>(), (int)S, d_coef.as<double>(), d_status_all.as<int>() + 10 * j);
       if (getenv("STC_CF_DEBUG")) {                        // test aid: fit inputs / coefficients of every date on stderr
