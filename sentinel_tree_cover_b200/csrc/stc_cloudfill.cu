@@ -217,22 +217,25 @@ __global__ void __launch_bounds__(128) k_quantile_finish(const float* __restrict
 }
 
 // np.nanstd(rows, axis=0) of a [K][10] float32 matrix: NumPy reduces axis 0 row by row, i.e. each column is a
-// SEQUENTIAL float32 sum (a dependent chain of K adds, 4 clk each at best).  One warp per column: the 32 lanes
-// prefetch a tile of 512 rows into shared memory (double-buffered through registers), then every lane replays
-// the same chain from broadcast shared-memory reads, so the loads are off the dependency chain.
-// grid = (2 matrices, dates), block = 10 warps: the chains of all dates run side by side (one launch per date kept
-// 2 of 148 SMs busy for 3.5 ms, 43 % of the preprocessing chain).
+// SEQUENTIAL float32 sum (a dependent chain of K adds, 4 clk each at best: 2 passes x 3.8e5 rows = 1.6 ms whatever the
+// machine).  One warp per column: the 32 lanes prefetch a tile of 512 rows into shared memory (double-buffered through
+// registers), then every lane replays the same chain from broadcast shared-memory reads, so the loads are off the
+// dependency chain.  The chain is the longest single item of the mosaic phase, so nothing else may slow it: the values come
+// back as 128-bit shared-memory loads (one per four additions -- with one 32-bit load per addition the ten warps of a block
+// asked the shared-memory pipe for 2.5 loads per clock and ran at 8.7 clk per row), and the 20 chains of a date are spread
+// over ten blocks of two warps instead of two blocks of ten.
 #define CS_TILE 512
-__global__ void __launch_bounds__(320) k_col_std(const float* __restrict__ m0_all, const float* __restrict__ m1_all, int64_t slab,
-                                                 const int* __restrict__ Ks, int i0, float* __restrict__ out_all) {
-  __shared__ float tile[10][CS_TILE];
+__global__ void __launch_bounds__(64) k_col_std(const float* __restrict__ m0_all, const float* __restrict__ m1_all, int64_t slab,
+                                                const int* __restrict__ Ks, int i0, float* __restrict__ out_all) {
+  __shared__ __align__(16) float tile[2][CS_TILE];
   const int date = i0 + blockIdx.y;
   const int K = Ks[date];
   if (K <= 1000) return;                                   // date not aligned (:617)
-  const float* m = (blockIdx.x ? m1_all : m0_all) + (int64_t)date * slab;
+  const int mat = blockIdx.x / 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = (blockIdx.x % 5) * 2 + w;
+  const float* m = (mat ? m1_all : m0_all) + (int64_t)date * slab;
   float* out = out_all + (int64_t)date * 20;
-  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* tl = tile[c];
+  float* tl = tile[w];
   float avg = 0.f;
   for (int pass = 0; pass < 2; ++pass) {
     float s = 0.f;
@@ -252,14 +255,18 @@ __global__ void __launch_bounds__(320) k_col_std(const float* __restrict__ m0_al
       for (int j = 0; j < CS_TILE / 32; ++j) { int r = r0 + CS_TILE + j * 32 + lane; pre[j] = (r < K) ? m[(int64_t)r * 10 + c] : 0.f; }
       const int cnt = (K - r0) < CS_TILE ? (K - r0) : CS_TILE;
       if (cnt == CS_TILE) {
-#pragma unroll 16
-        for (int l = 0; l < CS_TILE; ++l) s = __fadd_rn(s, tl[l]);
+        const float4* t4 = reinterpret_cast<const float4*>(tl);
+#pragma unroll 8
+        for (int l = 0; l < CS_TILE / 4; ++l) {
+          const float4 v = t4[l];
+          s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
+        }
       } else {
         for (int l = 0; l < cnt; ++l) s = __fadd_rn(s, tl[l]);
       }
     }
     float r = (float)((double)s / (double)K);
-    if (pass == 0) avg = r; else if (lane == 0) out[blockIdx.x * 10 + c] = __fsqrt_rn(r);
+    if (pass == 0) avg = r; else if (lane == 0) out[mat * 10 + c] = __fsqrt_rn(r);
   }
 }
 
@@ -1262,7 +1269,7 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
       }
       STC_CUDA(cudaEventRecord(ctx->aux_ev[0], ctx->stream));
       STC_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
-      { k_col_std<<<dim3(2, cv), 320, 0, ctx->aux_stream>>>(d_srcall.as<float>(), d_refrowsall.as<float>(), slab, d_Ks.as<int>(), start, d_sdall.as<float>()); }
+      { k_col_std<<<dim3(10, cv), 64, 0, ctx->aux_stream>>>(d_srcall.as<float>(), d_refrowsall.as<float>(), slab, d_Ks.as<int>(), start, d_sdall.as<float>()); }
       ctx->launches++;
       STC_CUDA(cudaEventRecord(ctx->aux_ev[1], ctx->aux_stream));
       std::vector<SelJob> jobs; std::vector<QSpec> specs;

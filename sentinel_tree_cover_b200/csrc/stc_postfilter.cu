@@ -14,7 +14,7 @@ namespace {
 
 struct PBuf { void* p = nullptr; ~PBuf() { if (p) stc_dfree(p); } template <typename T> T* as() { return (T*)p; } };
 
-// ---- np.sum of contiguous float32 segments, NumPy's pairwise order (see stc_cloud.cu k_np_moments) ----
+// ---- np.sum of contiguous float32 segments, NumPy's pairwise order (see stc_cloud.cu k_np_tree / k_np_leaves) ----
 // mode 0: x          mode 1: x < 255 ? x*100 : x  (the in-place scaling of :1570 before the sum of :1573)
 // mode 2: NaN -> 0, valid[] counts the non-NaN values (np.nanmean)
 __device__ __forceinline__ float seg_value(float v, int mode) {
