@@ -379,7 +379,7 @@ def chain_kernel_table(csv_path, n, px, peaks, top=14):
     tot = {}
     for r in csv.DictReader(open(csv_path)):
         d = float(r["end_ms"]) - float(r["start_ms"])
-        e = tot.setdefault(r["label"], [0, 0.0])
+        e = tot.setdefault(r["label"].split("<")[0], [0, 0.0])      # template instantiations of one kernel count together
         e[0] += 1; e[1] += d
     all_ms = sum(v[1] for v in tot.values()) or 1.0
     rows = []

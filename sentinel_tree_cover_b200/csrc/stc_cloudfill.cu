@@ -97,16 +97,17 @@ __global__ void __launch_bounds__(128) k_mosaic_prep(const float* __restrict__ t
 // order.  One thread per (pixel, band) keeps the band's values of all dates in registers and forms the n ordered sums from
 // them, so the cube is read once (the per-date version re-read it for every date: n^2 * HW * 40 bytes, 1.7 ms at n = 24).
 // ref / flag are per-date slabs ([n][HW][10], [n][HW]).
+template <int NMAX>
 __global__ void __launch_bounds__(256) k_mosaic_ref(const float* __restrict__ tiles, const float* __restrict__ areas,
                                                     const unsigned char* __restrict__ water, int n, int HW, int i0,
                                                     float* __restrict__ ref_all, unsigned char* __restrict__ flag_all) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (int64_t)HW * 10) return;
   const int p = (int)(e / 10), c = (int)(e - (int64_t)p * 10);
-  float x[CF_MAX_DATES];
+  float x[NMAX];
   unsigned use = 0, lowa = 0;                       // bit b: areas[b] < 1 (contributes), areas[b] < 0.25 (gets a reference)
 #pragma unroll
-  for (int b = 0; b < CF_MAX_DATES; ++b) {
+  for (int b = 0; b < NMAX; ++b) {
     x[b] = 0.f;
     if (b < n) {
       x[b] = tiles[(int64_t)b * HW * 10 + e];
@@ -116,16 +117,24 @@ __global__ void __launch_bounds__(256) k_mosaic_ref(const float* __restrict__ ti
     }
   }
   const bool land = !water[p];
-  for (int i = i0; i < n; ++i) {
-    const unsigned others = use & ~(1u << i);
-    const bool ok = land && ((lowa >> i) & 1u) && others;
-    if (ok) {
-      float s = 0.f;
+  // the ordered sum over the other dates = (sum of the usable dates before i, shared by all later i) continued behind i
+  float prefix = 0.f;
 #pragma unroll
-      for (int b = 0; b < CF_MAX_DATES; ++b) if ((others >> b) & 1u) s = __fadd_rn(s, x[b]);
-      ref_all[(int64_t)i * HW * 10 + e] = __fdiv_rn(s, (float)__popc(others));
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      if (i >= i0) {
+        const unsigned others = use & ~(1u << i);
+        const bool ok = land && ((lowa >> i) & 1u) && others;
+        if (ok) {
+          float s = prefix;
+#pragma unroll
+          for (int b = i + 1; b < NMAX; ++b) if ((use >> b) & 1u) s = __fadd_rn(s, x[b]);
+          ref_all[(int64_t)i * HW * 10 + e] = __fdiv_rn(s, (float)__popc(others));
+        }
+        if (c == 0) flag_all[(int64_t)i * HW + p] = ok;
+      }
+      if ((use >> i) & 1u) prefix = __fadd_rn(prefix, x[i]);
     }
-    if (c == 0) flag_all[(int64_t)i * HW + p] = ok;
   }
 }
 
@@ -1249,7 +1258,9 @@ int remove_clouds_dev(stc_ctx* ctx, float* tiles, const float* probs_dev, const 
   int start = 0;
   while (start < n) {
     const int m = n - start;
-    CF_LAUNCH(k_mosaic_ref, cdiv((int64_t)HW * 10, 256), 256, tiles, areas, water0, n, HW, start, d_refall.as<float>(), d_flagall.as<unsigned char>());
+    if (n <= 8) CF_LAUNCH(k_mosaic_ref<8>, cdiv((int64_t)HW * 10, 256), 256, tiles, areas, water0, n, HW, start, d_refall.as<float>(), d_flagall.as<unsigned char>());
+    else if (n <= 16) CF_LAUNCH(k_mosaic_ref<16>, cdiv((int64_t)HW * 10, 256), 256, tiles, areas, water0, n, HW, start, d_refall.as<float>(), d_flagall.as<unsigned char>());
+    else CF_LAUNCH(k_mosaic_ref<32>, cdiv((int64_t)HW * 10, 256), 256, tiles, areas, water0, n, HW, start, d_refall.as<float>(), d_flagall.as<unsigned char>());
     if ((rc = scan_flags_dev(ctx, d_flagall.as<unsigned char>() + (int64_t)start * HW, m, HW, d_posall.as<int>() + (int64_t)start * HW,
                              d_Ks.as<int>() + start))) return rc;
     STC_CUDA(cudaMemcpyAsync(Ks.data() + start, d_Ks.as<int>() + start, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
