@@ -791,7 +791,11 @@ static int launch_umma2(stc_ctx* ctx, const ConvParams& p, int ndir, int iss_req
   // not by the tensor pipe: two CTAs per SM (each with half the shared-memory budget and 256 of the 512 TMEM columns) keep
   // twice the copies and epilogue stores in flight.  STC_SR_OCC=1 restores one CTA per SM (A/B).
   static const int sr_occ = getenv("STC_SR_OCC") ? atoi(getenv("STC_SR_OCC")) : 2;
-  const bool two_ctas = (MODE == MODE_BIAS || MODE == MODE_BIAS_RELU) && N <= 32 && sr_occ >= 2;
+  // The GRU candidate convolution (N = 32, 256 TMEM columns) is neither tensor- nor HBM-bound with one CTA per SM (31 % tensor
+  // pipe, 39 % of the HBM peak): STC_CAND_OCC=2 runs two, each with per-stage weights (resident weights + three stages do
+  // not fit twice).  A/B switch, default from the measurement in DESIGN.md section 4.
+  static const int cand_occ = getenv("STC_CAND_OCC") ? atoi(getenv("STC_CAND_OCC")) : 1;
+  const bool two_ctas = ((MODE == MODE_BIAS || MODE == MODE_BIAS_RELU) && N <= 32 && sr_occ >= 2) || (MODE == MODE_CAND && cand_occ >= 2);
   const int SMEM_MAX = two_ctas ? std::min(SMEM_MAX_1, 104 * 1024) : SMEM_MAX_1;
   static bool configured = false;
   auto kern = conv3x3_umma2_kernel<N, NT, G, MODE, WRES>;
