@@ -41,6 +41,39 @@ STC_CLONES void regen_block(const uint32_t* prev, uint32_t* __restrict__ mt, uin
     out[k] = y;
   }
 }
+#if defined(__x86_64__) && defined(__GNUC__)
+// The same regeneration + tempering with explicit AVX-512: the state is 39 aligned vectors; mt[k + 1] and mt[k + 397] are
+// built from two aligned loads each (valignd by 1 and by 13 lanes: 397 = 24 * 16 + 13), so no load crosses a cache line,
+// and updating in place with wrapped vector indices IS the reference recurrence (a wrapped index reads a vector this pass
+// already rewrote, which is exactly mt[k - 227] / the new mt[0] of the scalar loops).  ~1.5x the auto-vectorised loops.
+__attribute__((target("avx512f"))) void regen_block_avx512(uint32_t* __restrict__ mt /*64-byte aligned, in place*/, uint32_t* __restrict__ out) {
+  const __m512i UPPER = _mm512_set1_epi32((int)0x80000000u), MATRIX = _mm512_set1_epi32((int)0x9908b0dfu), ONE = _mm512_set1_epi32(1);
+  const __m512i TB = _mm512_set1_epi32((int)0x9d2c5680u), TC = _mm512_set1_epi32((int)0xefc60000u);
+  for (int j = 0; j < 39; ++j) {
+    const int j1 = j + 1 == 39 ? 0 : j + 1, ja = j + 24 >= 39 ? j + 24 - 39 : j + 24, jb = j + 25 >= 39 ? j + 25 - 39 : j + 25;
+    const __m512i cur = _mm512_load_si512(mt + 16 * j), nxt = _mm512_load_si512(mt + 16 * j1);
+    const __m512i mlo = _mm512_load_si512(mt + 16 * ja), mhi = _mm512_load_si512(mt + 16 * jb);
+    const __m512i v = _mm512_alignr_epi32(nxt, cur, 1), m = _mm512_alignr_epi32(mhi, mlo, 13);
+    const __m512i y = _mm512_ternarylogic_epi32(UPPER, cur, v, 0xCA);                 // (cur & UPPER) | (v & ~UPPER)
+    __m512i t = _mm512_xor_si512(m, _mm512_srli_epi32(y, 1));
+    t = _mm512_mask_xor_epi32(t, _mm512_test_epi32_mask(y, ONE), t, MATRIX);
+    _mm512_store_si512(mt + 16 * j, t);
+    __m512i z = _mm512_xor_si512(t, _mm512_srli_epi32(t, 11));
+    z = _mm512_xor_si512(z, _mm512_and_si512(_mm512_slli_epi32(z, 7), TB));
+    z = _mm512_xor_si512(z, _mm512_and_si512(_mm512_slli_epi32(z, 15), TC));
+    z = _mm512_xor_si512(z, _mm512_srli_epi32(z, 18));
+    _mm512_storeu_si512(out + 16 * j, z);
+  }
+}
+const bool have_avx512 = __builtin_cpu_supports("avx512f") && !(getenv("STC_PYRANDOM_ISA") && atoi(getenv("STC_PYRANDOM_ISA")) < 2);
+#else
+const bool have_avx512 = false;
+inline void regen_block_avx512(uint32_t*, uint32_t*) {}
+#endif
+// in-place regeneration of a 64-byte aligned state with the widest instruction set at hand
+inline void regen_inplace(uint32_t* mt, uint32_t* out) {
+  if (have_avx512) regen_block_avx512(mt, out); else regen_block(mt, mt, out);
+}
 STC_CLONES void temper_block(const uint32_t* __restrict__ mt, uint32_t* __restrict__ out) {
   for (int k = 0; k < 624; ++k) {
     uint32_t y = mt[k];
@@ -94,7 +127,7 @@ void PyRandomProducer::start(const uint32_t* state624) {
       }
       if (quit.load(std::memory_order_relaxed)) return;
       Chunk& k = ring[c % R];
-      for (int b = 0; b < CB; ++b) regen_block(mt, mt, k.out + b * 624);
+      for (int b = 0; b < CB; ++b) regen_inplace(mt, k.out + b * 624);
       produced.store(c + 1, std::memory_order_release);
     }
   });
@@ -127,8 +160,9 @@ void PyRandom::refill() {                              // only called when an ou
   const int last = len_ / 624 - 1;
   alignas(64) uint32_t prev[624];
   memcpy(prev, hist[last], sizeof(prev));
-  regen_block(prev, hist_own[0], out_own);
-  for (int b = 1; b < NB; ++b) regen_block(hist_own[b - 1], hist_own[b], out_own + b * 624);
+  memcpy(hist_own[0], prev, sizeof(prev));
+  regen_inplace(hist_own[0], out_own);
+  for (int b = 1; b < NB; ++b) { memcpy(hist_own[b], hist_own[b - 1], 624 * 4); regen_inplace(hist_own[b], out_own + b * 624); }
   hist = hist_own; out = out_own;
   pos = 0; len_ = NB * 624;
 }
