@@ -83,8 +83,10 @@ int stc_trace(stc_ctx* ctx, int enable, const char* csv_path);
  *      pb:strided_slice_1).  `length` is the uniform sequence length
  *      (np.full(B, args.length), :354).  If normalize != 0, normalize_subtile
  *      (:316-325) is applied first with min17/max17.  out: [B,H-14,W-14].
- *      Limits (STC_ERR_ARG otherwise): H == W (the released graphs are square: 76 / 124 / 172 / 220), H a multiple of 4,
- *      H >= 28, 1 <= length <= T.  The patch entry points (stc_predict_patches_*) take 12 months x 13 bands, H == W.
+ *      Limits (STC_ERR_ARG otherwise): H and W multiples of 4 and >= 28 (independent: the released graphs are square,
+ *      76 / 124 / 172 / 220; the border re-segmentation pass, src/resegment_tiles_wide.py:182-222,478, runs 220 x 684
+ *      windows through the same call), 1 <= length <= T.  The patch entry points (stc_predict_patches_*) take 12 months
+ *      x 13 bands, H == W.
  *      Date-axis limit of the preprocessing entry points: n <= 32 dates per tile (registers hold a pixel's time series;
  *      the reference has no limit, its date selection leaves <= 24). ---- */
 int stc_predict_host(stc_ctx* ctx, const float* x_host, int B, int T, int H, int W, int length,

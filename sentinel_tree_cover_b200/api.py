@@ -285,15 +285,17 @@ class StcSession:
         self._check(self.lib.stc_trace(self.h, int(enable), csv_path.encode() if csv_path else None))
 
     # -- model -------------------------------------------------------------------
-    def predict(self, x, length=None, normalize=False):
-        """x [B,T+1,H,W,17] float32 -> [B,H-14,W-14] float32 (pb:conv2d/Sigmoid)."""
+    def predict(self, x, length=None, normalize=False, mins=None, maxs=None):
+        """x [B,T+1,H,W,17] float32 -> [B,H-14,W-14] float32 (pb:conv2d/Sigmoid).  H and W are independent (multiples of 4,
+        >= 28): square for the released graphs, 220 x 684 for the border re-segmentation pass.  `mins` / `maxs` override the
+        session's 17 normalisation constants for this call (resegment_tiles_wide.py uses a different DEM maximum)."""
         x = np.ascontiguousarray(x, np.float32)
         B, T1, H, W, Cc = x.shape
         assert Cc == 17
         length = int(self.length if length is None else length)
         out = np.empty((B, H - 14, W - 14), np.float32)
-        mn, mnp = _f64(self.min_all)
-        mx, mxp = _f64(self.max_all)
+        mn, mnp = _f64(self.min_all if mins is None else mins)
+        mx, mxp = _f64(self.max_all if maxs is None else maxs)
         self._check(self.lib.stc_predict_host(self.h, _dptr(x), B, T1 - 1, H, W, length, int(bool(normalize)), mnp, mxp, _dptr(out)))
         return out
 

@@ -452,10 +452,10 @@ struct ApplyParams {
   int Hd, Wd; int mode; int off;  // mode 0 identity(+crop off) 1 maxpool2 2 upsample2 3 head
   const float* head_w; const float* head_b; float* head_out;
   float* feat_out;             // mode 3, optional: the block's sSE output (pb:csse_out_mul/mul) [B,Hd,Wd,C] float32
-  // mode 1, optional second consumer of the same block output: the centre crop [off2, off2 + Hd2)^2 of the un-pooled tensor
+  // mode 1, optional second consumer of the same block output: the centre crop [off2, off2 + Hd2) x [off2, off2 + Wd2) of the un-pooled tensor
   // (skip connection into a decoder concat buffer), written by the thread that pools the pixel -- the block's raw output
   // is then read once instead of by two launches
-  uint4* dst2; int64_t dst2_plane; int d2Hp, d2Wp, off2, Hd2;
+  uint4* dst2; int64_t dst2_plane; int d2Hp, d2Wp, off2, Hd2, Wd2;
 };
 
 // Compiled per (C, MODE) so that the channel loops unroll and all plane loads of a pixel are in flight at once
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(256, 2) block_apply_t(ApplyParams p) {
       }
       if (MODE == 1 && p.dst2) {
         const int y2 = 2 * yd + (k >> 1) - p.off2, x2 = 2 * xd + (k & 1) - p.off2;
-        if (y2 >= 0 && y2 < p.Hd2 && x2 >= 0 && x2 < p.Hd2)
+        if (y2 >= 0 && y2 < p.Hd2 && x2 >= 0 && x2 < p.Wd2)
           p.dst2[(int64_t)c8 * p.dst2_plane + ((int64_t)b * p.d2Hp + y2 + 1) * p.d2Wp + x2 + 1] = pack8(zk);
       }
     }
@@ -573,17 +573,17 @@ static void launch_apply_c(const ApplyParams& ap, dim3 grid, cudaStream_t s) {
 
 // --gen_feats early features (src/download_and_predict_job.py:1431, pb:gru_drop/drop_block2d/cond/Merge = the
 // bidirectional ConvGRU output, DropBlock is the identity at inference): channels 0..63 of the concat buffer,
-// centre-cropped by `crop` like predict_subtile does (:360-362), float32 [B,Hd,Hd,64].
-__global__ void feat_early_kernel(const uint4* src, int64_t plane, int B, int Hp, int Wp, int crop, int Hd, float* out) {
+// centre-cropped by `crop` like predict_subtile does (:360-362), float32 [B,Hd,Wd,64].
+__global__ void feat_early_kernel(const uint4* src, int64_t plane, int B, int Hp, int Wp, int crop, int Hd, int Wd, float* out) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t n = (int64_t)B * Hd * Hd * 8;
+  int64_t n = (int64_t)B * Hd * Wd * 8;
   if (idx >= n) return;
   int c = (int)(idx & 7); int64_t r = idx >> 3;
-  int x = (int)(r % Hd); r /= Hd; int y = (int)(r % Hd); int b = (int)(r / Hd);
+  int x = (int)(r % Wd); r /= Wd; int y = (int)(r % Hd); int b = (int)(r / Hd);
   int64_t P = ((int64_t)b * Hp + y + crop + 1) * Wp + x + crop + 1;
   float v[8];
   unpack8(src[(int64_t)c * plane + P], v);
-  float4* o = reinterpret_cast<float4*>(out + (((int64_t)b * Hd + y) * Hd + x) * 64 + c * 8);
+  float4* o = reinterpret_cast<float4*>(out + (((int64_t)b * Hd + y) * Wd + x) * 64 + c * 8);
   o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
@@ -620,7 +620,7 @@ struct ModelState {
   float* fparams = nullptr;   // all small f32 vectors, contiguous
   std::map<std::string, const float*> fp;
   // scratch plan
-  int Bc = 0, H = 0, T1 = 0;
+  int Bc = 0, H = 0, W = 0, T1 = 0;
   void* arena = nullptr; size_t arena_bytes = 0;
   Act X16; int64_t x_frame_stride = 0;
   Act Hh[2], RH[2], CCin, P1, CAT1, P2, U2in, U3in, CAT2;
@@ -758,20 +758,23 @@ void model_destroy(stc_ctx* ctx) {
   if (ctx->ev_fork) { cudaEventDestroy(ctx->ev_fork); ctx->ev_fork = nullptr; }
 }
 
-struct Geo { int H, Hp; int64_t P; };   // square images
-static Geo geo(int Bc, int H) { Geo g; g.H = H; g.Hp = H + 2; g.P = (int64_t)Bc * g.Hp * g.Hp; return g; }
+// One resolution level of the network: H x W images (the released graphs are square; the border re-segmentation pass of
+// src/resegment_tiles_wide.py:478 predicts 220 x 684 seams), padded by one pixel on every side.
+struct Geo { int H, W, Hp, Wp; int64_t P; };
+static Geo geo(int Bc, int H, int W) { Geo g; g.H = H; g.W = W; g.Hp = H + 2; g.Wp = W + 2; g.P = (int64_t)Bc * g.Hp * g.Wp; return g; }
 
 static size_t act_units(int chunks, const Geo& g, int& guard) {
-  guard = ((g.Hp + 2 + 544 + 7) / 8) * 8;   // >= Wp + 1 + (NT*128 + 8) staged rows past the last tile
+  guard = ((g.Wp + 2 + 544 + 7) / 8) * 8;   // >= Wp + 1 + (NT*128 + 8) staged rows past the last tile
   return (size_t)chunks * (size_t)(g.P + 2 * guard);
 }
 
-static int ensure_plan(stc_ctx* ctx, ModelState* m, int Bc, int H, int T1) {
-  if (m->arena && m->Bc == Bc && m->H == H && m->T1 == T1) return STC_OK;
+static int ensure_plan(stc_ctx* ctx, ModelState* m, int Bc, int H, int W, int T1) {
+  if (m->arena && m->Bc == Bc && m->H == H && m->W == W && m->T1 == T1) return STC_OK;
   if (m->arena) { cudaFree(m->arena); m->arena = nullptr; }
   if (m->stats) { cudaFree(m->stats); m->stats = nullptr; }
   const int p1 = H / 2, c1 = p1 - 2, p2 = c1 / 2, c2 = p2 - 2, u2 = 2 * c2, u3 = 2 * u2;
-  Geo g0 = geo(Bc, H), g1 = geo(Bc, p1), g2 = geo(Bc, p2), gu2 = geo(Bc, u2), gu3 = geo(Bc, u3);
+  const int q1 = W / 2, d1 = q1 - 2, q2 = d1 / 2, d2 = q2 - 2, v2 = 2 * d2, v3 = 2 * v2;       // the same chain along x
+  Geo g0 = geo(Bc, H, W), g1 = geo(Bc, p1, q1), g2 = geo(Bc, p2, q2), gu2 = geo(Bc, u2, v2), gu3 = geo(Bc, u3, v3);
   struct Item { Act* a; int chunks; Geo g; };
   std::vector<Item> acts = {
       {&m->X16, 4 * T1, g0}, {&m->Hh[0], 4, g0}, {&m->Hh[1], 4, g0}, {&m->RH[0], 4, g0}, {&m->RH[1], 4, g0},
@@ -793,7 +796,7 @@ static int ensure_plan(stc_ctx* ctx, ModelState* m, int Bc, int H, int T1) {
   for (size_t i = 0; i < acts.size(); ++i) {
     Act& a = *acts[i].a; int guard; act_units(acts[i].chunks, acts[i].g, guard);
     a.base = (uint4*)((char*)m->arena + offs[i]); a.guard = guard; a.plane = acts[i].g.P + 2 * guard;
-    a.chunks = acts[i].chunks; a.B = Bc; a.Hp = acts[i].g.Hp; a.Wp = acts[i].g.Hp;
+    a.chunks = acts[i].chunks; a.B = Bc; a.Hp = acts[i].g.Hp; a.Wp = acts[i].g.Wp;
   }
   m->x_frame_stride = 4 * m->X16.plane;
   for (size_t i = 0; i < raws.size(); ++i) {
@@ -805,7 +808,7 @@ static int ensure_plan(stc_ctx* ctx, ModelState* m, int Bc, int H, int T1) {
   m->stats_bytes = (nG + nY + nB) * sizeof(double);
   STC_CUDA(cudaMalloc((void**)&m->stats, m->stats_bytes));
   m->stG = m->stats; m->stY = m->stats + nG; m->stB = m->stats + nG + nY;
-  m->Bc = Bc; m->H = H; m->T1 = T1;
+  m->Bc = Bc; m->H = H; m->W = W; m->T1 = T1;
   return STC_OK;
 }
 
@@ -830,22 +833,22 @@ static int run_block_conv(stc_ctx* ctx, ModelState* m, int blk, const Act& in, i
 }
 
 static int run_apply(stc_ctx* ctx, ModelState* m, int blk, const Act& src_geo, bool same, int mode, int off,
-                     Act* dst, int dst_chunk_off, int Hd, int B, float* head_out,
-                     Act* dst2 = nullptr, int dst2_chunk_off = 0, int off2 = 0, int Hd2 = 0) {
+                     Act* dst, int dst_chunk_off, int Hd, int Wd, int B, float* head_out,
+                     Act* dst2 = nullptr, int dst2_chunk_off = 0, int off2 = 0, int Hd2 = 0, int Wd2 = 0) {
   ApplyParams ap; memset(&ap, 0, sizeof(ap));
   ap.raw = m->rawB.base; ap.raw_plane = (int64_t)((src_geo.Ptot() + 511) / 512 * 512); ap.C = BLK_COUT[blk];
   ap.sHp = src_geo.Hp; ap.sWp = src_geo.Wp; ap.so = same ? 1 : 2;
   ap.stats = m->stB + (size_t)blk * m->Bc * 16;
-  int Hv = src_geo.Hp - 2 * ap.so;
-  ap.count = (float)Hv * (float)Hv * (float)(ap.C / 8);
+  int Hv = src_geo.Hp - 2 * ap.so, Wv = src_geo.Wp - 2 * ap.so;
+  ap.count = (float)Hv * (float)Wv * (float)(ap.C / 8);
   std::string n = BLK[blk];
   ap.gamma = m->fp[n + ".gamma"]; ap.beta = m->fp[n + ".beta"]; ap.sse_w = m->fp[n + ".sse_w"]; ap.sse_b = m->fp[n + ".sse_b"];
   if (dst) { ap.dst = dst->at(dst_chunk_off); ap.dst_plane = dst->plane; ap.dHp = dst->Hp; ap.dWp = dst->Wp; }
-  if (dst2 && mode == 1) { ap.dst2 = dst2->at(dst2_chunk_off); ap.dst2_plane = dst2->plane; ap.d2Hp = dst2->Hp; ap.d2Wp = dst2->Wp; ap.off2 = off2; ap.Hd2 = Hd2; }
-  ap.Hd = Hd; ap.Wd = Hd; ap.mode = mode; ap.off = off;
+  if (dst2 && mode == 1) { ap.dst2 = dst2->at(dst2_chunk_off); ap.dst2_plane = dst2->plane; ap.d2Hp = dst2->Hp; ap.d2Wp = dst2->Wp; ap.off2 = off2; ap.Hd2 = Hd2; ap.Wd2 = Wd2; }
+  ap.Hd = Hd; ap.Wd = Wd; ap.mode = mode; ap.off = off;
   ap.head_w = m->fp["head.w"]; ap.head_b = m->fp["head.b"]; ap.head_out = head_out;
   ap.feat_out = (mode == 3) ? ctx->feat_late_chunk : nullptr;
-  dim3 grid(cdiv((int64_t)Hd * Hd, 256), B);
+  dim3 grid(cdiv((int64_t)Hd * Wd, 256), B);
   trace_begin(ctx, "block_apply");
   if (ap.C == 64) launch_apply_c<64>(ap, grid, ctx->stream);
   else if (ap.C == 128) launch_apply_c<128>(ap, grid, ctx->stream);
@@ -857,20 +860,21 @@ static int run_apply(stc_ctx* ctx, ModelState* m, int blk, const Act& src_geo, b
   return STC_OK;
 }
 
-static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const float* monthly_dev, int B, int T, int H, int length,
+static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const float* monthly_dev, int B, int T, int H, int W, int length,
                          int normalize, const double* mn, const double* mx, float* out_dev, cudaEvent_t input_consumed) {
   const int T1 = T + 1;
   const int p1 = H / 2, c1 = p1 - 2, p2 = c1 / 2, c2 = p2 - 2, u2 = 2 * c2, u3 = 2 * u2;
-  (void)c2;
+  const int q1 = W / 2, d1 = q1 - 2, q2 = d1 / 2, d2 = q2 - 2, v2 = 2 * d2, v3 = 2 * v2;
+  (void)c2; (void)d2;
   // ---- reset state ----
   // (the GRU state needs no clearing: step 0 runs with h == 0 folded in -- no h K-steps, no r*h stage)
   STC_CUDA(cudaMemsetAsync(m->stats, 0, m->stats_bytes, ctx->stream));
   // ---- pack input ----
   {
     PrepParams pp; memset(&pp, 0, sizeof(pp));
-    pp.x = x_dev; pp.B = B; pp.T1 = T1; pp.H = H; pp.W = H;
+    pp.x = x_dev; pp.B = B; pp.T1 = T1; pp.H = H; pp.W = W;
     pp.dst = m->X16.at(0); pp.plane = m->X16.plane; pp.frame_stride = m->x_frame_stride;
-    pp.Hp = H + 2; pp.Wp = H + 2; pp.normalize = normalize;
+    pp.Hp = H + 2; pp.Wp = W + 2; pp.normalize = normalize;
     for (int c = 0; c < 17; ++c) {
       // normalize_subtile: python-float (double) mins/maxs, float32 array arithmetic
       double lo = normalize ? mn[c] : 0.0, hi = normalize ? mx[c] : 1.0;
@@ -881,7 +885,7 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
     if (monthly_dev && !fe_direct) {
       // staged front end: half[] carries the reciprocal (the product is rounded to fp16 right after)
       for (int c = 0; c < 17; ++c) pp.half[c] = 1.0f / pp.half[c];
-      const int gps = cdiv((int64_t)H * H, 32), total = gps * B;
+      const int gps = cdiv((int64_t)H * W, 32), total = gps * B;
       const int grid = total < 8 * ctx->num_sms ? cdiv(total, 8) : ctx->num_sms;
       if (ctx->monthly_u16) {
         const int smem = 8 * 12 * 32 * 13 * 2 + 64;
@@ -895,7 +899,7 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
         assemble_prep_staged_kernel<float><<<grid, 256, smem, ctx->stream>>>(monthly_dev, pp, gps, total);
       }
     } else if (monthly_dev) {
-      dim3 agrid(cdiv((int64_t)H * H, 128), B);
+      dim3 agrid(cdiv((int64_t)H * W, 128), B);
       if (ctx->monthly_u16)
         assemble_prep_kernel<uint16_t><<<agrid, 128, 0, ctx->stream>>>(reinterpret_cast<const uint16_t*>(monthly_dev), pp);
       else
@@ -941,9 +945,9 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
     }
     gp.rawG_plane = m->rawG[0].plane; gp.rawY_plane = m->rawY[0].plane; gp.Hf_plane = m->Hf[0].plane;
     gp.act_plane = m->Hh[0].plane; gp.cc_plane = m->CCin.plane;
-    gp.B = B; gp.H = H; gp.W = H; gp.Hp = H + 2; gp.Wp = H + 2; gp.count = (float)H * (float)H * 4.f;
+    gp.B = B; gp.H = H; gp.W = W; gp.Hp = H + 2; gp.Wp = W + 2; gp.count = (float)H * (float)W * 4.f;
     gp.h_zero = (t == 0);
-    dim3 ggrid(cdiv((int64_t)H * H, 256), B, 2);
+    dim3 ggrid(cdiv((int64_t)H * W, 256), B, 2);
     if (t > 0) {
       trace_begin(ctx, "apply1");
       gru_apply1_kernel<<<ggrid, 256, 0, ctx->stream>>>(gp);
@@ -967,39 +971,39 @@ static int forward_chunk(stc_ctx* ctx, ModelState* m, const float* x_dev, const 
     STC_CUDA(cudaGetLastError()); ctx->launches++;
   }
   // ---- optional feature taps (--gen_feats) ----
-  const int Ho_f = u3 - 2;
+  const int Ho_f = u3 - 2, Wo_f = v3 - 2;
   if (ctx->feat_early_chunk) {
-    int64_t work = (int64_t)B * Ho_f * Ho_f * 8;
-    feat_early_kernel<<<cdiv(work, 256), 256, 0, ctx->stream>>>(m->CCin.at(0), m->CCin.plane, B, m->CCin.Hp, m->CCin.Wp, (H - Ho_f) / 2, Ho_f, ctx->feat_early_chunk);
+    int64_t work = (int64_t)B * Ho_f * Wo_f * 8;
+    feat_early_kernel<<<cdiv(work, 256), 256, 0, ctx->stream>>>(m->CCin.at(0), m->CCin.plane, B, m->CCin.Hp, m->CCin.Wp, (H - Ho_f) / 2, Ho_f, Wo_f, ctx->feat_early_chunk);
     STC_CUDA(cudaGetLastError()); ctx->launches++;
   }
   // ---- U-Net ----
   int rc;
   Act xmed = m->X16; xmed.base = m->X16.base + (int64_t)T * m->x_frame_stride; xmed.chunks = 4;
   rc = run_block_conv(ctx, m, 0, xmed, 4, true, B); if (rc) return rc;                       // conv_median
-  rc = run_apply(ctx, m, 0, m->CCin, true, 0, 0, &m->CCin, 8, H, B, nullptr); if (rc) return rc;
+  rc = run_apply(ctx, m, 0, m->CCin, true, 0, 0, &m->CCin, 8, H, W, B, nullptr); if (rc) return rc;
   rc = run_block_conv(ctx, m, 1, m->CCin, 16, true, B); if (rc) return rc;                   // conv_concat
   // maxpool -> P1 and the centre crop (skip connection) -> CAT2 from one read of the block's raw output
-  rc = run_apply(ctx, m, 1, m->CCin, true, 1, 0, &m->P1, 0, p1, B, nullptr, &m->CAT2, 8, 6, u3); if (rc) return rc;
+  rc = run_apply(ctx, m, 1, m->CCin, true, 1, 0, &m->P1, 0, p1, q1, B, nullptr, &m->CAT2, 8, 6, u3, v3); if (rc) return rc;
   rc = run_block_conv(ctx, m, 2, m->P1, 8, false, B); if (rc) return rc;                     // conv1 (VALID)
-  rc = run_apply(ctx, m, 2, m->P1, false, 1, 0, &m->P2, 0, p2, B, nullptr, &m->CAT1, 16, 2, u2); if (rc) return rc;
+  rc = run_apply(ctx, m, 2, m->P1, false, 1, 0, &m->P2, 0, p2, q2, B, nullptr, &m->CAT1, 16, 2, u2, v2); if (rc) return rc;
   rc = run_block_conv(ctx, m, 3, m->P2, 16, false, B); if (rc) return rc;                    // conv2 (VALID)
-  rc = run_apply(ctx, m, 3, m->P2, false, 2, 0, &m->U2in, 0, u2, B, nullptr); if (rc) return rc;
+  rc = run_apply(ctx, m, 3, m->P2, false, 2, 0, &m->U2in, 0, u2, v2, B, nullptr); if (rc) return rc;
   rc = run_block_conv(ctx, m, 4, m->U2in, 32, true, B); if (rc) return rc;                   // up2
-  rc = run_apply(ctx, m, 4, m->U2in, true, 0, 0, &m->CAT1, 0, u2, B, nullptr); if (rc) return rc;
+  rc = run_apply(ctx, m, 4, m->U2in, true, 0, 0, &m->CAT1, 0, u2, v2, B, nullptr); if (rc) return rc;
   rc = run_block_conv(ctx, m, 5, m->CAT1, 32, true, B); if (rc) return rc;                   // up2_out
-  rc = run_apply(ctx, m, 5, m->CAT1, true, 2, 0, &m->U3in, 0, u3, B, nullptr); if (rc) return rc;
+  rc = run_apply(ctx, m, 5, m->CAT1, true, 2, 0, &m->U3in, 0, u3, v3, B, nullptr); if (rc) return rc;
   rc = run_block_conv(ctx, m, 6, m->U3in, 16, true, B); if (rc) return rc;                   // up3
-  rc = run_apply(ctx, m, 6, m->U3in, true, 0, 0, &m->CAT2, 0, u3, B, nullptr); if (rc) return rc;
+  rc = run_apply(ctx, m, 6, m->U3in, true, 0, 0, &m->CAT2, 0, u3, v3, B, nullptr); if (rc) return rc;
   rc = run_block_conv(ctx, m, 7, m->CAT2, 16, false, B); if (rc) return rc;                  // out (VALID)
-  rc = run_apply(ctx, m, 7, m->CAT2, false, 3, 0, nullptr, 0, u3 - 2, B, out_dev); if (rc) return rc;
+  rc = run_apply(ctx, m, 7, m->CAT2, false, 3, 0, nullptr, 0, u3 - 2, v3 - 2, B, out_dev); if (rc) return rc;
   return STC_OK;
 }
 
 // Chunked forward over a device-resident batch.  Consecutive chunks rotate over model_num_slots() scratch slots /
 // streams so the HBM-bound elementwise stages of some chunks run in the shadow of the tensor-bound convolutions of
 // others (STC_SINGLE_STREAM=1 disables this; STC_SLOTS sets the number of slots).
-static int run_chunks(stc_ctx* ctx, const float* x_dev, const float* monthly_dev, int B, int T, int H, int length,
+static int run_chunks(stc_ctx* ctx, const float* x_dev, const float* monthly_dev, int B, int T, int H, int W, int length,
                       int normalize, const double* mn, const double* mx, float* out_dev) {
   if (B <= 0) return STC_OK;
   const char* env = getenv("STC_CHUNK");
@@ -1022,8 +1026,8 @@ static int run_chunks(stc_ctx* ctx, const float* x_dev, const float* monthly_dev
       STC_CUDA(cudaStreamWaitEvent(model_slot_stream(ctx, i), ctx->ev_fork, 0));
     }
   }
-  const int Ho = H - 14;
-  const size_t per_in = monthly_dev ? (size_t)12 * H * H * 13 : (size_t)(T + 1) * H * H * 17;
+  const int Ho = H - 14, Wo = W - 14;
+  const size_t per_in = monthly_dev ? (size_t)12 * H * W * 13 : (size_t)(T + 1) * H * W * 17;
   int rc = STC_OK, k = 0;
   for (int b0 = 0; b0 < B && !rc; b0 += Bc, ++k) {
     const int nb = (B - b0) < Bc ? (B - b0) : Bc;
@@ -1031,13 +1035,13 @@ static int run_chunks(stc_ctx* ctx, const float* x_dev, const float* monthly_dev
     ModelState* m = (ModelState*)ctx->slots[slot];
     ctx->stream = slot ? model_slot_stream(ctx, slot) : main_stream;
     ctx->cur_slot = slot;
-    rc = ensure_plan(ctx, m, Bc, H, T + 1);
+    rc = ensure_plan(ctx, m, Bc, H, W, T + 1);
     const float* mchunk = nullptr;
     if (monthly_dev) mchunk = reinterpret_cast<const float*>(reinterpret_cast<const char*>(monthly_dev) + b0 * per_in * (ctx->monthly_u16 ? 2 : 4));
-    ctx->feat_early_chunk = ctx->feat_early_dev ? ctx->feat_early_dev + (size_t)b0 * Ho * Ho * 64 : nullptr;
-    ctx->feat_late_chunk = ctx->feat_late_dev ? ctx->feat_late_dev + (size_t)b0 * Ho * Ho * 64 : nullptr;
+    ctx->feat_early_chunk = ctx->feat_early_dev ? ctx->feat_early_dev + (size_t)b0 * Ho * Wo * 64 : nullptr;
+    ctx->feat_late_chunk = ctx->feat_late_dev ? ctx->feat_late_dev + (size_t)b0 * Ho * Wo * 64 : nullptr;
     if (!rc) rc = forward_chunk(ctx, m, x_dev ? x_dev + b0 * per_in : nullptr, mchunk,
-                                nb, T, H, length, normalize, mn, mx, out_dev + (size_t)b0 * Ho * Ho, nullptr);
+                                nb, T, H, W, length, normalize, mn, mx, out_dev + (size_t)b0 * Ho * Wo, nullptr);
     m->lastB = nb; ctx->last_slot = slot;
   }
   ctx->stream = main_stream;
@@ -1053,12 +1057,13 @@ static int run_chunks(stc_ctx* ctx, const float* x_dev, const float* monthly_dev
 
 int model_predict_dev(stc_ctx* ctx, const float* x_dev, int B, int T, int H, int W, int length,
                       int normalize, const double* min17, const double* max17, float* out_dev) {
-  if (H != W) STC_FAIL(STC_ERR_ARG, "predict: H must equal W");
-  if (H % 4 != 0 || H < 28) STC_FAIL(STC_ERR_ARG, "predict: H must be a multiple of 4 and >= 28");
+  // The network is fully convolutional: any H x W whose sides survive the two pool / crop levels (multiples of 4, >= 28).
+  // Square for the released graphs; the border re-segmentation pass predicts 220 x 684 seams (resegment_tiles_wide.py:478).
+  if (H % 4 != 0 || H < 28 || W % 4 != 0 || W < 28) STC_FAIL(STC_ERR_ARG, "predict: H and W must be multiples of 4 and >= 28");
   if (T < 1 || T > 12 || length < 1) STC_FAIL(STC_ERR_ARG, "predict: bad T/length");
   if (length > T) STC_FAIL(STC_ERR_ARG, "predict: length exceeds the number of sequence frames (the backward direction would read past them)");
   if (normalize && (!min17 || !max17)) STC_FAIL(STC_ERR_ARG, "predict: normalize needs min/max");
-  return run_chunks(ctx, x_dev, nullptr, B, T, H, length, normalize, min17, max17, out_dev);
+  return run_chunks(ctx, x_dev, nullptr, B, T, H, W, length, normalize, min17, max17, out_dev);
 }
 
 int64_t model_debug_read(stc_ctx* ctx, const char* name, float* out_host) {
@@ -1071,12 +1076,12 @@ int64_t model_debug_read(stc_ctx* ctx, const char* name, float* out_host) {
   auto it = tab.find(name);
   if (it == tab.end()) { ctx->err = "debug_read: unknown buffer"; return STC_ERR_ARG; }
   Act& a = *it->second;
-  int B = m->lastB, H = a.Hp - 2;
-  int64_t n = (int64_t)B * H * H * a.chunks * 8;
+  int B = m->lastB, H = a.Hp - 2, W = a.Wp - 2;
+  int64_t n = (int64_t)B * H * W * a.chunks * 8;
   if (!out_host) return n;
   float* d = nullptr;
   if (cudaMalloc((void**)&d, n * sizeof(float)) != cudaSuccess) { ctx->err = "debug_read: cudaMalloc"; return STC_ERR_NOMEM; }
-  int64_t work = (int64_t)B * H * H * a.chunks;
+  int64_t work = (int64_t)B * H * W * a.chunks;
   act_decode_kernel<<<cdiv(work, 256), 256, 0, ctx->stream>>>(a.at(0), a.plane, a.chunks, B, a.Hp, a.Wp, d);
   cudaError_t e = cudaMemcpyAsync(out_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -1090,7 +1095,7 @@ int model_predict_patches_dev(stc_ctx* ctx, const float* monthly_dev, int B, int
                               const double* min17, const double* max17, float* out_dev) {
   if (H != W || H % 4 != 0 || H < 28) STC_FAIL(STC_ERR_ARG, "predict_patches: H must equal W, be a multiple of 4 and >= 28");
   if (!min17 || !max17) STC_FAIL(STC_ERR_ARG, "predict_patches: min/max required");
-  return run_chunks(ctx, nullptr, monthly_dev, B, 4, H, 4, 1, min17, max17, out_dev);
+  return run_chunks(ctx, nullptr, monthly_dev, B, 4, H, W, 4, 1, min17, max17, out_dev);
 }
 
 // One chunk on scratch slot `slot`, enqueued on that slot's stream.  Used by the host-buffer tile path, which
@@ -1105,8 +1110,8 @@ int model_forward_slot(stc_ctx* ctx, int slot, const float* monthly_dev, int nb,
   cudaStream_t saved = ctx->stream;
   ctx->stream = model_slot_stream(ctx, slot);
   ctx->cur_slot = slot;
-  int rc = ensure_plan(ctx, m, Bc, H, 5);
-  if (!rc) rc = forward_chunk(ctx, m, nullptr, monthly_dev, nb, 4, H, 4, 1, min17, max17, out_dev, input_consumed);
+  int rc = ensure_plan(ctx, m, Bc, H, H, 5);
+  if (!rc) rc = forward_chunk(ctx, m, nullptr, monthly_dev, nb, 4, H, H, 4, 1, min17, max17, out_dev, input_consumed);
   ctx->stream = saved;
   ctx->cur_slot = 0;
   if (rc) return rc;

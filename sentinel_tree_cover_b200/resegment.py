@@ -12,13 +12,26 @@ Mirrored here, same names / arguments / return values, arrays in and out, every 
     align_subtile_histograms    :284-345   stc_align_histograms_host
     adjust_predictions          :348-357
     balance_seam_predictions    :541-553   the left/right mean correction applied to a border prediction
-NOT mirrored (said plainly in DESIGN.md): the S3 / GeoTIFF / .hkl plumbing of resegment_border (:846-1166), and the wide
-border model itself -- the reference predicts the seam with an UNRELEASED 220 x 684 graph (`retrain-combined-ca-220-684`,
-:1604) while the released graphs and this library's forward are square; recreate_resegmented_tifs (:1240) builds on it."""
+    assemble_border_subtile     :455-489   reflect padding of the edge windows + the 17-channel [LEN + 1, SIZE_Y + 14, SIZE + 14] stack
+    predict_subtile             :182-222   clip / normalise / forward of one RECTANGULAR border window (220 x 684 -> 206 x 670)
+    predict_border_subtile      :411-553   window cut-out -> NaN-date removal -> histogram alignment -> assemble -> predict -> balance
+    process_subtiles            :360-616   the loop over the border window table (arrays in, {window: prediction} out)
+    seam_prediction_accepted    :536-611   is the border prediction inside the range the two tiles' own maps allow?
+NOT mirrored (said plainly in DESIGN.md): the S3 / GeoTIFF / .hkl plumbing of resegment_border (:846-1166) and of
+recreate_resegmented_tifs (:1240).  The reference predicts the seam with an UNRELEASED weight set
+(`retrain-combined-ca-220-684`, :1605); the network is fully convolutional, so the forward here takes the 220 x 684 window
+with whatever weights the session holds (the released 172-px set in the tests, checked against the float32 restatement of
+the same graph evaluated at the same rectangular size)."""
 import numpy as np
 
 from . import api as _api
 from . import regrid as _regrid
+
+# :1664-1676 -- the 17 band ranges of the border model; identical to download_and_predict_job.py:1828-1844 except for the DEM
+# maximum (0.509... here, 0.4 there).
+MIN_ALL = list(_api.MIN_ALL)
+MAX_ALL = list(_api.MAX_ALL)
+MAX_ALL[10] = 0.509269855802243
 
 
 def align_dates(tile_date, neighb_date):
@@ -149,3 +162,127 @@ def balance_seam_predictions(preds, size):
         right[right > 0.05] -= shift
         preds = np.clip(preds, 0, 1)
     return preds
+
+
+def assemble_border_subtile(subtile_s2, s1_subtile, dem_subtile, median_s2, median_s1, start_y, size, size_y, length=4):
+    """:455-489.  A window cut at the tile edge is 7 pixels short on one side (make_tiles_right_neighb gives every window
+    SIZE + 14 columns and SIZE_Y + 7 rows at the two ends of the seam); the reference mirrors the missing rows in
+    (np.pad 'reflect': below the first window, above the others -- and the same for a short column axis) and stacks
+    [10 S2 bands | DEM | 2 S1 bands | 4 indices] for the `length` quarterly frames plus the median frame.
+    subtile_s2 [length, h, w, 14], s1_subtile [length, h, w, 2], dem_subtile [1, h, w], median_s2 [1, h, w, 14],
+    median_s1 [1, h, w, 2]  ->  float32 [length + 1, size_y + 14, size + 14, 17]."""
+    first = (start_y == 0)
+
+    def grow(a, axis):
+        pads = [(0, 0)] * a.ndim
+        pads[axis] = ((7, 0) if not first else (0, 7)) if axis == 2 else ((7, 0) if first else (0, 7))
+        return np.pad(a, pads, 'reflect')
+    arrs = [subtile_s2, s1_subtile, dem_subtile, median_s2, median_s1]
+    if subtile_s2.shape[2] == size + 7:                 # :455-463 (pad_u / pad_d are applied to axis 2 in the reference)
+        arrs = [grow(a, 2) for a in arrs]
+    if arrs[0].shape[1] == size_y + 7:                  # :466-474
+        arrs = [grow(a, 1) for a in arrs]
+    s2, s1, dem, ms2, ms1 = arrs
+    out = np.empty((length + 1, size_y + 14, size + 14, 17), np.float32)
+    out[:-1, ..., :10] = s2[..., :10]
+    out[:-1, ..., 11:13] = s1
+    out[:-1, ..., 13:] = s2[..., 10:]
+    out[:, ..., 10] = dem.repeat(length + 1, axis=0)
+    out[-1, ..., :10] = ms2[0, ..., :10]
+    out[-1, ..., 11:13] = ms1[0]
+    out[-1, ..., 13:] = ms2[0, ..., 10:]
+    return out
+
+
+def predict_subtile(subtile, sess, size=None):
+    """:182-222.  subtile [LEN + 1, SIZE_Y + 14, SIZE + 14, 17] (quarterly frames + median frame; uint16 storage is
+    rescaled by 1 / 65535 first) is clipped to the 17 band ranges, normalised to [-1, 1] and run through the ConvGRU / U-Net
+    forward at ITS OWN height and width: one rectangular launch sequence, no tiling into squares, so the seam the pass
+    exists to remove is not re-introduced inside the window.  Returns float32 [SIZE_Y, SIZE].  An all-zero window gives the
+    reference's integer 255 fill, which is SIZE x SIZE there (:220) -- `size` defaults to the window's own width - 14."""
+    subtile = np.asarray(subtile)
+    if np.sum(subtile) != 0:
+        if not isinstance(subtile.flat[0], np.floating):
+            assert np.max(subtile) > 1
+            subtile = sess.to_float32(np.ascontiguousarray(subtile).astype(np.uint16, copy=False))
+        batch_x = np.ascontiguousarray(subtile[np.newaxis], np.float32)
+        return np.float32(sess.predict(batch_x, length=subtile.shape[0] - 1, normalize=True, mins=MIN_ALL, maxs=MAX_ALL).squeeze())
+    size = subtile.shape[2] - 14 if size is None else size
+    return np.full((size, size), 255)
+
+
+def predict_border_subtile(s2, s1, s2_median, s1_median, dem, interp, dates, window, sess, size, size_y, hist_align=True,
+                           forward=None):
+    """:411-553 for one row of the border window table (make_tiles_right_neighb): cut the window out of the joint
+    two-tile arrays (s2 [LEN, H, W, 14] quarterly composites with indices, s1 [LEN, H, W, 2], medians [1, H, W, *],
+    dem [H, W], interp [n, H, W], dates [n]), drop NaN dates from the bookkeeping, align the two halves' histograms,
+    assemble, predict, balance the two sides of the seam.  `forward` (tests) replaces predict_subtile(x, sess, size).
+    Returns (preds [size_y, size] float32 -- or the integer 255 fill when fewer than two dates are left, :508-510 --,
+    dates_left)."""
+    start_x, start_y, w, h = (int(v) for v in window[:4])
+    ys, xs = slice(start_y, start_y + h), slice(start_x, start_x + w)
+    subset = np.copy(s2[:, ys, xs, :])
+    med_s2 = np.copy(s2_median[:, ys, xs, :])
+    dates_tile = np.copy(dates)
+    nan_dates = np.argwhere(np.sum(np.isnan(subset), axis=(1, 2, 3)) > 0).flatten()
+    if len(nan_dates) > 0:                              # :439-444
+        dates_tile = np.delete(dates_tile, nan_dates)
+        subset = np.delete(subset, nan_dates, 0)
+    if hist_align:                                      # in place, so the stack below is the aligned one (:446-451)
+        subset = align_subtile_histograms(subset, sess, size)
+        med_s2 = align_subtile_histograms(med_s2, sess, size)
+    x = assemble_border_subtile(subset, s1[:, ys, xs, :], dem[np.newaxis, ys, xs], med_s2, s1_median[:, ys, xs, :],
+                                start_y, size, size_y, length=s2.shape[0])
+    if len(dates_tile) < 2:
+        return np.full((size_y, size), 255), dates_tile
+    preds = forward(x) if forward is not None else predict_subtile(x, sess, size)
+    return balance_seam_predictions(preds, size), dates_tile
+
+
+def process_subtiles(s2, dates, interp, s1, dem, sess, tiles_folder, tiles_array, right_all, left_all, size, size_y,
+                     hist_align=True, length=4, forward=None):
+    """:360-616 without the file system: s2 [12, H, size + 14, 14] monthly composites with indices of the JOINT strip (the
+    tile's last and the neighbour's first (size + 14) // 2 columns), s1 [12, H, size + 14, 2], dem [H, size + 14],
+    interp [n, H, size + 14], dates [n]; right_all / left_all = the two tiles' own tree-cover maps next to the seam
+    (percent, [H, size // 2]).  NaN -> 0 (interpolate_na_vals), annual and quarterly medians on the GPU, then every window
+    of the table goes through predict_border_subtile; a prediction the acceptance rule rejects is left out, exactly like
+    the reference does not write its file.  Returns {(folder_y, folder_x): preds} -- the arrays the reference np.save's to
+    `processed/right<folder_y>/<folder_x>.npy` and to the neighbour's `processed/0/left<folder_x>.npy`."""
+    from . import tile as _tile
+    if sess is None:
+        raise RuntimeError("process_subtiles needs an StcSession (sess=...); there is no CPU path")
+    s2 = _tile.nan_to_zero(s2, sess)
+    s1 = np.ascontiguousarray(s1, np.float32)
+    s2_median = sess.temporal_median(s2)[np.newaxis]
+    s1_median = sess.temporal_median(s1)[np.newaxis]
+    if length == 4:                                     # :402-407: medians of the four 3-month groups
+        s2 = np.stack([sess.temporal_median(s2[3 * q: 3 * q + 3]) for q in range(4)])
+        s1 = np.stack([sess.temporal_median(s1[3 * q: 3 * q + 3]) for q in range(4)])
+    out = {}
+    for folder, window in zip(np.asarray(tiles_folder), np.asarray(tiles_array)):
+        preds, _ = predict_border_subtile(s2, s1, s2_median, s1_median, dem, interp, dates, window, sess, size, size_y,
+                                          hist_align=hist_align, forward=forward)
+        start_y = int(window[1])
+        if seam_prediction_accepted(preds, left_all[start_y:start_y + size_y], right_all[start_y:start_y + size_y], size):
+            out[(int(folder[0]), int(folder[1]))] = preds
+    return out
+
+
+def seam_prediction_accepted(preds, left_rows, right_rows, size):
+    """:536-611: the border prediction is written out only if its mean tree cover (percent) lies within 15 points of the
+    range spanned by the two tiles' own maps next to the seam (left_rows = the tile's last SIZE // 2 columns over the
+    window's rows, right_rows = the neighbour's first SIZE // 2; percent, NaN = no data), or if neither map has data.
+    (The three in-range / out-of-range branches of the reference all save the same array; only the last `else` skips.)"""
+    import warnings
+    if np.max(preds) >= 255:
+        return True
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        lo_ref = np.nanmean(left_rows[:, :100])
+        hi_ref = np.nanmean(right_rows[:, -100:])
+        src = 100 * np.nanmean(preds)
+    lo, hi = np.minimum(lo_ref, hi_ref), np.maximum(lo_ref, hi_ref)
+    if src <= lo - 15 or src >= hi + 15 or (lo - 15 <= src <= hi + 15):
+        return True
+    return bool(np.isnan(lo) and np.isnan(hi))
+
