@@ -432,6 +432,21 @@ int stc_align_histograms_host(stc_ctx* ctx, float* arr_host, int T, int H, int W
  * the last rank).  NaN sorts last.  Bit-exact (the values are elements of the input); three passes over the data. */
 int stc_order_stats_host(stc_ctx* ctx, const float* data, int64_t rows, int cols, int64_t ld, const int32_t* ks, float* out);
 
+/* ---- on-disk product: write_tif (src/downloading/io.py:229-263; called per tile at src/download_and_predict_job.py:2033-2036
+ * and by the border pass, src/resegment_tiles_wide.py:1240 ff) ----
+ * Single-band uint8 GeoTIFF, LZW-compressed strips, EPSG:4326, north-up: what rasterio writes for `driver='GTiff', count=1,
+ * dtype='uint8', compress='lzw', crs='+proj=longlat +datum=WGS84 +no_defs', transform=from_bounds(west, south, east, north,
+ * width=cols, height=rows)`.  img: row-major [rows][cols] (the reference passes arr.T).  Host-only (no ctx, no device work).
+ * STC_ERR_ARG: null / empty / west >= east / south >= north / more than 2^31 pixels; STC_ERR_STATE: the file could not be
+ * written (it is written under `<path>.part` and renamed); STC_ERR_NOMEM.
+ * stc_geotiff_encode_u8 returns the same bytes in a malloc'ed buffer (*out_buf, *out_len; release with stc_geotiff_free),
+ * for callers that upload the product instead of keeping a local file (the reference's next step is an S3 upload). */
+int stc_write_geotiff_u8(const char* path, const uint8_t* img, int rows, int cols, double west, double south, double east,
+                         double north);
+int stc_geotiff_encode_u8(const uint8_t* img, int rows, int cols, double west, double south, double east, double north,
+                          uint8_t** out_buf, int64_t* out_len);
+void stc_geotiff_free(uint8_t* buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,6 +136,10 @@ SYMBOLS = [
     ("stc_subtile_windows_plan", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     ("stc_adjust_shape_plan", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("stc_pool_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("stc_write_geotiff_u8", C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]),
+    ("stc_geotiff_encode_u8", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    ("stc_geotiff_free", None, [C.c_void_p]),
 ]
 
 
@@ -1029,3 +1033,35 @@ def load_mosaic_predictions(out_folder, depth, sess, size=None):
     if depth == 1:
         return sess.mosaic(preds, xs, ys, (max_x, max_y))
     return sess.mosaic_feats([p[..., :depth] for p in preds], xs, ys, (max_x, max_y))
+
+
+def write_tif(arr, point, x, y, out_folder, suffix="_FINAL"):
+    """src/downloading/io.py:229-263, same arguments and return value: `arr` (the uint8 tile of load_mosaic_predictions) is
+    written TRANSPOSED as `<out_folder><x>X<y>Y<suffix>.tif` -- single band, uint8, LZW, EPSG:4326, geotransform from the
+    bounding box point = [west, south, east, north].  Host-only (no session): the LZW / GeoTIFF writer is part of libstc
+    (csrc/stc_geotiff.cpp), rasterio / GDAL are not needed."""
+    file = out_folder + f"{str(x)}X{str(y)}Y{suffix}.tif"
+    west, east = point[0], point[2]
+    north, south = point[3], point[1]
+    a = np.ascontiguousarray(np.asarray(arr).T.astype(np.uint8))
+    rc = load_library().stc_write_geotiff_u8(os.fsencode(file), _dptr(a), a.shape[0], a.shape[1],
+                                             float(west), float(south), float(east), float(north))
+    if rc:
+        raise RuntimeError("write_tif: %s (%d)" % ({-2: "bad argument", -3: "cannot write " + file, -4: "out of memory"}.get(rc, "error"), rc))
+    return file
+
+
+def geotiff_bytes(arr, point):
+    """The bytes write_tif would put on disk for `arr` (already in raster orientation [rows, cols]) -- for callers that
+    upload the product instead of keeping a file."""
+    a = np.ascontiguousarray(arr, np.uint8)
+    buf, n = C.c_void_p(), C.c_int64()
+    lib = load_library()
+    rc = lib.stc_geotiff_encode_u8(_dptr(a), a.shape[0], a.shape[1], float(point[0]), float(point[1]), float(point[2]), float(point[3]),
+                                   C.byref(buf), C.byref(n))
+    if rc:
+        raise RuntimeError("geotiff_bytes: error %d" % rc)
+    try:
+        return C.string_at(buf, n.value)
+    finally:
+        lib.stc_geotiff_free(buf)

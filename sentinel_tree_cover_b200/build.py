@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstc.so")
-SOURCES = ["stc_api.cu", "stc_conv.cu", "stc_model.cu", "stc_preproc.cu", "stc_sr.cu", "stc_mosaic.cu", "stc_morph.cu", "stc_api2.cu", "stc_codec.cu", "stc_cloud.cu", "stc_interp.cu", "stc_cloudfill.cu", "stc_postfilter.cu", "stc_tileprep.cu", "stc_tilefuse.cu", "stc_region.cu", "stc_pool.cu", "stc_tile.cu", "stc_select.cu", "stc_pyrandom.cpp", "stc_pfcp.cu", "stc_reseg.cu"]
+SOURCES = ["stc_api.cu", "stc_conv.cu", "stc_model.cu", "stc_preproc.cu", "stc_sr.cu", "stc_mosaic.cu", "stc_morph.cu", "stc_api2.cu", "stc_codec.cu", "stc_cloud.cu", "stc_interp.cu", "stc_cloudfill.cu", "stc_postfilter.cu", "stc_tileprep.cu", "stc_tilefuse.cu", "stc_region.cu", "stc_pool.cu", "stc_tile.cu", "stc_select.cu", "stc_pyrandom.cpp", "stc_pfcp.cu", "stc_reseg.cu", "stc_geotiff.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
