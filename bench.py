@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 
 H = 168
 BATCH = 256
+PARITY_TILES = 2            # tiles of the timed batch re-run with the released weights and checked against the oracle
 METRIC = "tiles/sec (12-step 168x168x13 S1+S2 patches)"
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -241,6 +242,48 @@ def cpu_reference_tiles_per_s(n_tiles, seed=1234):
     return n_tiles / dt, torch.get_num_threads(), dt
 
 
+def quantise_u16(x):
+    """The reference's uint16 storage convention (to_int16, src/tof/tof_downloading.py:51-61): round(x * 65535)."""
+    return np.clip(np.rint(x * 65535.0), 0, 65535).astype(np.uint16)
+
+
+def cpu_parity_outputs(seed, n):
+    """Checker for the `parity` object of the bench line: the float32 oracle (NumPy assemble + normalize_subtile + torch-CPU
+    restatement of predict_graph-172.pb with the RELEASED weights) on the first `n` tiles of the batch the GPU arm timed
+    (same seeded generator): [0] on the float32 patches, [1] on the uint16-stored patches divided by 65535, which is what the
+    reference computes when it is handed the stored integers (predict_subtile :345-347).  Writes [2, n, Ho, Ho] to gpurun_out/."""
+    import torch
+    from oracle import preproc_ref as P
+    from oracle.model_ref import PredictRef
+    from sentinel_tree_cover_b200.api import MIN_ALL, MAX_ALL
+    from sentinel_tree_cover_b200.weights import load_npz
+    from sentinel_tree_cover_b200 import synth
+    base = synth.synth_monthly(16, H, seed)[:n]
+    stored = (quantise_u16(base) / 65535.).astype(np.float32)
+    model = PredictRef(load_npz(os.path.join(GOLD, "weights_predict_172.npz")))
+    outs = [[np.asarray(model.forward(P.normalize_subtile(P.assemble(src[i:i + 1]), MIN_ALL, MAX_ALL)))[0] for i in range(n)]
+            for src in (base, stored)]
+    path = os.path.join(ROOT, "gpurun_out", "bench_parity_oracle.npy")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    np.save(path, np.asarray(outs, np.float32))
+    return {"path": path, "tiles": n, "cores": torch.get_num_threads()}
+
+
+def parity_object(gpu_f32, gpu_u16, oracle, tol=1e-3):
+    """`parity` of the bench line from the GPU maps of the two wire formats and the oracle stack of cpu_parity_outputs."""
+    err_f32 = float(np.abs(gpu_f32 - oracle[0]).max())
+    err_u16 = float(np.abs(gpu_u16 - oracle[1]).max())
+    return {"max_abs_err": err_f32, "max_abs_err_uint16_wire": err_u16, "tol": tol, "ok": bool(err_f32 < tol and err_u16 < tol),
+            "tiles": int(oracle.shape[1]),
+            "oracle_shift_under_uint16_storage": float(np.abs(oracle[0] - oracle[1]).max()),
+            "note": "first tiles of the timed batch through stc_predict_patches_host with the released predict_graph-172 weights (the "
+                    "timed arm itself runs random-init weights) vs the float32 oracle (oracle/model_ref.py + preproc_ref.py) on the same "
+                    "inputs: float32 patches vs the oracle on those floats, uint16 patches vs the oracle on the same stored integers / "
+                    "65535 (the reference's integer branch, predict_subtile :345-347); oracle_shift_under_uint16_storage = how far the "
+                    "ORACLE itself moves when its input is rounded to the uint16 storage grid (the index bands divide by sums of "
+                    "near-zero synthetic reflectances)"}
+
+
 def cpu_reference_tile_chain(n_dates=12, px=206):
     """CPU leg of `tile_chain`: the oracle ports of every stage of the per-tile loop body on a px x px cut-out with
     n_dates dates (oracle/chain_ref.py); a 618-px tile is (618/px)^2 such samples."""
@@ -293,6 +336,9 @@ def run_cpu_leg(kind, arg):
             vals.append(v); secs.append(dt)
         print(json.dumps({"value": float(np.mean(vals)), "values": vals, "cores": cores, "seconds": float(np.sum(secs)), "tiles": n,
                           "steps": steps}), flush=True)
+    elif kind == "parity":                     # arg = "seed x tiles": the checker for the bench's own inputs
+        seed, n = [int(v) for v in str(arg).split("x")]
+        print(json.dumps(cpu_parity_outputs(seed, n)), flush=True)
     else:
         print(json.dumps(cpu_reference_tile_chain(int(str(arg).split("x")[0]))), flush=True)
 
@@ -526,7 +572,7 @@ def main():
     _log("e2e done; uint16 e2e")
     host_u16 = sess.pinned_empty((B, 12, H, H, 13), np.uint16, write_combined=bool(int(os.environ.get("STC_BENCH_WC", "0"))))
     for i in range(B):
-        host_u16[i] = np.clip(np.rint(host_in[i] * 65535.0), 0, 65535).astype(np.uint16)
+        host_u16[i] = quantise_u16(host_in[i])
     sess.predict_patches(host_u16, out=host_out)
     barrier()
     t0 = time.perf_counter()
@@ -539,6 +585,16 @@ def main():
     sampler.stop_flag = True                 # clocks / throttle reasons were sampled across all three timed regions
     sampler.join(timeout=2)
     chain = None
+    parity_gpu = None
+    if chain_sess is not None and rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # parity inside the bench run: the first tiles of the timed batch through the same host-buffer call with the RELEASED
+        # weights (the timed arm runs random-init weights, whose outputs no oracle bound applies to); checked below against the
+        # float32 oracle computed by a CPU child process on the same seeded inputs
+        try:
+            parity_gpu = (np.array(chain_sess.predict_patches(np.ascontiguousarray(host_in[:PARITY_TILES]))),
+                          np.array(chain_sess.predict_patches(np.ascontiguousarray(host_u16[:PARITY_TILES]))))
+        except Exception as e:
+            parity_gpu = str(e)[:200]
     if chain_sess is not None:
         _log("uint16 e2e done; whole-tile chain")
         chain = tile_chain_bench(chain_sess, rank, world, barrier, measured_peaks(), args.tile_reps)
@@ -613,6 +669,14 @@ def main():
             line["cpu_baseline"] = {"value": r["value"], "unit": "tiles/s", "cores": r["cores"], "kind": "port",
                                     "sample": "8 tiles (batch 1 each, %.1f s) of the same workload; torch-CPU restatement of the frozen "
                                               "graph (TensorFlow unavailable) + NumPy preprocessing" % r["seconds"]}
+            if isinstance(parity_gpu, tuple):
+                try:
+                    want = np.load(cpu_leg("parity", "%dx%d" % (1000 * 2 + rank, PARITY_TILES))["path"])
+                    line["parity"] = parity_object(parity_gpu[0], parity_gpu[1], want)
+                except Exception as e:
+                    line["parity"] = {"error": str(e)[:200]}
+            elif parity_gpu is not None:
+                line["parity"] = {"error": parity_gpu}
             if chain is not None:
                 try:
                     chain["cpu_baseline"] = cpu_leg("chain", 12)

@@ -35,3 +35,18 @@ def test_hbm_roofline_object(tmp_path):
     assert 0 < r["frac"] < 1
     p.write_text("label,slot,start_ms,end_ms\nconv_gates,0,0.2,0.3\n")
     assert bench.hbm_roofline(str(p), 32, peaks) is None
+
+
+def test_parity_object_and_its_cpu_leg():
+    """The `parity` entry of the bench line: the CPU child leg writes the oracle maps for the first tile of the timed batch on
+    the float32 patches and on the uint16-stored patches; parity_object compares each GPU wire format with ITS oracle."""
+    r = bench.cpu_parity_outputs(2000, 1)
+    want = np.load(r["path"])
+    assert want.shape == (2, 1, 154, 154) and want.dtype == np.float32 and 0 <= want.min() and want.max() <= 1
+    ok = bench.parity_object(want[0] + np.float32(2e-4), want[1] - np.float32(3e-4), want)
+    assert ok["ok"] and abs(ok["max_abs_err"] - 2e-4) < 1e-6 and abs(ok["max_abs_err_uint16_wire"] - 3e-4) < 1e-6 and ok["tiles"] == 1
+    assert ok["oracle_shift_under_uint16_storage"] == float(np.abs(want[0] - want[1]).max())
+    bad = bench.parity_object(want[0], want[1] + np.float32(2e-3), want)
+    assert not bad["ok"]
+    u = bench.quantise_u16(np.array([0.0, 0.5, 1.0, 1.5, -0.1], np.float32))
+    assert u.dtype == np.uint16 and u.tolist() == [0, 32768, 65535, 65535, 0]
