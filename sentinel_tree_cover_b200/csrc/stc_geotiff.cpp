@@ -17,56 +17,69 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
 
+// MSB-first bit packer writing through a raw pointer (the caller reserves the worst case: 12 bits per input byte + resets).
 struct BitSink {
-  std::vector<uint8_t>& out;
-  uint32_t acc = 0;
+  uint8_t* p;
+  uint64_t acc = 0;
   int nbits = 0;
-  explicit BitSink(std::vector<uint8_t>& o) : out(o) {}
+  explicit BitSink(uint8_t* dst) : p(dst) {}
   inline void put(uint32_t code, int width) {
     acc = (acc << width) | code;
     nbits += width;
     while (nbits >= 8) {
-      out.push_back(uint8_t(acc >> (nbits - 8)));
+      *p++ = uint8_t(acc >> (nbits - 8));
       nbits -= 8;
     }
-    acc &= (1u << nbits) - 1u;
   }
-  inline void flush() {
-    if (nbits > 0) out.push_back(uint8_t(acc << (8 - nbits)));
-    acc = 0; nbits = 0;
+  inline uint8_t* flush() {
+    if (nbits > 0) *p++ = uint8_t(acc << (8 - nbits));
+    nbits = 0;
+    return p;
   }
 };
 
-// Dictionary: open-addressed hash of (prefix code, next byte) -> code.  4096 codes at most, 8192 slots.
+// Dictionary: open-addressed hash of (prefix code, next byte) -> code.  At most 3836 entries in 8192 slots.  A slot is live
+// when its generation stamp equals the table's, so the reset at every strip start and at every Clear code is one increment
+// instead of a 32 KB memset (a 618-pixel-wide tile has a strip every 13 rows).
 struct LzwTable {
   static constexpr int SLOTS = 8192;
-  int32_t key[SLOTS];
-  int16_t val[SLOTS];
-  void clear() { memset(key, 0xff, sizeof(key)); }
+  uint32_t tag[SLOTS];      // generation << 20 | prefix << 8 | byte
+  uint16_t val[SLOTS];
+  uint32_t gen = 0;
+  void clear() {
+    if (gen == 0 || gen == 0xfff) { memset(tag, 0, sizeof(tag)); gen = 0; }
+    ++gen;
+  }
   static inline uint32_t slot(uint32_t k) { return (k * 2654435761u) >> 19; }   // 13 bits
   inline int find(uint32_t k, uint32_t& s) const {
+    const uint32_t want = (gen << 20) | k;
     s = slot(k);
-    while (key[s] != -1) {
-      if (uint32_t(key[s]) == k) return val[s];
+    while ((tag[s] >> 20) == gen) {
+      if (tag[s] == want) return val[s];
       s = (s + 1) & (SLOTS - 1);
     }
     return -1;
   }
-  inline void insert(uint32_t s, uint32_t k, int code) { key[s] = int32_t(k); val[s] = int16_t(code); }
+  inline void insert(uint32_t s, uint32_t k, int code) { tag[s] = (gen << 20) | k; val[s] = uint16_t(code); }
 };
 
-void lzw_encode_strip(const uint8_t* src, size_t n, std::vector<uint8_t>& out, LzwTable& tab) {
+// Worst-case encoded size of an n-byte strip: every byte its own 12-bit code, a Clear every 3836 codes, Clear + EOI, padding.
+inline size_t lzw_bound(size_t n) { return n + n / 2 + (n / 3836 + 4) * 2 + 8; }
+
+size_t lzw_encode_strip(const uint8_t* src, size_t n, uint8_t* dst, LzwTable& tab) {
   constexpr int CLEAR = 256, EOI = 257, FIRST = 258, LAST = 4094;   // the table is reset when code 4094 has been assigned
-  BitSink bits(out);
+  BitSink bits(dst);
   int width = 9, next = FIRST;
   tab.clear();
   bits.put(CLEAR, width);
-  if (n == 0) { bits.put(EOI, width); bits.flush(); return; }
+  if (n == 0) { bits.put(EOI, width); return size_t(bits.flush() - dst); }
   int prefix = src[0];
   for (size_t i = 1; i < n; ++i) {
     const uint32_t c = src[i];
@@ -94,7 +107,7 @@ void lzw_encode_strip(const uint8_t* src, size_t n, std::vector<uint8_t>& out, L
   if (next == LAST) { bits.put(CLEAR, width); width = 9; }
   else if (next == 512 || next == 1024 || next == 2048) ++width;
   bits.put(EOI, width);
-  bits.flush();
+  return size_t(bits.flush() - dst);
 }
 
 struct Entry { uint16_t tag, type; uint32_t count; uint32_t value; };
@@ -115,7 +128,7 @@ extern "C" int stc_geotiff_encode_u8(const uint8_t* img, int rows, int cols, dou
   if (int64_t(rows) * cols > (int64_t(1) << 31)) return STC_ERR_ARG;          // classic TIFF: 32-bit offsets
   try {
     std::vector<uint8_t> f;
-    f.reserve(size_t(rows) * cols / 2 + 4096);
+    f.reserve(size_t(rows) * cols / 2 + 65536);
     const uint8_t hdr[8] = {'I', 'I', 42, 0, 0, 0, 0, 0};             // IFD offset patched below
     append(f, hdr, 8);
 
@@ -124,12 +137,37 @@ extern "C" int stc_geotiff_encode_u8(const uint8_t* img, int rows, int cols, dou
     if (rps > rows) rps = rows;
     const int nstrips = (rows + rps - 1) / rps;
     std::vector<uint32_t> offs(nstrips), lens(nstrips);
-    static thread_local LzwTable tab;
+    // Strips are independent LZW streams (each opens with a Clear code), and the encoder is a serial dependency chain through
+    // its dictionary (~10 ns per byte): encode them on up to 8 host threads into per-strip slots, then pack the file in order.
+    const size_t slot_bytes = lzw_bound(size_t(rps) * cols);
+    std::vector<uint8_t> scratch(slot_bytes * size_t(nstrips));
+    std::vector<size_t> enc_len(nstrips);
+    auto encode_range = [&](std::atomic<int>& next_strip) {
+      static thread_local LzwTable tab;
+      for (int s = next_strip.fetch_add(1); s < nstrips; s = next_strip.fetch_add(1)) {
+        const int r0 = s * rps, nr = (r0 + rps <= rows) ? rps : rows - r0;
+        enc_len[s] = lzw_encode_strip(img + size_t(r0) * cols, size_t(nr) * cols, scratch.data() + slot_bytes * size_t(s), tab);
+      }
+    };
+    {
+      std::atomic<int> next_strip{0};
+      unsigned nt = std::thread::hardware_concurrency();
+      if (nt > 8) nt = 8;
+      if (nt > unsigned(nstrips)) nt = unsigned(nstrips);
+      if (size_t(rows) * cols < (size_t(1) << 16) || nt < 2) {
+        encode_range(next_strip);
+      } else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nt; ++t) pool.emplace_back([&] { encode_range(next_strip); });
+        encode_range(next_strip);
+        for (auto& th : pool) th.join();
+      }
+    }
     for (int s = 0; s < nstrips; ++s) {
-      const int r0 = s * rps, nr = (r0 + rps <= rows) ? rps : rows - r0;
+      if (f.size() + enc_len[s] > 0xfffffff0u) return STC_ERR_ARG;     // classic TIFF: 32-bit file offsets
       offs[s] = uint32_t(f.size());
-      lzw_encode_strip(img + size_t(r0) * cols, size_t(nr) * cols, f, tab);
-      lens[s] = uint32_t(f.size()) - offs[s];
+      lens[s] = uint32_t(enc_len[s]);
+      f.insert(f.end(), scratch.data() + slot_bytes * size_t(s), scratch.data() + slot_bytes * size_t(s) + enc_len[s]);
       pad_even(f);
     }
 
