@@ -591,8 +591,9 @@ def main():
         # weights (the timed arm runs random-init weights, whose outputs no oracle bound applies to); checked below against the
         # float32 oracle computed by a CPU child process on the same seeded inputs
         try:
-            parity_gpu = (np.array(chain_sess.predict_patches(np.ascontiguousarray(host_in[:PARITY_TILES]))),
-                          np.array(chain_sess.predict_patches(np.ascontiguousarray(host_u16[:PARITY_TILES]))))
+            n_par = min(PARITY_TILES, B)
+            parity_gpu = (np.array(chain_sess.predict_patches(np.ascontiguousarray(host_in[:n_par]))),
+                          np.array(chain_sess.predict_patches(np.ascontiguousarray(host_u16[:n_par]))))
         except Exception as e:
             parity_gpu = str(e)[:200]
     if chain_sess is not None:
@@ -671,7 +672,7 @@ def main():
                                               "graph (TensorFlow unavailable) + NumPy preprocessing" % r["seconds"]}
             if isinstance(parity_gpu, tuple):
                 try:
-                    want = np.load(cpu_leg("parity", "%dx%d" % (1000 * 2 + rank, PARITY_TILES))["path"])
+                    want = np.load(cpu_leg("parity", "%dx%d" % (1000 * 2 + rank, len(parity_gpu[0])))["path"])
                     line["parity"] = parity_object(parity_gpu[0], parity_gpu[1], want)
                 except Exception as e:
                     line["parity"] = {"error": str(e)[:200]}
