@@ -56,9 +56,182 @@ __global__ void __launch_bounds__(128) assemble_kernel(const float* __restrict__
   }
 }
 
+// Staged variants (default whenever H*W is a multiple of 4, which makes every 32-pixel run of the input 16-byte aligned):
+// same arithmetic, different data movement.  The direct kernel above reads a pixel's 12 x 13 values with 4-byte loads 52 bytes
+// apart and writes its 5 x 17 results 68 bytes apart: every 128-byte line passes through L1 thirteen (seventeen) times, and the
+// kernel sits at 32 % of the HBM peak whatever the batch (profiles/r01_h_sweep.md).  Here a 32-pixel GROUP is the unit: one
+// elected lane fetches the twelve contiguous 32 x 13-float runs with cp.async.bulk into the group's shared-memory tile
+// (completion on the tile's mbarrier) and lane l reads pixel l's values at a 13-word stride (odd: bank-conflict free).
+// Persistent grid, one CTA per SM; the warps drift apart so the copies of some overlap the sorting networks of others.
+//   MODE 0: one warp per group, 7 tiles per CTA; results go through a per-warp output tile (17-word stride) and leave as five
+//           contiguous 32 x 17-float runs, coalesced.  Measured 0.37 of the HBM peak (direct kernel 0.32): with 7 warps per SM
+//           the kernel is bound by the latency of its own arithmetic (IEEE divisions of the exact index forms, 60-comparator
+//           median networks), not by the memory system.
+//   MODE 1: one warp per group, 11 tiles per CTA, results stored directly (68-byte stride; L2 merges the partial lines).
+//   MODE 2: TWO warps per group, 11 tiles per CTA = 22 warps: warp 0 of a pair forms the medians of the 13 bands, warp 1
+//           computes the four indices from the same tile and their medians; a named barrier per pair releases the tile.
+//           MODES 1 and 2 measured 0.27 of the HBM peak, BELOW the direct kernel: the 68-byte-stride stores are what costs
+//           (seventeen partial writes per 32-byte sector), not the number of warps -- 22 warps are no faster than 11.
+//   MODE 3: two warps per group as in MODE 2 AND the output tile of MODE 0 (7 tiles, 14 warps); both warps store.  Measured
+//           0.395 of the HBM peak at B = 256 (MODE 0 on the same box: 0.370): the default.  Twice the warps buy 7 %, so the
+//           arithmetic latency is not the bound either; what is has not been profiled (profiles/r02_sweep.md).
+template <int MODE> struct AsCfg {
+  static constexpr bool HAS_OUT = (MODE == 0 || MODE == 3);         // results leave through an output tile, coalesced
+  static constexpr int TILES = HAS_OUT ? 7 : 11;
+  static constexpr int WPT = (MODE >= 2) ? 2 : 1;                    // warps per tile
+  static constexpr int GE = 32 * 13, GO = 32 * 17;
+  static constexpr int IN_BYTES = 12 * GE * 4;
+  static constexpr int OUT_BYTES = HAS_OUT ? 5 * GO * 4 : 0;
+  static constexpr int TILE_BYTES = IN_BYTES + OUT_BYTES;
+  static constexpr int THREADS = TILES * WPT * 32;
+  static constexpr int SMEM = TILES * TILE_BYTES + 8 * TILES;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(AsCfg<MODE>::THREADS, 1) assemble_staged_kernel(const float* __restrict__ in, float* __restrict__ out, int HW,
+                                                                                  int groups_per_sample, int total_groups) {
+  using C = AsCfg<MODE>;
+  constexpr int GE = C::GE, GO = C::GO;
+  extern __shared__ __align__(128) uint8_t as_smem[];
+  const int wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int tix = wid / C::WPT, role = wid - tix * C::WPT;
+  float* tile = reinterpret_cast<float*>(as_smem + tix * C::TILE_BYTES);
+  float* otile = reinterpret_cast<float*>(as_smem + tix * C::TILE_BYTES + C::IN_BYTES);      // MODE 0 only
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(as_smem + C::TILES * C::TILE_BYTES) + 8u * tix;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  if (role == 0 && lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t elected = 0;
+  asm volatile("{\n.reg .pred px;\nelect.sync _|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}" : "=r"(elected));
+  const bool leader = elected && role == 0;
+  const int64_t fs_in = (int64_t)HW * 13, fs_out = (int64_t)HW * 17;
+  uint32_t phase = 0;
+  for (int g = blockIdx.x * C::TILES + tix; g < total_groups; g += gridDim.x * C::TILES) {
+    const int b = g / groups_per_sample;
+    const int r0 = (g - b * groups_per_sample) * 32;
+    const int npx = (HW - r0 < 32) ? HW - r0 : 32;
+    const uint32_t run_bytes = (uint32_t)(npx * 13 * 4);
+    const float* src = in + ((int64_t)b * 12 * HW + r0) * 13;
+    if (C::WPT == 2)      // both warps of the pair are done with the tile of the previous group
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + tix) : "memory");
+    if (leader) {
+      // the tile was last read through the generic proxy (previous iteration): order those reads before the async writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(12u * run_bytes) : "memory");
+    }
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+      if (leader)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(tile_s + (uint32_t)(t * GE * 4)), "l"(src + (int64_t)t * fs_in), "r"(run_bytes), "r"(bar) : "memory");
+    }
+    {
+      uint32_t ok = 0;
+      long long t0 = clock64();
+      while (!ok) {
+        asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+        if (!ok && clock64() - t0 > 4000000000LL) __trap();          // never hang the box
+      }
+      phase ^= 1;
+    }
+    if (lane < npx) {
+      const float* mine = tile + lane * 13;
+      // where this lane's results go: its slot of the output tile (MODE 0) or its pixel of the five output frames
+      float* mo = C::HAS_OUT ? otile + lane * 17 : out + ((int64_t)b * 5 * HW + r0 + lane) * 17;
+      const int64_t fo = C::HAS_OUT ? (int64_t)GO : fs_out;           // frame stride of `mo`
+      float bands[5][12];   // B2, B3, B4, B8, B11 (channels 0,1,2,3,8)
+      if (C::WPT == 1 || role == 0) {
+#pragma unroll
+        for (int c = 0; c < 13; ++c) {
+          float v[12];
+#pragma unroll
+          for (int t = 0; t < 12; ++t) v[t] = mine[t * GE + c];
+          if (C::WPT == 1) {
+            if (c < 4) {
+#pragma unroll
+              for (int t = 0; t < 12; ++t) bands[c][t] = v[t];
+            } else if (c == 8) {
+#pragma unroll
+              for (int t = 0; t < 12; ++t) bands[4][t] = v[t];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mo[q * fo + c] = med3(v[3 * q], v[3 * q + 1], v[3 * q + 2]);
+          mo[4 * fo + c] = median12_net(v);
+        }
+      }
+      if (C::WPT == 1 || role == 1) {
+        if (C::WPT == 2) {
+#pragma unroll
+          for (int t = 0; t < 12; ++t) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bands[k][t] = mine[t * GE + k];
+            bands[4][t] = mine[t * GE + 8];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float v[12];
+#pragma unroll
+          for (int t = 0; t < 12; ++t) {
+            float b2 = bands[0][t], b3 = bands[1][t], b4 = bands[2][t], b8 = bands[3][t], b11 = bands[4][t];
+            v[t] = (k == 0) ? idx_evi(b2, b3, b4, b8) : (k == 1) ? idx_bi(b2, b4, b8, b11)
+                 : (k == 2) ? idx_msavi2(b4, b8) : idx_grndvi(b3, b4, b8);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mo[q * fo + 13 + k] = med3(v[3 * q], v[3 * q + 1], v[3 * q + 2]);
+          mo[4 * fo + 13 + k] = median12_net(v);
+        }
+      }
+    }
+    __syncwarp();      // every lane is done with the input tile (and this warp's part of the output tile is written)
+    if (C::HAS_OUT) {
+      if (C::WPT == 2)   // the partner's part of the output tile is written too
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + tix) : "memory");
+      float* dst = out + ((int64_t)b * 5 * HW + r0) * 17;
+      const int nrun = npx * 17;
+#pragma unroll
+      for (int f = 0; f < 5; ++f)
+        for (int i = lane + 32 * role; i < nrun; i += 32 * C::WPT) dst[f * fs_out + i] = otile[f * GO + i];
+      if (C::WPT == 1) __syncwarp();    // the stores have read the output tile before the next group overwrites it
+                                        // (two warps per tile: the pair barrier at the top of the next iteration)
+    }
+  }
+}
+
+template <int MODE>
+static int launch_assemble_staged(stc_ctx* ctx, const float* monthly_dev, int B, int HW, float* out_dev) {
+  using C = AsCfg<MODE>;
+  static bool cfg = false;
+  if (!cfg) { STC_CUDA(cudaFuncSetAttribute(assemble_staged_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); cfg = true; }
+  const int gps = cdiv((int64_t)HW, 32);
+  const int64_t total = (int64_t)gps * B;
+  if (total >= (1ll << 31)) STC_FAIL(STC_ERR_ARG, "assemble: batch too large");
+  const int grid = (int)std::min<int64_t>(cdiv(total, C::TILES), ctx->num_sms);
+  TraceScope ts_(ctx, "assemble_staged_kernel");
+  assemble_staged_kernel<MODE><<<grid, C::THREADS, C::SMEM, ctx->stream>>>(monthly_dev, out_dev, HW, gps, (int)total);
+  return STC_OK;
+}
+
 int pre_assemble_dev(stc_ctx* ctx, const float* monthly_dev, int B, int H, int W, float* out_dev) {
   int64_t n = (int64_t)B * H * W;
-  { TraceScope ts_(ctx, "assemble_kernel"); assemble_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(monthly_dev, out_dev, B, H * W); }
+  const int HW = H * W;
+  // STC_ASSEMBLE_V: -1 = the direct-load kernel, 0 .. 3 = the staged variants above (A/B switch; default from the measurement)
+  static const int variant = getenv("STC_ASSEMBLE_V") ? atoi(getenv("STC_ASSEMBLE_V")) : 3;
+  const bool aligned = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(monthly_dev) & 15) == 0);
+  if (aligned && variant >= 0) {
+    int rc = variant == 3 ? launch_assemble_staged<3>(ctx, monthly_dev, B, HW, out_dev)
+           : variant == 2 ? launch_assemble_staged<2>(ctx, monthly_dev, B, HW, out_dev)
+           : variant == 1 ? launch_assemble_staged<1>(ctx, monthly_dev, B, HW, out_dev)
+                          : launch_assemble_staged<0>(ctx, monthly_dev, B, HW, out_dev);
+    if (rc) return rc;
+  } else {
+    TraceScope ts_(ctx, "assemble_kernel"); assemble_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(monthly_dev, out_dev, B, HW);
+  }
   STC_CUDA(cudaGetLastError());
   ctx->launches++;
   return STC_OK;

@@ -19,9 +19,11 @@ def test_indices_bit_exact(sess):
 
 
 def test_assemble_bit_exact(sess):
-    for (B, H, seed) in ((1, 12, 5), (3, 33, 6)):
+    """H*W a multiple of 4 -> the bulk-copy staged kernel (12 x 12: a half-filled last group of 16 pixels; 44 and 168: many
+    groups per sample, several samples); 33 x 33 -> the direct-load kernel (runs not 16-byte aligned).  Both bit-exact."""
+    for (B, H, seed) in ((1, 12, 5), (3, 33, 6), (2, 44, 7), (3, 168, 8)):
         m = P.synth_monthly(B, H, seed)
-        assert np.array_equal(sess.assemble(m), P.assemble(m))
+        assert np.array_equal(sess.assemble(m), P.assemble(m)), (B, H)
 
 
 def test_temporal_median_bit_exact(sess):
