@@ -9,8 +9,10 @@ The reference imports network / geo / TF packages at module import time
 (src/download_and_predict_job.py:1-53) that are not installed here and are
 never touched by the numeric functions we call.  We register inert stub
 modules for them, give `bottleneck` NumPy equivalents, and provide
-`skimage.transform.resize` via scipy.ndimage.zoom (order 0 exact; order 1 is
-the one place the shim is not guaranteed identical to scikit-image).
+`skimage.transform.resize` via scipy.ndimage (the algorithm scikit-image >= 0.19
+publishes: anti-aliasing Gaussian when an axis shrinks, then ndimage.zoom with
+grid_mode; order 0 exact; order 1 is the one place the shim is not guaranteed
+identical to scikit-image).
 """
 import os
 import sys
@@ -95,12 +97,22 @@ def install():
     _stub("tensorflow.compat")
     _stub("tensorflow.compat.v1")
 
-    def resize(img, shape, order=1, **kw):
+    def resize(img, shape, order=1, anti_aliasing=None, **kw):
+        # scikit-image >= 0.19 (skimage/transform/_warps.py: resize): Gaussian pre-filter of sigma (in/out - 1) / 2 on the axes
+        # that shrink (anti_aliasing defaults to on for non-boolean input unless integer input with order 0), then ndimage.zoom
+        # with grid_mode=True.  Every call the goldens made before this branch existed enlarges or keeps the size.
         img = np.asarray(img)
-        zoom = [s / float(i) for s, i in zip(shape, img.shape)]
+        factors = np.divide(img.shape, shape)
+        if anti_aliasing is None:
+            anti_aliasing = (img.dtype != bool and not (np.issubdtype(img.dtype, np.integer) and order == 0)
+                             and bool(np.any(factors > 1)))
         # skimage's default mode 'reflect' is ndimage's 'mirror' (skimage.transform._warps._to_ndimage_mode)
-        return ndi.zoom(img, zoom, order=order, mode="nearest" if order == 0 else "mirror",
-                        grid_mode=True, prefilter=False)
+        mode = "nearest" if order == 0 else "mirror"
+        if anti_aliasing:
+            img = ndi.gaussian_filter(img.astype(np.float64) if img.dtype.kind != "f" else img, np.maximum(0, (factors - 1) / 2),
+                                      cval=0, mode="mirror")
+        zoom = [s / float(i) for s, i in zip(shape, img.shape)]
+        return ndi.zoom(img, zoom, order=order, mode=mode, grid_mode=True, prefilter=False)
     sys.modules["skimage.transform"].resize = resize
 
     try:

@@ -17,11 +17,14 @@ Mirrored here, same names / arguments / return values, arrays in and out, every 
     predict_border_subtile      :411-553   window cut-out -> NaN-date removal -> histogram alignment -> assemble -> predict -> balance
     process_subtiles            :360-616   the loop over the border window table (arrays in, {window: prediction} out)
     seam_prediction_accepted    :536-611   is the border prediction inside the range the two tiles' own maps allow?
-NOT mirrored (said plainly in DESIGN.md): the S3 / GeoTIFF / .hkl plumbing of resegment_border (:846-1166) and of
-recreate_resegmented_tifs (:1240).  The reference predicts the seam with an UNRELEASED weight set
+    mosaic_subtiles             :1169-1237  weighted mean of one kind of subtile layers + the kind's blending weight (host)
+    recreate_resegmented_tifs   :1240-1547  re-mosaic of a tile from its normal subtiles and border strips (host, .npy files)
+NOT mirrored (said plainly in DESIGN.md): the S3 / GeoTIFF / .hkl plumbing of resegment_border (:846-1166).  The reference predicts the seam with an UNRELEASED weight set
 (`retrain-combined-ca-220-684`, :1605); the network is fully convolutional, so the forward here takes the 220 x 684 window
 with whatever weights the session holds (the released 172-px set in the tests, checked against the float32 restatement of
 the same graph evaluated at the same rectangular size)."""
+import os
+
 import numpy as np
 
 from . import api as _api
@@ -286,3 +289,232 @@ def seam_prediction_accepted(preds, left_rows, right_rows, size):
         return True
     return bool(np.isnan(lo) and np.isnan(hi))
 
+
+
+# ---- re-mosaic of a tile's subtile predictions after the border pass (:1164-1547) -----------------------------------------
+# Host logic over small arrays (one 618 x 618 tile, a few dozen layers): file listing, float weights, one weighted mean.
+# It runs once per tile pair after the GPU work, like the window tables above.
+
+def resize_linear(img, shape, anti_aliasing=None):
+    """`skimage.transform.resize(img, shape, order=1)` as scikit-image >= 0.19 computes it (the package is not a dependency
+    here; this restates its published algorithm over SciPy, which is what scikit-image itself calls): when an axis shrinks, a
+    Gaussian of sigma (in / out - 1) / 2 along that axis first (`anti_aliasing`, on by default for non-boolean input), then
+    `scipy.ndimage.zoom(order=1, mode='mirror', grid_mode=True)` ('mirror' is ndimage's name for skimage's 'reflect')."""
+    import scipy.ndimage as ndi
+    img = np.asarray(img)
+    if img.dtype not in (np.float32, np.float64):
+        img = img.astype(np.float64)
+    factors = np.divide(img.shape, shape)
+    if anti_aliasing is None:
+        anti_aliasing = bool(np.any(factors > 1))
+    if anti_aliasing:
+        img = ndi.gaussian_filter(img, np.maximum(0, (factors - 1) / 2), cval=0, mode="mirror")
+    return ndi.zoom(img, [o / float(i) for o, i in zip(shape, img.shape)], order=1, mode="mirror", cval=0, grid_mode=True)
+
+
+def adjust_resegment(res, mults, n):
+    """:1164-1166."""
+    return res * np.maximum(np.sum(mults[..., :n], axis=-1), 1.)
+
+
+# which edge flags feather which end of the ramp, and where the zero half goes, per border kind (:1192-1235)
+#            flip the ramp, flag for columns [:300], flag for columns [-300:], zeros first, transpose
+_RAMP_PLAN = {"r": (False, "up", "down", True, None),
+              "l": (True, "up", "down", False, None),
+              "u": (True, "left", "right", False, "T"),
+              "d": (False, "right", "left", True, "T-flip")}
+
+
+def mosaic_subtiles(preds, mults, na, kind, left, right, up, down, size=670, resize=None):
+    """:1169-1237, same arguments (+ `size` = the reference's global SIZE, `resize` = the bilinear resize to use, default
+    `resize_linear`).  preds / mults [X, Y, n] float32 layers (NaN / 0 where a layer has no data; both are modified in place
+    like the reference does), na [X, Y, 1].  Returns (weighted mean of the layers [X, Y], blending weight of this kind [X, Y]):
+    a Gaussian for the normal subtiles, for a border kind a ramp (x / half) ** 1.2 rising towards the shared edge over
+    `size // 2` pixels, feathered by (t / 300) ** 1.33 over 300 pixels at the ends where another border strip exists."""
+    resize = resize or resize_linear
+    preds[np.tile(na, (1, 1, preds.shape[-1])) > 0] = np.nan
+    mults[np.isnan(preds)] = 0.
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mults = mults / np.sum(mults, axis=-1)[..., np.newaxis]
+    preds = np.nansum(preds * mults, axis=-1)
+    X, Y = preds.shape
+    half = size // 2
+    if kind == "n":
+        m = resize(_api.fspecial_gauss(X, X / 5.25), (X, Y))
+    else:
+        flip, flag_lo, flag_hi, zeros_first, post = _RAMP_PLAN[kind]
+        present = {"left": left is not None, "right": right is not None, "up": up is not None, "down": down is not None}
+        feather = np.tile((np.arange(0, 300, 1) / 300) ** 1.33, (half, 1))
+        m = (np.ones((half, Y)) * (np.arange(0, half, 1) / half)[:, np.newaxis]) ** 1.2
+        if flip:
+            m = np.flipud(m)
+        m = np.copy(m)
+        if present[flag_lo]:
+            m[:, :300] *= feather
+        if present[flag_hi]:
+            m[:, -300:] *= np.fliplr(feather)
+        m = resize(m, (half, Y))
+        zeros = np.zeros((X - half, Y))
+        m = np.concatenate([zeros, m] if zeros_first else [m, zeros], axis=0)
+        if post == "T":
+            m = m.T
+        elif post == "T-flip":
+            m = np.flipud(m.T)
+        m = resize(m, (X, Y))
+    m[np.isnan(preds)] = 0.
+    return preds, m
+
+
+def _gauss_sigma(subtile_size, border):
+    """:1301-1311 (normal subtiles), :1343-1352 (border strips): the Gaussian width for a subtile size."""
+    table = {208: 44, 216: 44, 348: 85, 412: 95}
+    if subtile_size in table:
+        return table[subtile_size]
+    if border:
+        return 150 if (subtile_size == 588 or subtile_size >= 620) else 28
+    return 38 if subtile_size == 168 else 28
+
+
+# per border kind: file-name prefix, which axis of the TRANSPOSED prediction is halved, which half is kept
+_STRIP_PLAN = {"l": ("left", 0, 1), "r": ("", 0, 0), "u": ("up", 1, 1), "d": ("down", 1, 0)}
+
+
+def _list_subtile_files(out_folder):
+    """The reference's os.listdir walk (:1254-1271): ({kind: [(x, y, path)]} in listing order, number of .npy files)."""
+    entries = [e for e in os.listdir(out_folder) if ".DS" not in e]
+    right_dirs = [e for e in entries if "right" in e]
+    x_dirs = [e for e in entries if "right" not in e and len(os.listdir(os.path.join(out_folder, e))) > 0]
+    found = {k: [] for k in "nlrud"}
+    for xd in x_dirs:
+        for f in os.listdir(os.path.join(out_folder, xd)):
+            if ".DS" in f:
+                continue
+            kind = "l" if "left" in f else "d" if "down" in f else "u" if "up" in f else "n"
+            y = int(f[len(_STRIP_PLAN[kind][0]) if kind != "n" else 0:-4])
+            found[kind].append((int(xd), y, os.path.join(out_folder, xd, f)))
+    for xd in right_dirs:
+        for f in os.listdir(os.path.join(out_folder, xd)):
+            if ".DS" not in f:
+                found["r"].append((int(xd[5:]), int(f[:-4]), os.path.join(out_folder, xd, f)))
+    n_files = sum(len(v) for v in found.values())
+    return found, n_files
+
+
+def recreate_resegmented_tifs(out_folder, shape, size=670, resize=None):
+    """:1240-1547, same arguments (+ `size` = the reference's global SIZE, + `resize`) and return value `(preds, sums)`.
+    Reads `<out_folder>/<x>/<y>.npy` (normal subtiles), `<x>/left<y>.npy`, `<x>/up<y>.npy`, `<x>/down<y>.npy` and
+    `right<x>/<y>.npy` (border strips written by the border pass of this tile and of its neighbours; a strip file holds the
+    window across the seam, of which this tile owns one half), builds one layer stack per kind, takes the weighted mean inside
+    each kind (`mosaic_subtiles`) and blends the five with the kind weights.  preds: float64 [shape[1], shape[0]], tree cover
+    in percent, 255 = no data (no normal prediction, or a border strip without data where strips exist)."""
+    resize = resize or resize_linear
+    X, Y = int(shape[1]), int(shape[0])
+    found, n_files = _list_subtile_files(out_folder)
+    n_border = sum(len(found[k]) for k in "lrud")
+    stacks = {}
+    covered = {"n": np.zeros((X, Y)), "b": np.zeros((X, Y))}                # how many subtiles / strips cover a pixel
+    nodata = {"n": np.zeros((X, Y)), "b": np.zeros((X, Y))}                 # ... of which without data there
+    for kind in "nlrud":
+        files = found[kind]
+        if kind != "n" and not files:
+            continue
+        n_layers = (n_files - n_border) if kind == "n" else len(files)
+        P = np.full((X, Y, n_layers), np.nan, dtype=np.float32)
+        M = np.full((X, Y, n_layers), 0, dtype=np.float32)
+        i = 0
+        for (x0, y0, path) in files:
+            raw = np.load(path)
+            if kind == "n":
+                sx, sy = raw.shape[1], raw.shape[0]
+                sub = max(sx, sy)
+                has_data = np.sum(raw) < sx * sy * 255
+                if not has_data:
+                    continue
+                p = (raw * 100).T.astype(np.float32)
+                if (x0 + sx - 1) < X and (y0 + sy - 1) < Y:
+                    w = _api.fspecial_gauss(sub, _gauss_sigma(sub, False))
+                    w[p > 100] = 0.
+                    P[x0:x0 + sx, y0:y0 + sy, i] = p
+                    M[x0:x0 + sx, y0:y0 + sy, i] = w
+                    group = "n"
+                else:
+                    i += 1
+                    continue
+            else:
+                _, axis, keep = _STRIP_PLAN[kind]
+                sx = raw.shape[1] // 2 if axis == 0 else raw.shape[1]
+                sy = raw.shape[0] // 2 if axis == 1 else raw.shape[0]
+                sub = max(2 * sx if axis == 0 else sx, 2 * sy if axis == 1 else sy)
+                cut = sx if axis == 0 else sy
+                half_of = (lambda a: (a[cut:] if keep else a[:cut]) if axis == 0 else (a[:, cut:] if keep else a[:, :cut]))
+                w = resize(half_of(_api.fspecial_gauss(sub, _gauss_sigma(sub, True))), (sx, sy))
+                has_data = np.sum(raw) < sx * sy * 255
+                if not has_data:
+                    i += 1
+                    continue
+                p = half_of((raw * 100).T.astype(np.float32))
+                P[x0:x0 + sx, y0:y0 + sy, i] = p
+                P[x0:x0 + sx, y0:y0 + sy, :][p > 100] = 255.          # :1361: every layer of the kind, at the strip's no-data px
+                w[p > 100] = 0.
+                M[x0:x0 + sx, y0:y0 + sy, i] = w
+                group = "b"
+            covered[group][x0:x0 + sx, y0:y0 + sy] += 1.
+            nodata[group][x0:x0 + sx, y0:y0 + sy] += (p > 100)
+            i += 1
+        stacks[kind] = (P, M)
+
+    # :1494-1501: no data where no normal subtile has data; under border strips also where any strip lacks data
+    normal_valid = covered["n"] - nodata["n"]
+    na = np.zeros((X, Y))
+    na[(covered["b"] == 0) & (normal_valid == 0)] = 1.
+    na[(covered["b"] > 0) & ((normal_valid == 0) | (nodata["b"] > 0))] = 1.
+    na = na[..., np.newaxis]
+    layers = {k: (stacks[k][0] if k in stacks else None) for k in "lrud"}
+    out = {}
+    for kind in "nrlud":
+        if kind in stacks:
+            P, M = stacks[kind]
+            pk, mk = mosaic_subtiles(P, M, na, kind, layers["l"], layers["r"], layers["u"], layers["d"], size=size, resize=resize)
+            if kind != "n":
+                mk[np.sum(~np.isnan(P), axis=-1) == 0] = 0.
+            out[kind] = (pk, mk)
+        else:
+            out[kind] = (np.zeros_like(out["n"][0]), np.zeros_like(out["n"][0]))
+    (pn, mn), (pl, ml), (pr, mr), (pu, mu), (pd_, md) = (out[k] for k in "nlrud")
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sums = (ml + mr + mu + md + mn)
+        preds = (pl * (ml / sums)) + (pd_ * (md / sums))
+        preds = preds + (pr * (mr / sums)) + (pu * (mu / sums))
+        preds = preds + (pn * (mn / sums))
+    preds[np.isnan(preds)] = 255.
+    preds[na.squeeze() == 1.] = 255.
+    return preds, sums
+
+
+def seam_smooth_diff(predictions_left, predictions_right):
+    """:1763-1770: mean absolute difference (percent) between the tile's last 8 rows and the neighbour's first 8 rows of the
+    re-mosaicked maps, each averaged over the 8 rows first; 255 = no data is ignored.  NaN if no column has data on both sides."""
+    import warnings
+    right = np.array(predictions_right[:8, :], np.float32)
+    left = np.array(predictions_left[-8:, :], np.float32)
+    right[right == 255] = np.nan
+    left[left == 255] = np.nan
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        return np.nanmean(abs(np.nanmean(right, axis=0) - np.nanmean(left, axis=0)))
+
+
+def write_smoothed_pair(predictions_left, predictions_right, bbx, neighb_bbx, x, y, path_to_tile, path_to_right, smooth_diff, diff):
+    """:1796-1816: if the seam got no worse than 20 points over the difference before the border pass (`diff`, NaN -> 100,
+    :1771), write both re-mosaicked tiles as `<x>X<y>Y_SMOOTH_X.tif` (`_SMOOTH_XY` when a Y pass has already written one)
+    through the libstc GeoTIFF writer.  Returns the two file names, or None when the pair is rejected.  Uploading and the
+    cleanup of the working folders (:1806,1818) are the caller's."""
+    diff = 100 if np.isnan(diff) else diff
+    if not (smooth_diff < (diff + 20) or np.isnan(smooth_diff)):
+        return None
+    files = []
+    for preds, box, tx, folder in ((predictions_left, bbx, x, path_to_tile), (predictions_right, neighb_bbx, str(int(x) + 1), path_to_right)):
+        stem = "%s/%sX%sY" % (folder, str(tx), str(y))
+        redo = os.path.exists(stem + "_SMOOTH_XY.tif") or os.path.exists(stem + "_SMOOTH_Y.tif")
+        files.append(_api.write_tif(preds, box, tx, y, folder, "_SMOOTH_XY" if redo else "_SMOOTH_X"))
+    return files
