@@ -1,4 +1,5 @@
 """GPU parity tests for the model path, through the C ABI (ctypes)."""
+import os
 import numpy as np
 import pytest
 from conftest import golden
@@ -125,6 +126,23 @@ def test_superresolve_vs_graph_golden(sess, sr_weights):
     eq = np.abs(y - SuperresolveRef(sr_weights, quant="fp16").forward(x, x[..., 4:])).max()
     print("superresolve vs fp16-operand oracle", eq)
     assert eq < 6e-4
+
+
+def test_superresolve_vs_opencv_execution_of_the_released_graph(sess):
+    """Against outputs of the released superresolve_graph.pb run by OpenCV's DNN module (tests/golden/superresolve_cv.npz,
+    tools/make_golden_cv.py): a third-party executor of the reference's own graph.  Same tolerance as the graph golden."""
+    import importlib.util
+    cv = golden("superresolve_cv.npz")
+    g = golden("superresolve.npz")
+    y = sess.superresolve(g["x"], g["x"][..., 4:])
+    assert np.abs(y - cv["y_small"]).max() < 2e-3
+    spec = importlib.util.spec_from_file_location("mk_cv", os.path.join(os.path.dirname(__file__), "..", "tools", "make_golden_cv.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    x = mk.window_input(int(cv["seed_window"]))
+    y = sess.superresolve(x, x[..., 4:])
+    err = np.abs(y - cv["y_window"]).max()
+    print("superresolve vs OpenCV, 118-px window", err)
+    assert err < 2e-3
 
 
 def test_superresolve_fused_epilogues_equal_separate_passes(sess, monkeypatch):

@@ -25,6 +25,40 @@ def test_superresolve_restatement_matches_graph_golden(sr_weights):
     assert np.abs(y - g["y"]).max() < 5e-6
 
 
+def _mk_cv():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk_cv", os.path.join(os.path.dirname(__file__), "..", "tools", "make_golden_cv.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def test_superresolve_oracle_pinned_to_opencv_execution_of_the_released_graph(sr_weights):
+    """tests/golden/superresolve_cv.npz = the released superresolve_graph.pb run by OpenCV's DNN module (a third-party
+    executor sharing no code with the oracle; tools/make_golden_cv.py).  The interpreter-made golden and the restatement
+    must agree with it to float32 op-order noise, on the golden's input and on a 118-px padded window."""
+    cv = golden("superresolve_cv.npz")
+    g = golden("superresolve.npz")
+    assert np.abs(g["y"] - cv["y_small"]).max() < 3e-5                      # interpreter vs OpenCV (measured 9.9e-6)
+    ref = SuperresolveRef(sr_weights)
+    assert np.abs(ref.forward(g["x"], g["x"][..., 4:]) - cv["y_small"]).max() < 3e-5
+    x = _mk_cv().window_input(int(cv["seed_window"]))
+    y = ref.forward(x, x[..., 4:])
+    assert y.shape == cv["y_window"].shape and np.abs(y - cv["y_window"]).max() < 3e-5
+    assert np.abs(cv["y_window"] - x[..., 4:]).max() > 1e-3                  # the network does change the bilinear input
+
+
+def test_opencv_runs_the_released_superresolve_graph_live():
+    """Where the reference tree and cv2 are present: re-run OpenCV on the released graph and compare with the stored file."""
+    pb = "/root/reference/models-release/supres-40k-swir/superresolve_graph.pb"
+    cv2 = pytest.importorskip("cv2")
+    if not os.path.exists(pb):
+        pytest.skip("reference not mounted")
+    mk = _mk_cv()
+    cv = golden("superresolve_cv.npz")
+    y = mk.run_opencv(pb, mk.window_input(int(cv["seed_window"])))
+    assert np.abs(y - cv["y_window"]).max() < 1e-5
+
+
 def test_model_structural_invariants(predict_weights):
     m = PredictRef(predict_weights)
     x = P.synth_model_input(2, 44, 1)
