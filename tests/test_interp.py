@@ -83,3 +83,23 @@ def test_gpu_median_fill_in_place_and_idempotent(sess):
     assert np.array_equal(b, c)                              # nothing left to fill
     with pytest.raises(ValueError):
         sess.median_fill(a.astype(np.float64))
+
+
+def test_bilinear_x2_oracle_interior_matches_opencv_and_pillow():
+    """scikit-image is absent (P3 unpinned against skimage itself); two third-party bilinear resizers with the same
+    pixel-centre alignment are here.  Away from the one-pixel border (where skimage's mode='reflect' mirrors and OpenCV /
+    Pillow replicate the edge) the x2 upsampling of the oracle equals both to float32 rounding."""
+    import cv2
+    from PIL import Image
+    from oracle import upsample_ref as U
+    r = np.random.default_rng(0)
+    for (h, w) in ((37, 41), (64, 30)):
+        a = r.uniform(0, 1, (h, w)).astype(np.float32)
+        want = U.resize_bilinear(a, (2 * h, 2 * w))
+        got_cv = cv2.resize(a, (2 * w, 2 * h), interpolation=cv2.INTER_LINEAR)
+        got_pil = np.array(Image.fromarray(a, mode="F").resize((2 * w, 2 * h), Image.BILINEAR))
+        assert np.abs(got_cv[1:-1, 1:-1] - want[1:-1, 1:-1]).max() < 5e-7
+        assert np.abs(got_pil[1:-1, 1:-1] - want[1:-1, 1:-1]).max() < 5e-7
+        # the border follows ndimage 'mirror' (d c b | a b c d): 0.75 * a[0] + 0.25 * a[1] per axis, not the replicated edge
+        row = 0.75 * a[0] + 0.25 * a[1]
+        assert abs(want[0, 0] - (0.75 * row[0] + 0.25 * row[1])) < 1e-6
