@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on " + s)
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"]    # arch also at link time: no default-arch stub
     subprocess.check_call(cmd)
     return LIB
 
