@@ -447,6 +447,17 @@ int stc_geotiff_encode_u8(const uint8_t* img, int rows, int cols, double west, d
                           uint8_t** out_buf, int64_t* out_len);
 void stc_geotiff_free(uint8_t* buf);
 
+/* ---- reading a tile product back: load_tif (src/resegment_tiles_wide.py:713-751, `rasterio.open(tif).read(1)` of a _FINAL /
+ * _POST / _SMOOTH* product before the border pass) ----
+ * Classic TIFF (either byte order), 8 bits per sample, strips or tiles, chunky or planar samples, compression none / LZW /
+ * PackBits, predictor 1 or 2: what this library, GDAL (compress='lzw'), libtiff and OpenCV write for a uint8 raster.
+ * band: 1-based like rasterio.  *out_img: malloc'ed row-major [rows][cols] (release with stc_geotiff_free).  bounds4 (may be
+ * NULL): west, south, east, north from ModelPixelScale + ModelTiepoint, NaN when the file carries none.  Host-only.
+ * STC_ERR_ARG: null / band out of range; STC_ERR_STATE: unreadable, unsupported (BigTIFF, Deflate, ZSTD, other sample widths)
+ * or corrupt file; STC_ERR_NOMEM. */
+int stc_read_geotiff_u8(const char* path, int band, uint8_t** out_img, int* rows, int* cols, double* bounds4);
+int stc_geotiff_decode_u8(const uint8_t* file, int64_t len, int band, uint8_t** out_img, int* rows, int* cols, double* bounds4);
+
 #ifdef __cplusplus
 }
 #endif

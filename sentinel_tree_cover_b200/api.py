@@ -140,6 +140,8 @@ SYMBOLS = [
     ("stc_geotiff_encode_u8", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     ("stc_geotiff_free", None, [C.c_void_p]),
+    ("stc_read_geotiff_u8", C.c_int, [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("stc_geotiff_decode_u8", C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 ]
 
 
@@ -1049,6 +1051,23 @@ def write_tif(arr, point, x, y, out_folder, suffix="_FINAL"):
     if rc:
         raise RuntimeError("write_tif: %s (%d)" % ({-2: "bad argument", -3: "cannot write " + file, -4: "out of memory"}.get(rc, "error"), rc))
     return file
+
+
+def read_tif(path, band=1, return_bounds=False):
+    """`rasterio.open(path).read(band)` for the uint8 tile products (src/resegment_tiles_wide.py:750): [rows, cols] uint8 through
+    the TIFF reader of libstc (strips / tiles, none / LZW / PackBits, predictor 1 / 2) -- no rasterio / GDAL.  With
+    `return_bounds` also [west, south, east, north] from the GeoTIFF tags (NaN when absent)."""
+    lib = load_library()
+    buf, rows, cols = C.c_void_p(), C.c_int(), C.c_int()
+    bounds = (C.c_double * 4)()
+    rc = lib.stc_read_geotiff_u8(os.fsencode(path), int(band), C.byref(buf), C.byref(rows), C.byref(cols), bounds)
+    if rc:
+        raise RuntimeError("read_tif: %s (%d): %s" % ({-2: "bad argument", -3: "unreadable, unsupported or corrupt TIFF", -4: "out of memory"}.get(rc, "error"), rc, path))
+    try:
+        img = np.frombuffer(C.string_at(buf, rows.value * cols.value), np.uint8).reshape(rows.value, cols.value).copy()
+    finally:
+        lib.stc_geotiff_free(buf)
+    return (img, [float(b) for b in bounds]) if return_bounds else img
 
 
 def geotiff_bytes(arr, point):

@@ -17,7 +17,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <string>
 #include <thread>
 #include <vector>
@@ -256,4 +258,222 @@ extern "C" int stc_write_geotiff_u8(const char* path, const uint8_t* img, int ro
   free(buf);
   if (!ok || !closed || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return STC_ERR_STATE; }
   return STC_OK;
+}
+
+// ---- reader: the tile products the border pass loads back (`load_tif`, /root/reference/src/resegment_tiles_wide.py:713-751:
+// `rasterio.open(tif).read(1)` of a `_FINAL` / `_POST` / `_SMOOTH*` product) ------------------------------------------------------
+// Classic TIFF (little- or big-endian), 8 bits per sample, strips or tiles, chunky or planar samples, compression none /
+// LZW (TIFF variant, as above) / PackBits, predictor 1 or 2 (horizontal differencing).  That covers what this library, GDAL
+// (`compress='lzw'`, striped or TILED=YES), libtiff (Pillow) and OpenCV write for a uint8 raster.  BigTIFF, Deflate / ZSTD and
+// other sample widths are refused with STC_ERR_STATE (no silent garbage).
+namespace {
+
+struct ByteView {
+  const uint8_t* p; size_t n; bool be;
+  bool ok(uint64_t off, uint64_t len) const { return off <= n && len <= n - off; }
+  uint16_t u16(uint64_t o) const { return be ? uint16_t(p[o] << 8 | p[o + 1]) : uint16_t(p[o] | p[o + 1] << 8); }
+  uint32_t u32(uint64_t o) const {
+    return be ? (uint32_t(p[o]) << 24 | uint32_t(p[o + 1]) << 16 | uint32_t(p[o + 2]) << 8 | p[o + 3])
+              : (uint32_t(p[o]) | uint32_t(p[o + 1]) << 8 | uint32_t(p[o + 2]) << 16 | uint32_t(p[o + 3]) << 24);
+  }
+  double f64(uint64_t o) const {
+    uint8_t b[8];
+    for (int i = 0; i < 8; ++i) b[i] = be ? p[o + 7 - i] : p[o + i];
+    double d; memcpy(&d, b, 8); return d;
+  }
+};
+
+struct TiffTag { uint16_t type = 0; uint32_t count = 0; uint64_t at = 0; bool present = false; };   // `at`: file offset of the values
+
+inline int type_size(uint16_t t) { return (t == 1 || t == 2 || t == 6 || t == 7) ? 1 : (t == 3 || t == 8) ? 2 : (t == 4 || t == 9 || t == 11) ? 4 : (t == 5 || t == 10 || t == 12) ? 8 : 0; }
+
+// value i of an integer-typed tag (BYTE / SHORT / LONG)
+inline bool tag_uint(const ByteView& v, const TiffTag& t, uint32_t i, uint32_t& out) {
+  if (!t.present || i >= t.count) return false;
+  if (t.type == 3) out = v.u16(t.at + 2ull * i);
+  else if (t.type == 4) out = v.u32(t.at + 4ull * i);
+  else if (t.type == 1) out = v.p[t.at + i];
+  else return false;
+  return true;
+}
+
+// TIFF LZW decode of one strip / tile into exactly `want` bytes (fewer decoded bytes -> the rest stays 0, like libtiff pads a
+// short strip; more -> error).  Returns false on a corrupt stream.
+bool lzw_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t want) {
+  constexpr int CLEAR = 256, EOI = 257, FIRST = 258;
+  static thread_local uint16_t prefix[4096];
+  static thread_local uint8_t suffix[4096], first[4096];
+  static thread_local uint16_t length[4096];
+  for (int i = 0; i < 256; ++i) { prefix[i] = 0xffff; suffix[i] = uint8_t(i); first[i] = uint8_t(i); length[i] = 1; }
+  uint64_t acc = 0; int nbits = 0; size_t ip = 0;
+  int width = 9, next = FIRST, old = -1;
+  size_t op = 0;
+  for (;;) {
+    while (nbits < width) {
+      if (ip >= n) return true;                      // stream ended without EOI: accept what was decoded (libtiff does)
+      acc = (acc << 8) | src[ip++]; nbits += 8;
+    }
+    const int code = int((acc >> (nbits - width)) & ((1u << width) - 1));
+    nbits -= width;
+    if (code == EOI) return true;
+    if (code == CLEAR) { width = 9; next = FIRST; old = -1; continue; }
+    int emit = code;
+    if (old < 0) {
+      if (code >= 256) return false;                 // the first code after a Clear must be a literal
+    } else {
+      if (code > next || (code == next && next >= 4096)) return false;
+      if (next < 4096) {       // (a full table without a Clear: keep decoding with what is there, as libtiff does)
+        // new entry = string(old) + first byte of string(code), where string(next) (the KwKwK case) starts like string(old)
+        prefix[next] = uint16_t(old); length[next] = uint16_t(length[old] + 1); first[next] = first[old];
+        suffix[next] = (code == next) ? first[old] : first[code];
+        ++next;
+        if (next + 1 == (1 << width) && width < 12) ++width;    // early change: the width steps one code before it must
+      }
+    }
+    const size_t len = length[emit];
+    if (op + len > want) return false;
+    uint8_t* q = dst + op + len;
+    for (int c = emit; c != 0xffff; c = prefix[c]) *--q = suffix[c];
+    op += len;
+    old = code;
+  }
+}
+
+bool packbits_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t want) {
+  size_t ip = 0, op = 0;
+  while (ip < n && op < want) {
+    const int8_t h = int8_t(src[ip++]);
+    if (h >= 0) {
+      const size_t len = size_t(h) + 1;
+      if (ip + len > n || op + len > want) return false;
+      memcpy(dst + op, src + ip, len); ip += len; op += len;
+    } else if (h != -128) {
+      const size_t len = size_t(1 - int(h));
+      if (ip >= n || op + len > want) return false;
+      memset(dst + op, src[ip++], len); op += len;
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+// STC_OK; STC_ERR_ARG: null arguments / band out of range; STC_ERR_STATE: not a TIFF this reader supports, or a corrupt one;
+// STC_ERR_NOMEM.  *out_img: malloc'ed [rows][cols] uint8 of sample `band` (1-based, rasterio's read(band)); release with
+// stc_geotiff_free.  bounds4 (optional): west, south, east, north from ModelPixelScale + ModelTiepoint, NaN when absent.
+extern "C" int stc_geotiff_decode_u8(const uint8_t* file, int64_t len, int band, uint8_t** out_img, int* rows, int* cols, double* bounds4) {
+  if (!file || !out_img || !rows || !cols || len < 8 || band < 1) return STC_ERR_ARG;
+  ByteView v{file, size_t(len), false};
+  if (file[0] == 'I' && file[1] == 'I') v.be = false;
+  else if (file[0] == 'M' && file[1] == 'M') v.be = true;
+  else return STC_ERR_STATE;
+  if (v.u16(2) != 42) return STC_ERR_STATE;                        // 43 = BigTIFF: not supported
+  const uint64_t ifd = v.u32(4);
+  if (!v.ok(ifd, 2)) return STC_ERR_STATE;
+  const uint32_t n_entries = v.u16(ifd);
+  if (!v.ok(ifd + 2, 12ull * n_entries)) return STC_ERR_STATE;
+  TiffTag width, height, bps, comp, strip_off, spp, rps, strip_cnt, planar, pred, tile_w, tile_h, tile_off, tile_cnt, scale, tie;
+  for (uint32_t e = 0; e < n_entries; ++e) {
+    const uint64_t at = ifd + 2 + 12ull * e;
+    const uint16_t tag = v.u16(at);
+    TiffTag t; t.type = v.u16(at + 2); t.count = v.u32(at + 4); t.present = true;
+    const uint64_t bytes = uint64_t(type_size(t.type)) * t.count;
+    if (bytes == 0) continue;
+    t.at = bytes <= 4 ? at + 8 : v.u32(at + 8);
+    if (!v.ok(t.at, bytes)) return STC_ERR_STATE;
+    switch (tag) {
+      case 256: width = t; break;      case 257: height = t; break;     case 258: bps = t; break;       case 259: comp = t; break;
+      case 273: strip_off = t; break;  case 277: spp = t; break;        case 278: rps = t; break;       case 279: strip_cnt = t; break;
+      case 284: planar = t; break;     case 317: pred = t; break;       case 322: tile_w = t; break;    case 323: tile_h = t; break;
+      case 324: tile_off = t; break;   case 325: tile_cnt = t; break;   case 33550: scale = t; break;   case 33922: tie = t; break;
+      default: break;
+    }
+  }
+  uint32_t W = 0, H = 0, bits = 1, compression = 1, samples = 1, planar_cfg = 1, predictor = 1;
+  if (!tag_uint(v, width, 0, W) || !tag_uint(v, height, 0, H) || W < 1 || H < 1) return STC_ERR_STATE;
+  tag_uint(v, spp, 0, samples); tag_uint(v, comp, 0, compression); tag_uint(v, planar, 0, planar_cfg); tag_uint(v, pred, 0, predictor);
+  if (samples < 1 || uint32_t(band) > samples) return STC_ERR_ARG;
+  for (uint32_t i = 0; i < (bps.present ? bps.count : 0); ++i) { tag_uint(v, bps, i, bits); if (bits != 8) return STC_ERR_STATE; }
+  if (!bps.present) return STC_ERR_STATE;                           // default is 1 bit per sample
+  if (compression != 1 && compression != 5 && compression != 32773) return STC_ERR_STATE;
+  if (predictor != 1 && predictor != 2) return STC_ERR_STATE;
+  if (uint64_t(W) * H > (uint64_t(1) << 31)) return STC_ERR_STATE;
+  const bool tiled = tile_off.present;
+  uint32_t bw = W, bh = H;                                          // block (strip or tile) size in pixels
+  if (tiled) { if (!tag_uint(v, tile_w, 0, bw) || !tag_uint(v, tile_h, 0, bh) || bw < 1 || bh < 1) return STC_ERR_STATE; }
+  else { uint32_t r = H; if (tag_uint(v, rps, 0, r) && r >= 1 && r < H) bh = r; }
+  const TiffTag& offs = tiled ? tile_off : strip_off;
+  const TiffTag& cnts = tiled ? tile_cnt : strip_cnt;
+  if (!offs.present) return STC_ERR_STATE;
+  const uint32_t across = (W + bw - 1) / bw, down = (H + bh - 1) / bh;
+  const uint32_t per_plane = across * down;
+  const uint32_t chunky = planar_cfg == 2 ? 1 : samples;            // samples interleaved inside a block
+  const uint32_t plane = planar_cfg == 2 ? uint32_t(band - 1) : 0;
+  if (uint64_t(per_plane) * (planar_cfg == 2 ? samples : 1) > offs.count) return STC_ERR_STATE;
+  uint8_t* img = static_cast<uint8_t*>(malloc(size_t(W) * H));
+  if (!img) return STC_ERR_NOMEM;
+  try {
+    std::vector<uint8_t> block;
+    for (uint32_t by = 0; by < down; ++by) {
+      for (uint32_t bx = 0; bx < across; ++bx) {
+        const uint32_t idx = plane * per_plane + by * across + bx;
+        uint32_t off = 0, cnt = 0;
+        tag_uint(v, offs, idx, off);
+        const uint32_t rows_here = tiled ? bh : std::min(bh, H - by * bh);     // tiles are always full size, the last strip is not
+        const size_t want = size_t(rows_here) * bw * chunky;
+        if (!tag_uint(v, cnts, idx, cnt)) cnt = (compression == 1) ? uint32_t(want) : uint32_t(v.n - std::min<size_t>(v.n, off));
+        if (!v.ok(off, cnt)) { free(img); return STC_ERR_STATE; }
+        block.assign(want, 0);
+        bool good = true;
+        if (compression == 1) { if (cnt < want) good = false; else memcpy(block.data(), file + off, want); }
+        else if (compression == 5) good = lzw_decode(file + off, cnt, block.data(), want);
+        else good = packbits_decode(file + off, cnt, block.data(), want);
+        if (!good) { free(img); return STC_ERR_STATE; }
+        if (predictor == 2)
+          for (uint32_t r = 0; r < rows_here; ++r) {
+            uint8_t* row = block.data() + size_t(r) * bw * chunky;
+            for (size_t i = chunky; i < size_t(bw) * chunky; ++i) row[i] = uint8_t(row[i] + row[i - chunky]);
+          }
+        const uint32_t x0 = bx * bw, y0 = by * bh;
+        const uint32_t cols_here = std::min(bw, W - x0), rows_copy = std::min(rows_here, H - y0);
+        const uint32_t s = planar_cfg == 2 ? 0 : uint32_t(band - 1);
+        for (uint32_t r = 0; r < rows_copy; ++r) {
+          const uint8_t* src = block.data() + size_t(r) * bw * chunky + s;
+          uint8_t* dst = img + size_t(y0 + r) * W + x0;
+          if (chunky == 1) memcpy(dst, src, cols_here);
+          else for (uint32_t c = 0; c < cols_here; ++c) dst[c] = src[size_t(c) * chunky];
+        }
+      }
+    }
+  } catch (...) { free(img); return STC_ERR_NOMEM; }
+  if (bounds4) {
+    const double nan = std::nan("");
+    bounds4[0] = bounds4[1] = bounds4[2] = bounds4[3] = nan;
+    if (scale.present && scale.type == 12 && scale.count >= 2 && tie.present && tie.type == 12 && tie.count >= 6) {
+      const double sx = v.f64(scale.at), sy = v.f64(scale.at + 8);
+      const double px = v.f64(tie.at), py = v.f64(tie.at + 8), gx = v.f64(tie.at + 24), gy = v.f64(tie.at + 32);
+      bounds4[0] = gx - px * sx;               // west
+      bounds4[3] = gy + py * sy;               // north
+      bounds4[2] = bounds4[0] + sx * W;        // east
+      bounds4[1] = bounds4[3] - sy * H;        // south
+    }
+  }
+  *out_img = img; *rows = int(H); *cols = int(W);
+  return STC_OK;
+}
+
+extern "C" int stc_read_geotiff_u8(const char* path, int band, uint8_t** out_img, int* rows, int* cols, double* bounds4) {
+  if (!path) return STC_ERR_ARG;
+  FILE* fp = fopen(path, "rb");
+  if (!fp) return STC_ERR_STATE;
+  std::vector<uint8_t> buf;
+  try {
+    if (fseek(fp, 0, SEEK_END) != 0) { fclose(fp); return STC_ERR_STATE; }
+    const long sz = ftell(fp);
+    if (sz < 8 || fseek(fp, 0, SEEK_SET) != 0) { fclose(fp); return STC_ERR_STATE; }
+    buf.resize(size_t(sz));
+    if (fread(buf.data(), 1, size_t(sz), fp) != size_t(sz)) { fclose(fp); return STC_ERR_STATE; }
+  } catch (...) { fclose(fp); return STC_ERR_NOMEM; }
+  fclose(fp);
+  return stc_geotiff_decode_u8(buf.data(), int64_t(buf.size()), band, out_img, rows, cols, bounds4);
 }

@@ -518,3 +518,38 @@ def write_smoothed_pair(predictions_left, predictions_right, bbx, neighb_bbx, x,
         redo = os.path.exists(stem + "_SMOOTH_XY.tif") or os.path.exists(stem + "_SMOOTH_Y.tif")
         files.append(_api.write_tif(preds, box, tx, y, folder, "_SMOOTH_XY" if redo else "_SMOOTH_X"))
     return files
+
+
+def load_tif(tile_id, local_path):
+    """:713-751, same arguments and return value `(raster, is_smooth_y)`: the tile's current tree-cover product, picked in the
+    reference's order of preference -- a `_SMOOTH_XY` product, else `_SMOOTH_X`, else `_SMOOTH_Y` (any `_SMOOTH*`: is_smooth_y
+    = 1 for XY / Y), else `_FINAL`, else `_POST` -- and read as band 1, uint8 [rows, cols], by libstc's TIFF reader
+    (api.read_tif; the reference uses rasterio).  Raises IndexError like the reference when the folder holds no product."""
+    dir_i = f"{local_path}/{tile_id[0]}/{tile_id[1]}/"
+    chosen, is_smooth_y = [], 0
+    if os.path.exists(dir_i):
+        files = [f for f in os.listdir(dir_i) if os.path.splitext(f)[-1] == '.tif']
+        by_kind = {k: [f for f in files if k in f] for k in ("_SMOOTH_XY", "_SMOOTH_X", "_SMOOTH_Y", "_SMOOTH", "_FINAL", "_POST")}
+        if by_kind["_SMOOTH"]:
+            # ("_SMOOTH_X" is a substring of "_SMOOTH_XY": the XY test comes first, as in the reference)
+            for kind, flag in (("_SMOOTH_XY", 1), ("_SMOOTH_X", 0), ("_SMOOTH_Y", 1)):
+                if by_kind[kind]:
+                    chosen, is_smooth_y = by_kind[kind], flag
+                    break
+            else:
+                chosen = files                              # a `_SMOOTH` name of no known kind: the reference keeps every .tif
+        elif by_kind["_FINAL"]:
+            chosen = by_kind["_FINAL"]
+        else:
+            chosen = by_kind["_POST"]
+    return _api.read_tif(os.path.join(dir_i, chosen[0])), is_smooth_y
+
+
+def concatenate_s2_files(s2, s2_neighb):
+    """:754-763: centre-crop the wider of the two tiles' cubes along axis 2 so that both have the neighbour's / tile's width."""
+    s2_diff = s2.shape[2] - s2_neighb.shape[2]
+    if s2_diff > 0:
+        s2 = s2[:, :, s2_diff // 2: -(s2_diff // 2), :]
+    if s2_diff < 0:
+        s2_neighb = s2_neighb[:, :, - (s2_diff // 2): (s2_diff // 2)]
+    return s2, s2_neighb

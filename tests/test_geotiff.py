@@ -84,3 +84,125 @@ def test_geotiff_header_is_classic_little_endian_tiff_and_errors_are_reported(tm
     assert lib.stc_write_geotiff_u8(os.fsencode(str(tmp_path / "no_such_dir" / "a.tif")), p, 3, 4, 0.0, 0.0, 1.0, 1.0) == -3
     with pytest.raises(RuntimeError):
         api.write_tif(img, [0, 0, 1, 1], 1, 2, str(tmp_path / "no_such_dir") + "/")
+
+
+# ---- the reader (api.read_tif = rasterio.open(f).read(1) of a tile product, src/resegment_tiles_wide.py:750) ----------------
+
+@pytest.mark.parametrize("name,img", list(_cases()), ids=[c[0] for c in _cases()])
+def test_read_tif_round_trips_own_writer(name, img, tmp_path):
+    point = [10.25, -3.5, 10.25 + 0.061, -3.5 + 0.0607]
+    f = api.write_tif(img.T, point, 7, 8, str(tmp_path) + "/")
+    got, bounds = api.read_tif(f, return_bounds=True)
+    assert got.dtype == np.uint8 and np.array_equal(got, img)
+    assert np.allclose(bounds, point, rtol=0, atol=1e-12)
+
+
+def _third_party_files(tmp_path, img):
+    """The same raster written by libtiff through Pillow (LZW, PackBits, uncompressed, tiled LZW, LZW + horizontal predictor)
+    and by OpenCV (its default: LZW with the horizontal predictor)."""
+    out = []
+    im = Image.fromarray(img)
+    for name, kw in (("pil_lzw", dict(compression="tiff_lzw")), ("pil_raw", dict(compression=None)), ("pil_packbits", dict(compression="packbits")),
+                     ("pil_lzw_pred2", dict(compression="tiff_lzw", tiffinfo={317: 2})),
+                     ("pil_lzw_tiled", dict(compression="tiff_lzw", tiffinfo={322: 128, 323: 64}))):
+        f = os.path.join(str(tmp_path), name + ".tif")
+        try:
+            im.save(f, **{k: v for k, v in kw.items() if v is not None})
+        except Exception:
+            continue
+        out.append((name, f))
+    try:
+        import cv2
+        f = os.path.join(str(tmp_path), "cv_lzw.tif")
+        if cv2.imwrite(f, img):
+            out.append(("cv_lzw", f))
+    except ImportError:
+        pass
+    return out
+
+
+@pytest.mark.parametrize("name,img", [c for c in _cases() if c[0] in ("noise", "tree_cover", "nodata", "binary", "one_pixel")],
+                         ids=["noise", "tree_cover", "nodata", "one_pixel", "binary"])
+def test_read_tif_decodes_files_written_by_libtiff_and_opencv(name, img, tmp_path):
+    files = _third_party_files(tmp_path, img)
+    assert len(files) >= 3
+    seen = set()
+    for kind, f in files:
+        with Image.open(f) as im:
+            tags = dict(im.tag_v2)
+            want = np.array(im)
+        seen.add((tags.get(259), tags.get(317, 1), 322 in tags))
+        got, bounds = api.read_tif(f, return_bounds=True)
+        assert np.array_equal(got, want) and np.array_equal(got, img), (kind, tags.get(259), tags.get(317))
+        assert all(np.isnan(b) for b in bounds)                            # no GeoTIFF tags in these
+    assert any(c == 5 for c, _, _ in seen)                                     # at least one third-party LZW stream was decoded
+
+
+def test_read_tif_multiband_big_endian_and_refusals(tmp_path):
+    r = np.random.default_rng(5)
+    rgb = r.integers(0, 256, (50, 70, 3)).astype(np.uint8)
+    f = os.path.join(str(tmp_path), "rgb.tif")
+    Image.fromarray(rgb).save(f, compression="tiff_lzw")
+    for b in range(3):
+        assert np.array_equal(api.read_tif(f, band=b + 1), rgb[..., b])
+    with pytest.raises(RuntimeError):
+        api.read_tif(f, band=4)
+    # a hand-made big-endian, uncompressed, single-strip file
+    img = r.integers(0, 256, (5, 7)).astype(np.uint8)
+    ent = [(256, 3, 1, 7), (257, 3, 1, 5), (258, 3, 1, 8), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 1, 8), (277, 3, 1, 1), (278, 3, 1, 5), (279, 4, 1, 35)]
+    body = img.tobytes() + b"\0"
+    ifd = struct.pack(">H", len(ent)) + b"".join(struct.pack(">HHI", t, ty, c) + (struct.pack(">HH", v, 0) if ty == 3 else struct.pack(">I", v))
+                                                 for t, ty, c, v in ent) + struct.pack(">I", 0)
+    be = os.path.join(str(tmp_path), "be.tif")
+    open(be, "wb").write(b"MM" + struct.pack(">HI", 42, 8 + len(body)) + body + ifd)
+    assert np.array_equal(api.read_tif(be), img)
+    with Image.open(be) as im:
+        assert np.array_equal(np.array(im), img)                               # libtiff agrees that this is a valid file
+    # refusals: 16-bit samples, deflate, truncated file, not a TIFF
+    f16 = os.path.join(str(tmp_path), "u16.tif"); Image.fromarray(r.integers(0, 60000, (9, 9)).astype(np.uint16)).save(f16)
+    fz = os.path.join(str(tmp_path), "z.tif"); Image.fromarray(img).save(fz, compression="tiff_adobe_deflate")
+    ft = os.path.join(str(tmp_path), "trunc.tif"); open(ft, "wb").write(open(f, "rb").read()[:200])
+    fn = os.path.join(str(tmp_path), "no.tif"); open(fn, "wb").write(b"not a tiff at all")
+    for bad in (f16, fz, ft, fn, os.path.join(str(tmp_path), "missing.tif")):
+        with pytest.raises(RuntimeError):
+            api.read_tif(bad)
+
+
+def test_read_tif_tiled_layout(tmp_path):
+    """Pillow does not write tiles; GDAL does with TILED=YES.  A hand-made tiled file (16 x 16 tiles, image 40 x 50: partial
+    tiles on both edges), uncompressed and with LZW tiles from libstc's own encoder, checked against libtiff's reading."""
+    r = np.random.default_rng(8)
+    img = r.integers(0, 256, (40, 50)).astype(np.uint8)
+    th = tw = 16
+    down, across = -(-40 // th), -(-50 // tw)
+    tiles = []
+    for by in range(down):
+        for bx in range(across):
+            t = np.zeros((th, tw), np.uint8)
+            part = img[by * th:(by + 1) * th, bx * tw:(bx + 1) * tw]
+            t[:part.shape[0], :part.shape[1]] = part
+            tiles.append(t)
+    for compression in (1, 5):
+        blobs = []
+        for t in tiles:
+            if compression == 1:
+                blobs.append(t.tobytes())
+            else:                                         # one LZW stream per tile: a single-strip TIFF of the tile from the writer
+                enc = api.geotiff_bytes(t, [0, 0, 1, 1])
+                off, cnt = [struct.unpack_from("<I", enc, enc.index(struct.pack("<HHI", tag, 4, 1)) + 8)[0] for tag in (273, 279)]
+                blobs.append(enc[off:off + cnt])
+        body, offs = b"", []
+        for b in blobs:
+            offs.append(8 + len(body)); body += b + (b"\0" if len(b) & 1 else b"")
+        n = len(blobs)
+        off_arr, cnt_arr = 8 + len(body), 8 + len(body) + 4 * n
+        body += struct.pack("<%dI" % n, *offs) + struct.pack("<%dI" % n, *[len(b) for b in blobs])
+        ent = [(256, 3, 1, 50), (257, 3, 1, 40), (258, 3, 1, 8), (259, 3, 1, compression), (262, 3, 1, 1), (277, 3, 1, 1),
+               (322, 3, 1, tw), (323, 3, 1, th), (324, 4, n, off_arr), (325, 4, n, cnt_arr)]
+        ifd = struct.pack("<H", len(ent)) + b"".join(struct.pack("<HHI", t, ty, c) + (struct.pack("<HH", v, 0) if ty == 3 else struct.pack("<I", v))
+                                                     for t, ty, c, v in ent) + struct.pack("<I", 0)
+        f = os.path.join(str(tmp_path), "tiled_%d.tif" % compression)
+        open(f, "wb").write(b"II" + struct.pack("<HI", 42, 8 + len(body)) + body + ifd)
+        with Image.open(f) as im:
+            assert np.array_equal(np.array(im), img)                           # libtiff reads the hand-made file
+        assert np.array_equal(api.read_tif(f), img), compression

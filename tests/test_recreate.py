@@ -109,3 +109,54 @@ def test_seam_smooth_diff_and_write_out(tmp_path):
     from PIL import Image
     im = np.array(Image.open(files[0]))
     assert np.array_equal(im, left.T.astype(np.uint8))
+
+
+def test_load_tif_picks_the_product_like_the_reference(tmp_path):
+    """:713-751: _SMOOTH_XY > _SMOOTH_X > _SMOOTH_Y > _FINAL > _POST; band 1 read by libstc's TIFF reader; the file the border
+    pass itself wrote (write_smoothed_pair) comes back pixel for pixel."""
+    from sentinel_tree_cover_b200 import api, resegment as R
+    r = np.random.default_rng(2)
+    root = str(tmp_path)
+    folder = os.path.join(root, "12", "34") + "/"
+    os.makedirs(folder)
+    box = [10.0, 5.0, 10.0 + 1 / 18, 5.0 + 1 / 18]
+    maps = {s: r.integers(0, 101, (60, 64)).astype(np.uint8) for s in ("_POST", "_FINAL", "_SMOOTH_Y", "_SMOOTH_X", "_SMOOTH_XY")}
+    expect_flag = {"_POST": 0, "_FINAL": 0, "_SMOOTH_Y": 1, "_SMOOTH_X": 0, "_SMOOTH_XY": 1}
+    with pytest.raises(IndexError):
+        R.load_tif(("12", "34"), root)
+    for s in ("_POST", "_FINAL", "_SMOOTH_Y", "_SMOOTH_X", "_SMOOTH_XY"):         # each new product outranks the ones before
+        api.write_tif(maps[s], box, "12", "34", folder, s)
+        got, flag = R.load_tif(("12", "34"), root)
+        assert np.array_equal(got, maps[s].T) and flag == expect_flag[s], s
+    a = np.zeros((3, 10, 30, 4)); b = np.zeros((3, 10, 24, 4))
+    x, y = R.concatenate_s2_files(a, b)
+    assert x.shape[2] == 24 and y.shape[2] == 24
+    x, y = R.concatenate_s2_files(b, a)
+    assert x.shape[2] == 24 and y.shape[2] == 24
+
+
+def test_load_tif_against_reference_function_with_a_stub_rasterio(tmp_path):
+    """Where the reference is mounted: its load_tif with `rasterio.open(f).read(1)` replaced by Pillow picks the same file."""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference not mounted")
+    from PIL import Image
+    from sentinel_tree_cover_b200 import api, resegment as R
+    m = refshim.ref("resegment_tiles_wide")
+
+    class _DS:
+        def __init__(self, f): self.f = f
+        def read(self, band): return np.array(Image.open(self.f))
+    m.rasterio.open = lambda f: _DS(f)
+    r = np.random.default_rng(3)
+    root = str(tmp_path)
+    box = [10.0, 5.0, 10.0 + 1 / 18, 5.0 + 1 / 18]
+    for case, names in enumerate((["_POST"], ["_POST", "_FINAL"], ["_FINAL", "_SMOOTH_Y"], ["_FINAL", "_SMOOTH_X", "_SMOOTH_Y"],
+                                  ["_FINAL", "_SMOOTH_X", "_SMOOTH_XY"])):
+        folder = os.path.join(root, str(case), "7") + "/"
+        os.makedirs(folder)
+        for s in names:
+            api.write_tif(r.integers(0, 101, (40, 44)).astype(np.uint8), box, case, 7, folder, s)
+        want, want_flag = m.load_tif((str(case), "7"), root)
+        got, flag = R.load_tif((str(case), "7"), root)
+        assert np.array_equal(got, want) and flag == want_flag, names
