@@ -53,46 +53,58 @@ def align_dates(tile_date, neighb_date):
     return rm_t, rm_n, int(min(len(t) - len(rm_t), len(nb) - len(rm_n)))
 
 
-def make_tiles_right_neighb(tiles_folder_x, tiles_folder_y, size, size_y):
+def make_tiles_right_neighb(tiles_folder_x, tiles_folder_y, size, size_y, edge="right"):
     """:267-281: window table of the border strip (one column of `size`-wide windows stepping down the seam).  Returns
     (tiles_array, tiles_folder) int arrays [n, 4] = (x, y, width, height) exactly as the reference builds them, including its
-    column-wise sort and the re-tiling of the y column."""
+    column-wise sort and the re-tiling of the y column.  edge="up": the table of the NORTH seam
+    (src/resegment_tiles_north_wide.py:253-266; `size_y` is that file's SIZE_X): windows stepping along x, SIZE + 14 tall."""
     fx, fy = np.asarray(tiles_folder_x), np.asarray(tiles_folder_y)
     pairs = np.stack([np.repeat(fx, len(fy)), np.tile(fy, len(fx))], 1)          # cartesian(tiles_folder_x, tiles_folder_y)
     folder = np.sort(np.hstack([pairs, np.full_like(pairs, size + 7)]), axis=0)  # np.sort(axis=0): every column on its own
     uy = np.unique(folder[:, 1])
     folder[:, 1] = np.tile(uy, len(folder) // len(uy))
     arr = folder.copy()
-    arr[1:, 1] -= 7
-    arr[:, 0] = 0
-    arr[:, 2] = size + 14
-    arr[:, 3] = size_y + 7
-    arr[1:-1, 3] += 7
+    step, fixed = (1, 0) if edge == "right" else (0, 1)        # which column steps along the seam, which is pinned to 0
+    arr[1:, step] -= 7
+    arr[:, fixed] = 0
+    arr[:, 2 + fixed] = size + 14
+    arr[:, 2 + step] = size_y + 7
+    arr[1:-1, 2 + step] += 7
     return arr, folder
 
 
-def check_if_artifact(tile, neighb):
+def check_if_artifact(tile, neighb, edge="right"):
     """:675-712 on the two uint8 tree-cover rasters (NaN where > 100): compares the last column of `tile` with the first column
-    of `neighb` in 10-row bins.  Returns 1 when the seam is visible.  (The reference prints a module-global x, y here.)"""
+    of `neighb` in 10-row bins.  Returns 1 when the seam is visible.  (The reference prints a module-global x, y here.)
+    edge="up": the north seam (src/resegment_tiles_north_wide.py:661-700): first row of `tile` against the last row of
+    `neighb`, both cut to the shorter one, and that file's thresholds."""
+    import warnings
+
     def bins(col):
         col = np.pad(np.asarray(col, np.float64), (10 - (col.shape[0] % 10)) // 2, constant_values=np.nan)
-        with np.errstate(all="ignore"):
-            import warnings
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore", RuntimeWarning)
-                return np.nanmean(np.reshape(col, (col.shape[0] // 10, 10)), axis=1)
-    import warnings
-    with warnings.catch_warnings():
+        return np.nanmean(np.reshape(col, (col.shape[0] // 10, 10)), axis=1)
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
         warnings.simplefilter("ignore", RuntimeWarning)
-        right_mean, left_mean = np.nanmean(neighb[:, :3]), np.nanmean(tile[:, -3:])
-        right, left = bins(neighb[:, 0]), bins(tile[:, -1])
+        if edge == "right":
+            right_mean, left_mean = np.nanmean(neighb[:, :3]), np.nanmean(tile[:, -3:])
+            right, left = bins(neighb[:, 0]), bins(tile[:, -1])
+            t_all, t_half, t_end, jump_a, jump_bc, f_half, f_all = 20, 12.5, 17.5, 6, 1, 0.5, 0.3
+        else:
+            right_mean, left_mean = np.nanmean(neighb[-3:]), np.nanmean(tile[:3])
+            right, left = neighb[-1], tile[0]
+            right = right[:left.shape[0]]
+            left = left[:right.shape[0]]
+            right, left = bins(right), bins(left)
+            t_all, t_half, t_end, jump_a, jump_bc, f_half, f_all = 25, 15, 15, 7, 0, 0.6, 0.25
         d = np.abs(right - left)
-        frac20, frac125 = np.nanmean(d > 20), np.nanmean(d > 12.5)
-        frac_l, frac_r = np.nanmean(d[:15] > 17.5), np.nanmean(d[-15:] > 17.5)
+        frac_all, frac_half = np.nanmean(d > t_all), np.nanmean(d > t_half)
+        frac_l, frac_r = np.nanmean(d[:15] > t_end), np.nanmean(d[-15:] > t_end)
     jump = abs(right_mean - left_mean)
-    a = jump > 6
-    b = (frac125 > 0.5) and (jump > 1)
-    c = ((frac20 > 0.3) or (frac_l > 0.5) or (frac_r > 0.5)) and (jump > 1)
+    a = jump > jump_a
+    b = (frac_half > f_half) and (jump > jump_bc)
+    c = (frac_all > f_all) or (frac_l > 0.5) or (frac_r > 0.5)
+    if edge == "right":
+        c = c and (jump > jump_bc)
     return 1 if (a or b or c) else 0
 
 
@@ -325,12 +337,13 @@ _RAMP_PLAN = {"r": (False, "up", "down", True, None),
               "d": (False, "right", "left", True, "T-flip")}
 
 
-def mosaic_subtiles(preds, mults, na, kind, left, right, up, down, size=670, resize=None):
+def mosaic_subtiles(preds, mults, na, kind, left, right, up, down, size=670, resize=None, feather_power=1.33):
     """:1169-1237, same arguments (+ `size` = the reference's global SIZE, `resize` = the bilinear resize to use, default
     `resize_linear`).  preds / mults [X, Y, n] float32 layers (NaN / 0 where a layer has no data; both are modified in place
     like the reference does), na [X, Y, 1].  Returns (weighted mean of the layers [X, Y], blending weight of this kind [X, Y]):
     a Gaussian for the normal subtiles, for a border kind a ramp (x / half) ** 1.2 rising towards the shared edge over
-    `size // 2` pixels, feathered by (t / 300) ** 1.33 over 300 pixels at the ends where another border strip exists."""
+    `size // 2` pixels, feathered by (t / 300) ** 1.33 over 300 pixels at the ends where another border strip exists
+    (`feather_power` = 1.5 in the north-seam file, src/resegment_tiles_north_wide.py:1155, otherwise identical)."""
     resize = resize or resize_linear
     preds[np.tile(na, (1, 1, preds.shape[-1])) > 0] = np.nan
     mults[np.isnan(preds)] = 0.
@@ -344,7 +357,7 @@ def mosaic_subtiles(preds, mults, na, kind, left, right, up, down, size=670, res
     else:
         flip, flag_lo, flag_hi, zeros_first, post = _RAMP_PLAN[kind]
         present = {"left": left is not None, "right": right is not None, "up": up is not None, "down": down is not None}
-        feather = np.tile((np.arange(0, 300, 1) / 300) ** 1.33, (half, 1))
+        feather = np.tile((np.arange(0, 300, 1) / 300) ** feather_power, (half, 1))
         m = (np.ones((half, Y)) * (np.arange(0, half, 1) / half)[:, np.newaxis]) ** 1.2
         if flip:
             m = np.flipud(m)
@@ -400,8 +413,10 @@ def _list_subtile_files(out_folder):
     return found, n_files
 
 
-def recreate_resegmented_tifs(out_folder, shape, size=670, resize=None):
+def recreate_resegmented_tifs(out_folder, shape, size=670, resize=None, edge="right"):
     """:1240-1547, same arguments (+ `size` = the reference's global SIZE, + `resize`) and return value `(preds, sums)`.
+    edge="up": the north-seam file's version (src/resegment_tiles_north_wide.py: the same function, its mosaic_subtiles
+    feathers with exponent 1.5 instead of 1.33).
     Reads `<out_folder>/<x>/<y>.npy` (normal subtiles), `<x>/left<y>.npy`, `<x>/up<y>.npy`, `<x>/down<y>.npy` and
     `right<x>/<y>.npy` (border strips written by the border pass of this tile and of its neighbours; a strip file holds the
     window across the seam, of which this tile owns one half), builds one layer stack per kind, takes the weighted mean inside
@@ -474,7 +489,8 @@ def recreate_resegmented_tifs(out_folder, shape, size=670, resize=None):
     for kind in "nrlud":
         if kind in stacks:
             P, M = stacks[kind]
-            pk, mk = mosaic_subtiles(P, M, na, kind, layers["l"], layers["r"], layers["u"], layers["d"], size=size, resize=resize)
+            pk, mk = mosaic_subtiles(P, M, na, kind, layers["l"], layers["r"], layers["u"], layers["d"], size=size, resize=resize,
+                                     feather_power=1.33 if edge == "right" else 1.5)
             if kind != "n":
                 mk[np.sum(~np.isnan(P), axis=-1) == 0] = 0.
             out[kind] = (pk, mk)
@@ -520,11 +536,13 @@ def write_smoothed_pair(predictions_left, predictions_right, bbx, neighb_bbx, x,
     return files
 
 
-def load_tif(tile_id, local_path):
+def load_tif(tile_id, local_path, edge="right"):
     """:713-751, same arguments and return value `(raster, is_smooth_y)`: the tile's current tree-cover product, picked in the
     reference's order of preference -- a `_SMOOTH_XY` product, else `_SMOOTH_X`, else `_SMOOTH_Y` (any `_SMOOTH*`: is_smooth_y
     = 1 for XY / Y), else `_FINAL`, else `_POST` -- and read as band 1, uint8 [rows, cols], by libstc's TIFF reader
-    (api.read_tif; the reference uses rasterio).  Raises IndexError like the reference when the folder holds no product."""
+    (api.read_tif; the reference uses rasterio).  Raises IndexError like the reference when the folder holds no product.
+    edge="up" (src/resegment_tiles_north_wide.py:703-742): same choice, but the flag says whether ANY file with "SMOOTH" in
+    its name exists in the folder."""
     dir_i = f"{local_path}/{tile_id[0]}/{tile_id[1]}/"
     chosen, is_smooth_y = [], 0
     if os.path.exists(dir_i):
@@ -542,6 +560,8 @@ def load_tif(tile_id, local_path):
             chosen = by_kind["_FINAL"]
         else:
             chosen = by_kind["_POST"]
+    if edge != "right":
+        is_smooth_y = 1 if (os.path.exists(dir_i) and any("SMOOTH" in f for f in os.listdir(dir_i))) else 0
     return _api.read_tif(os.path.join(dir_i, chosen[0])), is_smooth_y
 
 
