@@ -108,13 +108,15 @@ def check_if_artifact(tile, neighb, edge="right"):
     return 1 if (a or b or c) else 0
 
 
-def preprocess_tile(arr, dates, interp, clm, fname, dem, bbx, sess, forest_mask=None, urban_mask=None):
+def preprocess_tile(arr, dates, interp, clm, fname, dem, bbx, sess, forest_mask=None, urban_mask=None, edge="right"):
     """:619-672, same arguments (+ sess): returns (arr, interp, dates).  `interp` in and `fname` are unused by the reference
-    too.  Python's global `random` state is consumed by the cloud removal exactly as in the reference."""
+    too.  Python's global `random` state is consumed by the cloud removal exactly as in the reference.
+    edge="up": the north-seam file's version (src/resegment_tiles_north_wide.py:573-625): a date is dropped when a FIFTH of its
+    pixels is missing (a twentieth here), and the Sen2Cor mask loses its false-positive pixels only when a date was dropped."""
     del interp, fname
     arr = np.ascontiguousarray(arr, np.float32)
     dates = np.asarray(dates)
-    missing = _api.id_missing_px(arr, 20, sess)
+    missing = _api.id_missing_px(arr, 20 if edge == "right" else 5, sess)
     if len(missing) > 0:
         dates = np.delete(dates, missing)
         arr = np.delete(arr, missing, 0)
@@ -123,7 +125,8 @@ def preprocess_tile(arr, dates, interp, clm, fname, dem, bbx, sess, forest_mask=
         if len(missing) > 0:
             clm = np.delete(clm, missing, 0)
         if np.asarray(clm).shape == np.asarray(fcps).shape == np.asarray(cld).shape:       # the reference's try/except guards this
-            clm[fcps] = 0.
+            if edge == "right" or len(missing) > 0:
+                clm[fcps] = 0.
             cld = np.maximum(clm, cld)
     interp = _api.id_areas_to_interp(arr, cld, cld, dates, fcps, sess)
     to_remove = np.argwhere(np.mean(interp == 1, axis=(1, 2)) > 0.95)

@@ -2,7 +2,8 @@
 against outputs of /root/reference/src/resegment_tiles_north_wide.py (tools/make_golden_north.py through oracle/refshim.py):
 the window table, the seam-artifact test with that file's thresholds, the re-mosaic with its feather exponent, load_tif's
 flag.  The north file's array functions (regularize_and_smooth, align_dates, recreate_resegmented_tifs, adjust_*) are
-line-identical to the east file's; its preprocess_tile / process_subtiles differ in thresholds and are not mirrored."""
+line-identical to the east file's; its preprocess_tile is `edge="up"` too (host logic checked below against both files'
+functions with the oracle standing in for the GPU calls); its process_subtiles differs in its rules and is not mirrored."""
 import importlib.util
 import os
 import numpy as np
@@ -81,3 +82,45 @@ def test_north_functions_against_live_reference(tmp_path):
         want_p, want_s = m.recreate_resegmented_tifs(folder, case[2])
     got_p, got_s = R.recreate_resegmented_tifs(folder, case[2], size=case[1], edge="up")
     assert np.array_equal(got_p, want_p) and np.array_equal(got_s, want_s, equal_nan=True)
+
+
+@pytest.mark.parametrize("edge", ["right", "up"])
+def test_preprocess_tile_host_logic_against_live_reference(edge, tmp_path, monkeypatch):
+    """The HOST logic of resegment.preprocess_tile (which dates are screened out, how the Sen2Cor mask is merged, the second
+    mask pass after a removal) with the four GPU calls replaced by the oracle's NumPy restatements -- so the comparison with
+    the reference function (east file :619-672, north file :573-625) isolates the glue and runs without a GPU: a date missing
+    11 % of its pixels (dropped by the east file's threshold H^2 / 20, kept by the north file's H^2 / 5), one missing 40 %
+    (dropped by both), a Sen2Cor mask,
+    an almost fully clouded date (> 95 % interpolated: removed, masks recomputed).  Bit-identical, incl. Python's generator."""
+    import contextlib, io, random
+    from oracle import refshim, cloud_ref, cloudfill_ref, upsample_ref
+    if not refshim.available():
+        pytest.skip("reference not mounted")
+    from sentinel_tree_cover_b200 import api, resegment as R
+    m = refshim.ref("resegment_tiles_wide" if edge == "right" else "resegment_tiles_north_wide")
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(api, "id_missing_px", lambda arr, thresh, sess: upsample_ref.id_missing_px(arr, thresh))
+    monkeypatch.setattr(api, "identify_clouds_shadows", lambda img, dem, bbx, sess, forest_mask=None, urban_mask=None:
+                        cloud_ref.identify_clouds_shadows(np.copy(img), np.copy(dem))[:2])
+    monkeypatch.setattr(api, "id_areas_to_interp", lambda tiles, probs, shadows, dates, pfcps, sess:
+                        cloudfill_ref.feather(np.clip(np.copy(probs).astype(np.float32), 0, 1), 15))
+    monkeypatch.setattr(api, "remove_cloud_and_shadows", lambda tiles, probs, shadows, dates, pfcps, s1, mosaic=None, sess=None:
+                        cloudfill_ref.remove_cloud_and_shadows(tiles, probs, pfcps)[:3])
+    T, H, W = 9, 64, 64
+    img, dem = cloud_ref.synth_cloudy_cube(T, H, W, 321)
+    img[3, :, :7, :10] = 0.0                               # 11 % of the pixels missing: >= H^2 / 20 (east drops it), < H^2 / 5 (north keeps it)
+    img[6, :26, :, :10] = 0.0                              # 40 %: dropped by both
+    img[1, :, :, :3] = 0.9; img[1, :, :, 3:10] = 0.8       # a date that is cloud everywhere
+    dts = (np.arange(T) * 36 + 10).astype(np.int64)
+    clm = np.zeros((T, H, W), np.float32); clm[2, 10:30, 20:50] = 1.; clm[4, 40:60, 5:25] = 1.
+    random.seed(5)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        want_arr, want_interp, want_dates = m.preprocess_tile(np.copy(img), np.copy(dts), None, np.copy(clm), "tile", np.copy(dem), None)
+    want_next = random.random()
+    random.seed(5)
+    with np.errstate(all="ignore"):
+        arr, interp, dates = R.preprocess_tile(np.copy(img), np.copy(dts), None, np.copy(clm), "tile", np.copy(dem), None, sess=None, edge=edge)
+    assert np.array_equal(dates, want_dates) and len(dates) < T
+    assert (dts[3] in dates) == (edge == "up") and dts[6] not in dates and dts[1] not in dates
+    assert np.array_equal(np.asarray(interp), np.asarray(want_interp)) and np.array_equal(np.asarray(arr), np.asarray(want_arr))
+    assert random.random() == want_next
