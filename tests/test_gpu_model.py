@@ -128,23 +128,6 @@ def test_superresolve_vs_graph_golden(sess, sr_weights):
     assert eq < 6e-4
 
 
-def test_superresolve_vs_opencv_execution_of_the_released_graph(sess):
-    """Against outputs of the released superresolve_graph.pb run by OpenCV's DNN module (tests/golden/superresolve_cv.npz,
-    tools/make_golden_cv.py): a third-party executor of the reference's own graph.  Same tolerance as the graph golden."""
-    import importlib.util
-    cv = golden("superresolve_cv.npz")
-    g = golden("superresolve.npz")
-    y = sess.superresolve(g["x"], g["x"][..., 4:])
-    assert np.abs(y - cv["y_small"]).max() < 2e-3
-    spec = importlib.util.spec_from_file_location("mk_cv", os.path.join(os.path.dirname(__file__), "..", "tools", "make_golden_cv.py"))
-    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
-    x = mk.window_input(int(cv["seed_window"]))
-    y = sess.superresolve(x, x[..., 4:])
-    err = np.abs(y - cv["y_window"]).max()
-    print("superresolve vs OpenCV, 118-px window", err)
-    assert err < 2e-3
-
-
 def test_superresolve_fused_epilogues_equal_separate_passes(sess, monkeypatch):
     """The convolutions of the super-resolution network write the next layer's fp16 activation (with its reflect border), the
     fp32 residual and the final tanh + bilinear sum from their accumulators; STC_SR_FUSE=0 keeps the round-1 route (fp32 raw
