@@ -126,3 +126,43 @@ print("OK")
     env = dict(os.environ, STC_PYRANDOM_ISA=isa, PYTHONPATH=ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/stc.h compiles as strict C99, and a C program linked against libstc.so calls
+    two host-only entry points (GeoTIFF encode -> decode round trip; no GPU, no Python in between)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from sentinel_tree_cover_b200 import build
+    lib = build.build()
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    src = tmp_path / "client.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdint.h>
+#include <string.h>
+#include "stc.h"
+int main(void) {
+  uint8_t img[6 * 5], *file = 0, *back = 0;
+  int64_t len = 0;
+  int rows = 0, cols = 0, i;
+  double b[4];
+  for (i = 0; i < 30; ++i) img[i] = (uint8_t)(i * 7);
+  if (stc_geotiff_encode_u8(img, 6, 5, 10.0, -3.0, 10.5, -2.4, &file, &len) != STC_OK) return 1;
+  if (stc_geotiff_decode_u8(file, len, 1, &back, &rows, &cols, b) != STC_OK) return 2;
+  if (rows != 6 || cols != 5 || memcmp(img, back, 30) != 0) return 3;
+  if (b[0] != 10.0 || b[1] > -2.999999 || b[2] < 10.499999 || b[3] != -2.4) return 4;
+  if (stc_geotiff_encode_u8(0, 6, 5, 0, 0, 1, 1, &file, &len) != STC_ERR_ARG) return 5;
+  stc_geotiff_free(file); stc_geotiff_free(back);
+  printf("ok %lld\n", (long long)len);
+  return 0;
+}
+''')
+    exe = str(tmp_path / "client")
+    inc = os.path.join(root, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, str(src), "-o", exe,
+                    lib, "-Wl,-rpath," + os.path.dirname(lib)], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), (r.returncode, r.stdout, r.stderr)
