@@ -402,6 +402,7 @@ extern "C" int stc_geotiff_decode_u8(const uint8_t* file, int64_t len, int band,
   uint32_t bw = W, bh = H;                                          // block (strip or tile) size in pixels
   if (tiled) { if (!tag_uint(v, tile_w, 0, bw) || !tag_uint(v, tile_h, 0, bh) || bw < 1 || bh < 1) return STC_ERR_STATE; }
   else { uint32_t r = H; if (tag_uint(v, rps, 0, r) && r >= 1 && r < H) bh = r; }
+  if (uint64_t(bw) * bh * samples > (uint64_t(1) << 31)) return STC_ERR_STATE;      // a block this large is a corrupt tag, not a raster
   const TiffTag& offs = tiled ? tile_off : strip_off;
   const TiffTag& cnts = tiled ? tile_cnt : strip_cnt;
   if (!offs.present) return STC_ERR_STATE;
